@@ -1,0 +1,136 @@
+"""Python view of the C ABI: one method per entry point of include/impec2d_b200.h."""
+import ctypes as C
+import numpy as np
+from . import _lib
+
+
+class ImpecError(RuntimeError):
+    pass
+
+
+def default_params(emulated=False, **kw):
+    P = _lib.Params()
+    _lib.load(emulated).impec_default_params(C.byref(P))
+    for k, v in kw.items():
+        if not hasattr(P, k):
+            raise AttributeError(k)
+        setattr(P, k, v)
+    return P
+
+
+def _ptr(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """Owns one impec_ctx (one GPU).  Host arrays use the reference's layouts:
+    c, p : (N1+2g, N2+2g); velocity : (N1+1+2g, N2+1+2g, 2); q : (N1*N2,)."""
+
+    def __init__(self, params, device=0, rank=0, nranks=1, nccl_id=None, stream=None, emulated=False):
+        self.L = _lib.load(emulated)
+        self.P = params
+        self._h = C.c_void_p()
+        rc = self.L.impec_ctx_create(C.byref(params), device, rank, nranks, nccl_id, stream, C.byref(self._h))
+        if rc != 0:
+            msg = self.L.impec_last_error(self._h).decode() if self._h else "context allocation failed"
+            if self._h:
+                self.L.impec_ctx_destroy(self._h)
+                self._h = C.c_void_p()
+            raise ImpecError("impec_ctx_create failed (%d): %s" % (rc, msg))
+
+    def close(self):
+        if self._h:
+            self.L.impec_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise ImpecError("impec call failed (%d): %s" % (rc, self.L.impec_last_error(self._h).decode()))
+
+    # shapes
+    def scalar_shape(self):
+        return (self.P.N1 + 2 * self.P.g, self.P.N2 + 2 * self.P.g)
+
+    def velocity_shape(self):
+        return (self.P.N1 + 1 + 2 * self.P.g, self.P.N2 + 1 + 2 * self.P.g, 2)
+
+    # transfers
+    def upload_c(self, c): assert c.shape == self.scalar_shape(); self._chk(self.L.impec_upload_c(self._h, _ptr(c)))
+    def upload_p(self, p): assert p.shape == self.scalar_shape(); self._chk(self.L.impec_upload_p(self._h, _ptr(p)))
+    def upload_q(self, q): assert q.size == self.P.N1 * self.P.N2; self._chk(self.L.impec_upload_q(self._h, _ptr(q)))
+    def upload_velocity(self, v): assert v.shape == self.velocity_shape(); self._chk(self.L.impec_upload_velocity(self._h, _ptr(v)))
+
+    def download_c(self, out=None):
+        out = np.empty(self.scalar_shape()) if out is None else out
+        self._chk(self.L.impec_download_c(self._h, _ptr(out)))
+        return out
+
+    def download_p(self, out=None):
+        out = np.empty(self.scalar_shape()) if out is None else out
+        self._chk(self.L.impec_download_p(self._h, _ptr(out)))
+        return out
+
+    def download_velocity(self, out=None):
+        out = np.empty(self.velocity_shape()) if out is None else out
+        self._chk(self.L.impec_download_velocity(self._h, _ptr(out)))
+        return out
+
+    # path
+    def fill_boundaries(self): self._chk(self.L.impec_fill_boundaries(self._h))
+
+    def pressure_solve(self, eps=None):
+        info = _lib.SolveInfo()
+        self._chk(self.L.impec_pressure_solve(self._h, self.P.eps if eps is None else eps, C.byref(info)))
+        return info
+
+    def calc_velocities(self): self._chk(self.L.impec_calc_velocities(self._h))
+
+    def max_stable_dt(self):
+        dt = C.c_double()
+        self._chk(self.L.impec_max_stable_dt(self._h, C.byref(dt)))
+        return dt.value
+
+    def source_split(self, dt): self._chk(self.L.impec_source_split(self._h, dt))
+    def advect_x(self, dt): self._chk(self.L.impec_advect_x(self._h, dt))
+    def advect_y(self, dt): self._chk(self.L.impec_advect_y(self._h, dt))
+    def advect_split(self, dt): self._chk(self.L.impec_advect_split(self._h, dt))
+
+    def diffusion_split(self, dt):
+        info = _lib.SolveInfo()
+        self._chk(self.L.impec_diffusion_split(self._h, dt, C.byref(info)))
+        return info
+
+    def transport_step(self, dt): self._chk(self.L.impec_transport_step(self._h, dt))
+
+    def impes_step(self, t=0.0, t_next_output=0.0):
+        dt = C.c_double(); info = _lib.SolveInfo()
+        self._chk(self.L.impec_impes_step(self._h, t, t_next_output, C.byref(dt), C.byref(info)))
+        return dt.value, info
+
+    def diagnostics(self):
+        d = _lib.Diag()
+        self._chk(self.L.impec_diagnostics(self._h, C.byref(d)))
+        return d
+
+    def build_operator(self): self._chk(self.L.impec_build_operator(self._h))
+
+    def vcycle(self, r=None):
+        if r is None:
+            self._chk(self.L.impec_vcycle(self._h, None, None))
+            return None
+        z = np.empty_like(r)
+        self._chk(self.L.impec_vcycle(self._h, _ptr(r), _ptr(z)))
+        return z
+
+    def mg_levels(self): return self.L.impec_mg_levels(self._h)
+    def kernel_launches(self): return self.L.impec_kernel_launches(self._h)
+    def reset_state(self): self._chk(self.L.impec_reset_state(self._h))
+    def set_option(self, key, value): self._chk(self.L.impec_set_option(self._h, key.encode(), float(value)))
+    def synchronize(self): self._chk(self.L.impec_synchronize(self._h))

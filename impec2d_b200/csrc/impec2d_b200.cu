@@ -1,0 +1,733 @@
+// impec2d_b200.cu -- context, host orchestration and the C ABI (include/impec2d_b200.h).
+// Unity build: the kernels are included below so that nvcc (product) and g++ -DIMPEC_EMU (CPU
+// emulation for tests) compile exactly the same source.
+#include "common.h"
+#include "kernels_transport.inl"
+#include "kernels_pressure.inl"
+#include "../../include/impec2d_b200.h"
+
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstdarg>
+#include <algorithm>
+
+#define BX 32
+#define BY 8
+
+// ------------------------------------------------------------------------------------------------
+struct Level {
+    Grid g;
+    double *AW = nullptr, *AS = nullptr, *AV = nullptr;
+    double *x = nullptr, *f = nullptr, *t = nullptr, *r = nullptr;
+    long long pin = -1, sig_idx = -1;
+};
+
+struct impec_ctx {
+    impec_params P;
+    DevParams D;
+    Grid g;
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // fields (padded layout)
+    double *c = nullptr, *p = nullptr, *q = nullptr, *u = nullptr, *v = nullptr;
+    double *ta = nullptr, *tb = nullptr;             // transport temporaries (contiguous pair)
+    double *MU = nullptr, *KV11 = nullptr, *KV22 = nullptr;
+    double *r = nullptr, *z = nullptr, *d = nullptr, *s = nullptr, *rhs = nullptr, *t0 = nullptr;
+    std::vector<Level> L;
+    double *sigma_dev = nullptr;                    // per-level diagonal shift of the pin
+    // reductions
+    double *part = nullptr; long long part_cap = 0;
+    double *scal = nullptr;                         // device scalars
+    double *h_scal = nullptr;                       // pinned host mirror
+    // wells
+    int nwell = 0; int *well_i = nullptr, *well_j = nullptr; double *well_q = nullptr, *well_md = nullptr;
+    double q_pin = 0.0; bool have_q = false;
+    int prev_first_sweep = 1;                       // Y_SWEEP (src/HyperbolicSolver.cpp:84)
+    bool mob_valid = false, op_valid = false;
+    bool warm_start = false;
+    long long launches = 0;
+    std::string err;
+    std::vector<void *> allocs;
+};
+
+enum { S_GAMMA0 = 0, S_SDOTP = 1, S_IPROD = 2, S_GAMMA1 = 3, S_BIPROD = 4, S_BETA_NUM = 5, S_BETA_DEN = 6, S_TMP = 7, S_SRC = 8, S_OUTFLUX = 9,
+       S_DIAG = 10, S_DT = 20, S_NSCAL = 32 };
+
+static int fail(impec_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+#define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, IMPEC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define TRY(call) do { int rc_ = (call); if (rc_ != IMPEC_OK) return rc_; } while (0)
+
+static inline dim3 grid2d(int nx, int ny) { return dim3((unsigned)((nx + BX - 1) / BX), (unsigned)((ny + BY - 1) / BY)); }
+static const dim3 kBlock(BX, BY);
+
+static int dev_alloc(impec_ctx *ctx, double **ptr, size_t n) {
+    void *p = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&p, n * sizeof(double)));
+    CUDA_TRY(ctx, cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream));
+    ctx->allocs.push_back(p);
+    *ptr = (double *)p;
+    return IMPEC_OK;
+}
+
+static int check_launch(impec_ctx *ctx, const char *what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, IMPEC_ERR_CUDA, "kernel %s: %s", what, cudaGetErrorString(e));
+    return IMPEC_OK;
+}
+#define LAUNCH(ctx, kernel, grid, block, ...) do { IMPEC_LAUNCH(kernel, grid, block, 0, (ctx)->stream, __VA_ARGS__); TRY(check_launch(ctx, #kernel)); } while (0)
+#define LAUNCH_COOP(ctx, kernel, grid, block, ...) do { IMPEC_LAUNCH_COOP(kernel, grid, block, 0, (ctx)->stream, __VA_ARGS__); TRY(check_launch(ctx, #kernel)); } while (0)
+
+// ------------------------------------------------------------------------------------------------ misc kernels
+__global__ void k_deinterleave(Grid g, const double *__restrict__ aos, int H, int W, double *__restrict__ u, double *__restrict__ v, int ng) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)H * W) return;
+    const int i = (int)(t / W) - ng, j = (int)(t % W) - ng;
+    u[gidx(g, i, j)] = aos[2 * t];
+    v[gidx(g, i, j)] = aos[2 * t + 1];
+}
+__global__ void k_interleave(Grid g, double *__restrict__ aos, int H, int W, const double *__restrict__ u, const double *__restrict__ v, int ng) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)H * W) return;
+    const int i = (int)(t / W) - ng, j = (int)(t % W) - ng;
+    aos[2 * t] = u[gidx(g, i, j)];
+    aos[2 * t + 1] = v[gidx(g, i, j)];
+}
+// acc += |val|   (HyperbolicSolver::SourceSplit, src/HyperbolicSolver.cpp:201-205)
+__global__ void k_accum_abs(const double *__restrict__ val, double *__restrict__ acc) { acc[0] += fabs(val[0]); }
+__global__ void k_set_scalar(double *__restrict__ dst, double v) { dst[0] = v; }
+// diagonal shift that represents the fine-level Dirichlet pin on the coarse levels:
+// sigma_1 = 1/8 * sum of the links between the pinned cell and its siblings in its 2x2 block, sigma_{l+1} = sigma_l/4
+__global__ void k_pin_sigma(Grid g, const double *__restrict__ AW, const double *__restrict__ AS, const double *__restrict__ AV,
+                            int pi, int pj, int nlev, double *__restrict__ sigma) {
+    const int bi = (pi >> 1) << 1, bj = (pj >> 1) << 1;
+    double tot = 0.;
+    for (int di = -1; di <= 1; di++)
+        for (int dj = -1; dj <= 1; dj++) {
+            if (!di && !dj) continue;
+            const int ii = pi + di, jj = pj + dj;
+            if (ii < bi || ii > bi + 1 || jj < bj || jj > bj + 1) continue;
+            if (dj == 0) tot += AW[gidx(g, pi > ii ? pi : ii, pj)];
+            else if (di == 0) tot += AS[gidx(g, pi, pj > jj ? pj : jj)];
+            else tot += AV[gidx(g, pi > ii ? pi : ii, pj > jj ? pj : jj)];
+        }
+    double sg = 0.125 * tot;
+    sigma[0] = 0.;
+    for (int l = 1; l < nlev; l++) { sigma[l] = sg; sg *= 0.25; }
+}
+__global__ void k_copy_interior(Grid g, const double *__restrict__ src, double *__restrict__ dst) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.N1 || j >= g.N2) return;
+    dst[gidx(g, i, j)] = src[gidx(g, i, j)];
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+static int reduce_final(impec_ctx *ctx, int op, long long nparts, int count, long long stride, int scal_idx) {
+    double *out = ctx->scal + scal_idx;
+    if (op == RED_SUM) LAUNCH_COOP(ctx, k_reduce_final<RED_SUM>, dim3(count), dim3(1024), ctx->part, nparts, stride, out);
+    else if (op == RED_MAX) LAUNCH_COOP(ctx, k_reduce_final<RED_MAX>, dim3(count), dim3(1024), ctx->part, nparts, stride, out);
+    else LAUNCH_COOP(ctx, k_reduce_final<RED_MIN>, dim3(count), dim3(1024), ctx->part, nparts, stride, out);
+    return IMPEC_OK;
+}
+static int fetch_scalars(impec_ctx *ctx, int idx, int n) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal + idx, ctx->scal + idx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ setup
+static void fill_dev_params(impec_ctx *ctx) {
+    const impec_params &P = ctx->P;
+    DevParams &D = ctx->D;
+    D.dx = (P.x_ub - P.x_lb) / P.N1; D.dy = (P.y_ub - P.y_lb) / P.N2;       // src/SimParams.cpp:452-453
+    D.x_lb = P.x_lb; D.y_lb = P.y_lb;
+    D.mu_res = P.mu_res; D.mq = pow(P.mu_res / P.mu_inj, 0.25);              // src/EllipticSolver.cpp:126
+    D.nu = P.nu; D.porosity = P.porosity; D.inj_fluid_conc = P.inj_fluid_conc;
+    D.alpha_l = P.alpha_l; D.alpha_t = P.alpha_t;
+    const double alpha = atan(D.dx / D.dy), theta = atan(D.dy / D.dx);       // src/EllipticSolver.cpp:72-93
+    D.dxi = D.dx / cos(theta); D.deta = D.dy / cos(alpha);
+    const double secamt = 1. / cos(alpha - theta);
+    D.secamt2 = secamt * secamt;
+    D.cosa2 = cos(alpha) * cos(alpha); D.sina2 = sin(alpha) * sin(alpha);
+    D.costsina = cos(theta) * sin(alpha); D.cosasint = cos(alpha) * sin(theta);
+    D.cost2 = cos(theta) * cos(theta); D.sint2 = sin(theta) * sin(theta);
+    D.cosa = cos(alpha); D.sint = sin(theta); D.cost = cos(theta); D.sina = sin(alpha);
+    D.avgproc = P.avgproc; D.is_test = P.is_test; D.testno = P.is_test ? P.testno : 0;
+}
+
+extern "C" void impec_default_params(impec_params *P) {
+    memset(P, 0, sizeof(*P));
+    P->N1 = P->N2 = 64; P->g = 2;
+    P->x_ub = P->y_ub = 1.0;
+    P->mu_res = 41.0; P->mu_inj = 1.0; P->avgproc = IMPEC_HARMONIC;
+    P->nu = 2.0 / 3.0; P->stype = IMPEC_PARALLEL;
+    P->porosity = 1.0; P->cfl = 0.5; P->inj_fluid_conc = 1.0;
+    P->alpha_l = P->alpha_t = 1.0; P->dt_diff_limit = 0.9; P->ptype = IMPEC_CRANKNICOLSON;
+    P->eps = 1e-14; P->para_eps = 1e-14;
+    P->hyper_method = IMPEC_MUSCL; P->dim_splitting = IMPEC_SYMMETRIC_PARALLEL;
+    P->max_iter = 10000; P->mg_max_levels = 0; P->mg_nmin = 4; P->mg_ncoarse = 8; P->mg_w_from = 2; P->mg_w_to = 4;
+}
+
+extern "C" const char *impec_version(void) { return "impec2d_b200 0.1 (sm_100a)"; }
+extern "C" int impec_is_emulated(void) {
+#ifdef IMPEC_EMU
+    return 1;
+#else
+    return 0;
+#endif
+}
+extern "C" int impec_nccl_unique_id(char id_out[128]) { memset(id_out, 0, 128); return IMPEC_ERR_UNSUPPORTED; }
+
+extern "C" const char *impec_last_error(const impec_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->allocs) cudaFree(p);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int nranks, const char *nccl_unique_id, void *cuda_stream, impec_ctx **out) {
+    (void)nccl_unique_id;
+    if (!P || !out) return IMPEC_ERR_ARG;
+    *out = nullptr;
+    impec_ctx *ctx = new impec_ctx();
+    *out = ctx;                                   // returned even on failure so that the error text can be read
+    ctx->P = *P; ctx->device = device; ctx->rank = rank; ctx->nranks = nranks;
+    if (P->g != IMPEC_GH) return fail(ctx, IMPEC_ERR_ARG, "num_ghostcells must be %d (got %d)", IMPEC_GH, P->g);
+    if (P->N1 < 4 || P->N2 < 4) return fail(ctx, IMPEC_ERR_ARG, "grid too small: %d x %d", P->N1, P->N2);
+    if (nranks != 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "multi-GPU slabs not built into this library (nranks=%d)", nranks);
+    if (P->stype == IMPEC_HORIZONTAL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "source_type horizontal is outside the accelerated path");
+    if (P->diffusion && P->alpha_l != P->alpha_t) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t gives a non-symmetric CN operator; not supported");
+    CUDA_TRY(ctx, cudaSetDevice(device));
+    if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
+    else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    fill_dev_params(ctx);
+    ctx->g = make_grid(P->N1, P->N2);
+    const size_t n = grid_elems(ctx->g);
+    double **fields[] = {&ctx->c, &ctx->p, &ctx->q, &ctx->u, &ctx->v, &ctx->MU, &ctx->KV11, &ctx->r, &ctx->z, &ctx->d, &ctx->s, &ctx->rhs, &ctx->t0};
+    for (double **f : fields) TRY(dev_alloc(ctx, f, n));
+    TRY(dev_alloc(ctx, &ctx->ta, 2 * n)); ctx->tb = ctx->ta + n;
+    if (P->is_test) TRY(dev_alloc(ctx, &ctx->KV22, n)); else ctx->KV22 = ctx->KV11;
+    // multigrid hierarchy
+    int nl = 1, a = P->N1, b = P->N2;
+    const int nmin = P->mg_nmin > 1 ? P->mg_nmin : 2;
+    while ((a % 2 == 0) && (b % 2 == 0) && std::min(a, b) > nmin && (P->mg_max_levels <= 0 || nl < P->mg_max_levels)) { a /= 2; b /= 2; nl++; }
+    ctx->L.resize(nl);
+    for (int l = 0; l < nl; l++) {
+        Level &L = ctx->L[l];
+        L.g = (l == 0) ? ctx->g : make_grid(ctx->L[l - 1].g.N1 / 2, ctx->L[l - 1].g.N2 / 2);
+        const size_t nn = grid_elems(L.g);
+        TRY(dev_alloc(ctx, &L.AW, nn)); TRY(dev_alloc(ctx, &L.AS, nn)); TRY(dev_alloc(ctx, &L.AV, nn));
+        if (l == 0) { L.x = ctx->z; L.f = ctx->r; L.t = ctx->t0; L.r = ctx->s; }
+        else { TRY(dev_alloc(ctx, &L.x, nn)); TRY(dev_alloc(ctx, &L.f, nn)); TRY(dev_alloc(ctx, &L.t, nn)); TRY(dev_alloc(ctx, &L.r, nn)); }
+    }
+    // pinned cell (1,1): src/MGSolver.cpp:109-118
+    int pi = 1, pj = 1;
+    ctx->L[0].pin = (long long)gidx(ctx->g, pi, pj);
+    for (int l = 1; l < nl; l++) { pi >>= 1; pj >>= 1; ctx->L[l].sig_idx = (long long)gidx(ctx->L[l].g, pi, pj); }
+    TRY(dev_alloc(ctx, &ctx->sigma_dev, (size_t)nl + 1));
+    // reductions
+    const dim3 gg = grid2d(P->N2 + 2, P->N1 + 2);
+    ctx->part_cap = (long long)gg.x * gg.y;
+    TRY(dev_alloc(ctx, &ctx->part, (size_t)ctx->part_cap * 4));
+    TRY(dev_alloc(ctx, &ctx->scal, S_NSCAL));
+    CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_scal, sizeof(double) * S_NSCAL));
+    memset(ctx->h_scal, 0, sizeof(double) * S_NSCAL);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
+}
+
+extern "C" int impec_synchronize(impec_ctx *ctx) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return IMPEC_OK; }
+extern "C" int impec_mg_levels(const impec_ctx *ctx) { return (int)ctx->L.size(); }
+extern "C" long long impec_kernel_launches(const impec_ctx *ctx) { return ctx->launches; }
+
+extern "C" int impec_reset_state(impec_ctx *ctx) {
+    ctx->prev_first_sweep = 1;
+    LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_OUTFLUX, 0.0);
+    return IMPEC_OK;
+}
+extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
+    const std::string k(key ? key : "");
+    if (k == "warm_start") { ctx->warm_start = value != 0.0; return IMPEC_OK; }
+    if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; return IMPEC_OK; }
+    if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; return IMPEC_OK; }
+    if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; return IMPEC_OK; }
+    if (k == "max_iter") { ctx->P.max_iter = (int)value; return IMPEC_OK; }
+    return fail(ctx, IMPEC_ERR_ARG, "unknown option '%s'", k.c_str());
+}
+
+// ------------------------------------------------------------------------------------------------ transfers
+static int upload_scalar(impec_ctx *ctx, double *dst, const double *host) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    const size_t w = (size_t)(g.N2 + 2 * ng) * sizeof(double);
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(dst + gidx(g, -ng, -ng), (size_t)g.ld * sizeof(double), host, w, w, (size_t)(g.N1 + 2 * ng), cudaMemcpyHostToDevice, ctx->stream));
+    return IMPEC_OK;
+}
+static int download_scalar(impec_ctx *ctx, const double *src, double *host) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    const size_t w = (size_t)(g.N2 + 2 * ng) * sizeof(double);
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(host, w, src + gidx(g, -ng, -ng), (size_t)g.ld * sizeof(double), w, (size_t)(g.N1 + 2 * ng), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
+}
+extern "C" int impec_upload_c(impec_ctx *ctx, const double *h) { ctx->mob_valid = ctx->op_valid = false; return upload_scalar(ctx, ctx->c, h); }
+extern "C" int impec_upload_p(impec_ctx *ctx, const double *h) { return upload_scalar(ctx, ctx->p, h); }
+extern "C" int impec_download_c(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->c, h); }
+extern "C" int impec_download_p(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->p, h); }
+
+static int rebuild_wells(impec_ctx *ctx, const double *q) {
+    const int N1 = ctx->P.N1, N2 = ctx->P.N2;
+    std::vector<int> wi, wj; std::vector<double> wq;
+    for (int i = 0; i < N1; i++)
+        for (int j = 0; j < N2; j++) {
+            const double v = q[(size_t)i * N2 + j];
+            if (v != 0.0) { wi.push_back(i); wj.push_back(j); wq.push_back(v); }
+        }
+    ctx->nwell = (int)wq.size();
+    ctx->q_pin = (N1 > 1 && N2 > 1) ? q[(size_t)1 * N2 + 1] : 0.0;
+    if (ctx->nwell) {
+        void *p;
+        CUDA_TRY(ctx, cudaMalloc(&p, sizeof(int) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_i = (int *)p;
+        CUDA_TRY(ctx, cudaMalloc(&p, sizeof(int) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_j = (int *)p;
+        CUDA_TRY(ctx, cudaMalloc(&p, sizeof(double) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_q = (double *)p;
+        CUDA_TRY(ctx, cudaMalloc(&p, sizeof(double) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_md = (double *)p;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_i, wi.data(), sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_j, wj.data(), sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_q, wq.data(), sizeof(double) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // the host vectors die at return
+    }
+    ctx->have_q = true;
+    return IMPEC_OK;
+}
+extern "C" int impec_upload_q(impec_ctx *ctx, const double *q) {
+    const Grid &g = ctx->g;
+    const size_t w = (size_t)g.N2 * sizeof(double);
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->q + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), q, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
+    return rebuild_wells(ctx, q);
+}
+extern "C" int impec_set_q_dev_changed(impec_ctx *ctx) {
+    const Grid &g = ctx->g;
+    std::vector<double> q((size_t)g.N1 * g.N2);
+    const size_t w = (size_t)g.N2 * sizeof(double);
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(q.data(), w, ctx->q + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), w, (size_t)g.N1, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rebuild_wells(ctx, q.data());
+}
+extern "C" int impec_upload_velocity(impec_ctx *ctx, const double *v_aos) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    const int H = g.N1 + 1 + 2 * ng, W = g.N2 + 1 + 2 * ng;
+    const long long n = (long long)H * W;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ta, v_aos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_deinterleave, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->ta, H, W, ctx->u, ctx->v, ng);
+    return IMPEC_OK;
+}
+extern "C" int impec_download_velocity(impec_ctx *ctx, double *v_aos) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    const int H = g.N1 + 1 + 2 * ng, W = g.N2 + 1 + 2 * ng;
+    const long long n = (long long)H * W;
+    LAUNCH(ctx, k_interleave, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->ta, H, W, ctx->u, ctx->v, ng);
+    CUDA_TRY(ctx, cudaMemcpyAsync(v_aos, ctx->ta, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
+}
+extern "C" int impec_field_layout(const impec_ctx *ctx, int *ld, int *row0, int *col0, int *rows) {
+    if (ld) *ld = ctx->g.ld; if (row0) *row0 = IMPEC_GH; if (col0) *col0 = IMPEC_PJ; if (rows) *rows = ctx->g.rows;
+    return IMPEC_OK;
+}
+extern "C" void *impec_field_dev(impec_ctx *ctx, const char *name) {
+    const std::string k(name ? name : "");
+    if (k == "c") { ctx->mob_valid = ctx->op_valid = false; return ctx->c; }
+    if (k == "p") return ctx->p; if (k == "q") return ctx->q; if (k == "u") return ctx->u; if (k == "v") return ctx->v;
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ a1 ghost fills
+static int fill_scalar(impec_ctx *ctx, double *a, int periodic) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    const long long total = 2LL * ng * (g.N2 + 2 * ng) + 2LL * ng * g.N1;
+    LAUNCH(ctx, k_fill_scalar, dim3((unsigned)((total + 255) / 256)), dim3(256), g, a, periodic, ng);
+    return IMPEC_OK;
+}
+extern "C" int impec_fill_boundaries(impec_ctx *ctx) { return fill_scalar(ctx, ctx->c, ctx->P.is_test ? 1 : 0); }
+
+// ------------------------------------------------------------------------------------------------ a2-a8 operator
+static LevelDev level_dev(const impec_ctx *ctx, int l, double mass) {
+    const Level &L = ctx->L[l];
+    LevelDev D;
+    D.g = L.g; D.AW = L.AW; D.AS = L.AS; D.AV = L.AV; D.mass = mass;
+    D.pin = L.pin; D.sig_idx = L.sig_idx; D.sig_val = 0.;
+    return D;
+}
+
+static int build_mobility(impec_ctx *ctx) {
+    const Grid &g = ctx->g;
+    LAUNCH(ctx, k_mobility, grid2d(g.N2 + 2, g.N1 + 2), kBlock, g, ctx->c, ctx->MU, ctx->D.mq, ctx->D.mu_res);
+    if (ctx->P.nu != 1.) {
+        if (ctx->P.is_test) LAUNCH(ctx, k_vertex<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, ctx->D);
+        else LAUNCH(ctx, k_vertex<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, ctx->D);
+    }
+    ctx->mob_valid = true;
+    return IMPEC_OK;
+}
+
+extern "C" int impec_build_operator(impec_ctx *ctx) {
+    const Grid &g = ctx->g;
+    TRY(build_mobility(ctx));
+    Level &L0 = ctx->L[0];
+    if (ctx->P.is_test) LAUNCH(ctx, k_links<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
+    else LAUNCH(ctx, k_links<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
+    for (size_t l = 1; l < ctx->L.size(); l++) {
+        Level &F = ctx->L[l - 1], &C = ctx->L[l];
+        LAUNCH(ctx, k_coarsen_links, grid2d(C.g.N2 + 1, C.g.N1 + 1), kBlock, F.g, F.AW, F.AS, F.AV, C.g, C.AW, C.AS, C.AV);
+    }
+    LAUNCH(ctx, k_pin_sigma, dim3(1), dim3(1), g, L0.AW, L0.AS, L0.AV, 1, 1, (int)ctx->L.size(), ctx->sigma_dev);
+    ctx->op_valid = true;
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multigrid cycle
+// sigma lives in device memory (k_pin_sigma), so the level descriptor carries a pointer-free copy:
+// the smoother kernels read it through sig_val, which we refresh from the host mirror once per build.
+static int refresh_sigma(impec_ctx *ctx, std::vector<double> &sig) {
+    sig.assign(ctx->L.size() + 1, 0.0);
+    CUDA_TRY(ctx, cudaMemcpyAsync(sig.data(), ctx->sigma_dev, sizeof(double) * ctx->L.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
+}
+
+struct Cycle {
+    impec_ctx *ctx;
+    std::vector<LevelDev> D;
+    int ncoarse, w_from, w_to;
+};
+
+static int smooth(Cycle &C, int l, const double *f, double *x, bool forward, bool zero) {
+    impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
+    const dim3 gr = grid2d(L.g.N2, L.g.N1);
+    const int c0 = forward ? 0 : 1;
+    if (zero) LAUNCH(ctx, k_smooth_color<true>, gr, kBlock, C.D[l], c0, f, x, L.t);
+    else LAUNCH(ctx, k_smooth_color<false>, gr, kBlock, C.D[l], c0, f, x, L.t);
+    LAUNCH(ctx, k_smooth_color<false>, gr, kBlock, C.D[l], 1 - c0, f, L.t, x);
+    return IMPEC_OK;
+}
+
+static int mg_cycle(Cycle &C, int l, const double *f, double *x) {
+    impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
+    const int nl = (int)ctx->L.size();
+    if (l == nl - 1) {
+        for (int s = 0; s < C.ncoarse; s++) { TRY(smooth(C, l, f, x, true, s == 0)); TRY(smooth(C, l, f, x, false, false)); }
+        return IMPEC_OK;
+    }
+    Level &Lc = ctx->L[l + 1];
+    const int gamma = (l >= C.w_from && l <= C.w_to) ? 2 : 1;
+    TRY(smooth(C, l, f, x, true, true));
+    for (int gc = 0; gc < gamma; gc++) {
+        LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1), kBlock, C.D[l], f, x, L.r);
+        LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L.g, L.r, Lc.g, Lc.f);
+        TRY(mg_cycle(C, l + 1, Lc.f, Lc.x));
+        LAUNCH(ctx, k_prolong_add, grid2d(L.g.N2, L.g.N1), kBlock, Lc.g, Lc.x, L.g, x, L.pin);
+        if (gc < gamma - 1) { TRY(smooth(C, l, f, x, false, false)); TRY(smooth(C, l, f, x, true, false)); }
+    }
+    TRY(smooth(C, l, f, x, false, false));
+    return IMPEC_OK;
+}
+
+static int make_cycle(impec_ctx *ctx, Cycle &C, double mass, int nlevels_used) {
+    C.ctx = ctx;
+    std::vector<double> sig;
+    TRY(refresh_sigma(ctx, sig));
+    C.D.clear();
+    for (size_t l = 0; l < ctx->L.size(); l++) { LevelDev D = level_dev(ctx, (int)l, mass); D.sig_val = sig[l]; if (mass != 0.) { D.pin = -1; D.sig_idx = -1; } C.D.push_back(D); }
+    C.ncoarse = ctx->P.mg_ncoarse > 0 ? ctx->P.mg_ncoarse : 8;
+    C.w_from = ctx->P.mg_w_from; C.w_to = ctx->P.mg_w_to;
+    (void)nlevels_used;
+    return IMPEC_OK;
+}
+
+extern "C" int impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host) {
+    if (!ctx->op_valid) TRY(impec_build_operator(ctx));
+    Cycle C; TRY(make_cycle(ctx, C, 0.0, 0));
+    const Grid &g = ctx->g;
+    const size_t w = (size_t)g.N2 * sizeof(double);
+    if (r_host) {
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->r + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), r_host, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->r + ctx->L[0].pin, 0.0);
+    }
+    TRY(mg_cycle(C, 0, ctx->r, ctx->z));
+    if (z_host) {
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(z_host, w, ctx->z + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), w, (size_t)g.N1, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ a8-a11 pressure solve
+// src/EllipticSolver.cpp:357-410 / src/MGSolver.cpp:524-545: in test mode the pin's coefficient is chosen so
+// that p(1,1) equals the manufactured solution
+static double q_test_host(const impec_params &P, double x, double y) {
+    const double t = 2.;
+    switch (P.testno) {
+    case 1: return 2. / P.mu_res * cos(x) * cos(y);
+    case 2: { const double c1 = -0.3, c2 = -0.3, a1 = exp(c1 * x), a2 = exp(c2 * y), a1_x = c1 * exp(c1 * x), a2_y = c2 * exp(c2 * y);
+              return 1. / P.mu_res * ((a1 + a2) * cos(x) * cos(y) + a1_x * sin(x) * cos(y) + a2_y * cos(x) * sin(y)); }
+    case 3: { const double a1 = 2. + sin(t * x) * sin(y), a2 = 2. + sin(t * x) * sin(y), a1_x = t * cos(t * x) * sin(y), a2_y = cos(y) * sin(t * x);
+              return 1. / P.mu_res * ((a1 + a2) * cos(x) * cos(y) + a1_x * sin(x) * cos(y) + a2_y * cos(x) * sin(y)); }
+    case 4: { const double a1 = 2. + sin(t * x) * sin(y), a2 = 2. + sin(x) * sin(t * y), a1_x = t * cos(t * x) * sin(y), a2_y = t * cos(t * y) * sin(x);
+              return 1. / P.mu_res * ((a1 + a2) * cos(x) * cos(y) + a1_x * sin(x) * cos(y) + a2_y * cos(x) * sin(y)); }
+    default: return 0.;
+    }
+}
+
+extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info *info) {
+    if (!ctx->have_q) return fail(ctx, IMPEC_ERR_ARG, "pressure solve before impec_upload_q");
+    const Grid &g = ctx->g;
+    const dim3 gr = grid2d(g.N2, g.N1);
+    const long long nparts = (long long)gr.x * gr.y;
+    TRY(impec_build_operator(ctx));
+    Cycle C; TRY(make_cycle(ctx, C, 0.0, 0));
+    const LevelDev &A = C.D[0];
+    // pinned value p(1,1) = b/(kappa/dA) = -q(1,1) dA / kappa       (src/MGSolver.cpp:517-567)
+    const double dA = ctx->D.dx * ctx->D.dy;
+    double kappa = 1.;
+    if (ctx->P.is_test) {
+        const double x = ctx->P.x_lb + 1.5 * ctx->D.dx, y = ctx->P.y_lb + 1.5 * ctx->D.dy;
+        kappa = -dA * q_test_host(ctx->P, x, y) / (cos(x) * cos(y));
+    }
+    const double p_pin = -ctx->q_pin / (kappa / dA);
+    double *x = ctx->p;
+    if (ctx->warm_start) {
+        // keep the previous pressure as initial guess (not the reference's behaviour: x0 = 0, MGSolver.cpp:577)
+        LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->p, ctx->d);
+        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
+        LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->d, x);
+        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), x + A.pin, p_pin);
+    } else {
+        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
+    }
+    TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
+    LAUNCH(ctx, k_residual, gr, kBlock, A, ctx->rhs, x, ctx->r);
+    LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->r, ctx->part);
+    TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_IPROD));
+    TRY(fetch_scalars(ctx, S_IPROD, 3));                         // S_IPROD .. S_BIPROD
+    const double bi_prod = ctx->h_scal[S_BIPROD];
+    double i_prod = ctx->h_scal[S_IPROD];
+    int it = 0, converged = 0;
+    if (!(bi_prod > 0.)) converged = 1;                          // b = 0  =>  x = 0 (HYPRE returns immediately)
+    else if (i_prod / bi_prod < eps * eps) converged = 1;
+    int ig = S_GAMMA0;                                           // which scalar slot holds the current gamma
+    if (!converged) {
+        TRY(mg_cycle(C, 0, ctx->r, ctx->z));
+        LAUNCH(ctx, k_update_d<true>, gr, kBlock, g, ctx->scal, ctx->z, ctx->d);
+        LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part);
+        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, ig));
+    }
+    while (!converged && it < ctx->P.max_iter) {
+        it++;
+        LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, A, ctx->d, ctx->s, ctx->part);
+        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_SDOTP));
+        // alpha = gamma / <s,d>: the kernel reads scal[0]/scal[1], so gamma must sit in slot 0
+        if (ig != S_GAMMA0) { CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal + S_GAMMA0, ctx->scal + ig, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)); ig = S_GAMMA0; }
+        LAUNCH_COOP(ctx, k_update_xr, gr, kBlock, g, ctx->scal, ctx->d, ctx->s, x, ctx->r, ctx->part);
+        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_IPROD));
+        TRY(fetch_scalars(ctx, S_IPROD, 1));
+        i_prod = ctx->h_scal[S_IPROD];
+        if (i_prod / bi_prod < eps * eps) { converged = 1; break; }
+        if (!(i_prod == i_prod)) return fail(ctx, IMPEC_ERR_NOCONV, "PCG produced NaN at iteration %d", it);
+        TRY(mg_cycle(C, 0, ctx->r, ctx->z));
+        LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part);
+        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BETA_NUM));
+        // beta = gamma_new / gamma_old ; d = z + beta d      (k_update_d reads scal'[0]/scal'[1])
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal + S_BETA_DEN, ctx->scal + S_GAMMA0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_BETA_NUM, ctx->z, ctx->d);
+        ig = S_BETA_NUM;
+    }
+    // true residual with the final x
+    LAUNCH(ctx, k_residual, gr, kBlock, A, ctx->rhs, x, ctx->s);
+    LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->s, ctx->s, ctx->part);
+    TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_TMP));
+    TRY(fetch_scalars(ctx, S_TMP, 1));
+    if (info) {
+        info->iterations = it; info->converged = converged;
+        info->relres = bi_prod > 0. ? sqrt(i_prod / bi_prod) : 0.;
+        info->true_relres = bi_prod > 0. ? sqrt(ctx->h_scal[S_TMP] / bi_prod) : 0.;
+    }
+    return converged ? IMPEC_OK : fail(ctx, IMPEC_ERR_NOCONV, "PCG did not reach eps=%g in %d iterations (relres %g)", eps, it, sqrt(i_prod / bi_prod));
+}
+
+// ------------------------------------------------------------------------------------------------ a12 velocities
+extern "C" int impec_calc_velocities(impec_ctx *ctx) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    if (!ctx->mob_valid) TRY(build_mobility(ctx));
+    TRY(fill_scalar(ctx, ctx->p, 0));                               // src/EllipticSolver.cpp:663
+    if (ctx->P.is_test) LAUNCH(ctx, k_velocity<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->p, ctx->MU, ctx->KV11, ctx->KV22, ctx->u, ctx->v, ctx->D);
+    else LAUNCH(ctx, k_velocity<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->p, ctx->MU, ctx->KV11, ctx->KV22, ctx->u, ctx->v, ctx->D);
+    const long long n = (long long)(g.N1 + 1 + 2 * ng) * (g.N2 + 1 + 2 * ng);
+    LAUNCH(ctx, k_fill_velocity, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->u, ctx->v, ng);   // :682
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ a13 time step
+extern "C" int impec_max_stable_dt(impec_ctx *ctx, double *dt) {
+    const Grid &g = ctx->g;
+    const dim3 gr = grid2d(g.N2, g.N1);
+    const long long nparts = (long long)gr.x * gr.y;
+    const impec_params &P = ctx->P;
+    if (P.is_test) {                                                // src/HyperbolicSolver.cpp:100-121
+        LAUNCH_COOP(ctx, k_dt_reduce<1>, gr, kBlock, g, ctx->u, ctx->v, ctx->D, ctx->part);
+        TRY(reduce_final(ctx, RED_MIN, nparts, 1, 0, S_DT));
+        TRY(fetch_scalars(ctx, S_DT, 1));
+        *dt = ctx->h_scal[S_DT] * P.cfl;
+        return IMPEC_OK;
+    }
+    LAUNCH_COOP(ctx, k_dt_reduce<0>, gr, kBlock, g, ctx->u, ctx->v, ctx->D, ctx->part);
+    TRY(reduce_final(ctx, RED_MAX, nparts, 1, 0, S_DT));
+    if (P.diffusion) {
+        LAUNCH_COOP(ctx, k_dt_reduce<2>, gr, kBlock, g, ctx->u, ctx->v, ctx->D, ctx->part);
+        TRY(reduce_final(ctx, RED_MIN, nparts, 1, 0, S_DT + 1));
+    }
+    TRY(fetch_scalars(ctx, S_DT, 2));
+    const double max_vel = ctx->h_scal[S_DT];
+    const double a = ctx->D.dx / max_vel, b = ctx->D.dy / max_vel;
+    double dt_adv = (b < a ? b : a);
+    dt_adv *= P.cfl;
+    double dt_diff = DBL_MAX;
+    if (P.diffusion) { const double mn = ctx->h_scal[S_DT + 1] < 1.e10 ? ctx->h_scal[S_DT + 1] : 1.e10; dt_diff = mn * P.dt_diff_limit; }
+    *dt = (P.ptype == IMPEC_CRANKNICOLSON) ? dt_adv : (dt_diff < dt_adv ? dt_diff : dt_adv);
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ a15 source
+extern "C" int impec_source_split(impec_ctx *ctx, double dt) {
+    if (!ctx->have_q) return fail(ctx, IMPEC_ERR_ARG, "source step before impec_upload_q");
+    if (ctx->nwell == 0) return IMPEC_OK;
+    ctx->mob_valid = ctx->op_valid = false;
+    LAUNCH(ctx, k_source_tr, dim3((unsigned)((ctx->nwell + 255) / 256)), dim3(256), ctx->nwell, ctx->well_i, ctx->well_j, ctx->well_q, ctx->g, ctx->c,
+           dt, ctx->P.inj_fluid_conc, ctx->well_md);
+    LAUNCH_COOP(ctx, k_reduce_final<RED_SUM>, dim3(1), dim3(1024), ctx->well_md, (long long)ctx->nwell, 0LL, ctx->scal + S_SRC);
+    LAUNCH(ctx, k_accum_abs, dim3(1), dim3(1), ctx->scal + S_SRC, ctx->scal + S_OUTFLUX);
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ a16 advection
+template <int DIR>
+static int sweep(impec_ctx *ctx, const double *cin, double *cout, const double *other, double dt, int i0, int i1, int j0, int j1) {
+    const Grid &g = ctx->g;
+    const double *vel = DIR == 0 ? ctx->u : ctx->v;
+    const double h = DIR == 0 ? ctx->D.dx : ctx->D.dy;
+    const double phi = ctx->P.porosity;
+    const bool phi1 = (phi == 1.0), up = ctx->P.hyper_method == IMPEC_UPWIND, avg = other != nullptr;
+    const dim3 gr = grid2d(j1 - j0, i1 - i0);
+#define SW(M, PH, AV) do { auto kern = k_sweep<DIR, M, PH, AV>; LAUNCH(ctx, kern, gr, kBlock, g, cin, vel, cout, other, dt, h, phi, i0, i1, j0, j1); } while (0)
+    if (!up) { if (phi1) { if (avg) { SW(0, true, true); } else { SW(0, true, false); } } else { if (avg) { SW(0, false, true); } else { SW(0, false, false); } } }
+    else     { if (phi1) { if (avg) { SW(1, true, true); } else { SW(1, true, false); } } else { if (avg) { SW(1, false, true); } else { SW(1, false, false); } } }
+#undef SW
+    return IMPEC_OK;
+}
+
+static int copy_field(impec_ctx *ctx, const double *src, double *dst) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, grid_elems(ctx->g) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return IMPEC_OK;
+}
+
+// Reference semantics of a single sweep (src/HyperbolicSplitSolver.cpp:113-159): the x sweep updates
+// i in [0,N1) for ALL j in [-g,N2+g); the y sweep updates ALL i in [-g,N1+g) for j in [0,N2); other cells keep
+// their value.  In place on c (through the temporary ta).
+extern "C" int impec_advect_x(impec_ctx *ctx, double dt) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    ctx->mob_valid = ctx->op_valid = false;
+    TRY(copy_field(ctx, ctx->c, ctx->ta));
+    return sweep<0>(ctx, ctx->ta, ctx->c, nullptr, dt, 0, g.N1, -ng, g.N2 + ng);
+}
+extern "C" int impec_advect_y(impec_ctx *ctx, double dt) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    ctx->mob_valid = ctx->op_valid = false;
+    TRY(copy_field(ctx, ctx->c, ctx->ta));
+    return sweep<1>(ctx, ctx->ta, ctx->c, nullptr, dt, -ng, g.N1 + ng, 0, g.N2);
+}
+
+// src/HyperbolicSplitSolver.cpp:51-106
+extern "C" int impec_advect_split(impec_ctx *ctx, double dt) {
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    ctx->mob_valid = ctx->op_valid = false;
+    TRY(impec_fill_boundaries(ctx));
+    switch (ctx->P.dim_splitting) {
+    case IMPEC_ALTERNATING:
+        if (ctx->prev_first_sweep == 1) { TRY(impec_advect_x(ctx, dt)); TRY(impec_advect_y(ctx, dt)); ctx->prev_first_sweep = 0; }
+        else { TRY(impec_advect_y(ctx, dt)); TRY(impec_advect_x(ctx, dt)); ctx->prev_first_sweep = 1; }
+        break;
+    case IMPEC_X_FIRST: TRY(impec_advect_x(ctx, dt)); TRY(impec_advect_y(ctx, dt)); ctx->prev_first_sweep = 0; break;
+    case IMPEC_Y_FIRST: TRY(impec_advect_y(ctx, dt)); TRY(impec_advect_x(ctx, dt)); ctx->prev_first_sweep = 1; break;
+    case IMPEC_STRANG:  TRY(impec_advect_x(ctx, 0.5 * dt)); TRY(impec_advect_y(ctx, dt)); TRY(impec_advect_x(ctx, 0.5 * dt)); ctx->prev_first_sweep = 0; break;
+    default:
+        // c <- 1/2 ( Y(X(c)) + X(Y(c)) ); ghost strips are swept only where the second sweep reads them
+        TRY(sweep<0>(ctx, ctx->c, ctx->ta, nullptr, dt, 0, g.N1, -ng, g.N2 + ng));        // X(c)      -> ta
+        TRY(sweep<1>(ctx, ctx->ta, ctx->tb, nullptr, dt, 0, g.N1, 0, g.N2));              // Y(X(c))   -> tb
+        TRY(sweep<1>(ctx, ctx->c, ctx->ta, nullptr, dt, -ng, g.N1 + ng, 0, g.N2));        // Y(c)      -> ta
+        TRY(sweep<0>(ctx, ctx->ta, ctx->c, ctx->tb, dt, 0, g.N1, 0, g.N2));               // 1/2(tb + X(Y(c))) -> c
+        ctx->prev_first_sweep = 0;
+        break;
+    }
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ a19 dispersion
+extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info *info) {
+    (void)dt; (void)info;
+    return fail(ctx, IMPEC_ERR_UNSUPPORTED, "Crank-Nicolson dispersion is not built yet");
+}
+
+// ------------------------------------------------------------------------------------------------ a14 transport step
+extern "C" int impec_transport_step(impec_ctx *ctx, double dt) {
+    TRY(impec_source_split(ctx, 0.5 * dt));
+    TRY(impec_fill_boundaries(ctx));
+    if (ctx->P.diffusion) TRY(impec_diffusion_split(ctx, 0.5 * dt, nullptr));
+    TRY(impec_advect_split(ctx, dt));
+    TRY(impec_source_split(ctx, 0.5 * dt));
+    TRY(impec_fill_boundaries(ctx));
+    if (ctx->P.diffusion) TRY(impec_diffusion_split(ctx, 0.5 * dt, nullptr));
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ a20 IMPES step
+extern "C" int impec_impes_step(impec_ctx *ctx, double t, double t_next_output, double *dt_used, impec_solve_info *info) {
+    TRY(impec_fill_boundaries(ctx));
+    TRY(impec_pressure_solve(ctx, ctx->P.eps, info));
+    TRY(impec_calc_velocities(ctx));
+    double dt = 0.;
+    TRY(impec_max_stable_dt(ctx, &dt));
+    if (t_next_output > t && t + dt >= t_next_output) dt = t_next_output - t;      // src/Impec2DSolver.cpp:375-378
+    TRY(impec_transport_step(ctx, dt));
+    if (dt_used) *dt_used = dt;
+    return IMPEC_OK;
+}
+
+extern "C" int impec_diagnostics(impec_ctx *ctx, impec_diag *out) {
+    const Grid &g = ctx->g;
+    const dim3 gr = grid2d(g.N2, g.N1);
+    const long long nparts = (long long)gr.x * gr.y;
+    LAUNCH_COOP(ctx, k_diag_cells, gr, kBlock, g, ctx->c, ctx->u, ctx->v, ctx->q, ctx->D.dx, ctx->D.dy, ctx->part, ctx->part_cap);
+    TRY(reduce_final(ctx, RED_SUM, nparts, 2, ctx->part_cap, S_DIAG));
+    LAUNCH_COOP(ctx, k_reduce_final<RED_MAX>, dim3(1), dim3(1024), ctx->part + 2 * ctx->part_cap, nparts, 0LL, ctx->scal + S_DIAG + 2);
+    LAUNCH_COOP(ctx, k_reduce_final<RED_MIN>, dim3(1), dim3(1024), ctx->part + 3 * ctx->part_cap, nparts, 0LL, ctx->scal + S_DIAG + 3);
+    const int nb = (std::max(g.N1, g.N2) + 255) / 256;
+    LAUNCH_COOP(ctx, k_diag_boundary, dim3(nb), dim3(256), g, ctx->u, ctx->v, ctx->part);
+    TRY(reduce_final(ctx, RED_SUM, nb, 1, 0, S_DIAG + 4));
+    TRY(fetch_scalars(ctx, S_OUTFLUX, S_DIAG + 5 - S_OUTFLUX));
+    out->total_mass = ctx->h_scal[S_DIAG];
+    out->divergence_error = ctx->h_scal[S_DIAG + 1] * ctx->D.dx * ctx->D.dx;       // dx*dx as upstream (:556)
+    out->c_max = ctx->h_scal[S_DIAG + 2]; out->c_min = ctx->h_scal[S_DIAG + 3];
+    out->boundary_velocity_error = ctx->h_scal[S_DIAG + 4];
+    out->total_mass_outflux = ctx->h_scal[S_OUTFLUX];
+    return IMPEC_OK;
+}

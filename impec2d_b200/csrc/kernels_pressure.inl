@@ -1,0 +1,380 @@
+// kernels_pressure.inl -- mobility/link build, multigrid (smoother, residual, transfers), PCG vector
+// kernels and Darcy velocity reconstruction.
+//
+// Operator representation ("links").  After the reference's Neumann folding (src/MGSolver.cpp:305-515)
+// the 9-point row of cell (i,j) is   (A p)(i,j) = sum_nb a_nb (p_nb - p_ij)   with symmetric weights:
+//   AW(i,j): (i-1,j)-(i,j)      AS(i,j): (i,j-1)-(i,j)
+//   AV(i,j): lives on vertex (i-1/2,j-1/2) and couples (i-1,j-1)-(i,j) and (i-1,j)-(i,j-1)
+// and every link that crosses the domain boundary is ZERO (its weight was folded onto the mirror link).
+// Ghost values of all multigrid vectors are kept finite (zero) so that kernels need no edge branches.
+// We solve the SPD form  S = -A :  (S x) = diag*x - sum a_nb x_nb,  diag = mass + sigma + sum a_nb.
+
+// ---------------------------------------------------------------- a2-a4: viscosity and mobilities
+// src/EllipticSolver.cpp:692-695
+IMPEC_D double mu_of_c(double c, double mq, double mu_res) {
+    const double x = (1. - c + mq * c);
+    return 1. / (x * x * x * x) * mu_res;
+}
+// src/EllipticSolver.cpp:418-470 (manufactured-solution permeabilities; 1 in production runs)
+IMPEC_D double K11_fn(const DevParams &P, double x, double y) {
+    switch (P.testno) {
+    case 2: return exp(-0.3 * x);
+    case 3: return 2. + sin(2. * x) * sin(y);
+    case 4: return 2. + sin(2. * x) * sin(y);
+    default: return 1.;
+    }
+}
+IMPEC_D double K22_fn(const DevParams &P, double x, double y) {
+    switch (P.testno) {
+    case 2: return exp(-0.3 * y);
+    case 3: return 2. + sin(2. * x) * sin(y);
+    case 4: return 2. + sin(x) * sin(2. * y);
+    default: return 1.;
+    }
+}
+
+// MU(i,j) = mu(c(i,j)) on the interior plus one ghost ring (c ghosts must be filled).
+__global__ void __launch_bounds__(256) k_mobility(Grid g, const double *__restrict__ c, double *__restrict__ MU, double mq, double mu_res) {
+    const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
+    const int i = (int)(blockIdx.y * blockDim.y + threadIdx.y) - 1;
+    if (i > g.N1 || j > g.N2) return;
+    const size_t k = gidx(g, i, j);
+    MU[k] = mu_of_c(c[k], mq, mu_res);
+}
+
+// face mobility between cell a (lower index) and cell b: src/EllipticSolver.cpp:478-524
+template <bool TEST> IMPEC_D double face_mob(double mu_a, double mu_b, double Ka, double Kb, int avgproc) {
+    if (avgproc == 1) return TEST ? 2. / (mu_a / Ka + mu_b / Kb) : 2. / (mu_a + mu_b);
+    return TEST ? 1. / 2 * (Ka / mu_a + Kb / mu_b) : 1. / 2 * (1. / mu_a + 1. / mu_b);
+}
+
+// Vertex mobilities K11v,K22v at vertex (i-1/2,j-1/2), i in [0,N1], j in [0,N2]: src/EllipticSolver.cpp:697-754.
+// In production K = 1 so K11v == K22v bit for bit and only KV11 is written.
+template <bool TEST>
+__global__ void __launch_bounds__(256) k_vertex(Grid g, const double *__restrict__ MU, double *__restrict__ KV11, double *__restrict__ KV22, DevParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > g.N1 || j > g.N2) return;
+    const size_t k = gidx(g, i, j);
+    // the reference's argument order: (i0,j0)=(i-1,j-1): c_ij, c_ip1j, c_ijp1, c_ip1jp1, summed as ip1j, ij, ijp1, ip1jp1
+    const double mu_ij = MU[k - g.ld - 1], mu_ip1j = MU[k - 1], mu_ijp1 = MU[k - g.ld], mu_ip1jp1 = MU[k];
+    if (!TEST) {
+        KV11[k] = (P.avgproc == 1) ? 4. / (mu_ip1j + mu_ij + mu_ijp1 + mu_ip1jp1)
+                                   : 1. / 4 * (1. / mu_ip1j + 1. / mu_ij + 1. / mu_ijp1 + 1. / mu_ip1jp1);
+        return;
+    }
+    const double x = P.x_lb + ((i - 1) + 0.5) * P.dx, y = P.y_lb + ((j - 1) + 0.5) * P.dy;
+    {
+        const double Ka = K11_fn(P, x + P.dx, y), Kb = K11_fn(P, x, y), Kc = K11_fn(P, x, y + P.dy), Kd = K11_fn(P, x + P.dx, y + P.dy);
+        KV11[k] = (P.avgproc == 1) ? 4. / (mu_ip1j / Ka + mu_ij / Kb + mu_ijp1 / Kc + mu_ip1jp1 / Kd)
+                                   : 1. / 4 * (Ka / mu_ip1j + Kb / mu_ij + Kc / mu_ijp1 + Kd / mu_ip1jp1);
+    }
+    {
+        const double Ka = K22_fn(P, x + P.dx, y), Kb = K22_fn(P, x, y), Kc = K22_fn(P, x, y + P.dy), Kd = K22_fn(P, x + P.dx, y + P.dy);
+        KV22[k] = (P.avgproc == 1) ? 4. / (mu_ip1j / Ka + mu_ij / Kb + mu_ijp1 / Kc + mu_ip1jp1 / Kd)
+                                   : 1. / 4 * (Ka / mu_ip1j + Kb / mu_ij + Kc / mu_ijp1 + Kd / mu_ip1jp1);
+    }
+}
+
+IMPEC_D double vM11(const DevParams &P, double K11, double K22) { return P.secamt2 * (K11 * P.cosa2 + K22 * P.sina2); }
+IMPEC_D double vM12(const DevParams &P, double K11, double K22) { return P.secamt2 * (K22 * P.costsina - K11 * P.cosasint); }
+IMPEC_D double vM22(const DevParams &P, double K11, double K22) { return P.secamt2 * (K11 * P.sint2 + K22 * P.cost2); }
+
+// Links AW, AS, AV on i in [0,N1], j in [0,N2] from MU and the vertex mobilities: a5-a8.
+//   parallel part  src/MGSolver.cpp:760-773, rotated part :777-841, blend :748-756, folding :305-515.
+template <bool TEST>
+__global__ void __launch_bounds__(256) k_links(Grid g, const double *__restrict__ MU, const double *__restrict__ KV11, const double *__restrict__ KV22,
+                                               double *__restrict__ AW, double *__restrict__ AS, double *__restrict__ AV, DevParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > g.N1 || j > g.N2) return;
+    const size_t k = gidx(g, i, j);
+    const double nu = P.nu;
+    const double inv_xi2 = P.dxi * P.dxi, inv_xe = 1. / (P.deta * P.dxi);
+    const bool rot = (nu != 1.);
+#define AVRAW(kk) ((1 - nu) * (vM11(P, KV11[kk], KV22[kk]) / inv_xi2))
+#define M12AT(kk) (vM12(P, KV11[kk], KV22[kk]))
+    // vertex link
+    const bool vb = (i == 0 || i == g.N1 || j == 0 || j == g.N2);
+    AV[k] = (rot && !vb) ? AVRAW(k) : 0.;
+    // x-face link between (i-1,j) and (i,j)
+    if (j < g.N2) {
+        double w = 0.;
+        if (i > 0 && i < g.N1) {
+            double Ka = 1., Kb = 1.;
+            if (TEST) { const double x = P.x_lb + (i + 0.5) * P.dx, y = P.y_lb + (j + 0.5) * P.dy; Ka = K11_fn(P, x - P.dx, y); Kb = K11_fn(P, x, y); }
+            const double Wp = 1. / (P.dx * P.dx) * face_mob<TEST>(MU[k - g.ld], MU[k], Ka, Kb, P.avgproc);
+            double Wd = 0.;
+            if (rot) Wd = -inv_xe * (M12AT(k + 1) + M12AT(k));               // M21(i-1/2,j+1/2) + M12(i-1/2,j-1/2)
+            w = nu * Wp + (1 - nu) * Wd;
+            if (rot && j == 0) w = w + AVRAW(k);                              // bottom row: W += SW
+            if (rot && j == g.N2 - 1) w = w + AVRAW(k + 1);                   // top row:    W += NW
+        }
+        AW[k] = w;
+    }
+    // y-face link between (i,j-1) and (i,j)
+    if (i < g.N1) {
+        double s = 0.;
+        if (j > 0 && j < g.N2) {
+            double Ka = 1., Kb = 1.;
+            if (TEST) { const double x = P.x_lb + (i + 0.5) * P.dx, y = P.y_lb + (j + 0.5) * P.dy; Ka = K22_fn(P, x, y - P.dy); Kb = K22_fn(P, x, y); }
+            const double Sp = 1. / (P.dy * P.dy) * face_mob<TEST>(MU[k - 1], MU[k], Ka, Kb, P.avgproc);
+            double Sd = 0.;
+            if (rot) Sd = inv_xe * (M12AT(k) + M12AT(k + g.ld));              // M12(i-1/2,j-1/2) + M21(i+1/2,j-1/2)
+            s = nu * Sp + (1 - nu) * Sd;
+            if (rot && i == 0) s = s + AVRAW(k);                              // left column:  S += SW
+            if (rot && i == g.N1 - 1) s = s + AVRAW(k + g.ld);                // right column: S += SE
+        }
+        AS[k] = s;
+    }
+#undef AVRAW
+#undef M12AT
+}
+
+// ---------------------------------------------------------------- multigrid level kernels
+struct LevelDev {
+    Grid g;
+    const double *AW, *AS, *AV;
+    double mass;                 // 0 elliptic, 1 Crank-Nicolson
+    long long pin;               // fine level: padded index of the Dirichlet cell (or -1)
+    long long sig_idx;           // coarse levels: padded index of the cell carrying the pin's diagonal shift
+    double sig_val;
+};
+
+IMPEC_D double link_diag(const LevelDev &L, size_t k) {
+    const int ld = L.g.ld;
+    double d = L.mass + (((L.AW[k] + L.AW[k + ld]) + (L.AS[k] + L.AS[k + 1])) + ((L.AV[k] + L.AV[k + ld]) + (L.AV[k + 1] + L.AV[k + ld + 1])));
+    if ((long long)k == L.sig_idx) d += L.sig_val;
+    return d;
+}
+// order W,E,S,N,SW,SE,NW,NE (same as the oracle's off_sum)
+IMPEC_D double link_offsum(const LevelDev &L, const double *__restrict__ x, size_t k) {
+    const int ld = L.g.ld;
+    double s = L.AW[k] * x[k - ld];
+    s += L.AW[k + ld] * x[k + ld];
+    s += L.AS[k] * x[k - 1];
+    s += L.AS[k + 1] * x[k + 1];
+    s += L.AV[k] * x[k - ld - 1];
+    s += L.AV[k + ld] * x[k + ld - 1];
+    s += L.AV[k + 1] * x[k - ld + 1];
+    s += L.AV[k + ld + 1] * x[k + ld + 1];
+    return s;
+}
+
+// One colour pass of red-black Gauss-Seidel (Jacobi inside a colour: the same-colour diagonal neighbours
+// of the 9-point operator are read from xin).  Reads xin, writes xout for every cell (other colour copied),
+// so a sweep = two passes ping-ponging x -> t -> x.
+template <bool ZERO>
+__global__ void __launch_bounds__(256) k_smooth_color(LevelDev L, int color, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ xout) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= L.g.N1 || j >= L.g.N2) return;
+    const size_t k = gidx(L.g, i, j);
+    if (((i + j) & 1) != color || (long long)k == L.pin) { xout[k] = ZERO ? 0. : xin[k]; return; }
+    const double d = link_diag(L, k);
+    xout[k] = ZERO ? f[k] / d : (f[k] + link_offsum(L, xin, k)) / d;
+}
+
+// r = f - S x  (0 at the pinned cell); optionally accumulates <r,r> partials
+__global__ void __launch_bounds__(256) k_residual(LevelDev L, const double *__restrict__ f, const double *__restrict__ x, double *__restrict__ r) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= L.g.N1 || j >= L.g.N2) return;
+    const size_t k = gidx(L.g, i, j);
+    r[k] = ((long long)k == L.pin) ? 0. : f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k));
+}
+
+// full weighting = (bilinear prolongation)^T / 4 with mirrored ghosts (Neumann consistent)
+__global__ void __launch_bounds__(256) k_restrict(Grid gf, const double *__restrict__ r, Grid gc, double *__restrict__ fc) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= gc.N1 || J >= gc.N2) return;
+    const double w[4] = {0.25, 0.75, 0.75, 0.25};
+    double t4[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        int i = 2 * I - 1 + a; i = i < 0 ? 0 : (i > gf.N1 - 1 ? gf.N1 - 1 : i);
+        double s = 0.;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            int j = 2 * J - 1 + b; j = j < 0 ? 0 : (j > gf.N2 - 1 ? gf.N2 - 1 : j);
+            s += w[b] * r[gidx(gf, i, j)];
+        }
+        t4[a] = s;
+    }
+    fc[gidx(gc, I, J)] = 0.25 * (w[0] * t4[0] + w[1] * t4[1] + w[2] * t4[2] + w[3] * t4[3]);
+}
+
+// x += P e : cell-centred bilinear interpolation with edge replication
+__global__ void __launch_bounds__(256) k_prolong_add(Grid gc, const double *__restrict__ e, Grid gf, double *__restrict__ x, long long pin) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= gf.N1 || j >= gf.N2) return;
+    const size_t k = gidx(gf, i, j);
+    if ((long long)k == pin) return;
+    const int I = i >> 1, J = j >> 1;
+    int In = (i & 1) ? I + 1 : I - 1; In = In < 0 ? 0 : (In > gc.N1 - 1 ? gc.N1 - 1 : In);
+    int Jn = (j & 1) ? J + 1 : J - 1; Jn = Jn < 0 ? 0 : (Jn > gc.N2 - 1 ? gc.N2 - 1 : Jn);
+    const double a = 0.75 * e[gidx(gc, I, J)] + 0.25 * e[gidx(gc, In, J)];
+    const double b = 0.75 * e[gidx(gc, I, Jn)] + 0.25 * e[gidx(gc, In, Jn)];
+    x[k] += 0.75 * a + 0.25 * b;
+}
+
+// coarse links by rediscretisation on averaged fine links ("coarse operators")
+__global__ void __launch_bounds__(256) k_coarsen_links(Grid gf, const double *__restrict__ AWf, const double *__restrict__ ASf, const double *__restrict__ AVf,
+                                                       Grid gc, double *__restrict__ AWc, double *__restrict__ ASc, double *__restrict__ AVc) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I > gc.N1 || J > gc.N2) return;
+    const size_t kc = gidx(gc, I, J), kf = gidx(gf, 2 * I, 2 * J);
+    if (J < gc.N2) AWc[kc] = (I == gc.N1) ? 0. : 0.125 * (AWf[kf] + AWf[kf + 1]);
+    if (I < gc.N1) ASc[kc] = (J == gc.N2) ? 0. : 0.125 * (ASf[kf] + ASf[kf + gf.ld]);
+    AVc[kc] = (I == gc.N1 || J == gc.N2) ? 0. : 0.25 * AVf[kf];
+}
+
+// ---------------------------------------------------------------- PCG vector kernels (a10)
+// s = S d and partial <s,d>
+__global__ void __launch_bounds__(256) k_matvec_dot(LevelDev L, const double *__restrict__ d, double *__restrict__ s, double *__restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double v = 0.;
+    if (i < L.g.N1 && j < L.g.N2) {
+        const size_t k = gidx(L.g, i, j);
+        const double sk = ((long long)k == L.pin) ? 0. : link_diag(L, k) * d[k] - link_offsum(L, d, k);
+        s[k] = sk;
+        v = sk * d[k];
+    }
+    v = block_reduce<RED_SUM>(v);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
+// x += alpha d ; r -= alpha s ; partial <r,r>.  alpha = scal[0]/scal[1] is read from device memory.
+__global__ void __launch_bounds__(256) k_update_xr(Grid g, const double *__restrict__ scal, const double *__restrict__ d, const double *__restrict__ s,
+                                                   double *__restrict__ x, double *__restrict__ r, double *__restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const double alpha = scal[0] / scal[1];
+    double v = 0.;
+    if (i < g.N1 && j < g.N2) {
+        const size_t k = gidx(g, i, j);
+        x[k] += alpha * d[k];
+        const double rk = r[k] - alpha * s[k];
+        r[k] = rk;
+        v = rk * rk;
+    }
+    v = block_reduce<RED_SUM>(v);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
+// partial <a,b> (and optionally <a,a> in a second partial array)
+__global__ void __launch_bounds__(256) k_dot(Grid g, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double v = 0.;
+    if (i < g.N1 && j < g.N2) { const size_t k = gidx(g, i, j); v = a[k] * b[k]; }
+    v = block_reduce<RED_SUM>(v);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
+// d = z + beta d, beta = scal[0]/scal[1]   (FIRST: d = z)
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_update_d(Grid g, const double *__restrict__ scal, const double *__restrict__ z, double *__restrict__ d) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.N1 || j >= g.N2) return;
+    const size_t k = gidx(g, i, j);
+    d[k] = FIRST ? z[k] : z[k] + (scal[0] / scal[1]) * d[k];
+}
+
+// b = -q scattered into the padded layout, x0 = 0 except the pinned value; partial <b,b>
+__global__ void __launch_bounds__(256) k_setup_rhs(Grid g, const double *__restrict__ q, double *__restrict__ rhs, double *__restrict__ x,
+                                                   long long pin, double pin_value, double *__restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double v = 0.;
+    if (i < g.N1 && j < g.N2) {
+        const size_t k = gidx(g, i, j);
+        const double qk = q[k];
+        rhs[k] = qk;                       // SPD form: S x = -b = q
+        x[k] = ((long long)k == pin) ? pin_value : 0.;
+        v = qk * qk;                       // <b,b> = <q,q>
+    }
+    v = block_reduce<RED_SUM>(v);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
+// ---------------------------------------------------------------- a12: Darcy velocity
+// rotated-frame velocity at vertex (i-1/2,j-1/2) rotated back to (x,y): src/EllipticSolver.cpp:554-592
+IMPEC_D void vertex_vel(const DevParams &P, const double *__restrict__ p, double K11, double K22, size_t k, int ld, double &u1, double &u2) {
+    const double d1dp = 1. / P.dxi * (p[k] - p[k - ld - 1]);
+    const double d2dp = 1. / P.deta * (p[k - ld] - p[k - 1]);
+    const double M11 = vM11(P, K11, K22), M12 = vM12(P, K11, K22), M22 = vM22(P, K11, K22);
+    const double w1 = -d1dp * M11 - d2dp * M12;
+    const double w2 = -d1dp * M12 - d2dp * M22;
+    u1 = P.cost * w1 - P.sina * w2;
+    u2 = P.sint * w1 + P.cosa * w2;
+}
+
+// u on i in [0,N1], j in [0,N2); v on i in [0,N1), j in [0,N2]: src/EllipticSolver.cpp:541-547, 600-683.
+// p must carry one filled Neumann ghost ring.
+template <bool TEST>
+__global__ void __launch_bounds__(256) k_velocity(Grid g, const double *__restrict__ p, const double *__restrict__ MU, const double *__restrict__ KV11,
+                                                  const double *__restrict__ KV22, double *__restrict__ u, double *__restrict__ v, DevParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > g.N1 || j > g.N2) return;
+    const size_t k = gidx(g, i, j);
+    const int ld = g.ld;
+    const double nu = P.nu;
+    const bool rot = (nu != 1.);
+    double a1 = 0., a2 = 0.;
+    if (rot) vertex_vel(P, p, KV11[k], KV22[k], k, ld, a1, a2);
+    if (j < g.N2) {
+        double Ka = 1., Kb = 1.;
+        if (TEST) { const double x = P.x_lb + (i + 0.5) * P.dx, y = P.y_lb + (j + 0.5) * P.dy; Ka = K11_fn(P, x - P.dx, y); Kb = K11_fn(P, x, y); }
+        const double par = -face_mob<TEST>(MU[k - ld], MU[k], Ka, Kb, P.avgproc) * (p[k] - p[k - ld]) / P.dx;
+        double b1 = 0., b2 = 0.;
+        if (rot) vertex_vel(P, p, KV11[k + 1], KV22[k + 1], k + 1, ld, b1, b2);
+        u[k] = nu * par + (1. - nu) * (0.5 * (b1 + a1));
+    }
+    if (i < g.N1) {
+        double Ka = 1., Kb = 1.;
+        if (TEST) { const double x = P.x_lb + (i + 0.5) * P.dx, y = P.y_lb + (j + 0.5) * P.dy; Ka = K22_fn(P, x, y - P.dy); Kb = K22_fn(P, x, y); }
+        const double par = -face_mob<TEST>(MU[k - 1], MU[k], Ka, Kb, P.avgproc) * (p[k] - p[k - 1]) / P.dy;
+        double b1 = 0., b2 = 0.;
+        if (rot) vertex_vel(P, p, KV11[k + ld], KV22[k + ld], k + ld, ld, b1, b2);
+        v[k] = nu * par + (1. - nu) * (0.5 * (a2 + b2));
+    }
+}
+
+// ---------------------------------------------------------------- diagnostics (a20)
+// partial sums: [0] sum c, [1] sum |div v - q|, plus boundary velocity handled by a small kernel
+__global__ void __launch_bounds__(256) k_diag_cells(Grid g, const double *__restrict__ c, const double *__restrict__ u, const double *__restrict__ v,
+                                                    const double *__restrict__ q, double dx, double dy, double *__restrict__ part, long long stride) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double m = 0., e = 0., cmax = -DBL_MAX, cmin = DBL_MAX;
+    if (i < g.N1 && j < g.N2) {
+        const size_t k = gidx(g, i, j);
+        m = c[k]; cmax = m; cmin = m;
+        const double div = (v[k + 1] - v[k]) / dy + (u[k + g.ld] - u[k]) / dx;
+        e = fabs(div - q[k]);
+    }
+    m = block_reduce<RED_SUM>(m);
+    e = block_reduce<RED_SUM>(e);
+    cmax = block_reduce<RED_MAX>(cmax);
+    cmin = block_reduce<RED_MIN>(cmin);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const long long b = blockIdx.y * gridDim.x + blockIdx.x;
+        part[b] = m; part[stride + b] = e; part[2 * stride + b] = cmax; part[3 * stride + b] = cmin;
+    }
+}
+// no-flow boundary velocity sum: src/Impec2DSolver.cpp:562-588
+__global__ void __launch_bounds__(256) k_diag_boundary(Grid g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ part) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.;
+    if (t < g.N1) s += fabs(v[gidx(g, t, 0)]) + fabs(v[gidx(g, t, g.N2)]);
+    if (t < g.N2) s += fabs(u[gidx(g, 0, t)]) + fabs(u[gidx(g, g.N1, t)]);
+    s = block_reduce<RED_SUM>(s);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}

@@ -1,0 +1,203 @@
+// kernels_transport.inl -- ghost fills, source step, split advection sweeps, CFL reduction.
+// Replaces the loop nests of the reference cited at each kernel (paths under /root/reference/).
+// All arithmetic is FP64 and written in the reference's operation order; the library is compiled with
+// -fmad=false so this explicit path is bit-identical to the CPU oracle.
+
+struct DevParams {
+    double dx, dy, x_lb, y_lb;
+    double mu_res, mq;             // mq = (mu_res/mu_inj)^(1/4)
+    double nu, porosity, inj_fluid_conc;
+    double alpha_l, alpha_t;
+    // rotated-frame constants (src/EllipticSolver.cpp:72-93)
+    double dxi, deta, secamt2, cosa2, sina2, costsina, cosasint, cost2, sint2, cosa, sint, cost, sina;
+    int avgproc, is_test, testno;
+};
+
+// ---------------------------------------------------------------- ghost fills (a1, part of a12)
+IMPEC_HD int reflect_cell(int i, int N) { return i < 0 ? -i - 1 : (i >= N ? 2 * N - 1 - i : i); }
+IMPEC_HD int wrap_cell(int i, int N) { return i < 0 ? i + N : (i >= N ? i - N : i); }
+
+// Thread t enumerates the ghost cells only: first the 2*ng ghost rows (coalesced), then the 2*ng ghost
+// columns of the interior rows.  Neumann: src/Util.cpp:283-324; periodic: src/Util.cpp:215-256.
+__global__ void k_fill_scalar(Grid g, double *__restrict__ a, int periodic, int ng) {
+    const long long W = g.N2 + 2 * ng;
+    const long long nrowpart = 2LL * ng * W;
+    const long long total = nrowpart + 2LL * ng * g.N1;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int i, j;
+    if (t < nrowpart) {
+        const int r = (int)(t / W);
+        j = (int)(t % W) - ng;
+        i = r < ng ? r - ng : g.N1 + (r - ng);
+    } else {
+        t -= nrowpart;
+        i = (int)(t / (2 * ng));
+        const int cidx = (int)(t % (2 * ng));
+        j = cidx < ng ? cidx - ng : g.N2 + (cidx - ng);
+    }
+    const int si = periodic ? wrap_cell(i, g.N1) : reflect_cell(i, g.N1);
+    const int sj = periodic ? wrap_cell(j, g.N2) : reflect_cell(j, g.N2);
+    a[gidx(g, i, j)] = a[gidx(g, si, sj)];
+}
+
+// Closed form of the (order dependent) statement sequence in src/Util.cpp:331-438:
+//   u(i,j) = s_i * u(face-mirror(i), cell-mirror(j)),  v(i,j) = s_j * v(cell-mirror(i), face-mirror(j)),
+// with s = -1 when the normal index was mirrored.  u is filled on i in [-ng,N1+ng], j in [-ng,N2+ng);
+// v on i in [-ng,N1+ng), j in [-ng,N2+ng].
+__global__ void k_fill_velocity(Grid g, double *__restrict__ u, double *__restrict__ v, int ng) {
+    const int W = g.N2 + 1 + 2 * ng, H = g.N1 + 1 + 2 * ng;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)W * H) return;
+    const int i = (int)(t / W) - ng, j = (int)(t % W) - ng;
+    // u component
+    if (j < g.N2 + ng && !(i >= 0 && i <= g.N1 && j >= 0 && j < g.N2)) {
+        const int si = i < 0 ? -i : (i > g.N1 ? 2 * g.N1 - i : i);
+        const int sj = reflect_cell(j, g.N2);
+        const double val = u[gidx(g, si, sj)];
+        u[gidx(g, i, j)] = (si != i) ? -val : val;
+    }
+    // v component
+    if (i < g.N1 + ng && !(i >= 0 && i < g.N1 && j >= 0 && j <= g.N2)) {
+        const int si = reflect_cell(i, g.N1);
+        const int sj = j < 0 ? -j : (j > g.N2 ? 2 * g.N2 - j : j);
+        const double val = v[gidx(g, si, sj)];
+        v[gidx(g, i, j)] = (sj != j) ? -val : val;
+    }
+}
+
+// ---------------------------------------------------------------- source step (a15)
+// src/TRIntegrator.cpp:49-71.  q is non-zero only in the wells, so the step runs over a compact list
+// of (cell, q) pairs built once at upload time instead of over the whole field.
+__global__ void k_source_tr(int n, const int *__restrict__ cell_i, const int *__restrict__ cell_j,
+                            const double *__restrict__ qv, Grid g, double *__restrict__ c,
+                            double dt, double c_inj, double *__restrict__ massdiff) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double qij = qv[t];
+    const size_t k = gidx(g, cell_i[t], cell_j[t]);
+    double md = 0.0;
+    if (qij < 0) {
+        const double old = c[k];
+        const double nw = old * (1 + 0.5 * dt * qij) / (1 - 0.5 * dt * qij);
+        c[k] = nw;
+        md = nw - old;
+    } else if (qij > 0) {
+        c[k] += dt * c_inj * qij;
+    }
+    massdiff[t] = md;
+}
+
+// ---------------------------------------------------------------- MUSCL-Hancock / upwind fluxes (a17, a18)
+// src/HyperbolicSolver.cpp:208-210
+template <bool PHI1> IMPEC_D double flux_fn(double vel, double conc, double phi) {
+    return PHI1 ? vel * conc : vel * conc / phi;
+}
+// src/UpwindSplitSolver.cpp:63-65
+template <bool PHI1> IMPEC_D double upwind_flux(double speed, double UL, double UR, double phi) {
+    return (speed > 0) ? flux_fn<PHI1>(speed, UL, phi) : flux_fn<PHI1>(speed, UR, phi);
+}
+// src/MUSCLSplitSolver.cpp:61-85 (limiter argument ignored upstream: always the w = 0 van-Leer form)
+IMPEC_D double muscl_slope(double du_m, double du_p) {
+    double lim = 0.;
+    if (du_m * du_p > 0) {
+        double r = du_m / du_p;
+        if (r > DBL_MAX) r = DBL_MAX;
+        const double a = 2. * r / (1. + r);
+        const double b = 2. / (1. + r);
+        lim = (b < a) ? b : a;
+    }
+    return lim * 0.5 * (du_m + du_p);
+}
+// src/MUSCLSplitSolver.cpp:87-93 and :122-127: boundary-extrapolated values evolved by half a step
+template <bool PHI1>
+IMPEC_D void muscl_evolve(double vL, double vR, double Um, double U0, double Up, double h, double phi, double &ULbar, double &URbar) {
+    const double d = muscl_slope(U0 - Um, Up - U0);
+    const double UR = U0 + 0.5 * d, UL = U0 - 0.5 * d;
+    const double df = h * (flux_fn<PHI1>(vL, UL, phi) - flux_fn<PHI1>(vR, UR, phi));
+    URbar = UR + df;
+    ULbar = UL + df;
+}
+
+// One directional sweep c_out = c_in + dt/h (F_lo - F_hi) with the fluxes evaluated on the fly (no F/G or
+// U_Lin temporaries).  DIR 0: x sweep, stencil across rows (src/HyperbolicSplitSolver.cpp:113-133,
+// src/MUSCLSplitSolver.cpp:102-141); DIR 1: y sweep, stencil inside a row (:139-159, :152-189).
+// METHOD 0 MUSCL, 1 first-order upwind (src/UpwindSplitSolver.cpp:43-61).
+// AVG: also write 0.5*(other + result) -- the symmetric-parallel average of
+// src/HyperbolicSplitSolver.cpp:87-103 fused into the last sweep.
+// The cell range [i0,i1) x [j0,j1) is chosen by the host (ghost strips are swept only where a later
+// sweep reads them).
+template <int DIR, int METHOD, bool PHI1, bool AVG>
+__global__ void __launch_bounds__(256) k_sweep(Grid g, const double *__restrict__ cin, const double *__restrict__ vel,
+                                               double *__restrict__ cout, const double *__restrict__ other,
+                                               double dt, double hstep, double phi, int i0, int i1, int j0, int j1) {
+    const int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= i1 || j >= j1) return;
+    const int s = DIR == 0 ? g.ld : 1;                     // stride along the sweep direction
+    const size_t k = gidx(g, i, j);
+    const double c0 = cin[k];
+    double Flo, Fhi;
+    const double v0 = vel[k], v1 = vel[k + s];            // normal velocity on the low / high face of the cell
+    if (METHOD == 1) {
+        Flo = upwind_flux<PHI1>(v0, cin[k - s], c0, phi);
+        Fhi = upwind_flux<PHI1>(v1, c0, cin[k + s], phi);
+    } else {
+        const double cm2 = cin[k - 2 * s], cm1 = cin[k - s], cp1 = cin[k + s], cp2 = cin[k + 2 * s];
+        const double vm1 = vel[k - s], v2 = vel[k + 2 * s];
+        const double h = 0.5 * dt / hstep;
+        double Lm, Rm, L0, R0, Lp, Rp;
+        muscl_evolve<PHI1>(vm1, v0, cm2, cm1, c0, h, phi, Lm, Rm);     // cell - 1
+        muscl_evolve<PHI1>(v0, v1, cm1, c0, cp1, h, phi, L0, R0);      // this cell
+        muscl_evolve<PHI1>(v1, v2, c0, cp1, cp2, h, phi, Lp, Rp);      // cell + 1
+        Flo = upwind_flux<PHI1>(v0, Rm, L0, phi);
+        Fhi = upwind_flux<PHI1>(v1, R0, Lp, phi);
+    }
+    double r = c0 + dt / hstep * (Flo - Fhi);
+    if (AVG) r = 0.5 * (other[k] + r);
+    cout[k] = r;
+}
+
+// ---------------------------------------------------------------- time-step reductions (a13)
+// MODE 0: max over cells of max(|u_c|,|v_c|)            (src/HyperbolicSolver.cpp:123-156)
+// MODE 1: min over cells of min(dx/|u_c|, dy/|v_c|)     (test mode, :100-121)
+// MODE 2: min over cells of dx^2 / (2 (d11+d22))        (diffusive limit, :157-191)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dt_reduce(Grid g, const double *__restrict__ u, const double *__restrict__ v,
+                                                   DevParams P, double *__restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double val = (MODE == 0) ? red_identity<RED_MAX>() : red_identity<RED_MIN>();
+    if (i < g.N1 && j < g.N2) {
+        const size_t k = gidx(g, i, j);
+        if (MODE == 2) {
+            const double vij = 0.5 * (v[k] + v[k + 1]);
+            const double uij = 0.5 * (u[k] + u[k + g.ld]);
+            const double v2 = vij * vij, u2 = uij * uij, absu = sqrt(v2 + u2);
+            const double d11 = P.dx / absu * (P.alpha_l * u2 + P.alpha_t * v2);
+            const double d22 = P.dx / absu * (P.alpha_l * v2 + P.alpha_t * u2);
+            val = 1. / 2 * P.dx * P.dx / (d11 + d22);
+        } else {
+            double uc = fabs(0.5 * (u[k] + u[k + g.ld]));
+            double vc = fabs(0.5 * (v[k] + v[k + 1]));
+            if (uc < DBL_MIN) uc = DBL_MIN;
+            if (vc < DBL_MIN) vc = DBL_MIN;
+            if (MODE == 0) val = uc > vc ? uc : vc;
+            else { const double a = P.dx / uc, b = P.dy / vc; val = b < a ? b : a; }
+        }
+    }
+    val = (MODE == 0) ? block_reduce<RED_MAX>(val) : block_reduce<RED_MIN>(val);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = val;
+}
+
+// Stage 2 of every reduction: one block combines n partials in a fixed pairwise tree (deterministic).
+// Up to 3 independent reductions are finished by one launch (blockIdx.x selects which).
+template <int OP>
+__global__ void __launch_bounds__(1024) k_reduce_final(const double *__restrict__ part, long long n, long long stride, double *__restrict__ out) {
+    const double *p = part + (long long)blockIdx.x * stride;
+    double acc = red_identity<OP>();
+    // fixed assignment: thread t owns elements t, t+1024, ... combined in index order
+    for (long long k = threadIdx.x; k < n; k += blockDim.x) acc = red_op<OP>(acc, p[k]);
+    acc = block_reduce<OP>(acc);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}

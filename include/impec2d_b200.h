@@ -1,0 +1,145 @@
+/* impec2d_b200.h -- C ABI of the B200-native IMPES hot path for pw359/Impec2D.
+ *
+ * The reference has no FFI boundary: its solvers are C++ classes new-ed in
+ * Impec2DSolver::Initialize (src/Impec2DSolver.cpp:131-133).  This header is the boundary a
+ * maintainer binds instead: each entry point names the reference method whose loop nest it
+ * replaces (paths relative to the reference tree).  The host-side mirror of the reference classes
+ * (impec2d_b200/host/, same class and method names) is a thin layer over these calls; see
+ * INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a HOST pointer unless the name ends in _dev
+ *   - host field layouts are the reference's (src/Impec2DSolver.cpp:151-182):
+ *       scalar c,p : (N1+2g) x (N2+2g) doubles, C order, j fastest, g = num_ghostcells
+ *       velocity   : (N1+1+2g) x (N2+1+2g) x 2 doubles, component fastest (blitz Array3d)
+ *       q          : N1*N2 doubles, q[i*N2+j]
+ *   - one context per process / GPU; calls on one context must be serialised by the caller; all
+ *     device work is enqueued on the context's stream and calls that return scalars synchronise it
+ *   - return value: 0 = ok, negative = error (impec_last_error gives the text); never exit()
+ *   - there is NO CPU fallback: creating a context without a CUDA device fails
+ */
+#ifndef IMPEC2D_B200_H_
+#define IMPEC2D_B200_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMPEC_OK 0
+#define IMPEC_ERR_ARG (-1)
+#define IMPEC_ERR_CUDA (-2)
+#define IMPEC_ERR_UNSUPPORTED (-3)
+#define IMPEC_ERR_NOCONV (-4)
+#define IMPEC_ERR_NCCL (-5)
+
+/* enum values follow src/SimParams.h:13-27 */
+enum { IMPEC_PARALLEL = 0, IMPEC_DIAGONAL = 1, IMPEC_HORIZONTAL = 2 };                       /* S_Type        */
+enum { IMPEC_MEANCONC = 0, IMPEC_HARMONIC = 1 };                                             /* AVG_PROC      */
+enum { IMPEC_ALTERNATING = 0, IMPEC_X_FIRST = 1, IMPEC_Y_FIRST = 2, IMPEC_STRANG = 3, IMPEC_SYMMETRIC_PARALLEL = 4 }; /* DIM_SPLITTING */
+enum { IMPEC_MUSCL = 0, IMPEC_UPWIND = 1 };                                                  /* hyper_method  */
+enum { IMPEC_EXPLICIT = 0, IMPEC_CRANKNICOLSON = 1 };                                        /* P_Type        */
+
+/* The subset of SimParams (src/SimParams.h:29-173) the hot path reads. */
+typedef struct impec_params {
+    int    N1, N2, g;                 /* x_cells, y_cells, num_ghostcells (must be 2)              */
+    double x_lb, x_ub, y_lb, y_ub;
+    double mu_res, mu_inj;
+    int    avgproc;
+    double nu;
+    int    is_test, testno;
+    int    stype;
+    double porosity, cfl, inj_fluid_conc;
+    int    diffusion;
+    double alpha_l, alpha_t, dt_diff_limit;
+    int    ptype;
+    double eps, para_eps;
+    int    hyper_method;
+    int    dim_splitting;
+    /* solver controls (ours: the reference has HYPRE StructPCG+SMG here, src/MGSolver.cpp:594-629) */
+    int    max_iter;                  /* 10000 upstream                                            */
+    int    mg_max_levels;             /* 0 = as deep as the grid allows                            */
+    int    mg_nmin;                   /* stop coarsening once min(N1,N2) <= mg_nmin (default 4)    */
+    int    mg_ncoarse;                /* symmetric GS sweeps on the coarsest level (default 8)     */
+    int    mg_w_from, mg_w_to;        /* levels visited twice per cycle (default 2..4)             */
+} impec_params;
+
+typedef struct impec_diag {           /* src/Impec2DSolver.h:16-25 plus the per-step extrema        */
+    double total_mass;                /* GetTotalMass            src/Impec2DSolver.cpp:607-620      */
+    double divergence_error;          /* CalculateDivergenceError :542-557                          */
+    double boundary_velocity_error;   /* CalculateVelocityBoundaryError :562-588                    */
+    double total_mass_outflux;        /* HyperbolicSolver::GetTotalMassOutflux                      */
+    double c_min, c_max;
+} impec_diag;
+
+typedef struct impec_solve_info {
+    int    iterations;                /* PCG iterations (MGSolver::num_iterations)                  */
+    double relres;                    /* recurrence ||r||/||b||, the quantity HYPRE's PCG tests      */
+    double true_relres;               /* ||b - A x||/||b|| recomputed after the solve               */
+    int    converged;
+} impec_solve_info;
+
+typedef struct impec_ctx impec_ctx;
+
+void  impec_default_params(impec_params *p);
+const char *impec_version(void);
+int   impec_is_emulated(void);        /* 1 only for the CPU-emulated test build (never shipped)    */
+
+/* rank/nranks: slab decomposition along i over the GPUs of one node; nccl_unique_id = 128 bytes from
+ * impec_nccl_unique_id on rank 0 (NULL when nranks == 1).  cuda_stream: a cudaStream_t to enqueue on, or
+ * NULL for a context-owned stream. */
+int   impec_nccl_unique_id(char id_out[128]);
+int   impec_ctx_create(const impec_params *p, int device, int rank, int nranks, const char *nccl_unique_id,
+                       void *cuda_stream, impec_ctx **out);
+void  impec_ctx_destroy(impec_ctx *ctx);
+const char *impec_last_error(const impec_ctx *ctx);
+int   impec_synchronize(impec_ctx *ctx);
+
+/* host <-> device, reference layouts (Impec2DSolver owns p,c,v,q: src/Impec2DSolver.h:31-46) */
+int   impec_upload_c(impec_ctx *ctx, const double *c_ghosted);
+int   impec_upload_p(impec_ctx *ctx, const double *p_ghosted);
+int   impec_upload_q(impec_ctx *ctx, const double *q);
+int   impec_upload_velocity(impec_ctx *ctx, const double *v_aos);
+int   impec_download_c(impec_ctx *ctx, double *c_ghosted);
+int   impec_download_p(impec_ctx *ctx, double *p_ghosted);
+int   impec_download_velocity(impec_ctx *ctx, double *v_aos);
+/* device-resident alternatives for callers that already hold device memory (padded layout) */
+int   impec_field_layout(const impec_ctx *ctx, int *ld, int *row0, int *col0, int *rows);
+void *impec_field_dev(impec_ctx *ctx, const char *name);   /* "c","p","q","u","v" */
+int   impec_set_q_dev_changed(impec_ctx *ctx);             /* rebuild the well list after writing q on the device */
+
+/* a1   HyperbolicSolver::FillBoundaries            src/HyperbolicSolver.cpp:56-61 */
+int   impec_fill_boundaries(impec_ctx *ctx);
+/* a8-a11 EllipticSolver::Solve -> MGSolver::SolveLinearMultigrid -> Solve_Elliptic_cc_to_c
+ *      src/EllipticSolver.cpp:133-142, src/MGSolver.cpp:145-149, 223-248 */
+int   impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info *info);
+/* a12  EllipticSolver::CalcVelocities              src/EllipticSolver.cpp:660-683 */
+int   impec_calc_velocities(impec_ctx *ctx);
+/* a13  HyperbolicSolver::MaxStableTimestep         src/HyperbolicSolver.cpp:93-198 */
+int   impec_max_stable_dt(impec_ctx *ctx, double *dt);
+/* a15  HyperbolicSolver::SourceSplit / TRIntegrator::Integrate  src/HyperbolicSolver.cpp:201-205, src/TRIntegrator.cpp:49-71 */
+int   impec_source_split(impec_ctx *ctx, double dt);
+/* a16  HyperbolicSplitSolver::Advect_X / Advect_Y / AdvectSplit src/HyperbolicSplitSolver.cpp:51-159 */
+int   impec_advect_x(impec_ctx *ctx, double dt);
+int   impec_advect_y(impec_ctx *ctx, double dt);
+int   impec_advect_split(impec_ctx *ctx, double dt);
+/* a19  HyperbolicSolver::DiffusionSplitCN -> MGSolver::Solve_Parabolic_cc_to_c  src/HyperbolicSolver.cpp:213-223, src/MGSolver.cpp:952-976 */
+int   impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info *info);
+/* a14  HyperbolicSplitSolver::Solve                src/HyperbolicSplitSolver.cpp:162-198 */
+int   impec_transport_step(impec_ctx *ctx, double dt);
+/* a20  one iteration of the while loop in Impec2DSolver::Solve  src/Impec2DSolver.cpp:339-389.
+ *      t_next_output <= t disables output-time clipping.  dt_used and info may be NULL. */
+int   impec_impes_step(impec_ctx *ctx, double t, double t_next_output, double *dt_used, impec_solve_info *info);
+/* a20  diagnostics of the loop body                src/Impec2DSolver.cpp:391-415, 530-620 */
+int   impec_diagnostics(impec_ctx *ctx, impec_diag *out);
+
+/* benchmark / test hooks */
+int   impec_build_operator(impec_ctx *ctx);                              /* a2-a8: links from the current c */
+int   impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host); /* one MG cycle; NULL/NULL = on the internal residual */
+int   impec_mg_levels(const impec_ctx *ctx);
+long long impec_kernel_launches(const impec_ctx *ctx);                   /* kernels launched by this context so far */
+int   impec_reset_state(impec_ctx *ctx);                                 /* produced mass := 0, sweep parity := Y */
+int   impec_set_option(impec_ctx *ctx, const char *key, double value);   /* e.g. "warm_start" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

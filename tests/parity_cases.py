@@ -1,0 +1,177 @@
+"""Parity checks of the C-ABI library against the CPU oracle.  Each function takes `emulated`:
+tests/test_emu_parity.py runs them on the CPU emulator (no GPU needed), tests/test_gpu_parity.py runs the
+very same checks on the B200 through the real library (-m gpu)."""
+import ctypes as C
+import numpy as np
+import oracle as O
+import impec2d_b200 as I
+from helpers import production_case, advection_case, aos, interior, rel_l2
+
+# Tolerances (stated here, used below):
+#   explicit transport path (fills, source, sweeps, CFL): BIT-EXACT (same operation order, no FMA contraction)
+#   pressure / velocity: converged-solution parity, ||p_gpu - p_oracle||_2 / ||p_oracle||_2 <= 1e-9
+TOL_P = 1e-9
+TOL_VCYCLE = 1e-10
+
+
+def check_ghost_fills(emulated):
+    lib = O.lib()
+    for (N1, N2, test) in ((8, 8, 0), (12, 20, 0), (16, 8, 1)):
+        Po = O.default_params(N1=N1, N2=N2, is_test=test, testno=1)
+        Pi = I.default_params(emulated=emulated, N1=N1, N2=N2, is_test=test, testno=1)
+        rng = np.random.default_rng(N1 * 100 + N2)
+        c = rng.random((N1 + 4, N2 + 4))
+        ctx = I.Context(Pi, emulated=emulated)
+        ctx.upload_c(c); ctx.fill_boundaries()
+        cg = ctx.download_c()
+        lib.orc_fill_boundaries(C.byref(Po), c)
+        assert np.array_equal(cg, c), "scalar ghost fill differs (N=%dx%d test=%d)" % (N1, N2, test)
+        ctx.close()
+
+
+def check_velocity_roundtrip(emulated):
+    Pi = I.default_params(emulated=emulated, N1=12, N2=8)
+    ctx = I.Context(Pi, emulated=emulated)
+    v = np.random.default_rng(3).random(ctx.velocity_shape())
+    ctx.upload_velocity(v)
+    assert np.array_equal(ctx.download_velocity(), v)
+    ctx.close()
+
+
+def check_advection_bitexact(emulated, N=40, steps=4, method=O.MUSCL, split=O.SYMMETRIC_PARALLEL, porosity=1.0, perturb=True):
+    lib = O.lib()
+    base, Po, c, u, v = advection_case(N, hyper_method=method, dim_splitting=split, porosity=porosity)
+    if perturb:   # non-constant velocity and rough data exercise every limiter branch
+        rng = np.random.default_rng(7)
+        u += 0.4 * rng.random(u.shape); v -= 0.3 * rng.random(v.shape)
+        interior(Po, c)[...] += rng.random((N, N)) * (rng.random((N, N)) > 0.5)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    q = np.zeros(N * N)
+    ctx.upload_c(c); ctx.upload_q(q); ctx.upload_velocity(aos(u, v))
+    dt_o = lib.orc_max_stable_dt(C.byref(Po), u, v)
+    dt_g = ctx.max_stable_dt()
+    assert dt_o == dt_g, (dt_o, dt_g)
+    So = O.new_state()
+    co = c.copy()
+    for _ in range(steps):
+        lib.orc_transport_step(C.byref(Po), C.byref(So), co, u, v, q, dt_o)
+        ctx.transport_step(dt_o)
+    cg = ctx.download_c()
+    assert np.array_equal(cg, co), "max diff %g" % np.abs(cg - co).max()
+    ctx.close()
+
+
+def check_single_sweeps_bitexact(emulated, N=24):
+    lib = O.lib()
+    base, Po, c, u, v = advection_case(N)
+    rng = np.random.default_rng(11)
+    u += 0.4 * rng.random(u.shape); v -= 0.3 * rng.random(v.shape)
+    lib.orc_fill_boundaries(C.byref(Po), c)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_velocity(aos(u, v)); ctx.upload_q(np.zeros(N * N))
+    for fn_o, fn_g, vel in ((lib.orc_advect_x, ctx.advect_x, u), (lib.orc_advect_y, ctx.advect_y, v)):
+        co = c.copy()
+        ctx.upload_c(c)
+        fn_o(C.byref(Po), co, vel, 0.01)
+        fn_g(0.01)
+        assert np.array_equal(ctx.download_c(), co)
+    ctx.close()
+
+
+def check_source_step(emulated, N=32):
+    lib = O.lib()
+    base, Po, c, q = production_case(N)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    interior(Po, c)[...] = np.random.default_rng(5).random((N, N))
+    ctx.upload_c(c); ctx.upload_q(q)
+    co = c.copy()
+    md = 0.0
+    for dt in (1e-3, 2.5e-3):
+        md += abs(lib.orc_tr_integrate(C.byref(Po), co, q, dt))
+        ctx.source_split(dt)
+    assert np.array_equal(ctx.download_c(), co)
+    d = ctx.diagnostics()
+    assert abs(d.total_mass_outflux - md) <= 1e-13 * abs(md)
+    ctx.close()
+
+
+def check_vcycle(emulated, N1=32, N2=32, stype=O.PARALLEL, nu=2.0 / 3.0):
+    lib = O.lib()
+    base, Po, c, q = production_case(N1, N2, stype=stype, nu=nu)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    lib.orc_fill_boundaries(C.byref(Po), c)
+    A = np.zeros(N1 * N2 * 9); b = np.zeros(N1 * N2)
+    lib.orc_assemble_elliptic(C.byref(Po), c, q, A, b)
+    r = np.random.default_rng(1).standard_normal(N1 * N2)
+    zo = np.zeros(N1 * N2)
+    assert lib.orc_mg_apply(C.byref(Po), N1, N2, A, -1, r, zo) == 0
+    ctx.upload_c(c); ctx.upload_q(q); ctx.build_operator()
+    zg = ctx.vcycle(r)
+    assert np.abs(zg - zo).max() <= TOL_VCYCLE * np.abs(zo).max()
+    ctx.close()
+
+
+def check_impes_step(emulated, N1=48, N2=48, stype=O.PARALLEL, nu=2.0 / 3.0, avg=O.HARMONIC, eps=1e-12, steps=2):
+    """One and two full IMPES steps (a20): pressure to TOL_P, velocities/dt/c to the tolerance the pressure
+    tolerance implies, same iteration count +-1."""
+    lib = O.lib()
+    base, Po, c, q = production_case(N1, N2, stype=stype, nu=nu, avgproc=avg, eps=eps)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    So = O.new_state()
+    p = O.scalar_field(Po); u = O.velocity_field(Po); v = O.velocity_field(Po)
+    co = c.copy()
+    t = 0.0
+    for _ in range(steps):
+        dto = lib.orc_impes_step(C.byref(Po), C.byref(So), p, co, u, v, q, t, 0.0)
+        dtg, info = ctx.impes_step(t, 0.0)
+        assert info.converged == 1 and info.relres < eps
+        assert info.true_relres < 50 * eps
+        assert abs(info.iterations - So.last_its) <= 1
+        assert abs(dtg - dto) <= 1e-9 * dto
+        t += dto
+    pg = ctx.download_p(); cg = ctx.download_c(); vg = ctx.download_velocity()
+    assert rel_l2(interior(Po, pg), interior(Po, p)) <= TOL_P
+    assert np.abs(vg[..., 0] - u).max() <= 1e-8 * np.abs(u).max()
+    assert np.abs(vg[..., 1] - v).max() <= 1e-8 * np.abs(v).max()
+    assert np.abs(cg - co).max() <= 1e-8
+    d = ctx.diagnostics()
+    assert abs(d.total_mass - lib.orc_total_mass(C.byref(Po), co)) <= 1e-9 * d.total_mass
+    assert abs(d.total_mass_outflux - So.total_mass_outflux) <= 1e-8 * max(So.total_mass_outflux, 1e-30)
+    ctx.close()
+
+
+def check_elliptic_manufactured(emulated, N1=20, N2=30, testno=4, nu=1.0):
+    """elliptic_test.cfg: p = cos x cos y, Neumann, K(x,y) test fields; GPU pressure vs oracle and vs exact."""
+    lib = O.lib()
+    kw = dict(N1=N1, N2=N2, x_ub=2 * np.pi, y_ub=2 * np.pi, mu_res=1.0, mu_inj=1.0, avgproc=O.MEANCONC, nu=nu,
+              is_test=1, testno=testno, stype=O.DIAGONAL, eps=1e-12)
+    Po = O.default_params(**kw); Pi = I.default_params(emulated=emulated, **kw)
+    c = O.scalar_field(Po); p = O.scalar_field(Po); pex = O.scalar_field(Po)
+    u = O.velocity_field(Po); v = O.velocity_field(Po); uex = O.velocity_field(Po); vex = O.velocity_field(Po)
+    q = np.zeros(N1 * N2)
+    lib.orc_init_elliptic_test(C.byref(Po), pex, q, uex, vex)
+    So = O.new_state()
+    lib.orc_solve_elliptic(C.byref(Po), C.byref(So), c, q, p)
+    lib.orc_calc_velocities(C.byref(Po), p, c, u, v)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    # Neumann ghosts although is_test: TestNeumann fills c by hand (src/EllipticSolver.cpp:231)
+    info = ctx.pressure_solve()
+    ctx.calc_velocities()
+    pg = ctx.download_p(); vg = ctx.download_velocity()
+    assert info.converged == 1
+    assert rel_l2(interior(Po, pg), interior(Po, p)) <= TOL_P
+    g = Po.g
+    assert np.abs(vg[g:g + N1 + 1, g:g + N2, 0] - u[g:g + N1 + 1, g:g + N2]).max() <= 1e-8
+    assert np.abs(vg[g:g + N1, g:g + N2 + 1, 1] - v[g:g + N1, g:g + N2 + 1]).max() <= 1e-8
+    err_g = np.abs(interior(Po, pg) - interior(Po, pex)).sum() * Po.dx * Po.dy
+    err_o = np.abs(interior(Po, p) - interior(Po, pex)).sum() * Po.dx * Po.dy
+    assert abs(err_g - err_o) <= 1e-6 * err_o
+    ctx.close()
+    return Po.dx, err_g

@@ -1,0 +1,97 @@
+"""CPU checks of the drop-in boundary: every symbol include/impec2d_b200.h declares is exported by the built
+library, the ctypes structs match the C structs, and the product loader refuses a CPU fallback."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+import pytest
+import impec2d_b200 as I
+from impec2d_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "impec2d_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(impec_[a-z_0-9]+)\s*\(", src)))
+
+
+def build_emu():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "impec2d_b200", "csrc"), "emu"])
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_lib.EXPORTS)
+
+
+def test_cuda_library_exports_every_symbol():
+    path = I.library_path(False)
+    if not os.path.exists(path):
+        pytest.skip("CUDA library not built yet (run __graft_entry__.build())")
+    out = subprocess.check_output(["nm", "-D", "--defined-only", path]).decode()
+    exported = set(re.findall(r" T (impec_[a-z_0-9]+)", out))
+    missing = [s for s in declared_symbols() if s not in exported]
+    assert not missing, missing
+    # the product library must contain sm_100a code
+    elf = subprocess.check_output(["/usr/local/cuda/bin/cuobjdump", "-lelf", path]).decode()
+    assert "sm_100a" in elf
+
+
+def test_struct_sizes_match_c():
+    code = r'''
+    #include <stdio.h>
+    #include "include/impec2d_b200.h"
+    #include "oracle/impec_oracle.h"
+    int main(){ printf("%zu %zu %zu %zu %zu\n", sizeof(impec_params), sizeof(impec_diag), sizeof(impec_solve_info), sizeof(orc_params), sizeof(orc_state)); return 0; }
+    '''
+    import oracle as O
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(code)
+        subprocess.check_call(["/usr/bin/gcc", "-I", ROOT, "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [C.sizeof(I.Params), C.sizeof(I.Diag), C.sizeof(I.SolveInfo), C.sizeof(O.Params), C.sizeof(O.State)]
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, never silently compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    path = I.library_path(False)
+    if not os.path.exists(path):
+        with pytest.raises(RuntimeError):
+            I.load(False)
+        return
+    P = I.default_params(N1=16, N2=16)
+    with pytest.raises(I.ImpecError):
+        I.Context(P)
+
+
+def test_emulated_library_is_flagged_and_never_substituted():
+    build_emu()
+    assert I.load(emulated=True).impec_is_emulated() == 1
+    # the loader selects by file name and then verifies the flag: pointing it at the wrong file must raise
+    saved = _lib.library_path
+    try:
+        _lib._CACHE.pop(False, None)
+        _lib.library_path = lambda emulated=False: saved(True)      # pretend the product .so IS the emulator
+        with pytest.raises(RuntimeError, match="emulated"):
+            _lib.load(False)
+    finally:
+        _lib.library_path = saved
+        _lib._CACHE.pop(False, None)
+
+
+def test_argument_errors_are_reported_not_fatal():
+    build_emu()
+    P = I.default_params(emulated=True, N1=16, N2=16, g=3)
+    with pytest.raises(I.ImpecError, match="num_ghostcells"):
+        I.Context(P, emulated=True)
+    P = I.default_params(emulated=True, N1=16, N2=16)
+    ctx = I.Context(P, emulated=True)
+    with pytest.raises(I.ImpecError, match="upload_q"):
+        ctx.pressure_solve()
+    with pytest.raises(I.ImpecError, match="unknown option"):
+        ctx.set_option("nonsense", 1)

@@ -1,0 +1,38 @@
+"""CPU-side parity: the CUDA kernel SOURCE executed by the emulator (impec2d_b200/csrc/emu.cpp) against the
+oracle.  Validates index logic and host orchestration in this GPU-less container; the same checks run on the
+B200 in tests/test_gpu_parity.py.  The emulated library is never used by the product."""
+import os
+import subprocess
+import pytest
+import oracle as O
+import impec2d_b200 as I
+import parity_cases as pc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu_lib():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "..", "impec2d_b200", "csrc"), "emu"])
+    return I.load(emulated=True)
+
+
+def test_ghost_fills(): pc.check_ghost_fills(True)
+def test_velocity_roundtrip(): pc.check_velocity_roundtrip(True)
+def test_single_sweeps_bitexact(): pc.check_single_sweeps_bitexact(True)
+def test_advection_muscl_bitexact(): pc.check_advection_bitexact(True, N=24, steps=2)
+def test_advection_upwind_bitexact(): pc.check_advection_bitexact(True, N=24, steps=2, method=O.UPWIND)
+def test_advection_porosity_bitexact(): pc.check_advection_bitexact(True, N=16, steps=1, porosity=0.37)
+
+
+@pytest.mark.parametrize("split", [O.ALTERNATING, O.X_FIRST, O.Y_FIRST, O.STRANG])
+def test_advection_other_splittings_bitexact(split): pc.check_advection_bitexact(True, N=16, steps=2, split=split)
+
+
+def test_source_step(): pc.check_source_step(True, N=32)
+def test_vcycle_parallel(): pc.check_vcycle(True, 32, 32)
+def test_vcycle_rect_diagonal(): pc.check_vcycle(True, 32, 16, stype=O.DIAGONAL)
+def test_impes_step_parallel(): pc.check_impes_step(True, 32, 32, steps=1)
+def test_impes_step_diagonal_rect(): pc.check_impes_step(True, 32, 16, stype=O.DIAGONAL, steps=1)
+def test_elliptic_manufactured_5pt(): pc.check_elliptic_manufactured(True, 20, 30, testno=4, nu=1.0)
+def test_elliptic_manufactured_9pt(): pc.check_elliptic_manufactured(True, 20, 30, testno=2, nu=2.0 / 3.0)

@@ -1,0 +1,101 @@
+"""B200 parity tests proper: the real sm_100a library, called through the C ABI, against the CPU oracle on the
+same seeded inputs (sizes the oracle finishes in seconds) plus size-independent properties at larger sizes."""
+import ctypes as C
+import numpy as np
+import pytest
+import oracle as O
+import impec2d_b200 as I
+import parity_cases as pc
+from helpers import production_case, advection_case, aos
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_is_cuda():
+    assert I.load(False).impec_is_emulated() == 0
+
+
+def test_ghost_fills(): pc.check_ghost_fills(False)
+def test_velocity_roundtrip(): pc.check_velocity_roundtrip(False)
+def test_single_sweeps_bitexact(): pc.check_single_sweeps_bitexact(False, N=96)
+def test_advection_muscl_bitexact(): pc.check_advection_bitexact(False, N=200, steps=10)
+def test_advection_muscl_smooth_bitexact(): pc.check_advection_bitexact(False, N=128, steps=20, perturb=False)
+def test_advection_upwind_bitexact(): pc.check_advection_bitexact(False, N=128, steps=5, method=O.UPWIND)
+def test_advection_porosity_bitexact(): pc.check_advection_bitexact(False, N=64, steps=3, porosity=0.37)
+
+
+@pytest.mark.parametrize("split", [O.ALTERNATING, O.X_FIRST, O.Y_FIRST, O.STRANG])
+def test_advection_other_splittings_bitexact(split): pc.check_advection_bitexact(False, N=64, steps=3, split=split)
+
+
+def test_source_step(): pc.check_source_step(False, N=128)
+
+
+@pytest.mark.parametrize("N1,N2,stype", [(64, 64, O.PARALLEL), (128, 64, O.DIAGONAL), (100, 50, O.DIAGONAL), (141, 141, O.PARALLEL)])
+def test_vcycle(N1, N2, stype): pc.check_vcycle(False, N1, N2, stype=stype)
+
+
+@pytest.mark.parametrize("N1,N2,stype,nu,avg", [
+    (128, 128, O.PARALLEL, 2.0 / 3.0, O.HARMONIC),        # parallel.cfg operator
+    (128, 64, O.DIAGONAL, 2.0 / 3.0, O.HARMONIC),         # diagonal_dispersion.cfg aspect (dx != dy)
+    (96, 96, O.DIAGONAL, 1.0, O.MEANCONC),                # pure 5-point
+    (256, 256, O.PARALLEL, 2.0 / 3.0, O.HARMONIC),
+])
+def test_impes_step(N1, N2, stype, nu, avg): pc.check_impes_step(False, N1, N2, stype=stype, nu=nu, avg=avg, steps=2)
+
+
+def test_elliptic_manufactured_convergence():
+    """elliptic_test.cfg on the GPU: testno 4, nu = 1, 20x30 doubling; order 2.00 +- 0.03 on the finest pair."""
+    res = [pc.check_elliptic_manufactured(False, 20 * 2 ** k, 30 * 2 ** k, testno=4, nu=1.0) for k in range(5)]
+    assert abs(np.log2(res[-2][1] / res[-1][1]) - 2.0) < 0.03
+
+
+@pytest.mark.parametrize("testno,nu", [(1, 2.0 / 3.0), (2, 2.0 / 3.0), (3, 0.5), (4, 2.0 / 3.0)])
+def test_elliptic_manufactured_variants(testno, nu): pc.check_elliptic_manufactured(False, 80, 120, testno=testno, nu=nu)
+
+
+def test_hyperbolic_convergence_order_on_gpu():
+    """hyperbolic_test.cfg on the GPU (50..400 cells): the order is the published 1.85-1.88 and the 50^2 norm
+    equals the oracle's."""
+    lib = O.lib()
+    norms = []
+    for k in range(4):
+        N = 50 * 2 ** k
+        base, Po, c, u, v = advection_case(N)
+        Pi = I.default_params(**base)
+        ctx = I.Context(Pi)
+        ctx.upload_c(c); ctx.upload_q(np.zeros(N * N)); ctx.upload_velocity(aos(u, v))
+        dtmax = ctx.max_stable_dt()
+        t = 0.0
+        while t < 1.0:
+            dt = dtmax
+            if t + dt >= 1.0: dt = 1.0 - t
+            ctx.transport_step(dt); t += dt
+        cg = ctx.download_c()
+        norms.append((Po.dx, lib.orc_advection_norm(C.byref(Po), cg, O.SINE, 1)))
+        ctx.close()
+    r = np.array(norms)
+    order = np.polyfit(np.log(r[:, 0]), np.log(r[:, 1]), 1)[0]
+    assert 1.82 < order < 1.90, order
+    assert r[0, 1] == pytest.approx(1.851837e-03, rel=1e-5)      # oracle value at 50^2
+
+
+def test_large_grid_properties():
+    """4096^2 (BASELINE config 2 size): properties that need no oracle run -- mass conservation of the
+    advection step with closed walls, residual reduction of the pressure solve, no-flow walls."""
+    N = 4096
+    base, Po, c, q = production_case(N, N, eps=1e-8)
+    Pi = I.default_params(**base)
+    ctx = I.Context(Pi)
+    ctx.upload_c(c); ctx.upload_q(q)
+    dt, info = ctx.impes_step()
+    assert info.converged == 1 and info.relres < 1e-8 and info.true_relres < 1e-7
+    d0 = ctx.diagnostics()
+    assert d0.boundary_velocity_error <= 1e-9 * N
+    assert d0.divergence_error < 1e-4
+    m0 = d0.total_mass
+    ctx.advect_split(dt)
+    d1 = ctx.diagnostics()
+    assert abs(d1.total_mass - m0) <= 1e-11 * m0            # Neumann walls, zero normal velocity
+    assert -1e-12 <= d1.c_min and d1.c_max <= 1.0 + 1e-3
+    ctx.close()

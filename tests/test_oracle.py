@@ -1,0 +1,145 @@
+"""Pins the CPU oracle to the reference's own known answers (SURVEY.md 8c / BASELINE.md section 2):
+ - manufactured elliptic test p = cos x cos y: convergence order 2.00 (examples/elliptic.eps:801-1402)
+ - periodic diagonal advection: MUSCL L1 order 1.85-1.88, upwind 1.00 (examples/hyperbolic.eps:882,945;
+   examples/hyperbolic_test.cfg:132-134)
+ - no-flow boundary velocity zero to round-off (goe.pdf 4.3.4)
+and cross-checks the restated MG-PCG against an independent sparse direct solve of the assembled matrix."""
+import ctypes as C
+import numpy as np
+import pytest
+import oracle as O
+from helpers import production_case, advection_case, interior
+
+lib = O.lib()
+OFF = [(0, 0), (-1, 0), (-1, -1), (0, -1), (1, -1), (1, 0), (1, 1), (0, 1), (-1, 1)]   # MGSolver.cpp:164-166
+
+
+def to_csr(N1, N2, A):
+    import scipy.sparse as sp
+    A = A.reshape(N1, N2, 9)
+    rows, cols, vals = [], [], []
+    I, J = np.meshgrid(np.arange(N1), np.arange(N2), indexing="ij")
+    for e, (di, dj) in enumerate(OFF):
+        m = A[:, :, e] != 0
+        rows.append((I[m] * N2 + J[m])); cols.append(((I[m] + di) * N2 + (J[m] + dj))); vals.append(A[:, :, e][m])
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N1 * N2, N1 * N2))
+
+
+def elliptic_run(N1, N2, testno, nu, avg=O.MEANCONC):
+    P = O.default_params(N1=N1, N2=N2, x_ub=2 * np.pi, y_ub=2 * np.pi, mu_res=1.0, mu_inj=1.0, avgproc=avg, nu=nu,
+                         is_test=1, testno=testno, stype=O.DIAGONAL, eps=1e-12)
+    S = O.new_state()
+    c = O.scalar_field(P); p = O.scalar_field(P); pex = O.scalar_field(P)
+    u = O.velocity_field(P); v = O.velocity_field(P); uex = O.velocity_field(P); vex = O.velocity_field(P)
+    q = np.zeros(N1 * N2)
+    lib.orc_init_elliptic_test(C.byref(P), pex, q, uex, vex)
+    assert lib.orc_solve_elliptic(C.byref(P), C.byref(S), c, q, p) == 0
+    lib.orc_calc_velocities(C.byref(P), p, c, u, v)
+    g = P.g
+    ep = np.abs(interior(P, p) - interior(P, pex)).sum() * P.dx * P.dy            # EllipticSolver.cpp:242-268
+    eu = np.abs(u[g:g + N1 + 1, g:g + N2] - uex[g:g + N1 + 1, g:g + N2]).sum() * P.dx * P.dy
+    ev = np.abs(v[g:g + N1, g:g + N2 + 1] - vex[g:g + N1, g:g + N2 + 1]).sum() * P.dx * P.dy
+    return P.dx, ep, eu, ev, S
+
+
+@pytest.mark.parametrize("testno,nu", [(4, 1.0), (4, 2.0 / 3.0), (2, 2.0 / 3.0), (1, 0.0)])
+def test_elliptic_second_order(testno, nu):
+    """elliptic_test.cfg grids 40x60 .. 320x480; published orders 2.00 (p) and 1.99-2.00 (u, v)."""
+    res = np.array([elliptic_run(20 * 2 ** k, 30 * 2 ** k, testno, nu)[:4] for k in range(1, 5)])
+    for col, lo in ((1, 1.95), (2, 1.95), (3, 1.95)):
+        order = np.polyfit(np.log(res[:, 0]), np.log(res[:, col]), 1)[0]
+        assert lo < order < 2.08, (col, order)
+    # finest pair: asymptotic rate of the pressure error
+    assert abs(np.log2(res[-2, 1] / res[-1, 1]) - 2.0) < 0.03
+
+
+def test_mgpcg_matches_sparse_direct():
+    import scipy.sparse.linalg as spla
+    for (N1, N2, stype, nu) in ((24, 24, O.PARALLEL, 2.0 / 3.0), (20, 10, O.DIAGONAL, 2.0 / 3.0), (16, 16, O.DIAGONAL, 1.0)):
+        base, P, c, q = production_case(N1, N2, stype=stype, nu=nu, eps=1e-13)
+        lib.orc_fill_boundaries(C.byref(P), c)
+        A = np.zeros(N1 * N2 * 9); b = np.zeros(N1 * N2)
+        lib.orc_assemble_elliptic(C.byref(P), c, q, A, b)
+        M = to_csr(N1, N2, A)
+        x_direct = spla.spsolve(M.tocsc(), b)
+        x = np.zeros(N1 * N2); its = C.c_int(); rr = C.c_double(); tr = C.c_double()
+        assert lib.orc_mgpcg(C.byref(P), N1, N2, A, b, -1, 1e-13, x, C.byref(its), C.byref(rr), C.byref(tr)) == 0
+        assert np.linalg.norm(x - x_direct) <= 1e-9 * np.linalg.norm(x_direct)
+        assert tr.value < 1e-11
+        # rows sum to zero away from the pin; pin row is [kappa/dA, 0...]  (MGSolver.cpp:517-567)
+        rs = np.asarray(M.sum(axis=1)).ravel()
+        pin = 1 * N2 + 1
+        mask = np.ones(N1 * N2, bool); mask[pin] = False
+        assert np.abs(rs[mask]).max() <= 1e-9 * np.abs(M.diagonal()).max()
+        dA = P.dx * P.dy
+        assert M[pin, pin] == pytest.approx(1.0 / dA) and M[pin].nnz == 1
+
+
+def test_parabolic_matches_sparse_direct():
+    import scipy.sparse.linalg as spla
+    N = 24
+    base, P, c, q = production_case(N, N, diffusion=1)
+    S = O.new_state(); p = O.scalar_field(P); u = O.velocity_field(P); v = O.velocity_field(P)
+    lib.orc_fill_boundaries(C.byref(P), c)
+    lib.orc_solve_elliptic(C.byref(P), C.byref(S), c, q, p)
+    lib.orc_calc_velocities(C.byref(P), p, c, u, v)
+    dt = 0.5 * lib.orc_max_stable_dt(C.byref(P), u, v)
+    A = np.zeros(N * N * 9); b = np.zeros(N * N)
+    lib.orc_assemble_parabolic(C.byref(P), c, u, v, dt, A, b)
+    x_direct = spla.spsolve(to_csr(N, N, A).tocsc(), b)
+    cc = c.copy()
+    assert lib.orc_solve_parabolic(C.byref(P), C.byref(S), cc, u, v, dt) == 0
+    assert np.abs(interior(P, cc).ravel() - x_direct).max() <= 1e-11
+    # Crank-Nicolson with Neumann walls conserves mass
+    assert abs(interior(P, cc).sum() - interior(P, c).sum()) <= 1e-10 * interior(P, c).sum()
+
+
+def advect_norm(N, method):
+    base, P, c, u, v = advection_case(N, hyper_method=method)
+    S = O.new_state(); q = np.zeros(N * N)
+    dtmax = lib.orc_max_stable_dt(C.byref(P), u, v)
+    t = 0.0
+    while t < 1.0:                                      # src/Impec2DSolver.cpp:933-973
+        dt = dtmax
+        if t + dt >= 1.0: dt = 1.0 - t
+        lib.orc_transport_step(C.byref(P), C.byref(S), c, u, v, q, dt); t += dt
+    return P.dx, lib.orc_advection_norm(C.byref(P), c, O.SINE, 1)
+
+
+def test_hyperbolic_orders():
+    """hyperbolic_test.cfg: sine, L1, CFL 0.95, 50..200 cells (400 is covered by the GPU test)."""
+    r = np.array([advect_norm(50 * 2 ** k, O.MUSCL) for k in range(3)])
+    order = np.polyfit(np.log(r[:, 0]), np.log(r[:, 1]), 1)[0]
+    assert 1.80 < order < 1.92, order                   # published 1.85 (eps plot) / 1.876 (cfg comment)
+    r = np.array([advect_norm(50 * 2 ** k, O.UPWIND) for k in range(3)])
+    order = np.polyfit(np.log(r[:, 0]), np.log(r[:, 1]), 1)[0]
+    assert 0.95 < order < 1.08, order                   # published 1.00
+
+
+def test_noflow_and_divergence_invariants():
+    """Run-time invariants the reference logs every step (src/Impec2DSolver.cpp:530-588)."""
+    N = 64
+    base, P, c, q = production_case(N, N, eps=1e-13)
+    S = O.new_state(); p = O.scalar_field(P); u = O.velocity_field(P); v = O.velocity_field(P)
+    lib.orc_impes_step(C.byref(P), C.byref(S), p, c, u, v, q, 0.0, 0.0)
+    scale = np.abs(u).max()
+    assert lib.orc_boundary_velocity_error(C.byref(P), u, v) <= 1e-12 * scale * N
+    assert lib.orc_divergence_error(C.byref(P), u, v, q) <= 1e-8
+    assert abs(q.sum()) <= 1e-9 * np.abs(q).max()
+
+
+def test_wells_exact_area():
+    """InitQuarterCircle*: the injected volume equals I (x2 for the parallel layout): Util.cpp:497-559."""
+    for stype, mult in ((O.PARALLEL, 2.0), (O.DIAGONAL, 1.0)):
+        base, P, c, q = production_case(100, 100, stype=stype)
+        inj = q[q > 0].sum() * P.dx * P.dy
+        assert inj == pytest.approx(mult * 1.0, rel=1e-12)
+
+
+def test_ghost_fill_properties():
+    a = np.random.default_rng(0).random((10, 9))
+    b = a.copy(); lib.orc_fill_neumann_scalar(b, 6, 5, 2)
+    assert np.array_equal(b[1, 2:-2], b[2, 2:-2]) and np.array_equal(b[0, 2:-2], b[3, 2:-2])
+    assert b[0, 0] == b[3, 3] and b[-1, -1] == b[-4, -4]
+    b = a.copy(); lib.orc_fill_periodic_scalar(b, 6, 5, 2)
+    assert np.array_equal(b[0, 2:-2], b[6, 2:-2]) and np.array_equal(b[2:-2, -1], b[2:-2, 3])
