@@ -6,7 +6,7 @@ operator surface.  This Python package is the thin ctypes view of the same C ABI
 bench.py drive; it adds no numerics of its own.
 """
 from ._lib import Params, Diag, SolveInfo, load, library_path, EXPORTS  # noqa: F401
-from .api import Context, default_params, ImpecError  # noqa: F401
+from .api import Context, default_params, ImpecError, init_source, synth_state  # noqa: F401
 
 PARALLEL, DIAGONAL, HORIZONTAL = 0, 1, 2
 MEANCONC, HARMONIC = 0, 1

@@ -52,6 +52,7 @@ EXPORTS = [
     "impec_max_stable_dt", "impec_source_split", "impec_advect_x", "impec_advect_y", "impec_advect_split",
     "impec_diffusion_split", "impec_transport_step", "impec_impes_step", "impec_diagnostics", "impec_build_operator",
     "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_reset_state", "impec_set_option",
+    "impec_profile_kernel", "impec_init_source", "impec_synth_state",
 ]
 
 
@@ -99,5 +100,8 @@ def load(emulated=False):
     L.impec_mg_levels.argtypes = [vp]
     L.impec_kernel_launches.argtypes = [vp]; L.impec_kernel_launches.restype = C.c_longlong
     L.impec_set_option.argtypes = [vp, C.c_char_p, d]
+    L.impec_profile_kernel.argtypes = [vp, C.c_char_p, i, dptr]
+    L.impec_init_source.argtypes = [C.POINTER(Params), d, d, i, vp]
+    L.impec_synth_state.argtypes = [C.POINTER(Params), C.c_ulonglong, vp]
     _CACHE[key] = L
     return L

@@ -134,3 +134,26 @@ class Context:
     def reset_state(self): self._chk(self.L.impec_reset_state(self._h))
     def set_option(self, key, value): self._chk(self.L.impec_set_option(self._h, key.encode(), float(value)))
     def synchronize(self): self._chk(self.L.impec_synchronize(self._h))
+
+    def profile_kernel(self, name, reps=10):
+        ms = C.c_double()
+        self._chk(self.L.impec_profile_kernel(self._h, name.encode(), reps, C.byref(ms)))
+        return ms.value
+
+
+def init_source(params, I=1.0, well_rc=0.05, well_profile=0, emulated=False):
+    """Impec2DSolver::InitializeSource (host): returns q[N1*N2]."""
+    q = np.zeros(params.N1 * params.N2)
+    rc = _lib.load(emulated).impec_init_source(C.byref(params), I, well_rc, well_profile, _ptr(q))
+    if rc != 0:
+        raise ImpecError("impec_init_source failed (%d)" % rc)
+    return q
+
+
+def synth_state(params, seed=20260917, out=None, emulated=False):
+    """Developed synthetic concentration (ghosted array, interior written)."""
+    c = np.zeros((params.N1 + 2 * params.g, params.N2 + 2 * params.g)) if out is None else out
+    rc = _lib.load(emulated).impec_synth_state(C.byref(params), seed, _ptr(c))
+    if rc != 0:
+        raise ImpecError("impec_synth_state failed (%d)" % rc)
+    return c

@@ -1,0 +1,96 @@
+// host_util.inl -- host-side setup the hot path's callers need once per run (not kernels):
+// well/source initialisation (src/Impec2DSolver.cpp:241-280, src/Util.cpp:444-586) and the synthetic
+// developed concentration field used by bench.py and the tests.
+#include <thread>
+
+// exact area fraction of the cell [x1,x1+dx] x [y1,y1+dy] inside the circle of radius r about the origin
+// (src/Util.cpp:444-491)
+static double exact_vol_frac_circle(double x1, double y1, double r, double dx, double dy) {
+    if (!(x1 * x1 + y1 * y1 < r * r)) return 0;
+    const double y2 = y1 + dy, x2 = x1 + dx;
+    if (!(x2 * x2 + y2 * y2 > r * r)) return 1.;
+    const double xs = sqrt(r * r - y1 * y1), ys = sqrt(r * r - x1 * x1);
+    double area = 0, xub, xlb;
+    if (ys <= y2 && xs <= x2) { xlb = x1; xub = xs; }
+    else if (ys < y2 && xs > x2) { xlb = x1; xub = x2; }
+    else if (ys > y2 && xs < x2) { xlb = sqrt(r * r - y2 * y2); xub = xs; area += (xlb - x1) * dy; }
+    else { xlb = sqrt(r * r - y2 * y2); xub = x2; area += dy * (xlb - x1); }
+    const double t1 = asin(xlb / r), t2 = asin(xub / r);
+    area += r * r / 2 * (sin(2 * t2) / 2. + t2 - sin(2 * t1) / 2. - t1);
+    area -= y1 * (xub - xlb);
+    return area / (dx * dy);
+}
+
+template <class F> static void parallel_rows(int n, F f) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1; if (nt > 64) nt = 64; if ((int)nt > n) nt = (unsigned)n;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back([=]() { for (int i = (int)t; i < n; i += (int)nt) f(i); });
+    for (auto &x : th) x.join();
+}
+
+// InitializeSource: quarter-circle wells (diagonal: injector at (0,0), producer opposite; parallel: injectors
+// at (0,0) and (N1-1,N2-1), producers in the other two corners) or one-cell wells.
+extern "C" int impec_init_source(const impec_params *P, double I, double well_rc, int well_profile, double *q) {
+    if (!P || !q) return IMPEC_ERR_ARG;
+    if (P->stype == IMPEC_HORIZONTAL) return IMPEC_ERR_UNSUPPORTED;
+    const int N1 = P->N1, N2 = P->N2;
+    const double dx = (P->x_ub - P->x_lb) / N1, dy = (P->y_ub - P->y_lb) / N2;
+    const double r = well_rc * (P->x_ub - P->x_lb);
+    const double circval = I * 4. / (M_PI * r * r), qval = I / (dx * dy);
+    const size_t M = (size_t)N1 * N2;
+    if (well_profile == 2) {                                       // one_cell (src/Util.cpp:565-586)
+        for (size_t k = 0; k < M; k++) q[k] = 0.;
+        q[0] = qval;
+        if (P->stype == IMPEC_PARALLEL) { q[M - 1] = qval; q[N2 - 1] = -qval; q[(size_t)(N1 - 1) * N2] = -qval; }
+        else q[M - 1] = -qval;
+        return IMPEC_OK;
+    }
+    if (well_profile != 0) return IMPEC_ERR_UNSUPPORTED;           // "gauss" is a no-op upstream (:253-254)
+    auto qI = [&](int i, int j) { return circval * exact_vol_frac_circle(P->x_lb + i * dx, P->y_lb + j * dy, r, dx, dy); };
+    const bool par = P->stype == IMPEC_PARALLEL;
+    parallel_rows(N1, [&](int i) {
+        for (int j = 0; j < N2; j++) {
+            const double a = qI(i, j), b = qI(N1 - 1 - i, N2 - 1 - j);
+            q[(size_t)i * N2 + j] = par ? ((a + b) - qI(i, N2 - 1 - j)) - qI(N1 - 1 - i, j) : a - b;
+        }
+    });
+    return IMPEC_OK;
+}
+
+static inline unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+// Developed synthetic state: c = 1/2 [1 - tanh((r - r0(theta))/w)], r0 = L (0.45 + 0.08 sin 16 theta), w = 4 dx,
+// plus 1e-3 (U - 1/2) with U a counter-based splitmix64 stream (decomposition independent), clipped to [0,1];
+// the parallel layout adds the mirrored front of the second injector.  Writes the interior of a ghosted
+// (N1+2g) x (N2+2g) array.
+extern "C" int impec_synth_state(const impec_params *P, unsigned long long seed, double *c_ghosted) {
+    if (!P || !c_ghosted) return IMPEC_ERR_ARG;
+    const int N1 = P->N1, N2 = P->N2, g = P->g;
+    const double dx = (P->x_ub - P->x_lb) / N1, dy = (P->y_ub - P->y_lb) / N2, L = P->x_ub - P->x_lb, w = 4. * dx;
+    const int pitch = N2 + 2 * g;
+    parallel_rows(N1, [&](int i) {
+        for (int j = 0; j < N2; j++) {
+            const double x = (i + 0.5) * dx, y = (j + 0.5) * dy;
+            double r = sqrt(x * x + y * y), th = atan2(y, x);
+            double val = 0.5 * (1. - tanh((r - L * (0.45 + 0.08 * sin(16. * th))) / w));
+            if (P->stype == IMPEC_PARALLEL) {
+                const double x2 = L - x, y2 = (P->y_ub - P->y_lb) - y;
+                r = sqrt(x2 * x2 + y2 * y2); th = atan2(y2, x2);
+                const double v2 = 0.5 * (1. - tanh((r - L * (0.45 + 0.08 * sin(16. * th))) / w));
+                if (v2 > val) val = v2;
+            }
+            const unsigned long long h = splitmix64(seed ^ ((unsigned long long)i * (unsigned long long)N2 + (unsigned long long)j));
+            val += 1e-3 * ((double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5);
+            if (val < 0.) val = 0.;
+            if (val > 1.) val = 1.;
+            c_ghosted[(size_t)(i + g) * pitch + (j + g)] = val;
+        }
+    });
+    return IMPEC_OK;
+}

@@ -731,3 +731,57 @@ extern "C" int impec_diagnostics(impec_ctx *ctx, impec_diag *out) {
     out->total_mass_outflux = ctx->h_scal[S_OUTFLUX];
     return IMPEC_OK;
 }
+
+#include "host_util.inl"
+
+// ------------------------------------------------------------------------------------------------ profiling hook
+// Launches one named piece of the path `reps` times on the context stream between two events and returns the
+// average duration.  Used by bench.py for the per-kernel roofline numbers (never under a profiler).
+extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, double *avg_ms) {
+    if (!name || reps < 1 || !avg_ms) return fail(ctx, IMPEC_ERR_ARG, "bad arguments to impec_profile_kernel");
+    const std::string k(name);
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    if (!ctx->op_valid) TRY(impec_build_operator(ctx));
+    Cycle C; TRY(make_cycle(ctx, C, 0.0, 0));
+    const dim3 gr = grid2d(g.N2, g.N1);
+    Level &L0 = ctx->L[0];
+    auto body = [&]() -> int {
+        if (k == "smooth_sweep") return smooth(C, 0, ctx->r, ctx->z, true, false);
+        if (k == "smooth_sweep_zero") return smooth(C, 0, ctx->r, ctx->z, true, true);
+        if (k == "residual") { LAUNCH(ctx, k_residual, gr, kBlock, C.D[0], ctx->r, ctx->z, L0.r); return IMPEC_OK; }
+        if (k == "restrict") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L0.g, L0.r, Lc.g, Lc.f); return IMPEC_OK; }
+        if (k == "prolong_add") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_prolong_add, gr, kBlock, Lc.g, Lc.x, L0.g, ctx->z, L0.pin); return IMPEC_OK; }
+        if (k == "matvec_dot") { LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, C.D[0], ctx->d, ctx->s, ctx->part); return IMPEC_OK; }
+        if (k == "update_xr") { LAUNCH_COOP(ctx, k_update_xr, gr, kBlock, g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part); return IMPEC_OK; }
+        if (k == "dot") { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part); return IMPEC_OK; }
+        if (k == "update_d") { LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_TMP, ctx->z, ctx->d); return IMPEC_OK; }
+        if (k == "vcycle") return mg_cycle(C, 0, ctx->r, ctx->z);
+        if (k == "sweep_x") return sweep<0>(ctx, ctx->c, ctx->ta, nullptr, 0.0, 0, g.N1, -ng, g.N2 + ng);
+        if (k == "sweep_y") return sweep<1>(ctx, ctx->c, ctx->ta, nullptr, 0.0, -ng, g.N1 + ng, 0, g.N2);
+        if (k == "build_operator") return impec_build_operator(ctx);
+        if (k == "calc_velocities") return impec_calc_velocities(ctx);
+        return fail(ctx, IMPEC_ERR_ARG, "unknown kernel name '%s'", k.c_str());
+    };
+    if (k == "update_xr" || k == "update_d") {      // alpha = beta = 0/1 so the vectors stay finite
+        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_TMP, 0.0);
+        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_TMP + 1, 1.0);
+    }
+    if (k == "restrict" || k == "prolong_add") { if (ctx->L.size() < 2) return fail(ctx, IMPEC_ERR_ARG, "single-level hierarchy"); }
+    TRY(body());                                   // warm-up
+#ifndef IMPEC_EMU
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+    CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < reps; i++) TRY(body());
+    CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *avg_ms = (double)ms / reps;
+#else
+    for (int i = 0; i < reps; i++) TRY(body());
+    *avg_ms = 0.0;
+#endif
+    return IMPEC_OK;
+}

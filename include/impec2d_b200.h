@@ -138,6 +138,15 @@ int   impec_mg_levels(const impec_ctx *ctx);
 long long impec_kernel_launches(const impec_ctx *ctx);                   /* kernels launched by this context so far */
 int   impec_reset_state(impec_ctx *ctx);                                 /* produced mass := 0, sweep parity := Y */
 int   impec_set_option(impec_ctx *ctx, const char *key, double value);   /* e.g. "warm_start" */
+/* average device time of one named piece of the path ("smooth_sweep", "residual", "vcycle", "sweep_x", ...) over
+ * `reps` launches, measured with CUDA events on the context stream */
+int   impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, double *avg_ms);
+
+/* host-side setup helpers (no device work) */
+/* Impec2DSolver::InitializeSource  src/Impec2DSolver.cpp:241-280, src/Util.cpp:444-586; well_profile 0 circle, 2 one_cell */
+int   impec_init_source(const impec_params *p, double I, double well_rc, int well_profile, double *q);
+/* developed synthetic concentration for benchmarks; writes the interior of a ghosted array */
+int   impec_synth_state(const impec_params *p, unsigned long long seed, double *c_ghosted);
 
 #ifdef __cplusplus
 }
