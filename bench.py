@@ -205,7 +205,7 @@ def main():
 
     # ------------------------------------------------------------------ per-kernel device times (CUDA events, live)
     prof = {}
-    for name, reps in () if args.profile_mode else (("vcycle", 5), ("smooth_sweep", 10), ("residual", 10), ("restrict", 10), ("prolong_add", 10), ("matvec_dot", 10),
+    for name, reps in () if args.profile_mode else (("vcycle", 5), ("fused_pre", 10), ("fused_post", 10), ("fused_plain", 10), ("smooth_sweep", 10), ("residual", 10), ("restrict", 10), ("prolong_add", 10), ("matvec_dot", 10),
                        ("update_xr", 10), ("dot", 10), ("update_d", 10), ("sweep_x", 10), ("sweep_y", 10), ("build_operator", 5), ("calc_velocities", 5)):
         prof[name] = ctx.profile_kernel(name, reps)
     if args.profile_mode:
@@ -219,17 +219,24 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    # dominant kernel: one red-black smoothing sweep of the fine level (2 colour passes); algorithmic bytes
-    # = R p,f,AW,AS,AV + W p = 48 B/cell
-    smooth_bytes = 48.0 * N * N
-    achieved = smooth_bytes / (prof["smooth_sweep"] * 1e-3) / 1e9
-    vc_bytes = 208.0 * N * N
-    roofline = {"bound": "hbm", "kernel": "k_smooth_color x2 (one red-black sweep, fine level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": smooth_bytes,
+    # Algorithmic bytes per fine-level launch (FP64, each distinct array once; DESIGN.md "kernels"):
+    #   k_mg_fused<POST>  : R x,f,AW,AS,AV (40) + coarse e (2) + W x (8)            = 50 B/cell
+    #   k_mg_fused<PRE>   : R f,AW,AS,AV (32) + W x (8) + coarse f (2)              = 42 B/cell
+    #   k_mg_fused<PLAIN> : R x,f,AW,AS,AV (40) + W x (8)                           = 48 B/cell
+    #   one multigrid cycle, all levels                        = 208 B/cell
+    cells = float(N) * N
+    kb = {"fused_post": 50.0, "fused_pre": 42.0, "fused_plain": 48.0, "matvec_dot": 40.0, "update_xr": 48.0, "update_d": 24.0,
+          "sweep_x": 24.0, "sweep_y": 24.0, "residual": 48.0, "smooth_sweep": 48.0}
+    per_kernel = {k: {"ms": prof[k], "algorithmic_bytes": kb[k] * cells, "achieved_gbs": kb[k] * cells / (prof[k] * 1e-3) / 1e9,
+                      "frac": kb[k] * cells / (prof[k] * 1e-3) / 1e9 / peak} for k in kb}
+    dom = "fused_post"
+    vc_bytes = 208.0 * cells
+    roofline = {"bound": "hbm", "kernel": "k_mg_fused<FUSED_POST> (prolong + correct + red-black post-smooth + <r,z>, fine level)",
+                "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": per_kernel[dom]["algorithmic_bytes"],
                 "vcycle": {"ms": prof["vcycle"], "algorithmic_bytes": vc_bytes, "achieved": vc_bytes / (prof["vcycle"] * 1e-3) / 1e9,
                            "frac": vc_bytes / (prof["vcycle"] * 1e-3) / 1e9 / peak},
-                "kernel_ms": prof}
+                "kernels": per_kernel, "kernel_ms": prof}
 
     # ------------------------------------------------------------------ end-to-end through the C ABI with host buffers
     e2e = None

@@ -4,6 +4,7 @@
 #include "common.h"
 #include "kernels_transport.inl"
 #include "kernels_pressure.inl"
+#include "kernels_fused.inl"
 #include "../../include/impec2d_b200.h"
 
 #include <string>
@@ -18,7 +19,7 @@
 // ------------------------------------------------------------------------------------------------
 struct Level {
     Grid g;
-    double *AW = nullptr, *AS = nullptr, *AV = nullptr;
+    double *AW = nullptr, *AS = nullptr, *AV = nullptr, *DINV = nullptr;
     double *x = nullptr, *f = nullptr, *t = nullptr, *r = nullptr;
     long long pin = -1, sig_idx = -1;
 };
@@ -47,6 +48,7 @@ struct impec_ctx {
     int prev_first_sweep = 1;                       // Y_SWEEP (src/HyperbolicSolver.cpp:84)
     bool mob_valid = false, op_valid = false;
     bool warm_start = false;
+    bool fused = true;                              // fused tile kernels (kernels_fused.inl) vs one kernel per colour pass
     long long launches = 0;
     std::string err;
     std::vector<void *> allocs;
@@ -83,6 +85,7 @@ static int check_launch(impec_ctx *ctx, const char *what) {
     return IMPEC_OK;
 }
 #define LAUNCH(ctx, kernel, grid, block, ...) do { IMPEC_LAUNCH(kernel, grid, block, 0, (ctx)->stream, __VA_ARGS__); TRY(check_launch(ctx, #kernel)); } while (0)
+#define LAUNCH_COOP_SMEM(ctx, kernel, grid, block, smem, ...) do { IMPEC_LAUNCH_COOP(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__); TRY(check_launch(ctx, #kernel)); } while (0)
 #define LAUNCH_COOP(ctx, kernel, grid, block, ...) do { IMPEC_LAUNCH_COOP(kernel, grid, block, 0, (ctx)->stream, __VA_ARGS__); TRY(check_launch(ctx, #kernel)); } while (0)
 
 // ------------------------------------------------------------------------------------------------ misc kernels
@@ -212,6 +215,11 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     CUDA_TRY(ctx, cudaSetDevice(device));
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+#ifndef IMPEC_EMU
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
+#endif
     fill_dev_params(ctx);
     ctx->g = make_grid(P->N1, P->N2);
     const size_t n = grid_elems(ctx->g);
@@ -228,7 +236,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
         Level &L = ctx->L[l];
         L.g = (l == 0) ? ctx->g : make_grid(ctx->L[l - 1].g.N1 / 2, ctx->L[l - 1].g.N2 / 2);
         const size_t nn = grid_elems(L.g);
-        TRY(dev_alloc(ctx, &L.AW, nn)); TRY(dev_alloc(ctx, &L.AS, nn)); TRY(dev_alloc(ctx, &L.AV, nn));
+        TRY(dev_alloc(ctx, &L.AW, nn)); TRY(dev_alloc(ctx, &L.AS, nn)); TRY(dev_alloc(ctx, &L.AV, nn)); TRY(dev_alloc(ctx, &L.DINV, nn));
         if (l == 0) { L.x = ctx->z; L.f = ctx->r; L.t = ctx->t0; L.r = ctx->s; }
         else { TRY(dev_alloc(ctx, &L.x, nn)); TRY(dev_alloc(ctx, &L.f, nn)); TRY(dev_alloc(ctx, &L.t, nn)); TRY(dev_alloc(ctx, &L.r, nn)); }
     }
@@ -260,6 +268,7 @@ extern "C" int impec_reset_state(impec_ctx *ctx) {
 extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     const std::string k(key ? key : "");
     if (k == "warm_start") { ctx->warm_start = value != 0.0; return IMPEC_OK; }
+    if (k == "mg_fused") { ctx->fused = value != 0.0; return IMPEC_OK; }
     if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; return IMPEC_OK; }
     if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; return IMPEC_OK; }
     if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; return IMPEC_OK; }
@@ -365,7 +374,7 @@ extern "C" int impec_fill_boundaries(impec_ctx *ctx) { return fill_scalar(ctx, c
 static LevelDev level_dev(const impec_ctx *ctx, int l, double mass) {
     const Level &L = ctx->L[l];
     LevelDev D;
-    D.g = L.g; D.AW = L.AW; D.AS = L.AS; D.AV = L.AV; D.mass = mass;
+    D.g = L.g; D.AW = L.AW; D.AS = L.AS; D.AV = L.AV; D.DINV = L.DINV; D.mass = mass;
     D.pin = L.pin; D.sig_idx = L.sig_idx; D.sig_val = 0.;
     return D;
 }
@@ -392,6 +401,10 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
         LAUNCH(ctx, k_coarsen_links, grid2d(C.g.N2 + 1, C.g.N1 + 1), kBlock, F.g, F.AW, F.AS, F.AV, C.g, C.AW, C.AS, C.AV);
     }
     LAUNCH(ctx, k_pin_sigma, dim3(1), dim3(1), g, L0.AW, L0.AS, L0.AV, 1, 1, (int)ctx->L.size(), ctx->sigma_dev);
+    for (size_t l = 0; l < ctx->L.size(); l++) {
+        Level &L = ctx->L[l];
+        LAUNCH(ctx, k_diag_inv, grid2d(L.g.N2, L.g.N1), kBlock, level_dev(ctx, (int)l, 0.0), (const double *)(ctx->sigma_dev + l), L.DINV);
+    }
     ctx->op_valid = true;
     return IMPEC_OK;
 }
@@ -422,20 +435,73 @@ static int smooth(Cycle &C, int l, const double *f, double *x, bool forward, boo
     return IMPEC_OK;
 }
 
-static int mg_cycle(Cycle &C, int l, const double *f, double *x) {
+// ---- fused path (kernels_fused.inl)
+static const dim3 kFusedBlock(FT_W / 2, FT_NTY);
+static const int kFusedSmem = FT_W * FT_H * (int)sizeof(double);
+template <int MODE> static dim3 fused_grid(const Grid &g) {
+    return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + FusedGeom<MODE>::TI - 1) / FusedGeom<MODE>::TI));
+}
+// PLAIN and POST read the iterate with a halo that belongs to neighbouring tiles, so they cannot run in place:
+// they read L.x, write L.t and the two pointers are swapped (the level's current iterate is always L.x).
+static int fused_plain(Cycle &C, int l, const double *f, bool forward) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
+    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_PLAIN>, fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
+                     (const double *)nullptr, (double *)nullptr, (double *)nullptr);
+    std::swap(L.x, L.t);
+    return IMPEC_OK;
+}
+static int fused_pre(Cycle &C, int l, const double *f) {
+    impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
+    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_PRE>, fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, Lc.g,
+                     (const double *)nullptr, Lc.f, (double *)nullptr);
+    return IMPEC_OK;
+}
+static int fused_post(Cycle &C, int l, const double *f, double *part, long long *nparts) {
+    impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
+    const dim3 gr = fused_grid<FUSED_POST>(L.g);
+    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_POST>, gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, Lc.g, (const double *)Lc.x, (double *)nullptr, part);
+    std::swap(L.x, L.t);
+    if (nparts) *nparts = (long long)gr.x * gr.y;
+    return IMPEC_OK;
+}
+
+// One multigrid cycle for S x = f from a zero initial guess; the result is left in ctx->L[l].x (the fused path
+// ping-pongs between the level's two buffers).  dot_part/dot_nparts (level 0, fused path): the last kernel also
+// leaves the partial sums of <f,x> in dot_part.
+static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr, long long *dot_nparts = nullptr) {
+    impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
+    double *x = L.x;
     const int nl = (int)ctx->L.size();
+    const bool fused = ctx->fused;
+    if (dot_nparts) *dot_nparts = 0;
     if (l == nl - 1) {
-        for (int s = 0; s < C.ncoarse; s++) { TRY(smooth(C, l, f, x, true, s == 0)); TRY(smooth(C, l, f, x, false, false)); }
+        if (fused) {
+            CUDA_TRY(ctx, cudaMemsetAsync(L.x, 0, grid_elems(L.g) * sizeof(double), ctx->stream));
+            for (int s = 0; s < C.ncoarse; s++) { TRY(fused_plain(C, l, f, true)); TRY(fused_plain(C, l, f, false)); }
+        } else
+            for (int s = 0; s < C.ncoarse; s++) { TRY(smooth(C, l, f, x, true, s == 0)); TRY(smooth(C, l, f, x, false, false)); }
         return IMPEC_OK;
     }
     Level &Lc = ctx->L[l + 1];
     const int gamma = (l >= C.w_from && l <= C.w_to) ? 2 : 1;
+    if (fused) {
+        TRY(fused_pre(C, l, f));                                      // pre-smooth(0) + residual + restrict
+        TRY(mg_cycle(C, l + 1, Lc.f));
+        for (int gc = 1; gc < gamma; gc++) {
+            TRY(fused_post(C, l, f, nullptr, nullptr));               // prolong + correct + backward sweep
+            TRY(fused_plain(C, l, f, true));
+            LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1), kBlock, C.D[l], f, (const double *)L.x, L.r);
+            LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L.g, L.r, Lc.g, Lc.f);
+            TRY(mg_cycle(C, l + 1, Lc.f));
+        }
+        TRY(fused_post(C, l, f, dot_part, dot_nparts));               // prolong + correct + post-smooth (+ <f,x>)
+        return IMPEC_OK;
+    }
     TRY(smooth(C, l, f, x, true, true));
     for (int gc = 0; gc < gamma; gc++) {
         LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1), kBlock, C.D[l], f, x, L.r);
         LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L.g, L.r, Lc.g, Lc.f);
-        TRY(mg_cycle(C, l + 1, Lc.f, Lc.x));
+        TRY(mg_cycle(C, l + 1, Lc.f));
         LAUNCH(ctx, k_prolong_add, grid2d(L.g.N2, L.g.N1), kBlock, Lc.g, Lc.x, L.g, x, L.pin);
         if (gc < gamma - 1) { TRY(smooth(C, l, f, x, false, false)); TRY(smooth(C, l, f, x, true, false)); }
     }
@@ -464,9 +530,9 @@ extern "C" int impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host
         CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->r + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), r_host, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->r + ctx->L[0].pin, 0.0);
     }
-    TRY(mg_cycle(C, 0, ctx->r, ctx->z));
+    TRY(mg_cycle(C, 0, ctx->r));
     if (z_host) {
-        CUDA_TRY(ctx, cudaMemcpy2DAsync(z_host, w, ctx->z + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), w, (size_t)g.N1, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(z_host, w, ctx->L[0].x + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), w, (size_t)g.N1, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return IMPEC_OK;
@@ -526,11 +592,12 @@ extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info
     if (!(bi_prod > 0.)) converged = 1;                          // b = 0  =>  x = 0 (HYPRE returns immediately)
     else if (i_prod / bi_prod < eps * eps) converged = 1;
     int ig = S_GAMMA0;                                           // which scalar slot holds the current gamma
+    long long dparts = 0;
     if (!converged) {
-        TRY(mg_cycle(C, 0, ctx->r, ctx->z));
-        LAUNCH(ctx, k_update_d<true>, gr, kBlock, g, ctx->scal, ctx->z, ctx->d);
-        LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part);
-        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, ig));
+        TRY(mg_cycle(C, 0, ctx->r, ctx->part, &dparts));
+        LAUNCH(ctx, k_update_d<true>, gr, kBlock, g, ctx->scal, (const double *)ctx->L[0].x, ctx->d);
+        if (!dparts) { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->L[0].x, ctx->part); dparts = nparts; }
+        TRY(reduce_final(ctx, RED_SUM, dparts, 1, 0, ig));
     }
     while (!converged && it < ctx->P.max_iter) {
         it++;
@@ -544,12 +611,12 @@ extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info
         i_prod = ctx->h_scal[S_IPROD];
         if (i_prod / bi_prod < eps * eps) { converged = 1; break; }
         if (!(i_prod == i_prod)) return fail(ctx, IMPEC_ERR_NOCONV, "PCG produced NaN at iteration %d", it);
-        TRY(mg_cycle(C, 0, ctx->r, ctx->z));
-        LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part);
-        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BETA_NUM));
+        TRY(mg_cycle(C, 0, ctx->r, ctx->part, &dparts));
+        if (!dparts) { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->L[0].x, ctx->part); dparts = nparts; }
+        TRY(reduce_final(ctx, RED_SUM, dparts, 1, 0, S_BETA_NUM));
         // beta = gamma_new / gamma_old ; d = z + beta d      (k_update_d reads scal'[0]/scal'[1])
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal + S_BETA_DEN, ctx->scal + S_GAMMA0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_BETA_NUM, ctx->z, ctx->d);
+        LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_BETA_NUM, (const double *)ctx->L[0].x, ctx->d);
         ig = S_BETA_NUM;
     }
     // true residual with the final x
@@ -746,16 +813,19 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
     const dim3 gr = grid2d(g.N2, g.N1);
     Level &L0 = ctx->L[0];
     auto body = [&]() -> int {
-        if (k == "smooth_sweep") return smooth(C, 0, ctx->r, ctx->z, true, false);
-        if (k == "smooth_sweep_zero") return smooth(C, 0, ctx->r, ctx->z, true, true);
-        if (k == "residual") { LAUNCH(ctx, k_residual, gr, kBlock, C.D[0], ctx->r, ctx->z, L0.r); return IMPEC_OK; }
+        if (k == "fused_plain") return fused_plain(C, 0, ctx->r, true);
+        if (k == "fused_pre") return fused_pre(C, 0, ctx->r);
+        if (k == "fused_post") return fused_post(C, 0, ctx->r, ctx->part, nullptr);
+        if (k == "smooth_sweep") return smooth(C, 0, ctx->r, L0.x, true, false);
+        if (k == "smooth_sweep_zero") return smooth(C, 0, ctx->r, L0.x, true, true);
+        if (k == "residual") { LAUNCH(ctx, k_residual, gr, kBlock, C.D[0], ctx->r, (const double *)L0.x, L0.r); return IMPEC_OK; }
         if (k == "restrict") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L0.g, L0.r, Lc.g, Lc.f); return IMPEC_OK; }
-        if (k == "prolong_add") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_prolong_add, gr, kBlock, Lc.g, Lc.x, L0.g, ctx->z, L0.pin); return IMPEC_OK; }
+        if (k == "prolong_add") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_prolong_add, gr, kBlock, Lc.g, Lc.x, L0.g, L0.x, L0.pin); return IMPEC_OK; }
         if (k == "matvec_dot") { LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, C.D[0], ctx->d, ctx->s, ctx->part); return IMPEC_OK; }
         if (k == "update_xr") { LAUNCH_COOP(ctx, k_update_xr, gr, kBlock, g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part); return IMPEC_OK; }
         if (k == "dot") { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part); return IMPEC_OK; }
         if (k == "update_d") { LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_TMP, ctx->z, ctx->d); return IMPEC_OK; }
-        if (k == "vcycle") return mg_cycle(C, 0, ctx->r, ctx->z);
+        if (k == "vcycle") return mg_cycle(C, 0, ctx->r);
         if (k == "sweep_x") return sweep<0>(ctx, ctx->c, ctx->ta, nullptr, 0.0, 0, g.N1, -ng, g.N2 + ng);
         if (k == "sweep_y") return sweep<1>(ctx, ctx->c, ctx->ta, nullptr, 0.0, -ng, g.N1 + ng, 0, g.N2);
         if (k == "build_operator") return impec_build_operator(ctx);

@@ -1,0 +1,245 @@
+// kernels_fused.inl -- fused multigrid tile kernels (the hot kernels of the pressure solve).
+//
+// One CTA stages a 64 x 128 tile of the iterate (halo included) in shared memory and performs BOTH colour
+// passes of the red-black sweep on it, so a sweep costs one read and one write of x instead of two each.
+// Halo cells are recomputed redundantly (identical arithmetic, so tiles agree bit for bit).
+//
+//   FUSED_PLAIN : x <- sweep(x)                                   (coarsest level, W-cycle mid sweeps)
+//   FUSED_PRE   : x <- sweep(0); r = f - S x; fc = R r            (pre-smooth from a zero guess + residual +
+//                                                                  full-weighting restriction; x is never read)
+//   FUSED_POST  : x <- x + P ec; x <- sweep(x); part += <f,x>     (prolongation + correction + post-smooth,
+//                                                                  with the PCG dot product <r,z> on level 0)
+//
+// Thread (tx,ty) owns the cell pair (columns 2tx, 2tx+1) of rows ty, ty+8, ...: one cell of the pair is red
+// and one black, so both colour stages keep every lane busy and global accesses are 128-bit.
+// Shared memory holds x only, split into an even-column and an odd-column plane so that every access of a
+// colour stage is unit-stride across the warp (no bank conflicts).  Link coefficients and the stored inverse
+// diagonal are read through L1.  Tiles that touch the domain boundary (or hold the pinned cell) take the EDGE
+// instantiation with full bounds checks; all others run the check-free body.
+#define FT_W 128                 // tile width in cells, halo included
+#define FT_H 64                  // tile height in cells, halo included
+#define FT_HJ 4                  // halo in j (keeps 32-byte alignment of the tile's first column)
+#define FT_NTY 8                 // thread rows per CTA
+#define FT_ROWS (FT_H / FT_NTY)  // rows per thread
+#define FT_TJ (FT_W - 2 * FT_HJ) // interior columns per tile (120)
+enum { FUSED_PLAIN = 0, FUSED_PRE = 1, FUSED_POST = 2 };
+template <int MODE> struct FusedGeom { enum { HI = (MODE == FUSED_PRE) ? 3 : 2, TI = FT_H - 2 * HI }; };
+
+struct d2 { double x, y; };
+IMPEC_D d2 ld2(const double *p) {
+#ifndef IMPEC_EMU
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    d2 r; r.x = v.x; r.y = v.y; return r;
+#else
+    d2 r; r.x = p[0]; r.y = p[1]; return r;
+#endif
+}
+IMPEC_D void st2(double *p, double a, double b) {
+#ifndef IMPEC_EMU
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
+// shared-memory index of tile cell (r, jj): row-major, even columns in the first half of the row
+IMPEC_D int xi(int r, int jj) { return r * FT_W + ((jj & 1) << 6) + (jj >> 1); }
+
+// sum_nb a_nb x_nb for the cell `off` of the pair owned by lane tx in tile row r (k = its global index)
+IMPEC_D double tile_offsum(const LevelDev &L, const double *__restrict__ X, int r, int tx, int off, size_t k) {
+    const int ld = L.g.ld;
+    const double *own = X + r * FT_W + (off << 6) + tx;                  // same column: rows r-1, r+1
+    const double *oth = X + r * FT_W + ((1 - off) << 6) + tx + off;      // other plane: [-1] is column jj-1, [0] is jj+1
+    double s = L.AW[k] * own[-FT_W];
+    s = fma(L.AW[k + ld], own[FT_W], s);
+    s = fma(L.AS[k], oth[-1], s);
+    s = fma(L.AS[k + 1], oth[0], s);
+    s = fma(L.AV[k], oth[-FT_W - 1], s);
+    s = fma(L.AV[k + ld], oth[FT_W - 1], s);
+    s = fma(L.AV[k + 1], oth[-FT_W], s);
+    s = fma(L.AV[k + ld + 1], oth[FT_W], s);
+    return s;
+}
+// the four diagonal terms only
+IMPEC_D double tile_diagsum(const LevelDev &L, const double *__restrict__ X, int r, int tx, int off, size_t k) {
+    const int ld = L.g.ld;
+    const double *oth = X + r * FT_W + ((1 - off) << 6) + tx + off;
+    double s = L.AV[k] * oth[-FT_W - 1];
+    s = fma(L.AV[k + ld], oth[FT_W - 1], s);
+    s = fma(L.AV[k + 1], oth[-FT_W], s);
+    s = fma(L.AV[k + ld + 1], oth[FT_W], s);
+    return s;
+}
+
+template <int MODE, bool EDGE>
+IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, const int c0,
+                        const Grid &gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part, double *__restrict__ X) {
+    constexpr int HI = FusedGeom<MODE>::HI, TI = FusedGeom<MODE>::TI;
+    const Grid g = L.g;
+    const int ld = g.ld;
+    const int tx = threadIdx.x, ty = threadIdx.y & (FT_NTY - 1);
+    const int jl = 2 * tx;                                   // local column of the pair
+    const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ;          // global column of tile column 0 (even)
+    const int i0 = (int)blockIdx.y * TI - HI;                // global row of tile row 0
+    const int jg = j0 + jl;
+    const int par = (i0 + ty + jg) & 1;                      // colour of the pair's first cell (same in all rows of this thread)
+    const long long kbase = (long long)(i0 + ty + IMPEC_GH) * ld + (jg + IMPEC_PJ);   // global index of the pair in row ty
+    const bool col_alloc = !EDGE || ((jg + IMPEC_PJ >= 0) && (jg + 1 + IMPEC_PJ < ld));
+
+    // ---- stage L: tile of x (zero for a zero initial guess), plus the prolongated correction
+#pragma unroll
+    for (int n = 0; n < FT_ROWS; n++) {
+        const int r = ty + n * FT_NTY, ig = i0 + r;
+        double a = 0., b = 0.;
+        const bool row_alloc = !EDGE || ((ig >= -IMPEC_GH) && (ig < g.rows - IMPEC_GH));
+        if (MODE != FUSED_PRE && row_alloc && col_alloc) {
+            const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
+            const d2 v = ld2(xin + k);
+            a = v.x; b = v.y;
+            if (MODE == FUSED_POST && (!EDGE || (ig >= 0 && ig < g.N1))) {
+                // x += P ec : cell-centred bilinear with edge replication.  Both cells of the pair share the coarse
+                // column J; the even cell interpolates towards J-1, the odd one towards J+1.
+                const int I = ig >> 1, J = jg >> 1;
+                int In = (ig & 1) ? I + 1 : I - 1, Jm = J - 1, Jp = J + 1;
+                if (EDGE) {
+                    In = In < 0 ? 0 : (In > gc.N1 - 1 ? gc.N1 - 1 : In);
+                    Jm = Jm < 0 ? 0 : Jm; Jp = Jp > gc.N2 - 1 ? gc.N2 - 1 : Jp;
+                }
+                const double *e0 = ec + gidx(gc, I, 0), *e1 = ec + gidx(gc, In, 0);
+                const double pc = 0.75 * e0[J] + 0.25 * e1[J];
+                const double pm = 0.75 * e0[Jm] + 0.25 * e1[Jm];
+                const double pp = 0.75 * e0[Jp] + 0.25 * e1[Jp];
+                if (!EDGE) { a += 0.75 * pc + 0.25 * pm; b += 0.75 * pc + 0.25 * pp; }
+                else {
+                    if (jg >= 0 && jg < g.N2 && (long long)k != L.pin) a += 0.75 * pc + 0.25 * pm;
+                    if (jg + 1 >= 0 && jg + 1 < g.N2 && (long long)(k + 1) != L.pin) b += 0.75 * pc + 0.25 * pp;
+                }
+            }
+        }
+        X[r * FT_W + tx] = a; X[r * FT_W + 64 + tx] = b;
+    }
+    IMPEC_SYNCTHREADS();
+    // (xin and x are different buffers for PLAIN / POST: the halo of this tile is the interior of its
+    //  neighbours, which other CTAs overwrite concurrently.)
+
+    // ---- two colour stages.  Stage s updates colour (s == 0 ? c0 : 1 - c0) on the tile shrunk by s+1 cells
+    //      (by s cells in PRE mode, whose first stage is the neighbour-free zero-guess update x = f/diag).
+    //      The pinned cell has dinv = 0 and x = 0, so it needs no special case here.
+    double nv[FT_ROWS];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int col = s == 0 ? c0 : 1 - c0;
+        const int shrink = (MODE == FUSED_PRE) ? s : s + 1;
+        const int off = (par == col) ? 0 : 1;                            // which cell of the pair has this colour
+        const int jj = jl + off, j = jg + off;
+        const bool colok = jj >= shrink && jj < FT_W - shrink && (!EDGE || (j >= 0 && j < g.N2));
+#pragma unroll
+        for (int n = 0; n < FT_ROWS; n++) {
+            const int r = ty + n * FT_NTY, ig = i0 + r;
+            double val = X[r * FT_W + (off << 6) + tx];
+            const bool act = colok && r >= shrink && r < FT_H - shrink && (!EDGE || (ig >= 0 && ig < g.N1));
+            if (act) {
+                const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld + off);
+                if (MODE == FUSED_PRE && s == 0) val = f[k] * L.DINV[k];
+                else val = (f[k] + tile_offsum(L, X, r, tx, off, k)) * L.DINV[k];
+            }
+            nv[n] = val;
+        }
+        if (!(MODE == FUSED_PRE && s == 0)) IMPEC_SYNCTHREADS();        // every read of the old colour is done
+#pragma unroll
+        for (int n = 0; n < FT_ROWS; n++) X[(ty + n * FT_NTY) * FT_W + (off << 6) + tx] = nv[n];
+        IMPEC_SYNCTHREADS();
+    }
+
+    // ---- write the interior of the tile back (128-bit stores), and the fused dot product
+    const bool col_int = jl >= FT_HJ && jl < FT_W - FT_HJ && (!EDGE || jg < g.N2);
+    double dotv = 0.;
+#pragma unroll
+    for (int n = 0; n < FT_ROWS; n++) {
+        const int r = ty + n * FT_NTY, ig = i0 + r;
+        if (r < HI || r >= FT_H - HI || !col_int || (EDGE && ig >= g.N1)) continue;
+        const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
+        const double a = X[r * FT_W + tx], b = X[r * FT_W + 64 + tx];
+        if (!EDGE || jg + 1 < g.N2) st2(x + k, a, b); else x[k] = a;
+        if (MODE == FUSED_POST && part) {
+            if (!EDGE || jg + 1 < g.N2) { const d2 fv = ld2(f + k); dotv = fma(fv.x, a, dotv); dotv = fma(fv.y, b, dotv); }
+            else dotv = fma(f[k], a, dotv);
+        }
+    }
+    if (MODE == FUSED_POST && part) {
+        dotv = block_reduce<RED_SUM>(dotv);
+        if (tx == 0 && ty == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
+    }
+    if (MODE != FUSED_PRE) return;
+
+    // ---- PRE: residual on the tile shrunk by 2, then full-weighting restriction.
+    // After a sweep from a ZERO guess the residual needs no diagonal: a first-colour cell was solved when all
+    // its neighbours were still zero, so r = sum over all 8 neighbours of a_nb x_nb; a second-colour cell was
+    // solved against the final first-colour values, so only its (same-colour) diagonal neighbours contribute.
+    // (The dropped terms f - d x + s_at_update are rounding noise, O(eps |f|).)
+    double ra[FT_ROWS], rb[FT_ROWS];
+    {
+        const int off0 = (par == c0) ? 0 : 1;                            // first-colour cell of the pair
+#pragma unroll
+        for (int n = 0; n < FT_ROWS; n++) {
+            const int r = ty + n * FT_NTY, ig = i0 + r;
+            double v0 = 0., v1 = 0.;                                     // residual of the first / second colour cell
+            if (r >= 2 && r < FT_H - 2 && (!EDGE || (ig >= 0 && ig < g.N1))) {
+                const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
+                const int ja = jl + off0, jb = jl + 1 - off0;
+                if (ja >= 2 && ja < FT_W - 2 && (!EDGE || (jg + off0 >= 0 && jg + off0 < g.N2 && (long long)(k + off0) != L.pin)))
+                    v0 = tile_offsum(L, X, r, tx, off0, k + off0);
+                if (jb >= 2 && jb < FT_W - 2 && (!EDGE || (jg + 1 - off0 >= 0 && jg + 1 - off0 < g.N2 && (long long)(k + 1 - off0) != L.pin)))
+                    v1 = tile_diagsum(L, X, r, tx, 1 - off0, k + 1 - off0);
+            }
+            ra[n] = off0 == 0 ? v0 : v1;                                 // even-column cell
+            rb[n] = off0 == 0 ? v1 : v0;                                 // odd-column cell
+        }
+    }
+    IMPEC_SYNCTHREADS();
+#pragma unroll
+    for (int n = 0; n < FT_ROWS; n++) {
+        const int r = ty + n * FT_NTY;
+        X[r * FT_W + tx] = ra[n]; X[r * FT_W + 64 + tx] = rb[n];
+    }
+    IMPEC_SYNCTHREADS();
+    // coarse cells of this tile: fine interior rows [i0+HI, i0+HI+TI) -> TI/2 coarse rows, FT_TJ/2 coarse columns
+    const int I0 = (i0 + HI) >> 1, J0 = (j0 + FT_HJ) >> 1;
+    const int tid = ty * (FT_W / 2) + tx, nthreads = (FT_W / 2) * FT_NTY;
+    for (int t = tid; t < (TI / 2) * (FT_TJ / 2); t += nthreads) {
+        const int I = I0 + t / (FT_TJ / 2), J = J0 + t % (FT_TJ / 2);
+        if (EDGE && (I >= gc.N1 || J >= gc.N2)) continue;
+        double t4[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            int i = 2 * I - 1 + a;
+            if (EDGE) i = i < 0 ? 0 : (i > g.N1 - 1 ? g.N1 - 1 : i);
+            int jm = 2 * J - 1, jp = 2 * J + 2;
+            if (EDGE) { jm = jm < 0 ? 0 : jm; jp = jp > g.N2 - 1 ? g.N2 - 1 : jp; }
+            const int rr = i - i0;
+            // 0.25 r(2J-1) + 0.75 r(2J) + 0.75 r(2J+1) + 0.25 r(2J+2)
+            double s = 0.25 * X[xi(rr, jm - j0)];
+            s += 0.75 * X[xi(rr, 2 * J - j0)];
+            s += 0.75 * X[xi(rr, 2 * J + 1 - j0)];
+            s += 0.25 * X[xi(rr, jp - j0)];
+            t4[a] = s;
+        }
+        fc[gidx(gc, I, J)] = 0.25 * (0.25 * t4[0] + 0.75 * t4[1] + 0.75 * t4[2] + 0.25 * t4[3]);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_fused(LevelDev L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, int c0,
+                                                               Grid gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part) {
+    IMPEC_DYN_SMEM(double, X);
+    constexpr int HI = FusedGeom<MODE>::HI, TI = FusedGeom<MODE>::TI;
+    const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ, i0 = (int)blockIdx.y * TI - HI;
+    // tile (halo included, plus the one-cell reach of the link arrays) strictly inside the domain and free of the pin?
+    bool edge = i0 < 0 || j0 < 0 || i0 + FT_H >= L.g.N1 || j0 + FT_W >= L.g.N2;
+    if (L.pin >= 0) {
+        const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
+        edge = edge || (pi >= i0 && pi < i0 + FT_H && pj >= j0 && pj < j0 + FT_W);
+    }
+    if (edge) fused_body<MODE, true>(L, f, xin, x, c0, gc, ec, fc, part, X);
+    else fused_body<MODE, false>(L, f, xin, x, c0, gc, ec, fc, part, X);
+}

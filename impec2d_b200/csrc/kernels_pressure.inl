@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256) k_links(Grid g, const double *__restrict_
 struct LevelDev {
     Grid g;
     const double *AW, *AS, *AV;
+    const double *DINV;          // 1/diag (0 at the pinned cell), built once per operator by k_diag_inv
     double mass;                 // 0 elliptic, 1 Crank-Nicolson
     long long pin;               // fine level: padded index of the Dirichlet cell (or -1)
     long long sig_idx;           // coarse levels: padded index of the cell carrying the pin's diagonal shift
@@ -151,13 +152,13 @@ IMPEC_D double link_diag(const LevelDev &L, size_t k) {
 IMPEC_D double link_offsum(const LevelDev &L, const double *__restrict__ x, size_t k) {
     const int ld = L.g.ld;
     double s = L.AW[k] * x[k - ld];
-    s += L.AW[k + ld] * x[k + ld];
-    s += L.AS[k] * x[k - 1];
-    s += L.AS[k + 1] * x[k + 1];
-    s += L.AV[k] * x[k - ld - 1];
-    s += L.AV[k + ld] * x[k + ld - 1];
-    s += L.AV[k + 1] * x[k - ld + 1];
-    s += L.AV[k + ld + 1] * x[k + ld + 1];
+    s = fma(L.AW[k + ld], x[k + ld], s);
+    s = fma(L.AS[k], x[k - 1], s);
+    s = fma(L.AS[k + 1], x[k + 1], s);
+    s = fma(L.AV[k], x[k - ld - 1], s);
+    s = fma(L.AV[k + ld], x[k + ld - 1], s);
+    s = fma(L.AV[k + 1], x[k - ld + 1], s);
+    s = fma(L.AV[k + ld + 1], x[k + ld + 1], s);
     return s;
 }
 
@@ -171,8 +172,20 @@ __global__ void __launch_bounds__(256) k_smooth_color(LevelDev L, int color, con
     if (i >= L.g.N1 || j >= L.g.N2) return;
     const size_t k = gidx(L.g, i, j);
     if (((i + j) & 1) != color || (long long)k == L.pin) { xout[k] = ZERO ? 0. : xin[k]; return; }
-    const double d = link_diag(L, k);
-    xout[k] = ZERO ? f[k] / d : (f[k] + link_offsum(L, xin, k)) / d;
+    xout[k] = ZERO ? f[k] * L.DINV[k] : (f[k] + link_offsum(L, xin, k)) * L.DINV[k];
+}
+
+// DINV = 1/diag on the interior (0 at the pinned cell); sigma (the pin's diagonal shift on coarse levels) is read
+// from device memory so that no host round trip is needed between k_pin_sigma and this kernel.
+__global__ void __launch_bounds__(256) k_diag_inv(LevelDev L, const double *__restrict__ sigma, double *__restrict__ DINV) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= L.g.N1 || j >= L.g.N2) return;
+    const size_t k = gidx(L.g, i, j);
+    const int ld = L.g.ld;
+    double d = L.mass + (((L.AW[k] + L.AW[k + ld]) + (L.AS[k] + L.AS[k + 1])) + ((L.AV[k] + L.AV[k + ld]) + (L.AV[k + 1] + L.AV[k + ld + 1])));
+    if ((long long)k == L.sig_idx && sigma) d += sigma[0];
+    DINV[k] = ((long long)k == L.pin) ? 0. : 1. / d;
 }
 
 // r = f - S x  (0 at the pinned cell); optionally accumulates <r,r> partials
