@@ -423,6 +423,7 @@ struct Cycle {
     impec_ctx *ctx;
     std::vector<LevelDev> D;
     int ncoarse, w_from, w_to;
+    int nl;                       // levels used (1 = symmetric Gauss-Seidel preconditioner only)
 };
 
 static int smooth(Cycle &C, int l, const double *f, double *x, bool forward, bool zero) {
@@ -471,7 +472,7 @@ static int fused_post(Cycle &C, int l, const double *f, double *part, long long 
 static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr, long long *dot_nparts = nullptr) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
     double *x = L.x;
-    const int nl = (int)ctx->L.size();
+    const int nl = C.nl;
     const bool fused = ctx->fused;
     if (dot_nparts) *dot_nparts = 0;
     if (l == nl - 1) {
@@ -517,7 +518,7 @@ static int make_cycle(impec_ctx *ctx, Cycle &C, double mass, int nlevels_used) {
     for (size_t l = 0; l < ctx->L.size(); l++) { LevelDev D = level_dev(ctx, (int)l, mass); D.sig_val = sig[l]; if (mass != 0.) { D.pin = -1; D.sig_idx = -1; } C.D.push_back(D); }
     C.ncoarse = ctx->P.mg_ncoarse > 0 ? ctx->P.mg_ncoarse : 8;
     C.w_from = ctx->P.mg_w_from; C.w_to = ctx->P.mg_w_to;
-    (void)nlevels_used;
+    C.nl = nlevels_used > 0 ? nlevels_used : (int)ctx->L.size();
     return IMPEC_OK;
 }
 
@@ -555,34 +556,15 @@ static double q_test_host(const impec_params &P, double x, double y) {
     }
 }
 
-extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info *info) {
-    if (!ctx->have_q) return fail(ctx, IMPEC_ERR_ARG, "pressure solve before impec_upload_q");
+// PCG exactly as HYPRE's struct PCG is configured upstream (src/MGSolver.cpp:597-603: TwoNorm, RelChange off, zero
+// initial guess): stop when <r,r>/<b,b> < eps^2 with r the RECURRENCE residual.  On entry: rhs and x are set, the
+// partial sums of <b,b> are already reduced into scal[S_BIPROD].  The preconditioner is one multigrid cycle C.
+static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, double eps, impec_solve_info *info) {
     const Grid &g = ctx->g;
     const dim3 gr = grid2d(g.N2, g.N1);
     const long long nparts = (long long)gr.x * gr.y;
-    TRY(impec_build_operator(ctx));
-    Cycle C; TRY(make_cycle(ctx, C, 0.0, 0));
     const LevelDev &A = C.D[0];
-    // pinned value p(1,1) = b/(kappa/dA) = -q(1,1) dA / kappa       (src/MGSolver.cpp:517-567)
-    const double dA = ctx->D.dx * ctx->D.dy;
-    double kappa = 1.;
-    if (ctx->P.is_test) {
-        const double x = ctx->P.x_lb + 1.5 * ctx->D.dx, y = ctx->P.y_lb + 1.5 * ctx->D.dy;
-        kappa = -dA * q_test_host(ctx->P, x, y) / (cos(x) * cos(y));
-    }
-    const double p_pin = -ctx->q_pin / (kappa / dA);
-    double *x = ctx->p;
-    if (ctx->warm_start) {
-        // keep the previous pressure as initial guess (not the reference's behaviour: x0 = 0, MGSolver.cpp:577)
-        LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->p, ctx->d);
-        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
-        LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->d, x);
-        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), x + A.pin, p_pin);
-    } else {
-        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
-    }
-    TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
-    LAUNCH(ctx, k_residual, gr, kBlock, A, ctx->rhs, x, ctx->r);
+    LAUNCH(ctx, k_residual, gr, kBlock, A, rhs, (const double *)x, ctx->r);
     LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->r, ctx->part);
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_IPROD));
     TRY(fetch_scalars(ctx, S_IPROD, 3));                         // S_IPROD .. S_BIPROD
@@ -620,7 +602,7 @@ extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info
         ig = S_BETA_NUM;
     }
     // true residual with the final x
-    LAUNCH(ctx, k_residual, gr, kBlock, A, ctx->rhs, x, ctx->s);
+    LAUNCH(ctx, k_residual, gr, kBlock, A, rhs, (const double *)x, ctx->s);
     LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->s, ctx->s, ctx->part);
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_TMP));
     TRY(fetch_scalars(ctx, S_TMP, 1));
@@ -630,6 +612,36 @@ extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info
         info->true_relres = bi_prod > 0. ? sqrt(ctx->h_scal[S_TMP] / bi_prod) : 0.;
     }
     return converged ? IMPEC_OK : fail(ctx, IMPEC_ERR_NOCONV, "PCG did not reach eps=%g in %d iterations (relres %g)", eps, it, sqrt(i_prod / bi_prod));
+}
+
+extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info *info) {
+    if (!ctx->have_q) return fail(ctx, IMPEC_ERR_ARG, "pressure solve before impec_upload_q");
+    const Grid &g = ctx->g;
+    const dim3 gr = grid2d(g.N2, g.N1);
+    const long long nparts = (long long)gr.x * gr.y;
+    TRY(impec_build_operator(ctx));
+    Cycle C; TRY(make_cycle(ctx, C, 0.0, 0));
+    const LevelDev &A = C.D[0];
+    // pinned value p(1,1) = b/(kappa/dA) = -q(1,1) dA / kappa       (src/MGSolver.cpp:517-567)
+    const double dA = ctx->D.dx * ctx->D.dy;
+    double kappa = 1.;
+    if (ctx->P.is_test) {
+        const double x = ctx->P.x_lb + 1.5 * ctx->D.dx, y = ctx->P.y_lb + 1.5 * ctx->D.dy;
+        kappa = -dA * q_test_host(ctx->P, x, y) / (cos(x) * cos(y));
+    }
+    const double p_pin = -ctx->q_pin / (kappa / dA);
+    double *x = ctx->p;
+    if (ctx->warm_start) {
+        // keep the previous pressure as initial guess (not the reference's behaviour: x0 = 0, MGSolver.cpp:577)
+        LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->p, ctx->d);
+        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
+        LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->d, x);
+        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), x + A.pin, p_pin);
+    } else {
+        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
+    }
+    TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
+    return pcg_solve(ctx, C, ctx->rhs, x, eps, info);
 }
 
 // ------------------------------------------------------------------------------------------------ a12 velocities
@@ -749,9 +761,30 @@ extern "C" int impec_advect_split(impec_ctx *ctx, double dt) {
 }
 
 // ------------------------------------------------------------------------------------------------ a19 dispersion
+// Crank-Nicolson half step (I - dt/2 L_D) c+ = (I + dt/2 L_D) c with the velocity-dependent dispersion tensor of
+// src/MGSolver.cpp:846-919.  With alpha_l == alpha_t (all shipped cfgs) d12 = d21 = 0 and the operator is the 5-point
+// links operator AW = dt/(2dx^2) d11, AS = dt/(2dy^2) d22 with mass term 1; Neumann folding (:1031-1289) again just
+// removes the wall links.  Solved by the same PCG with one symmetric red-black sweep as preconditioner (the system
+// is strongly diagonally dominant: dt D / dx^2 <~ cfl).  c must carry filled ghosts (the caller's FillBoundaries) and
+// u, v their ghost fill (CalcVelocities).  x0 = 0 as upstream (:1379-1391).
 extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info *info) {
-    (void)dt; (void)info;
-    return fail(ctx, IMPEC_ERR_UNSUPPORTED, "Crank-Nicolson dispersion is not built yet");
+    const Grid &g = ctx->g;
+    const dim3 gr = grid2d(g.N2, g.N1);
+    const long long nparts = (long long)gr.x * gr.y;
+    Level &L0 = ctx->L[0];
+    ctx->op_valid = false; ctx->mob_valid = false;          // the level-0 link arrays are reused for the parabolic operator
+    LAUNCH(ctx, k_disp_links, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, (const double *)ctx->u, (const double *)ctx->v, dt, ctx->D, L0.AW, L0.AS, L0.AV);
+    LevelDev A = level_dev(ctx, 0, 1.0);
+    A.pin = -1; A.sig_idx = -1;
+    LAUNCH(ctx, k_diag_inv, gr, kBlock, A, (const double *)nullptr, L0.DINV);
+    Cycle C; C.ctx = ctx; C.D.assign(1, A); C.ncoarse = 1; C.w_from = 1; C.w_to = 0; C.nl = 1;
+    double *x = ctx->ta;
+    LAUNCH_COOP(ctx, k_cn_rhs, gr, kBlock, A, (const double *)ctx->c, ctx->rhs, x, ctx->part);
+    TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
+    const int rc = pcg_solve(ctx, C, ctx->rhs, x, ctx->P.para_eps, info);
+    if (rc != IMPEC_OK && rc != IMPEC_ERR_NOCONV) return rc;
+    LAUNCH(ctx, k_copy_interior, gr, kBlock, g, (const double *)x, ctx->c);     // MapHYPREVectorToVertex: interior only
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ a14 transport step

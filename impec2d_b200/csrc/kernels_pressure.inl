@@ -316,6 +316,63 @@ __global__ void __launch_bounds__(256) k_setup_rhs(Grid g, const double *__restr
     if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
 }
 
+// ---------------------------------------------------------------- a19: Crank-Nicolson dispersion
+// face dispersion coefficients (src/MGSolver.cpp:846-919) turned into links of (I - dt/2 L_D):
+//   AW(i,j) = dt/(2 dx^2) d11(i-1/2,j),  AS(i,j) = dt/(2 dy^2) d22(i,j-1/2),  AV = 0   (alpha_l == alpha_t => d12 = d21 = 0)
+// |u| = 0 gives 0/0 upstream (:868-869); here such a face simply has no dispersion.
+__global__ void __launch_bounds__(256) k_disp_links(Grid g, const double *__restrict__ u, const double *__restrict__ v, double dt, DevParams P,
+                                                    double *__restrict__ AW, double *__restrict__ AS, double *__restrict__ AV) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > g.N1 || j > g.N2) return;
+    const size_t k = gidx(g, i, j);
+    const int ld = g.ld;
+    const double maxdx = P.dx > P.dy ? P.dx : P.dy;
+    const double al = P.alpha_l * maxdx, at = P.alpha_t * maxdx;
+    AV[k] = 0.;
+    if (j < g.N2) {
+        double w = 0.;
+        if (i > 0 && i < g.N1) {
+            const double uu = u[k];
+            const double vv = 1. / 4 * (v[k - ld + 1] + v[k + 1] + v[k - ld] + v[k]);
+            const double u2 = uu * uu, v2 = vv * vv, n2 = u2 + v2;
+            if (n2 > 0.) {
+                const double fl = P.porosity * al / sqrt(n2), ft = P.porosity * at / sqrt(n2);
+                w = dt / (2. * P.dx * P.dx) * (fl * u2 + ft * v2);
+            }
+        }
+        AW[k] = w;
+    }
+    if (i < g.N1) {
+        double s = 0.;
+        if (j > 0 && j < g.N2) {
+            const double uu = 1. / 4 * (u[k + ld - 1] + u[k + ld] + u[k - 1] + u[k]);
+            const double vv = v[k];
+            const double u2 = uu * uu, v2 = vv * vv, n2 = u2 + v2;
+            if (n2 > 0.) {
+                const double fl = P.porosity * al / sqrt(n2), ft = P.porosity * at / sqrt(n2);
+                s = dt / (2. * P.dy * P.dy) * (fl * v2 + ft * u2);
+            }
+        }
+        AS[k] = s;
+    }
+}
+// rhs = (I + dt/2 L_D) c = c + sum links (c_nb - c)   (src/MGSolver.cpp:1324-1371), x0 = 0, partial <b,b>
+__global__ void __launch_bounds__(256) k_cn_rhs(LevelDev L, const double *__restrict__ c, double *__restrict__ rhs, double *__restrict__ x, double *__restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double v = 0.;
+    if (i < L.g.N1 && j < L.g.N2) {
+        const size_t k = gidx(L.g, i, j);
+        const double links = link_diag(L, k) - L.mass;
+        const double b = c[k] + (link_offsum(L, c, k) - links * c[k]);
+        rhs[k] = b; x[k] = 0.;
+        v = b * b;
+    }
+    v = block_reduce<RED_SUM>(v);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
 // ---------------------------------------------------------------- a12: Darcy velocity
 // rotated-frame velocity at vertex (i-1/2,j-1/2) rotated back to (x,y): src/EllipticSolver.cpp:554-592
 IMPEC_D void vertex_vel(const DevParams &P, const double *__restrict__ p, double K11, double K22, size_t k, int ld, double &u1, double &u2) {

@@ -1,0 +1,94 @@
+#include "DeviceContext.h"
+#include <map>
+#include <cstring>
+#include <cstdlib>
+#include <iostream>
+
+namespace {
+struct Entry { impec_ctx *ctx = nullptr; impec_params P; const double *q_uploaded = nullptr; };
+std::map<SimParams *, Entry> g_ctx;
+}
+
+void DeviceContext::Check(impec_ctx *ctx, int rc, const char *what) {
+    if (rc == IMPEC_OK) return;
+    std::cerr << "impec2d_b200: " << what << " failed (" << rc << "): " << impec_last_error(ctx) << std::endl;
+    exit(1);                                             // the reference's error convention for fatal errors
+}
+
+impec_params DeviceContext::ToParams(const SimParams *sp) {
+    impec_params P; impec_default_params(&P);
+    P.N1 = sp->N1; P.N2 = sp->N2; P.g = sp->c_bounds;
+    P.x_lb = sp->x_lb; P.x_ub = sp->x_ub; P.y_lb = sp->y_lb; P.y_ub = sp->y_ub;
+    P.mu_res = sp->mu_res; P.mu_inj = sp->mu_inj;
+    P.avgproc = sp->avgproc == HARMONIC ? IMPEC_HARMONIC : IMPEC_MEANCONC;
+    P.nu = sp->nu; P.is_test = sp->is_test ? 1 : 0; P.testno = sp->is_test ? sp->testno : 0;
+    P.stype = sp->stype == PARALLEL ? IMPEC_PARALLEL : (sp->stype == DIAGONAL ? IMPEC_DIAGONAL : IMPEC_HORIZONTAL);
+    P.porosity = sp->porosity; P.cfl = sp->cfl; P.inj_fluid_conc = sp->inj_fluid_conc;
+    P.diffusion = sp->diffusion ? 1 : 0; P.alpha_l = sp->alpha_l; P.alpha_t = sp->alpha_t; P.dt_diff_limit = sp->dt_diff_limit;
+    P.ptype = sp->ptype == CRANKNICOLSON ? IMPEC_CRANKNICOLSON : IMPEC_EXPLICIT;
+    P.eps = sp->eps; P.para_eps = sp->para_eps;
+    P.hyper_method = sp->hmtype == UPWINDSPLIT ? IMPEC_UPWIND : IMPEC_MUSCL;
+    switch (sp->dim_splitting) {
+    case ALTERNATING: P.dim_splitting = IMPEC_ALTERNATING; break;
+    case X_FIRST: P.dim_splitting = IMPEC_X_FIRST; break;
+    case Y_FIRST: P.dim_splitting = IMPEC_Y_FIRST; break;
+    case STRANG: P.dim_splitting = IMPEC_STRANG; break;
+    default: P.dim_splitting = IMPEC_SYMMETRIC_PARALLEL; break;
+    }
+    return P;
+}
+
+impec_ctx *DeviceContext::Get(SimParams *sp) {
+    Entry &e = g_ctx[sp];
+    const impec_params P = ToParams(sp);
+    if (e.ctx && std::memcmp(&P, &e.P, sizeof(P)) == 0) return e.ctx;
+    if (e.ctx) { impec_ctx_destroy(e.ctx); e.ctx = nullptr; }
+    const char *dev = getenv("IMPEC_DEVICE");
+    const int rc = impec_ctx_create(&P, dev ? atoi(dev) : 0, 0, 1, nullptr, nullptr, &e.ctx);
+    Check(e.ctx, rc, "impec_ctx_create");
+    e.P = P; e.q_uploaded = nullptr;
+    return e.ctx;
+}
+
+void DeviceContext::Release(SimParams *sp) {
+    auto it = g_ctx.find(sp);
+    if (it == g_ctx.end()) return;
+    if (it->second.ctx) impec_ctx_destroy(it->second.ctx);
+    g_ctx.erase(it);
+}
+
+void DeviceContext::InvalidateSource(SimParams *sp) { g_ctx[sp].q_uploaded = nullptr; }
+
+void DeviceContext::Use(impec_ctx *ctx, const Array2d *c, const Array2d *p, const Array3d *v, const double *q, SimParams *sp) {
+    if (c) { if (!c->BoundTo(ctx)) c->Bind(ctx, FIELD_C); c->SyncToDevice(); }
+    if (p) { if (!p->BoundTo(ctx)) p->Bind(ctx, FIELD_P); p->SyncToDevice(); }
+    if (v) { if (!v->BoundTo(ctx)) v->Bind(ctx, FIELD_V); v->SyncToDevice(); }
+    if (q) {
+        Entry &e = g_ctx[sp];
+        if (e.q_uploaded != q) { Check(ctx, impec_upload_q(ctx, q), "impec_upload_q"); e.q_uploaded = q; }
+    }
+}
+
+// ---- DeviceBound (declared in GenSimDefs.h)
+void DeviceBound::Bind(impec_ctx *ctx, int field) const {
+    if (ctx_ && ctx_ != ctx) pull();
+    ctx_ = ctx; field_ = field; host_dirty_ = true; dev_newer_ = false;
+}
+void DeviceBound::pull() const {
+    if (!dev_newer_ || !ctx_) return;
+    int rc = IMPEC_OK;
+    if (field_ == FIELD_C) rc = impec_download_c(ctx_, raw());
+    else if (field_ == FIELD_P) rc = impec_download_p(ctx_, raw());
+    else if (field_ == FIELD_V) rc = impec_download_velocity(ctx_, raw());
+    DeviceContext::Check(ctx_, rc, "download");
+    dev_newer_ = false;
+}
+void DeviceBound::SyncToDevice() const {
+    if (!ctx_ || !host_dirty_) return;
+    int rc = IMPEC_OK;
+    if (field_ == FIELD_C) rc = impec_upload_c(ctx_, raw());
+    else if (field_ == FIELD_P) rc = impec_upload_p(ctx_, raw());
+    else if (field_ == FIELD_V) rc = impec_upload_velocity(ctx_, raw());
+    DeviceContext::Check(ctx_, rc, "upload");
+    host_dirty_ = false;
+}

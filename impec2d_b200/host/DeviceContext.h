@@ -1,0 +1,20 @@
+// DeviceContext.h -- one impec_ctx (one GPU) per SimParams, shared by the solver objects that borrow the same
+// SimParams* (the reference's solvers all borrow sp and never own it: src/EllipticSolver.cpp:59, src/HyperbolicSolver.cpp:63).
+#ifndef DEVICECONTEXT_H_
+#define DEVICECONTEXT_H_
+#include "SimParams.h"
+#include "GenSimDefs.h"
+#include "../../include/impec2d_b200.h"
+
+class DeviceContext {
+public:
+    // returns the context for sp, creating or re-creating it when the grid or physics in sp changed
+    static impec_ctx *Get(SimParams *sp);
+    static void Release(SimParams *sp);
+    static impec_params ToParams(const SimParams *sp);
+    // make the device copies current for an operation that reads them
+    static void Use(impec_ctx *ctx, const Array2d *c, const Array2d *p, const Array3d *v, const double *q, SimParams *sp);
+    static void InvalidateSource(SimParams *sp);          // call after changing q in place
+    static void Check(impec_ctx *ctx, int rc, const char *what);
+};
+#endif

@@ -194,3 +194,40 @@ def check_fused_vs_unfused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
         out.append(z1)
         ctx.close()
     assert np.abs(out[0] - out[1]).max() <= 1e-12 * np.abs(out[0]).max()
+
+
+def check_dispersion(emulated, N1=32, N2=32, stype=O.PARALLEL, steps=1):
+    """a19: Crank-Nicolson dispersion half step on its own and inside a full IMPES step of a *_dispersion.cfg
+    operator (two CN solves per step).  Tolerance: max|dc| <= 1e-9 (both sides iterate to para_eps = 1e-14)."""
+    lib = O.lib()
+    base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=1, eps=1e-12)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    So = O.new_state()
+    p = O.scalar_field(Po); u = O.velocity_field(Po); v = O.velocity_field(Po)
+    co = c.copy()
+    # velocities first (pressure solve), then one stand-alone CN half step on both sides
+    lib.orc_fill_boundaries(C.byref(Po), co)
+    lib.orc_solve_elliptic(C.byref(Po), C.byref(So), co, q, p)
+    lib.orc_calc_velocities(C.byref(Po), p, co, u, v)
+    dt = lib.orc_max_stable_dt(C.byref(Po), u, v)
+    ctx.fill_boundaries(); ctx.pressure_solve(); ctx.calc_velocities()
+    assert abs(ctx.max_stable_dt() - dt) <= 1e-9 * dt
+    lib.orc_solve_parabolic(C.byref(Po), C.byref(So), co, u, v, 0.5 * dt)
+    info = ctx.diffusion_split(0.5 * dt)
+    assert info.converged == 1 and abs(info.iterations - So.last_parabolic_its) <= 2
+    cg = ctx.download_c()
+    assert np.abs(interior(Po, cg) - interior(Po, co)).max() <= 1e-9
+    # mass is conserved by the CN step with closed walls
+    assert abs(interior(Po, cg).sum() - interior(Po, c).sum()) <= 1e-10 * interior(Po, c).sum()
+    # full steps
+    ctx.upload_c(c); co = c.copy(); t = 0.0
+    for _ in range(steps):
+        dto = lib.orc_impes_step(C.byref(Po), C.byref(So), p, co, u, v, q, t, 0.0)
+        dtg, _ = ctx.impes_step(t, 0.0)
+        assert abs(dtg - dto) <= 1e-9 * dto
+        t += dto
+    cg = ctx.download_c()
+    assert np.abs(cg - co).max() <= 1e-8
+    ctx.close()

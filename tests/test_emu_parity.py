@@ -37,3 +37,5 @@ def test_impes_step_diagonal_rect(): pc.check_impes_step(True, 32, 16, stype=O.D
 def test_elliptic_manufactured_5pt(): pc.check_elliptic_manufactured(True, 20, 30, testno=4, nu=1.0)
 def test_elliptic_manufactured_9pt(): pc.check_elliptic_manufactured(True, 20, 30, testno=2, nu=2.0 / 3.0)
 def test_fused_vs_unfused_cycle(): pc.check_fused_vs_unfused(True, 256, 384)
+def test_dispersion_parallel(): pc.check_dispersion(True, 32, 32)
+def test_dispersion_diagonal_rect(): pc.check_dispersion(True, 32, 16, stype=O.DIAGONAL)

@@ -45,6 +45,10 @@ def test_vcycle(N1, N2, stype): pc.check_vcycle(False, N1, N2, stype=stype)
 def test_impes_step(N1, N2, stype, nu, avg): pc.check_impes_step(False, N1, N2, stype=stype, nu=nu, avg=avg, steps=2)
 
 
+@pytest.mark.parametrize("N1,N2,stype", [(128, 128, O.PARALLEL), (100, 50, O.DIAGONAL), (256, 128, O.DIAGONAL)])
+def test_dispersion(N1, N2, stype): pc.check_dispersion(False, N1, N2, stype=stype, steps=2)
+
+
 def test_elliptic_manufactured_convergence():
     """elliptic_test.cfg on the GPU: testno 4, nu = 1, 20x30 doubling; order 2.00 +- 0.03 on the finest pair."""
     res = [pc.check_elliptic_manufactured(False, 20 * 2 ** k, 30 * 2 ** k, testno=4, nu=1.0) for k in range(5)]
