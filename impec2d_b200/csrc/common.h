@@ -6,23 +6,41 @@
 // layout: rows are x (i, slow), columns y (j, contiguous) exactly like the reference's blitz arrays
 // (src/GenSimDefs.h:25-31), with GH ghost rows on either side and PJ pad columns on the left so that
 // the first interior element of every row is 32-byte aligned and rows start on 128-byte boundaries.
-#define IMPEC_GH 2      // ghost rows (the reference's num_ghostcells = 2)
+#define IMPEC_GH 4      // allocated halo rows (>= the reference's num_ghostcells = 2; 4 so that the fused multigrid kernels
+                        // can treat 3 halo rows of a neighbouring slab as active cells)
+#define IMPEC_HALO 3    // halo rows of a neighbouring slab that carry valid cells
 #define IMPEC_PJ 4      // left pad in doubles (>= ghost width, multiple of 4)
 
-struct Grid {           // geometry of one level (or of the fine grid)
-    int N1, N2;         // interior cells
+struct Grid {           // geometry of one level (or of the fine grid) as seen by one rank (a slab of rows)
+    int N1, N2;         // interior cells of this slab
     int ld;             // pitch in doubles
     int rows;           // allocated rows = N1 + 1 + 2*GH
+    int wall_lo, wall_hi;   // 1 if row 0 / row N1 is a physical wall of the domain, 0 if a neighbouring slab continues there
+    int rlo, rhi;       // rows [rlo, rhi) hold valid cells (interior plus IMPEC_HALO rows towards neighbouring slabs)
+    int i_off;          // global row index of local row 0
 };
 
 IMPEC_HD size_t gidx(const Grid &g, int i, int j) { return (size_t)(i + IMPEC_GH) * (size_t)g.ld + (size_t)(j + IMPEC_PJ); }
 IMPEC_HD size_t grid_elems(const Grid &g) { return (size_t)g.rows * (size_t)g.ld; }
 
+static inline Grid make_grid(int N1, int N2);
+// slab of a distributed level: rank `rank` of `nranks` owns N1g/nranks rows
+static inline Grid make_slab(int N1g, int N2, int rank, int nranks);
 static inline Grid make_grid(int N1, int N2) {
     Grid g;
     g.N1 = N1; g.N2 = N2;
     g.ld = ((N2 + 1 + 2 * IMPEC_PJ) + 15) / 16 * 16;
     g.rows = N1 + 1 + 2 * IMPEC_GH;
+    g.wall_lo = g.wall_hi = 1; g.rlo = 0; g.rhi = N1; g.i_off = 0;
+    return g;
+}
+
+static inline Grid make_slab(int N1g, int N2, int rank, int nranks) {
+    Grid g = make_grid(N1g / nranks, N2);
+    g.i_off = rank * (N1g / nranks);
+    g.wall_lo = rank == 0; g.wall_hi = rank == nranks - 1;
+    g.rlo = g.wall_lo ? 0 : -IMPEC_HALO;
+    g.rhi = g.N1 + (g.wall_hi ? 0 : IMPEC_HALO);
     return g;
 }
 

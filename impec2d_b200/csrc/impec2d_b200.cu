@@ -207,7 +207,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     impec_ctx *ctx = new impec_ctx();
     *out = ctx;                                   // returned even on failure so that the error text can be read
     ctx->P = *P; ctx->device = device; ctx->rank = rank; ctx->nranks = nranks;
-    if (P->g != IMPEC_GH) return fail(ctx, IMPEC_ERR_ARG, "num_ghostcells must be %d (got %d)", IMPEC_GH, P->g);
+    if (P->g != 2) return fail(ctx, IMPEC_ERR_ARG, "num_ghostcells must be 2 (got %d)", P->g);
     if (P->N1 < 4 || P->N2 < 4) return fail(ctx, IMPEC_ERR_ARG, "grid too small: %d x %d", P->N1, P->N2);
     if (nranks != 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "multi-GPU slabs not built into this library (nranks=%d)", nranks);
     if (P->stype == IMPEC_HORIZONTAL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "source_type horizontal is outside the accelerated path");

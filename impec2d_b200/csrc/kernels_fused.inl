@@ -96,13 +96,14 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
             const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
             const d2 v = ld2(xin + k);
             a = v.x; b = v.y;
-            if (MODE == FUSED_POST && (!EDGE || (ig >= 0 && ig < g.N1))) {
+            if (MODE == FUSED_POST && (!EDGE || (ig >= g.rlo && ig < g.rhi))) {
                 // x += P ec : cell-centred bilinear with edge replication.  Both cells of the pair share the coarse
                 // column J; the even cell interpolates towards J-1, the odd one towards J+1.
                 const int I = ig >> 1, J = jg >> 1;
                 int In = (ig & 1) ? I + 1 : I - 1, Jm = J - 1, Jp = J + 1;
                 if (EDGE) {
-                    In = In < 0 ? 0 : (In > gc.N1 - 1 ? gc.N1 - 1 : In);
+                    if (In < 0 && gc.wall_lo) In = 0;
+                    if (In > gc.N1 - 1 && gc.wall_hi) In = gc.N1 - 1;
                     Jm = Jm < 0 ? 0 : Jm; Jp = Jp > gc.N2 - 1 ? gc.N2 - 1 : Jp;
                 }
                 const double *e0 = ec + gidx(gc, I, 0), *e1 = ec + gidx(gc, In, 0);
@@ -137,7 +138,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
         for (int n = 0; n < FT_ROWS; n++) {
             const int r = ty + n * FT_NTY, ig = i0 + r;
             double val = X[r * FT_W + (off << 6) + tx];
-            const bool act = colok && r >= shrink && r < FT_H - shrink && (!EDGE || (ig >= 0 && ig < g.N1));
+            const bool act = colok && r >= shrink && r < FT_H - shrink && (!EDGE || (ig >= g.rlo && ig < g.rhi));
             if (act) {
                 const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld + off);
                 if (MODE == FUSED_PRE && s == 0) val = f[k] * L.DINV[k];
@@ -184,7 +185,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
         for (int n = 0; n < FT_ROWS; n++) {
             const int r = ty + n * FT_NTY, ig = i0 + r;
             double v0 = 0., v1 = 0.;                                     // residual of the first / second colour cell
-            if (r >= 2 && r < FT_H - 2 && (!EDGE || (ig >= 0 && ig < g.N1))) {
+            if (r >= 2 && r < FT_H - 2 && (!EDGE || (ig >= g.rlo && ig < g.rhi))) {
                 const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
                 const int ja = jl + off0, jb = jl + 1 - off0;
                 if (ja >= 2 && ja < FT_W - 2 && (!EDGE || (jg + off0 >= 0 && jg + off0 < g.N2 && (long long)(k + off0) != L.pin)))
@@ -213,7 +214,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
 #pragma unroll
         for (int a = 0; a < 4; a++) {
             int i = 2 * I - 1 + a;
-            if (EDGE) i = i < 0 ? 0 : (i > g.N1 - 1 ? g.N1 - 1 : i);
+            if (EDGE) { if (i < 0 && g.wall_lo) i = 0; if (i > g.N1 - 1 && g.wall_hi) i = g.N1 - 1; }
             int jm = 2 * J - 1, jp = 2 * J + 2;
             if (EDGE) { jm = jm < 0 ? 0 : jm; jp = jp > g.N2 - 1 ? g.N2 - 1 : jp; }
             const int rr = i - i0;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_fused(LevelDev L, cons
     constexpr int HI = FusedGeom<MODE>::HI, TI = FusedGeom<MODE>::TI;
     const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ, i0 = (int)blockIdx.y * TI - HI;
     // tile (halo included, plus the one-cell reach of the link arrays) strictly inside the domain and free of the pin?
-    bool edge = i0 < 0 || j0 < 0 || i0 + FT_H >= L.g.N1 || j0 + FT_W >= L.g.N2;
+    bool edge = i0 < L.g.rlo || j0 < 0 || i0 + FT_H >= L.g.rhi || j0 + FT_W >= L.g.N2;
     if (L.pin >= 0) {
         const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
         edge = edge || (pi >= i0 && pi < i0 + FT_H && pj >= j0 && pj < j0 + FT_W);

@@ -95,12 +95,13 @@ __global__ void __launch_bounds__(256) k_links(Grid g, const double *__restrict_
 #define AVRAW(kk) ((1 - nu) * (vM11(P, KV11[kk], KV22[kk]) / inv_xi2))
 #define M12AT(kk) (vM12(P, KV11[kk], KV22[kk]))
     // vertex link
-    const bool vb = (i == 0 || i == g.N1 || j == 0 || j == g.N2);
+    const bool at_lo = (i == 0 && g.wall_lo), at_hi = (i == g.N1 && g.wall_hi);      // on a physical x-wall?
+    const bool vb = (at_lo || at_hi || j == 0 || j == g.N2);
     AV[k] = (rot && !vb) ? AVRAW(k) : 0.;
     // x-face link between (i-1,j) and (i,j)
     if (j < g.N2) {
         double w = 0.;
-        if (i > 0 && i < g.N1) {
+        if (!at_lo && !at_hi) {
             double Ka = 1., Kb = 1.;
             if (TEST) { const double x = P.x_lb + (i + 0.5) * P.dx, y = P.y_lb + (j + 0.5) * P.dy; Ka = K11_fn(P, x - P.dx, y); Kb = K11_fn(P, x, y); }
             const double Wp = 1. / (P.dx * P.dx) * face_mob<TEST>(MU[k - g.ld], MU[k], Ka, Kb, P.avgproc);
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(256) k_links(Grid g, const double *__restrict_
             double Sd = 0.;
             if (rot) Sd = inv_xe * (M12AT(k) + M12AT(k + g.ld));              // M12(i-1/2,j-1/2) + M21(i+1/2,j-1/2)
             s = nu * Sp + (1 - nu) * Sd;
-            if (rot && i == 0) s = s + AVRAW(k);                              // left column:  S += SW
-            if (rot && i == g.N1 - 1) s = s + AVRAW(k + g.ld);                // right column: S += SE
+            if (rot && i == 0 && g.wall_lo) s = s + AVRAW(k);                 // left column:  S += SW
+            if (rot && i == g.N1 - 1 && g.wall_hi) s = s + AVRAW(k + g.ld);   // right column: S += SE
         }
         AS[k] = s;
     }
@@ -191,8 +192,8 @@ __global__ void __launch_bounds__(256) k_diag_inv(LevelDev L, const double *__re
 // r = f - S x  (0 at the pinned cell); optionally accumulates <r,r> partials
 __global__ void __launch_bounds__(256) k_residual(LevelDev L, const double *__restrict__ f, const double *__restrict__ x, double *__restrict__ r) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= L.g.N1 || j >= L.g.N2) return;
+    const int i = (int)(blockIdx.y * blockDim.y + threadIdx.y) - (L.g.wall_lo ? 0 : 1);     // one halo row where a slab continues
+    if (i >= L.g.N1 + (L.g.wall_hi ? 0 : 1) || j >= L.g.N2) return;
     const size_t k = gidx(L.g, i, j);
     r[k] = ((long long)k == L.pin) ? 0. : f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k));
 }
@@ -206,7 +207,9 @@ __global__ void __launch_bounds__(256) k_restrict(Grid gf, const double *__restr
     double t4[4];
 #pragma unroll
     for (int a = 0; a < 4; a++) {
-        int i = 2 * I - 1 + a; i = i < 0 ? 0 : (i > gf.N1 - 1 ? gf.N1 - 1 : i);
+        int i = 2 * I - 1 + a;
+        if (i < 0 && gf.wall_lo) i = 0;
+        if (i > gf.N1 - 1 && gf.wall_hi) i = gf.N1 - 1;
         double s = 0.;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -226,7 +229,9 @@ __global__ void __launch_bounds__(256) k_prolong_add(Grid gc, const double *__re
     const size_t k = gidx(gf, i, j);
     if ((long long)k == pin) return;
     const int I = i >> 1, J = j >> 1;
-    int In = (i & 1) ? I + 1 : I - 1; In = In < 0 ? 0 : (In > gc.N1 - 1 ? gc.N1 - 1 : In);
+    int In = (i & 1) ? I + 1 : I - 1;
+    if (In < 0 && gc.wall_lo) In = 0;
+    if (In > gc.N1 - 1 && gc.wall_hi) In = gc.N1 - 1;
     int Jn = (j & 1) ? J + 1 : J - 1; Jn = Jn < 0 ? 0 : (Jn > gc.N2 - 1 ? gc.N2 - 1 : Jn);
     const double a = 0.75 * e[gidx(gc, I, J)] + 0.25 * e[gidx(gc, In, J)];
     const double b = 0.75 * e[gidx(gc, I, Jn)] + 0.25 * e[gidx(gc, In, Jn)];
@@ -240,9 +245,10 @@ __global__ void __launch_bounds__(256) k_coarsen_links(Grid gf, const double *__
     const int I = blockIdx.y * blockDim.y + threadIdx.y;
     if (I > gc.N1 || J > gc.N2) return;
     const size_t kc = gidx(gc, I, J), kf = gidx(gf, 2 * I, 2 * J);
-    if (J < gc.N2) AWc[kc] = (I == gc.N1) ? 0. : 0.125 * (AWf[kf] + AWf[kf + 1]);
+    const bool wall = (I == gc.N1 && gc.wall_hi);
+    if (J < gc.N2) AWc[kc] = wall ? 0. : 0.125 * (AWf[kf] + AWf[kf + 1]);
     if (I < gc.N1) ASc[kc] = (J == gc.N2) ? 0. : 0.125 * (ASf[kf] + ASf[kf + gf.ld]);
-    AVc[kc] = (I == gc.N1 || J == gc.N2) ? 0. : 0.25 * AVf[kf];
+    AVc[kc] = (wall || J == gc.N2) ? 0. : 0.25 * AVf[kf];
 }
 
 // ---------------------------------------------------------------- PCG vector kernels (a10)
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(256) k_disp_links(Grid g, const double *__rest
     AV[k] = 0.;
     if (j < g.N2) {
         double w = 0.;
-        if (i > 0 && i < g.N1) {
+        if (!(i == 0 && g.wall_lo) && !(i == g.N1 && g.wall_hi)) {
             const double uu = u[k];
             const double vv = 1. / 4 * (v[k - ld + 1] + v[k + 1] + v[k - ld] + v[k]);
             const double u2 = uu * uu, v2 = vv * vv, n2 = u2 + v2;
@@ -444,7 +450,7 @@ __global__ void __launch_bounds__(256) k_diag_boundary(Grid g, const double *__r
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0.;
     if (t < g.N1) s += fabs(v[gidx(g, t, 0)]) + fabs(v[gidx(g, t, g.N2)]);
-    if (t < g.N2) s += fabs(u[gidx(g, 0, t)]) + fabs(u[gidx(g, g.N1, t)]);
+    if (t < g.N2) s += (g.wall_lo ? fabs(u[gidx(g, 0, t)]) : 0.) + (g.wall_hi ? fabs(u[gidx(g, g.N1, t)]) : 0.);
     s = block_reduce<RED_SUM>(s);
     if (threadIdx.x == 0) part[blockIdx.x] = s;
 }

@@ -36,6 +36,7 @@ __global__ void k_fill_scalar(Grid g, double *__restrict__ a, int periodic, int 
         const int cidx = (int)(t % (2 * ng));
         j = cidx < ng ? cidx - ng : g.N2 + (cidx - ng);
     }
+    if ((i < 0 && !g.wall_lo) || (i >= g.N1 && !g.wall_hi)) return;      // halo rows of a neighbouring slab: filled by the exchange
     const int si = periodic ? wrap_cell(i, g.N1) : reflect_cell(i, g.N1);
     const int sj = periodic ? wrap_cell(j, g.N2) : reflect_cell(j, g.N2);
     a[gidx(g, i, j)] = a[gidx(g, si, sj)];
@@ -50,6 +51,7 @@ __global__ void k_fill_velocity(Grid g, double *__restrict__ u, double *__restri
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)W * H) return;
     const int i = (int)(t / W) - ng, j = (int)(t % W) - ng;
+    if ((i < 0 && !g.wall_lo) || (i > g.N1 && !g.wall_hi)) return;       // halo rows of a neighbouring slab: filled by the exchange
     // u component
     if (j < g.N2 + ng && !(i >= 0 && i <= g.N1 && j >= 0 && j < g.N2)) {
         const int si = i < 0 ? -i : (i > g.N1 ? 2 * g.N1 - i : i);
@@ -58,7 +60,7 @@ __global__ void k_fill_velocity(Grid g, double *__restrict__ u, double *__restri
         u[gidx(g, i, j)] = (si != i) ? -val : val;
     }
     // v component
-    if (i < g.N1 + ng && !(i >= 0 && i < g.N1 && j >= 0 && j <= g.N2)) {
+    if (i < g.N1 + ng && (i < g.N1 || g.wall_hi) && !(i >= 0 && i < g.N1 && j >= 0 && j <= g.N2)) {
         const int si = reflect_cell(i, g.N1);
         const int sj = j < 0 ? -j : (j > g.N2 ? 2 * g.N2 - j : j);
         const double val = v[gidx(g, si, sj)];
