@@ -35,6 +35,16 @@ class Params(C.Structure):
         return (self.y_ub - self.y_lb) / self.N2
 
 
+SENDRECV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong)
+BCAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int)
+
+
+class CommCallbacks(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("sendrecv", SENDRECV_FN), ("allreduce", ALLREDUCE_FN), ("allgather", ALLGATHER_FN), ("bcast", BCAST_FN)]
+
+
 class Diag(C.Structure):
     _fields_ = [("total_mass", C.c_double), ("divergence_error", C.c_double), ("boundary_velocity_error", C.c_double),
                 ("total_mass_outflux", C.c_double), ("c_min", C.c_double), ("c_max", C.c_double)]
@@ -52,7 +62,8 @@ EXPORTS = [
     "impec_max_stable_dt", "impec_source_split", "impec_advect_x", "impec_advect_y", "impec_advect_split",
     "impec_diffusion_split", "impec_transport_step", "impec_impes_step", "impec_diagnostics", "impec_build_operator",
     "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_reset_state", "impec_set_option",
-    "impec_profile_kernel", "impec_init_source", "impec_synth_state",
+    "impec_profile_kernel", "impec_init_source", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
+    "impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows", "impec_init_source_rows", "impec_synth_state_rows",
 ]
 
 
@@ -103,5 +114,11 @@ def load(emulated=False):
     L.impec_profile_kernel.argtypes = [vp, C.c_char_p, i, dptr]
     L.impec_init_source.argtypes = [C.POINTER(Params), d, d, i, vp]
     L.impec_synth_state.argtypes = [C.POINTER(Params), C.c_ulonglong, vp]
+    L.impec_ctx_set_comm_callbacks.argtypes = [vp, C.POINTER(CommCallbacks)]
+    L.impec_local_rows.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    for n in ("impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows"):
+        getattr(L, n).argtypes = [vp, vp]
+    L.impec_init_source_rows.argtypes = [C.POINTER(Params), d, d, i, i, i, vp]
+    L.impec_synth_state_rows.argtypes = [C.POINTER(Params), C.c_ulonglong, i, i, vp]
     _CACHE[key] = L
     return L

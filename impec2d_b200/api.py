@@ -135,6 +135,18 @@ class Context:
     def set_option(self, key, value): self._chk(self.L.impec_set_option(self._h, key.encode(), float(value)))
     def synchronize(self): self._chk(self.L.impec_synchronize(self._h))
 
+    def local_rows(self):
+        r0 = C.c_int(); n = C.c_int()
+        self._chk(self.L.impec_local_rows(self._h, C.byref(r0), C.byref(n)))
+        return r0.value, n.value
+
+    def upload_c_rows(self, c): self._chk(self.L.impec_upload_c_rows(self._h, _ptr(c)))
+    def upload_q_rows(self, q): self._chk(self.L.impec_upload_q_rows(self._h, _ptr(q)))
+
+    def download_c_rows(self, out):
+        self._chk(self.L.impec_download_c_rows(self._h, _ptr(out)))
+        return out
+
     def profile_kernel(self, name, reps=10):
         ms = C.c_double()
         self._chk(self.L.impec_profile_kernel(self._h, name.encode(), reps, C.byref(ms)))
@@ -150,6 +162,22 @@ def init_source(params, I=1.0, well_rc=0.05, well_profile=0, emulated=False):
     return q
 
 
+def init_source_rows(params, row0, nrows, I=1.0, well_rc=0.05, well_profile=0, emulated=False):
+    q = np.zeros(nrows * params.N2)
+    rc = _lib.load(emulated).impec_init_source_rows(C.byref(params), I, well_rc, well_profile, row0, nrows, _ptr(q))
+    if rc != 0:
+        raise ImpecError("impec_init_source_rows failed (%d)" % rc)
+    return q
+
+
+def synth_state_rows(params, row0, nrows, seed=20260917, out=None, emulated=False):
+    c = np.zeros((nrows + 2 * params.g, params.N2 + 2 * params.g)) if out is None else out
+    rc = _lib.load(emulated).impec_synth_state_rows(C.byref(params), seed, row0, nrows, _ptr(c))
+    if rc != 0:
+        raise ImpecError("impec_synth_state_rows failed (%d)" % rc)
+    return c
+
+
 def synth_state(params, seed=20260917, out=None, emulated=False):
     """Developed synthetic concentration (ghosted array, interior written)."""
     c = np.zeros((params.N1 + 2 * params.g, params.N2 + 2 * params.g)) if out is None else out
@@ -157,3 +185,40 @@ def synth_state(params, seed=20260917, out=None, emulated=False):
     if rc != 0:
         raise ImpecError("impec_synth_state failed (%d)" % rc)
     return c
+
+
+def attach_torch_comm(ctx, rank, nranks):
+    """Tests only (CPU-emulated library): route the slab halo exchanges and small collectives of a multi-rank context
+    through torch.distributed (gloo).  The CUDA library talks NCCL itself and does not use this."""
+    import torch
+    import torch.distributed as dist
+
+    def view(ptr, n):
+        return torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(int(n),)))
+
+    def sendrecv(user, send_lo, recv_lo, send_hi, recv_hi, n):
+        ops = []
+        if send_lo:
+            ops += [dist.P2POp(dist.isend, view(send_lo, n).clone(), rank - 1), dist.P2POp(dist.irecv, view(recv_lo, n), rank - 1)]
+        if send_hi:
+            ops += [dist.P2POp(dist.isend, view(send_hi, n).clone(), rank + 1), dist.P2POp(dist.irecv, view(recv_hi, n), rank + 1)]
+        for r in dist.batch_isend_irecv(ops) if ops else []:
+            r.wait()
+        return 0
+
+    def allreduce(user, buf, n, op):
+        dist.all_reduce(view(buf, n), op={0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MAX, 2: dist.ReduceOp.MIN}[op])
+        return 0
+
+    def allgather(user, send, recv, n):
+        out = view(recv, n * nranks)
+        dist.all_gather_into_tensor(out, view(send, n).clone())
+        return 0
+
+    def bcast(user, buf, n, root):
+        dist.broadcast(view(buf, n), src=root)
+        return 0
+
+    cb = _lib.CommCallbacks(None, _lib.SENDRECV_FN(sendrecv), _lib.ALLREDUCE_FN(allreduce), _lib.ALLGATHER_FN(allgather), _lib.BCAST_FN(bcast))
+    ctx._comm_cb = cb                                  # keep the ctypes thunks alive
+    ctx._chk(ctx.L.impec_ctx_set_comm_callbacks(ctx._h, C.byref(cb)))

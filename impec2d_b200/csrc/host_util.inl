@@ -31,28 +31,33 @@ template <class F> static void parallel_rows(int n, F f) {
 
 // InitializeSource: quarter-circle wells (diagonal: injector at (0,0), producer opposite; parallel: injectors
 // at (0,0) and (N1-1,N2-1), producers in the other two corners) or one-cell wells.
+extern "C" int impec_init_source_rows(const impec_params *P, double I, double well_rc, int well_profile, int row0, int nrows, double *q);
 extern "C" int impec_init_source(const impec_params *P, double I, double well_rc, int well_profile, double *q) {
-    if (!P || !q) return IMPEC_ERR_ARG;
+    return impec_init_source_rows(P, I, well_rc, well_profile, 0, P ? P->N1 : 0, q);
+}
+extern "C" int impec_init_source_rows(const impec_params *P, double I, double well_rc, int well_profile, int row0, int nrows, double *q) {
+    if (!P || !q || row0 < 0 || row0 + nrows > P->N1) return IMPEC_ERR_ARG;
     if (P->stype == IMPEC_HORIZONTAL) return IMPEC_ERR_UNSUPPORTED;
     const int N1 = P->N1, N2 = P->N2;
     const double dx = (P->x_ub - P->x_lb) / N1, dy = (P->y_ub - P->y_lb) / N2;
     const double r = well_rc * (P->x_ub - P->x_lb);
     const double circval = I * 4. / (M_PI * r * r), qval = I / (dx * dy);
-    const size_t M = (size_t)N1 * N2;
     if (well_profile == 2) {                                       // one_cell (src/Util.cpp:565-586)
-        for (size_t k = 0; k < M; k++) q[k] = 0.;
-        q[0] = qval;
-        if (P->stype == IMPEC_PARALLEL) { q[M - 1] = qval; q[N2 - 1] = -qval; q[(size_t)(N1 - 1) * N2] = -qval; }
-        else q[M - 1] = -qval;
+        for (size_t k = 0; k < (size_t)nrows * N2; k++) q[k] = 0.;
+        auto put = [&](int i, int j, double v) { if (i >= row0 && i < row0 + nrows) q[(size_t)(i - row0) * N2 + j] = v; };
+        put(0, 0, qval);
+        if (P->stype == IMPEC_PARALLEL) { put(N1 - 1, N2 - 1, qval); put(0, N2 - 1, -qval); put(N1 - 1, 0, -qval); }
+        else put(N1 - 1, N2 - 1, -qval);
         return IMPEC_OK;
     }
     if (well_profile != 0) return IMPEC_ERR_UNSUPPORTED;           // "gauss" is a no-op upstream (:253-254)
     auto qI = [&](int i, int j) { return circval * exact_vol_frac_circle(P->x_lb + i * dx, P->y_lb + j * dy, r, dx, dy); };
     const bool par = P->stype == IMPEC_PARALLEL;
-    parallel_rows(N1, [&](int i) {
+    parallel_rows(nrows, [&](int il) {
+        const int i = row0 + il;
         for (int j = 0; j < N2; j++) {
             const double a = qI(i, j), b = qI(N1 - 1 - i, N2 - 1 - j);
-            q[(size_t)i * N2 + j] = par ? ((a + b) - qI(i, N2 - 1 - j)) - qI(N1 - 1 - i, j) : a - b;
+            q[(size_t)il * N2 + j] = par ? ((a + b) - qI(i, N2 - 1 - j)) - qI(N1 - 1 - i, j) : a - b;
         }
     });
     return IMPEC_OK;
@@ -69,12 +74,18 @@ static inline unsigned long long splitmix64(unsigned long long x) {
 // plus 1e-3 (U - 1/2) with U a counter-based splitmix64 stream (decomposition independent), clipped to [0,1];
 // the parallel layout adds the mirrored front of the second injector.  Writes the interior of a ghosted
 // (N1+2g) x (N2+2g) array.
+extern "C" int impec_synth_state_rows(const impec_params *P, unsigned long long seed, int row0, int nrows, double *c_ghosted);
 extern "C" int impec_synth_state(const impec_params *P, unsigned long long seed, double *c_ghosted) {
-    if (!P || !c_ghosted) return IMPEC_ERR_ARG;
+    return impec_synth_state_rows(P, seed, 0, P ? P->N1 : 0, c_ghosted);
+}
+extern "C" int impec_synth_state_rows(const impec_params *P, unsigned long long seed, int row0, int nrows, double *c_ghosted) {
+    if (!P || !c_ghosted || row0 < 0 || row0 + nrows > P->N1) return IMPEC_ERR_ARG;
     const int N1 = P->N1, N2 = P->N2, g = P->g;
     const double dx = (P->x_ub - P->x_lb) / N1, dy = (P->y_ub - P->y_lb) / N2, L = P->x_ub - P->x_lb, w = 4. * dx;
     const int pitch = N2 + 2 * g;
-    parallel_rows(N1, [&](int i) {
+    (void)N1;
+    parallel_rows(nrows, [&](int il) {
+        const int i = row0 + il;
         for (int j = 0; j < N2; j++) {
             const double x = (i + 0.5) * dx, y = (j + 0.5) * dy;
             double r = sqrt(x * x + y * y), th = atan2(y, x);
@@ -89,7 +100,7 @@ extern "C" int impec_synth_state(const impec_params *P, unsigned long long seed,
             val += 1e-3 * ((double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5);
             if (val < 0.) val = 0.;
             if (val > 1.) val = 1.;
-            c_ghosted[(size_t)(i + g) * pitch + (j + g)] = val;
+            c_ghosted[(size_t)(il + g) * pitch + (j + g)] = val;
         }
     });
     return IMPEC_OK;

@@ -7,6 +7,9 @@
 #include "kernels_fused.inl"
 #include "../../include/impec2d_b200.h"
 
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+#include <nccl.h>
+#endif
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -22,6 +25,9 @@ struct Level {
     double *AW = nullptr, *AS = nullptr, *AV = nullptr, *DINV = nullptr;
     double *x = nullptr, *f = nullptr, *t = nullptr, *r = nullptr;
     long long pin = -1, sig_idx = -1;
+    bool dist = false;           // rows of this level are slab-distributed over the ranks
+    // first replicated level only: this rank's slab view of it and slab-sized staging for the all-gathers
+    Grid gl; double *AWl = nullptr, *ASl = nullptr, *AVl = nullptr, *fl = nullptr;
 };
 
 struct impec_ctx {
@@ -52,6 +58,14 @@ struct impec_ctx {
     long long launches = 0;
     std::string err;
     std::vector<void *> allocs;
+    // multi-GPU: slab decomposition along i
+    int Ld = 0;                                     // levels [0,Ld) are distributed, [Ld,nl) replicated on every rank
+    int N1g = 0;                                    // global number of rows
+    impec_comm_callbacks cb; bool has_cb = false;
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    ncclComm_t nccl = nullptr;
+#endif
+    bool comm_ready = false;
 };
 
 enum { S_GAMMA0 = 0, S_SDOTP = 1, S_IPROD = 2, S_GAMMA1 = 3, S_BIPROD = 4, S_BETA_NUM = 5, S_BETA_DEN = 6, S_TMP = 7, S_SRC = 8, S_OUTFLUX = 9,
@@ -133,16 +147,96 @@ __global__ void k_copy_interior(Grid g, const double *__restrict__ src, double *
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
+static int comm_allreduce(impec_ctx *ctx, double *buf, int n, int op);
 static int reduce_final(impec_ctx *ctx, int op, long long nparts, int count, long long stride, int scal_idx) {
     double *out = ctx->scal + scal_idx;
     if (op == RED_SUM) LAUNCH_COOP(ctx, k_reduce_final<RED_SUM>, dim3(count), dim3(1024), ctx->part, nparts, stride, out);
     else if (op == RED_MAX) LAUNCH_COOP(ctx, k_reduce_final<RED_MAX>, dim3(count), dim3(1024), ctx->part, nparts, stride, out);
     else LAUNCH_COOP(ctx, k_reduce_final<RED_MIN>, dim3(count), dim3(1024), ctx->part, nparts, stride, out);
-    return IMPEC_OK;
+    return comm_allreduce(ctx, out, count, op);
 }
 static int fetch_scalars(impec_ctx *ctx, int idx, int n) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal + idx, ctx->scal + idx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ communication
+// One process per GPU; fine levels are slabs of rows.  Product build: NCCL point-to-point (halo rows) and tiny
+// collectives on the context stream.  Emulated build: host callbacks supplied by the test harness (gloo).
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+#define NCCL_TRY(ctx, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(ctx, IMPEC_ERR_NCCL, "%s failed: %s", #call, ncclGetErrorString(r_)); } while (0)
+#endif
+static int comm_check(impec_ctx *ctx) {
+    if (ctx->nranks == 1) return IMPEC_OK;
+    if (!ctx->comm_ready) return fail(ctx, IMPEC_ERR_NCCL, "multi-rank context without a communicator (pass an NCCL id or set callbacks)");
+    return IMPEC_OK;
+}
+static int comm_sendrecv(impec_ctx *ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, long long n) {
+    TRY(comm_check(ctx));
+    if (ctx->has_cb) { if (ctx->cb.sendrecv(ctx->cb.user, send_lo, recv_lo, send_hi, recv_hi, n)) return fail(ctx, IMPEC_ERR_NCCL, "sendrecv callback failed"); return IMPEC_OK; }
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    NCCL_TRY(ctx, ncclGroupStart());
+    if (send_lo) { NCCL_TRY(ctx, ncclSend(send_lo, (size_t)n, ncclDouble, ctx->rank - 1, ctx->nccl, ctx->stream)); NCCL_TRY(ctx, ncclRecv(recv_lo, (size_t)n, ncclDouble, ctx->rank - 1, ctx->nccl, ctx->stream)); }
+    if (send_hi) { NCCL_TRY(ctx, ncclSend(send_hi, (size_t)n, ncclDouble, ctx->rank + 1, ctx->nccl, ctx->stream)); NCCL_TRY(ctx, ncclRecv(recv_hi, (size_t)n, ncclDouble, ctx->rank + 1, ctx->nccl, ctx->stream)); }
+    NCCL_TRY(ctx, ncclGroupEnd());
+    return IMPEC_OK;
+#else
+    return fail(ctx, IMPEC_ERR_NCCL, "no communication back end");
+#endif
+}
+static int comm_allreduce(impec_ctx *ctx, double *buf, int n, int op) {
+    if (ctx->nranks == 1) return IMPEC_OK;
+    TRY(comm_check(ctx));
+    if (ctx->has_cb) { if (ctx->cb.allreduce(ctx->cb.user, buf, n, op)) return fail(ctx, IMPEC_ERR_NCCL, "allreduce callback failed"); return IMPEC_OK; }
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    NCCL_TRY(ctx, ncclAllReduce(buf, buf, (size_t)n, ncclDouble, op == RED_SUM ? ncclSum : (op == RED_MAX ? ncclMax : ncclMin), ctx->nccl, ctx->stream));
+    return IMPEC_OK;
+#else
+    return fail(ctx, IMPEC_ERR_NCCL, "no communication back end");
+#endif
+}
+static int comm_allgather(impec_ctx *ctx, const double *send, double *recv, long long n) {
+    TRY(comm_check(ctx));
+    if (ctx->has_cb) { if (ctx->cb.allgather(ctx->cb.user, send, recv, n)) return fail(ctx, IMPEC_ERR_NCCL, "allgather callback failed"); return IMPEC_OK; }
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    NCCL_TRY(ctx, ncclAllGather(send, recv, (size_t)n, ncclDouble, ctx->nccl, ctx->stream));
+    return IMPEC_OK;
+#else
+    return fail(ctx, IMPEC_ERR_NCCL, "no communication back end");
+#endif
+}
+static int comm_bcast(impec_ctx *ctx, double *buf, long long n, int root) {
+    if (ctx->nranks == 1) return IMPEC_OK;
+    TRY(comm_check(ctx));
+    if (ctx->has_cb) { if (ctx->cb.bcast(ctx->cb.user, buf, n, root)) return fail(ctx, IMPEC_ERR_NCCL, "bcast callback failed"); return IMPEC_OK; }
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    NCCL_TRY(ctx, ncclBroadcast(buf, buf, (size_t)n, ncclDouble, root, ctx->nccl, ctx->stream));
+    return IMPEC_OK;
+#else
+    return fail(ctx, IMPEC_ERR_NCCL, "no communication back end");
+#endif
+}
+// Halo rows of a slab field: my first n rows go to the previous rank's rows [N1, N1+n), my last n rows to the next
+// rank's rows [-n, 0).  Works unchanged for face/vertex arrays (their row N1 duplicates the neighbour's row 0).
+static int exchange_rows(impec_ctx *ctx, double *a, const Grid &g, int n) {
+    if (ctx->nranks == 1 || (g.wall_lo && g.wall_hi)) return IMPEC_OK;
+    const size_t ld = (size_t)g.ld;
+    const bool prev = !g.wall_lo, next = !g.wall_hi;
+    return comm_sendrecv(ctx, prev ? a + (size_t)IMPEC_GH * ld : nullptr, prev ? a + (size_t)(IMPEC_GH - n) * ld : nullptr,
+                         next ? a + (size_t)(g.N1 - n + IMPEC_GH) * ld : nullptr, next ? a + (size_t)(g.N1 + IMPEC_GH) * ld : nullptr, (long long)n * g.ld);
+}
+extern "C" int impec_ctx_set_comm_callbacks(impec_ctx *ctx, const impec_comm_callbacks *cb) {
+    if (!cb || !cb->sendrecv || !cb->allreduce || !cb->allgather || !cb->bcast) return fail(ctx, IMPEC_ERR_ARG, "incomplete callback table");
+#ifndef IMPEC_EMU
+    return fail(ctx, IMPEC_ERR_UNSUPPORTED, "host callbacks are for the emulated build; the CUDA library uses NCCL");
+#else
+    ctx->cb = *cb; ctx->has_cb = true; ctx->comm_ready = true;
+    return IMPEC_OK;
+#endif
+}
+extern "C" int impec_local_rows(const impec_ctx *ctx, int *row0, int *nrows) {
+    if (row0) *row0 = ctx->g.i_off; if (nrows) *nrows = ctx->g.N1;
     return IMPEC_OK;
 }
 
@@ -187,7 +281,18 @@ extern "C" int impec_is_emulated(void) {
     return 0;
 #endif
 }
-extern "C" int impec_nccl_unique_id(char id_out[128]) { memset(id_out, 0, 128); return IMPEC_ERR_UNSUPPORTED; }
+extern "C" int impec_nccl_unique_id(char id_out[128]) {
+    memset(id_out, 0, 128);
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    static_assert(sizeof(ncclUniqueId) <= 128, "ncclUniqueId does not fit the ABI buffer");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return IMPEC_ERR_NCCL;
+    memcpy(id_out, &id, sizeof(id));
+    return IMPEC_OK;
+#else
+    return IMPEC_ERR_UNSUPPORTED;
+#endif
+}
 
 extern "C" const char *impec_last_error(const impec_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
@@ -195,13 +300,15 @@ extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->nccl) ncclCommDestroy(ctx->nccl);
+#endif
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int nranks, const char *nccl_unique_id, void *cuda_stream, impec_ctx **out) {
-    (void)nccl_unique_id;
     if (!P || !out) return IMPEC_ERR_ARG;
     *out = nullptr;
     impec_ctx *ctx = new impec_ctx();
@@ -209,7 +316,12 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     ctx->P = *P; ctx->device = device; ctx->rank = rank; ctx->nranks = nranks;
     if (P->g != 2) return fail(ctx, IMPEC_ERR_ARG, "num_ghostcells must be 2 (got %d)", P->g);
     if (P->N1 < 4 || P->N2 < 4) return fail(ctx, IMPEC_ERR_ARG, "grid too small: %d x %d", P->N1, P->N2);
-    if (nranks != 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "multi-GPU slabs not built into this library (nranks=%d)", nranks);
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, IMPEC_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    if (nranks > 1) {
+        if (P->is_test) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "the periodic/manufactured test modes run on one GPU");
+        if (P->dim_splitting != IMPEC_SYMMETRIC_PARALLEL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "multi-GPU transport supports dimensional_splitting = parallel only");
+        if (P->N1 % (2 * nranks) != 0 || P->N1 / nranks < 8) return fail(ctx, IMPEC_ERR_ARG, "x_cells = %d cannot be cut into %d slabs of an even number (>= 8) of rows", P->N1, nranks);
+    }
     if (P->stype == IMPEC_HORIZONTAL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "source_type horizontal is outside the accelerated path");
     if (P->diffusion && P->alpha_l != P->alpha_t) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t gives a non-symmetric CN operator; not supported");
     CUDA_TRY(ctx, cudaSetDevice(device));
@@ -220,8 +332,18 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
 #endif
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (nranks > 1 && nccl_unique_id) {
+        ncclUniqueId id; memcpy(&id, nccl_unique_id, sizeof(id));
+        NCCL_TRY(ctx, ncclCommInitRank(&ctx->nccl, nranks, id, rank));
+        ctx->comm_ready = true;
+    }
+#else
+    (void)nccl_unique_id;
+#endif
     fill_dev_params(ctx);
-    ctx->g = make_grid(P->N1, P->N2);
+    ctx->N1g = P->N1;
+    ctx->g = make_slab(P->N1, P->N2, rank, nranks);
     const size_t n = grid_elems(ctx->g);
     double **fields[] = {&ctx->c, &ctx->p, &ctx->q, &ctx->u, &ctx->v, &ctx->MU, &ctx->KV11, &ctx->r, &ctx->z, &ctx->d, &ctx->s, &ctx->rhs, &ctx->t0};
     for (double **f : fields) TRY(dev_alloc(ctx, f, n));
@@ -232,9 +354,18 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     const int nmin = P->mg_nmin > 1 ? P->mg_nmin : 2;
     while ((a % 2 == 0) && (b % 2 == 0) && std::min(a, b) > nmin && (P->mg_max_levels <= 0 || nl < P->mg_max_levels)) { a /= 2; b /= 2; nl++; }
     ctx->L.resize(nl);
-    for (int l = 0; l < nl; l++) {
+    // distributed levels: as long as every slab keeps an even number (>= 8) of rows; the coarsest level is always replicated
+    ctx->Ld = 0;
+    if (nranks > 1) { int rows = P->N1; while (ctx->Ld < nl - 1 && rows % (2 * nranks) == 0 && rows / nranks >= 8) { ctx->Ld++; rows /= 2; } }
+    for (int l = 0, n1 = P->N1, n2 = P->N2; l < nl; l++, n1 /= 2, n2 /= 2) {
         Level &L = ctx->L[l];
-        L.g = (l == 0) ? ctx->g : make_grid(ctx->L[l - 1].g.N1 / 2, ctx->L[l - 1].g.N2 / 2);
+        L.dist = l < ctx->Ld;
+        L.g = L.dist ? make_slab(n1, n2, rank, nranks) : make_grid(n1, n2);
+        if (l == ctx->Ld && nranks > 1) {
+            L.gl = make_slab(n1, n2, rank, nranks);
+            const size_t ns = grid_elems(L.gl);
+            TRY(dev_alloc(ctx, &L.AWl, ns)); TRY(dev_alloc(ctx, &L.ASl, ns)); TRY(dev_alloc(ctx, &L.AVl, ns)); TRY(dev_alloc(ctx, &L.fl, ns));
+        } else L.gl = L.g;
         const size_t nn = grid_elems(L.g);
         TRY(dev_alloc(ctx, &L.AW, nn)); TRY(dev_alloc(ctx, &L.AS, nn)); TRY(dev_alloc(ctx, &L.AV, nn)); TRY(dev_alloc(ctx, &L.DINV, nn));
         if (l == 0) { L.x = ctx->z; L.f = ctx->r; L.t = ctx->t0; L.r = ctx->s; }
@@ -242,11 +373,11 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     }
     // pinned cell (1,1): src/MGSolver.cpp:109-118
     int pi = 1, pj = 1;
-    ctx->L[0].pin = (long long)gidx(ctx->g, pi, pj);
-    for (int l = 1; l < nl; l++) { pi >>= 1; pj >>= 1; ctx->L[l].sig_idx = (long long)gidx(ctx->L[l].g, pi, pj); }
+    ctx->L[0].pin = (rank == 0) ? (long long)gidx(ctx->g, pi, pj) : -1;
+    for (int l = 1; l < nl; l++) { pi >>= 1; pj >>= 1; ctx->L[l].sig_idx = (rank == 0 || !ctx->L[l].dist) ? (long long)gidx(ctx->L[l].g, pi, pj) : -1; }
     TRY(dev_alloc(ctx, &ctx->sigma_dev, (size_t)nl + 1));
     // reductions
-    const dim3 gg = grid2d(P->N2 + 2, P->N1 + 2);
+    const dim3 gg = grid2d(P->N2 + 2, ctx->g.N1 + 2);
     ctx->part_cap = (long long)gg.x * gg.y;
     TRY(dev_alloc(ctx, &ctx->part, (size_t)ctx->part_cap * 4));
     TRY(dev_alloc(ctx, &ctx->scal, S_NSCAL));
@@ -277,6 +408,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
 }
 
 // ------------------------------------------------------------------------------------------------ transfers
+// `host` points at the slab's first ghost row: row -ng of the slab = global row i_off - ng
 static int upload_scalar(impec_ctx *ctx, double *dst, const double *host) {
     const Grid &g = ctx->g; const int ng = ctx->P.g;
     const size_t w = (size_t)(g.N2 + 2 * ng) * sizeof(double);
@@ -290,13 +422,17 @@ static int download_scalar(impec_ctx *ctx, const double *src, double *host) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return IMPEC_OK;
 }
-extern "C" int impec_upload_c(impec_ctx *ctx, const double *h) { ctx->mob_valid = ctx->op_valid = false; return upload_scalar(ctx, ctx->c, h); }
-extern "C" int impec_upload_p(impec_ctx *ctx, const double *h) { return upload_scalar(ctx, ctx->p, h); }
-extern "C" int impec_download_c(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->c, h); }
-extern "C" int impec_download_p(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->p, h); }
+static size_t slab_off(const impec_ctx *ctx) { return (size_t)ctx->g.i_off * (size_t)(ctx->g.N2 + 2 * ctx->P.g); }
+extern "C" int impec_upload_c(impec_ctx *ctx, const double *h) { ctx->mob_valid = ctx->op_valid = false; return upload_scalar(ctx, ctx->c, h + slab_off(ctx)); }
+extern "C" int impec_upload_p(impec_ctx *ctx, const double *h) { return upload_scalar(ctx, ctx->p, h + slab_off(ctx)); }
+extern "C" int impec_download_c(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->c, h + slab_off(ctx)); }
+extern "C" int impec_download_p(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->p, h + slab_off(ctx)); }
+extern "C" int impec_upload_c_rows(impec_ctx *ctx, const double *h) { ctx->mob_valid = ctx->op_valid = false; return upload_scalar(ctx, ctx->c, h); }
+extern "C" int impec_download_c_rows(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->c, h); }
 
+// q: this rank's rows (N1loc x N2)
 static int rebuild_wells(impec_ctx *ctx, const double *q) {
-    const int N1 = ctx->P.N1, N2 = ctx->P.N2;
+    const int N1 = ctx->g.N1, N2 = ctx->P.N2;
     std::vector<int> wi, wj; std::vector<double> wq;
     for (int i = 0; i < N1; i++)
         for (int j = 0; j < N2; j++) {
@@ -304,7 +440,7 @@ static int rebuild_wells(impec_ctx *ctx, const double *q) {
             if (v != 0.0) { wi.push_back(i); wj.push_back(j); wq.push_back(v); }
         }
     ctx->nwell = (int)wq.size();
-    ctx->q_pin = (N1 > 1 && N2 > 1) ? q[(size_t)1 * N2 + 1] : 0.0;
+    ctx->q_pin = (ctx->rank == 0 && N1 > 1 && N2 > 1) ? q[(size_t)1 * N2 + 1] : 0.0;
     if (ctx->nwell) {
         void *p;
         CUDA_TRY(ctx, cudaMalloc(&p, sizeof(int) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_i = (int *)p;
@@ -319,12 +455,13 @@ static int rebuild_wells(impec_ctx *ctx, const double *q) {
     ctx->have_q = true;
     return IMPEC_OK;
 }
-extern "C" int impec_upload_q(impec_ctx *ctx, const double *q) {
+extern "C" int impec_upload_q_rows(impec_ctx *ctx, const double *q) {
     const Grid &g = ctx->g;
     const size_t w = (size_t)g.N2 * sizeof(double);
     CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->q + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), q, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
     return rebuild_wells(ctx, q);
 }
+extern "C" int impec_upload_q(impec_ctx *ctx, const double *q) { return impec_upload_q_rows(ctx, q + (size_t)ctx->g.i_off * ctx->g.N2); }
 extern "C" int impec_set_q_dev_changed(impec_ctx *ctx) {
     const Grid &g = ctx->g;
     std::vector<double> q((size_t)g.N1 * g.N2);
@@ -337,6 +474,7 @@ extern "C" int impec_upload_velocity(impec_ctx *ctx, const double *v_aos) {
     const Grid &g = ctx->g; const int ng = ctx->P.g;
     const int H = g.N1 + 1 + 2 * ng, W = g.N2 + 1 + 2 * ng;
     const long long n = (long long)H * W;
+    v_aos += (size_t)g.i_off * W * 2;                                          // this rank's rows of the global array
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ta, v_aos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(ctx, k_deinterleave, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->ta, H, W, ctx->u, ctx->v, ng);
     return IMPEC_OK;
@@ -346,6 +484,7 @@ extern "C" int impec_download_velocity(impec_ctx *ctx, double *v_aos) {
     const int H = g.N1 + 1 + 2 * ng, W = g.N2 + 1 + 2 * ng;
     const long long n = (long long)H * W;
     LAUNCH(ctx, k_interleave, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->ta, H, W, ctx->u, ctx->v, ng);
+    v_aos += (size_t)g.i_off * W * 2;
     CUDA_TRY(ctx, cudaMemcpyAsync(v_aos, ctx->ta, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return IMPEC_OK;
@@ -368,7 +507,10 @@ static int fill_scalar(impec_ctx *ctx, double *a, int periodic) {
     LAUNCH(ctx, k_fill_scalar, dim3((unsigned)((total + 255) / 256)), dim3(256), g, a, periodic, ng);
     return IMPEC_OK;
 }
-extern "C" int impec_fill_boundaries(impec_ctx *ctx) { return fill_scalar(ctx, ctx->c, ctx->P.is_test ? 1 : 0); }
+extern "C" int impec_fill_boundaries(impec_ctx *ctx) {
+    TRY(fill_scalar(ctx, ctx->c, ctx->P.is_test ? 1 : 0));
+    return exchange_rows(ctx, ctx->c, ctx->g, ctx->P.g);          // halo rows (with their ghost columns) from the neighbouring slabs
+}
 
 // ------------------------------------------------------------------------------------------------ a2-a8 operator
 static LevelDev level_dev(const impec_ctx *ctx, int l, double mass) {
@@ -396,14 +538,26 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
     Level &L0 = ctx->L[0];
     if (ctx->P.is_test) LAUNCH(ctx, k_links<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
     else LAUNCH(ctx, k_links<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
+    if (L0.dist) { TRY(exchange_rows(ctx, L0.AW, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AS, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AV, L0.g, IMPEC_GH)); }
     for (size_t l = 1; l < ctx->L.size(); l++) {
         Level &F = ctx->L[l - 1], &C = ctx->L[l];
+        if ((int)l == ctx->Ld && ctx->nranks > 1) {
+            // first replicated level: coarsen this rank's slab, then all-gather the rows into the global arrays
+            LAUNCH(ctx, k_coarsen_links, grid2d(C.gl.N2 + 1, C.gl.N1 + 1), kBlock, F.g, F.AW, F.AS, F.AV, C.gl, C.AWl, C.ASl, C.AVl);
+            const long long n = (long long)C.gl.N1 * C.gl.ld;
+            const size_t r0 = (size_t)IMPEC_GH * C.gl.ld;
+            TRY(comm_allgather(ctx, C.AWl + r0, C.AW + r0, n)); TRY(comm_allgather(ctx, C.ASl + r0, C.AS + r0, n)); TRY(comm_allgather(ctx, C.AVl + r0, C.AV + r0, n));
+            continue;
+        }
         LAUNCH(ctx, k_coarsen_links, grid2d(C.g.N2 + 1, C.g.N1 + 1), kBlock, F.g, F.AW, F.AS, F.AV, C.g, C.AW, C.AS, C.AV);
+        if (C.dist) { TRY(exchange_rows(ctx, C.AW, C.g, IMPEC_GH)); TRY(exchange_rows(ctx, C.AS, C.g, IMPEC_GH)); TRY(exchange_rows(ctx, C.AV, C.g, IMPEC_GH)); }
     }
-    LAUNCH(ctx, k_pin_sigma, dim3(1), dim3(1), g, L0.AW, L0.AS, L0.AV, 1, 1, (int)ctx->L.size(), ctx->sigma_dev);
+    if (ctx->rank == 0) LAUNCH(ctx, k_pin_sigma, dim3(1), dim3(1), g, L0.AW, L0.AS, L0.AV, 1, 1, (int)ctx->L.size(), ctx->sigma_dev);
+    TRY(comm_bcast(ctx, ctx->sigma_dev, (long long)ctx->L.size(), 0));
     for (size_t l = 0; l < ctx->L.size(); l++) {
         Level &L = ctx->L[l];
         LAUNCH(ctx, k_diag_inv, grid2d(L.g.N2, L.g.N1), kBlock, level_dev(ctx, (int)l, 0.0), (const double *)(ctx->sigma_dev + l), L.DINV);
+        if (L.dist) TRY(exchange_rows(ctx, L.DINV, L.g, IMPEC_GH));
     }
     ctx->op_valid = true;
     return IMPEC_OK;
@@ -451,16 +605,31 @@ static int fused_plain(Cycle &C, int l, const double *f, bool forward) {
     std::swap(L.x, L.t);
     return IMPEC_OK;
 }
+// coarse-level view seen from a distributed level: a slab grid, and the matching window of a replicated array
+static bool at_transition(const impec_ctx *ctx, int l) { return ctx->nranks > 1 && l + 1 == ctx->Ld; }
+static const double *coarse_x_view(const impec_ctx *ctx, int l) {
+    const Level &Lc = ctx->L[l + 1];
+    return at_transition(ctx, l) ? Lc.x + (size_t)Lc.gl.i_off * Lc.gl.ld : Lc.x;
+}
 static int fused_pre(Cycle &C, int l, const double *f) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
-    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_PRE>, fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, Lc.g,
-                     (const double *)nullptr, Lc.f, (double *)nullptr);
+    const bool tr = at_transition(ctx, l);
+    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_PRE>, fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
+                     (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
     return IMPEC_OK;
+}
+// restricted right-hand side of the first replicated level: all-gather the slabs
+static int gather_coarse_rhs(impec_ctx *ctx, int l) {
+    if (!at_transition(ctx, l)) return IMPEC_OK;
+    Level &Lc = ctx->L[l + 1];
+    const size_t r0 = (size_t)IMPEC_GH * Lc.gl.ld;
+    return comm_allgather(ctx, Lc.fl + r0, Lc.f + r0, (long long)Lc.gl.N1 * Lc.gl.ld);
 }
 static int fused_post(Cycle &C, int l, const double *f, double *part, long long *nparts) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
     const dim3 gr = fused_grid<FUSED_POST>(L.g);
-    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_POST>, gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, Lc.g, (const double *)Lc.x, (double *)nullptr, part);
+    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_POST>, gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
+                     coarse_x_view(ctx, l), (double *)nullptr, part);
     std::swap(L.x, L.t);
     if (nparts) *nparts = (long long)gr.x * gr.y;
     return IMPEC_OK;
@@ -478,7 +647,11 @@ static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr
     if (l == nl - 1) {
         if (fused) {
             CUDA_TRY(ctx, cudaMemsetAsync(L.x, 0, grid_elems(L.g) * sizeof(double), ctx->stream));
-            for (int s = 0; s < C.ncoarse; s++) { TRY(fused_plain(C, l, f, true)); TRY(fused_plain(C, l, f, false)); }
+            if (L.dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
+            for (int s = 0; s < C.ncoarse; s++) {
+                TRY(fused_plain(C, l, f, true));  if (L.dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
+                TRY(fused_plain(C, l, f, false)); if (L.dist && s + 1 < C.ncoarse) TRY(exchange_rows(ctx, L.x, L.g, 2));
+            }
         } else
             for (int s = 0; s < C.ncoarse; s++) { TRY(smooth(C, l, f, x, true, s == 0)); TRY(smooth(C, l, f, x, false, false)); }
         return IMPEC_OK;
@@ -486,18 +659,31 @@ static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr
     Level &Lc = ctx->L[l + 1];
     const int gamma = (l >= C.w_from && l <= C.w_to) ? 2 : 1;
     if (fused) {
+        // On a slab level every kernel that reads a field with a halo is preceded by the exchange of exactly the rows it
+        // reads (f: 3, x: 2); with the halos in place each rank computes the same values a single GPU would.
+        const bool dist = L.dist, tr = at_transition(ctx, l);
+        if (dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
         TRY(fused_pre(C, l, f));                                      // pre-smooth(0) + residual + restrict
+        if (dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
+        TRY(gather_coarse_rhs(ctx, l));
         TRY(mg_cycle(C, l + 1, Lc.f));
+        if (Lc.dist) TRY(exchange_rows(ctx, Lc.x, Lc.g, 2));
         for (int gc = 1; gc < gamma; gc++) {
             TRY(fused_post(C, l, f, nullptr, nullptr));               // prolong + correct + backward sweep
+            if (dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
             TRY(fused_plain(C, l, f, true));
-            LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1), kBlock, C.D[l], f, (const double *)L.x, L.r);
-            LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L.g, L.r, Lc.g, Lc.f);
+            if (dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
+            LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1 + 2), kBlock, C.D[l], f, (const double *)L.x, L.r);
+            if (tr) LAUNCH(ctx, k_restrict, grid2d(Lc.gl.N2, Lc.gl.N1), kBlock, L.g, L.r, Lc.gl, Lc.fl);
+            else LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L.g, L.r, Lc.g, Lc.f);
+            TRY(gather_coarse_rhs(ctx, l));
             TRY(mg_cycle(C, l + 1, Lc.f));
+            if (Lc.dist) TRY(exchange_rows(ctx, Lc.x, Lc.g, 2));
         }
         TRY(fused_post(C, l, f, dot_part, dot_nparts));               // prolong + correct + post-smooth (+ <f,x>)
         return IMPEC_OK;
     }
+    if (ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "the per-colour (mg_fused = 0) path is single-GPU only");
     TRY(smooth(C, l, f, x, true, true));
     for (int gc = 0; gc < gamma; gc++) {
         LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1), kBlock, C.D[l], f, x, L.r);
@@ -528,12 +714,12 @@ extern "C" int impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host
     const Grid &g = ctx->g;
     const size_t w = (size_t)g.N2 * sizeof(double);
     if (r_host) {
-        CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->r + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), r_host, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->r + ctx->L[0].pin, 0.0);
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->r + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), r_host + (size_t)g.i_off * g.N2, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->L[0].pin >= 0) LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->r + ctx->L[0].pin, 0.0);
     }
     TRY(mg_cycle(C, 0, ctx->r));
     if (z_host) {
-        CUDA_TRY(ctx, cudaMemcpy2DAsync(z_host, w, ctx->L[0].x + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), w, (size_t)g.N1, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(z_host + (size_t)g.i_off * g.N2, w, ctx->L[0].x + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), w, (size_t)g.N1, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return IMPEC_OK;
@@ -564,7 +750,9 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
     const dim3 gr = grid2d(g.N2, g.N1);
     const long long nparts = (long long)gr.x * gr.y;
     const LevelDev &A = C.D[0];
-    LAUNCH(ctx, k_residual, gr, kBlock, A, rhs, (const double *)x, ctx->r);
+    const dim3 gres = grid2d(g.N2, g.N1 + 2);                    // k_residual also fills one halo row per neighbouring slab
+    TRY(exchange_rows(ctx, x, g, 2));
+    LAUNCH(ctx, k_residual, gres, kBlock, A, rhs, (const double *)x, ctx->r);
     LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->r, ctx->part);
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_IPROD));
     TRY(fetch_scalars(ctx, S_IPROD, 3));                         // S_IPROD .. S_BIPROD
@@ -583,6 +771,7 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
     }
     while (!converged && it < ctx->P.max_iter) {
         it++;
+        TRY(exchange_rows(ctx, ctx->d, g, 1));
         LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, A, ctx->d, ctx->s, ctx->part);
         TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_SDOTP));
         // alpha = gamma / <s,d>: the kernel reads scal[0]/scal[1], so gamma must sit in slot 0
@@ -602,7 +791,8 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         ig = S_BETA_NUM;
     }
     // true residual with the final x
-    LAUNCH(ctx, k_residual, gr, kBlock, A, rhs, (const double *)x, ctx->s);
+    TRY(exchange_rows(ctx, x, g, 2));
+    LAUNCH(ctx, k_residual, gres, kBlock, A, rhs, (const double *)x, ctx->s);
     LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->s, ctx->s, ctx->part);
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_TMP));
     TRY(fetch_scalars(ctx, S_TMP, 1));
@@ -649,10 +839,13 @@ extern "C" int impec_calc_velocities(impec_ctx *ctx) {
     const Grid &g = ctx->g; const int ng = ctx->P.g;
     if (!ctx->mob_valid) TRY(build_mobility(ctx));
     TRY(fill_scalar(ctx, ctx->p, 0));                               // src/EllipticSolver.cpp:663
+    TRY(exchange_rows(ctx, ctx->p, g, ng));
     if (ctx->P.is_test) LAUNCH(ctx, k_velocity<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->p, ctx->MU, ctx->KV11, ctx->KV22, ctx->u, ctx->v, ctx->D);
     else LAUNCH(ctx, k_velocity<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->p, ctx->MU, ctx->KV11, ctx->KV22, ctx->u, ctx->v, ctx->D);
     const long long n = (long long)(g.N1 + 1 + 2 * ng) * (g.N2 + 1 + 2 * ng);
     LAUNCH(ctx, k_fill_velocity, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->u, ctx->v, ng);   // :682
+    TRY(exchange_rows(ctx, ctx->u, g, ng + 1));                     // u row N1 is the neighbour's row 0; N1+1, N1+2 are its rows 1, 2
+    TRY(exchange_rows(ctx, ctx->v, g, ng));
     return IMPEC_OK;
 }
 
@@ -689,11 +882,18 @@ extern "C" int impec_max_stable_dt(impec_ctx *ctx, double *dt) {
 // ------------------------------------------------------------------------------------------------ a15 source
 extern "C" int impec_source_split(impec_ctx *ctx, double dt) {
     if (!ctx->have_q) return fail(ctx, IMPEC_ERR_ARG, "source step before impec_upload_q");
-    if (ctx->nwell == 0) return IMPEC_OK;
+    if (ctx->nwell == 0) {
+        if (ctx->nranks == 1) return IMPEC_OK;
+        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_SRC, 0.0);      // a slab without wells still joins the sum
+        TRY(comm_allreduce(ctx, ctx->scal + S_SRC, 1, RED_SUM));
+        LAUNCH(ctx, k_accum_abs, dim3(1), dim3(1), ctx->scal + S_SRC, ctx->scal + S_OUTFLUX);
+        return IMPEC_OK;
+    }
     ctx->mob_valid = ctx->op_valid = false;
     LAUNCH(ctx, k_source_tr, dim3((unsigned)((ctx->nwell + 255) / 256)), dim3(256), ctx->nwell, ctx->well_i, ctx->well_j, ctx->well_q, ctx->g, ctx->c,
            dt, ctx->P.inj_fluid_conc, ctx->well_md);
     LAUNCH_COOP(ctx, k_reduce_final<RED_SUM>, dim3(1), dim3(1024), ctx->well_md, (long long)ctx->nwell, 0LL, ctx->scal + S_SRC);
+    TRY(comm_allreduce(ctx, ctx->scal + S_SRC, 1, RED_SUM));
     LAUNCH(ctx, k_accum_abs, dim3(1), dim3(1), ctx->scal + S_SRC, ctx->scal + S_OUTFLUX);
     return IMPEC_OK;
 }
@@ -774,9 +974,11 @@ extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info
     Level &L0 = ctx->L[0];
     ctx->op_valid = false; ctx->mob_valid = false;          // the level-0 link arrays are reused for the parabolic operator
     LAUNCH(ctx, k_disp_links, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, (const double *)ctx->u, (const double *)ctx->v, dt, ctx->D, L0.AW, L0.AS, L0.AV);
+    if (L0.dist) { TRY(exchange_rows(ctx, L0.AW, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AS, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AV, L0.g, IMPEC_GH)); }
     LevelDev A = level_dev(ctx, 0, 1.0);
     A.pin = -1; A.sig_idx = -1;
     LAUNCH(ctx, k_diag_inv, gr, kBlock, A, (const double *)nullptr, L0.DINV);
+    if (L0.dist) TRY(exchange_rows(ctx, L0.DINV, L0.g, IMPEC_GH));
     Cycle C; C.ctx = ctx; C.D.assign(1, A); C.ncoarse = 1; C.w_from = 1; C.w_to = 0; C.nl = 1;
     double *x = ctx->ta;
     LAUNCH_COOP(ctx, k_cn_rhs, gr, kBlock, A, (const double *)ctx->c, ctx->rhs, x, ctx->part);
@@ -820,6 +1022,8 @@ extern "C" int impec_diagnostics(impec_ctx *ctx, impec_diag *out) {
     TRY(reduce_final(ctx, RED_SUM, nparts, 2, ctx->part_cap, S_DIAG));
     LAUNCH_COOP(ctx, k_reduce_final<RED_MAX>, dim3(1), dim3(1024), ctx->part + 2 * ctx->part_cap, nparts, 0LL, ctx->scal + S_DIAG + 2);
     LAUNCH_COOP(ctx, k_reduce_final<RED_MIN>, dim3(1), dim3(1024), ctx->part + 3 * ctx->part_cap, nparts, 0LL, ctx->scal + S_DIAG + 3);
+    TRY(comm_allreduce(ctx, ctx->scal + S_DIAG + 2, 1, RED_MAX));
+    TRY(comm_allreduce(ctx, ctx->scal + S_DIAG + 3, 1, RED_MIN));
     const int nb = (std::max(g.N1, g.N2) + 255) / 256;
     LAUNCH_COOP(ctx, k_diag_boundary, dim3(nb), dim3(256), g, ctx->u, ctx->v, ctx->part);
     TRY(reduce_final(ctx, RED_SUM, nb, 1, 0, S_DIAG + 4));

@@ -79,6 +79,17 @@ typedef struct impec_solve_info {
 
 typedef struct impec_ctx impec_ctx;
 
+/* Communication back end for host-memory builds (the CPU-emulated test library): the product library talks NCCL itself.
+ * All buffers are host pointers.  op: 0 sum, 1 max, 2 min.  Return 0 on success. */
+typedef struct impec_comm_callbacks {
+    void *user;
+    /* send n doubles to rank-1 (send_lo) and rank+1 (send_hi), receive n from each; NULL where there is no neighbour */
+    int (*sendrecv)(void *user, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, long long n);
+    int (*allreduce)(void *user, double *buf, int n, int op);
+    int (*allgather)(void *user, const double *send, double *recv, long long n_per_rank);
+    int (*bcast)(void *user, double *buf, long long n, int root);
+} impec_comm_callbacks;
+
 void  impec_default_params(impec_params *p);
 const char *impec_version(void);
 int   impec_is_emulated(void);        /* 1 only for the CPU-emulated test build (never shipped)    */
@@ -92,6 +103,9 @@ int   impec_ctx_create(const impec_params *p, int device, int rank, int nranks, 
 void  impec_ctx_destroy(impec_ctx *ctx);
 const char *impec_last_error(const impec_ctx *ctx);
 int   impec_synchronize(impec_ctx *ctx);
+int   impec_ctx_set_comm_callbacks(impec_ctx *ctx, const impec_comm_callbacks *cb);
+/* slab owned by this context: rows [row0, row0 + nrows) of the global grid (everything when nranks == 1) */
+int   impec_local_rows(const impec_ctx *ctx, int *row0, int *nrows);
 
 /* host <-> device, reference layouts (Impec2DSolver owns p,c,v,q: src/Impec2DSolver.h:31-46) */
 int   impec_upload_c(impec_ctx *ctx, const double *c_ghosted);
@@ -101,6 +115,11 @@ int   impec_upload_velocity(impec_ctx *ctx, const double *v_aos);
 int   impec_download_c(impec_ctx *ctx, double *c_ghosted);
 int   impec_download_p(impec_ctx *ctx, double *p_ghosted);
 int   impec_download_velocity(impec_ctx *ctx, double *v_aos);
+/* Multi-rank note: upload/download take the GLOBAL host arrays and move only this rank's slab (plus its ghost rows);
+ * the *_rows variants take just the slab: c,p as (nrows+2g) x (N2+2g), q as nrows x N2. */
+int   impec_upload_c_rows(impec_ctx *ctx, const double *c_slab_ghosted);
+int   impec_upload_q_rows(impec_ctx *ctx, const double *q_slab);
+int   impec_download_c_rows(impec_ctx *ctx, double *c_slab_ghosted);
 /* device-resident alternatives for callers that already hold device memory (padded layout) */
 int   impec_field_layout(const impec_ctx *ctx, int *ld, int *row0, int *col0, int *rows);
 void *impec_field_dev(impec_ctx *ctx, const char *name);   /* "c","p","q","u","v" */
@@ -147,6 +166,9 @@ int   impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, double *a
 int   impec_init_source(const impec_params *p, double I, double well_rc, int well_profile, double *q);
 /* developed synthetic concentration for benchmarks; writes the interior of a ghosted array */
 int   impec_synth_state(const impec_params *p, unsigned long long seed, double *c_ghosted);
+/* the same restricted to global rows [row0, row0+nrows): q_slab is nrows x N2, c_slab_ghosted is (nrows+2g) x (N2+2g) */
+int   impec_init_source_rows(const impec_params *p, double I, double well_rc, int well_profile, int row0, int nrows, double *q_slab);
+int   impec_synth_state_rows(const impec_params *p, unsigned long long seed, int row0, int nrows, double *c_slab_ghosted);
 
 #ifdef __cplusplus
 }

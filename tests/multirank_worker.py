@@ -1,0 +1,58 @@
+"""Worker for tests/test_multirank.py: one process per rank (gloo), CPU-emulated kernel library.  Runs the same
+problem on nranks slabs and, on every rank, also on a single-rank context; the slab result must agree with this
+rank's rows of the single-rank result."""
+import os
+import sys
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import impec2d_b200 as I   # noqa: E402
+import oracle as O         # noqa: E402
+from helpers import production_case   # noqa: E402
+
+
+def main():
+    N1, N2, stype, diffusion, steps = (int(x) for x in sys.argv[1:6])
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=diffusion, eps=1e-12)
+    Pi = I.default_params(emulated=True, **base)
+
+    ref = I.Context(Pi, emulated=True)                      # single-rank reference (same library, same kernels)
+    ref.upload_c(c); ref.upload_q(q)
+    ctx = I.Context(Pi, rank=rank, nranks=world, emulated=True)
+    I.attach_torch_comm(ctx, rank, world)
+    ctx.upload_c(c); ctx.upload_q(q)
+    r0, n = ctx.local_rows()
+    assert n == N1 // world and r0 == rank * n
+    g = Pi.g
+    t = 0.0
+    for s in range(steps):
+        dt_ref, info_ref = ref.impes_step(t, 0.0)
+        dt, info = ctx.impes_step(t, 0.0)
+        assert abs(dt - dt_ref) <= 1e-10 * dt_ref, (dt, dt_ref)
+        assert info.converged == 1 and abs(info.iterations - info_ref.iterations) <= 1, (info.iterations, info_ref.iterations)
+        t += dt_ref
+    cg = np.zeros_like(c); pg = np.zeros_like(c)
+    ctx.download_c(cg); ctx.download_p(pg)
+    cr = ref.download_c(); pr = ref.download_p()
+    rows = slice(g + r0, g + r0 + n)
+    dc = np.abs(cg[rows, g:-g] - cr[rows, g:-g]).max()
+    dp = np.abs(pg[rows, g:-g] - pr[rows, g:-g]).max() / np.abs(pr).max()
+    d = ctx.diagnostics(); dr = ref.diagnostics()
+    assert dc <= 1e-9, dc
+    assert dp <= 1e-9, dp
+    assert abs(d.total_mass - dr.total_mass) <= 1e-9 * dr.total_mass
+    assert abs(d.total_mass_outflux - dr.total_mass_outflux) <= 1e-9 * max(dr.total_mass_outflux, 1e-30)
+    assert abs(d.c_max - dr.c_max) <= 1e-9 and abs(d.c_min - dr.c_min) <= 1e-9, (d.c_max, dr.c_max)
+    assert abs(d.divergence_error - dr.divergence_error) <= 1e-9 + 1e-3 * dr.divergence_error, (d.divergence_error, dr.divergence_error)
+    assert abs(d.boundary_velocity_error - dr.boundary_velocity_error) <= 1e-9, (d.boundary_velocity_error, dr.boundary_velocity_error)
+    print("rank %d ok: dc %.2e dp %.2e its %d/%d levels %d" % (rank, dc, dp, info.iterations, info_ref.iterations, ctx.mg_levels()), flush=True)
+    ctx.close(); ref.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

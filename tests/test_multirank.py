@@ -1,0 +1,24 @@
+"""Slab decomposition across ranks on CPU: world_size-2 and -4 gloo runs of the emulated kernel library.
+Each rank owns N1/P rows; halo rows travel by send/recv, norms by all-reduce, the first replicated multigrid level by
+all-gather.  The slab run must reproduce the single-rank run (same kernels) to 1e-9."""
+import os
+import subprocess
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(world, N1, N2, stype, diffusion, steps, port):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "impec2d_b200", "csrc"), "emu"])
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multirank_worker.py"), str(N1), str(N2), str(stype), str(diffusion), str(steps)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count(" ok: ") == world, out.stdout
+
+
+def test_two_ranks_parallel_cfg(): run(2, 64, 64, 0, 0, 2, 29611)
+def test_two_ranks_rect_diagonal_with_dispersion(): run(2, 64, 32, 1, 1, 1, 29612)
+def test_four_ranks(): run(4, 128, 64, 1, 0, 1, 29613)
