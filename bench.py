@@ -159,17 +159,28 @@ def main():
     stream = torch.cuda.current_stream()
 
     P = workload_params(N, args.eps, I)
-    # host inputs in pinned memory (reference layouts)
-    shape = (N + 2 * P.g, N + 2 * P.g)
+    # one process per GPU; rank r owns rows [r N/P, (r+1) N/P) (slab decomposition along x).  The NCCL communicator of
+    # the library is bootstrapped with an id broadcast over torch.distributed.
+    nccl_id = None
+    if world > 1:
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            rc = I.load().impec_nccl_unique_id(idbuf)
+            assert rc == 0, "impec_nccl_unique_id failed (%d)" % rc
+        idt = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, src=0)
+        nccl_id = bytes(idt.cpu().tolist())
+    ctx = I.Context(P, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id, stream=C.c_void_p(stream.cuda_stream))
+    row0, nrows = ctx.local_rows()
+    # host inputs in pinned memory (reference layouts, this rank's rows)
+    shape = (nrows + 2 * P.g, N + 2 * P.g)
     c_host_t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
-    q_host_t = torch.empty(N * N, dtype=torch.float64, pin_memory=True)
+    q_host_t = torch.empty(nrows * N, dtype=torch.float64, pin_memory=True)
     c_host = c_host_t.numpy(); q_host = q_host_t.numpy()
     c_host[...] = 0.0
-    I.synth_state(P, 20260917, out=c_host)
-    q_host[...] = I.init_source(P, 1.0, 0.05, 0)
-
-    ctx = I.Context(P, device=local_rank, stream=C.c_void_p(stream.cuda_stream))
-    ctx.upload_c(c_host); ctx.upload_q(q_host)
+    I.synth_state_rows(P, row0, nrows, 20260917, out=c_host)
+    q_host[...] = I.init_source_rows(P, row0, nrows, 1.0, 0.05, 0)
+    ctx.upload_c_rows(c_host); ctx.upload_q_rows(q_host)
     ctx.synchronize()
 
     def barrier():
@@ -199,8 +210,7 @@ def main():
     if world > 1:
         tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms_total = float(tt.item())
-    # slab decomposition is not built yet: N > 1 runs one replica per GPU (reported as such)
-    cells_all = N * N * K * world
+    cells_all = N * N * K                           # whole job: the grid is cut into slabs, total work is fixed
     value = cells_all / (ms_total * 1e-3) / 1e9
 
     # ------------------------------------------------------------------ per-kernel device times (CUDA events, live)
@@ -241,15 +251,15 @@ def main():
     # ------------------------------------------------------------------ end-to-end through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
-        ctx.download_c(c_host)
+        ctx.download_c_rows(c_host)
         barrier()
         t0 = time.perf_counter()
         f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         for _ in range(K):
-            ctx.upload_c(c_host); ctx.upload_q(q_host)
+            ctx.upload_c_rows(c_host); ctx.upload_q_rows(q_host)
             dt, info = ctx.impes_step(t, 0.0); t += dt
-            ctx.download_c(c_host)
+            ctx.download_c_rows(c_host)
         f1.record(stream)
         barrier()
         ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
@@ -257,7 +267,7 @@ def main():
             tt = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms_e2e = float(tt.item())
         e2e = {"value": cells_all / (ms_e2e * 1e-3) / 1e9, "unit": "Gcell-updates/s",
-               "h2d_bytes_per_step": int(c_host.nbytes + q_host.nbytes), "d2h_bytes_per_step": int(c_host.nbytes), "ms_per_step": ms_e2e / K}
+               "h2d_bytes_per_step": int(c_host.nbytes + q_host.nbytes) * world, "d2h_bytes_per_step": int(c_host.nbytes) * world, "ms_per_step": ms_e2e / K}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -269,10 +279,10 @@ def main():
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True,
-                "scaling": "strong" if world == 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "grid": [N, N], "eps": args.eps, "stop_rule": "<r,r>/<b,b> < eps^2, recurrence residual, x0 = 0 (HYPRE StructPCG semantics)",
                            "pcg_iterations": its, "relres": relres, "true_relres": true_rr, "mg_levels": ctx.mg_levels(),
-                           "parallelism": "1 GPU" if world == 1 else "replicas x%d (slab decomposition not built yet)" % world,
+                           "parallelism": "1 GPU" if world == 1 else "%d slabs of %d rows (halo send/recv over NCCL; multigrid levels below %d rows per slab replicated after an all-gather)" % (world, nrows, 8),
                            "l2": "inputs larger than L2 (every field is %.2f GB)" % (8.0 * N * N / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "vcycle_ms": prof["vcycle"]}

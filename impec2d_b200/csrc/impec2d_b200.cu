@@ -331,6 +331,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_coarse_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
 #endif
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
     if (nranks > 1 && nccl_unique_id) {
@@ -356,7 +357,14 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     ctx->L.resize(nl);
     // distributed levels: as long as every slab keeps an even number (>= 8) of rows; the coarsest level is always replicated
     ctx->Ld = 0;
-    if (nranks > 1) { int rows = P->N1; while (ctx->Ld < nl - 1 && rows % (2 * nranks) == 0 && rows / nranks >= 8) { ctx->Ld++; rows /= 2; } }
+    // Small levels are latency-bound: three halo exchanges per visit cost more than the slab saves, so levels below
+    // IMPEC_DIST_MIN_CELLS cells (default 4M; 0 in the parity tests) are replicated as well.
+    if (nranks > 1) {
+        const char *e = getenv("IMPEC_DIST_MIN_CELLS");
+        const double min_cells = e ? atof(e) : 4.0e6;
+        int rows = P->N1, cols = P->N2;
+        while (ctx->Ld < nl - 1 && rows % (2 * nranks) == 0 && rows / nranks >= 8 && (double)rows * cols >= min_cells) { ctx->Ld++; rows /= 2; cols /= 2; }
+    }
     for (int l = 0, n1 = P->N1, n2 = P->N2; l < nl; l++, n1 /= 2, n2 /= 2) {
         Level &L = ctx->L[l];
         L.dist = l < ctx->Ld;
@@ -645,6 +653,11 @@ static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr
     const bool fused = ctx->fused;
     if (dot_nparts) *dot_nparts = 0;
     if (l == nl - 1) {
+        if (fused && !L.dist && L.g.N1 <= FT_H - 4 && L.g.N2 <= FT_TJ) {
+            // the whole level fits one tile: all 2*ncoarse sweeps in a single launch (x0 = 0 inside the kernel)
+            LAUNCH_COOP_SMEM(ctx, k_mg_coarse_solve, dim3(1, 1), kFusedBlock, kFusedSmem, C.D[l], f, L.x, 2 * C.ncoarse);
+            return IMPEC_OK;
+        }
         if (fused) {
             CUDA_TRY(ctx, cudaMemsetAsync(L.x, 0, grid_elems(L.g) * sizeof(double), ctx->stream));
             if (L.dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));

@@ -71,9 +71,11 @@ IMPEC_D double tile_diagsum(const LevelDev &L, const double *__restrict__ X, int
     return s;
 }
 
+// nsweeps > 1 (PLAIN only, and only when this single tile holds the WHOLE level so that no halo can go stale): the
+// sweeps alternate forward/backward starting with colour c0 -- the coarsest-level solve in one launch.
 template <int MODE, bool EDGE>
 IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, const int c0,
-                        const Grid &gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part, double *__restrict__ X) {
+                        const Grid &gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part, double *__restrict__ X, const int nsweeps = 1) {
     constexpr int HI = FusedGeom<MODE>::HI, TI = FusedGeom<MODE>::TI;
     const Grid g = L.g;
     const int ld = g.ld;
@@ -92,7 +94,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
         const int r = ty + n * FT_NTY, ig = i0 + r;
         double a = 0., b = 0.;
         const bool row_alloc = !EDGE || ((ig >= -IMPEC_GH) && (ig < g.rows - IMPEC_GH));
-        if (MODE != FUSED_PRE && row_alloc && col_alloc) {
+        if (MODE != FUSED_PRE && row_alloc && col_alloc && xin) {
             const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
             const d2 v = ld2(xin + k);
             a = v.x; b = v.y;
@@ -127,9 +129,11 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     //      (by s cells in PRE mode, whose first stage is the neighbour-free zero-guess update x = f/diag).
     //      The pinned cell has dinv = 0 and x = 0, so it needs no special case here.
     double nv[FT_ROWS];
+    for (int sw = 0; sw < nsweeps; sw++)
 #pragma unroll
     for (int s = 0; s < 2; s++) {
-        const int col = s == 0 ? c0 : 1 - c0;
+        const int cfirst = (sw & 1) ? 1 - c0 : c0;
+        const int col = s == 0 ? cfirst : 1 - cfirst;
         const int shrink = (MODE == FUSED_PRE) ? s : s + 1;
         const int off = (par == col) ? 0 : 1;                            // which cell of the pair has this colour
         const int jj = jl + off, j = jg + off;
@@ -243,4 +247,11 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_fused(LevelDev L, cons
     }
     if (edge) fused_body<MODE, true>(L, f, xin, x, c0, gc, ec, fc, part, X);
     else fused_body<MODE, false>(L, f, xin, x, c0, gc, ec, fc, part, X);
+}
+
+// Coarsest-level solve: `nsweeps` alternating red-black sweeps from a zero guess in ONE launch.  Requires that a
+// single tile holds the whole level (N1 <= FT_H - 4, N2 <= FT_TJ), which the host checks.
+__global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_coarse_solve(LevelDev L, const double *__restrict__ f, double *__restrict__ x, int nsweeps) {
+    IMPEC_DYN_SMEM(double, X);
+    fused_body<FUSED_PLAIN, true>(L, f, (const double *)nullptr, x, 0, L.g, (const double *)nullptr, (double *)nullptr, (double *)nullptr, X, nsweeps);
 }

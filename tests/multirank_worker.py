@@ -15,15 +15,27 @@ from helpers import production_case   # noqa: E402
 
 def main():
     N1, N2, stype, diffusion, steps = (int(x) for x in sys.argv[1:6])
+    cuda = len(sys.argv) > 6 and sys.argv[6] == "cuda"      # real library + NCCL on GPUs instead of emulator + gloo
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=diffusion, eps=1e-12)
-    Pi = I.default_params(emulated=True, **base)
+    Pi = I.default_params(emulated=not cuda, **base)
+    dev = int(os.environ.get("LOCAL_RANK", "0")) if cuda else 0
 
-    ref = I.Context(Pi, emulated=True)                      # single-rank reference (same library, same kernels)
+    ref = I.Context(Pi, device=dev, emulated=not cuda)      # single-rank reference (same library, same kernels)
     ref.upload_c(c); ref.upload_q(q)
-    ctx = I.Context(Pi, rank=rank, nranks=world, emulated=True)
-    I.attach_torch_comm(ctx, rank, world)
+    if cuda:
+        import ctypes as C
+        ids = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            assert I.load().impec_nccl_unique_id(buf) == 0
+            ids = [buf.raw]
+        dist.broadcast_object_list(ids, src=0)
+        ctx = I.Context(Pi, device=dev, rank=rank, nranks=world, nccl_id=ids[0])
+    else:
+        ctx = I.Context(Pi, rank=rank, nranks=world, emulated=True)
+        I.attach_torch_comm(ctx, rank, world)
     ctx.upload_c(c); ctx.upload_q(q)
     r0, n = ctx.local_rows()
     assert n == N1 // world and r0 == rank * n
