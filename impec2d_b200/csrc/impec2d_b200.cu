@@ -41,7 +41,7 @@ struct impec_ctx {
     double *c = nullptr, *p = nullptr, *q = nullptr, *u = nullptr, *v = nullptr;
     double *ta = nullptr, *tb = nullptr;             // transport temporaries (contiguous pair)
     double *MU = nullptr, *KV11 = nullptr, *KV22 = nullptr;
-    double *r = nullptr, *z = nullptr, *d = nullptr, *s = nullptr, *rhs = nullptr, *t0 = nullptr;
+    double *r = nullptr, *z = nullptr, *d = nullptr, *s = nullptr, *rhs = nullptr, *t0 = nullptr, *d2buf = nullptr;
     std::vector<Level> L;
     double *sigma_dev = nullptr;                    // per-level diagonal shift of the pin
     // reductions
@@ -332,6 +332,8 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_coarse_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
 #endif
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
     if (nranks > 1 && nccl_unique_id) {
@@ -346,7 +348,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     ctx->N1g = P->N1;
     ctx->g = make_slab(P->N1, P->N2, rank, nranks);
     const size_t n = grid_elems(ctx->g);
-    double **fields[] = {&ctx->c, &ctx->p, &ctx->q, &ctx->u, &ctx->v, &ctx->MU, &ctx->KV11, &ctx->r, &ctx->z, &ctx->d, &ctx->s, &ctx->rhs, &ctx->t0};
+    double **fields[] = {&ctx->c, &ctx->p, &ctx->q, &ctx->u, &ctx->v, &ctx->MU, &ctx->KV11, &ctx->r, &ctx->z, &ctx->d, &ctx->s, &ctx->rhs, &ctx->t0, &ctx->d2buf};
     for (double **f : fields) TRY(dev_alloc(ctx, f, n));
     TRY(dev_alloc(ctx, &ctx->ta, 2 * n)); ctx->tb = ctx->ta + n;
     if (P->is_test) TRY(dev_alloc(ctx, &ctx->KV22, n)); else ctx->KV22 = ctx->KV11;
@@ -776,20 +778,37 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
     else if (i_prod / bi_prod < eps * eps) converged = 1;
     int ig = S_GAMMA0;                                           // which scalar slot holds the current gamma
     long long dparts = 0;
+    // Fused path: d <- z + beta d, s <- S d and <s,d> in ONE tile kernel (k_pcg_matvec); the search direction ping-pongs
+    // between two buffers because the kernel reads d with a halo and writes its interior.
+    const bool fuse_dir = ctx->fused;
+    const dim3 gmv = fused_grid<FUSED_PLAIN>(g);
+    const long long nmv = (long long)gmv.x * gmv.y;
+    double *dcur = ctx->d, *dalt = ctx->d2buf;
+    bool first_dir = true;
     if (!converged) {
         TRY(mg_cycle(C, 0, ctx->r, ctx->part, &dparts));
-        LAUNCH(ctx, k_update_d<true>, gr, kBlock, g, ctx->scal, (const double *)ctx->L[0].x, ctx->d);
+        if (!fuse_dir) LAUNCH(ctx, k_update_d<true>, gr, kBlock, g, ctx->scal, (const double *)ctx->L[0].x, dcur);
         if (!dparts) { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->L[0].x, ctx->part); dparts = nparts; }
         TRY(reduce_final(ctx, RED_SUM, dparts, 1, 0, ig));
     }
     while (!converged && it < ctx->P.max_iter) {
         it++;
-        TRY(exchange_rows(ctx, ctx->d, g, 1));
-        LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, A, ctx->d, ctx->s, ctx->part);
-        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_SDOTP));
+        if (fuse_dir) {
+            // beta = gamma_new / gamma_old sits in scal[S_BETA_NUM], scal[S_BETA_DEN] (set at the end of the previous pass)
+            TRY(exchange_rows(ctx, ctx->L[0].x, g, 1));
+            if (!first_dir) TRY(exchange_rows(ctx, dcur, g, 1));
+            if (first_dir) LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<true>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
+            else LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
+            std::swap(dcur, dalt); first_dir = false;
+            TRY(reduce_final(ctx, RED_SUM, nmv, 1, 0, S_SDOTP));
+        } else {
+            TRY(exchange_rows(ctx, dcur, g, 1));
+            LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, A, dcur, ctx->s, ctx->part);
+            TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_SDOTP));
+        }
         // alpha = gamma / <s,d>: the kernel reads scal[0]/scal[1], so gamma must sit in slot 0
         if (ig != S_GAMMA0) { CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal + S_GAMMA0, ctx->scal + ig, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)); ig = S_GAMMA0; }
-        LAUNCH_COOP(ctx, k_update_xr, gr, kBlock, g, ctx->scal, ctx->d, ctx->s, x, ctx->r, ctx->part);
+        LAUNCH_COOP(ctx, k_update_xr, gr, kBlock, g, ctx->scal, (const double *)dcur, ctx->s, x, ctx->r, ctx->part);
         TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_IPROD));
         TRY(fetch_scalars(ctx, S_IPROD, 1));
         i_prod = ctx->h_scal[S_IPROD];
@@ -800,7 +819,7 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         TRY(reduce_final(ctx, RED_SUM, dparts, 1, 0, S_BETA_NUM));
         // beta = gamma_new / gamma_old ; d = z + beta d      (k_update_d reads scal'[0]/scal'[1])
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal + S_BETA_DEN, ctx->scal + S_GAMMA0, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_BETA_NUM, (const double *)ctx->L[0].x, ctx->d);
+        if (!fuse_dir) LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_BETA_NUM, (const double *)ctx->L[0].x, dcur);
         ig = S_BETA_NUM;
     }
     // true residual with the final x
@@ -1071,6 +1090,7 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "residual") { LAUNCH(ctx, k_residual, gr, kBlock, C.D[0], ctx->r, (const double *)L0.x, L0.r); return IMPEC_OK; }
         if (k == "restrict") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L0.g, L0.r, Lc.g, Lc.f); return IMPEC_OK; }
         if (k == "prolong_add") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_prolong_add, gr, kBlock, Lc.g, Lc.x, L0.g, L0.x, L0.pin); return IMPEC_OK; }
+        if (k == "pcg_matvec") { LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, fused_grid<FUSED_PLAIN>(g), kFusedBlock, kFusedSmem, C.D[0], (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part); return IMPEC_OK; }
         if (k == "matvec_dot") { LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, C.D[0], ctx->d, ctx->s, ctx->part); return IMPEC_OK; }
         if (k == "update_xr") { LAUNCH_COOP(ctx, k_update_xr, gr, kBlock, g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part); return IMPEC_OK; }
         if (k == "dot") { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part); return IMPEC_OK; }
@@ -1082,7 +1102,7 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "calc_velocities") return impec_calc_velocities(ctx);
         return fail(ctx, IMPEC_ERR_ARG, "unknown kernel name '%s'", k.c_str());
     };
-    if (k == "update_xr" || k == "update_d") {      // alpha = beta = 0/1 so the vectors stay finite
+    if (k == "update_xr" || k == "update_d" || k == "pcg_matvec") {      // alpha = beta = 0/1 so the vectors stay finite
         LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_TMP, 0.0);
         LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_TMP + 1, 1.0);
     }

@@ -255,3 +255,72 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_coarse_solve(LevelDev 
     IMPEC_DYN_SMEM(double, X);
     fused_body<FUSED_PLAIN, true>(L, f, (const double *)nullptr, x, 0, L.g, (const double *)nullptr, (double *)nullptr, (double *)nullptr, X, nsweeps);
 }
+
+// ---------------------------------------------------------------- fused PCG search-direction update + mat-vec
+//   d <- z + beta d   (FIRST: d <- z),   s <- S d,   part <- <s,d>       beta = scal[0]/scal[1] from device memory
+// One pass over z, d and the links instead of k_update_d followed by k_matvec_dot (56 instead of 64 B/cell, one launch).
+// Same tile scheme as k_mg_fused: the new d is staged in shared memory with a one-cell halo (recomputed redundantly).
+template <bool FIRST, bool EDGE>
+IMPEC_D void pcg_matvec_body_rw(const LevelDev &L, const double *__restrict__ scal, const double *__restrict__ z, const double *__restrict__ din,
+                                double *__restrict__ d, double *__restrict__ s, double *__restrict__ part, double *__restrict__ X) {
+    constexpr int HI = 2, TI = FT_H - 2 * HI;
+    const Grid g = L.g;
+    const int ld = g.ld;
+    const int tx = threadIdx.x, ty = threadIdx.y & (FT_NTY - 1);
+    const int jl = 2 * tx;
+    const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ, i0 = (int)blockIdx.y * TI - HI;
+    const int jg = j0 + jl;
+    const long long kbase = (long long)(i0 + ty + IMPEC_GH) * ld + (jg + IMPEC_PJ);
+    const bool col_alloc = !EDGE || ((jg + IMPEC_PJ >= 0) && (jg + 1 + IMPEC_PJ < ld));
+    const double beta = FIRST ? 0. : scal[0] / scal[1];
+    const bool col_int = jl >= FT_HJ && jl < FT_W - FT_HJ && (!EDGE || jg < g.N2);
+    // new search direction on the whole tile; the interior is written back
+#pragma unroll
+    for (int n = 0; n < FT_ROWS; n++) {
+        const int r = ty + n * FT_NTY, ig = i0 + r;
+        double a = 0., b = 0.;
+        const bool row_alloc = !EDGE || ((ig >= -IMPEC_GH) && (ig < g.rows - IMPEC_GH));
+        if (row_alloc && col_alloc) {
+            const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
+            const d2 zv = ld2(z + k);
+            if (FIRST) { a = zv.x; b = zv.y; }
+            else { const d2 dv = ld2(din + k); a = zv.x + beta * dv.x; b = zv.y + beta * dv.y; }
+        }
+        X[r * FT_W + tx] = a; X[r * FT_W + 64 + tx] = b;
+    }
+    IMPEC_SYNCTHREADS();
+    double dotv = 0.;
+#pragma unroll
+    for (int n = 0; n < FT_ROWS; n++) {
+        const int r = ty + n * FT_NTY, ig = i0 + r;
+        if (r < HI || r >= FT_H - HI || !col_int || (EDGE && ig >= g.N1)) continue;
+        const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
+        const double da = X[r * FT_W + tx], db = X[r * FT_W + 64 + tx];
+        const bool two = !EDGE || jg + 1 < g.N2;
+        double sa = ((long long)k == L.pin) ? 0. : link_diag(L, k) * da - tile_offsum(L, X, r, tx, 0, k);
+        double sb = 0.;
+        if (two) sb = ((long long)(k + 1) == L.pin) ? 0. : link_diag(L, k + 1) * db - tile_offsum(L, X, r, tx, 1, k + 1);
+        if (two) { st2(d + k, da, db); st2(s + k, sa, sb); } else { d[k] = da; s[k] = sa; }
+        dotv = fma(sa, da, dotv);
+        if (two) dotv = fma(sb, db, dotv);
+    }
+    dotv = block_reduce<RED_SUM>(dotv);
+    if (tx == 0 && ty == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
+}
+
+// NOTE: d is read (with halo) and written (interior) by the same launch, so the read and write buffers must differ:
+// the host ping-pongs between two search-direction buffers (din -> dout).
+template <bool FIRST>
+__global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_pcg_matvec(LevelDev L, const double *__restrict__ scal, const double *__restrict__ z, const double *__restrict__ din,
+                                                                 double *__restrict__ dout, double *__restrict__ s, double *__restrict__ part) {
+    IMPEC_DYN_SMEM(double, X);
+    constexpr int HI = 2, TI = FT_H - 2 * HI;
+    const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ, i0 = (int)blockIdx.y * TI - HI;
+    bool edge = i0 < L.g.rlo || j0 < 0 || i0 + FT_H >= L.g.rhi || j0 + FT_W >= L.g.N2;
+    if (L.pin >= 0) {
+        const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
+        edge = edge || (pi >= i0 && pi < i0 + FT_H && pj >= j0 && pj < j0 + FT_W);
+    }
+    if (edge) pcg_matvec_body_rw<FIRST, true>(L, scal, z, din, dout, s, part, X);
+    else pcg_matvec_body_rw<FIRST, false>(L, scal, z, din, dout, s, part, X);
+}

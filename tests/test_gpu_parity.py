@@ -104,3 +104,47 @@ def test_large_grid_properties():
     assert abs(d1.total_mass - m0) <= 1e-11 * m0            # Neumann walls, zero normal velocity
     assert -1e-12 <= d1.c_min and d1.c_max <= 1.0 + 1e-3
     ctx.close()
+
+
+def test_full_fingering_run_integral_diagnostics():
+    """North-star check 2: a full quarter-five-spot displacement (parallel.cfg operator, M = 41, 64^2, to t = 0.4).
+    Pointwise agreement with the oracle over early times (max|dc| <= 1e-8 for t <= 0.05), afterwards the integral
+    diagnostics computed by the ONE shared post-processor (impec2d_b200/diagnostics.py):
+      breakthrough time +-1 %, produced (recovered) mass +-0.5 %, mass in place +-0.5 %, mixing-zone length +-2 %."""
+    from impec2d_b200.diagnostics import RunDiagnostics
+    lib = O.lib()
+    N = 64
+    base, Po, c, q = production_case(N, N, eps=1e-10)
+    c[...] = 0.0                                              # the shipped run starts from c = 0 (src/Impec2DSolver.cpp:222-230)
+    Pi = I.default_params(**base)
+    ctx = I.Context(Pi)
+    ctx.upload_c(c); ctx.upload_q(q)
+    So = O.new_state()
+    p = O.scalar_field(Po); u = O.velocity_field(Po); v = O.velocity_field(Po)
+    co = c.copy()
+    L = Po.x_ub - Po.x_lb
+    dg = RunDiagnostics(q, Po.dx, Po.dy, L, L); do = RunDiagnostics(q, Po.dx, Po.dy, L, L)
+    t, tfinal, g = 0.0, 0.4, Po.g
+    early_checked = False
+    while t < tfinal:
+        dto = lib.orc_impes_step(C.byref(Po), C.byref(So), p, co, u, v, q, t, tfinal)
+        dtg, info = ctx.impes_step(t, tfinal)
+        assert abs(dtg - dto) <= 1e-6 * dto
+        t += dto
+        cg = ctx.download_c()
+        if t <= 0.05:
+            assert np.abs(cg - co).max() <= 1e-8, (t, np.abs(cg - co).max())
+            early_checked = True
+        dg.record(t, cg[g:-g, g:-g]); do.record(t, co[g:-g, g:-g])
+    assert early_checked
+    sg, so = dg.summary(), do.summary()
+    assert so["breakthrough_time"] is not None and 0.05 < so["breakthrough_time"] < 0.4
+    assert abs(sg["breakthrough_time"] - so["breakthrough_time"]) <= 0.01 * so["breakthrough_time"]
+    assert abs(sg["mixing_zone_length"] - so["mixing_zone_length"]) <= 0.02 * so["mixing_zone_length"]
+    assert abs(sg["mass_in_place"] - so["mass_in_place"]) <= 0.005 * so["mass_in_place"]
+    d = ctx.diagnostics()
+    assert abs(d.total_mass_outflux - So.total_mass_outflux) <= 0.005 * So.total_mass_outflux
+    # global mass balance of the run: in place + produced = injected (2 I t for the parallel layout), in cell units
+    injected = 2.0 * 1.0 * t / (Po.dx * Po.dy)
+    assert abs(d.total_mass + d.total_mass_outflux - injected) <= 1e-6 * injected
+    ctx.close()
