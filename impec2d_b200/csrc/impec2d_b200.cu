@@ -66,6 +66,14 @@ struct impec_ctx {
     ncclComm_t nccl = nullptr;
 #endif
     bool comm_ready = false;
+    // CUDA graph of the replicated multigrid tail (levels >= tail_level): identical launch sequence every visit
+    int tail_level = -1;
+    bool use_graph = true, graph_ready = false;
+    long long graph_launches = 0;
+    std::vector<std::pair<double *, double *> > tail_init, tail_final;
+#ifndef IMPEC_EMU
+    cudaGraph_t tail_graph = nullptr; cudaGraphExec_t tail_exec = nullptr;
+#endif
 };
 
 enum { S_GAMMA0 = 0, S_SDOTP = 1, S_IPROD = 2, S_GAMMA1 = 3, S_BIPROD = 4, S_BETA_NUM = 5, S_BETA_DEN = 6, S_TMP = 7, S_SRC = 8, S_OUTFLUX = 9,
@@ -303,6 +311,10 @@ extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
     if (ctx->nccl) ncclCommDestroy(ctx->nccl);
 #endif
+#ifndef IMPEC_EMU
+    if (ctx->tail_exec) cudaGraphExecDestroy(ctx->tail_exec);
+    if (ctx->tail_graph) cudaGraphDestroy(ctx->tail_graph);
+#endif
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -381,6 +393,8 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
         if (l == 0) { L.x = ctx->z; L.f = ctx->r; L.t = ctx->t0; L.r = ctx->s; }
         else { TRY(dev_alloc(ctx, &L.x, nn)); TRY(dev_alloc(ctx, &L.f, nn)); TRY(dev_alloc(ctx, &L.t, nn)); TRY(dev_alloc(ctx, &L.r, nn)); }
     }
+    for (int l = std::max(ctx->Ld, 1); l < nl; l++)
+        if ((double)ctx->L[l].g.N1 * ctx->L[l].g.N2 <= 2097152.0 && l < nl - 1) { ctx->tail_level = l; break; }
     // pinned cell (1,1): src/MGSolver.cpp:109-118
     int pi = 1, pj = 1;
     ctx->L[0].pin = (rank == 0) ? (long long)gidx(ctx->g, pi, pj) : -1;
@@ -409,10 +423,11 @@ extern "C" int impec_reset_state(impec_ctx *ctx) {
 extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     const std::string k(key ? key : "");
     if (k == "warm_start") { ctx->warm_start = value != 0.0; return IMPEC_OK; }
-    if (k == "mg_fused") { ctx->fused = value != 0.0; return IMPEC_OK; }
-    if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; return IMPEC_OK; }
-    if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; return IMPEC_OK; }
-    if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; return IMPEC_OK; }
+    if (k == "mg_fused") { ctx->fused = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "max_iter") { ctx->P.max_iter = (int)value; return IMPEC_OK; }
     return fail(ctx, IMPEC_ERR_ARG, "unknown option '%s'", k.c_str());
 }
@@ -527,7 +542,7 @@ static LevelDev level_dev(const impec_ctx *ctx, int l, double mass) {
     const Level &L = ctx->L[l];
     LevelDev D;
     D.g = L.g; D.AW = L.AW; D.AS = L.AS; D.AV = L.AV; D.DINV = L.DINV; D.mass = mass;
-    D.pin = L.pin; D.sig_idx = L.sig_idx; D.sig_val = 0.;
+    D.pin = L.pin; D.sig_idx = L.sig_idx; D.sig = ctx->sigma_dev + l;
     return D;
 }
 
@@ -574,15 +589,6 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------ multigrid cycle
-// sigma lives in device memory (k_pin_sigma), so the level descriptor carries a pointer-free copy:
-// the smoother kernels read it through sig_val, which we refresh from the host mirror once per build.
-static int refresh_sigma(impec_ctx *ctx, std::vector<double> &sig) {
-    sig.assign(ctx->L.size() + 1, 0.0);
-    CUDA_TRY(ctx, cudaMemcpyAsync(sig.data(), ctx->sigma_dev, sizeof(double) * ctx->L.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return IMPEC_OK;
-}
-
 struct Cycle {
     impec_ctx *ctx;
     std::vector<LevelDev> D;
@@ -648,7 +654,41 @@ static int fused_post(Cycle &C, int l, const double *f, double *part, long long 
 // One multigrid cycle for S x = f from a zero initial guess; the result is left in ctx->L[l].x (the fused path
 // ping-pongs between the level's two buffers).  dot_part/dot_nparts (level 0, fused path): the last kernel also
 // leaves the partial sums of <f,x> in dot_part.
+static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, long long *dot_nparts);
 static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr, long long *dot_nparts = nullptr) {
+    impec_ctx *ctx = C.ctx;
+#ifndef IMPEC_EMU
+    // The replicated tail (levels >= tail_level) is the same launch sequence on the same buffers at every visit: it is
+    // captured once into a CUDA graph and replayed, which removes the launch gaps of ~100 tiny kernels per visit.
+    if (l == ctx->tail_level && ctx->use_graph && ctx->fused && C.nl == (int)ctx->L.size() && C.D[0].mass == 0.) {
+        const int nl = (int)ctx->L.size();
+        if (!ctx->graph_ready) {
+            if (ctx->tail_exec) { cudaGraphExecDestroy(ctx->tail_exec); ctx->tail_exec = nullptr; }
+            if (ctx->tail_graph) { cudaGraphDestroy(ctx->tail_graph); ctx->tail_graph = nullptr; }
+            ctx->tail_init.clear(); ctx->tail_final.clear();
+            for (int k = l; k < nl; k++) ctx->tail_init.push_back(std::make_pair(ctx->L[k].x, ctx->L[k].t));
+            const long long l0 = ctx->launches;
+            CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = mg_cycle_impl(C, l, f, nullptr, nullptr);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &ctx->tail_graph);
+            if (rc != IMPEC_OK) return rc;
+            if (ce != cudaSuccess) return fail(ctx, IMPEC_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            CUDA_TRY(ctx, cudaGraphInstantiate(&ctx->tail_exec, ctx->tail_graph, 0));
+            ctx->graph_launches = ctx->launches - l0; ctx->launches = l0;
+            for (int k = l; k < nl; k++) ctx->tail_final.push_back(std::make_pair(ctx->L[k].x, ctx->L[k].t));
+            ctx->graph_ready = true;
+        }
+        if (f != ctx->L[l].f) return fail(ctx, IMPEC_ERR_ARG, "multigrid tail called with a foreign right-hand side");
+        CUDA_TRY(ctx, cudaGraphLaunch(ctx->tail_exec, ctx->stream));
+        ctx->launches += ctx->graph_launches;
+        for (int k = l; k < nl; k++) { ctx->L[k].x = ctx->tail_final[k - l].first; ctx->L[k].t = ctx->tail_final[k - l].second; }
+        if (dot_nparts) *dot_nparts = 0;
+        return IMPEC_OK;
+    }
+#endif
+    return mg_cycle_impl(C, l, f, dot_part, dot_nparts);
+}
+static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, long long *dot_nparts) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
     double *x = L.x;
     const int nl = C.nl;
@@ -713,10 +753,8 @@ static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr
 
 static int make_cycle(impec_ctx *ctx, Cycle &C, double mass, int nlevels_used) {
     C.ctx = ctx;
-    std::vector<double> sig;
-    TRY(refresh_sigma(ctx, sig));
     C.D.clear();
-    for (size_t l = 0; l < ctx->L.size(); l++) { LevelDev D = level_dev(ctx, (int)l, mass); D.sig_val = sig[l]; if (mass != 0.) { D.pin = -1; D.sig_idx = -1; } C.D.push_back(D); }
+    for (size_t l = 0; l < ctx->L.size(); l++) { LevelDev D = level_dev(ctx, (int)l, mass); if (mass != 0.) { D.pin = -1; D.sig_idx = -1; } C.D.push_back(D); }
     C.ncoarse = ctx->P.mg_ncoarse > 0 ? ctx->P.mg_ncoarse : 8;
     C.w_from = ctx->P.mg_w_from; C.w_to = ctx->P.mg_w_to;
     C.nl = nlevels_used > 0 ? nlevels_used : (int)ctx->L.size();

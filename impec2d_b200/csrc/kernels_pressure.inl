@@ -140,13 +140,13 @@ struct LevelDev {
     double mass;                 // 0 elliptic, 1 Crank-Nicolson
     long long pin;               // fine level: padded index of the Dirichlet cell (or -1)
     long long sig_idx;           // coarse levels: padded index of the cell carrying the pin's diagonal shift
-    double sig_val;
+    const double *sig;           // device pointer to that shift (k_pin_sigma): kernel arguments stay constant across steps
 };
 
 IMPEC_D double link_diag(const LevelDev &L, size_t k) {
     const int ld = L.g.ld;
     double d = L.mass + (((L.AW[k] + L.AW[k + ld]) + (L.AS[k] + L.AS[k + 1])) + ((L.AV[k] + L.AV[k + ld]) + (L.AV[k + 1] + L.AV[k + ld + 1])));
-    if ((long long)k == L.sig_idx) d += L.sig_val;
+    if ((long long)k == L.sig_idx) d += L.sig[0];
     return d;
 }
 // order W,E,S,N,SW,SE,NW,NE (same as the oracle's off_sum)
