@@ -215,7 +215,7 @@ def main():
 
     # ------------------------------------------------------------------ per-kernel device times (CUDA events, live)
     prof = {}
-    for name, reps in () if args.profile_mode else (("vcycle", 5), ("fused_pre", 10), ("fused_post", 10), ("fused_plain", 10), ("smooth_sweep", 10), ("residual", 10), ("restrict", 10), ("prolong_add", 10), ("matvec_dot", 10),
+    for name, reps in () if args.profile_mode else (("vcycle", 5), ("fused_pre", 10), ("fused_post", 10), ("fused_plain", 10), ("smooth_sweep", 10), ("residual", 10), ("restrict", 10), ("prolong_add", 10), ("pcg_matvec", 10), ("matvec_dot", 10),
                        ("update_xr", 10), ("dot", 10), ("update_d", 10), ("sweep_x", 10), ("sweep_y", 10), ("build_operator", 5), ("calc_velocities", 5)):
         prof[name] = ctx.profile_kernel(name, reps)
     if args.profile_mode:
@@ -230,17 +230,18 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     # Algorithmic bytes per fine-level launch (FP64, each distinct array once; DESIGN.md "kernels"):
-    #   k_mg_fused<POST>  : R x,f,AW,AS,AV (40) + coarse e (2) + W x (8)            = 50 B/cell
-    #   k_mg_fused<PRE>   : R f,AW,AS,AV (32) + W x (8) + coarse f (2)              = 42 B/cell
-    #   k_mg_fused<PLAIN> : R x,f,AW,AS,AV (40) + W x (8)                           = 48 B/cell
+    #   k_mg_fused<POST>  : R x,f,AW,AS,AV,DINV (48) + coarse e (2) + W x (8)       = 58 B/cell
+    #   k_mg_fused<PRE>   : R f,AW,AS,AV,DINV (40) + W x (8) + coarse f (2)         = 50 B/cell
+    #   k_mg_fused<PLAIN> : R x,f,AW,AS,AV,DINV (48) + W x (8)                      = 56 B/cell
+    #   k_pcg_matvec      : R z,d,AW,AS,AV (40) + W d,s (16)                        = 56 B/cell
     #   one multigrid cycle, all levels                        = 208 B/cell
-    cells = float(N) * N
-    kb = {"fused_post": 50.0, "fused_pre": 42.0, "fused_plain": 48.0, "matvec_dot": 40.0, "update_xr": 48.0, "update_d": 24.0,
+    cells = float(N) * N / world                   # cells per GPU: the kernels are timed on this rank's slab
+    kb = {"fused_post": 58.0, "fused_pre": 50.0, "fused_plain": 56.0, "pcg_matvec": 56.0, "matvec_dot": 40.0, "update_xr": 48.0, "update_d": 24.0,
           "sweep_x": 24.0, "sweep_y": 24.0, "residual": 48.0, "smooth_sweep": 48.0}
     per_kernel = {k: {"ms": prof[k], "algorithmic_bytes": kb[k] * cells, "achieved_gbs": kb[k] * cells / (prof[k] * 1e-3) / 1e9,
                       "frac": kb[k] * cells / (prof[k] * 1e-3) / 1e9 / peak} for k in kb}
     dom = "fused_post"
-    vc_bytes = 208.0 * cells
+    vc_bytes = 208.0 * float(N) * N / world
     roofline = {"bound": "hbm", "kernel": "k_mg_fused<FUSED_POST> (prolong + correct + red-black post-smooth + <r,z>, fine level)",
                 "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_kernel[dom]["algorithmic_bytes"],

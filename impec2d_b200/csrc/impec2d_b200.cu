@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <algorithm>
+#include <thread>
 
 #define BX 32
 #define BY 8
@@ -455,15 +456,28 @@ extern "C" int impec_download_p(impec_ctx *ctx, double *h) { return download_sca
 extern "C" int impec_upload_c_rows(impec_ctx *ctx, const double *h) { ctx->mob_valid = ctx->op_valid = false; return upload_scalar(ctx, ctx->c, h); }
 extern "C" int impec_download_c_rows(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->c, h); }
 
-// q: this rank's rows (N1loc x N2)
+// q: this rank's rows (N1loc x N2).  The scan for non-zero cells runs on all host threads (it is on the e2e path:
+// 2 GB of q per upload at 16384^2).
 static int rebuild_wells(impec_ctx *ctx, const double *q) {
     const int N1 = ctx->g.N1, N2 = ctx->P.N2;
     std::vector<int> wi, wj; std::vector<double> wq;
-    for (int i = 0; i < N1; i++)
-        for (int j = 0; j < N2; j++) {
-            const double v = q[(size_t)i * N2 + j];
-            if (v != 0.0) { wi.push_back(i); wj.push_back(j); wq.push_back(v); }
-        }
+    {
+        unsigned nt = std::thread::hardware_concurrency();
+        if (nt < 1) nt = 1; if (nt > 32) nt = 32; if ((int)nt > N1) nt = (unsigned)N1;
+        std::vector<std::vector<int> > ti(nt), tj(nt); std::vector<std::vector<double> > tq(nt);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                const int r0 = (int)((long long)N1 * t / nt), r1 = (int)((long long)N1 * (t + 1) / nt);     // contiguous row blocks keep row-major order
+                for (int i = r0; i < r1; i++)
+                    for (int j = 0; j < N2; j++) {
+                        const double v = q[(size_t)i * N2 + j];
+                        if (v != 0.0) { ti[t].push_back(i); tj[t].push_back(j); tq[t].push_back(v); }
+                    }
+            });
+        for (auto &x : th) x.join();
+        for (unsigned t = 0; t < nt; t++) { wi.insert(wi.end(), ti[t].begin(), ti[t].end()); wj.insert(wj.end(), tj[t].begin(), tj[t].end()); wq.insert(wq.end(), tq[t].begin(), tq[t].end()); }
+    }
     ctx->nwell = (int)wq.size();
     ctx->q_pin = (ctx->rank == 0 && N1 > 1 && N2 > 1) ? q[(size_t)1 * N2 + 1] : 0.0;
     if (ctx->nwell) {
