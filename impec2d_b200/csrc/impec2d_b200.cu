@@ -24,6 +24,7 @@
 struct Level {
     Grid g;
     double *AW = nullptr, *AS = nullptr, *AV = nullptr, *DINV = nullptr;
+    float *AWf = nullptr, *ASf = nullptr, *AVf = nullptr, *DINVf = nullptr;      // FP32 copies for the cycle kernels
     double *x = nullptr, *f = nullptr, *t = nullptr, *r = nullptr;
     long long pin = -1, sig_idx = -1;
     bool dist = false;           // rows of this level are slab-distributed over the ranks
@@ -50,12 +51,13 @@ struct impec_ctx {
     double *scal = nullptr;                         // device scalars
     double *h_scal = nullptr;                       // pinned host mirror
     // wells
-    int nwell = 0; int *well_i = nullptr, *well_j = nullptr; double *well_q = nullptr, *well_md = nullptr;
+    int nwell = 0, well_cap = 0; int *well_i = nullptr, *well_j = nullptr; double *well_q = nullptr, *well_md = nullptr;
     double q_pin = 0.0; bool have_q = false;
     int prev_first_sweep = 1;                       // Y_SWEEP (src/HyperbolicSolver.cpp:84)
     bool mob_valid = false, op_valid = false;
     bool warm_start = false;
     bool fused = true;                              // fused tile kernels (kernels_fused.inl) vs one kernel per colour pass
+    bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
     long long launches = 0;
     std::string err;
     std::vector<void *> allocs;
@@ -309,6 +311,7 @@ extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
+    for (void *p : {(void *)ctx->well_i, (void *)ctx->well_j, (void *)ctx->well_q, (void *)ctx->well_md}) if (p) cudaFree(p);
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
     if (ctx->nccl) ncclCommDestroy(ctx->nccl);
 #endif
@@ -341,10 +344,12 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
 #ifndef IMPEC_EMU
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_fused<FUSED_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_coarse_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
+#define SMEM_ATTR(kern) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)))
+    SMEM_ATTR((k_mg_fused<FUSED_PLAIN, true>)); SMEM_ATTR((k_mg_fused<FUSED_PLAIN, false>));
+    SMEM_ATTR((k_mg_fused<FUSED_PRE, true>)); SMEM_ATTR((k_mg_fused<FUSED_PRE, false>));
+    SMEM_ATTR((k_mg_fused<FUSED_POST, true>)); SMEM_ATTR((k_mg_fused<FUSED_POST, false>));
+    SMEM_ATTR(k_mg_coarse_solve<true>); SMEM_ATTR(k_mg_coarse_solve<false>);
+#undef SMEM_ATTR
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
 #endif
@@ -391,6 +396,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
         } else L.gl = L.g;
         const size_t nn = grid_elems(L.g);
         TRY(dev_alloc(ctx, &L.AW, nn)); TRY(dev_alloc(ctx, &L.AS, nn)); TRY(dev_alloc(ctx, &L.AV, nn)); TRY(dev_alloc(ctx, &L.DINV, nn));
+        { double *f32 = nullptr; TRY(dev_alloc(ctx, &f32, 2 * nn + 8)); L.AWf = (float *)f32; L.ASf = L.AWf + nn; L.AVf = L.ASf + nn; L.DINVf = L.AVf + nn; }
         if (l == 0) { L.x = ctx->z; L.f = ctx->r; L.t = ctx->t0; L.r = ctx->s; }
         else { TRY(dev_alloc(ctx, &L.x, nn)); TRY(dev_alloc(ctx, &L.f, nn)); TRY(dev_alloc(ctx, &L.t, nn)); TRY(dev_alloc(ctx, &L.r, nn)); }
     }
@@ -425,6 +431,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     const std::string k(key ? key : "");
     if (k == "warm_start") { ctx->warm_start = value != 0.0; return IMPEC_OK; }
     if (k == "mg_fused") { ctx->fused = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
@@ -481,11 +488,15 @@ static int rebuild_wells(impec_ctx *ctx, const double *q) {
     ctx->nwell = (int)wq.size();
     ctx->q_pin = (ctx->rank == 0 && N1 > 1 && N2 > 1) ? q[(size_t)1 * N2 + 1] : 0.0;
     if (ctx->nwell) {
-        void *p;
-        CUDA_TRY(ctx, cudaMalloc(&p, sizeof(int) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_i = (int *)p;
-        CUDA_TRY(ctx, cudaMalloc(&p, sizeof(int) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_j = (int *)p;
-        CUDA_TRY(ctx, cudaMalloc(&p, sizeof(double) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_q = (double *)p;
-        CUDA_TRY(ctx, cudaMalloc(&p, sizeof(double) * ctx->nwell)); ctx->allocs.push_back(p); ctx->well_md = (double *)p;
+        if (ctx->nwell > ctx->well_cap) {                           // grow (rare): buffers are reused across uploads
+            for (void *old : {(void *)ctx->well_i, (void *)ctx->well_j, (void *)ctx->well_q, (void *)ctx->well_md}) if (old) cudaFree(old);
+            void *p;
+            CUDA_TRY(ctx, cudaMalloc(&p, sizeof(int) * ctx->nwell)); ctx->well_i = (int *)p;
+            CUDA_TRY(ctx, cudaMalloc(&p, sizeof(int) * ctx->nwell)); ctx->well_j = (int *)p;
+            CUDA_TRY(ctx, cudaMalloc(&p, sizeof(double) * ctx->nwell)); ctx->well_q = (double *)p;
+            CUDA_TRY(ctx, cudaMalloc(&p, sizeof(double) * ctx->nwell)); ctx->well_md = (double *)p;
+            ctx->well_cap = ctx->nwell;
+        }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_i, wi.data(), sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_j, wj.data(), sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_q, wq.data(), sizeof(double) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
@@ -556,6 +567,7 @@ static LevelDev level_dev(const impec_ctx *ctx, int l, double mass) {
     const Level &L = ctx->L[l];
     LevelDev D;
     D.g = L.g; D.AW = L.AW; D.AS = L.AS; D.AV = L.AV; D.DINV = L.DINV; D.mass = mass;
+    D.AWf = L.AWf; D.ASf = L.ASf; D.AVf = L.AVf; D.DINVf = L.DINVf;
     D.pin = L.pin; D.sig_idx = L.sig_idx; D.sig = ctx->sigma_dev + l;
     return D;
 }
@@ -597,6 +609,9 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
         Level &L = ctx->L[l];
         LAUNCH(ctx, k_diag_inv, grid2d(L.g.N2, L.g.N1), kBlock, level_dev(ctx, (int)l, 0.0), (const double *)(ctx->sigma_dev + l), L.DINV);
         if (L.dist) TRY(exchange_rows(ctx, L.DINV, L.g, IMPEC_GH));
+        const long long nn = (long long)grid_elems(L.g);
+        LAUNCH(ctx, k_links_to_f32, dim3((unsigned)((nn + 255) / 256)), dim3(256), nn, (const double *)L.AW, (const double *)L.AS, (const double *)L.AV, (const double *)L.DINV,
+               L.AWf, L.ASf, L.AVf, L.DINVf);
     }
     ctx->op_valid = true;
     return IMPEC_OK;
@@ -630,7 +645,9 @@ template <int MODE> static dim3 fused_grid(const Grid &g) {
 // they read L.x, write L.t and the two pointers are swapped (the level's current iterate is always L.x).
 static int fused_plain(Cycle &C, int l, const double *f, bool forward) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
-    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_PLAIN>, fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
+    if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PLAIN, true>), fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
+                     (const double *)nullptr, (double *)nullptr, (double *)nullptr);
+    else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PLAIN, false>), fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
                      (const double *)nullptr, (double *)nullptr, (double *)nullptr);
     std::swap(L.x, L.t);
     return IMPEC_OK;
@@ -644,7 +661,9 @@ static const double *coarse_x_view(const impec_ctx *ctx, int l) {
 static int fused_pre(Cycle &C, int l, const double *f) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
     const bool tr = at_transition(ctx, l);
-    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_PRE>, fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
+    if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PRE, true>), fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
+                     (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
+    else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PRE, false>), fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
                      (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
     return IMPEC_OK;
 }
@@ -658,7 +677,9 @@ static int gather_coarse_rhs(impec_ctx *ctx, int l) {
 static int fused_post(Cycle &C, int l, const double *f, double *part, long long *nparts) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
     const dim3 gr = fused_grid<FUSED_POST>(L.g);
-    LAUNCH_COOP_SMEM(ctx, k_mg_fused<FUSED_POST>, gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
+    if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_POST, true>), gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
+                     coarse_x_view(ctx, l), (double *)nullptr, part);
+    else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_POST, false>), gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
                      coarse_x_view(ctx, l), (double *)nullptr, part);
     std::swap(L.x, L.t);
     if (nparts) *nparts = (long long)gr.x * gr.y;
@@ -711,7 +732,8 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
     if (l == nl - 1) {
         if (fused && !L.dist && L.g.N1 <= FT_H - 4 && L.g.N2 <= FT_TJ) {
             // the whole level fits one tile: all 2*ncoarse sweeps in a single launch (x0 = 0 inside the kernel)
-            LAUNCH_COOP_SMEM(ctx, k_mg_coarse_solve, dim3(1, 1), kFusedBlock, kFusedSmem, C.D[l], f, L.x, 2 * C.ncoarse);
+            if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, k_mg_coarse_solve<true>, dim3(1, 1), kFusedBlock, kFusedSmem, C.D[l], f, L.x, 2 * C.ncoarse);
+            else LAUNCH_COOP_SMEM(ctx, k_mg_coarse_solve<false>, dim3(1, 1), kFusedBlock, kFusedSmem, C.D[l], f, L.x, 2 * C.ncoarse);
             return IMPEC_OK;
         }
         if (fused) {
@@ -1063,6 +1085,9 @@ extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info
     A.pin = -1; A.sig_idx = -1;
     LAUNCH(ctx, k_diag_inv, gr, kBlock, A, (const double *)nullptr, L0.DINV);
     if (L0.dist) TRY(exchange_rows(ctx, L0.DINV, L0.g, IMPEC_GH));
+    { const long long nn = (long long)grid_elems(L0.g);
+      LAUNCH(ctx, k_links_to_f32, dim3((unsigned)((nn + 255) / 256)), dim3(256), nn, (const double *)L0.AW, (const double *)L0.AS, (const double *)L0.AV, (const double *)L0.DINV,
+             L0.AWf, L0.ASf, L0.AVf, L0.DINVf); }
     Cycle C; C.ctx = ctx; C.D.assign(1, A); C.ncoarse = 1; C.w_from = 1; C.w_to = 0; C.nl = 1;
     double *x = ctx->ta;
     LAUNCH_COOP(ctx, k_cn_rhs, gr, kBlock, A, (const double *)ctx->c, ctx->rhs, x, ctx->part);

@@ -45,40 +45,52 @@ IMPEC_D void st2(double *p, double a, double b) {
 // shared-memory index of tile cell (r, jj): row-major, even columns in the first half of the row
 IMPEC_D int xi(int r, int jj) { return r * FT_W + ((jj & 1) << 6) + (jj >> 1); }
 
+// coefficient views: F32 = the cycle's FP32 copies, otherwise the FP64 arrays
+template <bool F32> struct Coef;
+template <> struct Coef<false> {
+    const double *AW, *AS, *AV, *DINV;
+    IMPEC_D Coef(const LevelDev &L) : AW(L.AW), AS(L.AS), AV(L.AV), DINV(L.DINV) {}
+};
+template <> struct Coef<true> {
+    const float *AW, *AS, *AV, *DINV;
+    IMPEC_D Coef(const LevelDev &L) : AW(L.AWf), AS(L.ASf), AV(L.AVf), DINV(L.DINVf) {}
+};
+
 // sum_nb a_nb x_nb for the cell `off` of the pair owned by lane tx in tile row r (k = its global index)
-IMPEC_D double tile_offsum(const LevelDev &L, const double *__restrict__ X, int r, int tx, int off, size_t k) {
-    const int ld = L.g.ld;
+template <class CF>
+IMPEC_D double tile_offsum(const CF &A, int ld, const double *__restrict__ X, int r, int tx, int off, size_t k) {
     const double *own = X + r * FT_W + (off << 6) + tx;                  // same column: rows r-1, r+1
     const double *oth = X + r * FT_W + ((1 - off) << 6) + tx + off;      // other plane: [-1] is column jj-1, [0] is jj+1
-    double s = L.AW[k] * own[-FT_W];
-    s = fma(L.AW[k + ld], own[FT_W], s);
-    s = fma(L.AS[k], oth[-1], s);
-    s = fma(L.AS[k + 1], oth[0], s);
-    s = fma(L.AV[k], oth[-FT_W - 1], s);
-    s = fma(L.AV[k + ld], oth[FT_W - 1], s);
-    s = fma(L.AV[k + 1], oth[-FT_W], s);
-    s = fma(L.AV[k + ld + 1], oth[FT_W], s);
+    double s = (double)A.AW[k] * own[-FT_W];
+    s = fma((double)A.AW[k + ld], own[FT_W], s);
+    s = fma((double)A.AS[k], oth[-1], s);
+    s = fma((double)A.AS[k + 1], oth[0], s);
+    s = fma((double)A.AV[k], oth[-FT_W - 1], s);
+    s = fma((double)A.AV[k + ld], oth[FT_W - 1], s);
+    s = fma((double)A.AV[k + 1], oth[-FT_W], s);
+    s = fma((double)A.AV[k + ld + 1], oth[FT_W], s);
     return s;
 }
 // the four diagonal terms only
-IMPEC_D double tile_diagsum(const LevelDev &L, const double *__restrict__ X, int r, int tx, int off, size_t k) {
-    const int ld = L.g.ld;
+template <class CF>
+IMPEC_D double tile_diagsum(const CF &A, int ld, const double *__restrict__ X, int r, int tx, int off, size_t k) {
     const double *oth = X + r * FT_W + ((1 - off) << 6) + tx + off;
-    double s = L.AV[k] * oth[-FT_W - 1];
-    s = fma(L.AV[k + ld], oth[FT_W - 1], s);
-    s = fma(L.AV[k + 1], oth[-FT_W], s);
-    s = fma(L.AV[k + ld + 1], oth[FT_W], s);
+    double s = (double)A.AV[k] * oth[-FT_W - 1];
+    s = fma((double)A.AV[k + ld], oth[FT_W - 1], s);
+    s = fma((double)A.AV[k + 1], oth[-FT_W], s);
+    s = fma((double)A.AV[k + ld + 1], oth[FT_W], s);
     return s;
 }
 
 // nsweeps > 1 (PLAIN only, and only when this single tile holds the WHOLE level so that no halo can go stale): the
 // sweeps alternate forward/backward starting with colour c0 -- the coarsest-level solve in one launch.
-template <int MODE, bool EDGE>
+template <int MODE, bool EDGE, bool F32>
 IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, const int c0,
                         const Grid &gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part, double *__restrict__ X, const int nsweeps = 1) {
     constexpr int HI = FusedGeom<MODE>::HI, TI = FusedGeom<MODE>::TI;
     const Grid g = L.g;
     const int ld = g.ld;
+    const Coef<F32> A(L);
     const int tx = threadIdx.x, ty = threadIdx.y & (FT_NTY - 1);
     const int jl = 2 * tx;                                   // local column of the pair
     const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ;          // global column of tile column 0 (even)
@@ -145,8 +157,8 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
             const bool act = colok && r >= shrink && r < FT_H - shrink && (!EDGE || (ig >= g.rlo && ig < g.rhi));
             if (act) {
                 const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld + off);
-                if (MODE == FUSED_PRE && s == 0) val = f[k] * L.DINV[k];
-                else val = (f[k] + tile_offsum(L, X, r, tx, off, k)) * L.DINV[k];
+                if (MODE == FUSED_PRE && s == 0) val = f[k] * (double)A.DINV[k];
+                else val = (f[k] + tile_offsum(A, ld, X, r, tx, off, k)) * (double)A.DINV[k];
             }
             nv[n] = val;
         }
@@ -193,9 +205,9 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
                 const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
                 const int ja = jl + off0, jb = jl + 1 - off0;
                 if (ja >= 2 && ja < FT_W - 2 && (!EDGE || (jg + off0 >= 0 && jg + off0 < g.N2 && (long long)(k + off0) != L.pin)))
-                    v0 = tile_offsum(L, X, r, tx, off0, k + off0);
+                    v0 = tile_offsum(A, ld, X, r, tx, off0, k + off0);
                 if (jb >= 2 && jb < FT_W - 2 && (!EDGE || (jg + 1 - off0 >= 0 && jg + 1 - off0 < g.N2 && (long long)(k + 1 - off0) != L.pin)))
-                    v1 = tile_diagsum(L, X, r, tx, 1 - off0, k + 1 - off0);
+                    v1 = tile_diagsum(A, ld, X, r, tx, 1 - off0, k + 1 - off0);
             }
             ra[n] = off0 == 0 ? v0 : v1;                                 // even-column cell
             rb[n] = off0 == 0 ? v1 : v0;                                 // odd-column cell
@@ -233,7 +245,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     }
 }
 
-template <int MODE>
+template <int MODE, bool F32>
 __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_fused(LevelDev L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, int c0,
                                                                Grid gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part) {
     IMPEC_DYN_SMEM(double, X);
@@ -245,15 +257,16 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_fused(LevelDev L, cons
         const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
         edge = edge || (pi >= i0 && pi < i0 + FT_H && pj >= j0 && pj < j0 + FT_W);
     }
-    if (edge) fused_body<MODE, true>(L, f, xin, x, c0, gc, ec, fc, part, X);
-    else fused_body<MODE, false>(L, f, xin, x, c0, gc, ec, fc, part, X);
+    if (edge) fused_body<MODE, true, F32>(L, f, xin, x, c0, gc, ec, fc, part, X);
+    else fused_body<MODE, false, F32>(L, f, xin, x, c0, gc, ec, fc, part, X);
 }
 
 // Coarsest-level solve: `nsweeps` alternating red-black sweeps from a zero guess in ONE launch.  Requires that a
 // single tile holds the whole level (N1 <= FT_H - 4, N2 <= FT_TJ), which the host checks.
+template <bool F32>
 __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_coarse_solve(LevelDev L, const double *__restrict__ f, double *__restrict__ x, int nsweeps) {
     IMPEC_DYN_SMEM(double, X);
-    fused_body<FUSED_PLAIN, true>(L, f, (const double *)nullptr, x, 0, L.g, (const double *)nullptr, (double *)nullptr, (double *)nullptr, X, nsweeps);
+    fused_body<FUSED_PLAIN, true, F32>(L, f, (const double *)nullptr, x, 0, L.g, (const double *)nullptr, (double *)nullptr, (double *)nullptr, X, nsweeps);
 }
 
 // ---------------------------------------------------------------- fused PCG search-direction update + mat-vec
@@ -297,9 +310,10 @@ IMPEC_D void pcg_matvec_body_rw(const LevelDev &L, const double *__restrict__ sc
         const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
         const double da = X[r * FT_W + tx], db = X[r * FT_W + 64 + tx];
         const bool two = !EDGE || jg + 1 < g.N2;
-        double sa = ((long long)k == L.pin) ? 0. : link_diag(L, k) * da - tile_offsum(L, X, r, tx, 0, k);
+        const Coef<false> A(L);
+        double sa = ((long long)k == L.pin) ? 0. : link_diag(L, k) * da - tile_offsum(A, ld, X, r, tx, 0, k);
         double sb = 0.;
-        if (two) sb = ((long long)(k + 1) == L.pin) ? 0. : link_diag(L, k + 1) * db - tile_offsum(L, X, r, tx, 1, k + 1);
+        if (two) sb = ((long long)(k + 1) == L.pin) ? 0. : link_diag(L, k + 1) * db - tile_offsum(A, ld, X, r, tx, 1, k + 1);
         if (two) { st2(d + k, da, db); st2(s + k, sa, sb); } else { d[k] = da; s[k] = sa; }
         dotv = fma(sa, da, dotv);
         if (two) dotv = fma(sb, db, dotv);

@@ -137,6 +137,9 @@ struct LevelDev {
     Grid g;
     const double *AW, *AS, *AV;
     const double *DINV;          // 1/diag (0 at the pinned cell), built once per operator by k_diag_inv
+    // FP32 copies of the four coefficient arrays, read by the multigrid cycle kernels only (the arithmetic stays FP64
+    // and the PCG mat-vec uses the FP64 links, so this changes the preconditioner by ~6e-8 relative, not the solution)
+    const float *AWf, *ASf, *AVf, *DINVf;
     double mass;                 // 0 elliptic, 1 Crank-Nicolson
     long long pin;               // fine level: padded index of the Dirichlet cell (or -1)
     long long sig_idx;           // coarse levels: padded index of the cell carrying the pin's diagonal shift
@@ -174,6 +177,14 @@ __global__ void __launch_bounds__(256) k_smooth_color(LevelDev L, int color, con
     const size_t k = gidx(L.g, i, j);
     if (((i + j) & 1) != color || (long long)k == L.pin) { xout[k] = ZERO ? 0. : xin[k]; return; }
     xout[k] = ZERO ? f[k] * L.DINV[k] : (f[k] + link_offsum(L, xin, k)) * L.DINV[k];
+}
+
+// FP32 copies of the coefficient arrays over ALL allocated rows (halo rows included, so no extra exchange)
+__global__ void __launch_bounds__(256) k_links_to_f32(long long n, const double *__restrict__ AW, const double *__restrict__ AS, const double *__restrict__ AV,
+                                                      const double *__restrict__ DINV, float *__restrict__ AWf, float *__restrict__ ASf, float *__restrict__ AVf, float *__restrict__ DINVf) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    AWf[k] = (float)AW[k]; ASf[k] = (float)AS[k]; AVf[k] = (float)AV[k]; DINVf[k] = (float)DINV[k];
 }
 
 // DINV = 1/diag on the interior (0 at the pinned cell); sigma (the pin's diagonal shift on coarse levels) is read

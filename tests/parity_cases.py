@@ -109,9 +109,15 @@ def check_vcycle(emulated, N1=32, N2=32, stype=O.PARALLEL, nu=2.0 / 3.0):
     r = np.random.default_rng(1).standard_normal(N1 * N2)
     zo = np.zeros(N1 * N2)
     assert lib.orc_mg_apply(C.byref(Po), N1, N2, A, -1, r, zo) == 0
-    ctx.upload_c(c); ctx.upload_q(q); ctx.build_operator()
+    ctx.upload_c(c); ctx.upload_q(q)
+    # the cycle kernels normally read FP32 copies of the coefficients (a 6e-8 relative perturbation of the
+    # preconditioner, none of the solution): strict parity with FP64 coefficients, loose parity with the default
+    ctx.set_option("mg_links_fp32", 0); ctx.build_operator()
     zg = ctx.vcycle(r)
     assert np.abs(zg - zo).max() <= TOL_VCYCLE * np.abs(zo).max()
+    ctx.set_option("mg_links_fp32", 1); ctx.build_operator()
+    zg = ctx.vcycle(r)
+    assert np.abs(zg - zo).max() <= 1e-5 * np.abs(zo).max()
     ctx.close()
 
 
@@ -187,7 +193,7 @@ def check_fused_vs_unfused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
     out = []
     for fused in (0, 1):
         ctx = I.Context(Pi, emulated=emulated)
-        ctx.set_option("mg_fused", fused)
+        ctx.set_option("mg_fused", fused); ctx.set_option("mg_links_fp32", 0)
         ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
         z1 = ctx.vcycle(r); z2 = ctx.vcycle(r)
         assert np.array_equal(z1, z2), "cycle is not repeatable (race?)"
