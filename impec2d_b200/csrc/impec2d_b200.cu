@@ -5,6 +5,7 @@
 #include "kernels_transport.inl"
 #include "kernels_pressure.inl"
 #include "kernels_fused.inl"
+#include "kernels_staged.inl"
 #include "../../include/impec2d_b200.h"
 
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
@@ -57,6 +58,7 @@ struct impec_ctx {
     bool mob_valid = false, op_valid = false;
     bool warm_start = false;
     bool fused = true;                              // fused tile kernels (kernels_fused.inl) vs one kernel per colour pass
+    bool staged = true;                             // cp.async-staged 32-row tile kernels (kernels_staged.inl); needs links_f32
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
     long long launches = 0;
     std::string err;
@@ -350,6 +352,9 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     SMEM_ATTR((k_mg_fused<FUSED_POST, true>)); SMEM_ATTR((k_mg_fused<FUSED_POST, false>));
     SMEM_ATTR(k_mg_coarse_solve<true>); SMEM_ATTR(k_mg_coarse_solve<false>);
 #undef SMEM_ATTR
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
 #endif
@@ -431,6 +436,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     const std::string k(key ? key : "");
     if (k == "warm_start") { ctx->warm_start = value != 0.0; return IMPEC_OK; }
     if (k == "mg_fused") { ctx->fused = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
@@ -638,6 +644,11 @@ static int smooth(Cycle &C, int l, const double *f, double *x, bool forward, boo
 // ---- fused path (kernels_fused.inl)
 static const dim3 kFusedBlock(FT_W / 2, FT_NTY);
 static const int kFusedSmem = FT_W * FT_H * (int)sizeof(double);
+static const dim3 kStagedBlock(FT_W / 2, ST_NTY);
+template <int MODE> static dim3 staged_grid(const Grid &g) {
+    return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + StagedGeom<MODE>::TI - 1) / StagedGeom<MODE>::TI));
+}
+static bool use_staged(const impec_ctx *ctx) { return ctx->staged && ctx->links_f32; }
 template <int MODE> static dim3 fused_grid(const Grid &g) {
     return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + FusedGeom<MODE>::TI - 1) / FusedGeom<MODE>::TI));
 }
@@ -645,7 +656,9 @@ template <int MODE> static dim3 fused_grid(const Grid &g) {
 // they read L.x, write L.t and the two pointers are swapped (the level's current iterate is always L.x).
 static int fused_plain(Cycle &C, int l, const double *f, bool forward) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
-    if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PLAIN, true>), fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
+    if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PLAIN>, staged_grid<FUSED_PLAIN>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
+                     (const double *)nullptr, (double *)nullptr, (double *)nullptr);
+    else if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PLAIN, true>), fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
                      (const double *)nullptr, (double *)nullptr, (double *)nullptr);
     else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PLAIN, false>), fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
                      (const double *)nullptr, (double *)nullptr, (double *)nullptr);
@@ -661,7 +674,9 @@ static const double *coarse_x_view(const impec_ctx *ctx, int l) {
 static int fused_pre(Cycle &C, int l, const double *f) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
     const bool tr = at_transition(ctx, l);
-    if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PRE, true>), fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
+    if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PRE>, staged_grid<FUSED_PRE>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
+                     (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
+    else if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PRE, true>), fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
                      (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
     else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PRE, false>), fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
                      (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
@@ -676,8 +691,10 @@ static int gather_coarse_rhs(impec_ctx *ctx, int l) {
 }
 static int fused_post(Cycle &C, int l, const double *f, double *part, long long *nparts) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
-    const dim3 gr = fused_grid<FUSED_POST>(L.g);
-    if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_POST, true>), gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
+    const dim3 gr = use_staged(ctx) ? staged_grid<FUSED_POST>(L.g) : fused_grid<FUSED_POST>(L.g);
+    if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_POST>, gr, kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
+                     coarse_x_view(ctx, l), (double *)nullptr, part);
+    else if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_POST, true>), gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
                      coarse_x_view(ctx, l), (double *)nullptr, part);
     else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_POST, false>), gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
                      coarse_x_view(ctx, l), (double *)nullptr, part);

@@ -25,6 +25,12 @@
 #define IMPEC_SYNCTHREADS() __syncthreads()
 #define IMPEC_HD __host__ __device__ __forceinline__
 #define IMPEC_D __device__ __forceinline__
+// 16-byte asynchronous global->shared copy (LDGSTS, bypasses L1) and its completion wait
+__device__ __forceinline__ void impec_cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void impec_cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory"); }
 #else
 // ------------------------------------------------------------------------------------ emulator
 #include <functional>
@@ -65,6 +71,8 @@ double shfl(double v, int src_lane_delta, int mode);   // mode 0 down, 1 up, 2 i
 #define IMPEC_SYNCTHREADS() emu::syncthreads()
 #define IMPEC_HD inline
 #define IMPEC_D inline
+inline void impec_cp_async16(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 16); }
+inline void impec_cp_async_wait_all() {}
 inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }

@@ -237,3 +237,21 @@ def check_dispersion(emulated, N1=32, N2=32, stype=O.PARALLEL, steps=1):
     cg = ctx.download_c()
     assert np.abs(cg - co).max() <= 1e-8
     ctx.close()
+
+
+def check_staged_vs_fused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
+    """The cp.async-staged 32-row tile kernels against the 64-row fused kernels, both on FP32 coefficient copies:
+    same arithmetic per cell, so the cycle must agree bit for bit."""
+    base, Po, c, q = production_case(N1, N2, stype=stype)
+    Pi = I.default_params(emulated=emulated, **base)
+    r = np.random.default_rng(2).standard_normal(N1 * N2)
+    out = []
+    for staged in (0, 1):
+        ctx = I.Context(Pi, emulated=emulated)
+        ctx.set_option("mg_links_fp32", 1); ctx.set_option("mg_staged", staged)
+        ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
+        z1 = ctx.vcycle(r); z2 = ctx.vcycle(r)
+        assert np.array_equal(z1, z2), "cycle is not repeatable (race?)"
+        out.append(z1)
+        ctx.close()
+    assert np.array_equal(out[0], out[1]), np.abs(out[0] - out[1]).max()

@@ -39,3 +39,4 @@ def test_elliptic_manufactured_9pt(): pc.check_elliptic_manufactured(True, 20, 3
 def test_fused_vs_unfused_cycle(): pc.check_fused_vs_unfused(True, 256, 384)
 def test_dispersion_parallel(): pc.check_dispersion(True, 32, 32)
 def test_dispersion_diagonal_rect(): pc.check_dispersion(True, 32, 16, stype=O.DIAGONAL)
+def test_staged_vs_fused_cycle(): pc.check_staged_vs_fused(True, 256, 384)
