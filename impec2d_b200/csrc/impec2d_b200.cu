@@ -58,7 +58,9 @@ struct impec_ctx {
     bool mob_valid = false, op_valid = false;
     bool warm_start = false;
     bool fused = true;                              // fused tile kernels (kernels_fused.inl) vs one kernel per colour pass
-    bool staged = true;                             // cp.async-staged 32-row tile kernels (kernels_staged.inl); needs links_f32
+    bool staged = false;                            // cp.async-staged 32-row tile kernels (kernels_staged.inl); needs links_f32.
+                                                    // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
+    bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
     long long launches = 0;
     std::string err;
@@ -238,6 +240,26 @@ static int exchange_rows(impec_ctx *ctx, double *a, const Grid &g, int n) {
     const bool prev = !g.wall_lo, next = !g.wall_hi;
     return comm_sendrecv(ctx, prev ? a + (size_t)IMPEC_GH * ld : nullptr, prev ? a + (size_t)(IMPEC_GH - n) * ld : nullptr,
                          next ? a + (size_t)(g.N1 - n + IMPEC_GH) * ld : nullptr, next ? a + (size_t)(g.N1 + IMPEC_GH) * ld : nullptr, (long long)n * g.ld);
+}
+// two fields in one NCCL group (one launch instead of two)
+static int exchange_rows2(impec_ctx *ctx, double *a, double *b, const Grid &g, int n) {
+    if (ctx->nranks == 1 || (g.wall_lo && g.wall_hi)) return IMPEC_OK;
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (!ctx->has_cb && b) {
+        TRY(comm_check(ctx));
+        const size_t ld = (size_t)g.ld; const size_t cnt = (size_t)n * ld;
+        NCCL_TRY(ctx, ncclGroupStart());
+        for (double *f : {a, b}) {
+            if (!g.wall_lo) { NCCL_TRY(ctx, ncclSend(f + (size_t)IMPEC_GH * ld, cnt, ncclDouble, ctx->rank - 1, ctx->nccl, ctx->stream)); NCCL_TRY(ctx, ncclRecv(f + (size_t)(IMPEC_GH - n) * ld, cnt, ncclDouble, ctx->rank - 1, ctx->nccl, ctx->stream)); }
+            if (!g.wall_hi) { NCCL_TRY(ctx, ncclSend(f + (size_t)(g.N1 - n + IMPEC_GH) * ld, cnt, ncclDouble, ctx->rank + 1, ctx->nccl, ctx->stream)); NCCL_TRY(ctx, ncclRecv(f + (size_t)(g.N1 + IMPEC_GH) * ld, cnt, ncclDouble, ctx->rank + 1, ctx->nccl, ctx->stream)); }
+        }
+        NCCL_TRY(ctx, ncclGroupEnd());
+        return IMPEC_OK;
+    }
+#endif
+    TRY(exchange_rows(ctx, a, g, n));
+    if (b) TRY(exchange_rows(ctx, b, g, n));
+    return IMPEC_OK;
 }
 extern "C" int impec_ctx_set_comm_callbacks(impec_ctx *ctx, const impec_comm_callbacks *cb) {
     if (!cb || !cb->sendrecv || !cb->allreduce || !cb->allgather || !cb->bcast) return fail(ctx, IMPEC_ERR_ARG, "incomplete callback table");
@@ -436,6 +458,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     const std::string k(key ? key : "");
     if (k == "warm_start") { ctx->warm_start = value != 0.0; return IMPEC_OK; }
     if (k == "mg_fused") { ctx->fused = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
     if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
@@ -865,6 +888,7 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
     const double bi_prod = ctx->h_scal[S_BIPROD];
     double i_prod = ctx->h_scal[S_IPROD];
     int it = 0, converged = 0;
+    double last_true = -1.;
     if (!(bi_prod > 0.)) converged = 1;                          // b = 0  =>  x = 0 (HYPRE returns immediately)
     else if (i_prod / bi_prod < eps * eps) converged = 1;
     int ig = S_GAMMA0;                                           // which scalar slot holds the current gamma
@@ -886,8 +910,7 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         it++;
         if (fuse_dir) {
             // beta = gamma_new / gamma_old sits in scal[S_BETA_NUM], scal[S_BETA_DEN] (set at the end of the previous pass)
-            TRY(exchange_rows(ctx, ctx->L[0].x, g, 1));
-            if (!first_dir) TRY(exchange_rows(ctx, dcur, g, 1));
+            TRY(exchange_rows2(ctx, ctx->L[0].x, first_dir ? nullptr : dcur, g, 1));
             if (first_dir) LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<true>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
             else LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
             std::swap(dcur, dalt); first_dir = false;
@@ -905,6 +928,19 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         i_prod = ctx->h_scal[S_IPROD];
         if (i_prod / bi_prod < eps * eps) { converged = 1; break; }
         if (!(i_prod == i_prod)) return fail(ctx, IMPEC_ERR_NOCONV, "PCG produced NaN at iteration %d", it);
+        if (ctx->stagnation_guard && it >= 8 && it % 3 == 2) {
+            // Optional: eps = 1e-14 is below what FP64 can deliver on large grids; the recurrence residual keeps
+            // falling while b - A x does not.  Every third iteration compare the two; stop when the true residual is an
+            // order of magnitude above the recurrence value and no longer improving.
+            TRY(exchange_rows(ctx, x, g, 2));
+            LAUNCH(ctx, k_residual, gres, kBlock, A, rhs, (const double *)x, ctx->s);
+            LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->s, ctx->s, ctx->part);
+            TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_TMP));
+            TRY(fetch_scalars(ctx, S_TMP, 1));
+            const double true_prod = ctx->h_scal[S_TMP];
+            if (true_prod > 100. * i_prod && last_true > 0. && true_prod > 0.25 * last_true) { converged = 2; break; }
+            last_true = true_prod;
+        }
         TRY(mg_cycle(C, 0, ctx->r, ctx->part, &dparts));
         if (!dparts) { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->L[0].x, ctx->part); dparts = nparts; }
         TRY(reduce_final(ctx, RED_SUM, dparts, 1, 0, S_BETA_NUM));
@@ -924,6 +960,7 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         info->relres = bi_prod > 0. ? sqrt(i_prod / bi_prod) : 0.;
         info->true_relres = bi_prod > 0. ? sqrt(ctx->h_scal[S_TMP] / bi_prod) : 0.;
     }
+    if (info && converged == 2) info->converged = 2;          // stopped by the stagnation guard at the attainable accuracy
     return converged ? IMPEC_OK : fail(ctx, IMPEC_ERR_NOCONV, "PCG did not reach eps=%g in %d iterations (relres %g)", eps, it, sqrt(i_prod / bi_prod));
 }
 

@@ -74,7 +74,7 @@ typedef struct impec_solve_info {
     int    iterations;                /* PCG iterations (MGSolver::num_iterations)                  */
     double relres;                    /* recurrence ||r||/||b||, the quantity HYPRE's PCG tests      */
     double true_relres;               /* ||b - A x||/||b|| recomputed after the solve               */
-    int    converged;
+    int    converged;                 /* 1 = recurrence criterion met; 2 = stopped by the optional stagnation guard     */
 } impec_solve_info;
 
 typedef struct impec_ctx impec_ctx;
@@ -156,7 +156,10 @@ int   impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host); /* one
 int   impec_mg_levels(const impec_ctx *ctx);
 long long impec_kernel_launches(const impec_ctx *ctx);                   /* kernels launched by this context so far */
 int   impec_reset_state(impec_ctx *ctx);                                 /* produced mass := 0, sweep parity := Y */
-int   impec_set_option(impec_ctx *ctx, const char *key, double value);   /* e.g. "warm_start" */
+/* options: "warm_start" (x0 = previous p instead of the reference's 0), "stagnation_guard" (stop PCG at the FP64
+ * residual floor instead of iterating the recurrence residual down to eps), "mg_fused", "mg_links_fp32", "mg_staged",
+ * "mg_graph", "mg_w_from", "mg_w_to", "mg_ncoarse", "max_iter".  Defaults reproduce the reference's semantics. */
+int   impec_set_option(impec_ctx *ctx, const char *key, double value);
 /* average device time of one named piece of the path ("smooth_sweep", "residual", "vcycle", "sweep_x", ...) over
  * `reps` launches, measured with CUDA events on the context stream */
 int   impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, double *avg_ms);
