@@ -230,20 +230,27 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     # Algorithmic bytes per fine-level launch (FP64, each distinct array once; DESIGN.md "kernels"):
-    #   k_mg_fused<POST>  : R x,f,AW,AS,AV,DINV (48) + coarse e (2) + W x (8)       = 58 B/cell
-    #   k_mg_fused<PRE>   : R f,AW,AS,AV,DINV (40) + W x (8) + coarse f (2)         = 50 B/cell
-    #   k_mg_fused<PLAIN> : R x,f,AW,AS,AV,DINV (48) + W x (8)                      = 56 B/cell
+    #   k_mg_fused<POST>  : R x,f (16) + FP32 AW,AS,AV,DINV (16) + coarse e (2) + W x (8)   = 42 B/cell
+    #   k_mg_fused<PRE>   : R f (8) + FP32 AW,AS,AV,DINV (16) + W x (8) + coarse f (2)     = 34 B/cell
+    #   k_mg_fused<PLAIN> : R x,f (16) + FP32 coefficients (16) + W x (8)                   = 40 B/cell
     #   k_pcg_matvec      : R z,d,AW,AS,AV (40) + W d,s (16)                        = 56 B/cell
-    #   one multigrid cycle, all levels                        = 208 B/cell
+    #   one multigrid cycle, all levels: SURVEY 8d's model figure (unfused, FP64 coefficients) = 208 B/cell
     cells = float(N) * N / world                   # cells per GPU: the kernels are timed on this rank's slab
-    kb = {"fused_post": 58.0, "fused_pre": 50.0, "fused_plain": 56.0, "pcg_matvec": 56.0, "matvec_dot": 40.0, "update_xr": 48.0, "update_d": 24.0,
+    kb = {"fused_post": 42.0, "fused_pre": 34.0, "fused_plain": 40.0, "pcg_matvec": 56.0, "matvec_dot": 40.0, "update_xr": 48.0, "update_d": 24.0,
           "sweep_x": 24.0, "sweep_y": 24.0, "residual": 48.0, "smooth_sweep": 48.0}
     per_kernel = {k: {"ms": prof[k], "algorithmic_bytes": kb[k] * cells, "achieved_gbs": kb[k] * cells / (prof[k] * 1e-3) / 1e9,
                       "frac": kb[k] * cells / (prof[k] * 1e-3) / 1e9 / peak} for k in kb}
     dom = "fused_post"
+    traffic = None                                 # measured DRAM bytes of the dominant kernel from the committed ncu capture (same grid, 1 GPU)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+        if tr.get("grid") == [N, N] and world == 1:
+            traffic = tr.get(dom)
+    except Exception:
+        pass
     vc_bytes = 208.0 * float(N) * N / world
     roofline = {"bound": "hbm", "kernel": "k_mg_fused<FUSED_POST> (prolong + correct + red-black post-smooth + <r,z>, fine level)",
-                "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": None,
+                "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_kernel[dom]["algorithmic_bytes"],
                 "vcycle": {"ms": prof["vcycle"], "algorithmic_bytes": vc_bytes, "achieved": vc_bytes / (prof["vcycle"] * 1e-3) / 1e9,
                            "frac": vc_bytes / (prof["vcycle"] * 1e-3) / 1e9 / peak},
@@ -284,6 +291,7 @@ def main():
                 "config": {"workload": workload, "grid": [N, N], "eps": args.eps, "stop_rule": "<r,r>/<b,b> < eps^2, recurrence residual, x0 = 0 (HYPRE StructPCG semantics)",
                            "pcg_iterations": its, "relres": relres, "true_relres": true_rr, "mg_levels": ctx.mg_levels(),
                            "parallelism": "1 GPU" if world == 1 else "%d slabs of %d rows (halo send/recv over NCCL; multigrid levels below %d rows per slab replicated after an all-gather)" % (world, nrows, 8),
+                           "coefficients": "multigrid cycle reads FP32 copies of the link/diagonal arrays (all arithmetic FP64; PCG mat-vec uses the FP64 operator)",
                            "l2": "inputs larger than L2 (every field is %.2f GB)" % (8.0 * N * N / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "vcycle_ms": prof["vcycle"]}
