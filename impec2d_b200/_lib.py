@@ -64,6 +64,7 @@ EXPORTS = [
     "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_reset_state", "impec_set_option",
     "impec_profile_kernel", "impec_init_source", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
     "impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows", "impec_init_source_rows", "impec_synth_state_rows",
+    "impec_comm_backend",
 ]
 
 
@@ -92,6 +93,7 @@ def load(emulated=False):
     L.impec_ctx_create.argtypes = [C.POINTER(Params), i, i, i, C.c_char_p, vp, C.POINTER(vp)]
     L.impec_ctx_destroy.argtypes = [vp]; L.impec_ctx_destroy.restype = None
     L.impec_last_error.argtypes = [vp]; L.impec_last_error.restype = C.c_char_p
+    L.impec_comm_backend.argtypes = [vp]; L.impec_comm_backend.restype = C.c_char_p
     L.impec_synchronize.argtypes = [vp]
     for n in ("impec_upload_c", "impec_upload_p", "impec_upload_q", "impec_upload_velocity",
               "impec_download_c", "impec_download_p", "impec_download_velocity"):

@@ -134,6 +134,7 @@ class Context:
     def reset_state(self): self._chk(self.L.impec_reset_state(self._h))
     def set_option(self, key, value): self._chk(self.L.impec_set_option(self._h, key.encode(), float(value)))
     def synchronize(self): self._chk(self.L.impec_synchronize(self._h))
+    def comm_backend(self): return self.L.impec_comm_backend(self._h).decode()
 
     def local_rows(self):
         r0 = C.c_int(); n = C.c_int()

@@ -6,6 +6,7 @@
 #include "kernels_pressure.inl"
 #include "kernels_fused.inl"
 #include "kernels_staged.inl"
+#include "kernels_small.inl"
 #include "../../include/impec2d_b200.h"
 
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
@@ -20,6 +21,7 @@
 
 #define BX 32
 #define BY 8
+#include "comm_p2p.inl"
 
 // ------------------------------------------------------------------------------------------------
 struct Level {
@@ -29,6 +31,7 @@ struct Level {
     double *x = nullptr, *f = nullptr, *t = nullptr, *r = nullptr;
     long long pin = -1, sig_idx = -1;
     bool dist = false;           // rows of this level are slab-distributed over the ranks
+    int th = 64;                 // tile height of the fused kernels on this level (64 / 32 / 16)
     // first replicated level only: this rank's slab view of it and slab-sized staging for the all-gathers
     Grid gl; double *AWl = nullptr, *ASl = nullptr, *AVl = nullptr, *fl = nullptr;
 };
@@ -62,6 +65,7 @@ struct impec_ctx {
                                                     // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
     bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
+    bool use_small = true;                          // levels of <= SM_MAXCELLS cells: whole V-cycle in one single-CTA launch (kernels_small.inl)
     long long launches = 0;
     std::string err;
     std::vector<void *> allocs;
@@ -73,6 +77,13 @@ struct impec_ctx {
     ncclComm_t nccl = nullptr;
 #endif
     bool comm_ready = false;
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    // peer-memory transport (comm_p2p.inl): my mailbox, the mapped mailboxes of the other ranks, exchange epochs
+    bool p2p = false;
+    unsigned char *mail = nullptr, *peer_mail[P2P_MAXR] = {};
+    size_t p2p_slot_bytes = 0;
+    unsigned long long halo_epoch = 0, ar_epoch = 0;
+#endif
     // CUDA graph of the replicated multigrid tail (levels >= tail_level): identical launch sequence every visit
     int tail_level = -1;
     bool use_graph = true, graph_ready = false;
@@ -84,7 +95,7 @@ struct impec_ctx {
 };
 
 enum { S_GAMMA0 = 0, S_SDOTP = 1, S_IPROD = 2, S_GAMMA1 = 3, S_BIPROD = 4, S_BETA_NUM = 5, S_BETA_DEN = 6, S_TMP = 7, S_SRC = 8, S_OUTFLUX = 9,
-       S_DIAG = 10, S_DT = 20, S_NSCAL = 32 };
+       S_DIAG = 10, S_DT = 20, S_ERR = 31, S_NSCAL = 32 };
 
 static int fail(impec_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
@@ -172,7 +183,13 @@ static int reduce_final(impec_ctx *ctx, int op, long long nparts, int count, lon
 }
 static int fetch_scalars(impec_ctx *ctx, int idx, int n) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal + idx, ctx->scal + idx, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->p2p) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scal + S_ERR, ctx->scal + S_ERR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+#endif
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->p2p && ctx->h_scal[S_ERR] != 0.) return fail(ctx, IMPEC_ERR_NCCL, "peer-memory exchange timed out waiting for a neighbouring rank");
+#endif
     return IMPEC_OK;
 }
 
@@ -200,11 +217,15 @@ static int comm_sendrecv(impec_ctx *ctx, const double *send_lo, double *recv_lo,
     return fail(ctx, IMPEC_ERR_NCCL, "no communication back end");
 #endif
 }
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+static int p2p_allreduce(impec_ctx *ctx, double *buf, int n, int op);
+#endif
 static int comm_allreduce(impec_ctx *ctx, double *buf, int n, int op) {
     if (ctx->nranks == 1) return IMPEC_OK;
     TRY(comm_check(ctx));
     if (ctx->has_cb) { if (ctx->cb.allreduce(ctx->cb.user, buf, n, op)) return fail(ctx, IMPEC_ERR_NCCL, "allreduce callback failed"); return IMPEC_OK; }
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->p2p && n <= P2P_AR_MAXN) return p2p_allreduce(ctx, buf, n, op);
     NCCL_TRY(ctx, ncclAllReduce(buf, buf, (size_t)n, ncclDouble, op == RED_SUM ? ncclSum : (op == RED_MAX ? ncclMax : ncclMin), ctx->nccl, ctx->stream));
     return IMPEC_OK;
 #else
@@ -232,10 +253,89 @@ static int comm_bcast(impec_ctx *ctx, double *buf, long long n, int root) {
     return fail(ctx, IMPEC_ERR_NCCL, "no communication back end");
 #endif
 }
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+// ---- peer-memory transport (comm_p2p.inl)
+static const size_t kP2PHaloOff = P2P_FLAG_BYTES + P2P_AR_BYTES;
+static int p2p_setup(impec_ctx *ctx) {
+    const int R = ctx->nranks;
+    if (R < 2 || !ctx->comm_ready) return IMPEC_OK;
+    const char *e = getenv("IMPEC_P2P");
+    int ok = (e && atoi(e) == 0) ? 0 : 1;
+    if (R > P2P_MAXR) ok = 0;
+    // mailbox: flags | all-reduce records | 2 sides x 2 parities of (2 fields x IMPEC_GH rows of the fine level)
+    ctx->p2p_slot_bytes = (size_t)2 * IMPEC_GH * ctx->g.ld * sizeof(double);
+    const size_t bytes = kP2PHaloOff + 4 * ctx->p2p_slot_bytes;
+    void *m = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&m, bytes));
+    CUDA_TRY(ctx, cudaMemsetAsync(m, 0, bytes, ctx->stream));
+    ctx->allocs.push_back(m); ctx->mail = (unsigned char *)m;
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, m) != cudaSuccess) { cudaGetLastError(); ok = 0; memset(&mine, 0, sizeof(mine)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+    double *hb = nullptr;
+    TRY(dev_alloc(ctx, &hb, (size_t)R * 8));
+    CUDA_TRY(ctx, cudaMemcpyAsync((char *)hb + (size_t)ctx->rank * 64, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(ctx, ncclAllGather((char *)hb + (size_t)ctx->rank * 64, hb, 64, ncclChar, ctx->nccl, ctx->stream));
+    std::vector<cudaIpcMemHandle_t> all(R);
+    CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), hb, (size_t)R * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < R && ok; r++) {
+        if (r == ctx->rank) { ctx->peer_mail[r] = ctx->mail; continue; }
+        void *pm = nullptr;
+        if (cudaIpcOpenMemHandle(&pm, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        ctx->peer_mail[r] = (unsigned char *)pm;
+    }
+    // every rank must take the same path
+    double flag = ok;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal + S_TMP, &flag, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(ctx, ncclAllReduce(ctx->scal + S_TMP, ctx->scal + S_TMP, 1, ncclDouble, ncclMin, ctx->nccl, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&flag, ctx->scal + S_TMP, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->p2p = flag > 0.5;
+    if (!ctx->p2p)
+        for (int r = 0; r < R; r++) { if (r != ctx->rank && ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]); ctx->peer_mail[r] = nullptr; }
+    return IMPEC_OK;
+}
+static int p2p_exchange(impec_ctx *ctx, double *a, double *b, const Grid &g, int n) {
+    HaloArgs h;
+    h.fld[0] = a; h.fld[1] = b; h.nfld = b ? 2 : 1;
+    h.cnt = (long long)n * g.ld;
+    const long long ld = g.ld;
+    h.send_lo = (long long)IMPEC_GH * ld; h.recv_lo = (long long)(IMPEC_GH - n) * ld;
+    h.send_hi = (long long)(g.N1 - n + IMPEC_GH) * ld; h.recv_hi = (long long)(g.N1 + IMPEC_GH) * ld;
+    h.epoch = ++ctx->halo_epoch;
+    const size_t par = (size_t)(h.epoch & 1);
+    unsigned char *me = ctx->mail;
+    unsigned char *prev = g.wall_lo ? nullptr : ctx->peer_mail[ctx->rank - 1], *next = g.wall_hi ? nullptr : ctx->peer_mail[ctx->rank + 1];
+    // side 0 of a mailbox receives from the owner's previous rank, side 1 from its next rank
+    h.rem_lo = prev ? (double *)(prev + kP2PHaloOff + (2 + par) * ctx->p2p_slot_bytes) : nullptr;
+    h.rem_lo_flag = prev ? (unsigned long long *)prev + 64 : nullptr;
+    h.rem_hi = next ? (double *)(next + kP2PHaloOff + (0 + par) * ctx->p2p_slot_bytes) : nullptr;
+    h.rem_hi_flag = next ? (unsigned long long *)next : nullptr;
+    h.my_lo = (const double *)(me + kP2PHaloOff + (0 + par) * ctx->p2p_slot_bytes); h.my_lo_flag = (const unsigned long long *)me;
+    h.my_hi = (const double *)(me + kP2PHaloOff + (2 + par) * ctx->p2p_slot_bytes); h.my_hi_flag = (const unsigned long long *)me + 64;
+    h.err = ctx->scal + S_ERR;
+    LAUNCH(ctx, k_halo_p2p, dim3(P2P_NCTA), dim3(P2P_THREADS), h);
+    return IMPEC_OK;
+}
+static int p2p_allreduce(impec_ctx *ctx, double *buf, int n, int op) {
+    ArArgs a;
+    a.buf = buf; a.n = n; a.op = op; a.rank = ctx->rank; a.nranks = ctx->nranks;
+    for (int r = 0; r < P2P_MAXR; r++) a.mail[r] = r < ctx->nranks ? (double *)(ctx->peer_mail[r] + P2P_FLAG_BYTES) : nullptr;
+    a.epoch = ++ctx->ar_epoch;
+    a.err = ctx->scal + S_ERR;
+    LAUNCH(ctx, k_allreduce_p2p, dim3(1), dim3(32), a);
+    return IMPEC_OK;
+}
+#endif
+
 // Halo rows of a slab field: my first n rows go to the previous rank's rows [N1, N1+n), my last n rows to the next
 // rank's rows [-n, 0).  Works unchanged for face/vertex arrays (their row N1 duplicates the neighbour's row 0).
 static int exchange_rows(impec_ctx *ctx, double *a, const Grid &g, int n) {
     if (ctx->nranks == 1 || (g.wall_lo && g.wall_hi)) return IMPEC_OK;
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->p2p && !ctx->has_cb && (size_t)n * g.ld * sizeof(double) <= ctx->p2p_slot_bytes) return p2p_exchange(ctx, a, nullptr, g, n);
+#endif
     const size_t ld = (size_t)g.ld;
     const bool prev = !g.wall_lo, next = !g.wall_hi;
     return comm_sendrecv(ctx, prev ? a + (size_t)IMPEC_GH * ld : nullptr, prev ? a + (size_t)(IMPEC_GH - n) * ld : nullptr,
@@ -245,6 +345,7 @@ static int exchange_rows(impec_ctx *ctx, double *a, const Grid &g, int n) {
 static int exchange_rows2(impec_ctx *ctx, double *a, double *b, const Grid &g, int n) {
     if (ctx->nranks == 1 || (g.wall_lo && g.wall_hi)) return IMPEC_OK;
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->p2p && !ctx->has_cb && b && (size_t)2 * n * g.ld * sizeof(double) <= ctx->p2p_slot_bytes) return p2p_exchange(ctx, a, b, g, n);
     if (!ctx->has_cb && b) {
         TRY(comm_check(ctx));
         const size_t ld = (size_t)g.ld; const size_t cnt = (size_t)n * ld;
@@ -337,6 +438,7 @@ extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
     for (void *p : ctx->allocs) cudaFree(p);
     for (void *p : {(void *)ctx->well_i, (void *)ctx->well_j, (void *)ctx->well_q, (void *)ctx->well_md}) if (p) cudaFree(p);
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->p2p) for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]);
     if (ctx->nccl) ncclCommDestroy(ctx->nccl);
 #endif
 #ifndef IMPEC_EMU
@@ -369,16 +471,20 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
 #ifndef IMPEC_EMU
 #define SMEM_ATTR(kern) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)))
-    SMEM_ATTR((k_mg_fused<FUSED_PLAIN, true>)); SMEM_ATTR((k_mg_fused<FUSED_PLAIN, false>));
-    SMEM_ATTR((k_mg_fused<FUSED_PRE, true>)); SMEM_ATTR((k_mg_fused<FUSED_PRE, false>));
-    SMEM_ATTR((k_mg_fused<FUSED_POST, true>)); SMEM_ATTR((k_mg_fused<FUSED_POST, false>));
+#define SMEM_ATTR3(MODE, F32) SMEM_ATTR((k_mg_fused<MODE, F32, 64>)); SMEM_ATTR((k_mg_fused<MODE, F32, 32>)); SMEM_ATTR((k_mg_fused<MODE, F32, 16>))
+    SMEM_ATTR3(FUSED_PLAIN, true); SMEM_ATTR3(FUSED_PLAIN, false);
+    SMEM_ATTR3(FUSED_PRE, true); SMEM_ATTR3(FUSED_PRE, false);
+    SMEM_ATTR3(FUSED_POST, true); SMEM_ATTR3(FUSED_POST, false);
     SMEM_ATTR(k_mg_coarse_solve<true>); SMEM_ATTR(k_mg_coarse_solve<false>);
+#undef SMEM_ATTR3
 #undef SMEM_ATTR
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 #endif
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
     if (nranks > 1 && nccl_unique_id) {
@@ -421,6 +527,12 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
             const size_t ns = grid_elems(L.gl);
             TRY(dev_alloc(ctx, &L.AWl, ns)); TRY(dev_alloc(ctx, &L.ASl, ns)); TRY(dev_alloc(ctx, &L.AVl, ns)); TRY(dev_alloc(ctx, &L.fl, ns));
         } else L.gl = L.g;
+        {   // tile height: big levels amortise the halo best with 64-row tiles; small levels are a few tiles only, and
+            // the duration of a launch is the time one CTA needs for its tile, so they get more, shorter tiles
+            const char *e32 = getenv("IMPEC_TH32_BELOW"), *e16 = getenv("IMPEC_TH16_BELOW");
+            const double c32 = e32 ? atof(e32) : 6.0e6, c16 = e16 ? atof(e16) : 6.0e6, cells = (double)L.g.N1 * L.g.N2;
+            L.th = cells < c16 ? 16 : (cells < c32 ? 32 : 64);
+        }
         const size_t nn = grid_elems(L.g);
         TRY(dev_alloc(ctx, &L.AW, nn)); TRY(dev_alloc(ctx, &L.AS, nn)); TRY(dev_alloc(ctx, &L.AV, nn)); TRY(dev_alloc(ctx, &L.DINV, nn));
         { double *f32 = nullptr; TRY(dev_alloc(ctx, &f32, 2 * nn + 8)); L.AWf = (float *)f32; L.ASf = L.AWf + nn; L.AVf = L.ASf + nn; L.DINVf = L.AVf + nn; }
@@ -442,7 +554,20 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_scal, sizeof(double) * S_NSCAL));
     memset(ctx->h_scal, 0, sizeof(double) * S_NSCAL);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    TRY(p2p_setup(ctx));
+#endif
     return IMPEC_OK;
+}
+
+extern "C" const char *impec_comm_backend(const impec_ctx *ctx) {
+    if (!ctx || ctx->nranks == 1) return "single";
+    if (ctx->has_cb) return "callbacks";
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->p2p) return "nvlink-p2p+nccl";
+    if (ctx->comm_ready) return "nccl";
+#endif
+    return "none";
 }
 
 extern "C" int impec_synchronize(impec_ctx *ctx) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return IMPEC_OK; }
@@ -461,6 +586,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
     if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_small") { ctx->use_small = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
@@ -667,13 +793,26 @@ static int smooth(Cycle &C, int l, const double *f, double *x, bool forward, boo
 // ---- fused path (kernels_fused.inl)
 static const dim3 kFusedBlock(FT_W / 2, FT_NTY);
 static const int kFusedSmem = FT_W * FT_H * (int)sizeof(double);
+// k_mg_fused with the tile height chosen for the level (Level::th)
+#define LAUNCH_FUSED(ctx, MODE, th, grid, ...) do { \
+        const int smem_ = FT_W * (th) * (int)sizeof(double); \
+        if ((ctx)->links_f32) { \
+            if ((th) == 64) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<MODE, true, 64>), grid, kFusedBlock, smem_, __VA_ARGS__); \
+            else if ((th) == 32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<MODE, true, 32>), grid, kFusedBlock, smem_, __VA_ARGS__); \
+            else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<MODE, true, 16>), grid, kFusedBlock, smem_, __VA_ARGS__); \
+        } else { \
+            if ((th) == 64) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<MODE, false, 64>), grid, kFusedBlock, smem_, __VA_ARGS__); \
+            else if ((th) == 32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<MODE, false, 32>), grid, kFusedBlock, smem_, __VA_ARGS__); \
+            else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<MODE, false, 16>), grid, kFusedBlock, smem_, __VA_ARGS__); \
+        } } while (0)
 static const dim3 kStagedBlock(FT_W / 2, ST_NTY);
 template <int MODE> static dim3 staged_grid(const Grid &g) {
     return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + StagedGeom<MODE>::TI - 1) / StagedGeom<MODE>::TI));
 }
 static bool use_staged(const impec_ctx *ctx) { return ctx->staged && ctx->links_f32; }
-template <int MODE> static dim3 fused_grid(const Grid &g) {
-    return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + FusedGeom<MODE>::TI - 1) / FusedGeom<MODE>::TI));
+template <int MODE> static dim3 fused_grid(const Grid &g, int th = FT_H) {
+    const int ti = th - 2 * (int)FusedGeom<MODE>::HI;
+    return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + ti - 1) / ti));
 }
 // PLAIN and POST read the iterate with a halo that belongs to neighbouring tiles, so they cannot run in place:
 // they read L.x, write L.t and the two pointers are swapped (the level's current iterate is always L.x).
@@ -681,10 +820,8 @@ static int fused_plain(Cycle &C, int l, const double *f, bool forward) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PLAIN>, staged_grid<FUSED_PLAIN>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
                      (const double *)nullptr, (double *)nullptr, (double *)nullptr);
-    else if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PLAIN, true>), fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
-                     (const double *)nullptr, (double *)nullptr, (double *)nullptr);
-    else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PLAIN, false>), fused_grid<FUSED_PLAIN>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
-                     (const double *)nullptr, (double *)nullptr, (double *)nullptr);
+    else LAUNCH_FUSED(ctx, FUSED_PLAIN, L.th, fused_grid<FUSED_PLAIN>(L.g, L.th), C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
+                      (const double *)nullptr, (double *)nullptr, (double *)nullptr);
     std::swap(L.x, L.t);
     return IMPEC_OK;
 }
@@ -699,10 +836,8 @@ static int fused_pre(Cycle &C, int l, const double *f) {
     const bool tr = at_transition(ctx, l);
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PRE>, staged_grid<FUSED_PRE>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
                      (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
-    else if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PRE, true>), fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
-                     (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
-    else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_PRE, false>), fused_grid<FUSED_PRE>(L.g), kFusedBlock, kFusedSmem, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
-                     (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
+    else LAUNCH_FUSED(ctx, FUSED_PRE, L.th, fused_grid<FUSED_PRE>(L.g, L.th), C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
+                      (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
     return IMPEC_OK;
 }
 // restricted right-hand side of the first replicated level: all-gather the slabs
@@ -714,13 +849,11 @@ static int gather_coarse_rhs(impec_ctx *ctx, int l) {
 }
 static int fused_post(Cycle &C, int l, const double *f, double *part, long long *nparts) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
-    const dim3 gr = use_staged(ctx) ? staged_grid<FUSED_POST>(L.g) : fused_grid<FUSED_POST>(L.g);
+    const dim3 gr = use_staged(ctx) ? staged_grid<FUSED_POST>(L.g) : fused_grid<FUSED_POST>(L.g, L.th);
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_POST>, gr, kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
                      coarse_x_view(ctx, l), (double *)nullptr, part);
-    else if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_POST, true>), gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
-                     coarse_x_view(ctx, l), (double *)nullptr, part);
-    else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<FUSED_POST, false>), gr, kFusedBlock, kFusedSmem, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
-                     coarse_x_view(ctx, l), (double *)nullptr, part);
+    else LAUNCH_FUSED(ctx, FUSED_POST, L.th, gr, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
+                      coarse_x_view(ctx, l), (double *)nullptr, part);
     std::swap(L.x, L.t);
     if (nparts) *nparts = (long long)gr.x * gr.y;
     return IMPEC_OK;
@@ -769,6 +902,15 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
     const int nl = C.nl;
     const bool fused = ctx->fused;
     if (dot_nparts) *dot_nparts = 0;
+    if (fused && ctx->use_small && l > 0 && l < nl - 1 && l > C.w_to && !L.dist && nl - l <= SM_MAXLEV && (long long)L.g.N1 * L.g.N2 <= SM_MAXCELLS && C.D[l].mass == 0.) {
+        // bottom of the hierarchy: the whole V-cycle over levels l .. nl-1 in one single-CTA launch
+        SmallArgs A; A.nl = nl - l; A.ncoarse = C.ncoarse; A.xout = ctx->L[l].x;
+        for (int k = l; k < nl; k++) A.D[k - l] = C.D[k];
+        const size_t smem = small_smem_doubles(A) * sizeof(double);
+        if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, k_mg_small<true>, dim3(1), dim3(SM_T), smem, A, f);
+        else LAUNCH_COOP_SMEM(ctx, k_mg_small<false>, dim3(1), dim3(SM_T), smem, A, f);
+        return IMPEC_OK;
+    }
     if (l == nl - 1) {
         if (fused && !L.dist && L.g.N1 <= FT_H - 4 && L.g.N2 <= FT_TJ) {
             // the whole level fits one tile: all 2*ncoarse sweeps in a single launch (x0 = 0 inside the kernel)
@@ -1213,6 +1355,20 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
     const dim3 gr = grid2d(g.N2, g.N1);
     Level &L0 = ctx->L[0];
     auto body = [&]() -> int {
+        // "<kernel>@<level>": the tile kernels on a coarser level (replicated or single-GPU levels)
+        const size_t at = k.find('@');
+        if (at != std::string::npos) {
+            const int l = atoi(k.c_str() + at + 1);
+            const std::string kk = k.substr(0, at);
+            if (l < 0 || l + 1 >= (int)ctx->L.size()) return fail(ctx, IMPEC_ERR_ARG, "no such level: %s", k.c_str());
+            Level &L = ctx->L[l];
+            const double *fl = l == 0 ? ctx->r : L.f;
+            if (kk == "fused_pre") return fused_pre(C, l, fl);
+            if (kk == "fused_post") return fused_post(C, l, fl, nullptr, nullptr);
+            if (kk == "fused_plain") return fused_plain(C, l, fl, true);
+            if (kk == "cycle") return mg_cycle(C, l, fl);
+            return fail(ctx, IMPEC_ERR_ARG, "unknown kernel name '%s'", k.c_str());
+        }
         if (k == "fused_plain") return fused_plain(C, 0, ctx->r, true);
         if (k == "fused_pre") return fused_pre(C, 0, ctx->r);
         if (k == "fused_post") return fused_post(C, 0, ctx->r, ctx->part, nullptr);
@@ -1227,6 +1383,12 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "dot") { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part); return IMPEC_OK; }
         if (k == "update_d") { LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_TMP, ctx->z, ctx->d); return IMPEC_OK; }
         if (k == "vcycle") return mg_cycle(C, 0, ctx->r);
+        if (k == "tail") { const int tl = ctx->tail_level >= 0 ? ctx->tail_level : (int)ctx->L.size() - 1; return mg_cycle(C, tl, ctx->L[tl].f); }
+        // communication primitives as the solver issues them (multi-rank contexts; no-ops on one rank)
+        if (k == "halo_x2") return exchange_rows(ctx, L0.x, g, 2);
+        if (k == "halo_f3") return exchange_rows(ctx, ctx->r, g, IMPEC_HALO);
+        if (k == "allreduce1") return comm_allreduce(ctx, ctx->scal + S_TMP, 1, RED_MAX);
+        if (k == "gather_rhs") { for (int l = 0; l + 1 < (int)ctx->L.size(); l++) if (at_transition(ctx, l)) return gather_coarse_rhs(ctx, l); return IMPEC_OK; }
         if (k == "sweep_x") return sweep<0>(ctx, ctx->c, ctx->ta, nullptr, 0.0, 0, g.N1, -ng, g.N2 + ng);
         if (k == "sweep_y") return sweep<1>(ctx, ctx->c, ctx->ta, nullptr, 0.0, -ng, g.N1 + ng, 0, g.N2);
         if (k == "build_operator") return impec_build_operator(ctx);

@@ -23,7 +23,9 @@
 #define FT_ROWS (FT_H / FT_NTY)  // rows per thread
 #define FT_TJ (FT_W - 2 * FT_HJ) // interior columns per tile (120)
 enum { FUSED_PLAIN = 0, FUSED_PRE = 1, FUSED_POST = 2 };
-template <int MODE> struct FusedGeom { enum { HI = (MODE == FUSED_PRE) ? 3 : 2, TI = FT_H - 2 * HI }; };
+// TH = tile height: 64 on the big levels (least halo overhead); 32 / 16 on the small ones, where a level is only a few
+// tiles and the time of a launch is the time ONE CTA needs for its tile (more, shorter CTAs finish sooner)
+template <int MODE, int TH = FT_H> struct FusedGeom { enum { HI = (MODE == FUSED_PRE) ? 3 : 2, TI = TH - 2 * HI }; };
 
 struct d2 { double x, y; };
 IMPEC_D d2 ld2(const double *p) {
@@ -84,10 +86,10 @@ IMPEC_D double tile_diagsum(const CF &A, int ld, const double *__restrict__ X, i
 
 // nsweeps > 1 (PLAIN only, and only when this single tile holds the WHOLE level so that no halo can go stale): the
 // sweeps alternate forward/backward starting with colour c0 -- the coarsest-level solve in one launch.
-template <int MODE, bool EDGE, bool F32>
+template <int MODE, bool EDGE, bool F32, int TH>
 IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, const int c0,
                         const Grid &gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part, double *__restrict__ X, const int nsweeps = 1) {
-    constexpr int HI = FusedGeom<MODE>::HI, TI = FusedGeom<MODE>::TI;
+    constexpr int HI = FusedGeom<MODE, TH>::HI, TI = FusedGeom<MODE, TH>::TI;
     const Grid g = L.g;
     const int ld = g.ld;
     const Coef<F32> A(L);
@@ -102,7 +104,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
 
     // ---- stage L: tile of x (zero for a zero initial guess), plus the prolongated correction
 #pragma unroll
-    for (int n = 0; n < FT_ROWS; n++) {
+    for (int n = 0; n < (TH / FT_NTY); n++) {
         const int r = ty + n * FT_NTY, ig = i0 + r;
         double a = 0., b = 0.;
         const bool row_alloc = !EDGE || ((ig >= -IMPEC_GH) && (ig < g.rows - IMPEC_GH));
@@ -140,7 +142,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     // ---- two colour stages.  Stage s updates colour (s == 0 ? c0 : 1 - c0) on the tile shrunk by s+1 cells
     //      (by s cells in PRE mode, whose first stage is the neighbour-free zero-guess update x = f/diag).
     //      The pinned cell has dinv = 0 and x = 0, so it needs no special case here.
-    double nv[FT_ROWS];
+    double nv[(TH / FT_NTY)];
     for (int sw = 0; sw < nsweeps; sw++)
 #pragma unroll
     for (int s = 0; s < 2; s++) {
@@ -151,10 +153,10 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
         const int jj = jl + off, j = jg + off;
         const bool colok = jj >= shrink && jj < FT_W - shrink && (!EDGE || (j >= 0 && j < g.N2));
 #pragma unroll
-        for (int n = 0; n < FT_ROWS; n++) {
+        for (int n = 0; n < (TH / FT_NTY); n++) {
             const int r = ty + n * FT_NTY, ig = i0 + r;
             double val = X[r * FT_W + (off << 6) + tx];
-            const bool act = colok && r >= shrink && r < FT_H - shrink && (!EDGE || (ig >= g.rlo && ig < g.rhi));
+            const bool act = colok && r >= shrink && r < TH - shrink && (!EDGE || (ig >= g.rlo && ig < g.rhi));
             if (act) {
                 const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld + off);
                 if (MODE == FUSED_PRE && s == 0) val = f[k] * (double)A.DINV[k];
@@ -164,7 +166,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
         }
         if (!(MODE == FUSED_PRE && s == 0)) IMPEC_SYNCTHREADS();        // every read of the old colour is done
 #pragma unroll
-        for (int n = 0; n < FT_ROWS; n++) X[(ty + n * FT_NTY) * FT_W + (off << 6) + tx] = nv[n];
+        for (int n = 0; n < (TH / FT_NTY); n++) X[(ty + n * FT_NTY) * FT_W + (off << 6) + tx] = nv[n];
         IMPEC_SYNCTHREADS();
     }
 
@@ -172,9 +174,9 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     const bool col_int = jl >= FT_HJ && jl < FT_W - FT_HJ && (!EDGE || jg < g.N2);
     double dotv = 0.;
 #pragma unroll
-    for (int n = 0; n < FT_ROWS; n++) {
+    for (int n = 0; n < (TH / FT_NTY); n++) {
         const int r = ty + n * FT_NTY, ig = i0 + r;
-        if (r < HI || r >= FT_H - HI || !col_int || (EDGE && ig >= g.N1)) continue;
+        if (r < HI || r >= TH - HI || !col_int || (EDGE && ig >= g.N1)) continue;
         const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
         const double a = X[r * FT_W + tx], b = X[r * FT_W + 64 + tx];
         if (!EDGE || jg + 1 < g.N2) st2(x + k, a, b); else x[k] = a;
@@ -194,14 +196,14 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     // its neighbours were still zero, so r = sum over all 8 neighbours of a_nb x_nb; a second-colour cell was
     // solved against the final first-colour values, so only its (same-colour) diagonal neighbours contribute.
     // (The dropped terms f - d x + s_at_update are rounding noise, O(eps |f|).)
-    double ra[FT_ROWS], rb[FT_ROWS];
+    double ra[(TH / FT_NTY)], rb[(TH / FT_NTY)];
     {
         const int off0 = (par == c0) ? 0 : 1;                            // first-colour cell of the pair
 #pragma unroll
-        for (int n = 0; n < FT_ROWS; n++) {
+        for (int n = 0; n < (TH / FT_NTY); n++) {
             const int r = ty + n * FT_NTY, ig = i0 + r;
             double v0 = 0., v1 = 0.;                                     // residual of the first / second colour cell
-            if (r >= 2 && r < FT_H - 2 && (!EDGE || (ig >= g.rlo && ig < g.rhi))) {
+            if (r >= 2 && r < TH - 2 && (!EDGE || (ig >= g.rlo && ig < g.rhi))) {
                 const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
                 const int ja = jl + off0, jb = jl + 1 - off0;
                 if (ja >= 2 && ja < FT_W - 2 && (!EDGE || (jg + off0 >= 0 && jg + off0 < g.N2 && (long long)(k + off0) != L.pin)))
@@ -215,7 +217,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     }
     IMPEC_SYNCTHREADS();
 #pragma unroll
-    for (int n = 0; n < FT_ROWS; n++) {
+    for (int n = 0; n < (TH / FT_NTY); n++) {
         const int r = ty + n * FT_NTY;
         X[r * FT_W + tx] = ra[n]; X[r * FT_W + 64 + tx] = rb[n];
     }
@@ -245,20 +247,20 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     }
 }
 
-template <int MODE, bool F32>
+template <int MODE, bool F32, int TH>
 __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_fused(LevelDev L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, int c0,
                                                                Grid gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part) {
     IMPEC_DYN_SMEM(double, X);
-    constexpr int HI = FusedGeom<MODE>::HI, TI = FusedGeom<MODE>::TI;
+    constexpr int HI = FusedGeom<MODE, TH>::HI, TI = FusedGeom<MODE, TH>::TI;
     const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ, i0 = (int)blockIdx.y * TI - HI;
     // tile (halo included, plus the one-cell reach of the link arrays) strictly inside the domain and free of the pin?
-    bool edge = i0 < L.g.rlo || j0 < 0 || i0 + FT_H >= L.g.rhi || j0 + FT_W >= L.g.N2;
+    bool edge = i0 < L.g.rlo || j0 < 0 || i0 + TH >= L.g.rhi || j0 + FT_W >= L.g.N2;
     if (L.pin >= 0) {
         const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
-        edge = edge || (pi >= i0 && pi < i0 + FT_H && pj >= j0 && pj < j0 + FT_W);
+        edge = edge || (pi >= i0 && pi < i0 + TH && pj >= j0 && pj < j0 + FT_W);
     }
-    if (edge) fused_body<MODE, true, F32>(L, f, xin, x, c0, gc, ec, fc, part, X);
-    else fused_body<MODE, false, F32>(L, f, xin, x, c0, gc, ec, fc, part, X);
+    if (edge) fused_body<MODE, true, F32, TH>(L, f, xin, x, c0, gc, ec, fc, part, X);
+    else fused_body<MODE, false, F32, TH>(L, f, xin, x, c0, gc, ec, fc, part, X);
 }
 
 // Coarsest-level solve: `nsweeps` alternating red-black sweeps from a zero guess in ONE launch.  Requires that a
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_fused(LevelDev L, cons
 template <bool F32>
 __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_coarse_solve(LevelDev L, const double *__restrict__ f, double *__restrict__ x, int nsweeps) {
     IMPEC_DYN_SMEM(double, X);
-    fused_body<FUSED_PLAIN, true, F32>(L, f, (const double *)nullptr, x, 0, L.g, (const double *)nullptr, (double *)nullptr, (double *)nullptr, X, nsweeps);
+    fused_body<FUSED_PLAIN, true, F32, FT_H>(L, f, (const double *)nullptr, x, 0, L.g, (const double *)nullptr, (double *)nullptr, (double *)nullptr, X, nsweeps);
 }
 
 // ---------------------------------------------------------------- fused PCG search-direction update + mat-vec

@@ -23,6 +23,7 @@
 #define IMPEC_SHFL_UP(v, d) __shfl_up_sync(0xffffffffu, (v), (d))
 #define IMPEC_SHFL_IDX(v, l) __shfl_sync(0xffffffffu, (v), (l))
 #define IMPEC_SYNCTHREADS() __syncthreads()
+#define IMPEC_SYNCWARP() __syncwarp()
 #define IMPEC_HD __host__ __device__ __forceinline__
 #define IMPEC_D __device__ __forceinline__
 // 16-byte asynchronous global->shared copy (LDGSTS, bypasses L1) and its completion wait
@@ -69,6 +70,7 @@ double shfl(double v, int src_lane_delta, int mode);   // mode 0 down, 1 up, 2 i
 #define IMPEC_SHFL_UP(v, d) emu::shfl((v), (d), 1)
 #define IMPEC_SHFL_IDX(v, l) emu::shfl((v), (l), 2)
 #define IMPEC_SYNCTHREADS() emu::syncthreads()
+#define IMPEC_SYNCWARP() emu::syncthreads()   /* block barrier: callers keep all 32 lanes of the warp on the same path */
 #define IMPEC_HD inline
 #define IMPEC_D inline
 inline void impec_cp_async16(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 16); }

@@ -103,6 +103,10 @@ int   impec_ctx_create(const impec_params *p, int device, int rank, int nranks, 
 void  impec_ctx_destroy(impec_ctx *ctx);
 const char *impec_last_error(const impec_ctx *ctx);
 int   impec_synchronize(impec_ctx *ctx);
+/* transport used between the ranks of this context: "single", "nccl", "nvlink-p2p+nccl" (halo rows and scalar
+ * reductions through mapped peer memory, NCCL for bootstrap and large collectives; needs peer access between the
+ * GPUs, IMPEC_P2P=0 disables it) or "callbacks" (test harness) */
+const char *impec_comm_backend(const impec_ctx *ctx);
 int   impec_ctx_set_comm_callbacks(impec_ctx *ctx, const impec_comm_callbacks *cb);
 /* slab owned by this context: rows [row0, row0 + nrows) of the global grid (everything when nranks == 1) */
 int   impec_local_rows(const impec_ctx *ctx, int *row0, int *nrows);
@@ -158,7 +162,7 @@ long long impec_kernel_launches(const impec_ctx *ctx);                   /* kern
 int   impec_reset_state(impec_ctx *ctx);                                 /* produced mass := 0, sweep parity := Y */
 /* options: "warm_start" (x0 = previous p instead of the reference's 0), "stagnation_guard" (stop PCG at the FP64
  * residual floor instead of iterating the recurrence residual down to eps), "mg_fused", "mg_links_fp32", "mg_staged",
- * "mg_graph", "mg_w_from", "mg_w_to", "mg_ncoarse", "max_iter".  Defaults reproduce the reference's semantics. */
+ * "mg_graph", "mg_small", "mg_w_from", "mg_w_to", "mg_ncoarse", "max_iter".  Defaults reproduce the reference's semantics. */
 int   impec_set_option(impec_ctx *ctx, const char *key, double value);
 /* average device time of one named piece of the path ("smooth_sweep", "residual", "vcycle", "sweep_x", ...) over
  * `reps` launches, measured with CUDA events on the context stream */

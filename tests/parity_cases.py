@@ -1,6 +1,7 @@
 """Parity checks of the C-ABI library against the CPU oracle.  Each function takes `emulated`:
 tests/test_emu_parity.py runs them on the CPU emulator (no GPU needed), tests/test_gpu_parity.py runs the
 very same checks on the B200 through the real library (-m gpu)."""
+import os
 import ctypes as C
 import numpy as np
 import oracle as O
@@ -191,15 +192,48 @@ def check_fused_vs_unfused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
     Pi = I.default_params(emulated=emulated, **base)
     r = np.random.default_rng(1).standard_normal(N1 * N2)
     out = []
-    for fused in (0, 1):
-        ctx = I.Context(Pi, emulated=emulated)
-        ctx.set_option("mg_fused", fused); ctx.set_option("mg_links_fp32", 0)
-        ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
-        z1 = ctx.vcycle(r); z2 = ctx.vcycle(r)
-        assert np.array_equal(z1, z2), "cycle is not repeatable (race?)"
-        out.append(z1)
-        ctx.close()
+    # tile heights of the fused kernels: all levels 64 rows / all 32 / all 16 / the default per-level choice
+    policies = ((0, None, None), (1, "0", "0"), (1, "1e30", "0"), (1, "1e30", "1e30"), (1, None, None))
+    try:
+        for fused, th32, th16 in policies:
+            for key, val in (("IMPEC_TH32_BELOW", th32), ("IMPEC_TH16_BELOW", th16)):
+                if val is None: os.environ.pop(key, None)
+                else: os.environ[key] = val
+            ctx = I.Context(Pi, emulated=emulated)
+            ctx.set_option("mg_fused", fused); ctx.set_option("mg_links_fp32", 0); ctx.set_option("mg_small", 0)
+            ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
+            z1 = ctx.vcycle(r); z2 = ctx.vcycle(r)
+            assert np.array_equal(z1, z2), "cycle is not repeatable (race?)"
+            out.append(z1)
+            ctx.close()
+    finally:
+        os.environ.pop("IMPEC_TH32_BELOW", None); os.environ.pop("IMPEC_TH16_BELOW", None)
     assert np.abs(out[0] - out[1]).max() <= 1e-12 * np.abs(out[0]).max()
+    # identical arithmetic per cell: the result does not depend on how the level is cut into tiles
+    for z in out[2:]:
+        assert np.array_equal(z, out[1]), "tile height changes the result"
+
+
+def check_small_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
+    """The single-CTA bottom-of-hierarchy kernel (kernels_small.inl, levels of <= 4096 cells) against the tile kernels
+    on the same levels: same arithmetic per cell, so one cycle agrees to rounding (<= 1e-13 relative), with FP64 and
+    with FP32 coefficient copies."""
+    base, Po, c, q = production_case(N1, N2, stype=stype)
+    Pi = I.default_params(emulated=emulated, **base)
+    r = np.random.default_rng(2).standard_normal(N1 * N2)
+    for f32 in (0, 1):
+        out = []
+        for small in (0, 1):
+            ctx = I.Context(Pi, emulated=emulated)
+            ctx.set_option("mg_small", small); ctx.set_option("mg_links_fp32", f32)
+            ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
+            n0 = ctx.kernel_launches()
+            z1 = ctx.vcycle(r); n1 = ctx.kernel_launches(); z2 = ctx.vcycle(r)
+            assert np.array_equal(z1, z2), "cycle is not repeatable (race?)"
+            out.append((z1, n1 - n0))
+            ctx.close()
+        assert out[1][1] < out[0][1], "the small-level kernel was not used"
+        assert np.abs(out[0][0] - out[1][0]).max() <= 1e-13 * np.abs(out[0][0]).max()
 
 
 def check_dispersion(emulated, N1=32, N2=32, stype=O.PARALLEL, steps=1):

@@ -31,6 +31,7 @@ def test_advection_other_splittings_bitexact(split): pc.check_advection_bitexact
 def test_source_step(): pc.check_source_step(False, N=128)
 def test_fused_vs_unfused_cycle(): pc.check_fused_vs_unfused(False, 1024, 1536)
 def test_staged_vs_fused_cycle(): pc.check_staged_vs_fused(False, 1024, 1536)
+def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(False, 1024, 1536)
 
 
 @pytest.mark.parametrize("N1,N2,stype", [(64, 64, O.PARALLEL), (128, 64, O.DIAGONAL), (100, 50, O.DIAGONAL), (141, 141, O.PARALLEL)])
