@@ -69,20 +69,22 @@ __global__ void __launch_bounds__(P2P_THREADS) k_halo_p2p(HaloArgs a) {
             for (long long k = c0 + threadIdx.x; k < c1; k += blockDim.x) dst[k] = src[k];
         }
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                       // the CTA's stores happen-before thread 0's release below (cumulativity)
     // 2. publish, 3. wait
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        if (a.rem_lo) p2p_st_flag(a.rem_lo_flag + blockIdx.x, a.epoch);
-        if (a.rem_hi) p2p_st_flag(a.rem_hi_flag + blockIdx.x, a.epoch);
-        bool good = true;
-        if (a.rem_lo) good = p2p_wait(a.my_lo_flag + blockIdx.x, a.epoch, a.err) && good;
-        if (a.rem_hi) good = p2p_wait(a.my_hi_flag + blockIdx.x, a.epoch, a.err) && good;
-        ok = good ? 1 : 0;
-        __threadfence_system();
-    }
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
     __syncthreads();
+    // warp 0 talks to the previous rank, warp 1 to the next one (the two waits overlap)
+    if (threadIdx.x == 0 && a.rem_lo) {
+        p2p_st_flag(a.rem_lo_flag + blockIdx.x, a.epoch);
+        if (!p2p_wait(a.my_lo_flag + blockIdx.x, a.epoch, a.err)) bad = 1;
+    }
+    if (threadIdx.x == 32 && a.rem_hi) {
+        p2p_st_flag(a.rem_hi_flag + blockIdx.x, a.epoch);
+        if (!p2p_wait(a.my_hi_flag + blockIdx.x, a.epoch, a.err)) bad = 1;
+    }
+    __syncthreads();                       // the acquire loads above order the unpack below after the neighbours' stores
+    const int ok = !bad;
     if (!ok) return;
     // 4. unpack (L2 loads: the rows were written by another GPU)
     for (int f = 0; f < a.nfld; f++) {

@@ -79,7 +79,8 @@ struct impec_ctx {
     bool comm_ready = false;
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
     // peer-memory transport (comm_p2p.inl): my mailbox, the mapped mailboxes of the other ranks, exchange epochs
-    bool p2p = false;
+    bool p2p = false;                               // mailboxes mapped: scalar all-reduces go through peer memory
+    bool p2p_halo = false;                          // ... and so do the halo rows (IMPEC_P2P_HALO=0/1)
     unsigned char *mail = nullptr, *peer_mail[P2P_MAXR] = {};
     size_t p2p_slot_bytes = 0;
     unsigned long long halo_epoch = 0, ar_epoch = 0;
@@ -292,6 +293,7 @@ static int p2p_setup(impec_ctx *ctx) {
     CUDA_TRY(ctx, cudaMemcpyAsync(&flag, ctx->scal + S_TMP, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->p2p = flag > 0.5;
+    { const char *eh = getenv("IMPEC_P2P_HALO"); ctx->p2p_halo = ctx->p2p && (eh ? atoi(eh) != 0 : true); }
     if (!ctx->p2p)
         for (int r = 0; r < R; r++) { if (r != ctx->rank && ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]); ctx->peer_mail[r] = nullptr; }
     return IMPEC_OK;
@@ -334,7 +336,7 @@ static int p2p_allreduce(impec_ctx *ctx, double *buf, int n, int op) {
 static int exchange_rows(impec_ctx *ctx, double *a, const Grid &g, int n) {
     if (ctx->nranks == 1 || (g.wall_lo && g.wall_hi)) return IMPEC_OK;
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
-    if (ctx->p2p && !ctx->has_cb && (size_t)n * g.ld * sizeof(double) <= ctx->p2p_slot_bytes) return p2p_exchange(ctx, a, nullptr, g, n);
+    if (ctx->p2p_halo && !ctx->has_cb && (size_t)n * g.ld * sizeof(double) <= ctx->p2p_slot_bytes) return p2p_exchange(ctx, a, nullptr, g, n);
 #endif
     const size_t ld = (size_t)g.ld;
     const bool prev = !g.wall_lo, next = !g.wall_hi;
@@ -345,7 +347,7 @@ static int exchange_rows(impec_ctx *ctx, double *a, const Grid &g, int n) {
 static int exchange_rows2(impec_ctx *ctx, double *a, double *b, const Grid &g, int n) {
     if (ctx->nranks == 1 || (g.wall_lo && g.wall_hi)) return IMPEC_OK;
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
-    if (ctx->p2p && !ctx->has_cb && b && (size_t)2 * n * g.ld * sizeof(double) <= ctx->p2p_slot_bytes) return p2p_exchange(ctx, a, b, g, n);
+    if (ctx->p2p_halo && !ctx->has_cb && b && (size_t)2 * n * g.ld * sizeof(double) <= ctx->p2p_slot_bytes) return p2p_exchange(ctx, a, b, g, n);
     if (!ctx->has_cb && b) {
         TRY(comm_check(ctx));
         const size_t ld = (size_t)g.ld; const size_t cnt = (size_t)n * ld;
@@ -564,7 +566,7 @@ extern "C" const char *impec_comm_backend(const impec_ctx *ctx) {
     if (!ctx || ctx->nranks == 1) return "single";
     if (ctx->has_cb) return "callbacks";
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
-    if (ctx->p2p) return "nvlink-p2p+nccl";
+    if (ctx->p2p) return ctx->p2p_halo ? "nvlink-p2p+nccl" : "nccl+p2p-allreduce";
     if (ctx->comm_ready) return "nccl";
 #endif
     return "none";
@@ -936,8 +938,8 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
         // reads (f: 3, x: 2); with the halos in place each rank computes the same values a single GPU would.
         const bool dist = L.dist, tr = at_transition(ctx, l);
         if (dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
-        TRY(fused_pre(C, l, f));                                      // pre-smooth(0) + residual + restrict
-        if (dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
+        TRY(fused_pre(C, l, f));                                      // pre-smooth(0) + residual + restrict; writes x on 2 halo rows too
+        if (dist && use_staged(ctx)) TRY(exchange_rows(ctx, L.x, L.g, 2));   // (the staged variant writes its interior only)
         TRY(gather_coarse_rhs(ctx, l));
         TRY(mg_cycle(C, l + 1, Lc.f));
         if (Lc.dist) TRY(exchange_rows(ctx, Lc.x, Lc.g, 2));

@@ -173,10 +173,16 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     // ---- write the interior of the tile back (128-bit stores), and the fused dot product
     const bool col_int = jl >= FT_HJ && jl < FT_W - FT_HJ && (!EDGE || jg < g.N2);
     double dotv = 0.;
+    // PRE on a slab: f is valid on 3 halo rows of the neighbouring slabs, so the sweep from zero is exact on 2 halo
+    // rows as well.  The first / last row of tiles writes them too, which saves the exchange of x that the
+    // post-smoothing kernel would otherwise need.
+    const int rmin_w = (MODE == FUSED_PRE && blockIdx.y == 0 && !g.wall_lo) ? HI - 2 : HI;
 #pragma unroll
     for (int n = 0; n < (TH / FT_NTY); n++) {
         const int r = ty + n * FT_NTY, ig = i0 + r;
-        if (r < HI || r >= TH - HI || !col_int || (EDGE && ig >= g.N1)) continue;
+        const bool top_halo = MODE == FUSED_PRE && EDGE && !g.wall_hi && ig >= g.N1 && ig < g.N1 + 2 && r < TH - 1;
+        if (r < rmin_w || !col_int) continue;
+        if (!top_halo && (r >= TH - HI || (EDGE && ig >= g.N1))) continue;
         const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
         const double a = X[r * FT_W + tx], b = X[r * FT_W + 64 + tx];
         if (!EDGE || jg + 1 < g.N2) st2(x + k, a, b); else x[k] = a;
@@ -248,7 +254,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
 }
 
 template <int MODE, bool F32, int TH>
-__global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_fused(LevelDev L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, int c0,
+__global__ void __launch_bounds__(FT_W / 2 * FT_NTY, (TH == 64 ? 2 : (TH == 32 ? 3 : 4))) k_mg_fused(LevelDev L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, int c0,
                                                                Grid gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part) {
     IMPEC_DYN_SMEM(double, X);
     constexpr int HI = FusedGeom<MODE, TH>::HI, TI = FusedGeom<MODE, TH>::TI;
@@ -327,7 +333,7 @@ IMPEC_D void pcg_matvec_body_rw(const LevelDev &L, const double *__restrict__ sc
 // NOTE: d is read (with halo) and written (interior) by the same launch, so the read and write buffers must differ:
 // the host ping-pongs between two search-direction buffers (din -> dout).
 template <bool FIRST>
-__global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_pcg_matvec(LevelDev L, const double *__restrict__ scal, const double *__restrict__ z, const double *__restrict__ din,
+__global__ void __launch_bounds__(FT_W / 2 * FT_NTY, 2) k_pcg_matvec(LevelDev L, const double *__restrict__ scal, const double *__restrict__ z, const double *__restrict__ din,
                                                                  double *__restrict__ dout, double *__restrict__ s, double *__restrict__ part) {
     IMPEC_DYN_SMEM(double, X);
     constexpr int HI = 2, TI = FT_H - 2 * HI;
