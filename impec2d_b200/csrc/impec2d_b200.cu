@@ -65,6 +65,7 @@ struct impec_ctx {
                                                     // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
     bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
+    bool sweep_shared = true;                       // MUSCL sweeps evaluate each reconstruction once (k_muscl_x / k_muscl_y); 0 = k_sweep
     bool use_small = true;                          // levels of <= SM_MAXCELLS cells: whole V-cycle in one single-CTA launch (kernels_small.inl)
     long long launches = 0;
     std::string err;
@@ -588,6 +589,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
     if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "sweep_shared") { ctx->sweep_shared = value != 0.0; return IMPEC_OK; }
     if (k == "mg_small") { ctx->use_small = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
@@ -1210,6 +1212,22 @@ static int sweep(impec_ctx *ctx, const double *cin, double *cout, const double *
     const double h = DIR == 0 ? ctx->D.dx : ctx->D.dy;
     const double phi = ctx->P.porosity;
     const bool phi1 = (phi == 1.0), up = ctx->P.hyper_method == IMPEC_UPWIND, avg = other != nullptr;
+    if (!up && ctx->sweep_shared) {
+        // MUSCL with every reconstruction evaluated once (k_muscl_x marches down the rows, k_muscl_y shares through smem)
+        if (DIR == 0) {
+            const int jstart = j0 - ((j0 + IMPEC_PJ) & 3);            // 32-byte aligned first column
+            const dim3 gx((unsigned)((j1 - jstart + SX_BLOCK - 1) / SX_BLOCK), (unsigned)((i1 - i0 + SX_ROWS - 1) / SX_ROWS));
+#define SWX(PH, AV) do { auto kern = k_muscl_x<PH, AV>; LAUNCH(ctx, kern, gx, dim3(SX_BLOCK), g, cin, vel, cout, other, dt, h, phi, i0, i1, j0, j1, jstart); } while (0)
+            if (phi1) { if (avg) { SWX(true, true); } else { SWX(true, false); } } else { if (avg) { SWX(false, true); } else { SWX(false, false); } }
+#undef SWX
+        } else {
+            const dim3 gy((unsigned)((j1 - j0 + SY_BLOCK - 1) / SY_BLOCK), (unsigned)((i1 - i0 + SY_ROWS - 1) / SY_ROWS));
+#define SWY(PH, AV) do { auto kern = k_muscl_y<PH, AV>; LAUNCH_COOP(ctx, kern, gy, dim3(SY_BLOCK), g, cin, vel, cout, other, dt, h, phi, i0, i1, j0, j1); } while (0)
+            if (phi1) { if (avg) { SWY(true, true); } else { SWY(true, false); } } else { if (avg) { SWY(false, true); } else { SWY(false, false); } }
+#undef SWY
+        }
+        return IMPEC_OK;
+    }
     const dim3 gr = grid2d(j1 - j0, i1 - i0);
 #define SW(M, PH, AV) do { auto kern = k_sweep<DIR, M, PH, AV>; LAUNCH(ctx, kern, gr, kBlock, g, cin, vel, cout, other, dt, h, phi, i0, i1, j0, j1); } while (0)
     if (!up) { if (phi1) { if (avg) { SW(0, true, true); } else { SW(0, true, false); } } else { if (avg) { SW(0, false, true); } else { SW(0, false, false); } } }

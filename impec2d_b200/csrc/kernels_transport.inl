@@ -160,6 +160,112 @@ __global__ void __launch_bounds__(256) k_sweep(Grid g, const double *__restrict_
     cout[k] = r;
 }
 
+// ---------------------------------------------------------------- MUSCL sweeps, one reconstruction per cell
+// k_sweep evaluates the reconstruction of cells i-1, i, i+1 in every thread: 9 IEEE divisions per cell, which made the
+// sweep FP64-pipe bound (ncu: 61 % fp64 pipe, 22 % of the HBM roofline).  The two kernels below evaluate every cell's
+// reconstruction ONCE with the very same device functions (so results stay bit-identical to the oracle) and share it:
+//
+//  k_muscl_x: the stencil runs across rows.  A thread owns one column j and MARCHES down SX_ROWS rows keeping
+//             c(i-1), c(i), c(i+1), the previous cell's evolved right state and the previous face flux in registers;
+//             loads of the next four rows are issued before the arithmetic of the current four (coalesced along j).
+//  k_muscl_y: the stencil runs inside a row.  A CTA owns a 256 x SY_ROWS tile, every thread reconstructs its own cells
+//             and publishes the evolved states in shared memory; the 2*SY_ROWS halo cells of the tile are done by
+//             the first lanes of warp 0.
+#define SX_ROWS 64
+#define SX_BLOCK 128
+template <bool PHI1, bool AVG>
+__global__ void __launch_bounds__(SX_BLOCK) k_muscl_x(Grid g, const double *__restrict__ cin, const double *__restrict__ vel,
+                                                      double *__restrict__ cout, const double *__restrict__ other,
+                                                      double dt, double hstep, double phi, int i0, int i1, int j0, int j1, int jstart) {
+    const int j = jstart + (int)(blockIdx.x * SX_BLOCK + threadIdx.x);
+    if (j < j0 || j >= j1) return;
+    const int ia = i0 + (int)blockIdx.y * SX_ROWS;
+    const int ib = (ia + SX_ROWS < i1) ? ia + SX_ROWS : i1;          // cells [ia, ib) are written by this thread
+    const size_t ld = (size_t)g.ld;
+    const double h = 0.5 * dt / hstep;
+    const size_t kb = gidx(g, ia - 1, j);                            // cell ia-1: reconstructed only
+    double cm = cin[kb - ld], c0 = cin[kb], cp = cin[kb + ld];
+    double v0 = vel[kb], v1 = vel[kb + ld];
+    double L, Rprev, Fprev = 0.;
+    muscl_evolve<PHI1>(v0, v1, cm, c0, cp, h, phi, L, Rprev);
+    for (int ib0 = ia; ib0 <= ib; ib0 += 4) {
+        double cn[4], vn[4], on[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {                                // rows past ib are clamped: loaded, never used
+            const int i = (ib0 + u < ib) ? ib0 + u : ib;
+            const size_t k = kb + (size_t)(i - ia + 1) * ld;         // cell i
+            cn[u] = cin[k + ld]; vn[u] = vel[k + ld];
+            on[u] = AVG ? other[k - ld] : 0.;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = ib0 + u;
+            if (i > ib) break;
+            cm = c0; c0 = cp; cp = cn[u]; v0 = v1; v1 = vn[u];       // now centred on cell i
+            double R;
+            muscl_evolve<PHI1>(v0, v1, cm, c0, cp, h, phi, L, R);
+            const double F = upwind_flux<PHI1>(v0, Rprev, L, phi);   // face i-1/2
+            if (i > ia) {                                            // cell i-1 has both its fluxes
+                double r = cm + dt / hstep * (Fprev - F);
+                if (AVG) r = 0.5 * (on[u] + r);
+                cout[kb + (size_t)(i - ia) * ld] = r;
+            }
+            Fprev = F; Rprev = R;
+        }
+    }
+}
+
+#define SY_ROWS 4
+#define SY_BLOCK 256
+template <bool PHI1, bool AVG>
+__global__ void __launch_bounds__(SY_BLOCK) k_muscl_y(Grid g, const double *__restrict__ cin, const double *__restrict__ vel,
+                                                      double *__restrict__ cout, const double *__restrict__ other,
+                                                      double dt, double hstep, double phi, int i0, int i1, int j0, int j1) {
+    __shared__ double Ls[SY_ROWS][SY_BLOCK + 2], Rs[SY_ROWS][SY_BLOCK + 2];
+    const int tx = threadIdx.x;
+    const int jb = j0 + (int)blockIdx.x * SY_BLOCK;                  // first cell of the tile
+    const int jn = (j1 - jb < SY_BLOCK) ? j1 - jb : SY_BLOCK;        // cells per row in this tile
+    const int ib = i0 + (int)blockIdx.y * SY_ROWS;
+    const int rn = (i1 - ib < SY_ROWS) ? i1 - ib : SY_ROWS;
+    const double h = 0.5 * dt / hstep;
+    double cc[SY_ROWS], va[SY_ROWS], vb[SY_ROWS];
+    if (tx < jn) {
+#pragma unroll
+        for (int n = 0; n < SY_ROWS; n++) {
+            if (n >= rn) break;
+            const size_t k = gidx(g, ib + n, jb + tx);
+            const double cm = cin[k - 1], c0 = cin[k], cp = cin[k + 1];
+            const double v0 = vel[k], v1 = vel[k + 1];
+            double L, R;
+            muscl_evolve<PHI1>(v0, v1, cm, c0, cp, h, phi, L, R);
+            Ls[n][tx + 1] = L; Rs[n][tx + 1] = R;
+            cc[n] = c0; va[n] = v0; vb[n] = v1;
+        }
+    }
+    if (tx < 2 * SY_ROWS) {                                          // halo cells jb-1 and jb+jn of every row
+        const int n = tx >> 1, side = tx & 1;
+        if (n < rn) {
+            const size_t k = gidx(g, ib + n, side ? jb + jn : jb - 1);
+            double L, R;
+            muscl_evolve<PHI1>(vel[k], vel[k + 1], cin[k - 1], cin[k], cin[k + 1], h, phi, L, R);
+            Ls[n][side ? jn + 1 : 0] = L; Rs[n][side ? jn + 1 : 0] = R;
+        }
+    }
+    IMPEC_SYNCTHREADS();
+    if (tx < jn) {
+#pragma unroll
+        for (int n = 0; n < SY_ROWS; n++) {
+            if (n >= rn) break;
+            const size_t k = gidx(g, ib + n, jb + tx);
+            const double Flo = upwind_flux<PHI1>(va[n], Rs[n][tx], Ls[n][tx + 1], phi);
+            const double Fhi = upwind_flux<PHI1>(vb[n], Rs[n][tx + 1], Ls[n][tx + 2], phi);
+            double r = cc[n] + dt / hstep * (Flo - Fhi);
+            if (AVG) r = 0.5 * (other[k] + r);
+            cout[k] = r;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- time-step reductions (a13)
 // MODE 0: max over cells of max(|u_c|,|v_c|)            (src/HyperbolicSolver.cpp:123-156)
 // MODE 1: min over cells of min(dx/|u_c|, dy/|v_c|)     (test mode, :100-121)

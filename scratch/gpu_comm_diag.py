@@ -25,7 +25,7 @@ t = 0.0
 for _ in range(2): dt, info = ctx.impes_step(t, 0.0); t += dt
 out = {"world": world, "its": info.iterations, "backend": ctx.comm_backend()}
 if rank == 0: print("backend", ctx.comm_backend(), flush=True)
-for name, reps in (("halo_x2", 200), ("halo_f3", 200), ("allreduce1", 200), ("gather_rhs", 100), ("tail", 50), ("vcycle", 10),
+for name, reps in (("halo_x2", 200), ("halo_f3", 200), ("allreduce1", 200), ("gather_rhs", 100), ("tail", 50), ("cycle@1", 20), ("cycle@2", 20), ("cycle@3", 20), ("cycle@4", 20), ("cycle@5", 20), ("fused_pre@1", 20), ("fused_post@1", 20), ("fused_pre@3", 20), ("fused_post@3", 20), ("vcycle", 10),
                    ("fused_pre", 10), ("fused_post", 10), ("pcg_matvec", 10), ("update_xr", 10)):
     if world > 1: dist.barrier()
     torch.cuda.synchronize()

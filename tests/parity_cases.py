@@ -81,6 +81,28 @@ def check_single_sweeps_bitexact(emulated, N=24):
     ctx.close()
 
 
+def check_sweep_variants(emulated, N=150):
+    """k_muscl_x / k_muscl_y (one reconstruction per cell) against k_sweep (three per cell): bit-identical, any size
+    (no oracle needed, so this also runs at sizes the oracle would be slow on)."""
+    base, Po, c, u, v = advection_case(N)
+    rng = np.random.default_rng(13)
+    u += 0.4 * rng.random(u.shape); v -= 0.3 * rng.random(v.shape)
+    interior(Po, c)[...] += rng.random((N, N)) * (rng.random((N, N)) > 0.5)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_velocity(aos(u, v)); ctx.upload_q(np.zeros(N * N))
+    out = {}
+    for shared in (1, 0):
+        ctx.set_option("sweep_shared", shared)
+        ctx.upload_c(c)
+        ctx.transport_step(0.4 / N)
+        ctx.advect_x(0.2 / N); ctx.advect_y(0.2 / N)
+        out[shared] = ctx.download_c()
+    ctx.set_option("sweep_shared", 1)
+    assert np.array_equal(out[0], out[1]), "max diff %g" % np.abs(out[0] - out[1]).max()
+    ctx.close()
+
+
 def check_source_step(emulated, N=32):
     lib = O.lib()
     base, Po, c, q = production_case(N)

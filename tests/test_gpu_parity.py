@@ -18,6 +18,8 @@ def test_library_is_cuda():
 def test_ghost_fills(): pc.check_ghost_fills(False)
 def test_velocity_roundtrip(): pc.check_velocity_roundtrip(False)
 def test_single_sweeps_bitexact(): pc.check_single_sweeps_bitexact(False, N=96)
+def test_single_sweeps_multitile_bitexact(): pc.check_single_sweeps_bitexact(False, N=700)
+def test_sweep_kernels_agree(): pc.check_sweep_variants(False, N=1030)
 def test_advection_muscl_bitexact(): pc.check_advection_bitexact(False, N=200, steps=10)
 def test_advection_muscl_smooth_bitexact(): pc.check_advection_bitexact(False, N=128, steps=20, perturb=False)
 def test_advection_upwind_bitexact(): pc.check_advection_bitexact(False, N=128, steps=5, method=O.UPWIND)
