@@ -44,6 +44,24 @@ static inline Grid make_slab(int N1g, int N2, int rank, int nranks) {
     return g;
 }
 
+// ---- 128-bit accesses of an aligned pair of doubles
+struct d2 { double x, y; };
+IMPEC_D d2 ld2(const double *p) {
+#ifndef IMPEC_EMU
+    const double2 v = *reinterpret_cast<const double2 *>(p);
+    d2 r; r.x = v.x; r.y = v.y; return r;
+#else
+    d2 r; r.x = p[0]; r.y = p[1]; return r;
+#endif
+}
+IMPEC_D void st2(double *p, double a, double b) {
+#ifndef IMPEC_EMU
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
 // ---- reductions -------------------------------------------------------------------------------
 // Stage 1: every block reduces its values with warp shuffles + one shared-memory hop and writes ONE
 // partial to part[blockIdx]; stage 2 (k_reduce_final) combines the partials in a fixed pairwise tree,

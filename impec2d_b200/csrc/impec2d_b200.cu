@@ -65,6 +65,8 @@ struct impec_ctx {
                                                     // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
     bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
+    bool fused_mid = true;                          // W-cycle revisit: sweep + residual + restriction in one tile kernel (FUSED_MID)
+    bool matvec_march = true;                       // PCG direction update + mat-vec as a register march (k_pcg_matvec_march); 0 = shared-memory tiles
     bool sweep_shared = true;                       // MUSCL sweeps evaluate each reconstruction once (k_muscl_x / k_muscl_y); 0 = k_sweep
     bool use_small = true;                          // levels of <= SM_MAXCELLS cells: whole V-cycle in one single-CTA launch (kernels_small.inl)
     long long launches = 0;
@@ -110,6 +112,11 @@ static int fail(impec_ctx *ctx, int code, const char *fmt, ...) {
 
 static inline dim3 grid2d(int nx, int ny) { return dim3((unsigned)((nx + BX - 1) / BX), (unsigned)((ny + BY - 1) / BY)); }
 static const dim3 kBlock(BX, BY);
+// k_pcg_matvec_march: a CTA marches down `rows` rows of a 256-column strip (64 rows; 32 on short slabs so that the grid
+// still fills the 148 SMs several times over)
+static inline int matvec_march_rows(const Grid &g) { return g.N1 > 4096 ? 64 : 32; }
+static inline dim3 matvec_march_grid(const Grid &g) { const int r = matvec_march_rows(g); return dim3((unsigned)((g.N2 + 2 * MV_BLOCK - 1) / (2 * MV_BLOCK)), (unsigned)((g.N1 + r - 1) / r)); }
+static inline dim3 update_xr_grid(const Grid &g) { return dim3((unsigned)((g.N2 + 2 * UX_BLOCK - 1) / (2 * UX_BLOCK)), (unsigned)((g.N1 + UX_ROWS - 1) / UX_ROWS)); }
 
 static int dev_alloc(impec_ctx *ctx, double **ptr, size_t n) {
     void *p = nullptr;
@@ -478,6 +485,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     SMEM_ATTR3(FUSED_PLAIN, true); SMEM_ATTR3(FUSED_PLAIN, false);
     SMEM_ATTR3(FUSED_PRE, true); SMEM_ATTR3(FUSED_PRE, false);
     SMEM_ATTR3(FUSED_POST, true); SMEM_ATTR3(FUSED_POST, false);
+    SMEM_ATTR3(FUSED_MID, true); SMEM_ATTR3(FUSED_MID, false);
     SMEM_ATTR(k_mg_coarse_solve<true>); SMEM_ATTR(k_mg_coarse_solve<false>);
 #undef SMEM_ATTR3
 #undef SMEM_ATTR
@@ -589,6 +597,8 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
     if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "matvec_march") { ctx->matvec_march = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_shared") { ctx->sweep_shared = value != 0.0; return IMPEC_OK; }
     if (k == "mg_small") { ctx->use_small = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
@@ -948,11 +958,17 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
         for (int gc = 1; gc < gamma; gc++) {
             TRY(fused_post(C, l, f, nullptr, nullptr));               // prolong + correct + backward sweep
             if (dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
+            if (!dist && ctx->fused_mid && !use_staged(ctx)) {
+                // sweep + residual + restriction in one tile kernel (needs 4 halo rows: single-GPU / replicated levels only)
+                LAUNCH_FUSED(ctx, FUSED_MID, L.th, fused_grid<FUSED_MID>(L.g, L.th), C.D[l], f, (const double *)L.x, L.t, 0, Lc.g, (const double *)nullptr, Lc.f, (double *)nullptr);
+                std::swap(L.x, L.t);
+            } else {
             TRY(fused_plain(C, l, f, true));
             if (dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
             LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1 + 2), kBlock, C.D[l], f, (const double *)L.x, L.r);
             if (tr) LAUNCH(ctx, k_restrict, grid2d(Lc.gl.N2, Lc.gl.N1), kBlock, L.g, L.r, Lc.gl, Lc.fl);
             else LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L.g, L.r, Lc.g, Lc.f);
+            }
             TRY(gather_coarse_rhs(ctx, l));
             TRY(mg_cycle(C, l + 1, Lc.f));
             if (Lc.dist) TRY(exchange_rows(ctx, Lc.x, Lc.g, 2));
@@ -1042,6 +1058,9 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
     // Fused path: d <- z + beta d, s <- S d and <s,d> in ONE tile kernel (k_pcg_matvec); the search direction ping-pongs
     // between two buffers because the kernel reads d with a halo and writes its interior.
     const bool fuse_dir = ctx->fused;
+    const dim3 gux = update_xr_grid(g);
+    const int mvrows = matvec_march_rows(g);
+    const dim3 gmm = matvec_march_grid(g);
     const dim3 gmv = fused_grid<FUSED_PLAIN>(g);
     const long long nmv = (long long)gmv.x * gmv.y;
     double *dcur = ctx->d, *dalt = ctx->d2buf;
@@ -1057,10 +1076,15 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         if (fuse_dir) {
             // beta = gamma_new / gamma_old sits in scal[S_BETA_NUM], scal[S_BETA_DEN] (set at the end of the previous pass)
             TRY(exchange_rows2(ctx, ctx->L[0].x, first_dir ? nullptr : dcur, g, 1));
-            if (first_dir) LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<true>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
-            else LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
+            if (ctx->matvec_march) {
+                if (first_dir) LAUNCH_COOP(ctx, k_pcg_matvec_march<true>, gmm, dim3(MV_BLOCK), A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part, mvrows);
+                else LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, gmm, dim3(MV_BLOCK), A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part, mvrows);
+            } else {
+                if (first_dir) LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<true>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
+                else LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
+            }
             std::swap(dcur, dalt); first_dir = false;
-            TRY(reduce_final(ctx, RED_SUM, nmv, 1, 0, S_SDOTP));
+            TRY(reduce_final(ctx, RED_SUM, ctx->matvec_march ? (long long)gmm.x * gmm.y : nmv, 1, 0, S_SDOTP));
         } else {
             TRY(exchange_rows(ctx, dcur, g, 1));
             LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, A, dcur, ctx->s, ctx->part);
@@ -1068,8 +1092,8 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         }
         // alpha = gamma / <s,d>: the kernel reads scal[0]/scal[1], so gamma must sit in slot 0
         if (ig != S_GAMMA0) { CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal + S_GAMMA0, ctx->scal + ig, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)); ig = S_GAMMA0; }
-        LAUNCH_COOP(ctx, k_update_xr, gr, kBlock, g, ctx->scal, (const double *)dcur, ctx->s, x, ctx->r, ctx->part);
-        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_IPROD));
+        LAUNCH_COOP(ctx, k_update_xr, gux, dim3(UX_BLOCK), g, ctx->scal, (const double *)dcur, ctx->s, x, ctx->r, ctx->part);
+        TRY(reduce_final(ctx, RED_SUM, (long long)gux.x * gux.y, 1, 0, S_IPROD));
         TRY(fetch_scalars(ctx, S_IPROD, 1));
         i_prod = ctx->h_scal[S_IPROD];
         if (i_prod / bi_prod < eps * eps) { converged = 1; break; }
@@ -1397,9 +1421,10 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "residual") { LAUNCH(ctx, k_residual, gr, kBlock, C.D[0], ctx->r, (const double *)L0.x, L0.r); return IMPEC_OK; }
         if (k == "restrict") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L0.g, L0.r, Lc.g, Lc.f); return IMPEC_OK; }
         if (k == "prolong_add") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_prolong_add, gr, kBlock, Lc.g, Lc.x, L0.g, L0.x, L0.pin); return IMPEC_OK; }
+        if (k == "pcg_matvec" && ctx->matvec_march) { LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, matvec_march_grid(g), dim3(MV_BLOCK), C.D[0], (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part, matvec_march_rows(g)); return IMPEC_OK; }
         if (k == "pcg_matvec") { LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, fused_grid<FUSED_PLAIN>(g), kFusedBlock, kFusedSmem, C.D[0], (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part); return IMPEC_OK; }
         if (k == "matvec_dot") { LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, C.D[0], ctx->d, ctx->s, ctx->part); return IMPEC_OK; }
-        if (k == "update_xr") { LAUNCH_COOP(ctx, k_update_xr, gr, kBlock, g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part); return IMPEC_OK; }
+        if (k == "update_xr") { LAUNCH_COOP(ctx, k_update_xr, update_xr_grid(g), dim3(UX_BLOCK), g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part); return IMPEC_OK; }
         if (k == "dot") { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part); return IMPEC_OK; }
         if (k == "update_d") { LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_TMP, ctx->z, ctx->d); return IMPEC_OK; }
         if (k == "vcycle") return mg_cycle(C, 0, ctx->r);

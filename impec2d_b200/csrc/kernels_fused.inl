@@ -9,6 +9,8 @@
 //                                                                  full-weighting restriction; x is never read)
 //   FUSED_POST  : x <- x + P ec; x <- sweep(x); part += <f,x>     (prolongation + correction + post-smooth,
 //                                                                  with the PCG dot product <r,z> on level 0)
+//   FUSED_MID   : x <- sweep(x); r = f - S x; fc = R r            (second visit of a W-cycle level: sweep from the current
+//                                                                  iterate + full residual + restriction; single-GPU levels)
 //
 // Thread (tx,ty) owns the cell pair (columns 2tx, 2tx+1) of rows ty, ty+8, ...: one cell of the pair is red
 // and one black, so both colour stages keep every lane busy and global accesses are 128-bit.
@@ -22,27 +24,10 @@
 #define FT_NTY 8                 // thread rows per CTA
 #define FT_ROWS (FT_H / FT_NTY)  // rows per thread
 #define FT_TJ (FT_W - 2 * FT_HJ) // interior columns per tile (120)
-enum { FUSED_PLAIN = 0, FUSED_PRE = 1, FUSED_POST = 2 };
+enum { FUSED_PLAIN = 0, FUSED_PRE = 1, FUSED_POST = 2, FUSED_MID = 3 };
 // TH = tile height: 64 on the big levels (least halo overhead); 32 / 16 on the small ones, where a level is only a few
 // tiles and the time of a launch is the time ONE CTA needs for its tile (more, shorter CTAs finish sooner)
-template <int MODE, int TH = FT_H> struct FusedGeom { enum { HI = (MODE == FUSED_PRE) ? 3 : 2, TI = TH - 2 * HI }; };
-
-struct d2 { double x, y; };
-IMPEC_D d2 ld2(const double *p) {
-#ifndef IMPEC_EMU
-    const double2 v = *reinterpret_cast<const double2 *>(p);
-    d2 r; r.x = v.x; r.y = v.y; return r;
-#else
-    d2 r; r.x = p[0]; r.y = p[1]; return r;
-#endif
-}
-IMPEC_D void st2(double *p, double a, double b) {
-#ifndef IMPEC_EMU
-    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
-#else
-    p[0] = a; p[1] = b;
-#endif
-}
+template <int MODE, int TH = FT_H> struct FusedGeom { enum { HI = (MODE == FUSED_PRE) ? 3 : ((MODE == FUSED_MID) ? 4 : 2), TI = TH - 2 * HI }; };
 
 // shared-memory index of tile cell (r, jj): row-major, even columns in the first half of the row
 IMPEC_D int xi(int r, int jj) { return r * FT_W + ((jj & 1) << 6) + (jj >> 1); }
@@ -82,6 +67,15 @@ IMPEC_D double tile_diagsum(const CF &A, int ld, const double *__restrict__ X, i
     s = fma((double)A.AV[k + 1], oth[-FT_W], s);
     s = fma((double)A.AV[k + ld + 1], oth[FT_W], s);
     return s;
+}
+
+// diagonal of the links operator from the coefficient view (same association as link_diag)
+template <class CF>
+IMPEC_D double tile_diag(const CF &A, const LevelDev &L, int ld, size_t k) {
+    double d = L.mass + ((((double)A.AW[k] + (double)A.AW[k + ld]) + ((double)A.AS[k] + (double)A.AS[k + 1])) +
+                         (((double)A.AV[k] + (double)A.AV[k + ld]) + ((double)A.AV[k + 1] + (double)A.AV[k + ld + 1])));
+    if ((long long)k == L.sig_idx) d += L.sig[0];
+    return d;
 }
 
 // nsweeps > 1 (PLAIN only, and only when this single tile holds the WHOLE level so that no halo can go stale): the
@@ -195,15 +189,32 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
         dotv = block_reduce<RED_SUM>(dotv);
         if (tx == 0 && ty == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
     }
-    if (MODE != FUSED_PRE) return;
+    if (MODE != FUSED_PRE && MODE != FUSED_MID) return;
 
     // ---- PRE: residual on the tile shrunk by 2, then full-weighting restriction.
     // After a sweep from a ZERO guess the residual needs no diagonal: a first-colour cell was solved when all
     // its neighbours were still zero, so r = sum over all 8 neighbours of a_nb x_nb; a second-colour cell was
     // solved against the final first-colour values, so only its (same-colour) diagonal neighbours contribute.
     // (The dropped terms f - d x + s_at_update are rounding noise, O(eps |f|).)
+    // ---- MID: the sweep started from a non-zero iterate, so the residual is evaluated in full, on the tile shrunk by 3.
     double ra[(TH / FT_NTY)], rb[(TH / FT_NTY)];
-    {
+    if (MODE == FUSED_MID) {
+#pragma unroll
+        for (int n = 0; n < (TH / FT_NTY); n++) {
+            const int r = ty + n * FT_NTY, ig = i0 + r;
+            double v[2] = {0., 0.};
+            if (r >= 3 && r < TH - 3 && (!EDGE || (ig >= g.rlo && ig < g.rhi))) {
+                const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
+#pragma unroll
+                for (int off = 0; off < 2; off++) {
+                    const int jc = jl + off;
+                    if (jc >= 3 && jc < FT_W - 3 && (!EDGE || (jg + off >= 0 && jg + off < g.N2 && (long long)(k + off) != L.pin)))
+                        v[off] = f[k + off] - (tile_diag(A, L, ld, k + off) * X[r * FT_W + (off << 6) + tx] - tile_offsum(A, ld, X, r, tx, off, k + off));
+                }
+            }
+            ra[n] = v[0]; rb[n] = v[1];
+        }
+    } else {
         const int off0 = (par == c0) ? 0 : 1;                            // first-colour cell of the pair
 #pragma unroll
         for (int n = 0; n < (TH / FT_NTY); n++) {
@@ -345,4 +356,96 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY, 2) k_pcg_matvec(LevelDev L,
     }
     if (edge) pcg_matvec_body_rw<FIRST, true>(L, scal, z, din, dout, s, part, X);
     else pcg_matvec_body_rw<FIRST, false>(L, scal, z, din, dout, s, part, X);
+}
+
+// ---------------------------------------------------------------- marching variant of the fused direction update + mat-vec
+// Same operation as k_pcg_matvec, organised as a 2.5-D march instead of shared-memory tiles (the tile kernel spends most
+// of its time with every warp waiting on the tile load: ncu long_scoreboard 25 warps per issue, 22 % issue activity, 57 %
+// of DRAM peak).  A WARP owns 64 columns (a 128-bit column pair per lane) and marches down `nrows` rows:
+//   * the new direction d = z + beta d of rows i-1, i, i+1 lives in registers; the two neighbour columns of a pair come
+//     from the adjacent lanes by shuffle, and the two columns just outside the warp are recomputed by lanes 0 and 31
+//     (two extra scalar loads per row and warp) -- no shared memory, no block barrier, warps never wait for each other;
+//   * every link value is loaded ONCE per thread (rows i and i+1 of AW / AV are carried over to the next step), the tile
+//     kernel fetched each twice through L1;
+//   * the loads of the next MV_PF rows are in flight while a row is processed (~100 B per row and thread), so the
+//     memory-level parallelism no longer depends on occupancy.
+#define MV_BLOCK 128
+#define MV_PF 2
+struct MvRow { d2 z, d, aw, av, as; double ez, ed, av2, as2; };
+
+template <bool FIRST>
+IMPEC_D MvRow mv_load_row(const LevelDev &L, const double *__restrict__ z, const double *__restrict__ din, size_t k, bool ok, int eoff) {
+    MvRow R;
+    R.z.x = R.z.y = R.d.x = R.d.y = R.aw.x = R.aw.y = R.av.x = R.av.y = R.as.x = R.as.y = 0.;
+    R.ez = R.ed = R.av2 = R.as2 = 0.;
+    if (ok) {
+        R.z = ld2(z + k);
+        if (!FIRST) R.d = ld2(din + k);
+        R.aw = ld2(L.AW + k); R.av = ld2(L.AV + k); R.as = ld2(L.AS + k);
+        R.av2 = L.AV[k + 2]; R.as2 = L.AS[k + 2];
+        if (eoff) { R.ez = z[(long long)k + eoff]; if (!FIRST) R.ed = din[(long long)k + eoff]; }
+    }
+    return R;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(MV_BLOCK, 3) k_pcg_matvec_march(LevelDev L, const double *__restrict__ scal, const double *__restrict__ z, const double *__restrict__ din,
+                                                                  double *__restrict__ dout, double *__restrict__ s, double *__restrict__ part, int nrows) {
+    const Grid g = L.g;
+    const size_t ld = (size_t)g.ld;
+    const int lane = threadIdx.x & 31;
+    const int jA = 2 * (int)(blockIdx.x * MV_BLOCK + threadIdx.x);       // columns jA, jA+1
+    const int ia = (int)blockIdx.y * nrows;
+    const int ib = (ia + nrows < g.N1) ? ia + nrows : g.N1;               // rows [ia, ib)
+    const bool ok = jA < g.N2, two = jA + 1 < g.N2;
+    // lane 0 also evaluates column jA-1, lane 31 column jA+2 (allocated: pad columns on both sides of a row)
+    const int eoff = !ok ? 0 : (lane == 0 ? -1 : ((lane == 31 && jA + 2 <= g.N2) ? 2 : 0));
+    const double beta = FIRST ? 0. : scal[0] / scal[1];
+    const size_t kb = gidx(g, ia - 1, ok ? jA : 0);
+    // state: direction on rows r-2, r-1, r (columns jA-1 | jA, jA+1 | jA+2) and the links of row r-1
+    double l0 = 0., a0 = 0., b0 = 0., r0 = 0., l1 = 0., a1 = 0., b1 = 0., r1 = 0.;
+    d2 awc, avc, asc; double avc2 = 0., asc2 = 0.;
+    awc.x = awc.y = avc.x = avc.y = asc.x = asc.y = 0.;
+    double dotv = 0.;
+    MvRow q[MV_PF];
+#pragma unroll
+    for (int u = 0; u < MV_PF; u++) { const int row = (ia - 1 + u < ib) ? ia - 1 + u : ib; q[u] = mv_load_row<FIRST>(L, z, din, kb + (size_t)(row - ia + 1) * ld, ok, eoff); }
+    for (int base = ia - 1; base <= ib; base += MV_PF) {
+#pragma unroll
+        for (int u = 0; u < MV_PF; u++) {
+            const int row = base + u;
+            if (row > ib) continue;
+            const MvRow R = q[u];
+            { const int nx = (row + MV_PF < ib) ? row + MV_PF : ib; q[u] = mv_load_row<FIRST>(L, z, din, kb + (size_t)(nx - ia + 1) * ld, ok, eoff); }
+            // new direction on this row
+            const double a2 = FIRST ? R.z.x : R.z.x + beta * R.d.x;
+            const double b2 = FIRST ? R.z.y : R.z.y + beta * R.d.y;
+            const double e2 = FIRST ? R.ez : R.ez + beta * R.ed;
+            double l2 = IMPEC_SHFL_UP(b2, 1), r2 = IMPEC_SHFL_DOWN(a2, 1);
+            if (lane == 0) l2 = e2;
+            if (lane == 31) r2 = e2;
+            if (row > ia) {                                              // s on row row-1 from rows row-2, row-1, row
+                const size_t k = kb + (size_t)(row - ia) * ld;           // cell (row-1, jA)
+                double dA = L.mass + (((awc.x + R.aw.x) + (asc.x + asc.y)) + ((avc.x + R.av.x) + (avc.y + R.av.y)));
+                double dB = L.mass + (((awc.y + R.aw.y) + (asc.y + asc2)) + ((avc.y + R.av.y) + (avc2 + R.av2)));
+                if ((long long)k == L.sig_idx) dA += L.sig[0];
+                if ((long long)(k + 1) == L.sig_idx) dB += L.sig[0];
+                double oA = awc.x * a0;
+                oA = fma(R.aw.x, a2, oA); oA = fma(asc.x, l1, oA); oA = fma(asc.y, b1, oA);
+                oA = fma(avc.x, l0, oA); oA = fma(R.av.x, l2, oA); oA = fma(avc.y, b0, oA); oA = fma(R.av.y, b2, oA);
+                double oB = awc.y * b0;
+                oB = fma(R.aw.y, b2, oB); oB = fma(asc.y, a1, oB); oB = fma(asc2, r1, oB);
+                oB = fma(avc.y, a0, oB); oB = fma(R.av.y, a2, oB); oB = fma(avc2, r0, oB); oB = fma(R.av2, r2, oB);
+                const double sA = ((long long)k == L.pin) ? 0. : dA * a1 - oA;
+                const double sB = ((long long)(k + 1) == L.pin) ? 0. : dB * b1 - oB;
+                if (two) { st2(dout + k, a1, b1); st2(s + k, sA, sB); dotv = fma(sA, a1, dotv); dotv = fma(sB, b1, dotv); }
+                else if (ok) { dout[k] = a1; s[k] = sA; dotv = fma(sA, a1, dotv); }
+            }
+            l0 = l1; a0 = a1; b0 = b1; r0 = r1;
+            l1 = l2; a1 = a2; b1 = b2; r1 = r2;
+            awc = R.aw; avc = R.av; avc2 = R.av2; asc = R.as; asc2 = R.as2;
+        }
+    }
+    dotv = block_reduce<RED_SUM>(dotv);
+    if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
 }

@@ -279,21 +279,45 @@ __global__ void __launch_bounds__(256) k_matvec_dot(LevelDev L, const double *__
 }
 
 // x += alpha d ; r -= alpha s ; partial <r,r>.  alpha = scal[0]/scal[1] is read from device memory.
-__global__ void __launch_bounds__(256) k_update_xr(Grid g, const double *__restrict__ scal, const double *__restrict__ d, const double *__restrict__ s,
-                                                   double *__restrict__ x, double *__restrict__ r, double *__restrict__ part) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+// A pure stream (48 B/cell): a thread owns a column PAIR in UX_ROWS rows and issues all its 128-bit loads before the
+// first store (256 B in flight per thread), and a CTA covers 256 x UX_ROWS cells, so there are 4x fewer partial sums
+// for k_reduce_final than with one cell per thread.
+#define UX_ROWS 4
+#define UX_BLOCK 128
+__global__ void __launch_bounds__(UX_BLOCK) k_update_xr(Grid g, const double *__restrict__ scal, const double *__restrict__ d, const double *__restrict__ s,
+                                                        double *__restrict__ x, double *__restrict__ r, double *__restrict__ part) {
+    const int j = 2 * (int)(blockIdx.x * UX_BLOCK + threadIdx.x);
+    const int i0 = (int)blockIdx.y * UX_ROWS;
     const double alpha = scal[0] / scal[1];
     double v = 0.;
-    if (i < g.N1 && j < g.N2) {
-        const size_t k = gidx(g, i, j);
-        x[k] += alpha * d[k];
-        const double rk = r[k] - alpha * s[k];
-        r[k] = rk;
-        v = rk * rk;
+    if (j + 1 < g.N2) {
+        d2 dv[UX_ROWS], sv[UX_ROWS], xv[UX_ROWS], rv[UX_ROWS];
+#pragma unroll
+        for (int n = 0; n < UX_ROWS; n++) {
+            if (i0 + n >= g.N1) continue;
+            const size_t k = gidx(g, i0 + n, j);
+            dv[n] = ld2(d + k); sv[n] = ld2(s + k); xv[n] = ld2(x + k); rv[n] = ld2(r + k);
+        }
+#pragma unroll
+        for (int n = 0; n < UX_ROWS; n++) {
+            if (i0 + n >= g.N1) continue;
+            const size_t k = gidx(g, i0 + n, j);
+            st2(x + k, xv[n].x + alpha * dv[n].x, xv[n].y + alpha * dv[n].y);
+            const double ra = rv[n].x - alpha * sv[n].x, rb = rv[n].y - alpha * sv[n].y;
+            st2(r + k, ra, rb);
+            v += ra * ra; v += rb * rb;
+        }
+    } else if (j < g.N2) {
+        for (int n = 0; n < UX_ROWS && i0 + n < g.N1; n++) {
+            const size_t k = gidx(g, i0 + n, j);
+            x[k] += alpha * d[k];
+            const double rk = r[k] - alpha * s[k];
+            r[k] = rk;
+            v += rk * rk;
+        }
     }
     v = block_reduce<RED_SUM>(v);
-    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+    if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
 }
 
 // partial <a,b> (and optionally <a,a> in a second partial array)

@@ -236,6 +236,26 @@ def check_fused_vs_unfused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
         assert np.array_equal(z, out[1]), "tile height changes the result"
 
 
+def check_matvec_variants(emulated, N1=80, N2=272, stype=O.DIAGONAL, eps=1e-11):
+    """k_pcg_matvec_march (register march, warp shuffles) against k_pcg_matvec (shared-memory tiles) inside a full
+    pressure solve: identical arithmetic per cell, only the order of the dot-product partial sums differs, so the
+    iteration count is the same and the pressures agree to rounding (<= 1e-12 relative).  Several row chunks and
+    column strips, a partial last warp; callers add a small odd-N2 case (single level) for the unpaired last column."""
+    base, Po, c, q = production_case(N1, N2, stype=stype, eps=eps)
+    Pi = I.default_params(emulated=emulated, **base)
+    res = []
+    for march in (1, 0):
+        ctx = I.Context(Pi, emulated=emulated)
+        ctx.set_option("matvec_march", march)
+        ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries()
+        info = ctx.pressure_solve()
+        assert info.converged == 1
+        res.append((info.iterations, ctx.download_p()))
+        ctx.close()
+    assert res[0][0] == res[1][0], (res[0][0], res[1][0])
+    assert rel_l2(interior(Po, res[0][1]), interior(Po, res[1][1])) <= 1e-12
+
+
 def check_small_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
     """The single-CTA bottom-of-hierarchy kernel (kernels_small.inl, levels of <= 4096 cells) against the tile kernels
     on the same levels: same arithmetic per cell, so one cycle agrees to rounding (<= 1e-13 relative), with FP64 and
@@ -305,6 +325,7 @@ def check_staged_vs_fused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
     for staged in (0, 1):
         ctx = I.Context(Pi, emulated=emulated)
         ctx.set_option("mg_links_fp32", 1); ctx.set_option("mg_staged", staged)
+        ctx.set_option("mg_fused_mid", 0)      # the staged variant has no MID kernel; compare like with like
         ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
         z1 = ctx.vcycle(r); z2 = ctx.vcycle(r)
         assert np.array_equal(z1, z2), "cycle is not repeatable (race?)"

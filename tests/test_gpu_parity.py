@@ -33,6 +33,8 @@ def test_advection_other_splittings_bitexact(split): pc.check_advection_bitexact
 def test_source_step(): pc.check_source_step(False, N=128)
 def test_fused_vs_unfused_cycle(): pc.check_fused_vs_unfused(False, 1024, 1536)
 def test_staged_vs_fused_cycle(): pc.check_staged_vs_fused(False, 1024, 1536)
+def test_matvec_march_vs_tiles(): pc.check_matvec_variants(False, 1152, 2064)
+def test_matvec_march_odd_columns(): pc.check_matvec_variants(False, 20, 31, eps=1e-9)
 def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(False, 1024, 1536)
 
 
