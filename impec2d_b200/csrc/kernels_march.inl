@@ -1,0 +1,310 @@
+// kernels_march.inl -- the fused multigrid kernels as register MARCHES (big levels).
+//
+// Same mathematics, cell for cell and bit for bit, as k_mg_fused<PRE/POST/PLAIN> in kernels_fused.inl, but organised
+// like k_pcg_matvec_march: a WARP owns 64 columns (one 128-bit column pair per lane) and marches down a chunk of rows.
+// The iterate of the last few rows lives in registers, the neighbour columns of a pair come from the adjacent lanes by
+// shuffle, nothing goes through shared memory and no warp ever waits at a block barrier.  The colour stages, the
+// residual and the restriction are SKEWED along the march: when row t arrives,
+//     PRE  : first colour on row t, second colour on row t-1, residual on row t-2, coarse row (t-4)/2;
+//     POST : prolongation on row t, first colour on row t-1, second colour on row t-2 (stored, dotted with f).
+// Halo: values that depend on a column outside the warp are wrong in the outermost lanes; the wrong region grows by one
+// column per dependent stage, so PRE discards two lanes per side (56 of 64 columns are stored, the same 4-column halo as
+// the tiles) and POST/PLAIN one lane per side (60 of 64).  Rows: a chunk of `nrows` rows starts 3 (PRE) / 2 (POST) rows
+// early.  Each link value and each vector element is loaded once per warp that needs it, the loads of the next MG_PF
+// rows are in flight while a row is processed, and the row parity (which cell of the pair has which colour) is a
+// template parameter of the step, so a step has no colour branches.
+//
+// Why: the tile kernels sit at 52-61 % of the HBM roofline with every warp stalled on the tile load (ncu long_scoreboard
+// 8-13 warps per issue at 50 % occupancy) and 147 instructions per cell; the same reorganisation took the PCG mat-vec
+// from 57 % to 95 % of the measured copy bandwidth.
+#define MG_BLOCK 128
+#define MG_PF 2
+#define MGP_OWN 56                // columns a warp stores in PRE (lanes 2..29)
+#define MGS_OWN 60                // columns a warp stores in POST / PLAIN (lanes 1..30)
+
+template <bool F32> struct CoefType;
+template <> struct CoefType<true> { typedef float T; };
+template <> struct CoefType<false> { typedef double T; };
+template <class T> struct cpair { T x, y; };
+IMPEC_D cpair<float> ldc2(const float *p) {
+#ifndef IMPEC_EMU
+    const float2 v = *reinterpret_cast<const float2 *>(p);
+    cpair<float> r; r.x = v.x; r.y = v.y; return r;
+#else
+    cpair<float> r; r.x = p[0]; r.y = p[1]; return r;
+#endif
+}
+IMPEC_D cpair<double> ldc2(const double *p) { const d2 v = ld2(p); cpair<double> r; r.x = v.x; r.y = v.y; return r; }
+
+// links and inverse diagonal of one row of a column pair: cell A uses .x (and .y for its right / upper-right link), cell B
+// uses .y and the third value
+template <bool F32> struct CoefRow {
+    typedef typename CoefType<F32>::T T;
+    cpair<T> dinv, aw, as, av; T as2, av2;
+};
+template <bool F32> IMPEC_D CoefRow<F32> coef_zero() {
+    CoefRow<F32> c; c.dinv.x = c.dinv.y = c.aw.x = c.aw.y = c.as.x = c.as.y = c.av.x = c.av.y = 0; c.as2 = c.av2 = 0; return c;
+}
+template <bool F32> IMPEC_D CoefRow<F32> coef_load(const Coef<F32> &A, size_t k) {
+    CoefRow<F32> c;
+    c.dinv = ldc2(A.DINV + k); c.aw = ldc2(A.AW + k); c.as = ldc2(A.AS + k); c.av = ldc2(A.AV + k);
+    c.as2 = A.AS[k + 2]; c.av2 = A.AV[k + 2];
+    return c;
+}
+// sum over the 8 neighbours in the order of tile_offsum: up, down, left, right, up-left, down-left, up-right, down-right
+IMPEC_D double sum8(double w_up, double w_dn, double w_l, double w_r, double w_ul, double w_dl, double w_ur, double w_dr,
+                    double up, double dn, double l, double r, double ul, double dl, double ur, double dr) {
+    double s = w_up * up;
+    s = fma(w_dn, dn, s); s = fma(w_l, l, s); s = fma(w_r, r, s);
+    s = fma(w_ul, ul, s); s = fma(w_dl, dl, s); s = fma(w_ur, ur, s); s = fma(w_dr, dr, s);
+    return s;
+}
+IMPEC_D double sum4(double w0, double w1, double w2, double w3, double v0, double v1, double v2, double v3) {
+    double s = w0 * v0;
+    s = fma(w1, v1, s); s = fma(w2, v2, s); s = fma(w3, v3, s);
+    return s;
+}
+
+// ================================================================ PRE: sweep from zero + residual + restriction
+template <bool F32> struct PreRow { d2 f; CoefRow<F32> c; };
+template <bool F32> IMPEC_D PreRow<F32> pre_load(const Coef<F32> &A, const double *__restrict__ f, long long k, bool ok) {
+    PreRow<F32> R; R.f.x = R.f.y = 0.; R.c = coef_zero<F32>();
+    if (ok) { R.f = ld2(f + k); R.c = coef_load<F32>(A, (size_t)k); }
+    return R;
+}
+template <bool F32> struct PreState {
+    double xF1, e01;                       // row t-1: its first-colour value and the first-colour value next to its second-colour cell
+    d2 f1; CoefRow<F32> c1;                // row t-1
+    double xl2, xA2, xB2, xr2; CoefRow<F32> c2;   // row t-2 (final)
+    double xl3, xA3, xB3, xr3;             // row t-3 (final)
+    double h0, h1, h2, h3;                 // j-restricted residual of rows t-5 .. t-2
+};
+struct PreGeom {
+    int t_rlo, t_rhi;                      // active rows
+    int wlo, whi;                          // rows of x this chunk stores
+    int Ilo, Ihi;                          // coarse rows this chunk stores
+    int jA, J; bool colok, own, own_c, clamp_l, clamp_r, wall_lo, wall_hi;
+    int N1;
+    long long kb, ld, pin;                 // index of (row 0, jA), pitch, pinned cell
+    long long kcb, ldc;                    // coarse: index of (row 0, J), pitch
+};
+
+// AF: on row t the even-column cell A carries the first colour
+template <bool F32, bool AF>
+IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const PreGeom &G, double *__restrict__ x, double *__restrict__ fc) {
+    // 1. first colour on row t (zero guess: no neighbours)
+    const bool act0 = G.colok && t >= G.t_rlo && t < G.t_rhi;
+    const double xF = act0 ? (AF ? R.f.x * (double)R.c.dinv.x : R.f.y * (double)R.c.dinv.y) : 0.;
+    const double e0 = AF ? IMPEC_SHFL_DOWN(xF, 1) : IMPEC_SHFL_UP(xF, 1);
+    // 2. second colour on row t-1: its face neighbours carry final first-colour values, its diagonal neighbours are still zero
+    const bool act1 = G.colok && t - 1 >= G.t_rlo && t - 1 < G.t_rhi;
+    double xl1, xA1, xB1, xr1;
+    if (AF) {   // row t-1: B first, A second
+        double off = (double)S.c1.aw.x * S.xA2;
+        off = fma((double)R.c.aw.x, xF, off); off = fma((double)S.c1.as.x, S.e01, off); off = fma((double)S.c1.as.y, S.xF1, off);
+        const double xS = act1 ? (S.f1.x + off) * (double)S.c1.dinv.x : 0.;
+        xA1 = xS; xB1 = S.xF1; xl1 = S.e01; xr1 = IMPEC_SHFL_DOWN(xS, 1);
+    } else {    // row t-1: A first, B second
+        double off = (double)S.c1.aw.y * S.xB2;
+        off = fma((double)R.c.aw.y, xF, off); off = fma((double)S.c1.as.y, S.xF1, off); off = fma((double)S.c1.as2, S.e01, off);
+        const double xS = act1 ? (S.f1.y + off) * (double)S.c1.dinv.y : 0.;
+        xA1 = S.xF1; xB1 = xS; xr1 = S.e01; xl1 = IMPEC_SHFL_UP(xS, 1);
+    }
+    if (G.own && t - 1 >= G.wlo && t - 1 < G.whi) st2(x + G.kb + (long long)(t - 1) * G.ld, xA1, xB1);
+    // 3. residual on row t-2 (same parity as row t).  After a sweep from zero: first colour = sum over all 8 neighbours,
+    //    second colour = sum over its 4 (same-colour) diagonal neighbours
+    const bool act2 = G.colok && t - 2 >= G.t_rlo && t - 2 < G.t_rhi;
+    const long long k2 = G.kb + (long long)(t - 2) * G.ld;
+    double rA, rB;
+    if (AF) {
+        rA = sum8((double)S.c2.aw.x, (double)S.c1.aw.x, (double)S.c2.as.x, (double)S.c2.as.y, (double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y,
+                  S.xA3, xA1, S.xl2, S.xB2, S.xl3, xl1, S.xB3, xB1);
+        rB = sum4((double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2, S.xA3, xA1, S.xr3, xr1);
+    } else {
+        rB = sum8((double)S.c2.aw.y, (double)S.c1.aw.y, (double)S.c2.as.y, (double)S.c2.as2, (double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2,
+                  S.xB3, xB1, S.xA2, S.xr2, S.xA3, xA1, S.xr3, xr1);
+        rA = sum4((double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y, S.xl3, xl1, S.xB3, xB1);
+    }
+    if (!act2 || k2 == G.pin) rA = 0.;
+    if (!act2 || k2 + 1 == G.pin) rB = 0.;
+    // 4. full weighting: along j now, along i when the fourth row of a coarse cell is complete
+    double rl = IMPEC_SHFL_UP(rB, 1), rr = IMPEC_SHFL_DOWN(rA, 1);
+    if (G.clamp_l) rl = rA;
+    if (G.clamp_r) rr = rB;
+    double h = 0.25 * rl;
+    h += 0.75 * rA; h += 0.75 * rB; h += 0.25 * rr;
+    S.h0 = S.h1; S.h1 = S.h2; S.h2 = S.h3; S.h3 = h;
+    if (AF) {                                  // t even: rows t-5 .. t-2 are rows 2I-1 .. 2I+2 of coarse row I
+        const int I = (t - 4) >> 1;
+        if (G.own_c && I >= G.Ilo && I < G.Ihi) {
+            const double t0 = (I == 0 && G.wall_lo) ? S.h1 : S.h0;                   // row -1 mirrors onto row 0
+            const double t3 = (2 * I + 2 > G.N1 - 1 && G.wall_hi) ? S.h2 : S.h3;     // row N1 mirrors onto row N1-1
+            fc[G.kcb + (long long)I * G.ldc] = 0.25 * (0.25 * t0 + 0.75 * S.h1 + 0.75 * S.h2 + 0.25 * t3);
+        }
+    }
+    // shift the pipeline
+    S.xl3 = S.xl2; S.xA3 = S.xA2; S.xB3 = S.xB2; S.xr3 = S.xr2;
+    S.xl2 = xl1; S.xA2 = xA1; S.xB2 = xB1; S.xr2 = xr1; S.c2 = S.c1;
+    S.xF1 = xF; S.e01 = e0; S.f1 = R.f; S.c1 = R.c;
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(MG_BLOCK, 3) k_mg_march_pre(LevelDev L, const double *__restrict__ f, double *__restrict__ x, Grid gc, double *__restrict__ fc, int nrows) {
+    const Grid g = L.g;
+    const Coef<F32> A(L);
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)blockIdx.x * (MG_BLOCK / 32) + (int)(threadIdx.x >> 5);
+    const int ia = (int)blockIdx.y * nrows;
+    const int ib = (ia + nrows < g.N1) ? ia + nrows : g.N1;
+    PreGeom G;
+    G.jA = MGP_OWN * gw - 4 + 2 * lane; G.J = G.jA >> 1;
+    G.colok = G.jA >= 0 && G.jA < g.N2;
+    G.own = G.colok && lane >= 2 && lane < 30;
+    G.own_c = G.own && G.J < gc.N2;
+    G.clamp_l = G.jA == 0; G.clamp_r = G.jA + 2 > g.N2 - 1;
+    G.wall_lo = g.wall_lo != 0; G.wall_hi = g.wall_hi != 0; G.N1 = g.N1;
+    G.t_rlo = g.rlo; G.t_rhi = g.rhi;
+    // a slab's first / last chunk also stores x on the 2 halo rows it has computed anyway (saves an exchange, see k_mg_fused)
+    G.wlo = (ia == 0 && !g.wall_lo) ? -2 : ia;
+    G.whi = (ib == g.N1 && !g.wall_hi) ? g.N1 + 2 : ib;
+    G.Ilo = ia >> 1; G.Ihi = (ib >> 1 < gc.N1) ? ib >> 1 : gc.N1;
+    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
+    G.ldc = gc.ld; G.kcb = (long long)IMPEC_GH * gc.ld + (G.colok ? G.J : 0) + IMPEC_PJ;
+    PreState<F32> S;
+    S.xF1 = S.e01 = 0.; S.f1.x = S.f1.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
+    S.xl2 = S.xA2 = S.xB2 = S.xr2 = S.xl3 = S.xA3 = S.xB3 = S.xr3 = 0.; S.h0 = S.h1 = S.h2 = S.h3 = 0.;
+    const int t0 = ia - 3, t1 = ib + 2;        // rows marched: [t0, t1], an even count; t0 is odd
+    PreRow<F32> q[MG_PF];
+#pragma unroll
+    for (int u = 0; u < MG_PF; u++) q[u] = pre_load<F32>(A, f, G.kb + (long long)(t0 + u) * G.ld, G.colok);
+    for (int t = t0; t <= t1; t += 2) {
+        { const PreRow<F32> R = q[0]; const int nx = (t + 2 <= t1) ? t + 2 : t1; q[0] = pre_load<F32>(A, f, G.kb + (long long)nx * G.ld, G.colok);
+          pre_step<F32, false>(t, R, S, G, x, fc); }
+        { const PreRow<F32> R = q[1]; const int nx = (t + 3 <= t1) ? t + 3 : t1; q[1] = pre_load<F32>(A, f, G.kb + (long long)nx * G.ld, G.colok);
+          pre_step<F32, true>(t + 1, R, S, G, x, fc); }
+    }
+}
+
+// ================================================================ POST / PLAIN: (prolongation +) sweep from the current iterate
+template <bool F32, bool PROLONG> struct PostRow { d2 xin, f; CoefRow<F32> c; double e[6]; };
+template <bool F32> struct PostState {
+    double il1, iA1, iB1, ir1, il2, iA2, iB2, ir2, il3, iA3, iB3, ir3;   // iterate before the sweep on rows t-1, t-2, t-3
+    double yF2, yF3, e2;                   // new first-colour values of rows t-2, t-3; first-colour value next to row t-2's second-colour cell
+    d2 f1, f2; CoefRow<F32> c1, c2;        // rows t-1, t-2
+};
+struct PostGeom {
+    int t_rlo, t_rhi, ia, ib;
+    int jA; bool colok, own;
+    long long kb, ld, pin;
+};
+template <bool F32, bool PROLONG>
+IMPEC_D PostRow<F32, PROLONG> post_load(const Coef<F32> &A, const double *__restrict__ f, const double *__restrict__ xin, const Grid &g, const Grid &gc,
+                                         const double *__restrict__ ec, const PostGeom &G, int t) {
+    PostRow<F32, PROLONG> R;
+    R.xin.x = R.xin.y = R.f.x = R.f.y = 0.; R.c = coef_zero<F32>();
+#pragma unroll
+    for (int a = 0; a < 6; a++) R.e[a] = 0.;
+    if (G.colok) {
+        const long long k = G.kb + (long long)t * G.ld;
+        R.xin = ld2(xin + k); R.f = ld2(f + k); R.c = coef_load<F32>(A, (size_t)k);
+        if (PROLONG && t >= G.t_rlo && t < G.t_rhi) {
+            // cell-centred bilinear prolongation with edge replication (same clamps as k_mg_fused)
+            const int I = t >> 1, J = G.jA >> 1;
+            int In = (t & 1) ? I + 1 : I - 1, Jm = J - 1, Jp = J + 1;
+            if (In < 0 && gc.wall_lo) In = 0;
+            if (In > gc.N1 - 1 && gc.wall_hi) In = gc.N1 - 1;
+            Jm = Jm < 0 ? 0 : Jm; Jp = Jp > gc.N2 - 1 ? gc.N2 - 1 : Jp;
+            const double *e0 = ec + gidx(gc, I, 0), *e1 = ec + gidx(gc, In, 0);
+            R.e[0] = e0[J]; R.e[1] = e1[J]; R.e[2] = e0[Jm]; R.e[3] = e1[Jm]; R.e[4] = e0[Jp]; R.e[5] = e1[Jp];
+        }
+    }
+    return R;
+}
+
+// AF: on row t the even-column cell A carries the first colour (so do rows t-2; rows t-1, t-3 have B first)
+template <bool F32, bool PROLONG, bool AF>
+IMPEC_D void post_step(const int t, const PostRow<F32, PROLONG> &R, PostState<F32> &S, const PostGeom &G, double *__restrict__ x, double &dotv) {
+    // 1. iterate on row t: x + P ec
+    double a = R.xin.x, b = R.xin.y;
+    if (PROLONG && G.colok && t >= G.t_rlo && t < G.t_rhi) {
+        const double pc = 0.75 * R.e[0] + 0.25 * R.e[1];
+        const double pm = 0.75 * R.e[2] + 0.25 * R.e[3];
+        const double pp = 0.75 * R.e[4] + 0.25 * R.e[5];
+        const long long k = G.kb + (long long)t * G.ld;
+        if (k != G.pin) a += 0.75 * pc + 0.25 * pm;
+        if (k + 1 != G.pin) b += 0.75 * pc + 0.25 * pp;
+    }
+    const double il0 = IMPEC_SHFL_UP(b, 1), ir0 = IMPEC_SHFL_DOWN(a, 1);
+    // 2. first colour on row t-1 (rows t-2, t-1, t of the old iterate; same-colour diagonal neighbours lagged)
+    const bool act1 = G.colok && t - 1 >= G.t_rlo && t - 1 < G.t_rhi;
+    double y, e1;
+    if (AF) {   // row t-1: B first
+        const double off = sum8((double)S.c1.aw.y, (double)R.c.aw.y, (double)S.c1.as.y, (double)S.c1.as2, (double)S.c1.av.y, (double)R.c.av.y, (double)S.c1.av2, (double)R.c.av2,
+                                S.iB2, b, S.iA1, S.ir1, S.iA2, a, S.ir2, ir0);
+        y = act1 ? (S.f1.y + off) * (double)S.c1.dinv.y : S.iB1;
+        e1 = IMPEC_SHFL_UP(y, 1);
+    } else {    // row t-1: A first
+        const double off = sum8((double)S.c1.aw.x, (double)R.c.aw.x, (double)S.c1.as.x, (double)S.c1.as.y, (double)S.c1.av.x, (double)R.c.av.x, (double)S.c1.av.y, (double)R.c.av.y,
+                                S.iA2, a, S.il1, S.iB1, S.il2, il0, S.iB2, b);
+        y = act1 ? (S.f1.x + off) * (double)S.c1.dinv.x : S.iA1;
+        e1 = IMPEC_SHFL_DOWN(y, 1);
+    }
+    // 3. second colour on row t-2: face neighbours new, diagonal neighbours (its own colour) old
+    const bool act2 = G.colok && t - 2 >= G.t_rlo && t - 2 < G.t_rhi;
+    double xA, xB;
+    if (AF) {   // row t-2: A first (new value yF2), B second
+        const double off = sum8((double)S.c2.aw.y, (double)S.c1.aw.y, (double)S.c2.as.y, (double)S.c2.as2, (double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2,
+                                S.yF3, y, S.yF2, S.e2, S.iA3, S.iA1, S.ir3, S.ir1);
+        xA = S.yF2; xB = act2 ? (S.f2.y + off) * (double)S.c2.dinv.y : S.iB2;
+    } else {    // row t-2: B first, A second
+        const double off = sum8((double)S.c2.aw.x, (double)S.c1.aw.x, (double)S.c2.as.x, (double)S.c2.as.y, (double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y,
+                                S.yF3, y, S.e2, S.yF2, S.il3, S.il1, S.iB3, S.iB1);
+        xB = S.yF2; xA = act2 ? (S.f2.x + off) * (double)S.c2.dinv.x : S.iA2;
+    }
+    if (G.own && t - 2 >= G.ia && t - 2 < G.ib) {
+        st2(x + G.kb + (long long)(t - 2) * G.ld, xA, xB);
+        dotv = fma(S.f2.x, xA, dotv); dotv = fma(S.f2.y, xB, dotv);
+    }
+    // shift the pipeline
+    S.il3 = S.il2; S.iA3 = S.iA2; S.iB3 = S.iB2; S.ir3 = S.ir2;
+    S.il2 = S.il1; S.iA2 = S.iA1; S.iB2 = S.iB1; S.ir2 = S.ir1;
+    S.il1 = il0; S.iA1 = a; S.iB1 = b; S.ir1 = ir0;
+    S.yF3 = S.yF2; S.yF2 = y; S.e2 = e1;
+    S.f2 = S.f1; S.f1 = R.f; S.c2 = S.c1; S.c1 = R.c;
+}
+
+// C0: colour of the first stage (0 forward, 1 backward); part: per-CTA partial sums of <f, x> (or nullptr)
+template <bool F32, bool PROLONG, int C0>
+__global__ void __launch_bounds__(MG_BLOCK, 3) k_mg_march_post(LevelDev L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x,
+                                                               Grid gc, const double *__restrict__ ec, double *__restrict__ part, int nrows) {
+    const Grid g = L.g;
+    const Coef<F32> A(L);
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)blockIdx.x * (MG_BLOCK / 32) + (int)(threadIdx.x >> 5);
+    PostGeom G;
+    G.ia = (int)blockIdx.y * nrows;
+    G.ib = (G.ia + nrows < g.N1) ? G.ia + nrows : g.N1;
+    G.jA = MGS_OWN * gw - 2 + 2 * lane;
+    G.colok = G.jA >= 0 && G.jA < g.N2;
+    G.own = G.colok && lane >= 1 && lane < 31;
+    G.t_rlo = g.rlo; G.t_rhi = g.rhi;
+    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
+    PostState<F32> S;
+    S.il1 = S.iA1 = S.iB1 = S.ir1 = S.il2 = S.iA2 = S.iB2 = S.ir2 = S.il3 = S.iA3 = S.iB3 = S.ir3 = 0.;
+    S.yF2 = S.yF3 = S.e2 = 0.; S.f1.x = S.f1.y = S.f2.x = S.f2.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
+    double dotv = 0.;
+    const int t0 = G.ia - 2, t1 = G.ib + 1;    // rows marched: [t0, t1], an even count; t0 is even
+    PostRow<F32, PROLONG> q[MG_PF];
+#pragma unroll
+    for (int u = 0; u < MG_PF; u++) q[u] = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, t0 + u);
+    for (int t = t0; t <= t1; t += 2) {
+        { const PostRow<F32, PROLONG> R = q[0]; q[0] = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 2 <= t1) ? t + 2 : t1);
+          post_step<F32, PROLONG, C0 == 0>(t, R, S, G, x, dotv); }
+        { const PostRow<F32, PROLONG> R = q[1]; q[1] = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 3 <= t1) ? t + 3 : t1);
+          post_step<F32, PROLONG, C0 != 0>(t + 1, R, S, G, x, dotv); }
+    }
+    if (part) {
+        dotv = block_reduce<RED_SUM>(dotv);
+        if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
+    }
+}
