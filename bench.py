@@ -233,7 +233,8 @@ def main():
     #   k_mg_fused<POST>  : R x,f (16) + FP32 AW,AS,AV,DINV (16) + coarse e (2) + W x (8)   = 42 B/cell
     #   k_mg_fused<PRE>   : R f (8) + FP32 AW,AS,AV,DINV (16) + W x (8) + coarse f (2)     = 34 B/cell
     #   k_mg_fused<PLAIN> : R x,f (16) + FP32 coefficients (16) + W x (8)                   = 40 B/cell
-    #   k_pcg_matvec      : R z,d,AW,AS,AV (40) + W d,s (16)                        = 56 B/cell
+    #   k_pcg_matvec_march: R z,d,AW,AS,AV (40) + W d,s (16)                        = 56 B/cell
+    #   k_update_xr 48, k_muscl_x / k_muscl_y: R c,vel + W c = 24 B/cell
     #   one multigrid cycle, all levels: SURVEY 8d's model figure (unfused, FP64 coefficients) = 208 B/cell
     cells = float(N) * N / world                   # cells per GPU: the kernels are timed on this rank's slab
     kb = {"fused_post": 42.0, "fused_pre": 34.0, "fused_plain": 40.0, "pcg_matvec": 56.0, "matvec_dot": 40.0, "update_xr": 48.0, "update_d": 24.0,
@@ -243,13 +244,13 @@ def main():
     dom = "fused_post"
     traffic = None                                 # measured DRAM bytes of the dominant kernel from the committed ncu capture (same grid, 1 GPU)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1n_traffic.json")))
         if tr.get("grid") == [N, N] and world == 1:
             traffic = tr.get(dom)
     except Exception:
         pass
     vc_bytes = 208.0 * float(N) * N / world
-    roofline = {"bound": "hbm", "kernel": "k_mg_fused<FUSED_POST> (prolong + correct + red-black post-smooth + <r,z>, fine level)",
+    roofline = {"bound": "hbm", "kernel": "k_mg_march_post<PROLONG> (prolong + correct + red-black post-smooth + <r,z>, fine level; register march)",
                 "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_kernel[dom]["algorithmic_bytes"],
                 "vcycle": {"ms": prof["vcycle"], "algorithmic_bytes": vc_bytes, "achieved": vc_bytes / (prof["vcycle"] * 1e-3) / 1e9,

@@ -5,6 +5,7 @@
 #include "kernels_transport.inl"
 #include "kernels_pressure.inl"
 #include "kernels_fused.inl"
+#include "kernels_march.inl"
 #include "kernels_staged.inl"
 #include "kernels_small.inl"
 #include "../../include/impec2d_b200.h"
@@ -32,6 +33,7 @@ struct Level {
     long long pin = -1, sig_idx = -1;
     bool dist = false;           // rows of this level are slab-distributed over the ranks
     int th = 64;                 // tile height of the fused kernels on this level (64 / 32 / 16)
+    int march_rows = 0;          // > 0: the level runs the marching kernels (kernels_march.inl) with chunks of this many rows
     // first replicated level only: this rank's slab view of it and slab-sized staging for the all-gathers
     Grid gl; double *AWl = nullptr, *ASl = nullptr, *AVl = nullptr, *fl = nullptr;
 };
@@ -65,11 +67,13 @@ struct impec_ctx {
                                                     // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
     bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
+    bool march = true;                              // big levels: PRE / POST / PLAIN as register marches (kernels_march.inl); 0 = shared-memory tiles
     bool fused_mid = true;                          // W-cycle revisit: sweep + residual + restriction in one tile kernel (FUSED_MID)
     bool matvec_march = true;                       // PCG direction update + mat-vec as a register march (k_pcg_matvec_march); 0 = shared-memory tiles
     bool sweep_shared = true;                       // MUSCL sweeps evaluate each reconstruction once (k_muscl_x / k_muscl_y); 0 = k_sweep
     bool use_small = true;                          // levels of <= SM_MAXCELLS cells: whole V-cycle in one single-CTA launch (kernels_small.inl)
     long long launches = 0;
+    long long march_launches = 0;                   // launches of the marching multigrid kernels (diagnostic, IMPEC_VERBOSE)
     std::string err;
     std::vector<void *> allocs;
     // multi-GPU: slab decomposition along i
@@ -444,6 +448,7 @@ extern "C" const char *impec_last_error(const impec_ctx *ctx) { return ctx ? ctx
 
 extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
     if (!ctx) return;
+    if (getenv("IMPEC_VERBOSE")) fprintf(stderr, "impec2d_b200: %lld kernel launches, %lld of them marching multigrid kernels\n", ctx->launches, ctx->march_launches);
     cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
     for (void *p : {(void *)ctx->well_i, (void *)ctx->well_j, (void *)ctx->well_q, (void *)ctx->well_md}) if (p) cudaFree(p);
@@ -543,6 +548,17 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
             const char *e32 = getenv("IMPEC_TH32_BELOW"), *e16 = getenv("IMPEC_TH16_BELOW");
             const double c32 = e32 ? atof(e32) : 6.0e6, c16 = e16 ? atof(e16) : 6.0e6, cells = (double)L.g.N1 * L.g.N2;
             L.th = cells < c16 ? 16 : (cells < c32 ? 32 : 64);
+            // big levels: register-march kernels.  Chunk height: as tall as possible (3 + 3 rows of every chunk are
+            // redundant) while the grid still fills the 148 SMs (3 CTAs each) about three times over.
+            const char *em = getenv("IMPEC_MARCH_MIN_CELLS");
+            const double cm = em ? atof(em) : 8.0e6;
+            L.march_rows = 0;
+            if (cells >= cm && L.g.N1 % 2 == 0 && L.g.N2 % 2 == 0 && l < nl - 1) {
+                const int ctas_x = ((L.g.N2 + MGP_OWN - 1) / MGP_OWN + MG_BLOCK / 32 - 1) / (MG_BLOCK / 32);
+                int ch = 256;
+                while (ch > 32 && (long long)ctas_x * ((L.g.N1 + ch - 1) / ch) < 1200) ch /= 2;
+                L.march_rows = ch;
+            }
         }
         const size_t nn = grid_elems(L.g);
         TRY(dev_alloc(ctx, &L.AW, nn)); TRY(dev_alloc(ctx, &L.AS, nn)); TRY(dev_alloc(ctx, &L.AV, nn)); TRY(dev_alloc(ctx, &L.DINV, nn));
@@ -597,6 +613,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
     if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "matvec_march") { ctx->matvec_march = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_shared") { ctx->sweep_shared = value != 0.0; return IMPEC_OK; }
@@ -828,10 +845,24 @@ template <int MODE> static dim3 fused_grid(const Grid &g, int th = FT_H) {
     const int ti = th - 2 * (int)FusedGeom<MODE>::HI;
     return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + ti - 1) / ti));
 }
+static bool use_march(const impec_ctx *ctx, const Level &L) { return ctx->march && L.march_rows > 0 && !use_staged(ctx); }
+static dim3 march_grid(const Level &L, int own) {
+    const int warps = (L.g.N2 + own - 1) / own;
+    return dim3((unsigned)((warps + MG_BLOCK / 32 - 1) / (MG_BLOCK / 32)), (unsigned)((L.g.N1 + L.march_rows - 1) / L.march_rows));
+}
 // PLAIN and POST read the iterate with a halo that belongs to neighbouring tiles, so they cannot run in place:
 // they read L.x, write L.t and the two pointers are swapped (the level's current iterate is always L.x).
 static int fused_plain(Cycle &C, int l, const double *f, bool forward) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
+    if (use_march(ctx, L)) {
+        ctx->march_launches++;
+        const dim3 gm = march_grid(L, MGS_OWN);
+#define MPLAIN(F32, C0) LAUNCH_COOP(ctx, (k_mg_march_post<F32, false, C0>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, L.g, (const double *)nullptr, (double *)nullptr, L.march_rows)
+        if (ctx->links_f32) { if (forward) MPLAIN(true, 0); else MPLAIN(true, 1); } else { if (forward) MPLAIN(false, 0); else MPLAIN(false, 1); }
+#undef MPLAIN
+        std::swap(L.x, L.t);
+        return IMPEC_OK;
+    }
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PLAIN>, staged_grid<FUSED_PLAIN>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
                      (const double *)nullptr, (double *)nullptr, (double *)nullptr);
     else LAUNCH_FUSED(ctx, FUSED_PLAIN, L.th, fused_grid<FUSED_PLAIN>(L.g, L.th), C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
@@ -848,6 +879,13 @@ static const double *coarse_x_view(const impec_ctx *ctx, int l) {
 static int fused_pre(Cycle &C, int l, const double *f) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
     const bool tr = at_transition(ctx, l);
+    if (use_march(ctx, L)) {
+        ctx->march_launches++;
+        const dim3 gm = march_grid(L, MGP_OWN);
+        if (ctx->links_f32) LAUNCH_COOP(ctx, (k_mg_march_pre<true, MG_PF_PRE>), gm, dim3(MG_BLOCK), C.D[l], f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows);
+        else LAUNCH_COOP(ctx, (k_mg_march_pre<false, MG_PF_PRE>), gm, dim3(MG_BLOCK), C.D[l], f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows);
+        return IMPEC_OK;
+    }
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PRE>, staged_grid<FUSED_PRE>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
                      (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
     else LAUNCH_FUSED(ctx, FUSED_PRE, L.th, fused_grid<FUSED_PRE>(L.g, L.th), C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
@@ -863,6 +901,15 @@ static int gather_coarse_rhs(impec_ctx *ctx, int l) {
 }
 static int fused_post(Cycle &C, int l, const double *f, double *part, long long *nparts) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
+    if (use_march(ctx, L)) {
+        ctx->march_launches++;
+        const dim3 gm = march_grid(L, MGS_OWN);
+        if (ctx->links_f32) LAUNCH_COOP(ctx, (k_mg_march_post<true, true, 1>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, at_transition(ctx, l) ? Lc.gl : Lc.g, coarse_x_view(ctx, l), part, L.march_rows);
+        else LAUNCH_COOP(ctx, (k_mg_march_post<false, true, 1>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, at_transition(ctx, l) ? Lc.gl : Lc.g, coarse_x_view(ctx, l), part, L.march_rows);
+        std::swap(L.x, L.t);
+        if (nparts) *nparts = (long long)gm.x * gm.y;
+        return IMPEC_OK;
+    }
     const dim3 gr = use_staged(ctx) ? staged_grid<FUSED_POST>(L.g) : fused_grid<FUSED_POST>(L.g, L.th);
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_POST>, gr, kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
                      coarse_x_view(ctx, l), (double *)nullptr, part);

@@ -10,7 +10,7 @@
 // Halo: values that depend on a column outside the warp are wrong in the outermost lanes; the wrong region grows by one
 // column per dependent stage, so PRE discards two lanes per side (56 of 64 columns are stored, the same 4-column halo as
 // the tiles) and POST/PLAIN one lane per side (60 of 64).  Rows: a chunk of `nrows` rows starts 3 (PRE) / 2 (POST) rows
-// early.  Each link value and each vector element is loaded once per warp that needs it, the loads of the next MG_PF
+// early.  Each link value and each vector element is loaded once per warp that needs it, the loads of the next 2-4
 // rows are in flight while a row is processed, and the row parity (which cell of the pair has which colour) is a
 // template parameter of the step, so a step has no colour branches.
 //
@@ -18,7 +18,7 @@
 // 8-13 warps per issue at 50 % occupancy) and 147 instructions per cell; the same reorganisation took the PCG mat-vec
 // from 57 % to 95 % of the measured copy bandwidth.
 #define MG_BLOCK 128
-#define MG_PF 2
+#define MG_PF_PRE 4              // PRE: rows in flight per thread (even: the row parity of a step is static); POST / PLAIN: 2
 #define MGP_OWN 56                // columns a warp stores in PRE (lanes 2..29)
 #define MGS_OWN 60                // columns a warp stores in POST / PLAIN (lanes 1..30)
 
@@ -148,7 +148,7 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
     S.xF1 = xF; S.e01 = e0; S.f1 = R.f; S.c1 = R.c;
 }
 
-template <bool F32>
+template <bool F32, int PF>
 __global__ void __launch_bounds__(MG_BLOCK, 3) k_mg_march_pre(LevelDev L, const double *__restrict__ f, double *__restrict__ x, Grid gc, double *__restrict__ fc, int nrows) {
     const Grid g = L.g;
     const Coef<F32> A(L);
@@ -173,15 +173,19 @@ __global__ void __launch_bounds__(MG_BLOCK, 3) k_mg_march_pre(LevelDev L, const 
     PreState<F32> S;
     S.xF1 = S.e01 = 0.; S.f1.x = S.f1.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
     S.xl2 = S.xA2 = S.xB2 = S.xr2 = S.xl3 = S.xA3 = S.xB3 = S.xr3 = 0.; S.h0 = S.h1 = S.h2 = S.h3 = 0.;
-    const int t0 = ia - 3, t1 = ib + 2;        // rows marched: [t0, t1], an even count; t0 is odd
-    PreRow<F32> q[MG_PF];
+    const int t0 = ia - 3, t1 = ib + 2;        // rows marched: [t0, t1]; t0 is odd
+    PreRow<F32> q[PF];
 #pragma unroll
-    for (int u = 0; u < MG_PF; u++) q[u] = pre_load<F32>(A, f, G.kb + (long long)(t0 + u) * G.ld, G.colok);
-    for (int t = t0; t <= t1; t += 2) {
-        { const PreRow<F32> R = q[0]; const int nx = (t + 2 <= t1) ? t + 2 : t1; q[0] = pre_load<F32>(A, f, G.kb + (long long)nx * G.ld, G.colok);
-          pre_step<F32, false>(t, R, S, G, x, fc); }
-        { const PreRow<F32> R = q[1]; const int nx = (t + 3 <= t1) ? t + 3 : t1; q[1] = pre_load<F32>(A, f, G.kb + (long long)nx * G.ld, G.colok);
-          pre_step<F32, true>(t + 1, R, S, G, x, fc); }
+    for (int u = 0; u < PF; u++) q[u] = pre_load<F32>(A, f, G.kb + (long long)((t0 + u <= t1) ? t0 + u : t1) * G.ld, G.colok);
+    for (int t = t0; t <= t1; t += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            if (t + u > t1) continue;
+            const PreRow<F32> R = q[u];
+            q[u] = pre_load<F32>(A, f, G.kb + (long long)((t + u + PF <= t1) ? t + u + PF : t1) * G.ld, G.colok);
+            if (u & 1) pre_step<F32, true>(t + u, R, S, G, x, fc);
+            else pre_step<F32, false>(t + u, R, S, G, x, fc);
+        }
     }
 }
 
@@ -294,13 +298,11 @@ __global__ void __launch_bounds__(MG_BLOCK, 3) k_mg_march_post(LevelDev L, const
     S.yF2 = S.yF3 = S.e2 = 0.; S.f1.x = S.f1.y = S.f2.x = S.f2.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
     double dotv = 0.;
     const int t0 = G.ia - 2, t1 = G.ib + 1;    // rows marched: [t0, t1], an even count; t0 is even
-    PostRow<F32, PROLONG> q[MG_PF];
-#pragma unroll
-    for (int u = 0; u < MG_PF; u++) q[u] = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, t0 + u);
+    PostRow<F32, PROLONG> q0 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, t0), q1 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, t0 + 1);
     for (int t = t0; t <= t1; t += 2) {
-        { const PostRow<F32, PROLONG> R = q[0]; q[0] = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 2 <= t1) ? t + 2 : t1);
+        { const PostRow<F32, PROLONG> R = q0; q0 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 2 <= t1) ? t + 2 : t1);
           post_step<F32, PROLONG, C0 == 0>(t, R, S, G, x, dotv); }
-        { const PostRow<F32, PROLONG> R = q[1]; q[1] = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 3 <= t1) ? t + 3 : t1);
+        { const PostRow<F32, PROLONG> R = q1; q1 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 3 <= t1) ? t + 3 : t1);
           post_step<F32, PROLONG, C0 != 0>(t + 1, R, S, G, x, dotv); }
     }
     if (part) {

@@ -256,6 +256,31 @@ def check_matvec_variants(emulated, N1=80, N2=272, stype=O.DIAGONAL, eps=1e-11):
     assert rel_l2(interior(Po, res[0][1]), interior(Po, res[1][1])) <= 1e-12
 
 
+def check_march_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
+    """The register-march multigrid kernels (kernels_march.inl) against the shared-memory tile kernels: the same
+    arithmetic per cell in the same order, so one cycle must agree BIT FOR BIT -- with FP64 and FP32 coefficients, with
+    the march forced onto every level that can run it (IMPEC_MARCH_MIN_CELLS = 0; chunks of 32 rows, several warps
+    and CTAs per row, a partial last warp)."""
+    base, Po, c, q = production_case(N1, N2, stype=stype)
+    Pi = I.default_params(emulated=emulated, **base)
+    r = np.random.default_rng(4).standard_normal(N1 * N2)
+    os.environ["IMPEC_MARCH_MIN_CELLS"] = "0"
+    try:
+        for f32 in (0, 1):
+            out = []
+            for march in (0, 1):
+                ctx = I.Context(Pi, emulated=emulated)
+                ctx.set_option("mg_march", march); ctx.set_option("mg_links_fp32", f32)
+                ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
+                z1 = ctx.vcycle(r); z2 = ctx.vcycle(r)
+                assert np.array_equal(z1, z2), "cycle is not repeatable (race?)"
+                out.append(z1)
+                ctx.close()
+            assert np.array_equal(out[0], out[1]), "march vs tiles (fp32 links %d): max diff %g of %g" % (f32, np.abs(out[0] - out[1]).max(), np.abs(out[0]).max())
+    finally:
+        os.environ.pop("IMPEC_MARCH_MIN_CELLS", None)
+
+
 def check_small_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
     """The single-CTA bottom-of-hierarchy kernel (kernels_small.inl, levels of <= 4096 cells) against the tile kernels
     on the same levels: same arithmetic per cell, so one cycle agrees to rounding (<= 1e-13 relative), with FP64 and

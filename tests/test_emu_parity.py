@@ -45,4 +45,5 @@ def test_dispersion_diagonal_rect(): pc.check_dispersion(True, 32, 16, stype=O.D
 def test_staged_vs_fused_cycle(): pc.check_staged_vs_fused(True, 256, 384)
 def test_matvec_march_vs_tiles(): pc.check_matvec_variants(True)
 def test_matvec_march_odd_columns(): pc.check_matvec_variants(True, 20, 31, eps=1e-9)
+def test_march_vs_tile_kernels(): pc.check_march_vs_tiles(True)
 def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(True, 256, 384)

@@ -9,11 +9,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(world, N1, N2, stype, diffusion, steps, port):
+def run(world, N1, N2, stype, diffusion, steps, port, extra_env=None):
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "impec2d_b200", "csrc"), "emu"])
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multirank_worker.py"), str(N1), str(N2), str(stype), str(diffusion), str(steps)]
     env = dict(os.environ, OMP_NUM_THREADS="1", IMPEC_DIST_MIN_CELLS="0")
+    env.update(extra_env or {})
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(" ok: ") == world, out.stdout
@@ -22,3 +23,6 @@ def run(world, N1, N2, stype, diffusion, steps, port):
 def test_two_ranks_parallel_cfg(): run(2, 64, 64, 0, 0, 2, 29611)
 def test_two_ranks_rect_diagonal_with_dispersion(): run(2, 64, 32, 1, 1, 1, 29612)
 def test_four_ranks(): run(4, 128, 64, 1, 0, 1, 29613)
+# the register-march multigrid kernels (big levels only by default) forced onto the slab levels: chunk edges at slab
+# boundaries, the 2 halo rows PRE stores for its neighbours, coarse slab views at the transition level
+def test_two_ranks_marching_kernels(): run(2, 128, 128, 0, 0, 1, 29614, {"IMPEC_MARCH_MIN_CELLS": "0"})
