@@ -67,6 +67,7 @@ struct impec_ctx {
                                                     // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
     bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
+    int march_variant = 1;                          // bit 0: k_mg_march_pre with 2 rows in flight and 4 CTAs/SM (default) instead of 4 rows and 3 CTAs/SM
     bool march = true;                              // big levels: PRE / POST / PLAIN as register marches (kernels_march.inl); 0 = shared-memory tiles
     bool fused_mid = true;                          // W-cycle revisit: sweep + residual + restriction in one tile kernel (FUSED_MID)
     bool matvec_march = true;                       // PCG direction update + mat-vec as a register march (k_pcg_matvec_march); 0 = shared-memory tiles
@@ -481,6 +482,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     }
     if (P->stype == IMPEC_HORIZONTAL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "source_type horizontal is outside the accelerated path");
     if (P->diffusion && P->alpha_l != P->alpha_t) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t gives a non-symmetric CN operator; not supported");
+    { const char *e = getenv("IMPEC_MARCH_VARIANT"); if (e) ctx->march_variant = atoi(e); }
     CUDA_TRY(ctx, cudaSetDevice(device));
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
@@ -613,6 +615,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
     if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "matvec_march") { ctx->matvec_march = value != 0.0; return IMPEC_OK; }
@@ -857,7 +860,7 @@ static int fused_plain(Cycle &C, int l, const double *f, bool forward) {
     if (use_march(ctx, L)) {
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGS_OWN);
-#define MPLAIN(F32, C0) LAUNCH_COOP(ctx, (k_mg_march_post<F32, false, C0>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, L.g, (const double *)nullptr, (double *)nullptr, L.march_rows)
+#define MPLAIN(F32, C0) LAUNCH_COOP(ctx, (k_mg_march_post<F32, false, C0, 3>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, L.g, (const double *)nullptr, (double *)nullptr, L.march_rows)
         if (ctx->links_f32) { if (forward) MPLAIN(true, 0); else MPLAIN(true, 1); } else { if (forward) MPLAIN(false, 0); else MPLAIN(false, 1); }
 #undef MPLAIN
         std::swap(L.x, L.t);
@@ -882,8 +885,11 @@ static int fused_pre(Cycle &C, int l, const double *f) {
     if (use_march(ctx, L)) {
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGP_OWN);
-        if (ctx->links_f32) LAUNCH_COOP(ctx, (k_mg_march_pre<true, MG_PF_PRE>), gm, dim3(MG_BLOCK), C.D[l], f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows);
-        else LAUNCH_COOP(ctx, (k_mg_march_pre<false, MG_PF_PRE>), gm, dim3(MG_BLOCK), C.D[l], f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows);
+#define MPRE(F32, PF, MB) LAUNCH_COOP(ctx, (k_mg_march_pre<F32, PF, MB>), gm, dim3(MG_BLOCK), C.D[l], f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows)
+        if (!ctx->links_f32) MPRE(false, 4, 3);
+        else if (ctx->march_variant & 1) MPRE(true, 2, 4);      // 2 rows in flight, 122 registers, 4 CTAs per SM: 2.10 ms at 16384^2
+        else MPRE(true, 4, 3);                                  // 4 rows in flight, 168 registers, 3 CTAs per SM: 2.31 ms
+#undef MPRE
         return IMPEC_OK;
     }
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PRE>, staged_grid<FUSED_PRE>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
@@ -904,8 +910,11 @@ static int fused_post(Cycle &C, int l, const double *f, double *part, long long 
     if (use_march(ctx, L)) {
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGS_OWN);
-        if (ctx->links_f32) LAUNCH_COOP(ctx, (k_mg_march_post<true, true, 1>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, at_transition(ctx, l) ? Lc.gl : Lc.g, coarse_x_view(ctx, l), part, L.march_rows);
-        else LAUNCH_COOP(ctx, (k_mg_march_post<false, true, 1>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, at_transition(ctx, l) ? Lc.gl : Lc.g, coarse_x_view(ctx, l), part, L.march_rows);
+#define MPOST(F32, MB) LAUNCH_COOP(ctx, (k_mg_march_post<F32, true, 1, MB>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, at_transition(ctx, l) ? Lc.gl : Lc.g, coarse_x_view(ctx, l), part, L.march_rows)
+        // 168 registers, 3 CTAs per SM.  (Forcing 4 CTAs per SM makes ptxas spill ~300 B per thread and DOUBLES the time:
+        // 2.13 -> 4.12 ms at 16384^2.)
+        if (!ctx->links_f32) MPOST(false, 3); else MPOST(true, 3);
+#undef MPOST
         std::swap(L.x, L.t);
         if (nparts) *nparts = (long long)gm.x * gm.y;
         return IMPEC_OK;

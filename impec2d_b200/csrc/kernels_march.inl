@@ -148,8 +148,8 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
     S.xF1 = xF; S.e01 = e0; S.f1 = R.f; S.c1 = R.c;
 }
 
-template <bool F32, int PF>
-__global__ void __launch_bounds__(MG_BLOCK, 3) k_mg_march_pre(LevelDev L, const double *__restrict__ f, double *__restrict__ x, Grid gc, double *__restrict__ fc, int nrows) {
+template <bool F32, int PF, int MINB>
+__global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_pre(LevelDev L, const double *__restrict__ f, double *__restrict__ x, Grid gc, double *__restrict__ fc, int nrows) {
     const Grid g = L.g;
     const Coef<F32> A(L);
     const int lane = threadIdx.x & 31;
@@ -278,8 +278,8 @@ IMPEC_D void post_step(const int t, const PostRow<F32, PROLONG> &R, PostState<F3
 }
 
 // C0: colour of the first stage (0 forward, 1 backward); part: per-CTA partial sums of <f, x> (or nullptr)
-template <bool F32, bool PROLONG, int C0>
-__global__ void __launch_bounds__(MG_BLOCK, 3) k_mg_march_post(LevelDev L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x,
+template <bool F32, bool PROLONG, int C0, int MINB>
+__global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_post(LevelDev L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x,
                                                                Grid gc, const double *__restrict__ ec, double *__restrict__ part, int nrows) {
     const Grid g = L.g;
     const Coef<F32> A(L);
