@@ -244,7 +244,7 @@ def main():
     dom = "fused_post"
     traffic = None                                 # measured DRAM bytes of the dominant kernel from the committed ncu capture (same grid, 1 GPU)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1n_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1q_traffic.json")))
         if tr.get("grid") == [N, N] and world == 1:
             traffic = tr.get(dom)
     except Exception:
