@@ -64,7 +64,7 @@ EXPORTS = [
     "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_reset_state", "impec_set_option",
     "impec_profile_kernel", "impec_init_source", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
     "impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows", "impec_init_source_rows", "impec_synth_state_rows",
-    "impec_comm_backend",
+    "impec_comm_backend", "impec_project_dims", "impec_project_to_diagonal", "impec_checkpoint_save", "impec_checkpoint_load",
 ]
 
 
@@ -109,6 +109,10 @@ def load(emulated=False):
     L.impec_diffusion_split.argtypes = [vp, d, C.POINTER(SolveInfo)]
     L.impec_impes_step.argtypes = [vp, d, d, dptr, C.POINTER(SolveInfo)]
     L.impec_diagnostics.argtypes = [vp, C.POINTER(Diag)]
+    L.impec_project_dims.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    L.impec_project_to_diagonal.argtypes = [vp, i, vp]
+    L.impec_checkpoint_save.argtypes = [vp, C.c_char_p, d, C.c_longlong]
+    L.impec_checkpoint_load.argtypes = [vp, C.c_char_p, dptr, C.POINTER(C.c_longlong)]
     L.impec_vcycle.argtypes = [vp, vp, vp]
     L.impec_mg_levels.argtypes = [vp]
     L.impec_kernel_launches.argtypes = [vp]; L.impec_kernel_launches.restype = C.c_longlong

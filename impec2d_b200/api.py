@@ -119,6 +119,21 @@ class Context:
         self._chk(self.L.impec_diagnostics(self._h, C.byref(d)))
         return d
 
+    def project_to_diagonal(self, field=0):
+        """Impec2DSolver::Project: c (field 0) or p (field 1) of a parallel run on the diagonal grid (dN1 x dN2 array)."""
+        n1 = C.c_int(); n2 = C.c_int()
+        self._chk(self.L.impec_project_dims(self._h, C.byref(n1), C.byref(n2)))
+        out = np.empty((n1.value, n2.value))
+        self._chk(self.L.impec_project_to_diagonal(self._h, field, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def checkpoint_save(self, path, t=0.0, step=0): self._chk(self.L.impec_checkpoint_save(self._h, str(path).encode(), t, step))
+
+    def checkpoint_load(self, path):
+        t = C.c_double(); step = C.c_longlong()
+        self._chk(self.L.impec_checkpoint_load(self._h, str(path).encode(), C.byref(t), C.byref(step)))
+        return t.value, step.value
+
     def build_operator(self): self._chk(self.L.impec_build_operator(self._h))
 
     def vcycle(self, r=None):

@@ -1394,6 +1394,89 @@ extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------------ 8f-3 projection
+// Impec2DSolver::Project (src/Impec2DSolver.cpp:690-716): the concentration (field 0) or the pressure (field 1) of a PARALLEL
+// run interpolated onto the diagonal grid of round(N/sqrt 2) cells; out_host receives dN1 x dN2 doubles (row-major, no ghosts).
+extern "C" int impec_project_dims(const impec_ctx *ctx, int *dN1, int *dN2) {
+    if (dN1) *dN1 = (int)round(ctx->P.N1 / sqrt(2.)); if (dN2) *dN2 = (int)round(ctx->P.N2 / sqrt(2.));
+    return IMPEC_OK;
+}
+extern "C" int impec_project_to_diagonal(impec_ctx *ctx, int field, double *out_host) {
+    if (ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "projection needs the whole field: single-GPU contexts only");
+    if (field != 0 && field != 1) return fail(ctx, IMPEC_ERR_ARG, "field must be 0 (c) or 1 (p)");
+    if (!out_host) return fail(ctx, IMPEC_ERR_ARG, "null output");
+    const impec_params &P = ctx->P; const Grid &g = ctx->g;
+    ProjectArgs A;
+    impec_project_dims(ctx, &A.dN1, &A.dN2);
+    const double angle = -M_PI / 4.;
+    A.x_lb = P.x_lb; A.y_lb = P.y_lb; A.x_ub = P.x_ub; A.y_ub = P.y_ub; A.ca = cos(angle); A.sa = sin(angle);
+    A.p_dx = (P.x_ub - P.x_lb) / P.N1; A.p_dy = (P.y_ub - P.y_lb) / P.N2;
+    A.d_dx = (P.x_ub - P.x_lb) / (sqrt(2.) * A.dN1); A.d_dy = (P.y_ub - P.y_lb) / (sqrt(2.) * A.dN2);
+    A.ng = P.g;
+    const size_t n = (size_t)A.dN1 * A.dN2;
+    if (n > grid_elems(g)) return fail(ctx, IMPEC_ERR_ARG, "diagonal grid larger than the scratch field");
+    double *dst = ctx->tb;                                   // transport scratch (free between steps)
+    LAUNCH(ctx, k_project_parallel, grid2d(A.dN2, A.dN1), kBlock, g, (const double *)(field == 0 ? ctx->c : ctx->p), A, dst);
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_host, dst, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ 8f-2 binary checkpoint
+// The reference restarts from a text file of c only (init_file, src/Impec2DSolver.cpp:194-220), which loses the pressure, the
+// produced mass and the sweep parity and is unusable at 16384^2 (268 M text lines).  A checkpoint here is the exact device state
+// of this rank: header + the padded c, p, u, v arrays (ghost / halo rows included) + produced mass + sweep parity, so a
+// restarted run continues BIT FOR BIT.  Multi-GPU: one file per rank (the caller chooses the names).
+struct CkptHeader { char magic[8]; int version, N1, N2, g, rank, nranks, ld, rows; long long step; double t, outflux; int prev_first_sweep, pad; };
+extern "C" int impec_checkpoint_save(impec_ctx *ctx, const char *path, double t, long long step) {
+    if (!path) return fail(ctx, IMPEC_ERR_ARG, "null path");
+    const Grid &g = ctx->g;
+    CkptHeader H; memset(&H, 0, sizeof(H));
+    memcpy(H.magic, "IMPECCK1", 8); H.version = 1; H.N1 = ctx->P.N1; H.N2 = ctx->P.N2; H.g = ctx->P.g; H.rank = ctx->rank; H.nranks = ctx->nranks;
+    H.ld = g.ld; H.rows = g.rows; H.step = step; H.t = t; H.prev_first_sweep = ctx->prev_first_sweep;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&H.outflux, ctx->scal + S_OUTFLUX, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(ctx, IMPEC_ERR_ARG, "cannot open %s for writing", path);
+    bool ok = fwrite(&H, sizeof(H), 1, f) == 1;
+    const size_t n = grid_elems(g);
+    std::vector<double> buf(n);
+    for (const double *fld : {(const double *)ctx->c, (const double *)ctx->p, (const double *)ctx->u, (const double *)ctx->v}) {
+        if (cudaMemcpyAsync(buf.data(), fld, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ok = false; break; }
+        ok = ok && fwrite(buf.data(), sizeof(double), n, f) == n;
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? IMPEC_OK : fail(ctx, IMPEC_ERR_CUDA, "writing checkpoint %s failed", path);
+}
+extern "C" int impec_checkpoint_load(impec_ctx *ctx, const char *path, double *t, long long *step) {
+    if (!path) return fail(ctx, IMPEC_ERR_ARG, "null path");
+    const Grid &g = ctx->g;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(ctx, IMPEC_ERR_ARG, "cannot open %s", path);
+    CkptHeader H;
+    if (fread(&H, sizeof(H), 1, f) != 1 || memcmp(H.magic, "IMPECCK1", 8) != 0 || H.version != 1) { fclose(f); return fail(ctx, IMPEC_ERR_ARG, "%s is not an impec2d_b200 checkpoint", path); }
+    if (H.N1 != ctx->P.N1 || H.N2 != ctx->P.N2 || H.g != ctx->P.g || H.rank != ctx->rank || H.nranks != ctx->nranks || H.ld != g.ld || H.rows != g.rows) {
+        fclose(f);
+        return fail(ctx, IMPEC_ERR_ARG, "checkpoint %s is for a %d x %d grid on rank %d of %d; this context is %d x %d on rank %d of %d", path, H.N1, H.N2, H.rank, H.nranks,
+                    ctx->P.N1, ctx->P.N2, ctx->rank, ctx->nranks);
+    }
+    const size_t n = grid_elems(g);
+    std::vector<double> buf(n);
+    bool ok = true;
+    for (double *fld : {ctx->c, ctx->p, ctx->u, ctx->v}) {
+        ok = ok && fread(buf.data(), sizeof(double), n, f) == n;
+        if (!ok) break;
+        if (cudaMemcpyAsync(fld, buf.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ok = false; break; }
+    }
+    fclose(f);
+    if (!ok) return fail(ctx, IMPEC_ERR_ARG, "checkpoint %s is truncated or unreadable", path);
+    LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_OUTFLUX, H.outflux);
+    ctx->prev_first_sweep = H.prev_first_sweep;
+    ctx->mob_valid = ctx->op_valid = false;
+    if (t) *t = H.t; if (step) *step = H.step;
+    return IMPEC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ a14 transport step
 extern "C" int impec_transport_step(impec_ctx *ctx, double dt) {
     TRY(impec_source_split(ctx, 0.5 * dt));

@@ -309,3 +309,29 @@ __global__ void __launch_bounds__(1024) k_reduce_final(const double *__restrict_
     acc = block_reduce<OP>(acc);
     if (threadIdx.x == 0) out[blockIdx.x] = acc;
 }
+
+// ---------------------------------------------------------------- parallel -> diagonal projection
+// ParallelProjector::FillDiagonal / GetFromParallel (src/ParallelProjector.cpp:91-199): one thread per cell of the diagonal
+// grid; rotate its centre by -pi/4 into the parallel frame, mirror y, interpolate the ghosted parallel field bilinearly
+// between the cells floor(x/L N) and +1 exactly as upstream (same operation order: bit-identical to the oracle).
+struct ProjectArgs { double x_lb, y_lb, x_ub, y_ub, ca, sa, p_dx, p_dy, d_dx, d_dy; int dN1, dN2, ng; };
+__global__ void __launch_bounds__(256) k_project_parallel(Grid g, const double *__restrict__ a, ProjectArgs A, double *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= A.dN1 || j >= A.dN2) return;
+    const double xd = A.x_lb + (i + 0.5) * A.d_dx, yd = A.y_lb + (j + 0.5) * A.d_dy;
+    const double x = A.ca * xd - A.sa * yd;
+    const double y = fabs(A.sa * xd + A.ca * yd);
+    int x00 = (int)floor(x / (A.x_ub - A.x_lb) * g.N1), y00 = (int)floor(y / (A.y_ub - A.y_lb) * g.N2);
+    // (upstream only warns about points outside the parallel domain; keep the reads inside the ghosted array)
+    x00 = x00 < -A.ng ? -A.ng : (x00 > g.N1 + A.ng - 2 ? g.N1 + A.ng - 2 : x00);
+    y00 = y00 < -A.ng ? -A.ng : (y00 > g.N2 + A.ng - 2 ? g.N2 + A.ng - 2 : y00);
+    const double x_00 = A.x_lb + (x00 + 0.5) * A.p_dx, x_11 = A.x_lb + (x00 + 1 + 0.5) * A.p_dx;
+    const double y_00 = A.y_lb + (y00 + 0.5) * A.p_dy, y_11 = A.y_lb + (y00 + 1 + 0.5) * A.p_dy;
+    const size_t k = gidx(g, x00, y00);
+    out[(size_t)i * A.dN2 + j] =
+        1. / ((x_11 - x_00) * (y_11 - y_00)) * (x_11 - x) * (y_11 - y) * a[k] +
+        1. / ((x_11 - x_00) * (y_11 - y_00)) * (x - x_00) * (y_11 - y) * a[k + g.ld] +
+        1. / ((x_11 - x_00) * (y_11 - y_00)) * (x_11 - x) * (y - y_00) * a[k + 1] +
+        1. / ((x_11 - x_00) * (y_11 - y_00)) * (x - x_00) * (y - y_00) * a[k + g.ld + 1];
+}

@@ -72,7 +72,17 @@ bool Impec2DSolver::Solve() {
     impec_ctx *ctx = DeviceContext::Get(sp);
     double maxc = 0, minc = 10e10, avg_fill = 0;
     diagstates.clear();
-    while (state && t < sp->tfinal && (max_steps < 0 || counter < max_steps)) {
+    if (!restart_file.empty()) {
+        DeviceContext::Use(ctx, &c, &p, &v, q, sp);                    // bind the arrays, upload q; then replace the device state
+        long long step0 = 0;
+        DeviceContext::Check(ctx, impec_checkpoint_load(ctx, restart_file.c_str(), &t, &step0), "impec_checkpoint_load");
+        c.MarkDeviceNewer(); p.MarkDeviceNewer(); v.MarkDeviceNewer();
+        counter = (int)step0;
+        while (tidx < sp->times.size() && sp->times[tidx] <= t) tidx++;
+        if (myid == 0) cout << "Restarted from " << restart_file << " at step " << counter << ", t = " << t << endl;
+    }
+    const int first_step = counter;
+    while (state && t < sp->tfinal && (max_steps < 0 || counter - first_step < max_steps)) {
         counter++;
         hs->FillBoundaries(c);                                         // :343
         state = state && es->Solve(p, c, q);                           // :348
@@ -101,8 +111,11 @@ bool Impec2DSolver::Solve() {
             if (listed || (sp->log_skip_steps != 0 && (counter == 1 || counter % sp->log_skip_steps == 0))) LogResults(counter, false);
         }
         maxc = max(maxc, d.c_max); minc = min(minc, d.c_min);
+        if (!checkpoint_file.empty() && checkpoint_every > 0 && counter % checkpoint_every == 0)
+            DeviceContext::Check(ctx, impec_checkpoint_save(ctx, checkpoint_file.c_str(), t, counter), "impec_checkpoint_save");
     }
-    if (counter) avg_fill /= counter;
+    if (!checkpoint_file.empty()) DeviceContext::Check(ctx, impec_checkpoint_save(ctx, checkpoint_file.c_str(), t, counter), "impec_checkpoint_save");
+    if (counter - first_step) avg_fill /= (counter - first_step);
     elapsed_ms = chrono::duration<double, milli>(chrono::steady_clock::now() - t_start).count();
     if (myid == 0) {
         cout << "overall maximum: " << maxc << endl << "overall minimum: " << minc << endl << "average filled cells per dt: " << avg_fill << endl;
@@ -137,18 +150,47 @@ void Impec2DSolver::WriteDiagnostics() {
         file << endl;
     }
 }
-// concentration (and, at the end, pressure and velocity) in the reference's text format.  The reference projects the
-// parallel layout onto the diagonal grid first (ParallelProjector, out of scope here): we write the native grid.
+// Impec2DSolver::Project (src/Impec2DSolver.cpp:690-716): the parallel-layout field arrp (the concentration or the pressure of
+// this solver) interpolated onto the diagonal grid of round(N/sqrt 2) cells by the device kernel behind
+// impec_project_to_diagonal (ParallelProjector::FillDiagonal, src/ParallelProjector.cpp:176-199).  arrd gets `bounds` zero ghosts.
+void Impec2DSolver::Project(Array2d &arrd, Array2d const *const arrp, int bounds, int &d_N1, int &d_N2, double &d_dx, double &d_dy) {
+    impec_ctx *ctx = DeviceContext::Get(sp);
+    if (arrp != &c && arrp != &p) { cerr << "Impec2DSolver::Project: only the solver's own concentration / pressure can be projected" << endl; exit(1); }
+    DeviceContext::Use(ctx, &c, &p, NULL, NULL, sp);
+    DeviceContext::Check(ctx, impec_project_dims(ctx, &d_N1, &d_N2), "impec_project_dims");
+    vector<double> buf((size_t)d_N1 * d_N2);
+    DeviceContext::Check(ctx, impec_project_to_diagonal(ctx, arrp == &p ? 1 : 0, buf.data()), "impec_project_to_diagonal");
+    arrd.resize(d_N1 + 2 * bounds, d_N2 + 2 * bounds);
+    Idx2d idx; idx[0] = -bounds; idx[1] = -bounds;
+    arrd.reindexSelf(idx);
+    arrd = 0;
+    for (int i = 0; i < d_N1; i++) for (int j = 0; j < d_N2; j++) arrd(i, j) = buf[(size_t)i * d_N2 + j];
+    d_dx = (sp->x_ub - sp->x_lb) / (sqrt(2.) * d_N1);
+    d_dy = (sp->y_ub - sp->y_lb) / (sqrt(2.) * d_N2);
+}
+
+// concentration (and, at the end, pressure and velocity) in the reference's text format (src/Impec2DSolver.cpp:622-686).
+// As upstream, a PARALLEL run writes c and p projected onto the diagonal grid (:650-667) and the velocity on the native grid.
 void Impec2DSolver::LogResults(double postfix, bool logTime) {
     string dir = sp->log_dir, post = ".dat";
     if (postfix < 0) dir = sp->results_dir;
     else { stringstream ss; ss << "_"; if (logTime) ss << "t_"; ss << postfix; post = ss.str() + ".dat"; }
     if ((size_t)sp->N1 * sp->N2 > (size_t)4096 * 4096) { if (postfix < 0) cout << "(text output skipped above 4096^2)" << endl; return; }
-    PrintDToPlotFile(dir + "/concentration" + post, c, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->c_bounds);
-    if (postfix < 0) {
-        PrintDToPlotFile(dir + "/pressure" + post, p, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->p_bounds);
-        PrintVelToPlotFile(dir + "/velocity_u" + post, dir + "/velocity_v" + post, v, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->v_bounds, sp->N1, sp->N2);
+    if (sp->stype == PARALLEL) {
+        int d_N1, d_N2; double d_dx, d_dy;
+        Array2d diag_c, diag_p;
+        Project(diag_c, &c, sp->c_bounds, d_N1, d_N2, d_dx, d_dy);
+        PrintDToPlotFile(dir + "/concentration" + post, diag_c, sp->x_lb, sp->y_lb, d_dx, d_dy, sp->c_bounds);
+        if (postfix < 0) {
+            Project(diag_p, &p, sp->p_bounds, d_N1, d_N2, d_dx, d_dy);
+            PrintDToPlotFile(dir + "/pressure" + post, diag_p, sp->x_lb, sp->y_lb, d_dx, d_dy, sp->p_bounds);
+        }
+    } else {
+        PrintDToPlotFile(dir + "/concentration" + post, c, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->c_bounds);
+        if (postfix < 0) PrintDToPlotFile(dir + "/pressure" + post, p, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->p_bounds);
     }
+    if (postfix < 0)
+        PrintVelToPlotFile(dir + "/velocity_u" + post, dir + "/velocity_v" + post, v, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->v_bounds, sp->N1, sp->N2);
 }
 
 bool Impec2DSolver::TestComponent() {

@@ -26,6 +26,9 @@ public:
     const std::vector<DiagState> &Diagnostics() const { return diagstates; }
     double ElapsedMs() const { return elapsed_ms; }
     int max_steps = -1;                               // stop after this many steps (-1: run to endtime)
+    // binary restart (impec_checkpoint_save / _load: exact device state, the restarted run continues bit for bit)
+    std::string checkpoint_file, restart_file;        // write to / start from this file (empty: off)
+    int checkpoint_every = 0;                         // also write every N steps (0: only at the end of the run)
 private:
     std::vector<DiagState> diagstates;
     double elapsed_ms = 0;
@@ -40,5 +43,6 @@ private:
     void OutputState(const DiagState &ds);
     void WriteDiagnostics();
     void LogResults(double postfix, bool logTime);
+    void Project(Array2d &arrd, Array2d const *const arrp, int bounds, int &d_N1, int &d_N2, double &d_dx, double &d_dy);   // src/Impec2DSolver.h
 };
 #endif

