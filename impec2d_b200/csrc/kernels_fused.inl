@@ -29,6 +29,23 @@ enum { FUSED_PLAIN = 0, FUSED_PRE = 1, FUSED_POST = 2, FUSED_MID = 3 };
 // tiles and the time of a launch is the time ONE CTA needs for its tile (more, shorter CTAs finish sooner)
 template <int MODE, int TH = FT_H> struct FusedGeom { enum { HI = (MODE == FUSED_PRE) ? 3 : ((MODE == FUSED_MID) ? 4 : 2), TI = TH - 2 * HI }; };
 
+// loads of ITERATES / right-hand sides.  CG = true bypasses L1 (ld.global.cg): needed inside the persistent tail kernel
+// (k_mg_tail), where one CTA reads arrays that other CTAs rewrite between the phases of the SAME launch -- L1 is only
+// coherent at launch boundaries.  Link coefficients never change during a launch and always use plain loads.
+template <bool CG> IMPEC_D double ldv(const double *p) {
+#ifndef IMPEC_EMU
+    return CG ? __ldcg(p) : *p;
+#else
+    return *p;
+#endif
+}
+template <bool CG> IMPEC_D d2 ldv2(const double *p) {
+#ifndef IMPEC_EMU
+    if (CG) { const double2 v = __ldcg(reinterpret_cast<const double2 *>(p)); d2 r; r.x = v.x; r.y = v.y; return r; }
+#endif
+    return ld2(p);
+}
+
 // shared-memory index of tile cell (r, jj): row-major, even columns in the first half of the row
 IMPEC_D int xi(int r, int jj) { return r * FT_W + ((jj & 1) << 6) + (jj >> 1); }
 
@@ -80,17 +97,20 @@ IMPEC_D double tile_diag(const CF &A, const LevelDev &L, int ld, size_t k) {
 
 // nsweeps > 1 (PLAIN only, and only when this single tile holds the WHOLE level so that no halo can go stale): the
 // sweeps alternate forward/backward starting with colour c0 -- the coarsest-level solve in one launch.
-template <int MODE, bool EDGE, bool F32, int TH>
-IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const double *__restrict__ xin, double *__restrict__ x, const int c0,
-                        const Grid &gc, const double *__restrict__ ec, double *__restrict__ fc, double *__restrict__ part, double *__restrict__ X, const int nsweeps = 1) {
+// (bx, by): tile coordinates, nbx: tiles per row of tiles (the tile kernels pass blockIdx / gridDim; the persistent tail kernel
+// loops over tiles).  The restrict qualifiers are dropped for CG: those arrays are written by other CTAs during the launch.
+template <int MODE, bool EDGE, bool F32, int TH, bool CG = false>
+IMPEC_D void fused_body(const LevelDev &L, const double *f, const double *xin, double *x, const int c0,
+                        const Grid &gc, const double *ec, double *fc, double *part, double *__restrict__ X, const int nsweeps,
+                        const int bx, const int by, const int nbx) {
     constexpr int HI = FusedGeom<MODE, TH>::HI, TI = FusedGeom<MODE, TH>::TI;
     const Grid g = L.g;
     const int ld = g.ld;
     const Coef<F32> A(L);
     const int tx = threadIdx.x, ty = threadIdx.y & (FT_NTY - 1);
     const int jl = 2 * tx;                                   // local column of the pair
-    const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ;          // global column of tile column 0 (even)
-    const int i0 = (int)blockIdx.y * TI - HI;                // global row of tile row 0
+    const int j0 = bx * FT_TJ - FT_HJ;                       // global column of tile column 0 (even)
+    const int i0 = by * TI - HI;                             // global row of tile row 0
     const int jg = j0 + jl;
     const int par = (i0 + ty + jg) & 1;                      // colour of the pair's first cell (same in all rows of this thread)
     const long long kbase = (long long)(i0 + ty + IMPEC_GH) * ld + (jg + IMPEC_PJ);   // global index of the pair in row ty
@@ -104,7 +124,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
         const bool row_alloc = !EDGE || ((ig >= -IMPEC_GH) && (ig < g.rows - IMPEC_GH));
         if (MODE != FUSED_PRE && row_alloc && col_alloc && xin) {
             const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
-            const d2 v = ld2(xin + k);
+            const d2 v = ldv2<CG>(xin + k);
             a = v.x; b = v.y;
             if (MODE == FUSED_POST && (!EDGE || (ig >= g.rlo && ig < g.rhi))) {
                 // x += P ec : cell-centred bilinear with edge replication.  Both cells of the pair share the coarse
@@ -117,9 +137,9 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
                     Jm = Jm < 0 ? 0 : Jm; Jp = Jp > gc.N2 - 1 ? gc.N2 - 1 : Jp;
                 }
                 const double *e0 = ec + gidx(gc, I, 0), *e1 = ec + gidx(gc, In, 0);
-                const double pc = 0.75 * e0[J] + 0.25 * e1[J];
-                const double pm = 0.75 * e0[Jm] + 0.25 * e1[Jm];
-                const double pp = 0.75 * e0[Jp] + 0.25 * e1[Jp];
+                const double pc = 0.75 * ldv<CG>(e0 + J) + 0.25 * ldv<CG>(e1 + J);
+                const double pm = 0.75 * ldv<CG>(e0 + Jm) + 0.25 * ldv<CG>(e1 + Jm);
+                const double pp = 0.75 * ldv<CG>(e0 + Jp) + 0.25 * ldv<CG>(e1 + Jp);
                 if (!EDGE) { a += 0.75 * pc + 0.25 * pm; b += 0.75 * pc + 0.25 * pp; }
                 else {
                     if (jg >= 0 && jg < g.N2 && (long long)k != L.pin) a += 0.75 * pc + 0.25 * pm;
@@ -153,8 +173,8 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
             const bool act = colok && r >= shrink && r < TH - shrink && (!EDGE || (ig >= g.rlo && ig < g.rhi));
             if (act) {
                 const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld + off);
-                if (MODE == FUSED_PRE && s == 0) val = f[k] * (double)A.DINV[k];
-                else val = (f[k] + tile_offsum(A, ld, X, r, tx, off, k)) * (double)A.DINV[k];
+                if (MODE == FUSED_PRE && s == 0) val = ldv<CG>(f + k) * (double)A.DINV[k];
+                else val = (ldv<CG>(f + k) + tile_offsum(A, ld, X, r, tx, off, k)) * (double)A.DINV[k];
             }
             nv[n] = val;
         }
@@ -170,7 +190,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
     // PRE on a slab: f is valid on 3 halo rows of the neighbouring slabs, so the sweep from zero is exact on 2 halo
     // rows as well.  The first / last row of tiles writes them too, which saves the exchange of x that the
     // post-smoothing kernel would otherwise need.
-    const int rmin_w = (MODE == FUSED_PRE && blockIdx.y == 0 && !g.wall_lo) ? HI - 2 : HI;
+    const int rmin_w = (MODE == FUSED_PRE && by == 0 && !g.wall_lo) ? HI - 2 : HI;
 #pragma unroll
     for (int n = 0; n < (TH / FT_NTY); n++) {
         const int r = ty + n * FT_NTY, ig = i0 + r;
@@ -181,13 +201,13 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
         const double a = X[r * FT_W + tx], b = X[r * FT_W + 64 + tx];
         if (!EDGE || jg + 1 < g.N2) st2(x + k, a, b); else x[k] = a;
         if (MODE == FUSED_POST && part) {
-            if (!EDGE || jg + 1 < g.N2) { const d2 fv = ld2(f + k); dotv = fma(fv.x, a, dotv); dotv = fma(fv.y, b, dotv); }
-            else dotv = fma(f[k], a, dotv);
+            if (!EDGE || jg + 1 < g.N2) { const d2 fv = ldv2<CG>(f + k); dotv = fma(fv.x, a, dotv); dotv = fma(fv.y, b, dotv); }
+            else dotv = fma(ldv<CG>(f + k), a, dotv);
         }
     }
     if (MODE == FUSED_POST && part) {
         dotv = block_reduce<RED_SUM>(dotv);
-        if (tx == 0 && ty == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
+        if (tx == 0 && ty == 0) part[by * nbx + bx] = dotv;
     }
     if (MODE != FUSED_PRE && MODE != FUSED_MID) return;
 
@@ -209,7 +229,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *__restrict__ f, const d
                 for (int off = 0; off < 2; off++) {
                     const int jc = jl + off;
                     if (jc >= 3 && jc < FT_W - 3 && (!EDGE || (jg + off >= 0 && jg + off < g.N2 && (long long)(k + off) != L.pin)))
-                        v[off] = f[k + off] - (tile_diag(A, L, ld, k + off) * X[r * FT_W + (off << 6) + tx] - tile_offsum(A, ld, X, r, tx, off, k + off));
+                        v[off] = ldv<CG>(f + k + off) - (tile_diag(A, L, ld, k + off) * X[r * FT_W + (off << 6) + tx] - tile_offsum(A, ld, X, r, tx, off, k + off));
                 }
             }
             ra[n] = v[0]; rb[n] = v[1];
@@ -276,8 +296,8 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY, (TH == 64 ? 2 : (TH == 32 ?
         const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
         edge = edge || (pi >= i0 && pi < i0 + TH && pj >= j0 && pj < j0 + FT_W);
     }
-    if (edge) fused_body<MODE, true, F32, TH>(L, f, xin, x, c0, gc, ec, fc, part, X);
-    else fused_body<MODE, false, F32, TH>(L, f, xin, x, c0, gc, ec, fc, part, X);
+    if (edge) fused_body<MODE, true, F32, TH>(L, f, xin, x, c0, gc, ec, fc, part, X, 1, (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x);
+    else fused_body<MODE, false, F32, TH>(L, f, xin, x, c0, gc, ec, fc, part, X, 1, (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x);
 }
 
 // Coarsest-level solve: `nsweeps` alternating red-black sweeps from a zero guess in ONE launch.  Requires that a
@@ -285,7 +305,7 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY, (TH == 64 ? 2 : (TH == 32 ?
 template <bool F32>
 __global__ void __launch_bounds__(FT_W / 2 * FT_NTY) k_mg_coarse_solve(LevelDev L, const double *__restrict__ f, double *__restrict__ x, int nsweeps) {
     IMPEC_DYN_SMEM(double, X);
-    fused_body<FUSED_PLAIN, true, F32, FT_H>(L, f, (const double *)nullptr, x, 0, L.g, (const double *)nullptr, (double *)nullptr, (double *)nullptr, X, nsweeps);
+    fused_body<FUSED_PLAIN, true, F32, FT_H>(L, f, (const double *)nullptr, x, 0, L.g, (const double *)nullptr, (double *)nullptr, (double *)nullptr, X, nsweeps, 0, 0, 1);
 }
 
 // ---------------------------------------------------------------- fused PCG search-direction update + mat-vec

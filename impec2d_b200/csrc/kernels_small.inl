@@ -13,7 +13,6 @@
 #define SM_T 1024
 #define SM_MAXLEV 8
 #define SM_MAXCELLS 4096
-#define SM_PER (SM_MAXCELLS / SM_T)
 
 struct SmallArgs { int nl, ncoarse; double *xout; LevelDev D[SM_MAXLEV]; };
 
@@ -48,17 +47,20 @@ IMPEC_D double small_diagsum(const CF &A, int ld, size_t k, const double *x, int
 }
 
 // Per-thread view of one level: the (at most SM_PER) cells this thread owns, with their indices computed once.
-struct SmallCells {
-    int c[SM_PER];        // index in the bordered shared iterate (-1: no cell)
-    int k[SM_PER];        // index in the global coefficient arrays
-    int t[SM_PER];        // linear interior index (right-hand side / residual buffers)
-    int par[SM_PER];      // colour (i + j) & 1
+// NT = threads that walk the levels (1024 in k_mg_small, 512 inside the persistent tail kernel); tid = linear thread index
+template <int NT> struct SmallCells {
+    enum { PER = SM_MAXCELLS / NT };
+    int c[PER];           // index in the bordered shared iterate (-1: no cell)
+    int k[PER];           // index in the global coefficient arrays
+    int t[PER];           // linear interior index (right-hand side / residual buffers)
+    int par[PER];         // colour (i + j) & 1
 };
-IMPEC_D void small_cells(const Grid &g, SmallCells &Q) {
-    const int n = g.N1 * g.N2, W = g.N2 + 2, tid = threadIdx.x;
+template <int NT> IMPEC_D void small_cells(const Grid &g, SmallCells<NT> &Q, const int tid) {
+    const int n = g.N1 * g.N2, W = g.N2 + 2;
+    constexpr int SM_PER = SM_MAXCELLS / NT;
 #pragma unroll
     for (int m = 0; m < SM_PER; m++) {
-        const int t = tid + m * SM_T;
+        const int t = tid + m * NT;
         if (t < n) {
             const int i = t / g.N2, j = t - i * g.N2;
             Q.c[m] = (i + 1) * W + j + 1; Q.k[m] = (int)gidx(g, i, j); Q.t[m] = t; Q.par[m] = (i + j) & 1;
@@ -67,8 +69,9 @@ IMPEC_D void small_cells(const Grid &g, SmallCells &Q) {
 }
 
 // one colour pass; ZERO: the iterate is zero on entry and is not read (first pass of a sweep from a zero guess)
-template <bool F32, bool ZERO>
-IMPEC_D void small_pass(const LevelDev &D, const SmallCells &Q, const double *f, double *x, const int col) {
+template <bool F32, bool ZERO, int NT>
+IMPEC_D void small_pass(const LevelDev &D, const SmallCells<NT> &Q, const double *f, double *x, const int col) {
+    constexpr int SM_PER = SM_MAXCELLS / NT;
     const Coef<F32> A(D);
     const int ld = D.g.ld, W = D.g.N2 + 2;
     double nv[SM_PER];
@@ -90,10 +93,10 @@ IMPEC_D void small_pass(const LevelDev &D, const SmallCells &Q, const double *f,
 
 // Coarsest level of at most 32 cells: one warp, one cell per lane, coefficients in registers, warp barriers only.
 template <bool F32>
-IMPEC_D void small_coarsest_warp(const LevelDev &D, const double *f, double *x, const int nsweeps) {
+IMPEC_D void small_coarsest_warp(const LevelDev &D, const double *f, double *x, const int nsweeps, const int tid) {
     const Coef<F32> A(D);
     const Grid g = D.g;
-    const int n = g.N1 * g.N2, W = g.N2 + 2, t = threadIdx.x;
+    const int n = g.N1 * g.N2, W = g.N2 + 2, t = tid;
 #ifdef IMPEC_EMU
     const bool in_warp = true;                    // the emulator's barriers are block-wide: every thread walks the loop
 #else
@@ -134,10 +137,10 @@ IMPEC_D void small_coarsest_warp(const LevelDev &D, const double *f, double *x, 
     IMPEC_SYNCTHREADS();
 }
 
-template <bool F32>
-__global__ void __launch_bounds__(SM_T) k_mg_small(SmallArgs A, const double *__restrict__ f0) {
-    IMPEC_DYN_SMEM(double, S);
-    const int tid = threadIdx.x;
+// CG: the entry right-hand side was written by other CTAs of the same launch (persistent tail kernel): bypass L1
+template <bool F32, int NT, bool CG>
+IMPEC_D void small_body(const SmallArgs &A, const double *f0, double *S, const int tid) {
+    constexpr int SM_PER = SM_MAXCELLS / NT;
     // carve shared memory: R | X_0 F_0 | X_1 F_1 | ...   (offsets in doubles, kept in shared memory)
     __shared__ int offX[SM_MAXLEV], offF[SM_MAXLEV];
     double *R = S;
@@ -151,25 +154,25 @@ __global__ void __launch_bounds__(SM_T) k_mg_small(SmallArgs A, const double *__
         total = p;
     }
     // zero everything once (borders must be zero; iterates start from zero), then load the entry level's rhs
-    for (int q = tid; q < total; q += SM_T) S[q] = 0.;
+    for (int q = tid; q < total; q += NT) S[q] = 0.;
     IMPEC_SYNCTHREADS();
     {
         const Grid g = A.D[0].g;
         const int n = g.N1 * g.N2;
         double *F0 = S + offF[0];
-        for (int t = tid; t < n; t += SM_T) { const int i = t / g.N2, j = t - i * g.N2; F0[t] = f0[gidx(g, i, j)]; }
+        for (int t = tid; t < n; t += NT) { const int i = t / g.N2, j = t - i * g.N2; F0[t] = ldv<CG>(f0 + gidx(g, i, j)); }
     }
     IMPEC_SYNCTHREADS();
-    SmallCells Q;
+    SmallCells<NT> Q;
     // ---- down: forward sweep from zero (colour 0, then 1), residual, restriction
     for (int l = 0; l + 1 < A.nl; l++) {
         const LevelDev &D = A.D[l];
         const Grid g = D.g, gc = A.D[l + 1].g;
         const int W = g.N2 + 2;
         double *x = S + offX[l], *f = S + offF[l], *fc = S + offF[l + 1];
-        small_cells(g, Q);
-        small_pass<F32, true>(D, Q, f, x, 0);
-        small_pass<F32, false>(D, Q, f, x, 1);
+        small_cells<NT>(g, Q, tid);
+        small_pass<F32, true, NT>(D, Q, f, x, 0);
+        small_pass<F32, false, NT>(D, Q, f, x, 1);
         // residual after a sweep from zero: the first colour sees all eight neighbours, the second only its diagonals
         {
             const Coef<F32> C(D);
@@ -184,8 +187,7 @@ __global__ void __launch_bounds__(SM_T) k_mg_small(SmallArgs A, const double *__
         IMPEC_SYNCTHREADS();
         {
             const int nc = gc.N1 * gc.N2;
-            const int t = tid;
-            if (t < nc) {
+            for (int t = tid; t < nc; t += NT) {
                 const int I = t / gc.N2, J = t - I * gc.N2;
                 int jm = 2 * J - 1, jp = 2 * J + 2;
                 jm = jm < 0 ? 0 : jm; jp = jp > g.N2 - 1 ? g.N2 - 1 : jp;
@@ -211,15 +213,15 @@ __global__ void __launch_bounds__(SM_T) k_mg_small(SmallArgs A, const double *__
         const int l = A.nl - 1;
         const LevelDev &D = A.D[l];
         double *x = S + offX[l], *f = S + offF[l];
-        if (D.g.N1 * D.g.N2 <= 32) small_coarsest_warp<F32>(D, f, x, 2 * A.ncoarse);
+        if (D.g.N1 * D.g.N2 <= 32) small_coarsest_warp<F32>(D, f, x, 2 * A.ncoarse, tid);
         else {
-            small_cells(D.g, Q);
-            small_pass<F32, true>(D, Q, f, x, 0);
-            small_pass<F32, false>(D, Q, f, x, 1);
+            small_cells<NT>(D.g, Q, tid);
+            small_pass<F32, true, NT>(D, Q, f, x, 0);
+            small_pass<F32, false, NT>(D, Q, f, x, 1);
             for (int sw = 1; sw < 2 * A.ncoarse; sw++) {
                 const int cfirst = sw & 1;
-                small_pass<F32, false>(D, Q, f, x, cfirst);
-                small_pass<F32, false>(D, Q, f, x, 1 - cfirst);
+                small_pass<F32, false, NT>(D, Q, f, x, cfirst);
+                small_pass<F32, false, NT>(D, Q, f, x, 1 - cfirst);
             }
         }
     }
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(SM_T) k_mg_small(SmallArgs A, const double *__
         const int Wc = gc.N2 + 2;
         double *x = S + offX[l], *f = S + offF[l];
         const double *ec = S + offX[l + 1];
-        small_cells(g, Q);
+        small_cells<NT>(g, Q, tid);
 #pragma unroll
         for (int m = 0; m < SM_PER; m++) {
             if (Q.c[m] < 0 || (long long)Q.k[m] == D.pin) continue;
@@ -245,14 +247,20 @@ __global__ void __launch_bounds__(SM_T) k_mg_small(SmallArgs A, const double *__
             x[Q.c[m]] += 0.75 * pc + 0.25 * pn;
         }
         IMPEC_SYNCTHREADS();
-        small_pass<F32, false>(D, Q, f, x, 1);
-        small_pass<F32, false>(D, Q, f, x, 0);
+        small_pass<F32, false, NT>(D, Q, f, x, 1);
+        small_pass<F32, false, NT>(D, Q, f, x, 0);
     }
     // ---- result of the entry level back to global memory (interior only; the padding of the array stays zero)
     {
         const Grid g = A.D[0].g;
         const int n = g.N1 * g.N2, W = g.N2 + 2;
         const double *x = S + offX[0];
-        for (int t = tid; t < n; t += SM_T) { const int i = t / g.N2, j = t - i * g.N2; A.xout[gidx(g, i, j)] = x[(i + 1) * W + j + 1]; }
+        for (int t = tid; t < n; t += NT) { const int i = t / g.N2, j = t - i * g.N2; A.xout[gidx(g, i, j)] = x[(i + 1) * W + j + 1]; }
     }
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(SM_T) k_mg_small(SmallArgs A, const double *__restrict__ f0) {
+    IMPEC_DYN_SMEM(double, S);
+    small_body<F32, SM_T, false>(A, f0, S, (int)threadIdx.x);
 }
