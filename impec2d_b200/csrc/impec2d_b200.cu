@@ -8,6 +8,7 @@
 #include "kernels_march.inl"
 #include "kernels_staged.inl"
 #include "kernels_small.inl"
+#include "kernels_tail.inl"
 #include "../../include/impec2d_b200.h"
 
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
@@ -95,6 +96,14 @@ struct impec_ctx {
 #endif
     // CUDA graph of the replicated multigrid tail (levels >= tail_level): identical launch sequence every visit
     int tail_level = -1;
+    // the same tail as ONE persistent launch (kernels_tail.inl): program of phases in device memory, barrier counter, error flag
+    // OFF by default: measured on the B200 it is SLOWER than the CUDA-graph replay of the launches (0.297 vs 0.214 ms per visit at
+    // 16384^2): one CTA per SM (the bottom V-cycle needs 125 KB of shared memory) leaves each phase latency-bound, and a grid barrier
+    // costs about what a kernel boundary inside a graph costs.  Kept as an option (bit-identical results, tests/).
+    bool persist_tail = false, tail_ready = false, tail_ok = false;
+    TailProgram *tail_prog = nullptr; unsigned *tail_ctr = nullptr; double *tail_err = nullptr;
+    std::vector<std::pair<double *, double *> > tail_xt_final;
+    int tail_grid = 0; size_t tail_smem = 0; long long tail_phases = 0;
     bool use_graph = true, graph_ready = false;
     long long graph_launches = 0;
     std::vector<std::pair<double *, double *> > tail_init, tail_final;
@@ -611,20 +620,21 @@ extern "C" int impec_reset_state(impec_ctx *ctx) {
 extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     const std::string k(key ? key : "");
     if (k == "warm_start") { ctx->warm_start = value != 0.0; return IMPEC_OK; }
-    if (k == "mg_fused") { ctx->fused = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_fused") { ctx->fused = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
-    if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
-    if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
-    if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
-    if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
-    if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "matvec_march") { ctx->matvec_march = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_shared") { ctx->sweep_shared = value != 0.0; return IMPEC_OK; }
-    if (k == "mg_small") { ctx->use_small = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
-    if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
-    if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
-    if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
-    if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_small") { ctx->use_small = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_persist_tail") { ctx->persist_tail = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "max_iter") { ctx->P.max_iter = (int)value; return IMPEC_OK; }
     return fail(ctx, IMPEC_ERR_ARG, "unknown option '%s'", k.c_str());
 }
@@ -932,9 +942,110 @@ static int fused_post(Cycle &C, int l, const double *f, double *part, long long 
 // One multigrid cycle for S x = f from a zero initial guess; the result is left in ctx->L[l].x (the fused path
 // ping-pongs between the level's two buffers).  dot_part/dot_nparts (level 0, fused path): the last kernel also
 // leaves the partial sums of <f,x> in dot_part.
+// ---- persistent tail (kernels_tail.inl): record the launch sequence of mg_cycle_impl for the levels >= l0 as a program
+struct TailRec { TailProgram P; std::vector<std::pair<double *, double *> > xt; int l0; bool ok; };
+static bool small_eligible(const Cycle &C, int l) {
+    const impec_ctx *ctx = C.ctx; const Level &L = ctx->L[l];
+    return ctx->fused && ctx->use_small && l > 0 && l < C.nl - 1 && l > C.w_to && !L.dist && C.nl - l <= SM_MAXLEV &&
+           (long long)L.g.N1 * L.g.N2 <= SM_MAXCELLS && C.D[l].mass == 0.;
+}
+template <int MODE> static void tail_push(Cycle &C, TailRec &R, int op, int l, const double *f, const double *xin, double *x, int c0, const double *ec, double *fc) {
+    if (R.P.nphases >= TAIL_MAXPHASES) { R.ok = false; return; }
+    impec_ctx *ctx = C.ctx; const Level &L = ctx->L[l]; const Level &Lc = ctx->L[l + 1];
+    TailPhase &ph = R.P.ph[R.P.nphases++];
+    const dim3 gr = fused_grid<MODE>(L.g, TAIL_TH);
+    ph.op = op; ph.c0 = c0; ph.nbx = (int)gr.x; ph.nby = (int)gr.y; ph.D = C.D[l]; ph.gc = Lc.g;
+    ph.f = f; ph.xin = xin; ph.ec = ec; ph.x = x; ph.fc = fc; ph.small_idx = 0;
+}
+static void tail_rec(Cycle &C, TailRec &R, int l, const double *f) {
+    impec_ctx *ctx = C.ctx;
+    if (!R.ok) return;
+    if (ctx->L[l].dist) { R.ok = false; return; }
+    if (small_eligible(C, l)) {
+        if (R.P.nphases >= TAIL_MAXPHASES) { R.ok = false; return; }
+        SmallArgs A; A.nl = C.nl - l; A.ncoarse = C.ncoarse; A.xout = R.xt[l - R.l0].first;
+        for (int k = l; k < C.nl; k++) A.D[k - l] = C.D[k];
+        R.P.small[0] = A;                                   // every visit of the bottom uses the same arguments
+        TailPhase &ph = R.P.ph[R.P.nphases++];
+        memset(&ph, 0, sizeof(ph));
+        ph.op = TAIL_SMALL; ph.f = f; ph.small_idx = 0;
+        return;
+    }
+    if (l >= C.nl - 1) { R.ok = false; return; }            // a coarsest level that is not handled by the small kernel
+    Level &Lc = ctx->L[l + 1];
+    double *&X = R.xt[l - R.l0].first, *&T = R.xt[l - R.l0].second;
+    const int gamma = (l >= C.w_from && l <= C.w_to) ? 2 : 1;
+    tail_push<FUSED_PRE>(C, R, TAIL_PRE, l, f, nullptr, X, 0, nullptr, Lc.f);
+    tail_rec(C, R, l + 1, Lc.f);
+    for (int gc = 1; gc < gamma; gc++) {
+        tail_push<FUSED_POST>(C, R, TAIL_POST, l, f, X, T, 1, R.xt[l + 1 - R.l0].first, nullptr); std::swap(X, T);
+        tail_push<FUSED_MID>(C, R, TAIL_MID, l, f, X, T, 0, nullptr, Lc.f); std::swap(X, T);
+        tail_rec(C, R, l + 1, Lc.f);
+    }
+    tail_push<FUSED_POST>(C, R, TAIL_POST, l, f, X, T, 1, R.xt[l + 1 - R.l0].first, nullptr); std::swap(X, T);
+}
+// build (once) and run the persistent tail for the visit of level l; returns IMPEC_OK, or a positive value if the tail
+// cannot run as one persistent launch (the caller falls back to the graph / the launches)
+static int tail_run(Cycle &C, int l, const double *f) {
+    impec_ctx *ctx = C.ctx;
+    const int nl = (int)ctx->L.size();
+    if (!ctx->tail_ready) {
+        ctx->tail_ready = true; ctx->tail_ok = false;
+        if (!ctx->fused_mid || use_staged(ctx) || f != ctx->L[l].f) return 1;
+        TailRec R; memset(&R.P, 0, sizeof(R.P)); R.l0 = l; R.ok = true;
+        for (int k = l; k < nl; k++) R.xt.push_back(std::make_pair(ctx->L[k].x, ctx->L[k].t));
+        tail_rec(C, R, l, f);
+        if (!R.ok || R.P.nphases < 2) return 1;
+        size_t smem = (size_t)FT_W * TAIL_TH * sizeof(double);
+        smem = std::max(smem, small_smem_doubles(R.P.small[0]) * sizeof(double));
+#ifndef IMPEC_EMU
+        int dev = 0, nsm = 0, coop = 0, per_sm = 0;
+        CUDA_TRY(ctx, cudaGetDevice(&dev));
+        CUDA_TRY(ctx, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        if (!coop) return 1;
+        if (ctx->links_f32) { CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                              CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mg_tail<true>, FT_W / 2 * FT_NTY, smem)); }
+        else { CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+               CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mg_tail<false>, FT_W / 2 * FT_NTY, smem)); }
+        if (per_sm < 1) return 1;
+        ctx->tail_grid = nsm;                              // one CTA per SM: all resident, as the grid barrier requires
+#else
+        ctx->tail_grid = 1;                                // the emulator runs blocks one after another: a single CTA walks all tiles
+#endif
+        if (!ctx->tail_prog) { TRY(dev_alloc(ctx, (double **)&ctx->tail_prog, (sizeof(TailProgram) + 7) / 8)); TRY(dev_alloc(ctx, (double **)&ctx->tail_ctr, 1)); TRY(dev_alloc(ctx, &ctx->tail_err, 1)); }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tail_prog, &R.P, sizeof(TailProgram), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // R.P is on the stack
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->tail_err, 0, sizeof(double), ctx->stream));
+        ctx->tail_xt_final = R.xt; ctx->tail_smem = smem; ctx->tail_phases = R.P.nphases;
+        ctx->tail_ok = true;
+    }
+    if (!ctx->tail_ok) return 1;
+    if (f != ctx->L[l].f) return 1;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->tail_ctr, 0, sizeof(unsigned), ctx->stream));
+#ifndef IMPEC_EMU
+    {
+        const TailProgram *pp = ctx->tail_prog; unsigned *pc = ctx->tail_ctr; double *pe = ctx->tail_err;
+        void *args[3] = {(void *)&pp, (void *)&pc, (void *)&pe};
+        const void *fn = ctx->links_f32 ? (const void *)k_mg_tail<true> : (const void *)k_mg_tail<false>;
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->tail_grid), kFusedBlock, args, ctx->tail_smem, ctx->stream));
+        ctx->launches++;
+    }
+#else
+    if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, k_mg_tail<true>, dim3(1), kFusedBlock, ctx->tail_smem, (const TailProgram *)ctx->tail_prog, ctx->tail_ctr, ctx->tail_err);
+    else LAUNCH_COOP_SMEM(ctx, k_mg_tail<false>, dim3(1), kFusedBlock, ctx->tail_smem, (const TailProgram *)ctx->tail_prog, ctx->tail_ctr, ctx->tail_err);
+#endif
+    for (int k = l; k < nl; k++) { ctx->L[k].x = ctx->tail_xt_final[k - l].first; ctx->L[k].t = ctx->tail_xt_final[k - l].second; }
+    return IMPEC_OK;
+}
+
 static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, long long *dot_nparts);
 static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr, long long *dot_nparts = nullptr) {
     impec_ctx *ctx = C.ctx;
+    if (l == ctx->tail_level && ctx->persist_tail && ctx->fused && C.nl == (int)ctx->L.size() && C.D[0].mass == 0.) {
+        const int rc = tail_run(C, l, f);
+        if (rc <= 0) { if (dot_nparts) *dot_nparts = 0; return rc; }          // ran (or failed); > 0: not eligible, fall through
+    }
 #ifndef IMPEC_EMU
     // The replicated tail (levels >= tail_level) is the same launch sequence on the same buffers at every visit: it is
     // captured once into a CUDA graph and replayed, which removes the launch gaps of ~100 tiny kernels per visit.

@@ -353,6 +353,27 @@ def check_march_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
         os.environ.pop("IMPEC_MARCH_MIN_CELLS", None)
 
 
+def check_persistent_tail(emulated, N1=256, N2=384, stype=O.DIAGONAL):
+    """The multigrid tail as ONE persistent launch (kernels_tail.inl: a program of phases interpreted by resident CTAs, grid
+    barriers instead of kernel boundaries) against the same tail issued as separate launches: the phases run the very same
+    tile / small-level bodies in the same order, so the cycle must agree BIT FOR BIT (FP64 and FP32 coefficients), and
+    repeated cycles must be repeatable (stale-L1 / barrier bugs show up as run-to-run differences)."""
+    base, Po, c, q = production_case(N1, N2, stype=stype)
+    Pi = I.default_params(emulated=emulated, **base)
+    r = np.random.default_rng(6).standard_normal(N1 * N2)
+    for f32 in (0, 1):
+        out = []
+        for persist in (0, 1):
+            ctx = I.Context(Pi, emulated=emulated)
+            ctx.set_option("mg_persist_tail", persist); ctx.set_option("mg_links_fp32", f32)      # (off by default: slower on the B200)
+            ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
+            zs = [ctx.vcycle(r) for _ in range(3)]
+            assert np.array_equal(zs[0], zs[1]) and np.array_equal(zs[0], zs[2]), "cycle is not repeatable (race?)"
+            out.append(zs[0])
+            ctx.close()
+        assert np.array_equal(out[0], out[1]), "persistent tail vs launches (fp32 links %d): max diff %g of %g" % (f32, np.abs(out[0] - out[1]).max(), np.abs(out[0]).max())
+
+
 def check_small_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
     """The single-CTA bottom-of-hierarchy kernel (kernels_small.inl, levels of <= 4096 cells) against the tile kernels
     on the same levels: same arithmetic per cell, so one cycle agrees to rounding (<= 1e-13 relative), with FP64 and
