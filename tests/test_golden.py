@@ -20,9 +20,11 @@ def test_oracle_reproduces_golden_vectors():
     now = make_golden.vectors()
     assert set(now) == set(G.files)
     for k in G.files:
-        if k in ("impes_c1", "impes_p", "impes_u", "impes_v", "impes_dt"):      # behind the PCG solve: OpenMP reductions are not
-            assert np.abs(now[k] - G[k]).max() <= 1e-11 * max(1.0, np.abs(G[k]).max()), k   # bitwise reproducible run to run
-        else:
+        if k == "impes_its":                      # the PCG stops at a threshold: OpenMP reduction order can move it by one iteration
+            assert abs(int(now[k][0]) - int(G[k][0])) <= 1
+        elif k in ("impes_c1", "impes_p", "impes_u", "impes_v", "impes_dt"):          # behind the solve (eps = 1e-12): solver tolerance
+            assert np.abs(now[k] - G[k]).max() <= 1e-9 * max(1.0, np.abs(G[k]).max()), k
+        else:                                     # everything explicit: bit for bit
             assert np.array_equal(now[k], G[k]), k
 
 
