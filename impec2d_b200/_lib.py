@@ -72,6 +72,22 @@ def library_path(emulated=False):
     return os.path.join(_HERE, "libimpec2d_emu.so" if emulated else "libimpec2d_b200.so")
 
 
+def _preload_nccl():
+    """libimpec2d_b200.so needs libnccl.so.2.  PyTorch ships its own, newer NCCL (nvidia/nccl/lib) and libtorch_cuda.so fails to
+    load (`undefined symbol: ncclDevCommCreate`) if the system's older libnccl.so.2 is already in the process.  So whichever of
+    torch / this library is imported first, make the bundled NCCL the one that gets loaded: processes that use both (bench.py,
+    the multi-GPU tests) then share one NCCL.  No torch import here, and no error if the wheel is absent (system NCCL is used)."""
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load(emulated=False):
     """Load the C-ABI library.  emulated=True is for tests only (CPU emulation of the CUDA kernels)."""
     key = bool(emulated)
@@ -82,6 +98,8 @@ def load(emulated=False):
         raise RuntimeError(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  There is no CPU fallback." % path)
+    if not emulated:
+        _preload_nccl()
     L = C.CDLL(path)
     if bool(L.impec_is_emulated()) != key:
         raise RuntimeError("library %s reports emulated=%d, expected %d" % (path, L.impec_is_emulated(), key))
