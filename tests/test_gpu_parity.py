@@ -1,6 +1,7 @@
 """B200 parity tests proper: the real sm_100a library, called through the C ABI, against the CPU oracle on the
 same seeded inputs (sizes the oracle finishes in seconds) plus size-independent properties at larger sizes."""
 import ctypes as C
+import os
 import numpy as np
 import pytest
 import oracle as O
@@ -113,6 +114,31 @@ def test_large_grid_properties():
     d1 = ctx.diagnostics()
     assert abs(d1.total_mass - m0) <= 1e-11 * m0            # Neumann walls, zero normal velocity
     assert -1e-12 <= d1.c_min and d1.c_max <= 1.0 + 1e-3
+    ctx.close()
+
+
+def test_headline_size_properties():
+    """16384^2 (the size BASELINE's metric is quoted on), oracle-free properties: the register-march multigrid kernels and the
+    tile kernels give the SAME cycle bit for bit at full size (every chunk / warp / tile boundary of the production
+    launch geometry is exercised), the marching mat-vec solve converges with HYPRE's stop rule, and the advection step conserves
+    mass with closed walls."""
+    N = 16384
+    P = I.default_params(N1=N, N2=N, x_ub=1.41421356237, y_ub=1.41421356237, stype=O.PARALLEL, nu=2.0 / 3.0, eps=1e-10)
+    c = I.synth_state(P); q = I.init_source(P)
+    ctx = I.Context(P)
+    ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
+    r = np.random.default_rng(3).standard_normal(N * N)
+    ctx.set_option("mg_march", 1); z1 = ctx.vcycle(r)
+    ctx.set_option("mg_march", 0); z0 = ctx.vcycle(r)
+    ctx.set_option("mg_march", 1)
+    assert np.array_equal(z0, z1), "march vs tiles at 16384^2: max diff %g" % np.abs(z0 - z1).max()
+    del z0, z1, r
+    dt, info = ctx.impes_step()
+    assert info.converged == 1 and info.relres < 1e-10 and info.iterations <= 20
+    d0 = ctx.diagnostics()
+    ctx.advect_split(dt)
+    d1 = ctx.diagnostics()
+    assert abs(d1.total_mass - d0.total_mass) <= 1e-11 * d0.total_mass
     ctx.close()
 
 
