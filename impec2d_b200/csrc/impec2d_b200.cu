@@ -1041,7 +1041,7 @@ static int tail_run(Cycle &C, int l, const double *f) {
 
 static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, long long *dot_nparts);
 static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr, long long *dot_nparts = nullptr) {
-    impec_ctx *ctx = C.ctx;
+    impec_ctx *ctx = C.ctx; (void)ctx;
     if (l == ctx->tail_level && ctx->persist_tail && ctx->fused && C.nl == (int)ctx->L.size() && C.D[0].mass == 0.) {
         const int rc = tail_run(C, l, f);
         if (rc <= 0) { if (dot_nparts) *dot_nparts = 0; return rc; }          // ran (or failed); > 0: not eligible, fall through
