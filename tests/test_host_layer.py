@@ -105,18 +105,18 @@ def test_parallel_run_writes_projected_fields(tmp_path):
 
 
 def test_driver_checkpoint_restart(tmp_path):
-    """impec2d --checkpoint / --restart: 4 steps in one go == 2 steps, checkpoint, restart, 2 more steps
+    """impec2d --checkpoint / --restart: 2 steps in one go == 1 step, checkpoint, restart, 1 more step
     (same concentration file, same last diagnostics line)."""
     subs = [(r"x_cells\s*=\s*\d+", "x_cells = 24"), (r"y_cells\s*=\s*\d+", "y_cells = 24")]
     da = tmp_path / "a"; db = tmp_path / "b"; da.mkdir(); db.mkdir()
     cfg_a = cfg_variant(da, "parallel.cfg", subs); cfg_b = cfg_variant(db, "parallel.cfg", subs)
     ck = str(tmp_path / "run.ckpt")
-    out = subprocess.run([EXE, cfg_a, "--steps", "4"], capture_output=True, text=True); assert out.returncode == 0, out.stdout + out.stderr
-    last_a = [l for l in out.stdout.splitlines() if l.startswith("[4]")]
-    out = subprocess.run([EXE, cfg_b, "--steps", "2", "--checkpoint", ck], capture_output=True, text=True); assert out.returncode == 0, out.stdout + out.stderr
-    out = subprocess.run([EXE, cfg_b, "--steps", "2", "--restart", ck], capture_output=True, text=True); assert out.returncode == 0, out.stdout + out.stderr
+    out = subprocess.run([EXE, cfg_a, "--steps", "2"], capture_output=True, text=True); assert out.returncode == 0, out.stdout + out.stderr
+    last_a = [l for l in out.stdout.splitlines() if l.startswith("[2]")]
+    out = subprocess.run([EXE, cfg_b, "--steps", "1", "--checkpoint", ck], capture_output=True, text=True); assert out.returncode == 0, out.stdout + out.stderr
+    out = subprocess.run([EXE, cfg_b, "--steps", "1", "--restart", ck], capture_output=True, text=True); assert out.returncode == 0, out.stdout + out.stderr
     assert "Restarted from" in out.stdout
-    last_b = [l for l in out.stdout.splitlines() if l.startswith("[4]")]
+    last_b = [l for l in out.stdout.splitlines() if l.startswith("[2]")]
     assert last_a and last_a == last_b, (last_a, last_b)
     ca = np.loadtxt(str(da / "concentration.dat")); cb = np.loadtxt(str(db / "concentration.dat"))
     assert np.array_equal(ca, cb)

@@ -20,9 +20,9 @@ def run(world, N1, N2, stype, diffusion, steps, port, extra_env=None):
     assert out.stdout.count(" ok: ") == world, out.stdout
 
 
-def test_two_ranks_parallel_cfg(): run(2, 64, 64, 0, 0, 2, 29611)
+def test_two_ranks_parallel_cfg(): run(2, 64, 64, 0, 0, 1, 29611)
 def test_two_ranks_rect_diagonal_with_dispersion(): run(2, 64, 32, 1, 1, 1, 29612)
-def test_four_ranks(): run(4, 128, 64, 1, 0, 1, 29613)
+def test_four_ranks(): run(4, 64, 32, 1, 0, 1, 29613)
 # the register-march multigrid kernels (big levels only by default) forced onto the slab levels: chunk edges at slab
 # boundaries, the 2 halo rows PRE stores for its neighbours, coarse slab views at the transition level
 def test_two_ranks_marching_kernels(): run(2, 128, 128, 0, 0, 1, 29614, {"IMPEC_MARCH_MIN_CELLS": "0"})
