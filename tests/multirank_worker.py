@@ -61,6 +61,18 @@ def main():
     assert abs(d.c_max - dr.c_max) <= 1e-9 and abs(d.c_min - dr.c_min) <= 1e-9, (d.c_max, dr.c_max)
     assert abs(d.divergence_error - dr.divergence_error) <= 1e-9 + 1e-3 * dr.divergence_error, (d.divergence_error, dr.divergence_error)
     assert abs(d.boundary_velocity_error - dr.boundary_velocity_error) <= 1e-9, (d.boundary_velocity_error, dr.boundary_velocity_error)
+    if os.environ.get("IMPEC_TEST_CKPT"):
+        # per-rank binary checkpoint: save, step, restore, step again -> the same slab bit for bit
+        import tempfile
+        path = os.path.join(tempfile.gettempdir(), "impec_ckpt_%d_rank%d.bin" % (os.getppid(), rank))
+        ctx.checkpoint_save(path, t, steps)
+        dt1, _ = ctx.impes_step(t, 0.0)
+        c1 = np.zeros_like(c); ctx.download_c(c1)
+        assert ctx.checkpoint_load(path) == (t, steps)
+        dt2, _ = ctx.impes_step(t, 0.0)
+        c2 = np.zeros_like(c); ctx.download_c(c2)
+        os.remove(path)
+        assert dt1 == dt2 and np.array_equal(c1[rows], c2[rows]), "restart from the per-rank checkpoint is not bit-exact"
     print("rank %d ok: dc %.2e dp %.2e its %d/%d levels %d" % (rank, dc, dp, info.iterations, info_ref.iterations, ctx.mg_levels()), flush=True)
     ctx.close(); ref.close()
     dist.destroy_process_group()
