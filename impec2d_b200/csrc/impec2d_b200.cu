@@ -68,6 +68,7 @@ struct impec_ctx {
                                                     // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
     bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
+    bool sgs_march = true;                          // Crank-Nicolson preconditioner (one symmetric sweep from zero) as ONE march (k_sgs_march)
     int march_variant = 1;                          // bit 0: k_mg_march_pre with 2 rows in flight and 4 CTAs/SM (default) instead of 4 rows and 3 CTAs/SM
     bool march = true;                              // big levels: PRE / POST / PLAIN as register marches (kernels_march.inl); 0 = shared-memory tiles
     bool fused_mid = true;                          // W-cycle revisit: sweep + residual + restriction in one tile kernel (FUSED_MID)
@@ -624,6 +625,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
     if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "sgs_march") { ctx->sgs_march = value != 0.0; return IMPEC_OK; }
     if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
@@ -1097,6 +1099,15 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
             // the whole level fits one tile: all 2*ncoarse sweeps in a single launch (x0 = 0 inside the kernel)
             if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, k_mg_coarse_solve<true>, dim3(1, 1), kFusedBlock, kFusedSmem, C.D[l], f, L.x, 2 * C.ncoarse);
             else LAUNCH_COOP_SMEM(ctx, k_mg_coarse_solve<false>, dim3(1, 1), kFusedBlock, kFusedSmem, C.D[l], f, L.x, 2 * C.ncoarse);
+            return IMPEC_OK;
+        }
+        if (fused && C.ncoarse == 1 && !L.dist && ctx->sgs_march && use_march(ctx, L)) {
+            // one symmetric sweep from zero (the Crank-Nicolson preconditioner) on a big level: all four colour stages in ONE march
+            ctx->march_launches++;
+            const dim3 gm = march_grid(L, MGP_OWN);
+            if (ctx->links_f32) LAUNCH_COOP(ctx, k_sgs_march<true>, gm, dim3(MG_BLOCK), C.D[l], f, L.x, dot_part, L.march_rows);
+            else LAUNCH_COOP(ctx, k_sgs_march<false>, gm, dim3(MG_BLOCK), C.D[l], f, L.x, dot_part, L.march_rows);
+            if (dot_part && dot_nparts) *dot_nparts = (long long)gm.x * gm.y;
             return IMPEC_OK;
         }
         if (fused) {

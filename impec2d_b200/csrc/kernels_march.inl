@@ -310,3 +310,105 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_post(LevelDev L, co
         if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
     }
 }
+
+// ================================================================ symmetric Gauss-Seidel from zero in ONE march
+// The Crank-Nicolson dispersion solve (a19) preconditions PCG with one symmetric red-black sweep from a zero guess.  As launches
+// that is a memset of x, a forward sweep (k_mg_march_post<PLAIN, 0>) and a backward sweep (<PLAIN, 1>): 8 + 40 + 40 B/cell, and a
+// separate <r,z> pass.  Here the four colour stages run skewed along one march -- when row t arrives: colour 0 on row t (zero
+// guess: f * dinv), colour 1 on row t-1 (forward sweep done on that row), colour 1 again on row t-2 (first stage of the backward
+// sweep, all eight neighbours from the forward result) and colour 0 on row t-3 (stored, dotted with f): 34 B/cell in one launch.
+// The arithmetic per cell is that of the three launches (the forward half is pre_step's, the backward half post_step's), so the
+// result is bit-identical; two halo lanes per side as in PRE.
+template <bool F32> struct SgsFwd { double xF1, e01, xA2, xB2; d2 f1; CoefRow<F32> c1; };
+template <bool F32, bool AF>
+IMPEC_D void sgs_step(const int t, const PreRow<F32> &R, SgsFwd<F32> &F, PostState<F32> &S, const PostGeom &G, double *__restrict__ x, double &dotv) {
+    // ---- forward sweep from zero (pre_step, parts 1 and 2): colour 0 on row t, colour 1 on row t-1
+    const bool act0 = G.colok && t >= G.t_rlo && t < G.t_rhi;
+    const double xF = act0 ? (AF ? R.f.x * (double)R.c.dinv.x : R.f.y * (double)R.c.dinv.y) : 0.;
+    const double e0 = AF ? IMPEC_SHFL_DOWN(xF, 1) : IMPEC_SHFL_UP(xF, 1);
+    const bool actf = G.colok && t - 1 >= G.t_rlo && t - 1 < G.t_rhi;
+    double il0, a, b, ir0;                                     // forward result on row t-1: columns jA-1 | jA, jA+1 | jA+2
+    if (AF) {
+        double off = (double)F.c1.aw.x * F.xA2;
+        off = fma((double)R.c.aw.x, xF, off); off = fma((double)F.c1.as.x, F.e01, off); off = fma((double)F.c1.as.y, F.xF1, off);
+        const double xS = actf ? (F.f1.x + off) * (double)F.c1.dinv.x : 0.;
+        a = xS; b = F.xF1; il0 = F.e01; ir0 = IMPEC_SHFL_DOWN(xS, 1);
+    } else {
+        double off = (double)F.c1.aw.y * F.xB2;
+        off = fma((double)R.c.aw.y, xF, off); off = fma((double)F.c1.as.y, F.xF1, off); off = fma((double)F.c1.as2, F.e01, off);
+        const double xS = actf ? (F.f1.y + off) * (double)F.c1.dinv.y : 0.;
+        a = F.xF1; b = xS; ir0 = F.e01; il0 = IMPEC_SHFL_UP(xS, 1);
+    }
+    // ---- backward sweep (post_step, parts 2 and 3, one row later): its "row t" is our row t-1, whose links are F.c1.
+    //      First colour of the backward sweep = colour 1, carried by A on row t-1 exactly when A carries colour 0 on row t.
+    const int tb = t - 1;
+    const bool act1 = G.colok && tb - 1 >= G.t_rlo && tb - 1 < G.t_rhi;
+    double y, e1;
+    if (AF) {   // row tb-1: B first
+        const double off = sum8((double)S.c1.aw.y, (double)F.c1.aw.y, (double)S.c1.as.y, (double)S.c1.as2, (double)S.c1.av.y, (double)F.c1.av.y, (double)S.c1.av2, (double)F.c1.av2,
+                                S.iB2, b, S.iA1, S.ir1, S.iA2, a, S.ir2, ir0);
+        y = act1 ? (S.f1.y + off) * (double)S.c1.dinv.y : S.iB1;
+        e1 = IMPEC_SHFL_UP(y, 1);
+    } else {    // row tb-1: A first
+        const double off = sum8((double)S.c1.aw.x, (double)F.c1.aw.x, (double)S.c1.as.x, (double)S.c1.as.y, (double)S.c1.av.x, (double)F.c1.av.x, (double)S.c1.av.y, (double)F.c1.av.y,
+                                S.iA2, a, S.il1, S.iB1, S.il2, il0, S.iB2, b);
+        y = act1 ? (S.f1.x + off) * (double)S.c1.dinv.x : S.iA1;
+        e1 = IMPEC_SHFL_DOWN(y, 1);
+    }
+    const bool act2 = G.colok && tb - 2 >= G.t_rlo && tb - 2 < G.t_rhi;
+    double xA, xB;
+    if (AF) {   // row tb-2: A first (new value yF2), B second
+        const double off = sum8((double)S.c2.aw.y, (double)S.c1.aw.y, (double)S.c2.as.y, (double)S.c2.as2, (double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2,
+                                S.yF3, y, S.yF2, S.e2, S.iA3, S.iA1, S.ir3, S.ir1);
+        xA = S.yF2; xB = act2 ? (S.f2.y + off) * (double)S.c2.dinv.y : S.iB2;
+    } else {    // row tb-2: B first, A second
+        const double off = sum8((double)S.c2.aw.x, (double)S.c1.aw.x, (double)S.c2.as.x, (double)S.c2.as.y, (double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y,
+                                S.yF3, y, S.e2, S.yF2, S.il3, S.il1, S.iB3, S.iB1);
+        xB = S.yF2; xA = act2 ? (S.f2.x + off) * (double)S.c2.dinv.x : S.iA2;
+    }
+    if (G.own && tb - 2 >= G.ia && tb - 2 < G.ib) {
+        st2(x + G.kb + (long long)(tb - 2) * G.ld, xA, xB);
+        dotv = fma(S.f2.x, xA, dotv); dotv = fma(S.f2.y, xB, dotv);
+    }
+    // shift both pipelines
+    S.il3 = S.il2; S.iA3 = S.iA2; S.iB3 = S.iB2; S.ir3 = S.ir2;
+    S.il2 = S.il1; S.iA2 = S.iA1; S.iB2 = S.iB1; S.ir2 = S.ir1;
+    S.il1 = il0; S.iA1 = a; S.iB1 = b; S.ir1 = ir0;
+    S.yF3 = S.yF2; S.yF2 = y; S.e2 = e1;
+    S.f2 = S.f1; S.f1 = F.f1; S.c2 = S.c1; S.c1 = F.c1;
+    F.xA2 = a; F.xB2 = b; F.xF1 = xF; F.e01 = e0; F.f1 = R.f; F.c1 = R.c;
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(MG_BLOCK, 3) k_sgs_march(LevelDev L, const double *__restrict__ f, double *__restrict__ x, double *__restrict__ part, int nrows) {
+    const Grid g = L.g;
+    const Coef<F32> A(L);
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)blockIdx.x * (MG_BLOCK / 32) + (int)(threadIdx.x >> 5);
+    PostGeom G;
+    G.ia = (int)blockIdx.y * nrows;
+    G.ib = (G.ia + nrows < g.N1) ? G.ia + nrows : g.N1;
+    G.jA = MGP_OWN * gw - 4 + 2 * lane;
+    G.colok = G.jA >= 0 && G.jA < g.N2;
+    G.own = G.colok && lane >= 2 && lane < 30;
+    G.t_rlo = g.rlo; G.t_rhi = g.rhi;
+    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
+    SgsFwd<F32> F;
+    F.xF1 = F.e01 = F.xA2 = F.xB2 = 0.; F.f1.x = F.f1.y = 0.; F.c1 = coef_zero<F32>();
+    PostState<F32> S;
+    S.il1 = S.iA1 = S.iB1 = S.ir1 = S.il2 = S.iA2 = S.iB2 = S.ir2 = S.il3 = S.iA3 = S.iB3 = S.ir3 = 0.;
+    S.yF2 = S.yF3 = S.e2 = 0.; S.f1.x = S.f1.y = S.f2.x = S.f2.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
+    double dotv = 0.;
+    const int t0 = G.ia - 3, t1 = G.ib + 2;    // rows marched: [t0, t1], an even count; t0 is odd
+    PreRow<F32> q0 = pre_load<F32>(A, f, G.kb + (long long)t0 * G.ld, G.colok), q1 = pre_load<F32>(A, f, G.kb + (long long)(t0 + 1) * G.ld, G.colok);
+    for (int t = t0; t <= t1; t += 2) {
+        { const PreRow<F32> R = q0; q0 = pre_load<F32>(A, f, G.kb + (long long)((t + 2 <= t1) ? t + 2 : t1) * G.ld, G.colok);
+          sgs_step<F32, false>(t, R, F, S, G, x, dotv); }
+        { const PreRow<F32> R = q1; q1 = pre_load<F32>(A, f, G.kb + (long long)((t + 3 <= t1) ? t + 3 : t1) * G.ld, G.colok);
+          sgs_step<F32, true>(t + 1, R, F, S, G, x, dotv); }
+    }
+    if (part) {
+        dotv = block_reduce<RED_SUM>(dotv);
+        if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
+    }
+}

@@ -374,6 +374,32 @@ def check_persistent_tail(emulated, N1=256, N2=384, stype=O.DIAGONAL):
         assert np.array_equal(out[0], out[1]), "persistent tail vs launches (fp32 links %d): max diff %g of %g" % (f32, np.abs(out[0] - out[1]).max(), np.abs(out[0]).max())
 
 
+def check_sgs_march(emulated, N1=64, N2=96, stype=O.DIAGONAL):
+    """The Crank-Nicolson preconditioner (one symmetric red-black sweep from zero) as ONE march (k_sgs_march) against the
+    same sweep issued as memset + forward PLAIN + backward PLAIN: identical arithmetic per cell, so the dispersion half
+    step gives the same concentration and the same iteration count (the fused <r,z> is summed in another order: 1e-13)."""
+    lib = O.lib()
+    base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=1)
+    Pi = I.default_params(emulated=emulated, **base)
+    os.environ["IMPEC_MARCH_MIN_CELLS"] = "0"
+    try:
+        out = []
+        for sgs in (1, 0):
+            ctx = I.Context(Pi, emulated=emulated)
+            ctx.set_option("sgs_march", sgs)
+            ctx.upload_c(c); ctx.upload_q(q)
+            dt, _ = ctx.impes_step(0.0, 0.0)          # velocities for the dispersion tensor
+            ctx.upload_c(c); ctx.fill_boundaries()
+            info = ctx.diffusion_split(0.5 * dt)
+            assert info.converged == 1
+            out.append((info.iterations, ctx.download_c()))
+            ctx.close()
+    finally:
+        os.environ.pop("IMPEC_MARCH_MIN_CELLS", None)
+    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-13, np.abs(out[0][1] - out[1][1]).max()
+
+
 def check_small_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
     """The single-CTA bottom-of-hierarchy kernel (kernels_small.inl, levels of <= 4096 cells) against the tile kernels
     on the same levels: same arithmetic per cell, so one cycle agrees to rounding (<= 1e-13 relative), with FP64 and

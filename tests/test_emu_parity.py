@@ -49,4 +49,5 @@ def test_matvec_march_vs_tiles(): pc.check_matvec_variants(True)
 def test_matvec_march_odd_columns(): pc.check_matvec_variants(True, 20, 31, eps=1e-9)
 def test_march_vs_tile_kernels(): pc.check_march_vs_tiles(True)
 def test_persistent_tail_vs_launches(): pc.check_persistent_tail(True)
+def test_sgs_march_vs_sweeps(): pc.check_sgs_march(True)
 def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(True, 256, 384)
