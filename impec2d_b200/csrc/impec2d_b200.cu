@@ -1101,8 +1101,10 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
             else LAUNCH_COOP_SMEM(ctx, k_mg_coarse_solve<false>, dim3(1, 1), kFusedBlock, kFusedSmem, C.D[l], f, L.x, 2 * C.ncoarse);
             return IMPEC_OK;
         }
-        if (fused && C.ncoarse == 1 && !L.dist && ctx->sgs_march && use_march(ctx, L)) {
-            // one symmetric sweep from zero (the Crank-Nicolson preconditioner) on a big level: all four colour stages in ONE march
+        if (fused && C.ncoarse == 1 && ctx->sgs_march && use_march(ctx, L)) {
+            // one symmetric sweep from zero (the Crank-Nicolson preconditioner) on a big level: all four colour stages in ONE march.
+            // On a slab the 3 halo rows of f make the sweep exact on the interior rows (no exchange of x between the two half sweeps).
+            if (L.dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
             ctx->march_launches++;
             const dim3 gm = march_grid(L, MGP_OWN);
             if (ctx->links_f32) LAUNCH_COOP(ctx, k_sgs_march<true>, gm, dim3(MG_BLOCK), C.D[l], f, L.x, dot_part, L.march_rows);
