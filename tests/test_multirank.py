@@ -23,7 +23,7 @@ def run(world, N1, N2, stype, diffusion, steps, port, extra_env=None):
 def test_two_ranks_parallel_cfg(): run(2, 64, 64, 0, 0, 1, 29611)
 def test_two_ranks_rect_diagonal_with_dispersion(): run(2, 64, 32, 1, 1, 1, 29612, {"IMPEC_TEST_CKPT": "1"})   # + per-rank checkpoint round trip
 # the marching kernels, including the one-march Crank-Nicolson preconditioner (k_sgs_march), forced onto the slabs of a dispersion run
-def test_two_ranks_dispersion_marching_kernels(): run(2, 128, 64, 1, 1, 1, 29615, {"IMPEC_MARCH_MIN_CELLS": "0"})
+def test_two_ranks_dispersion_marching_kernels(): run(2, 64, 64, 1, 1, 1, 29615, {"IMPEC_MARCH_MIN_CELLS": "0"})
 def test_four_ranks(): run(4, 64, 32, 1, 0, 1, 29613)
 # the register-march multigrid kernels (big levels only by default) forced onto the slab levels: chunk edges at slab
 # boundaries, the 2 halo rows PRE stores for its neighbours, coarse slab views at the transition level
