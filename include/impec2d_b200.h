@@ -174,7 +174,11 @@ long long impec_kernel_launches(const impec_ctx *ctx);                   /* kern
 int   impec_reset_state(impec_ctx *ctx);                                 /* produced mass := 0, sweep parity := Y */
 /* options: "warm_start" (x0 = previous p instead of the reference's 0), "stagnation_guard" (stop PCG at the FP64
  * residual floor instead of iterating the recurrence residual down to eps), "mg_fused", "mg_links_fp32", "mg_staged",
- * "mg_graph", "mg_small", "mg_w_from", "mg_w_to", "mg_ncoarse", "max_iter".  Defaults reproduce the reference's semantics. */
+ * "mg_graph", "mg_small", "mg_w_from", "mg_w_to", "mg_ncoarse", "max_iter".  Defaults reproduce the reference's semantics.
+ * Kernel-generation switches (results identical, for A/B measurements and tests): "mg_march" (register-march multigrid kernels
+ * on the big levels, default 1), "mg_march_variant", "matvec_march" (1), "sweep_shared" (MUSCL with one reconstruction per cell, 1),
+ * "mg_fused_mid" (1), "sgs_march" (one-march Crank-Nicolson preconditioner, 1), "mg_persist_tail" (persistent tail kernel, 0).
+ * Environment, read at context creation: IMPEC_MARCH_MIN_CELLS, IMPEC_TH32_BELOW, IMPEC_TH16_BELOW, IMPEC_DIST_MIN_CELLS. */
 int   impec_set_option(impec_ctx *ctx, const char *key, double value);
 /* average device time of one named piece of the path ("smooth_sweep", "residual", "vcycle", "sweep_x", ...) over
  * `reps` launches, measured with CUDA events on the context stream */
