@@ -1301,9 +1301,10 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
     }
     // true residual with the final x
     TRY(exchange_rows(ctx, x, g, 2));
-    LAUNCH(ctx, k_residual, gres, kBlock, A, rhs, (const double *)x, ctx->s);
-    LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->s, ctx->s, ctx->part);
-    TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_TMP));
+    { const int rrows = 64;
+      const dim3 grn((unsigned)((g.N2 + BX - 1) / BX), (unsigned)((g.N1 + rrows - 1) / rrows));
+      LAUNCH_COOP(ctx, k_residual_norm, grn, kBlock, A, rhs, (const double *)x, ctx->part, rrows);
+      TRY(reduce_final(ctx, RED_SUM, (long long)grn.x * grn.y, 1, 0, S_TMP)); }
     TRY(fetch_scalars(ctx, S_TMP, 1));
     if (info) {
         info->iterations = it; info->converged = converged;
