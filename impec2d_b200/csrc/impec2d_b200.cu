@@ -68,6 +68,7 @@ struct impec_ctx {
                                                     // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
     bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
+    bool fast_r0 = true;                            // initial PCG residual for x0 = 0: copy of rhs + fix-up around the pin instead of a residual pass
     bool sgs_march = true;                          // Crank-Nicolson preconditioner (one symmetric sweep from zero) as ONE march (k_sgs_march)
     int march_variant = 1;                          // bit 0: k_mg_march_pre with 2 rows in flight and 4 CTAs/SM (default) instead of 4 rows and 3 CTAs/SM
     bool march = true;                              // big levels: PRE / POST / PLAIN as register marches (kernels_march.inl); 0 = shared-memory tiles
@@ -625,6 +626,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
     if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "fast_r0") { ctx->fast_r0 = value != 0.0; return IMPEC_OK; }
     if (k == "sgs_march") { ctx->sgs_march = value != 0.0; return IMPEC_OK; }
     if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
@@ -1216,14 +1218,21 @@ static double q_test_host(const impec_params &P, double x, double y) {
 // PCG exactly as HYPRE's struct PCG is configured upstream (src/MGSolver.cpp:597-603: TwoNorm, RelChange off, zero
 // initial guess): stop when <r,r>/<b,b> < eps^2 with r the RECURRENCE residual.  On entry: rhs and x are set, the
 // partial sums of <b,b> are already reduced into scal[S_BIPROD].  The preconditioner is one multigrid cycle C.
-static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, double eps, impec_solve_info *info) {
+// x0_pin_only: the caller guarantees that x is zero except at the pinned cell (the reference's x0 = 0): the initial residual is
+// then a copy of rhs plus a 3 x 3 fix-up around the pin instead of a full residual pass (bit-identical)
+static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, double eps, impec_solve_info *info, bool x0_pin_only = false) {
     const Grid &g = ctx->g;
     const dim3 gr = grid2d(g.N2, g.N1);
     const long long nparts = (long long)gr.x * gr.y;
     const LevelDev &A = C.D[0];
     const dim3 gres = grid2d(g.N2, g.N1 + 2);                    // k_residual also fills one halo row per neighbouring slab
-    TRY(exchange_rows(ctx, x, g, 2));
-    LAUNCH(ctx, k_residual, gres, kBlock, A, rhs, (const double *)x, ctx->r);
+    if (x0_pin_only && ctx->fast_r0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->r, rhs, grid_elems(g) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (A.pin >= 0) LAUNCH(ctx, k_residual_pin_fix, dim3(1), dim3(32), A, rhs, (const double *)x, ctx->r);
+    } else {
+        TRY(exchange_rows(ctx, x, g, 2));
+        LAUNCH(ctx, k_residual, gres, kBlock, A, rhs, (const double *)x, ctx->r);
+    }
     LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->r, ctx->part);
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_IPROD));
     TRY(fetch_scalars(ctx, S_IPROD, 3));                         // S_IPROD .. S_BIPROD
@@ -1342,7 +1351,7 @@ extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info
         LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
     }
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
-    return pcg_solve(ctx, C, ctx->rhs, x, eps, info);
+    return pcg_solve(ctx, C, ctx->rhs, x, eps, info, !ctx->warm_start);
 }
 
 // ------------------------------------------------------------------------------------------------ a12 velocities
@@ -1513,7 +1522,7 @@ extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info
     double *x = ctx->ta;
     LAUNCH_COOP(ctx, k_cn_rhs, gr, kBlock, A, (const double *)ctx->c, ctx->rhs, x, ctx->part);
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
-    const int rc = pcg_solve(ctx, C, ctx->rhs, x, ctx->P.para_eps, info);
+    const int rc = pcg_solve(ctx, C, ctx->rhs, x, ctx->P.para_eps, info, true);      // k_cn_rhs zeroed x (x0 = 0 as upstream)
     if (rc != IMPEC_OK && rc != IMPEC_ERR_NOCONV) return rc;
     LAUNCH(ctx, k_copy_interior, gr, kBlock, g, (const double *)x, ctx->c);     // MapHYPREVectorToVertex: interior only
     return rc;

@@ -209,6 +209,18 @@ __global__ void __launch_bounds__(256) k_residual(LevelDev L, const double *__re
     r[k] = ((long long)k == L.pin) ? 0. : f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k));
 }
 
+// Residual r = f - S x when x is zero except at the pinned cell: r equals f everywhere but at the pin (0) and its 8 neighbours, so
+// the host copies f and this kernel (9 threads) evaluates k_residual's expression on the 3 x 3 block around the pin.
+__global__ void k_residual_pin_fix(LevelDev L, const double *__restrict__ f, const double *__restrict__ x, double *__restrict__ r) {
+    const int t = threadIdx.x;
+    if (t >= 9 || L.pin < 0) return;
+    const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
+    const int i = pi + t / 3 - 1, j = pj + t % 3 - 1;
+    if (i < 0 || i >= L.g.N1 || j < 0 || j >= L.g.N2) return;
+    const size_t k = gidx(L.g, i, j);
+    r[k] = ((long long)k == L.pin) ? 0. : f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k));
+}
+
 // || f - S x ||^2 without storing the residual (the true residual reported with every solve): 40 B/cell in one pass instead of
 // k_residual + k_dot (48 + 16).  A CTA walks `rows` rows of a 32-column strip, so there are few partial sums.
 __global__ void __launch_bounds__(256) k_residual_norm(LevelDev L, const double *__restrict__ f, const double *__restrict__ x, double *__restrict__ part, int rows) {

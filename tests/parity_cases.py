@@ -400,6 +400,23 @@ def check_sgs_march(emulated, N1=64, N2=96, stype=O.DIAGONAL):
     assert np.abs(out[0][1] - out[1][1]).max() <= 1e-13, np.abs(out[0][1] - out[1][1]).max()
 
 
+def check_fast_initial_residual(emulated, N1=48, N2=80, stype=O.DIAGONAL, eps=1e-10):
+    """x0 = 0 (the reference's start): the initial PCG residual as a copy of the right-hand side plus a 3 x 3 fix-up around the
+    pinned cell must give the very same solve as the full residual pass -- bit for bit."""
+    base, Po, c, q = production_case(N1, N2, stype=stype, eps=eps)
+    Pi = I.default_params(emulated=emulated, **base)
+    res = []
+    for fast in (1, 0):
+        ctx = I.Context(Pi, emulated=emulated)
+        ctx.set_option("fast_r0", fast)
+        ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries()
+        info = ctx.pressure_solve()
+        res.append((info.iterations, info.relres, ctx.download_p()))
+        ctx.close()
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+    assert np.array_equal(res[0][2], res[1][2])
+
+
 def check_small_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
     """The single-CTA bottom-of-hierarchy kernel (kernels_small.inl, levels of <= 4096 cells) against the tile kernels
     on the same levels: same arithmetic per cell, so one cycle agrees to rounding (<= 1e-13 relative), with FP64 and

@@ -50,4 +50,5 @@ def test_matvec_march_odd_columns(): pc.check_matvec_variants(True, 20, 31, eps=
 def test_march_vs_tile_kernels(): pc.check_march_vs_tiles(True)
 def test_persistent_tail_vs_launches(): pc.check_persistent_tail(True)
 def test_sgs_march_vs_sweeps(): pc.check_sgs_march(True)
+def test_fast_initial_residual(): pc.check_fast_initial_residual(True)
 def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(True, 256, 384)

@@ -41,6 +41,7 @@ def test_matvec_march_odd_columns(): pc.check_matvec_variants(False, 20, 31, eps
 def test_march_vs_tile_kernels(): pc.check_march_vs_tiles(False, 1024, 1536)
 def test_persistent_tail_vs_launches(): pc.check_persistent_tail(False, 2048, 3072)
 def test_sgs_march_vs_sweeps(): pc.check_sgs_march(False, 1024, 1536)
+def test_fast_initial_residual(): pc.check_fast_initial_residual(False, 1024, 1536)
 def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(False, 1024, 1536)
 
 
