@@ -51,6 +51,10 @@ class Context:
             pass
 
     def _chk(self, rc):
+        if rc > 0:          # IMPEC_WARN_NOCONV: the call completed with the last iterate (upstream never checks convergence)
+            import warnings
+            warnings.warn("impec: %s" % self.L.impec_last_error(self._h).decode())
+            return
         if rc != 0:
             raise ImpecError("impec call failed (%d): %s" % (rc, self.L.impec_last_error(self._h).decode()))
 

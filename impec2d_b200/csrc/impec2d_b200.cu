@@ -545,7 +545,10 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
         const char *e = getenv("IMPEC_DIST_MIN_CELLS");
         const double min_cells = e ? atof(e) : 4.0e6;
         int rows = P->N1, cols = P->N2;
-        while (ctx->Ld < nl - 1 && rows % (2 * nranks) == 0 && rows / nranks >= 8 && (double)rows * cols >= min_cells) { ctx->Ld++; rows /= 2; cols /= 2; }
+        // Level 0 is ALWAYS distributed on a multi-rank context (its vectors alias the slab-sized PCG vectors); min_cells applies
+        // from level 1 on.
+        while (ctx->Ld < nl - 1 && rows % (2 * nranks) == 0 && rows / nranks >= 8 && (ctx->Ld == 0 || (double)rows * cols >= min_cells)) { ctx->Ld++; rows /= 2; cols /= 2; }
+        if (ctx->Ld < 1) return fail(ctx, IMPEC_ERR_ARG, "a %d x %d grid on %d ranks leaves no coarser level to replicate (multigrid needs >= 2 levels on slabs)", P->N1, P->N2, nranks);
     }
     for (int l = 0, n1 = P->N1, n2 = P->N2; l < nl; l++, n1 /= 2, n2 /= 2) {
         Level &L = ctx->L[l];
@@ -640,6 +643,10 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "max_iter") { ctx->P.max_iter = (int)value; return IMPEC_OK; }
+    if (k == "hyper_method") {                   // MUSCL / upwind is a property of the calling solver object, not of the context
+        if ((int)value != IMPEC_MUSCL && (int)value != IMPEC_UPWIND) return fail(ctx, IMPEC_ERR_ARG, "hyper_method must be IMPEC_MUSCL or IMPEC_UPWIND");
+        ctx->P.hyper_method = (int)value; return IMPEC_OK;
+    }
     return fail(ctx, IMPEC_ERR_ARG, "unknown option '%s'", k.c_str());
 }
 
@@ -1087,6 +1094,7 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
     const int nl = C.nl;
     const bool fused = ctx->fused;
     if (dot_nparts) *dot_nparts = 0;
+    if (!fused && ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "the per-colour (mg_fused = 0) path is single-GPU only");
     if (fused && ctx->use_small && l > 0 && l < nl - 1 && l > C.w_to && !L.dist && nl - l <= SM_MAXLEV && (long long)L.g.N1 * L.g.N2 <= SM_MAXCELLS && C.D[l].mass == 0.) {
         // bottom of the hierarchy: the whole V-cycle over levels l .. nl-1 in one single-CTA launch
         SmallArgs A; A.nl = nl - l; A.ncoarse = C.ncoarse; A.xout = ctx->L[l].x;
@@ -1158,7 +1166,6 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
         TRY(fused_post(C, l, f, dot_part, dot_nparts));               // prolong + correct + post-smooth (+ <f,x>)
         return IMPEC_OK;
     }
-    if (ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "the per-colour (mg_fused = 0) path is single-GPU only");
     TRY(smooth(C, l, f, x, true, true));
     for (int gc = 0; gc < gamma; gc++) {
         LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1), kBlock, C.D[l], f, x, L.r);
@@ -1321,7 +1328,9 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         info->true_relres = bi_prod > 0. ? sqrt(ctx->h_scal[S_TMP] / bi_prod) : 0.;
     }
     if (info && converged == 2) info->converged = 2;          // stopped by the stagnation guard at the attainable accuracy
-    return converged ? IMPEC_OK : fail(ctx, IMPEC_ERR_NOCONV, "PCG did not reach eps=%g in %d iterations (relres %g)", eps, it, sqrt(i_prod / bi_prod));
+    // Not converged within max_iter: the reference never checks HYPRE's convergence and carries on with the last iterate
+    // (src/MGSolver.cpp:612-622), so this is a WARNING (positive code), reported through info->converged = 0 as well.
+    return converged ? IMPEC_OK : fail(ctx, IMPEC_WARN_NOCONV, "PCG did not reach eps=%g in %d iterations (relres %g)", eps, it, sqrt(i_prod / bi_prod));
 }
 
 extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info *info) {
@@ -1346,7 +1355,7 @@ extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info
         LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->p, ctx->d);
         LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
         LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->d, x);
-        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), x + A.pin, p_pin);
+        if (A.pin >= 0) LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), x + A.pin, p_pin);      // only the rank that owns cell (1,1)
     } else {
         LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
     }
@@ -1523,7 +1532,7 @@ extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info
     LAUNCH_COOP(ctx, k_cn_rhs, gr, kBlock, A, (const double *)ctx->c, ctx->rhs, x, ctx->part);
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
     const int rc = pcg_solve(ctx, C, ctx->rhs, x, ctx->P.para_eps, info, true);      // k_cn_rhs zeroed x (x0 = 0 as upstream)
-    if (rc != IMPEC_OK && rc != IMPEC_ERR_NOCONV) return rc;
+    if (rc < 0) return rc;                                                      // IMPEC_WARN_NOCONV: keep the last iterate as upstream does
     LAUNCH(ctx, k_copy_interior, gr, kBlock, g, (const double *)x, ctx->c);     // MapHYPREVectorToVertex: interior only
     return rc;
 }
@@ -1561,17 +1570,30 @@ extern "C" int impec_project_to_diagonal(impec_ctx *ctx, int field, double *out_
 // produced mass and the sweep parity and is unusable at 16384^2 (268 M text lines).  A checkpoint here is the exact device state
 // of this rank: header + the padded c, p, u, v arrays (ghost / halo rows included) + produced mass + sweep parity, so a
 // restarted run continues BIT FOR BIT.  Multi-GPU: one file per rank (the caller chooses the names).
-struct CkptHeader { char magic[8]; int version, N1, N2, g, rank, nranks, ld, rows; long long step; double t, outflux; int prev_first_sweep, pad; };
+// Version 2: little-endian marker and an FNV-1a hash of the physics in impec_params (a checkpoint must not be continued with other
+// viscosities, bounds, ... by accident); written to "<path>.tmp" and renamed into place, so a crash during a save never destroys
+// the previous restart point.
+struct CkptHeader { char magic[8]; int version, N1, N2, g, rank, nranks, ld, rows; long long step; double t, outflux; int prev_first_sweep; unsigned endian;
+                    unsigned long long params_hash; };
+static unsigned long long ckpt_params_hash(const impec_params &P) {
+    unsigned long long h = 1469598103934665603ULL;
+    auto mix = [&](const void *p, size_t n) { const unsigned char *b = (const unsigned char *)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; } };
+    const double d[] = {P.x_lb, P.x_ub, P.y_lb, P.y_ub, P.mu_res, P.mu_inj, P.nu, P.porosity, P.inj_fluid_conc, P.alpha_l, P.alpha_t};
+    const int i[] = {P.N1, P.N2, P.g, P.avgproc, P.is_test, P.testno, P.stype, P.diffusion, P.dim_splitting};
+    mix(d, sizeof(d)); mix(i, sizeof(i));
+    return h;
+}
 extern "C" int impec_checkpoint_save(impec_ctx *ctx, const char *path, double t, long long step) {
     if (!path) return fail(ctx, IMPEC_ERR_ARG, "null path");
     const Grid &g = ctx->g;
     CkptHeader H; memset(&H, 0, sizeof(H));
-    memcpy(H.magic, "IMPECCK1", 8); H.version = 1; H.N1 = ctx->P.N1; H.N2 = ctx->P.N2; H.g = ctx->P.g; H.rank = ctx->rank; H.nranks = ctx->nranks;
+    memcpy(H.magic, "IMPECCK1", 8); H.version = 2; H.endian = 0x01020304u; H.params_hash = ckpt_params_hash(ctx->P); H.N1 = ctx->P.N1; H.N2 = ctx->P.N2; H.g = ctx->P.g; H.rank = ctx->rank; H.nranks = ctx->nranks;
     H.ld = g.ld; H.rows = g.rows; H.step = step; H.t = t; H.prev_first_sweep = ctx->prev_first_sweep;
     CUDA_TRY(ctx, cudaMemcpyAsync(&H.outflux, ctx->scal + S_OUTFLUX, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    FILE *f = fopen(path, "wb");
-    if (!f) return fail(ctx, IMPEC_ERR_ARG, "cannot open %s for writing", path);
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(ctx, IMPEC_ERR_ARG, "cannot open %s for writing", tmp.c_str());
     bool ok = fwrite(&H, sizeof(H), 1, f) == 1;
     const size_t n = grid_elems(g);
     std::vector<double> buf(n);
@@ -1579,8 +1601,11 @@ extern "C" int impec_checkpoint_save(impec_ctx *ctx, const char *path, double t,
         if (cudaMemcpyAsync(buf.data(), fld, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ok = false; break; }
         ok = ok && fwrite(buf.data(), sizeof(double), n, f) == n;
     }
+    ok = (fflush(f) == 0) && ok;
     ok = (fclose(f) == 0) && ok;
-    return ok ? IMPEC_OK : fail(ctx, IMPEC_ERR_CUDA, "writing checkpoint %s failed", path);
+    if (!ok) { remove(tmp.c_str()); return fail(ctx, IMPEC_ERR_CUDA, "writing checkpoint %s failed", path); }
+    if (rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(ctx, IMPEC_ERR_ARG, "cannot move %s into place", path); }
+    return IMPEC_OK;
 }
 extern "C" int impec_checkpoint_load(impec_ctx *ctx, const char *path, double *t, long long *step) {
     if (!path) return fail(ctx, IMPEC_ERR_ARG, "null path");
@@ -1588,7 +1613,8 @@ extern "C" int impec_checkpoint_load(impec_ctx *ctx, const char *path, double *t
     FILE *f = fopen(path, "rb");
     if (!f) return fail(ctx, IMPEC_ERR_ARG, "cannot open %s", path);
     CkptHeader H;
-    if (fread(&H, sizeof(H), 1, f) != 1 || memcmp(H.magic, "IMPECCK1", 8) != 0 || H.version != 1) { fclose(f); return fail(ctx, IMPEC_ERR_ARG, "%s is not an impec2d_b200 checkpoint", path); }
+    if (fread(&H, sizeof(H), 1, f) != 1 || memcmp(H.magic, "IMPECCK1", 8) != 0 || H.version != 2 || H.endian != 0x01020304u) { fclose(f); return fail(ctx, IMPEC_ERR_ARG, "%s is not an impec2d_b200 (version 2, same byte order) checkpoint", path); }
+    if (H.params_hash != ckpt_params_hash(ctx->P)) { fclose(f); return fail(ctx, IMPEC_ERR_ARG, "checkpoint %s was written with different physical parameters (bounds, viscosities, nu, porosity, ...)", path); }
     if (H.N1 != ctx->P.N1 || H.N2 != ctx->P.N2 || H.g != ctx->P.g || H.rank != ctx->rank || H.nranks != ctx->nranks || H.ld != g.ld || H.rows != g.rows) {
         fclose(f);
         return fail(ctx, IMPEC_ERR_ARG, "checkpoint %s is for a %d x %d grid on rank %d of %d; this context is %d x %d on rank %d of %d", path, H.N1, H.N2, H.rank, H.nranks,
@@ -1612,28 +1638,33 @@ extern "C" int impec_checkpoint_load(impec_ctx *ctx, const char *path, double *t
 }
 
 // ------------------------------------------------------------------------------------------------ a14 transport step
+// A solver that stops at max_iter (IMPEC_WARN_NOCONV) does not abort the step: the step is finished with the last iterate, as
+// upstream, and the warning is returned at the end.
+#define TRY_WARN(call, warn) do { int rc_ = (call); if (rc_ < 0) return rc_; if (rc_ > 0) (warn) = rc_; } while (0)
 extern "C" int impec_transport_step(impec_ctx *ctx, double dt) {
+    int warn = IMPEC_OK;
     TRY(impec_source_split(ctx, 0.5 * dt));
     TRY(impec_fill_boundaries(ctx));
-    if (ctx->P.diffusion) TRY(impec_diffusion_split(ctx, 0.5 * dt, nullptr));
+    if (ctx->P.diffusion) TRY_WARN(impec_diffusion_split(ctx, 0.5 * dt, nullptr), warn);
     TRY(impec_advect_split(ctx, dt));
     TRY(impec_source_split(ctx, 0.5 * dt));
     TRY(impec_fill_boundaries(ctx));
-    if (ctx->P.diffusion) TRY(impec_diffusion_split(ctx, 0.5 * dt, nullptr));
-    return IMPEC_OK;
+    if (ctx->P.diffusion) TRY_WARN(impec_diffusion_split(ctx, 0.5 * dt, nullptr), warn);
+    return warn;
 }
 
 // ------------------------------------------------------------------------------------------------ a20 IMPES step
 extern "C" int impec_impes_step(impec_ctx *ctx, double t, double t_next_output, double *dt_used, impec_solve_info *info) {
+    int warn = IMPEC_OK;
     TRY(impec_fill_boundaries(ctx));
-    TRY(impec_pressure_solve(ctx, ctx->P.eps, info));
+    TRY_WARN(impec_pressure_solve(ctx, ctx->P.eps, info), warn);
     TRY(impec_calc_velocities(ctx));
     double dt = 0.;
     TRY(impec_max_stable_dt(ctx, &dt));
     if (t_next_output > t && t + dt >= t_next_output) dt = t_next_output - t;      // src/Impec2DSolver.cpp:375-378
-    TRY(impec_transport_step(ctx, dt));
+    TRY_WARN(impec_transport_step(ctx, dt), warn);
     if (dt_used) *dt_used = dt;
-    return IMPEC_OK;
+    return warn;
 }
 
 extern "C" int impec_diagnostics(impec_ctx *ctx, impec_diag *out) {

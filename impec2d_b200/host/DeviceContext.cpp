@@ -1,5 +1,7 @@
 #include "DeviceContext.h"
 #include <map>
+#include <set>
+#include <vector>
 #include <cstring>
 #include <cstdlib>
 #include <iostream>
@@ -7,10 +9,16 @@
 namespace {
 struct Entry { impec_ctx *ctx = nullptr; impec_params P; const double *q_uploaded = nullptr; };
 std::map<SimParams *, Entry> g_ctx;
+// arrays currently bound to a context: a context is never destroyed under them (DeviceBound::UnbindAll)
+std::set<const DeviceBound *> &bound_set() { static std::set<const DeviceBound *> s; return s; }
 }
 
 void DeviceContext::Check(impec_ctx *ctx, int rc, const char *what) {
     if (rc == IMPEC_OK) return;
+    if (rc > 0) {                                        // warning (a solver stopped at max_iter): upstream never checks, we say so and go on
+        std::cerr << "impec2d_b200: warning from " << what << ": " << impec_last_error(ctx) << std::endl;
+        return;
+    }
     std::cerr << "impec2d_b200: " << what << " failed (" << rc << "): " << impec_last_error(ctx) << std::endl;
     exit(1);                                             // the reference's error convention for fatal errors
 }
@@ -27,7 +35,9 @@ impec_params DeviceContext::ToParams(const SimParams *sp) {
     P.diffusion = sp->diffusion ? 1 : 0; P.alpha_l = sp->alpha_l; P.alpha_t = sp->alpha_t; P.dt_diff_limit = sp->dt_diff_limit;
     P.ptype = sp->ptype == CRANKNICOLSON ? IMPEC_CRANKNICOLSON : IMPEC_EXPLICIT;
     P.eps = sp->eps; P.para_eps = sp->para_eps;
-    P.hyper_method = sp->hmtype == UPWINDSPLIT ? IMPEC_UPWIND : IMPEC_MUSCL;
+    // hyper_method: the reference reads the key but hard-wires MUSCLSplitSolver (src/Impec2DSolver.cpp:132); here the method
+    // belongs to the solver OBJECT and is passed per call (DeviceContext::SetMethod), so it is not part of the context identity
+    P.hyper_method = IMPEC_MUSCL;
     switch (sp->dim_splitting) {
     case ALTERNATING: P.dim_splitting = IMPEC_ALTERNATING; break;
     case X_FIRST: P.dim_splitting = IMPEC_X_FIRST; break;
@@ -42,7 +52,7 @@ impec_ctx *DeviceContext::Get(SimParams *sp) {
     Entry &e = g_ctx[sp];
     const impec_params P = ToParams(sp);
     if (e.ctx && std::memcmp(&P, &e.P, sizeof(P)) == 0) return e.ctx;
-    if (e.ctx) { impec_ctx_destroy(e.ctx); e.ctx = nullptr; }
+    if (e.ctx) { DeviceBound::UnbindAll(e.ctx); impec_ctx_destroy(e.ctx); e.ctx = nullptr; }   // grid/physics changed: arrays keep their data on the host
     const char *dev = getenv("IMPEC_DEVICE");
     const int rc = impec_ctx_create(&P, dev ? atoi(dev) : 0, 0, 1, nullptr, nullptr, &e.ctx);
     Check(e.ctx, rc, "impec_ctx_create");
@@ -53,9 +63,11 @@ impec_ctx *DeviceContext::Get(SimParams *sp) {
 void DeviceContext::Release(SimParams *sp) {
     auto it = g_ctx.find(sp);
     if (it == g_ctx.end()) return;
-    if (it->second.ctx) impec_ctx_destroy(it->second.ctx);
+    if (it->second.ctx) { DeviceBound::UnbindAll(it->second.ctx); impec_ctx_destroy(it->second.ctx); }
     g_ctx.erase(it);
 }
+
+void DeviceContext::SetMethod(impec_ctx *ctx, int method) { Check(ctx, impec_set_option(ctx, "hyper_method", (double)method), "impec_set_option(hyper_method)"); }
 
 void DeviceContext::InvalidateSource(SimParams *sp) { g_ctx[sp].q_uploaded = nullptr; }
 
@@ -73,6 +85,14 @@ void DeviceContext::Use(impec_ctx *ctx, const Array2d *c, const Array2d *p, cons
 void DeviceBound::Bind(impec_ctx *ctx, int field) const {
     if (ctx_ && ctx_ != ctx) pull();
     ctx_ = ctx; field_ = field; host_dirty_ = true; dev_newer_ = false;
+    bound_set().insert(this);
+}
+void DeviceBound::Unbind() const { pull(); ctx_ = nullptr; field_ = FIELD_NONE; bound_set().erase(this); }
+DeviceBound::~DeviceBound() { bound_set().erase(this); }
+void DeviceBound::UnbindAll(const impec_ctx *ctx) {
+    std::vector<const DeviceBound *> mine;
+    for (const DeviceBound *b : bound_set()) if (b->ctx_ == ctx) mine.push_back(b);
+    for (const DeviceBound *b : mine) b->Unbind();
 }
 void DeviceBound::pull() const {
     if (!dev_newer_ || !ctx_) return;

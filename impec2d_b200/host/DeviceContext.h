@@ -15,6 +15,7 @@ public:
     // make the device copies current for an operation that reads them
     static void Use(impec_ctx *ctx, const Array2d *c, const Array2d *p, const Array3d *v, const double *q, SimParams *sp);
     static void InvalidateSource(SimParams *sp);          // call after changing q in place
-    static void Check(impec_ctx *ctx, int rc, const char *what);
+    static void Check(impec_ctx *ctx, int rc, const char *what);   // negative: fatal (exit 1, upstream's convention); positive: warning
+    static void SetMethod(impec_ctx *ctx, int method);            // MUSCL / upwind of the calling solver object, per call
 };
 #endif

@@ -31,9 +31,14 @@ protected:
     virtual double *raw() const = 0;
     void pull() const;                 // download if the device copy is newer
 public:
-    virtual ~DeviceBound() {}
+    DeviceBound() {}
+    // a copy is a plain host array: the source is brought up to date first, the binding is NOT inherited
+    DeviceBound(const DeviceBound &o) { o.pull(); }
+    DeviceBound &operator=(const DeviceBound &o) { if (this != &o) { o.pull(); host_dirty_ = true; dev_newer_ = false; } return *this; }
+    virtual ~DeviceBound();                       // leaves the registry of bound arrays (DeviceContext.cpp)
     void Bind(impec_ctx *ctx, int field) const;   // (re)bind; a new binding starts with the host copy as truth
-    void Unbind() const { pull(); ctx_ = nullptr; field_ = FIELD_NONE; }
+    void Unbind() const;                          // download if the device copy is newer, then detach
+    static void UnbindAll(const impec_ctx *ctx);  // detach every array bound to ctx (called before ctx is destroyed)
     void SyncToDevice() const;         // upload if the host copy is dirty
     void MarkDeviceNewer() const { dev_newer_ = true; host_dirty_ = false; }
     bool BoundTo(const impec_ctx *c) const { return ctx_ == c; }

@@ -54,8 +54,7 @@ bool MGSolver::Solve_Elliptic_cc_to_c(const Array2d &c_c, int c_bounds, Array2d 
     const int rc = impec_pressure_solve(ctx, sp->eps, &info);
     last_its = info.iterations; last_relres = info.relres; last_true_relres = info.true_relres;
     p_c.MarkDeviceNewer();
-    if (rc == IMPEC_ERR_NOCONV) { cerr << "MGSolver: " << impec_last_error(ctx) << endl; return true; }   // upstream never detects non-convergence
-    DeviceContext::Check(ctx, rc, "impec_pressure_solve");
+    DeviceContext::Check(ctx, rc, "impec_pressure_solve");   // IMPEC_WARN_NOCONV is only reported: upstream never detects non-convergence
     return true;
 }
 bool MGSolver::Solve_Parabolic_cc_to_c(Array2d &c_c, int c_bounds, const Array3d &v, int v_bounds, Array2d const *const ls, int ls_bounds, const double dt) {
@@ -184,18 +183,17 @@ bool HyperbolicSolver::DiffusionSplitCN(Array2d &c, const Array3d &v, const doub
 }
 
 // ------------------------------------------------------------------ HyperbolicSplitSolver (src/HyperbolicSplitSolver.cpp:51-198)
-static void sync_method(SimParams *sp, int method) { sp->hmtype = method == IMPEC_UPWIND ? UPWINDSPLIT : MUSCL; }
 bool HyperbolicSplitSolver::Advect_X(Array2d &c, const Array3d &v, const double dt) {
-    sync_method(sp, MethodId());
     impec_ctx *ctx = DeviceContext::Get(sp);
+    DeviceContext::SetMethod(ctx, MethodId());
     DeviceContext::Use(ctx, &c, nullptr, &v, nullptr, sp);
     DeviceContext::Check(ctx, impec_advect_x(ctx, dt), "impec_advect_x");
     c.MarkDeviceNewer();
     return true;
 }
 bool HyperbolicSplitSolver::Advect_Y(Array2d &c, const Array3d &v, const double dt) {
-    sync_method(sp, MethodId());
     impec_ctx *ctx = DeviceContext::Get(sp);
+    DeviceContext::SetMethod(ctx, MethodId());
     DeviceContext::Use(ctx, &c, nullptr, &v, nullptr, sp);
     DeviceContext::Check(ctx, impec_advect_y(ctx, dt), "impec_advect_y");
     c.MarkDeviceNewer();
@@ -203,8 +201,8 @@ bool HyperbolicSplitSolver::Advect_Y(Array2d &c, const Array3d &v, const double 
 }
 bool HyperbolicSplitSolver::AdvectSplit(Array2d &c, const Array3d &v, double const *const q, const double dt) {
     (void)q;
-    sync_method(sp, MethodId());
     impec_ctx *ctx = DeviceContext::Get(sp);
+    DeviceContext::SetMethod(ctx, MethodId());
     DeviceContext::Use(ctx, &c, nullptr, &v, nullptr, sp);
     DeviceContext::Check(ctx, impec_advect_split(ctx, dt), "impec_advect_split");
     c.MarkDeviceNewer();
@@ -212,8 +210,8 @@ bool HyperbolicSplitSolver::AdvectSplit(Array2d &c, const Array3d &v, double con
 }
 // S(dt/2) [D(dt/2)] A(dt) S(dt/2) [D(dt/2)] in one call (src/HyperbolicSplitSolver.cpp:162-198)
 bool HyperbolicSplitSolver::Solve(Array2d &c, const Array3d &v, double const *const q, const double dt) {
-    sync_method(sp, MethodId());
     impec_ctx *ctx = DeviceContext::Get(sp);
+    DeviceContext::SetMethod(ctx, MethodId());
     DeviceContext::Use(ctx, &c, nullptr, &v, q, sp);
     DeviceContext::Check(ctx, impec_transport_step(ctx, dt), "impec_transport_step");
     c.MarkDeviceNewer();

@@ -15,7 +15,7 @@
  *       q          : N1*N2 doubles, q[i*N2+j]
  *   - one context per process / GPU; calls on one context must be serialised by the caller; all
  *     device work is enqueued on the context's stream and calls that return scalars synchronise it
- *   - return value: 0 = ok, negative = error (impec_last_error gives the text); never exit()
+ *   - return value: 0 = ok, negative = error, positive = warning, call completed (impec_last_error gives the text); never exit()
  *   - there is NO CPU fallback: creating a context without a CUDA device fails
  */
 #ifndef IMPEC2D_B200_H_
@@ -25,10 +25,12 @@ extern "C" {
 #endif
 
 #define IMPEC_OK 0
+#define IMPEC_WARN_NOCONV 1        /* POSITIVE = warning: a solver stopped at max_iter; the call COMPLETED with the last iterate,
+                                      as upstream (src/MGSolver.cpp:612-622 never checks convergence); info->converged = 0 */
 #define IMPEC_ERR_ARG (-1)
 #define IMPEC_ERR_CUDA (-2)
 #define IMPEC_ERR_UNSUPPORTED (-3)
-#define IMPEC_ERR_NOCONV (-4)
+#define IMPEC_ERR_NOCONV (-4)      /* the solver broke down (NaN): fatal                                              */
 #define IMPEC_ERR_NCCL (-5)
 
 /* enum values follow src/SimParams.h:13-27 */

@@ -282,8 +282,13 @@ void orc_stencil_cell(const orc_params *P, const double *c, int i, int j, double
 static void fold_row(int N1, int N2, int i, int j, double coef[9]) {
     double out[9];
     for (int e = 0; e < 9; e++) out[e] = 0.;
-    /* accumulate in the reference's written order: own entry first, then folded ones in C,W,S,SW.. order */
-    static const int order[9] = { eC, eW, eE, eS, eN, eSW, eSE, eNW, eNE };
+    /* Accumulate in the reference's WRITTEN order (floating-point addition is not associative): the only sums of more than two
+     * terms are the four corner diagonals, C+W+S+SW (:431, 1190), C+W+N+NW (:454, 1219), C+N+NE+E (:478, 1249), C+S+E+SE
+     * (:501, 1277).  Checked bit for bit against the compiled reference (tests/test_oracle_vs_ref.py). */
+    static const int order_lo[9] = { eC, eW, eE, eS, eN, eSW, eSE, eNW, eNE };      /* corners (0,0) and (0,N2-1), all edges */
+    static const int order_hh[9] = { eC, eN, eNE, eE, eW, eS, eSW, eSE, eNW };      /* corner (N1-1,N2-1) */
+    static const int order_hl[9] = { eC, eS, eE, eSE, eW, eN, eSW, eNW, eNE };      /* corner (N1-1,0)    */
+    const int *order = (i == N1 - 1 && j == N2 - 1) ? order_hh : ((i == N1 - 1 && j == 0) ? order_hl : order_lo);
     for (int k = 0; k < 9; k++) {
         const int e = order[k];
         int ii = i + OFF[e][0], jj = j + OFF[e][1];

@@ -6,18 +6,28 @@
  *
  * It is a plain-C restatement of what pw359/Impec2D computes on the path named
  * in SURVEY.md section 8(a).  Each function cites the reference file:line it
- * follows (paths relative to /root/reference/).  The reference itself cannot be
- * built here (needs MPI, HYPRE, blitz++, libconfig++), and its
- * linear algebra lives in HYPRE (hypre-2.8.0b, INSTALL:44-46), which is not in
- * the tree.  The PCG loop below restates HYPRE's published struct-PCG stopping
- * rule (two-norm, relative, recurrence residual); the preconditioner is a
- * geometric multigrid cycle of our own design in place of SMG.
+ * follows (paths relative to /root/reference/).
  *
- * PARITY PINNING: converged-solution parity is pinned by the reference's own
- * known answers (manufactured p = cos x cos y, orders 2.00/1.99; periodic
- * advection order ~1.85-1.88; exact zero no-flow boundary velocity) -- see
- * tests/test_oracle_*.py.  Iteration-level parity with HYPRE SMG-PCG is
- * UNPINNED (no HYPRE source, no stored iterates anywhere in the reference).
+ * PARITY PINNING -- pinned to the reference itself:
+ *   * oracle/_ref/libimpec_ref.so is the reference's own translation units
+ *     (src/*.cpp, compiled UNMODIFIED by oracle/Makefile against the shim headers
+ *     in oracle/ref_shim/ for blitz, libconfig++, MPI and HYPRE, none of which is
+ *     installed here).  tests/test_oracle_vs_ref.py runs the reference's objects
+ *     and this oracle on the same inputs: ghost fills, wells, mobilities, the
+ *     9-entry matrix with Neumann folding and pin, right-hand sides, Darcy
+ *     velocity, time step, TR source step, MUSCL/upwind fluxes, all five
+ *     splittings, the Crank-Nicolson matrix/right-hand side and the projection
+ *     agree BIT FOR BIT; solves agree to 1e-10.
+ *   * tests/golden/ref_vectors.npz holds outputs of that compiled reference
+ *     (and of its own main() on elliptic_test.cfg / hyperbolic_test.cfg); the
+ *     oracle is checked against them wherever the tests run.
+ *   * the reference's analytic known answers (orders 2.00 / 1.85-1.88).
+ * What stays UNPINNED: iteration-level parity with HYPRE's SMG-PCG.  HYPRE
+ * (hypre-2.8.0b, INSTALL:44-46) is a third-party library outside the reference
+ * tree; the PCG loop below restates its published struct-PCG stopping rule
+ * (two-norm, relative, recurrence residual) with a geometric multigrid cycle of
+ * our own design in place of SMG.  Any solver reaching the same tolerance on the
+ * same matrix is conformant.
  *
  * Array conventions (src/Impec2DSolver.cpp:151-182, src/GenSimDefs.h:25-31):
  *   scalar fields c,p : (N1+2g) x (N2+2g) doubles, C order, j fastest, ghost g

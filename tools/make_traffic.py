@@ -1,4 +1,4 @@
-# dram bytes per launch of the hot kernels from an ncu summary (scratch/ncu_summary.py output) -> profiles/<tag>_traffic.json
+# dram bytes per launch of the hot kernels from an ncu summary (tools/ncu_summary.py output) -> profiles/<tag>_traffic.json
 import json, re, sys
 txt = open(sys.argv[1]).read()
 out = {"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 16384^2 fine level, one B200 (%s)" % sys.argv[1], "grid": [16384, 16384]}
