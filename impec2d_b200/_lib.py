@@ -50,6 +50,10 @@ class Diag(C.Structure):
                 ("total_mass_outflux", C.c_double), ("c_min", C.c_double), ("c_max", C.c_double)]
 
 
+class IntegralDiag(C.Structure):
+    _fields_ = [("produced_fraction", C.c_double), ("mixing_zone_length", C.c_double), ("mixing_zone_cells", C.c_double), ("mass_in_place", C.c_double)]
+
+
 class SolveInfo(C.Structure):
     _fields_ = [("iterations", C.c_int), ("relres", C.c_double), ("true_relres", C.c_double), ("converged", C.c_int)]
 
@@ -60,11 +64,11 @@ EXPORTS = [
     "impec_upload_velocity", "impec_download_c", "impec_download_p", "impec_download_velocity", "impec_field_layout",
     "impec_field_dev", "impec_set_q_dev_changed", "impec_fill_boundaries", "impec_pressure_solve", "impec_calc_velocities",
     "impec_max_stable_dt", "impec_source_split", "impec_advect_x", "impec_advect_y", "impec_advect_split",
-    "impec_diffusion_split", "impec_transport_step", "impec_impes_step", "impec_diagnostics", "impec_build_operator",
+    "impec_diffusion_split", "impec_transport_step", "impec_impes_step", "impec_diagnostics", "impec_integral_diagnostics", "impec_build_operator",
     "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_reset_state", "impec_set_option",
     "impec_profile_kernel", "impec_init_source", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
     "impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows", "impec_init_source_rows", "impec_synth_state_rows",
-    "impec_comm_backend", "impec_project_dims", "impec_project_to_diagonal", "impec_checkpoint_save", "impec_checkpoint_load",
+    "impec_comm_backend", "impec_transfer_bytes", "impec_project_dims", "impec_project_to_diagonal", "impec_checkpoint_save", "impec_checkpoint_load",
 ]
 
 
@@ -127,6 +131,7 @@ def load(emulated=False):
     L.impec_diffusion_split.argtypes = [vp, d, C.POINTER(SolveInfo)]
     L.impec_impes_step.argtypes = [vp, d, d, dptr, C.POINTER(SolveInfo)]
     L.impec_diagnostics.argtypes = [vp, C.POINTER(Diag)]
+    L.impec_integral_diagnostics.argtypes = [vp, d, d, C.POINTER(IntegralDiag)]
     L.impec_project_dims.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
     L.impec_project_to_diagonal.argtypes = [vp, i, vp]
     L.impec_checkpoint_save.argtypes = [vp, C.c_char_p, d, C.c_longlong]
@@ -140,6 +145,7 @@ def load(emulated=False):
     L.impec_synth_state.argtypes = [C.POINTER(Params), C.c_ulonglong, vp]
     L.impec_ctx_set_comm_callbacks.argtypes = [vp, C.POINTER(CommCallbacks)]
     L.impec_local_rows.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    L.impec_transfer_bytes.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     for n in ("impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows"):
         getattr(L, n).argtypes = [vp, vp]
     L.impec_init_source_rows.argtypes = [C.POINTER(Params), d, d, i, i, i, vp]

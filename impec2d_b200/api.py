@@ -123,6 +123,12 @@ class Context:
         self._chk(self.L.impec_diagnostics(self._h, C.byref(d)))
         return d
 
+    def integral_diagnostics(self, lo=0.1, hi=0.9):
+        """produced fraction, mixing-zone length, mass in place as device reductions (no field download)."""
+        d = _lib.IntegralDiag()
+        self._chk(self.L.impec_integral_diagnostics(self._h, lo, hi, C.byref(d)))
+        return d
+
     def project_to_diagonal(self, field=0):
         """Impec2DSolver::Project: c (field 0) or p (field 1) of a parallel run on the diagonal grid (dN1 x dN2 array)."""
         n1 = C.c_int(); n2 = C.c_int()
@@ -154,6 +160,14 @@ class Context:
     def set_option(self, key, value): self._chk(self.L.impec_set_option(self._h, key.encode(), float(value)))
     def synchronize(self): self._chk(self.L.impec_synchronize(self._h))
     def comm_backend(self): return self.L.impec_comm_backend(self._h).decode()
+
+    def transfer_bytes(self):
+        h = C.c_ulonglong(); d = C.c_ulonglong()
+        self._chk(self.L.impec_transfer_bytes(self._h, C.byref(h), C.byref(d)))
+        return h.value, d.value
+
+    def bytes_h2d(self): return self.transfer_bytes()[0]
+    def bytes_d2h(self): return self.transfer_bytes()[1]
 
     def local_rows(self):
         r0 = C.c_int(); n = C.c_int()

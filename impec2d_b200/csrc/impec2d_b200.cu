@@ -4,6 +4,7 @@
 #include "common.h"
 #include "kernels_transport.inl"
 #include "kernels_pressure.inl"
+#include "kernels_build.inl"
 #include "kernels_fused.inl"
 #include "kernels_march.inl"
 #include "kernels_staged.inl"
@@ -75,8 +76,13 @@ struct impec_ctx {
     bool fused_mid = true;                          // W-cycle revisit: sweep + residual + restriction in one tile kernel (FUSED_MID)
     bool matvec_march = true;                       // PCG direction update + mat-vec as a register march (k_pcg_matvec_march); 0 = shared-memory tiles
     bool sweep_shared = true;                       // MUSCL sweeps evaluate each reconstruction once (k_muscl_x / k_muscl_y); 0 = k_sweep
+    bool vel_march = true;                          // production runs: velocity + CFL reductions from c and p in ONE march (k_velocity_march); 0 = k_velocity + k_dt_reduce
+    bool dt_cached = false;                         // scal[S_DT], scal[S_DT+1] hold the reductions of the current velocity field
+    bool build_fused = true;                        // production runs: c -> links, DINV and FP32 copies in ONE march (kernels_build.inl); 0 = the five-pass build
     bool use_small = true;                          // levels of <= SM_MAXCELLS cells: whole V-cycle in one single-CTA launch (kernels_small.inl)
     long long launches = 0;
+    unsigned long long bytes_h2d = 0, bytes_d2h = 0;   // bytes of the field transfers this context issued (impec_transfer_bytes)
+    double profile_dt = 0.0;                        // time step used by the "transport_step" / "diffusion_split" profiling hooks
     long long march_launches = 0;                   // launches of the marching multigrid kernels (diagnostic, IMPEC_VERBOSE)
     std::string err;
     std::vector<void *> allocs;
@@ -636,6 +642,8 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "matvec_march") { ctx->matvec_march = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_shared") { ctx->sweep_shared = value != 0.0; return IMPEC_OK; }
+    if (k == "vel_march") { ctx->vel_march = value != 0.0; ctx->dt_cached = false; return IMPEC_OK; }
+    if (k == "build_fused") { ctx->build_fused = value != 0.0; ctx->op_valid = false; return IMPEC_OK; }
     if (k == "mg_small") { ctx->use_small = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_persist_tail") { ctx->persist_tail = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
@@ -643,6 +651,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "max_iter") { ctx->P.max_iter = (int)value; return IMPEC_OK; }
+    if (k == "profile_dt") { ctx->profile_dt = value; return IMPEC_OK; }
     if (k == "hyper_method") {                   // MUSCL / upwind is a property of the calling solver object, not of the context
         if ((int)value != IMPEC_MUSCL && (int)value != IMPEC_UPWIND) return fail(ctx, IMPEC_ERR_ARG, "hyper_method must be IMPEC_MUSCL or IMPEC_UPWIND");
         ctx->P.hyper_method = (int)value; return IMPEC_OK;
@@ -656,6 +665,7 @@ static int upload_scalar(impec_ctx *ctx, double *dst, const double *host) {
     const Grid &g = ctx->g; const int ng = ctx->P.g;
     const size_t w = (size_t)(g.N2 + 2 * ng) * sizeof(double);
     CUDA_TRY(ctx, cudaMemcpy2DAsync(dst + gidx(g, -ng, -ng), (size_t)g.ld * sizeof(double), host, w, w, (size_t)(g.N1 + 2 * ng), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->bytes_h2d += w * (size_t)(g.N1 + 2 * ng);
     return IMPEC_OK;
 }
 static int download_scalar(impec_ctx *ctx, const double *src, double *host) {
@@ -663,6 +673,7 @@ static int download_scalar(impec_ctx *ctx, const double *src, double *host) {
     const size_t w = (size_t)(g.N2 + 2 * ng) * sizeof(double);
     CUDA_TRY(ctx, cudaMemcpy2DAsync(host, w, src + gidx(g, -ng, -ng), (size_t)g.ld * sizeof(double), w, (size_t)(g.N1 + 2 * ng), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->bytes_d2h += w * (size_t)(g.N1 + 2 * ng);
     return IMPEC_OK;
 }
 static size_t slab_off(const impec_ctx *ctx) { return (size_t)ctx->g.i_off * (size_t)(ctx->g.N2 + 2 * ctx->P.g); }
@@ -673,28 +684,38 @@ extern "C" int impec_download_p(impec_ctx *ctx, double *h) { return download_sca
 extern "C" int impec_upload_c_rows(impec_ctx *ctx, const double *h) { ctx->mob_valid = ctx->op_valid = false; return upload_scalar(ctx, ctx->c, h); }
 extern "C" int impec_download_c_rows(impec_ctx *ctx, double *h) { return download_scalar(ctx, ctx->c, h); }
 
-// q: this rank's rows (N1loc x N2).  The scan for non-zero cells runs on all host threads (it is on the e2e path:
-// 2 GB of q per upload at 16384^2).
-static int rebuild_wells(impec_ctx *ctx, const double *q) {
+// q: this rank's rows (N1loc x N2), dense on the host as the reference passes it (double const *q).  The wells are a tiny part of the
+// grid (0.8 % of the cells in the shipped cfgs), so the host array is SCANNED on all host threads -- while earlier uploads on the
+// stream (c) are still in flight -- and only the compact list of non-zero cells crosses PCIe; the dense device array (read by
+// k_setup_rhs and the diagnostics) is rebuilt by a memset + scatter kernel.  A dense q (more than 1/16 of the cells non-zero) is copied
+// as it is.
+__global__ void k_scatter_wells(int n, const int *__restrict__ wi, const int *__restrict__ wj, const double *__restrict__ wq, Grid g, double *__restrict__ q) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) q[gidx(g, wi[t], wj[t])] = wq[t];
+}
+static int scan_wells(impec_ctx *ctx, const double *q, std::vector<int> &wi, std::vector<int> &wj, std::vector<double> &wq) {
     const int N1 = ctx->g.N1, N2 = ctx->P.N2;
-    std::vector<int> wi, wj; std::vector<double> wq;
-    {
-        unsigned nt = std::thread::hardware_concurrency();
-        if (nt < 1) nt = 1; if (nt > 32) nt = 32; if ((int)nt > N1) nt = (unsigned)N1;
-        std::vector<std::vector<int> > ti(nt), tj(nt); std::vector<std::vector<double> > tq(nt);
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; t++)
-            th.emplace_back([&, t]() {
-                const int r0 = (int)((long long)N1 * t / nt), r1 = (int)((long long)N1 * (t + 1) / nt);     // contiguous row blocks keep row-major order
-                for (int i = r0; i < r1; i++)
-                    for (int j = 0; j < N2; j++) {
-                        const double v = q[(size_t)i * N2 + j];
-                        if (v != 0.0) { ti[t].push_back(i); tj[t].push_back(j); tq[t].push_back(v); }
-                    }
-            });
-        for (auto &x : th) x.join();
-        for (unsigned t = 0; t < nt; t++) { wi.insert(wi.end(), ti[t].begin(), ti[t].end()); wj.insert(wj.end(), tj[t].begin(), tj[t].end()); wq.insert(wq.end(), tq[t].begin(), tq[t].end()); }
-    }
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1; if (nt > 64) nt = 64; if ((int)nt > N1) nt = (unsigned)N1;
+    std::vector<std::vector<int> > ti(nt), tj(nt); std::vector<std::vector<double> > tq(nt);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&, t]() {
+            const int r0 = (int)((long long)N1 * t / nt), r1 = (int)((long long)N1 * (t + 1) / nt);     // contiguous row blocks keep row-major order
+            for (int i = r0; i < r1; i++) {
+                const double *row = q + (size_t)i * N2;
+                for (int j = 0; j < N2; j++) {
+                    const double v = row[j];
+                    if (v != 0.0) { ti[t].push_back(i); tj[t].push_back(j); tq[t].push_back(v); }
+                }
+            }
+        });
+    for (auto &x : th) x.join();
+    for (unsigned t = 0; t < nt; t++) { wi.insert(wi.end(), ti[t].begin(), ti[t].end()); wj.insert(wj.end(), tj[t].begin(), tj[t].end()); wq.insert(wq.end(), tq[t].begin(), tq[t].end()); }
+    return IMPEC_OK;
+}
+static int set_wells(impec_ctx *ctx, const double *q, const std::vector<int> &wi, const std::vector<int> &wj, const std::vector<double> &wq) {
+    const int N1 = ctx->g.N1, N2 = ctx->P.N2;
     ctx->nwell = (int)wq.size();
     ctx->q_pin = (ctx->rank == 0 && N1 > 1 && N2 > 1) ? q[(size_t)1 * N2 + 1] : 0.0;
     if (ctx->nwell) {
@@ -710,16 +731,26 @@ static int rebuild_wells(impec_ctx *ctx, const double *q) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_i, wi.data(), sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_j, wj.data(), sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_q, wq.data(), sizeof(double) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // the host vectors die at return
+        ctx->bytes_h2d += (size_t)ctx->nwell * (2 * sizeof(int) + sizeof(double));
     }
     ctx->have_q = true;
     return IMPEC_OK;
 }
 extern "C" int impec_upload_q_rows(impec_ctx *ctx, const double *q) {
     const Grid &g = ctx->g;
-    const size_t w = (size_t)g.N2 * sizeof(double);
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->q + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), q, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
-    return rebuild_wells(ctx, q);
+    std::vector<int> wi, wj; std::vector<double> wq;
+    TRY(scan_wells(ctx, q, wi, wj, wq));
+    TRY(set_wells(ctx, q, wi, wj, wq));
+    if ((long long)ctx->nwell * 16 > (long long)g.N1 * g.N2) {      // dense source term: plain copy
+        const size_t w = (size_t)g.N2 * sizeof(double);
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->q + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), q, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->bytes_h2d += w * (size_t)g.N1;
+    } else {
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->q, 0, grid_elems(g) * sizeof(double), ctx->stream));
+        if (ctx->nwell) LAUNCH(ctx, k_scatter_wells, dim3((unsigned)((ctx->nwell + 255) / 256)), dim3(256), ctx->nwell, ctx->well_i, ctx->well_j, ctx->well_q, g, ctx->q);
+    }
+    if (ctx->nwell) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // the host vectors die at return
+    return IMPEC_OK;
 }
 extern "C" int impec_upload_q(impec_ctx *ctx, const double *q) { return impec_upload_q_rows(ctx, q + (size_t)ctx->g.i_off * ctx->g.N2); }
 extern "C" int impec_set_q_dev_changed(impec_ctx *ctx) {
@@ -728,14 +759,20 @@ extern "C" int impec_set_q_dev_changed(impec_ctx *ctx) {
     const size_t w = (size_t)g.N2 * sizeof(double);
     CUDA_TRY(ctx, cudaMemcpy2DAsync(q.data(), w, ctx->q + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), w, (size_t)g.N1, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return rebuild_wells(ctx, q.data());
+    std::vector<int> wi, wj; std::vector<double> wq;
+    TRY(scan_wells(ctx, q.data(), wi, wj, wq));
+    TRY(set_wells(ctx, q.data(), wi, wj, wq));
+    if (ctx->nwell) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
 }
 extern "C" int impec_upload_velocity(impec_ctx *ctx, const double *v_aos) {
     const Grid &g = ctx->g; const int ng = ctx->P.g;
     const int H = g.N1 + 1 + 2 * ng, W = g.N2 + 1 + 2 * ng;
     const long long n = (long long)H * W;
     v_aos += (size_t)g.i_off * W * 2;                                          // this rank's rows of the global array
+    ctx->dt_cached = false;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ta, v_aos, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->bytes_h2d += sizeof(double) * 2 * n;
     LAUNCH(ctx, k_deinterleave, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->ta, H, W, ctx->u, ctx->v, ng);
     return IMPEC_OK;
 }
@@ -746,7 +783,12 @@ extern "C" int impec_download_velocity(impec_ctx *ctx, double *v_aos) {
     LAUNCH(ctx, k_interleave, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->ta, H, W, ctx->u, ctx->v, ng);
     v_aos += (size_t)g.i_off * W * 2;
     CUDA_TRY(ctx, cudaMemcpyAsync(v_aos, ctx->ta, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->bytes_d2h += sizeof(double) * 2 * n;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return IMPEC_OK;
+}
+extern "C" int impec_transfer_bytes(const impec_ctx *ctx, unsigned long long *h2d, unsigned long long *d2h) {
+    if (h2d) *h2d = ctx->bytes_h2d; if (d2h) *d2h = ctx->bytes_d2h;
     return IMPEC_OK;
 }
 extern "C" int impec_field_layout(const impec_ctx *ctx, int *ld, int *row0, int *col0, int *rows) {
@@ -756,7 +798,9 @@ extern "C" int impec_field_layout(const impec_ctx *ctx, int *ld, int *row0, int 
 extern "C" void *impec_field_dev(impec_ctx *ctx, const char *name) {
     const std::string k(name ? name : "");
     if (k == "c") { ctx->mob_valid = ctx->op_valid = false; return ctx->c; }
-    if (k == "p") return ctx->p; if (k == "q") return ctx->q; if (k == "u") return ctx->u; if (k == "v") return ctx->v;
+    if (k == "p") return ctx->p; if (k == "q") return ctx->q;
+    if (k == "u") { ctx->dt_cached = false; return ctx->u; }
+    if (k == "v") { ctx->dt_cached = false; return ctx->v; }
     return nullptr;
 }
 
@@ -793,12 +837,46 @@ static int build_mobility(impec_ctx *ctx) {
     return IMPEC_OK;
 }
 
+// FP64 DINV is read only by the per-colour (unfused) smoother and by the cycle kernels when they do not use the FP32 copies; slabs need
+// it for the halo exchange.  Where nothing reads it, it is not written.
+static bool need_dinv64(const impec_ctx *ctx) { return !ctx->links_f32 || !ctx->fused || ctx->nranks > 1; }
+// DINV + FP32 copies of one level from its FP64 links (k_level_finish), halo rows of a slab by exchange
+static int finish_level(impec_ctx *ctx, int l, const LevelDev &D, const double *sigma) {
+    Level &L = ctx->L[l];
+    const dim3 gr((unsigned)((L.g.ld + BX - 1) / BX), (unsigned)((L.g.rows + BY - 1) / BY));
+    if (need_dinv64(ctx)) LAUNCH(ctx, k_level_finish<true>, gr, kBlock, D, sigma, L.DINV, L.AWf, L.ASf, L.AVf, L.DINVf);
+    else LAUNCH(ctx, k_level_finish<false>, gr, kBlock, D, sigma, L.DINV, L.AWf, L.ASf, L.AVf, L.DINVf);
+    if (L.dist) {
+        TRY(exchange_rows(ctx, L.DINV, L.g, IMPEC_GH));
+        for (int side = 0; side < 2; side++) {
+            const int r0 = side == 0 ? 0 : L.g.N1 + IMPEC_GH, r1 = side == 0 ? IMPEC_GH : L.g.rows;
+            const long long n = (long long)(r1 - r0) * L.g.ld;
+            LAUNCH(ctx, k_f32_rows, dim3((unsigned)((n + 255) / 256)), dim3(256), L.g, r0, r1, (const double *)L.AW, (const double *)L.AS, (const double *)L.AV, (const double *)L.DINV,
+                   L.AWf, L.ASf, L.AVf, L.DINVf);
+        }
+    }
+    return IMPEC_OK;
+}
+
 extern "C" int impec_build_operator(impec_ctx *ctx) {
     const Grid &g = ctx->g;
-    TRY(build_mobility(ctx));
     Level &L0 = ctx->L[0];
-    if (ctx->P.is_test) LAUNCH(ctx, k_links<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
-    else LAUNCH(ctx, k_links<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
+    const bool fused_build = ctx->build_fused && !ctx->P.is_test;
+    if (fused_build) {
+        // one march over c: links, inverse diagonal and FP32 copies of level 0 (MU / KV are not materialised: mob_valid stays false)
+        BuildArgs A;
+        A.g = g; A.c = ctx->c; A.AW = L0.AW; A.AS = L0.AS; A.AV = L0.AV; A.DINV = L0.DINV; A.AWf = L0.AWf; A.ASf = L0.ASf; A.AVf = L0.AVf; A.DINVf = L0.DINVf;
+        A.pin = L0.pin; A.P = ctx->D;
+        const int warps = (g.N2 + BL_OWN - 1) / BL_OWN;
+        const dim3 gb((unsigned)((warps + BL_BLOCK / 32 - 1) / (BL_BLOCK / 32)), (unsigned)((g.N1 + BL_ROWS - 1) / BL_ROWS));
+        if (need_dinv64(ctx)) LAUNCH_COOP(ctx, k_build_links_march<true>, gb, dim3(BL_BLOCK), A, BL_ROWS);
+        else LAUNCH_COOP(ctx, k_build_links_march<false>, gb, dim3(BL_BLOCK), A, BL_ROWS);
+        ctx->mob_valid = false;
+    } else {
+        TRY(build_mobility(ctx));
+        if (ctx->P.is_test) LAUNCH(ctx, k_links<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
+        else LAUNCH(ctx, k_links<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
+    }
     if (L0.dist) { TRY(exchange_rows(ctx, L0.AW, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AS, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AV, L0.g, IMPEC_GH)); }
     for (size_t l = 1; l < ctx->L.size(); l++) {
         Level &F = ctx->L[l - 1], &C = ctx->L[l];
@@ -817,11 +895,19 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
     TRY(comm_bcast(ctx, ctx->sigma_dev, (long long)ctx->L.size(), 0));
     for (size_t l = 0; l < ctx->L.size(); l++) {
         Level &L = ctx->L[l];
-        LAUNCH(ctx, k_diag_inv, grid2d(L.g.N2, L.g.N1), kBlock, level_dev(ctx, (int)l, 0.0), (const double *)(ctx->sigma_dev + l), L.DINV);
-        if (L.dist) TRY(exchange_rows(ctx, L.DINV, L.g, IMPEC_GH));
-        const long long nn = (long long)grid_elems(L.g);
-        LAUNCH(ctx, k_links_to_f32, dim3((unsigned)((nn + 255) / 256)), dim3(256), nn, (const double *)L.AW, (const double *)L.AS, (const double *)L.AV, (const double *)L.DINV,
-               L.AWf, L.ASf, L.AVf, L.DINVf);
+        if (l == 0 && fused_build) {
+            if (L.dist) {           // the march wrote the interior; halo rows of DINV and of the FP32 copies
+                TRY(exchange_rows(ctx, L.DINV, L.g, IMPEC_GH));
+                for (int side = 0; side < 2; side++) {
+                    const int r0 = side == 0 ? 0 : L.g.N1 + IMPEC_GH, r1 = side == 0 ? IMPEC_GH : L.g.rows;
+                    const long long n = (long long)(r1 - r0) * L.g.ld;
+                    LAUNCH(ctx, k_f32_rows, dim3((unsigned)((n + 255) / 256)), dim3(256), L.g, r0, r1, (const double *)L.AW, (const double *)L.AS, (const double *)L.AV, (const double *)L.DINV,
+                           L.AWf, L.ASf, L.AVf, L.DINVf);
+                }
+            }
+            continue;
+        }
+        TRY(finish_level(ctx, (int)l, level_dev(ctx, (int)l, 0.0), (const double *)(ctx->sigma_dev + l)));
     }
     ctx->op_valid = true;
     return IMPEC_OK;
@@ -1366,11 +1452,29 @@ extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info
 // ------------------------------------------------------------------------------------------------ a12 velocities
 extern "C" int impec_calc_velocities(impec_ctx *ctx) {
     const Grid &g = ctx->g; const int ng = ctx->P.g;
-    if (!ctx->mob_valid) TRY(build_mobility(ctx));
+    ctx->dt_cached = false;
     TRY(fill_scalar(ctx, ctx->p, 0));                               // src/EllipticSolver.cpp:663
     TRY(exchange_rows(ctx, ctx->p, g, ng));
-    if (ctx->P.is_test) LAUNCH(ctx, k_velocity<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->p, ctx->MU, ctx->KV11, ctx->KV22, ctx->u, ctx->v, ctx->D);
-    else LAUNCH(ctx, k_velocity<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->p, ctx->MU, ctx->KV11, ctx->KV22, ctx->u, ctx->v, ctx->D);
+    if (ctx->vel_march && !ctx->P.is_test) {
+        // one march from c and p: u, v and the reductions impec_max_stable_dt needs (kernels_build.inl)
+        VelArgs A;
+        A.g = g; A.c = ctx->c; A.p = ctx->p; A.u = ctx->u; A.v = ctx->v; A.part = ctx->part; A.stride = ctx->part_cap; A.P = ctx->D;
+        const int warps = (g.N2 + 1 + BL_OWN - 1) / BL_OWN;
+        const dim3 gb((unsigned)((warps + BL_BLOCK / 32 - 1) / (BL_BLOCK / 32)), (unsigned)((g.N1 + BL_ROWS - 1) / BL_ROWS));
+        const long long nparts = (long long)gb.x * gb.y;
+        if (ctx->P.diffusion) LAUNCH_COOP(ctx, k_velocity_march<true>, gb, dim3(BL_BLOCK), A, BL_ROWS);
+        else LAUNCH_COOP(ctx, k_velocity_march<false>, gb, dim3(BL_BLOCK), A, BL_ROWS);
+        TRY(reduce_final(ctx, RED_MAX, nparts, 1, 0, S_DT));
+        if (ctx->P.diffusion) {
+            LAUNCH_COOP(ctx, k_reduce_final<RED_MIN>, dim3(1), dim3(1024), ctx->part + ctx->part_cap, nparts, 0LL, ctx->scal + S_DT + 1);
+            TRY(comm_allreduce(ctx, ctx->scal + S_DT + 1, 1, RED_MIN));
+        }
+        ctx->dt_cached = true;
+    } else {
+        if (!ctx->mob_valid) TRY(build_mobility(ctx));
+        if (ctx->P.is_test) LAUNCH(ctx, k_velocity<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->p, ctx->MU, ctx->KV11, ctx->KV22, ctx->u, ctx->v, ctx->D);
+        else LAUNCH(ctx, k_velocity<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->p, ctx->MU, ctx->KV11, ctx->KV22, ctx->u, ctx->v, ctx->D);
+    }
     const long long n = (long long)(g.N1 + 1 + 2 * ng) * (g.N2 + 1 + 2 * ng);
     LAUNCH(ctx, k_fill_velocity, dim3((unsigned)((n + 255) / 256)), dim3(256), g, ctx->u, ctx->v, ng);   // :682
     TRY(exchange_rows(ctx, ctx->u, g, ng + 1));                     // u row N1 is the neighbour's row 0; N1+1, N1+2 are its rows 1, 2
@@ -1391,11 +1495,13 @@ extern "C" int impec_max_stable_dt(impec_ctx *ctx, double *dt) {
         *dt = ctx->h_scal[S_DT] * P.cfl;
         return IMPEC_OK;
     }
-    LAUNCH_COOP(ctx, k_dt_reduce<0>, gr, kBlock, g, ctx->u, ctx->v, ctx->D, ctx->part);
-    TRY(reduce_final(ctx, RED_MAX, nparts, 1, 0, S_DT));
-    if (P.diffusion) {
-        LAUNCH_COOP(ctx, k_dt_reduce<2>, gr, kBlock, g, ctx->u, ctx->v, ctx->D, ctx->part);
-        TRY(reduce_final(ctx, RED_MIN, nparts, 1, 0, S_DT + 1));
+    if (!ctx->dt_cached) {                                          // (calc_velocities reduces on the fly: nothing to launch then)
+        LAUNCH_COOP(ctx, k_dt_reduce<0>, gr, kBlock, g, ctx->u, ctx->v, ctx->D, ctx->part);
+        TRY(reduce_final(ctx, RED_MAX, nparts, 1, 0, S_DT));
+        if (P.diffusion) {
+            LAUNCH_COOP(ctx, k_dt_reduce<2>, gr, kBlock, g, ctx->u, ctx->v, ctx->D, ctx->part);
+            TRY(reduce_final(ctx, RED_MIN, nparts, 1, 0, S_DT + 1));
+        }
     }
     TRY(fetch_scalars(ctx, S_DT, 2));
     const double max_vel = ctx->h_scal[S_DT];
@@ -1522,11 +1628,7 @@ extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info
     if (L0.dist) { TRY(exchange_rows(ctx, L0.AW, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AS, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AV, L0.g, IMPEC_GH)); }
     LevelDev A = level_dev(ctx, 0, 1.0);
     A.pin = -1; A.sig_idx = -1;
-    LAUNCH(ctx, k_diag_inv, gr, kBlock, A, (const double *)nullptr, L0.DINV);
-    if (L0.dist) TRY(exchange_rows(ctx, L0.DINV, L0.g, IMPEC_GH));
-    { const long long nn = (long long)grid_elems(L0.g);
-      LAUNCH(ctx, k_links_to_f32, dim3((unsigned)((nn + 255) / 256)), dim3(256), nn, (const double *)L0.AW, (const double *)L0.AS, (const double *)L0.AV, (const double *)L0.DINV,
-             L0.AWf, L0.ASf, L0.AVf, L0.DINVf); }
+    TRY(finish_level(ctx, 0, A, nullptr));
     Cycle C; C.ctx = ctx; C.D.assign(1, A); C.ncoarse = 1; C.w_from = 1; C.w_to = 0; C.nl = 1;
     double *x = ctx->ta;
     LAUNCH_COOP(ctx, k_cn_rhs, gr, kBlock, A, (const double *)ctx->c, ctx->rhs, x, ctx->part);
@@ -1632,7 +1734,7 @@ extern "C" int impec_checkpoint_load(impec_ctx *ctx, const char *path, double *t
     if (!ok) return fail(ctx, IMPEC_ERR_ARG, "checkpoint %s is truncated or unreadable", path);
     LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_OUTFLUX, H.outflux);
     ctx->prev_first_sweep = H.prev_first_sweep;
-    ctx->mob_valid = ctx->op_valid = false;
+    ctx->mob_valid = ctx->op_valid = false; ctx->dt_cached = false;
     if (t) *t = H.t; if (step) *step = H.step;
     return IMPEC_OK;
 }
@@ -1689,6 +1791,34 @@ extern "C" int impec_diagnostics(impec_ctx *ctx, impec_diag *out) {
     return IMPEC_OK;
 }
 
+// the integral diagnostics the north-star compares fingering runs on, as device reductions (the host-side
+// definitions live in impec2d_b200/diagnostics.py and are checked against these on downloaded fields in the tests).
+extern "C" int impec_integral_diagnostics(impec_ctx *ctx, double lo, double hi, impec_integral_diag *out) {
+    if (!out) return fail(ctx, IMPEC_ERR_ARG, "null output");
+    if (!ctx->have_q) return fail(ctx, IMPEC_ERR_ARG, "integral diagnostics before impec_upload_q");
+    const Grid &g = ctx->g;
+    const dim3 gr = grid2d(g.N2, g.N1);
+    const long long nparts = (long long)gr.x * gr.y;
+    LAUNCH_COOP(ctx, k_diag_mixing, gr, kBlock, g, (const double *)ctx->c, lo, hi, ctx->part, ctx->part_cap);
+    TRY(reduce_final(ctx, RED_SUM, nparts, 2, ctx->part_cap, S_DIAG + 5));          // S_DIAG+5: cells in the mixing zone, +6: sum c
+    if (ctx->nwell) {
+        const int nb = (ctx->nwell + 255) / 256;
+        LAUNCH_COOP(ctx, k_diag_wells, dim3((unsigned)nb), dim3(256), ctx->nwell, ctx->well_i, ctx->well_j, ctx->well_q, g, (const double *)ctx->c, ctx->part, ctx->part_cap);
+        LAUNCH_COOP(ctx, k_reduce_final<RED_SUM>, dim3(2), dim3(1024), ctx->part, (long long)nb, ctx->part_cap, ctx->scal + S_DIAG + 7);
+    } else {
+        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_DIAG + 7, 0.0);
+        LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_DIAG + 8, 0.0);
+    }
+    TRY(comm_allreduce(ctx, ctx->scal + S_DIAG + 7, 2, RED_SUM));
+    TRY(fetch_scalars(ctx, S_DIAG + 5, 4));
+    const double lx = ctx->P.x_ub - ctx->P.x_lb, ly = ctx->P.y_ub - ctx->P.y_lb;
+    out->mixing_zone_cells = ctx->h_scal[S_DIAG + 5];
+    out->mixing_zone_length = ctx->h_scal[S_DIAG + 5] * ctx->D.dx * ctx->D.dy / sqrt(lx * lx + ly * ly);
+    out->mass_in_place = ctx->h_scal[S_DIAG + 6] * ctx->D.dx * ctx->D.dy;
+    out->produced_fraction = ctx->h_scal[S_DIAG + 7] > 0. ? ctx->h_scal[S_DIAG + 8] / ctx->h_scal[S_DIAG + 7] : 0.;
+    return IMPEC_OK;
+}
+
 #include "host_util.inl"
 
 // ------------------------------------------------------------------------------------------------ profiling hook
@@ -1740,6 +1870,8 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "gather_rhs") { for (int l = 0; l + 1 < (int)ctx->L.size(); l++) if (at_transition(ctx, l)) return gather_coarse_rhs(ctx, l); return IMPEC_OK; }
         if (k == "sweep_x") return sweep<0>(ctx, ctx->c, ctx->ta, nullptr, 0.0, 0, g.N1, -ng, g.N2 + ng);
         if (k == "sweep_y") return sweep<1>(ctx, ctx->c, ctx->ta, nullptr, 0.0, -ng, g.N1 + ng, 0, g.N2);
+        if (k == "transport_step") return impec_transport_step(ctx, ctx->profile_dt);
+        if (k == "diffusion_split") return impec_diffusion_split(ctx, 0.5 * ctx->profile_dt, nullptr);
         if (k == "build_operator") return impec_build_operator(ctx);
         if (k == "calc_velocities") return impec_calc_velocities(ctx);
         return fail(ctx, IMPEC_ERR_ARG, "unknown kernel name '%s'", k.c_str());

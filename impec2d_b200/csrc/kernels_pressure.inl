@@ -508,6 +508,36 @@ __global__ void __launch_bounds__(256) k_diag_cells(Grid g, const double *__rest
         part[b] = m; part[stride + b] = e; part[2 * stride + b] = cmax; part[3 * stride + b] = cmin;
     }
 }
+// Integral diagnostics of a displacement run (definitions: impec2d_b200/diagnostics.py) as device reductions:
+// partial sums [0] number of cells with lo <= c <= hi (the mixing zone), [1] sum c.  One pass over c, no field leaves the GPU.
+__global__ void __launch_bounds__(256) k_diag_mixing(Grid g, const double *__restrict__ c, double lo, double hi, double *__restrict__ part, long long stride) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double n = 0., m = 0.;
+    if (i < g.N1 && j < g.N2) {
+        m = c[gidx(g, i, j)];
+        n = (m >= lo && m <= hi) ? 1. : 0.;
+    }
+    n = block_reduce<RED_SUM>(n);
+    m = block_reduce<RED_SUM>(m);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const long long b = blockIdx.y * gridDim.x + blockIdx.x;
+        part[b] = n; part[stride + b] = m;
+    }
+}
+// |q|-weighted concentration over the production cells (q < 0) of the compact well list: partial sums [0] sum -q, [1] sum -q c
+__global__ void __launch_bounds__(256) k_diag_wells(int n, const int *__restrict__ wi, const int *__restrict__ wj, const double *__restrict__ wq, Grid g,
+                                                    const double *__restrict__ c, double *__restrict__ part, long long stride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double w = 0., wc = 0.;
+    if (t < n) {
+        const double q = wq[t];
+        if (q < 0.) { w = -q; wc = w * c[gidx(g, wi[t], wj[t])]; }
+    }
+    w = block_reduce<RED_SUM>(w);
+    wc = block_reduce<RED_SUM>(wc);
+    if (threadIdx.x == 0) { part[blockIdx.x] = w; part[stride + blockIdx.x] = wc; }
+}
 // no-flow boundary velocity sum: src/Impec2DSolver.cpp:562-588
 __global__ void __launch_bounds__(256) k_diag_boundary(Grid g, const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ part) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

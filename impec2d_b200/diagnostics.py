@@ -43,6 +43,11 @@ class RunDiagnostics:
         self.t.append(float(t)); self.frac.append(produced_fraction(c_int, self.q))
         self.mix.append(mixing_zone_length(c_int, self.dx, self.dy, self.lx, self.ly)); self.mass.append(mass_in_place(c_int, self.dx, self.dy))
 
+    def record_device(self, t, ctx):
+        """The same three series from the DEVICE reductions of impec_integral_diagnostics: nothing but four scalars crosses PCIe."""
+        d = ctx.integral_diagnostics()
+        self.t.append(float(t)); self.frac.append(d.produced_fraction); self.mix.append(d.mixing_zone_length); self.mass.append(d.mass_in_place)
+
     def breakthrough_time(self):
         f = np.asarray(self.frac); t = np.asarray(self.t)
         k = np.nonzero(f >= self.threshold)[0]

@@ -72,6 +72,13 @@ typedef struct impec_diag {           /* src/Impec2DSolver.h:16-25 plus the per-
     double c_min, c_max;
 } impec_diag;
 
+typedef struct impec_integral_diag {  /* integral diagnostics of a displacement run (north-star check 2)          */
+    double produced_fraction;         /* |q|-weighted mean c over the production cells (q < 0): what the wells produce             */
+    double mixing_zone_length;        /* area of {lo <= c <= hi} / injector-producer distance hypot(Lx, Ly)                        */
+    double mixing_zone_cells;         /* number of cells in that band (exact integer)                                              */
+    double mass_in_place;             /* sum c dx dy                                                                                */
+} impec_integral_diag;
+
 typedef struct impec_solve_info {
     int    iterations;                /* PCG iterations (MGSolver::num_iterations)                  */
     double relres;                    /* recurrence ||r||/||b||, the quantity HYPRE's PCG tests      */
@@ -126,6 +133,9 @@ int   impec_download_velocity(impec_ctx *ctx, double *v_aos);
 int   impec_upload_c_rows(impec_ctx *ctx, const double *c_slab_ghosted);
 int   impec_upload_q_rows(impec_ctx *ctx, const double *q_slab);
 int   impec_download_c_rows(impec_ctx *ctx, double *c_slab_ghosted);
+/* bytes of field data this context has moved over PCIe so far (counted from the copies the library issues; q is scanned on the
+ * host and only its non-zero cells are sent when it is sparse) */
+int   impec_transfer_bytes(const impec_ctx *ctx, unsigned long long *h2d, unsigned long long *d2h);
 /* device-resident alternatives for callers that already hold device memory (padded layout) */
 int   impec_field_layout(const impec_ctx *ctx, int *ld, int *row0, int *col0, int *rows);
 void *impec_field_dev(impec_ctx *ctx, const char *name);   /* "c","p","q","u","v" */
@@ -155,6 +165,9 @@ int   impec_transport_step(impec_ctx *ctx, double dt);
 int   impec_impes_step(impec_ctx *ctx, double t, double t_next_output, double *dt_used, impec_solve_info *info);
 /* a20  diagnostics of the loop body                src/Impec2DSolver.cpp:391-415, 530-620 */
 int   impec_diagnostics(impec_ctx *ctx, impec_diag *out);
+/* breakthrough / recovery / mixing-zone inputs as device reductions: no field is downloaded (2.1 GB per sample at 16384^2 otherwise).
+ * lo, hi: the concentration band of the mixing zone (0.1, 0.9 in impec2d_b200/diagnostics.py) */
+int   impec_integral_diagnostics(impec_ctx *ctx, double lo, double hi, impec_integral_diag *out);
 
 /* 8f  Impec2DSolver::Project / ParallelProjector::FillDiagonal  src/Impec2DSolver.cpp:690-716, src/ParallelProjector.cpp:91-199
  *     field 0 = c, 1 = p (ghosts must be filled: they are after impec_impes_step); out_host: dN1 x dN2 doubles, row-major.

@@ -10,7 +10,7 @@
  *
  * PARITY PINNING -- pinned to the reference itself:
  *   * oracle/_ref/libimpec_ref.so is the reference's own translation units
- *     (src/*.cpp, compiled UNMODIFIED by oracle/Makefile against the shim headers
+ *     (its src .cpp files, compiled UNMODIFIED by oracle/Makefile against the shim headers
  *     in oracle/ref_shim/ for blitz, libconfig++, MPI and HYPRE, none of which is
  *     installed here).  tests/test_oracle_vs_ref.py runs the reference's objects
  *     and this oracle on the same inputs: ghost fills, wells, mobilities, the

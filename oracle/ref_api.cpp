@@ -17,6 +17,8 @@
 #include "HYPRE_struct_ls.h"
 #include <string>
 #include <cstring>
+#include <cstdlib>
+#include <new>
 #include <omp.h>
 
 namespace {
@@ -70,7 +72,11 @@ extern "C" {
 
 void *ref_open(const char *cfg_path) {
     Ref *R = new Ref();
-    R->sp = new SimParams(std::string(cfg_path));          // exits the process on a bad file, as upstream
+    // SimParams leaves members uninitialised that it later reads (see ref_zero_new.cpp): construct it in zero-filled memory.  (The
+    // zero-filling operator new of ref_zero_new.cpp covers the reference's own `new SimParams` in its executable; inside a host
+    // process that loaded another C++ runtime first, the dynamic linker may bind operator new elsewhere, hence placement new here.)
+    void *mem = calloc(1, sizeof(SimParams));
+    R->sp = new (mem) SimParams(std::string(cfg_path));    // exits the process on a bad file, as upstream
     R->es = new MGOpen(R->sp);
     R->hs = new MusclOpen(R->sp);
     R->up = new UpwindOpen(R->sp);
@@ -83,7 +89,7 @@ void *ref_open(const char *cfg_path) {
 void ref_close(void *h) {
     Ref *R = (Ref *)h;
     if (!R) return;
-    delete R->hs; delete R->up; delete R->es; delete[] R->q; delete R->sp; delete R;
+    delete R->hs; delete R->up; delete R->es; delete[] R->q; R->sp->~SimParams(); free(R->sp); delete R;
 }
 void ref_dims(void *h, int *N1, int *N2, int *g) { Ref *R = (Ref *)h; *N1 = R->sp->N1; *N2 = R->sp->N2; *g = R->sp->c_bounds; }
 // the derived quantities SimParams computes (src/SimParams.cpp:449-456) plus a few parsed values, for cross-checking the cfg reader

@@ -493,3 +493,217 @@ def check_staged_vs_fused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
         out.append(z1)
         ctx.close()
     assert np.array_equal(out[0], out[1]), np.abs(out[0] - out[1]).max()
+
+
+# ---------------------------------------------------------------------------------------------------- round 2 additions
+def check_generators(emulated, N=96):
+    """impec_synth_state / impec_init_source (the product's input generators used by bench.py) against the oracle's, which are pinned
+    to the reference's well model (tests/test_oracle_vs_ref.py): bit for bit, circle and one-cell wells, both grid orientations."""
+    lib = O.lib()
+    for stype in (O.PARALLEL, O.DIAGONAL):
+        L = 1.41421356237 if stype == O.PARALLEL else 1.0
+        kw = dict(N1=N, N2=N + 16, x_ub=L, y_ub=L, stype=stype)
+        if stype == O.PARALLEL:
+            kw["N2"] = N
+        Po = O.default_params(**kw); Pi = I.default_params(emulated=emulated, **kw)
+        co = O.scalar_field(Po); lib.orc_synth_state(C.byref(Po), 20260917, co)
+        assert np.array_equal(I.synth_state(Pi, emulated=emulated), co)
+        for profile in (0, 2):
+            qo = np.zeros(Po.N1 * Po.N2); lib.orc_init_source(C.byref(Po), 1.0, 0.05, profile, qo)
+            assert np.array_equal(I.init_source(Pi, 1.0, 0.05, profile, emulated=emulated), qo) and np.abs(qo).max() > 0
+        # slab-wise generation (multi-GPU bench) equals the rows of the global arrays
+        r0, nr = Po.N1 // 4, Po.N1 // 2
+        cs = I.synth_state_rows(Pi, r0, nr, emulated=emulated)
+        assert np.array_equal(cs[Po.g:-Po.g], co[Po.g + r0:Po.g + r0 + nr])
+        qs = I.init_source_rows(Pi, r0, nr, 1.0, 0.05, 0, emulated=emulated)
+        qo = np.zeros(Po.N1 * Po.N2); lib.orc_init_source(C.byref(Po), 1.0, 0.05, 0, qo)
+        assert np.array_equal(qs, qo.reshape(Po.N1, Po.N2)[r0:r0 + nr].ravel())
+
+
+def check_one_cell_wells(emulated, N=64):
+    """well_profile = one_cell (src/Util.cpp:565-586): two IMPES steps against the oracle, parallel and diagonal layout."""
+    lib = O.lib()
+    for stype in (O.PARALLEL, O.DIAGONAL):
+        base, Po, c, _q = production_case(N, N, stype=stype, eps=1e-12)
+        Pi = I.default_params(emulated=emulated, **base)
+        q = np.zeros(N * N); lib.orc_init_source(C.byref(Po), 1.0, 0.05, 2, q)
+        assert np.count_nonzero(q) in (2, 4)
+        ctx = I.Context(Pi, emulated=emulated)
+        ctx.upload_c(c); ctx.upload_q(q)
+        So = O.new_state(); p = O.scalar_field(Po); u = O.velocity_field(Po); v = O.velocity_field(Po); co = c.copy()
+        t = 0.0
+        for _ in range(2):
+            dto = lib.orc_impes_step(C.byref(Po), C.byref(So), p, co, u, v, q, t, 0.0)
+            dtg, info = ctx.impes_step(t, 0.0)
+            assert info.converged == 1 and abs(dtg - dto) <= 1e-9 * dto
+            t += dto
+        assert rel_l2(interior(Po, ctx.download_p()), interior(Po, p)) <= TOL_P
+        assert np.abs(ctx.download_c() - co).max() <= 1e-8
+        ctx.close()
+
+
+def check_explicit_diffusive_dt(emulated, N=72):
+    """para_method = explicit with dispersion: dt = min(dt_A, lambda min dx^2 / (2 (d11 + d22))) (src/HyperbolicSolver.cpp:157-196).  The
+    device reduction evaluates the same expression per cell in the same order: BIT-EXACT."""
+    lib = O.lib()
+    for al, at, lim in ((1.0, 1.0, 0.9), (0.4, 0.4, 0.6)):
+        base, Po, c, q = production_case(N, N + 8, stype=O.DIAGONAL, diffusion=1, ptype=O.EXPLICIT, alpha_l=al, alpha_t=at, dt_diff_limit=lim)
+        Pi = I.default_params(emulated=emulated, **base)
+        rng = np.random.default_rng(31)
+        u = O.velocity_field(Po); v = O.velocity_field(Po)
+        u[...] = 6.0 * (rng.random(u.shape) - 0.5); v[...] = 6.0 * (rng.random(v.shape) - 0.5)
+        ctx = I.Context(Pi, emulated=emulated)
+        ctx.upload_velocity(aos(u, v))
+        dto = lib.orc_max_stable_dt(C.byref(Po), u, v)
+        dta = lib.orc_max_stable_advection_dt(C.byref(Po), u, v)
+        assert ctx.max_stable_dt() == dto, (ctx.max_stable_dt(), dto)
+        assert dto < dta                                          # the diffusive limit is the binding one here
+        ctx.close()
+
+
+def check_diagnostic_values(emulated, N=80):
+    """CalculateDivergenceError, CalculateVelocityBoundaryError, GetTotalMass (src/Impec2DSolver.cpp:542-620) as device reductions
+    against the oracle's restatement on the velocity field of a converged step; also with a perturbed (non-solenoidal, leaking) field."""
+    lib = O.lib()
+    base, Po, c, q = production_case(N, N, eps=1e-12)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    ctx.fill_boundaries(); ctx.pressure_solve(); ctx.calc_velocities()
+    vel = ctx.download_velocity()
+    for perturb in (False, True):
+        if perturb:
+            vel = vel + 0.05 * np.random.default_rng(8).standard_normal(vel.shape)
+            ctx.upload_velocity(np.ascontiguousarray(vel))
+        u = np.ascontiguousarray(vel[..., 0]); v = np.ascontiguousarray(vel[..., 1])
+        d = ctx.diagnostics()
+        dv = lib.orc_divergence_error(C.byref(Po), u, v, q)
+        bv = lib.orc_boundary_velocity_error(C.byref(Po), u, v)
+        assert abs(d.divergence_error - dv) <= 1e-9 * max(dv, 1e-12) + 1e-13, (d.divergence_error, dv)
+        assert abs(d.boundary_velocity_error - bv) <= 1e-10 * max(bv, 1e-12) + 1e-13, (d.boundary_velocity_error, bv)
+    cg = ctx.download_c()
+    assert abs(d.total_mass - lib.orc_total_mass(C.byref(Po), cg)) <= 1e-11 * d.total_mass
+    assert d.c_max == interior(Po, cg).max() and d.c_min == interior(Po, cg).min()
+    ctx.close()
+
+
+def check_impes_step_production(emulated, N, steps=1, tol_p=TOL_P, tol_c=1e-8):
+    """One IMPES step of the parallel.cfg operator with the cfg's own tolerance (eps = 1e-14) and the DEFAULT kernel selection (no
+    option or environment overrides) at a size where the production kernels run: >= 2896^2 puts the fine level on the register-march
+    kernels, everything below on the tile / small-level kernels.  Oracle: the same step on the CPU (seconds)."""
+    lib = O.lib()
+    base, Po, c, q = production_case(N, N, eps=1e-14)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    So = O.new_state(); p = O.scalar_field(Po); u = O.velocity_field(Po); v = O.velocity_field(Po); co = c.copy()
+    t = 0.0
+    for _ in range(steps):
+        dto = lib.orc_impes_step(C.byref(Po), C.byref(So), p, co, u, v, q, t, 0.0)
+        dtg, info = ctx.impes_step(t, 0.0)
+        assert info.converged == 1 and abs(info.iterations - So.last_its) <= 1, (info.iterations, So.last_its)
+        assert abs(dtg - dto) <= 1e-9 * dto
+        t += dto
+    ep = rel_l2(interior(Po, ctx.download_p()), interior(Po, p)); ec = np.abs(ctx.download_c() - co).max()
+    print("impes step %d^2: its gpu/oracle %d/%d  true_relres gpu/oracle %.2e/%.2e  |dp|/|p| %.3e  max|dc| %.3e" % (N, info.iterations, So.last_its, info.true_relres, So.last_true_relres, ep, ec))
+    assert ep <= tol_p and ec <= tol_c
+    ctx.close()
+    return ep, ec
+
+
+def check_dispersion_production(emulated, N1, N2):
+    """diagonal_dispersion.cfg step (two CN half steps) against the oracle at a size where the marching CN kernels run."""
+    lib = O.lib()
+    base, Po, c, q = production_case(N1, N2, stype=O.DIAGONAL, diffusion=1, eps=1e-14)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    So = O.new_state(); p = O.scalar_field(Po); u = O.velocity_field(Po); v = O.velocity_field(Po); co = c.copy()
+    dto = lib.orc_impes_step(C.byref(Po), C.byref(So), p, co, u, v, q, 0.0, 0.0)
+    dtg, info = ctx.impes_step(0.0, 0.0)
+    assert abs(dtg - dto) <= 1e-9 * dto and abs(info.iterations - So.last_its) <= 1
+    ep = rel_l2(interior(Po, ctx.download_p()), interior(Po, p)); ec = np.abs(ctx.download_c() - co).max()
+    print("dispersion step %dx%d: |dp|/|p| %.3e max|dc| %.3e" % (N1, N2, ep, ec))
+    assert ep <= TOL_P and ec <= 1e-8
+    ctx.close()
+
+
+def check_hyperbolic_test_config(emulated, N, steps=3):
+    """BASELINE config 2: hyperbolic_test.cfg transport steps (sine cell averages, velocity (-1,+1), periodic, CFL 0.95) at the
+    config's size: BIT-EXACT against the oracle."""
+    lib = O.lib()
+    base = dict(N1=N, N2=N, x_ub=1.0, y_ub=1.0, is_test=1, testno=1, stype=O.DIAGONAL, cfl=0.95, diffusion=0)
+    Po = O.default_params(**base); Pi = I.default_params(emulated=emulated, **base)
+    dx = 1.0 / N
+    x = (np.arange(N) + 0.5) * dx
+    f = np.cos(2.0 * np.pi * (x + dx / 2.0)) - np.cos(2.0 * np.pi * (x - dx / 2.0))
+    c = O.scalar_field(Po); interior(Po, c)[...] = 1.0 + 1.0 / (dx * dx * 4.0 * np.pi * np.pi) * np.outer(f, f)
+    u = O.velocity_field(Po, -1.0); v = O.velocity_field(Po, 1.0); q = np.zeros(N * N)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q); ctx.upload_velocity(aos(u, v))
+    dt = ctx.max_stable_dt()
+    assert dt == lib.orc_max_stable_dt(C.byref(Po), u, v) == 0.95 * Po.dx
+    So = O.new_state(); co = c.copy()
+    for _ in range(steps):
+        lib.orc_transport_step(C.byref(Po), C.byref(So), co, u, v, q, dt)
+        ctx.transport_step(dt)
+    assert np.array_equal(ctx.download_c(), co)
+    ctx.close()
+
+
+def check_integral_diagnostics(emulated, N=96, steps=3):
+    """impec_integral_diagnostics (device reductions) against the host definitions of impec2d_b200/diagnostics.py evaluated on the
+    downloaded field: the mixing-zone cell count is exact, the weighted sums agree to rounding."""
+    from impec2d_b200 import diagnostics as D
+    base, Po, c, q = production_case(N, N, eps=1e-10)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    L = Po.x_ub - Po.x_lb
+    rd_host = D.RunDiagnostics(q, Po.dx, Po.dy, L, L); rd_dev = D.RunDiagnostics(q, Po.dx, Po.dy, L, L)
+    t = 0.0
+    for _ in range(steps):
+        dt, _i = ctx.impes_step(t, 0.0); t += dt
+        ci = interior(Po, ctx.download_c())
+        d = ctx.integral_diagnostics()
+        assert d.mixing_zone_cells == float(((ci >= 0.1) & (ci <= 0.9)).sum())
+        assert abs(d.mixing_zone_length - D.mixing_zone_length(ci, Po.dx, Po.dy, L, L)) <= 1e-14
+        assert abs(d.mass_in_place - D.mass_in_place(ci, Po.dx, Po.dy)) <= 1e-12 * d.mass_in_place
+        pf = D.produced_fraction(ci, q)
+        assert pf > 0 and abs(d.produced_fraction - pf) <= 1e-12 * pf
+        rd_host.record(t, ci); rd_dev.record_device(t, ctx)
+    sh, sd = rd_host.summary(), rd_dev.summary()
+    for k in sh:
+        assert sh[k] == sd[k] or abs(sh[k] - sd[k]) <= 1e-12 * abs(sh[k]), k
+    ctx.close()
+
+
+def check_fused_build(emulated, N1=96, N2=141, big=False):
+    """The one-march operator build (kernels_build.inl: c -> links, inverse diagonal, FP32 copies) and the one-march velocity + CFL
+    kernel (c, p -> u, v, max speed, diffusive limit) against the first-generation passes (k_mobility, k_vertex, k_links, k_diag_inv,
+    k_links_to_f32; k_velocity, k_dt_reduce): every array must be BIT-IDENTICAL, observed through one multigrid cycle on a random
+    right-hand side (reads the FP32 or FP64 coefficient sets of every level), a full pressure solve (FP64 links in the PCG mat-vec),
+    the velocity field and the time step -- 9-point and 5-point operators, both averaging procedures, odd and even column counts,
+    dx != dy, with and without dispersion."""
+    cases = [(N1, N2, O.DIAGONAL, 2.0 / 3.0, O.HARMONIC, 1), (N1, N2 + 1, O.DIAGONAL, 1.0, O.MEANCONC, 0), (N1, N1, O.PARALLEL, 0.5, O.MEANCONC, 0)]
+    if big:
+        cases = [(N1, N2, O.DIAGONAL, 2.0 / 3.0, O.HARMONIC, 1)]
+    for (n1, n2, stype, nu, avg, diff) in cases:
+        base, Po, c, q = production_case(n1, n2, stype=stype, nu=nu, avgproc=avg, eps=1e-9, diffusion=diff, ptype=O.EXPLICIT)
+        Pi = I.default_params(emulated=emulated, **base)
+        r = np.random.default_rng(12).standard_normal(n1 * n2)
+        for f32 in ((1, 0) if not big else (1,)):
+            out = []
+            for fused in (1, 0):
+                ctx = I.Context(Pi, emulated=emulated)
+                ctx.set_option("build_fused", fused); ctx.set_option("vel_march", fused); ctx.set_option("mg_links_fp32", f32)
+                ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
+                z = ctx.vcycle(r)
+                info = ctx.pressure_solve()
+                ctx.calc_velocities()
+                out.append((z, info.iterations, ctx.download_p(), ctx.download_velocity(), ctx.max_stable_dt()))
+                ctx.close()
+            assert np.array_equal(out[0][0], out[1][0]), "cycle differs (fp32 %d): %g" % (f32, np.abs(out[0][0] - out[1][0]).max())
+            assert out[0][1] == out[1][1] and np.array_equal(out[0][2], out[1][2]), "pressure differs (fp32 %d)" % f32
+            assert np.array_equal(out[0][3], out[1][3]), "velocity differs: %g" % np.abs(out[0][3] - out[1][3]).max()
+            assert out[0][4] == out[1][4], ("time step differs", out[0][4], out[1][4])

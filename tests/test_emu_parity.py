@@ -52,3 +52,11 @@ def test_persistent_tail_vs_launches(): pc.check_persistent_tail(True)
 def test_sgs_march_vs_sweeps(): pc.check_sgs_march(True)
 def test_fast_initial_residual(): pc.check_fast_initial_residual(True)
 def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(True, 256, 384)
+# round 2
+def test_generators_bitexact(): pc.check_generators(True, N=48)
+def test_one_cell_wells(): pc.check_one_cell_wells(True, N=32)
+def test_explicit_diffusive_dt_bitexact(): pc.check_explicit_diffusive_dt(True, N=40)
+def test_diagnostic_values(): pc.check_diagnostic_values(True, N=40)
+def test_hyperbolic_test_config(): pc.check_hyperbolic_test_config(True, 64, steps=2)
+def test_integral_diagnostics_device_vs_host(): pc.check_integral_diagnostics(True, N=48, steps=2)
+def test_fused_operator_build_bitexact(): pc.check_fused_build(True, 40, 67)

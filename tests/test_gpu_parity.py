@@ -186,3 +186,28 @@ def test_full_fingering_run_integral_diagnostics():
     injected = 2.0 * 1.0 * t / (Po.dx * Po.dy)
     assert abs(d.total_mass + d.total_mass_outflux - injected) <= 1e-6 * injected
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+def test_generators_bitexact(): pc.check_generators(False, N=512)
+def test_one_cell_wells(): pc.check_one_cell_wells(False, N=128)
+def test_explicit_diffusive_dt_bitexact(): pc.check_explicit_diffusive_dt(False, N=300)
+def test_diagnostic_values(): pc.check_diagnostic_values(False, N=256)
+
+
+@pytest.mark.parametrize("N", [2048, 4096])
+def test_impes_step_production_kernels_vs_oracle(N):
+    """Oracle parity where the production kernels live: default kernel selection, cfg tolerance 1e-14; at 4096^2
+    the fine level runs the register-march kernels the bench times (levels of >= 8M cells)."""
+    pc.check_impes_step_production(False, N)
+
+
+def test_dispersion_step_production_kernels_vs_oracle(): pc.check_dispersion_production(False, 2048, 1024)
+
+
+def test_hyperbolic_test_config_at_4096():
+    """BASELINE config 2 at its size: 3 transport steps, bit-exact against the oracle."""
+    pc.check_hyperbolic_test_config(False, 4096, steps=3)
+def test_integral_diagnostics_device_vs_host(): pc.check_integral_diagnostics(False, N=512, steps=3)
+def test_fused_operator_build_bitexact(): pc.check_fused_build(False, 512, 777)
+def test_fused_operator_build_bitexact_4096(): pc.check_fused_build(False, 4096, 4096, big=True)
