@@ -273,7 +273,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream shared by the library, the timing events and torch's collectives: the library keeps a NULL
+    # stream argument for "create my own", so the legacy default stream cannot be handed to it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
     P = workload_params(wl, N, args.eps, I)
     # one process per GPU; rank r owns rows [r N/P, (r+1) N/P) (slab decomposition along x).  The NCCL communicator of

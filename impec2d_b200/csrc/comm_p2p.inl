@@ -16,12 +16,20 @@
 // All ranks must issue the same sequence of exchanges (they do: the solver is SPMD).  A wait that exceeds
 // P2P_TIMEOUT_CYCLES raises a device-side error flag instead of hanging the GPU.
 //
-// NCCL remains the bootstrap (handle all-gather) and the transport for large collectives (coefficient all-gathers).
+// The all-gather of the restricted right-hand side of the first replicated multigrid level (4 per cycle) is a kernel of the same kind
+// (k_allgather_p2p): every rank stores its slab into a window of EVERY rank's mailbox, raises one flag per chunk and destination,
+// waits for the matching chunks of all sources and copies the window into the level's array.  Two windows alternate with the epoch
+// parity (a rank may be a whole tail visit ahead of a far-away rank; it can never be two gathers ahead, because completing gather e
+// requires every rank to have posted gather e).
+//
+// NCCL remains the bootstrap (handle all-gather) and the transport for the once-per-step coefficient all-gathers.
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
 #define P2P_MAXR 16
 #define P2P_NCTA 8
 #define P2P_THREADS 512
-#define P2P_FLAG_BYTES 4096
+#define P2P_FLAG_BYTES 8192
+#define P2P_AG_NCTA 32                       /* CTAs (= chunks per source slab) of the all-gather kernel */
+#define P2P_AG_FLAG0 128                      /* first all-gather flag: flags [128 + src * P2P_AG_NCTA + cta] */
 #define P2P_AR_BYTES 8192
 #define P2P_AR_MAXN 8
 #define P2P_TIMEOUT_CYCLES 120000000000LL   /* ~60 s: ranks may reach their first exchange seconds apart */
@@ -98,6 +106,48 @@ __global__ void __launch_bounds__(P2P_THREADS) k_halo_p2p(HaloArgs a) {
             double2 *dst = reinterpret_cast<double2 *>(a.fld[f] + a.recv_hi);
             for (long long k = c0 + threadIdx.x; k < c1; k += blockDim.x) dst[k] = __ldcg(src + k);
         }
+    }
+}
+
+struct GatherArgs {
+    const double *src;                               // my slab (cnt doubles, contiguous rows)
+    long long cnt;                                   // doubles per rank (a multiple of 2)
+    double *rem_win[P2P_MAXR];                       // this epoch's gather window in every rank's mailbox (rem_win[rank] = mine)
+    unsigned long long *rem_flag[P2P_MAXR];          // flag area of every rank's mailbox
+    double *dst;                                     // my replicated array at the offset of rank 0's slab
+    int rank, nranks;
+    unsigned long long epoch;
+    double *err;
+};
+__global__ void __launch_bounds__(P2P_THREADS) k_allgather_p2p(GatherArgs a) {
+    if (a.err[0] != 0.) return;
+    const long long n2 = a.cnt / 2;
+    const long long chunk = (n2 + gridDim.x - 1) / gridDim.x;
+    const long long c0 = (long long)blockIdx.x * chunk, c1 = (c0 + chunk < n2) ? c0 + chunk : n2;
+    // 1. put my chunk into every rank's window (my own included: one code path, and the unpack below is uniform)
+    const double2 *src = reinterpret_cast<const double2 *>(a.src);
+    for (int r = 0; r < a.nranks; r++) {
+        double2 *dst = reinterpret_cast<double2 *>(a.rem_win[(a.rank + r) % a.nranks] + (long long)a.rank * a.cnt);      // start with myself, then the ring: spreads the links
+        for (long long k = c0 + threadIdx.x; k < c1; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    // 2. publish chunk blockIdx.x to every destination, 3. wait for chunk blockIdx.x of every source
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < a.nranks) {
+        const int t = threadIdx.x;
+        p2p_st_flag(a.rem_flag[t] + P2P_AG_FLAG0 + a.rank * P2P_AG_NCTA + blockIdx.x, a.epoch);
+        if (!p2p_wait(a.rem_flag[a.rank] + P2P_AG_FLAG0 + t * P2P_AG_NCTA + blockIdx.x, a.epoch, a.err)) bad = 1;
+    }
+    __syncthreads();
+    if (bad) return;
+    // 4. unpack: window -> the level's array (rows of all ranks are contiguous in both)
+    const double *win = a.rem_win[a.rank];
+    for (int s = 0; s < a.nranks; s++) {
+        const double2 *w2 = reinterpret_cast<const double2 *>(win + (long long)s * a.cnt);
+        double2 *d2p = reinterpret_cast<double2 *>(a.dst + (long long)s * a.cnt);
+        for (long long k = c0 + threadIdx.x; k < c1; k += blockDim.x) d2p[k] = __ldcg(w2 + k);
     }
 }
 

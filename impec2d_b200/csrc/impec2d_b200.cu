@@ -100,7 +100,9 @@ struct impec_ctx {
     bool p2p_halo = false;                          // ... and so do the halo rows (IMPEC_P2P_HALO=0/1)
     unsigned char *mail = nullptr, *peer_mail[P2P_MAXR] = {};
     size_t p2p_slot_bytes = 0;
-    unsigned long long halo_epoch = 0, ar_epoch = 0;
+    size_t p2p_win_bytes = 0;                       // one all-gather window (the restricted right-hand side of the first replicated level)
+    bool p2p_gather = false;                        // ... and that all-gather too (IMPEC_P2P_GATHER=0/1)
+    unsigned long long halo_epoch = 0, ar_epoch = 0, ag_epoch = 0;
 #endif
     // CUDA graph of the replicated multigrid tail (levels >= tail_level): identical launch sequence every visit
     int tail_level = -1;
@@ -295,7 +297,10 @@ static int p2p_setup(impec_ctx *ctx) {
     if (R > P2P_MAXR) ok = 0;
     // mailbox: flags | all-reduce records | 2 sides x 2 parities of (2 fields x IMPEC_GH rows of the fine level)
     ctx->p2p_slot_bytes = (size_t)2 * IMPEC_GH * ctx->g.ld * sizeof(double);
-    const size_t bytes = kP2PHaloOff + 4 * ctx->p2p_slot_bytes;
+    // ... | 2 parities of an all-gather window holding the interior rows of the first replicated level
+    ctx->p2p_win_bytes = 0;
+    if (ctx->Ld > 0 && ctx->Ld < (int)ctx->L.size()) { const Grid &gl = ctx->L[ctx->Ld].gl; ctx->p2p_win_bytes = (size_t)R * gl.N1 * gl.ld * sizeof(double); }
+    const size_t bytes = kP2PHaloOff + 4 * ctx->p2p_slot_bytes + 2 * ctx->p2p_win_bytes;
     void *m = nullptr;
     CUDA_TRY(ctx, cudaMalloc(&m, bytes));
     CUDA_TRY(ctx, cudaMemsetAsync(m, 0, bytes, ctx->stream));
@@ -324,6 +329,7 @@ static int p2p_setup(impec_ctx *ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->p2p = flag > 0.5;
     { const char *eh = getenv("IMPEC_P2P_HALO"); ctx->p2p_halo = ctx->p2p && (eh ? atoi(eh) != 0 : true); }
+    { const char *eg = getenv("IMPEC_P2P_GATHER"); ctx->p2p_gather = ctx->p2p && ctx->p2p_win_bytes > 0 && (eg ? atoi(eg) != 0 : true); }
     if (!ctx->p2p)
         for (int r = 0; r < R; r++) { if (r != ctx->rank && ctx->peer_mail[r]) cudaIpcCloseMemHandle(ctx->peer_mail[r]); ctx->peer_mail[r] = nullptr; }
     return IMPEC_OK;
@@ -348,6 +354,20 @@ static int p2p_exchange(impec_ctx *ctx, double *a, double *b, const Grid &g, int
     h.my_hi = (const double *)(me + kP2PHaloOff + (2 + par) * ctx->p2p_slot_bytes); h.my_hi_flag = (const unsigned long long *)me + 64;
     h.err = ctx->scal + S_ERR;
     LAUNCH(ctx, k_halo_p2p, dim3(P2P_NCTA), dim3(P2P_THREADS), h);
+    return IMPEC_OK;
+}
+// all-gather of `n` doubles per rank (contiguous rows of a slab) into dst_rank0 + rank * n on every rank
+static int p2p_allgather(impec_ctx *ctx, const double *send, double *recv, long long n) {
+    GatherArgs a;
+    a.src = send; a.cnt = n; a.dst = recv; a.rank = ctx->rank; a.nranks = ctx->nranks;
+    a.epoch = ++ctx->ag_epoch;
+    const size_t off = kP2PHaloOff + 4 * ctx->p2p_slot_bytes + (size_t)(a.epoch & 1) * ctx->p2p_win_bytes;
+    for (int r = 0; r < P2P_MAXR; r++) {
+        a.rem_win[r] = r < ctx->nranks ? (double *)(ctx->peer_mail[r] + off) : nullptr;
+        a.rem_flag[r] = r < ctx->nranks ? (unsigned long long *)ctx->peer_mail[r] : nullptr;
+    }
+    a.err = ctx->scal + S_ERR;
+    LAUNCH(ctx, k_allgather_p2p, dim3(P2P_AG_NCTA), dim3(P2P_THREADS), a);
     return IMPEC_OK;
 }
 static int p2p_allreduce(impec_ctx *ctx, double *buf, int n, int op) {
@@ -613,7 +633,7 @@ extern "C" const char *impec_comm_backend(const impec_ctx *ctx) {
     if (!ctx || ctx->nranks == 1) return "single";
     if (ctx->has_cb) return "callbacks";
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
-    if (ctx->p2p) return ctx->p2p_halo ? "nvlink-p2p+nccl" : "nccl+p2p-allreduce";
+    if (ctx->p2p) return ctx->p2p_halo ? (ctx->p2p_gather ? "nvlink-p2p (halo rows, scalar all-reduce, coarse right-hand-side all-gather) + nccl (bootstrap, coefficient all-gather)" : "nvlink-p2p+nccl") : "nccl+p2p-allreduce";
     if (ctx->comm_ready) return "nccl";
 #endif
     return "none";
@@ -1010,7 +1030,11 @@ static int gather_coarse_rhs(impec_ctx *ctx, int l) {
     if (!at_transition(ctx, l)) return IMPEC_OK;
     Level &Lc = ctx->L[l + 1];
     const size_t r0 = (size_t)IMPEC_GH * Lc.gl.ld;
-    return comm_allgather(ctx, Lc.fl + r0, Lc.f + r0, (long long)Lc.gl.N1 * Lc.gl.ld);
+    const long long n = (long long)Lc.gl.N1 * Lc.gl.ld;
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    if (ctx->p2p_gather && !ctx->has_cb && (size_t)n * ctx->nranks * sizeof(double) <= ctx->p2p_win_bytes) return p2p_allgather(ctx, Lc.fl + r0, Lc.f + r0, n);
+#endif
+    return comm_allgather(ctx, Lc.fl + r0, Lc.f + r0, n);
 }
 static int fused_post(Cycle &C, int l, const double *f, double *part, long long *nparts) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];

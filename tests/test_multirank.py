@@ -15,6 +15,8 @@ def run(world, N1, N2, stype, diffusion, steps, port, extra_env=None):
            "--master-port", str(port), os.path.join(ROOT, "tests", "multirank_worker.py"), str(N1), str(N2), str(stype), str(diffusion), str(steps)]
     env = dict(os.environ, OMP_NUM_THREADS="1", IMPEC_DIST_MIN_CELLS="0")
     env.update(extra_env or {})
+    for k in [k for k, v in env.items() if v is None]:
+        del env[k]
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(" ok: ") == world, out.stdout
@@ -28,3 +30,9 @@ def test_four_ranks(): run(4, 64, 32, 1, 0, 1, 29613)
 # the register-march multigrid kernels (big levels only by default) forced onto the slab levels: chunk edges at slab
 # boundaries, the 2 halo rows PRE stores for its neighbours, coarse slab views at the transition level
 def test_two_ranks_marching_kernels(): run(2, 128, 128, 0, 0, 1, 29614, {"IMPEC_MARCH_MIN_CELLS": "0"})
+
+
+def test_two_ranks_default_replication_threshold():
+    """WITHOUT IMPEC_DIST_MIN_CELLS (ADVICE r1, high): on a small grid every coarse level falls under the default 4M-cell threshold;
+    level 0 must still be distributed (its vectors alias the slab-sized PCG vectors) and everything below replicated."""
+    run(2, 64, 64, 0, 0, 1, 29616, {"IMPEC_DIST_MIN_CELLS": None})

@@ -13,7 +13,7 @@ if world > 1:
     if rank == 0: assert I.load().impec_nccl_unique_id(idbuf) == 0
     idt = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device="cuda"); dist.broadcast(idt, src=0)
     nccl_id = bytes(idt.cpu().tolist())
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 P = I.default_params(N1=N, N2=N, x_ub=1.41421356237, y_ub=1.41421356237, stype=0, nu=2/3, eps=1e-14)
 ctx = I.Context(P, device=lr, rank=rank, nranks=world, nccl_id=nccl_id, stream=C.c_void_p(stream.cuda_stream))
 row0, nrows = ctx.local_rows()
