@@ -156,6 +156,7 @@ class Context:
 
     def mg_levels(self): return self.L.impec_mg_levels(self._h)
     def kernel_launches(self): return self.L.impec_kernel_launches(self._h)
+    def overlapped_exchanges(self): return self.L.impec_overlapped_exchanges(self._h)
     def reset_state(self): self._chk(self.L.impec_reset_state(self._h))
     def set_option(self, key, value): self._chk(self.L.impec_set_option(self._h, key.encode(), float(value)))
     def synchronize(self): self._chk(self.L.impec_synchronize(self._h))

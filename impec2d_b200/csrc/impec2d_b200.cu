@@ -104,6 +104,13 @@ struct impec_ctx {
     bool p2p_gather = false;                        // ... and that all-gather too (IMPEC_P2P_GATHER=0/1)
     unsigned long long halo_epoch = 0, ar_epoch = 0, ag_epoch = 0;
 #endif
+    // Halo exchange overlapped with interior compute: the exchange and the two slab-edge row chunks of its consumer run on a
+    // second, high-priority stream while the interior chunks of the same kernel run on the main stream (halo_overlapped()).
+    bool overlap = true;                            // option "halo_overlap" / IMPEC_HALO_OVERLAP=0/1
+    long long overlapped = 0;                       // exchanges issued that way (diagnostic)
+#ifndef IMPEC_EMU
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+#endif
     // CUDA graph of the replicated multigrid tail (levels >= tail_level): identical launch sequence every visit
     int tail_level = -1;
     // the same tail as ONE persistent launch (kernels_tail.inl): program of phases in device memory, barrier counter, error flag
@@ -138,7 +145,9 @@ static inline dim3 grid2d(int nx, int ny) { return dim3((unsigned)((nx + BX - 1)
 static const dim3 kBlock(BX, BY);
 // k_pcg_matvec_march: a CTA marches down `rows` rows of a 256-column strip (64 rows; 32 on short slabs so that the grid
 // still fills the 148 SMs several times over)
-static inline int matvec_march_rows(const Grid &g) { return g.N1 > 4096 ? 64 : 32; }
+// (IMPEC_MARCH_ROWS: test hook -- short chunks so that small grids have interior chunks and exercise the overlapped halo exchange)
+static inline int march_rows_override() { static const int v = [] { const char *e = getenv("IMPEC_MARCH_ROWS"); const int r = e ? atoi(e) : 0; return (r >= 4 && r % 4 == 0) ? r : 0; }(); return v; }
+static inline int matvec_march_rows(const Grid &g) { if (march_rows_override()) return march_rows_override(); return g.N1 > 4096 ? 64 : 32; }
 static inline dim3 matvec_march_grid(const Grid &g) { const int r = matvec_march_rows(g); return dim3((unsigned)((g.N2 + 2 * MV_BLOCK - 1) / (2 * MV_BLOCK)), (unsigned)((g.N1 + r - 1) / r)); }
 static inline dim3 update_xr_grid(const Grid &g) { return dim3((unsigned)((g.N2 + 2 * UX_BLOCK - 1) / (2 * UX_BLOCK)), (unsigned)((g.N1 + UX_ROWS - 1) / UX_ROWS)); }
 
@@ -414,6 +423,42 @@ static int exchange_rows2(impec_ctx *ctx, double *a, double *b, const Grid &g, i
     if (b) TRY(exchange_rows(ctx, b, g, n));
     return IMPEC_OK;
 }
+// ---- halo exchange overlapped with interior compute
+// A marching kernel works on chunks of rows; only the first and the last chunk of a slab read halo rows.  `xchg` issues the exchange
+// of exactly the rows the kernel reads, `launch(y0, ys, ny)` launches the kernel on the ny chunks y0, y0 + ys, ...  Overlapped form:
+//     main stream :  [producer] -- fork --> interior chunks (1 .. ny-2) ----------------------- join --> [next kernel]
+//     side stream :               fork --> exchange --> chunk 0 and chunk ny-1 (the halo readers) --> join
+// so the NVLink round trip of the exchange (17-20 us) and the two edge chunks hide behind the interior chunks.  The side stream has
+// the higher priority: its CTAs are placed as soon as interior CTAs retire.  Same kernels, same arithmetic: bit-identical.
+template <class X, class K>
+static int halo_overlapped(impec_ctx *ctx, bool dist, int ny, int rows_per_chunk, int N1, X xchg, K launch) {
+    // (the last chunk must be at least 4 rows tall, or the chunk before it would read halo rows as well)
+    const bool ov = dist && ctx->overlap && ctx->nranks > 1 && ny >= 4 && rows_per_chunk >= 4 && N1 - (ny - 1) * rows_per_chunk >= 4;
+    if (!ov) { if (dist) TRY(xchg()); return launch(0, 1, ny); }
+    ctx->overlapped++;
+#ifndef IMPEC_EMU
+    if (!ctx->has_cb && ctx->side) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        cudaStream_t main = ctx->stream;
+        ctx->stream = ctx->side;
+        int rc = xchg();
+        if (rc == IMPEC_OK) rc = launch(0, ny - 1, 2);
+        ctx->stream = main;
+        if (rc != IMPEC_OK) return rc;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+        TRY(launch(1, 1, ny - 2));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        return IMPEC_OK;
+    }
+#endif
+    // emulated build / host-callback transport: the same three pieces, in order
+    TRY(xchg());
+    TRY(launch(0, ny - 1, 2));
+    return launch(1, 1, ny - 2);
+}
+static LevelDev chunked(LevelDev D, int y0, int ys) { D.cy0 = y0; D.cys = ys; return D; }
+
 extern "C" int impec_ctx_set_comm_callbacks(impec_ctx *ctx, const impec_comm_callbacks *cb) {
     if (!cb || !cb->sendrecv || !cb->allreduce || !cb->allgather || !cb->bcast) return fail(ctx, IMPEC_ERR_ARG, "incomplete callback table");
 #ifndef IMPEC_EMU
@@ -486,7 +531,7 @@ extern "C" const char *impec_last_error(const impec_ctx *ctx) { return ctx ? ctx
 
 extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
     if (!ctx) return;
-    if (getenv("IMPEC_VERBOSE")) fprintf(stderr, "impec2d_b200: %lld kernel launches, %lld of them marching multigrid kernels\n", ctx->launches, ctx->march_launches);
+    if (getenv("IMPEC_VERBOSE")) fprintf(stderr, "impec2d_b200: %lld kernel launches, %lld of them marching multigrid kernels, %lld halo exchanges overlapped with interior chunks\n", ctx->launches, ctx->march_launches, ctx->overlapped);
     cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->allocs) cudaFree(p);
     for (void *p : {(void *)ctx->well_i, (void *)ctx->well_j, (void *)ctx->well_q, (void *)ctx->well_md}) if (p) cudaFree(p);
@@ -497,6 +542,9 @@ extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
 #ifndef IMPEC_EMU
     if (ctx->tail_exec) cudaGraphExecDestroy(ctx->tail_exec);
     if (ctx->tail_graph) cudaGraphDestroy(ctx->tail_graph);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
 #endif
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -523,7 +571,15 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     CUDA_TRY(ctx, cudaSetDevice(device));
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    { const char *e = getenv("IMPEC_HALO_OVERLAP"); if (e) ctx->overlap = atoi(e) != 0; }
 #ifndef IMPEC_EMU
+    if (nranks > 1) {
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_hi));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
 #define SMEM_ATTR(kern) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)))
 #define SMEM_ATTR3(MODE, F32) SMEM_ATTR((k_mg_fused<MODE, F32, 64>)); SMEM_ATTR((k_mg_fused<MODE, F32, 32>)); SMEM_ATTR((k_mg_fused<MODE, F32, 16>))
     SMEM_ATTR3(FUSED_PLAIN, true); SMEM_ATTR3(FUSED_PLAIN, false);
@@ -599,7 +655,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
                 const int ctas_x = ((L.g.N2 + MGP_OWN - 1) / MGP_OWN + MG_BLOCK / 32 - 1) / (MG_BLOCK / 32);
                 int ch = 256;
                 while (ch > 32 && (long long)ctas_x * ((L.g.N1 + ch - 1) / ch) < 1200) ch /= 2;
-                L.march_rows = ch;
+                L.march_rows = march_rows_override() ? march_rows_override() : ch;
             }
         }
         const size_t nn = grid_elems(L.g);
@@ -642,6 +698,7 @@ extern "C" const char *impec_comm_backend(const impec_ctx *ctx) {
 extern "C" int impec_synchronize(impec_ctx *ctx) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return IMPEC_OK; }
 extern "C" int impec_mg_levels(const impec_ctx *ctx) { return (int)ctx->L.size(); }
 extern "C" long long impec_kernel_launches(const impec_ctx *ctx) { return ctx->launches; }
+extern "C" long long impec_overlapped_exchanges(const impec_ctx *ctx) { return ctx->overlapped; }
 
 extern "C" int impec_reset_state(impec_ctx *ctx) {
     ctx->prev_first_sweep = 1;
@@ -657,6 +714,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "fast_r0") { ctx->fast_r0 = value != 0.0; return IMPEC_OK; }
     if (k == "sgs_march") { ctx->sgs_march = value != 0.0; return IMPEC_OK; }
+    if (k == "halo_overlap") { ctx->overlap = value != 0.0; return IMPEC_OK; }
     if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
@@ -843,6 +901,7 @@ static LevelDev level_dev(const impec_ctx *ctx, int l, double mass) {
     D.g = L.g; D.AW = L.AW; D.AS = L.AS; D.AV = L.AV; D.DINV = L.DINV; D.mass = mass;
     D.AWf = L.AWf; D.ASf = L.ASf; D.AVf = L.AVf; D.DINVf = L.DINVf;
     D.pin = L.pin; D.sig_idx = L.sig_idx; D.sig = ctx->sigma_dev + l;
+    D.cy0 = 0; D.cys = 1;
     return D;
 }
 
@@ -982,17 +1041,24 @@ static dim3 march_grid(const Level &L, int own) {
 }
 // PLAIN and POST read the iterate with a halo that belongs to neighbouring tiles, so they cannot run in place:
 // they read L.x, write L.t and the two pointers are swapped (the level's current iterate is always L.x).
-static int fused_plain(Cycle &C, int l, const double *f, bool forward) {
+// xhalo > 0 (slab levels): exchange that many halo rows of the iterate first -- overlapped with the interior chunks on the marching path
+static int fused_plain(Cycle &C, int l, const double *f, bool forward, int xhalo = 0) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l];
     if (use_march(ctx, L)) {
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGS_OWN);
-#define MPLAIN(F32, C0) LAUNCH_COOP(ctx, (k_mg_march_post<F32, false, C0, 3>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, L.g, (const double *)nullptr, (double *)nullptr, L.march_rows)
-        if (ctx->links_f32) { if (forward) MPLAIN(true, 0); else MPLAIN(true, 1); } else { if (forward) MPLAIN(false, 0); else MPLAIN(false, 1); }
+        auto launch = [&](int y0, int ys, int ny) -> int {
+            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys);
+#define MPLAIN(F32, C0) LAUNCH_COOP(ctx, (k_mg_march_post<F32, false, C0, 3>), gg, dim3(MG_BLOCK), D, f, (const double *)L.x, L.t, L.g, (const double *)nullptr, (double *)nullptr, L.march_rows)
+            if (ctx->links_f32) { if (forward) MPLAIN(true, 0); else MPLAIN(true, 1); } else { if (forward) MPLAIN(false, 0); else MPLAIN(false, 1); }
 #undef MPLAIN
+            return IMPEC_OK;
+        };
+        TRY(halo_overlapped(ctx, xhalo > 0 && L.dist, (int)gm.y, L.march_rows, L.g.N1, [&]() { return exchange_rows(ctx, L.x, L.g, xhalo); }, launch));
         std::swap(L.x, L.t);
         return IMPEC_OK;
     }
+    if (xhalo > 0 && L.dist) TRY(exchange_rows(ctx, L.x, L.g, xhalo));
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PLAIN>, staged_grid<FUSED_PLAIN>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
                      (const double *)nullptr, (double *)nullptr, (double *)nullptr);
     else LAUNCH_FUSED(ctx, FUSED_PLAIN, L.th, fused_grid<FUSED_PLAIN>(L.g, L.th), C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
@@ -1006,19 +1072,25 @@ static const double *coarse_x_view(const impec_ctx *ctx, int l) {
     const Level &Lc = ctx->L[l + 1];
     return at_transition(ctx, l) ? Lc.x + (size_t)Lc.gl.i_off * Lc.gl.ld : Lc.x;
 }
+// On a slab level the IMPEC_HALO halo rows of f are exchanged first (overlapped with the interior chunks on the marching path)
 static int fused_pre(Cycle &C, int l, const double *f) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
     const bool tr = at_transition(ctx, l);
     if (use_march(ctx, L)) {
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGP_OWN);
-#define MPRE(F32, PF, MB) LAUNCH_COOP(ctx, (k_mg_march_pre<F32, PF, MB>), gm, dim3(MG_BLOCK), C.D[l], f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows)
-        if (!ctx->links_f32) MPRE(false, 4, 3);
-        else if (ctx->march_variant & 1) MPRE(true, 2, 4);      // 2 rows in flight, 122 registers, 4 CTAs per SM: 2.10 ms at 16384^2
-        else MPRE(true, 4, 3);                                  // 4 rows in flight, 168 registers, 3 CTAs per SM: 2.31 ms
+        auto launch = [&](int y0, int ys, int ny) -> int {
+            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys);
+#define MPRE(F32, PF, MB) LAUNCH_COOP(ctx, (k_mg_march_pre<F32, PF, MB>), gg, dim3(MG_BLOCK), D, f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows)
+            if (!ctx->links_f32) MPRE(false, 4, 3);
+            else if (ctx->march_variant & 1) MPRE(true, 2, 4);      // 2 rows in flight, 4 CTAs per SM
+            else MPRE(true, 4, 3);                                  // 4 rows in flight, 3 CTAs per SM
 #undef MPRE
-        return IMPEC_OK;
+            return IMPEC_OK;
+        };
+        return halo_overlapped(ctx, L.dist, (int)gm.y, L.march_rows, L.g.N1, [&]() { return exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO); }, launch);
     }
+    if (L.dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PRE>, staged_grid<FUSED_PRE>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
                      (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
     else LAUNCH_FUSED(ctx, FUSED_PRE, L.th, fused_grid<FUSED_PRE>(L.g, L.th), C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
@@ -1036,20 +1108,27 @@ static int gather_coarse_rhs(impec_ctx *ctx, int l) {
 #endif
     return comm_allgather(ctx, Lc.fl + r0, Lc.f + r0, n);
 }
+// If the coarse level is a slab level too, 2 halo rows of its iterate are exchanged first (overlapped with the interior chunks on the
+// marching path: only the first and the last chunk prolongate from coarse halo rows)
 static int fused_post(Cycle &C, int l, const double *f, double *part, long long *nparts) {
     impec_ctx *ctx = C.ctx; Level &L = ctx->L[l]; Level &Lc = ctx->L[l + 1];
     if (use_march(ctx, L)) {
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGS_OWN);
-#define MPOST(F32, MB) LAUNCH_COOP(ctx, (k_mg_march_post<F32, true, 1, MB>), gm, dim3(MG_BLOCK), C.D[l], f, (const double *)L.x, L.t, at_transition(ctx, l) ? Lc.gl : Lc.g, coarse_x_view(ctx, l), part, L.march_rows)
-        // 168 registers, 3 CTAs per SM.  (Forcing 4 CTAs per SM makes ptxas spill ~300 B per thread and DOUBLES the time:
-        // 2.13 -> 4.12 ms at 16384^2.)
-        if (!ctx->links_f32) MPOST(false, 3); else MPOST(true, 3);
+        auto launch = [&](int y0, int ys, int ny) -> int {
+            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys);
+#define MPOST(F32, MB) LAUNCH_COOP(ctx, (k_mg_march_post<F32, true, 1, MB>), gg, dim3(MG_BLOCK), D, f, (const double *)L.x, L.t, at_transition(ctx, l) ? Lc.gl : Lc.g, coarse_x_view(ctx, l), part, L.march_rows)
+            // 168 registers, 3 CTAs per SM.  (Forcing 4 CTAs per SM makes ptxas spill ~300 B per thread and DOUBLES the time.)
+            if (!ctx->links_f32) MPOST(false, 3); else MPOST(true, 3);
 #undef MPOST
+            return IMPEC_OK;
+        };
+        TRY(halo_overlapped(ctx, Lc.dist, (int)gm.y, L.march_rows, L.g.N1, [&]() { return exchange_rows(ctx, Lc.x, Lc.g, 2); }, launch));
         std::swap(L.x, L.t);
         if (nparts) *nparts = (long long)gm.x * gm.y;
         return IMPEC_OK;
     }
+    if (Lc.dist) TRY(exchange_rows(ctx, Lc.x, Lc.g, 2));
     const dim3 gr = use_staged(ctx) ? staged_grid<FUSED_POST>(L.g) : fused_grid<FUSED_POST>(L.g, L.th);
     if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_POST>, gr, kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
                      coarse_x_view(ctx, l), (double *)nullptr, part);
@@ -1224,11 +1303,15 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
         if (fused && C.ncoarse == 1 && ctx->sgs_march && use_march(ctx, L)) {
             // one symmetric sweep from zero (the Crank-Nicolson preconditioner) on a big level: all four colour stages in ONE march.
             // On a slab the 3 halo rows of f make the sweep exact on the interior rows (no exchange of x between the two half sweeps).
-            if (L.dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
             ctx->march_launches++;
             const dim3 gm = march_grid(L, MGP_OWN);
-            if (ctx->links_f32) LAUNCH_COOP(ctx, k_sgs_march<true>, gm, dim3(MG_BLOCK), C.D[l], f, L.x, dot_part, L.march_rows);
-            else LAUNCH_COOP(ctx, k_sgs_march<false>, gm, dim3(MG_BLOCK), C.D[l], f, L.x, dot_part, L.march_rows);
+            auto launch = [&](int y0, int ys, int ny) -> int {
+                const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys);
+                if (ctx->links_f32) LAUNCH_COOP(ctx, k_sgs_march<true>, gg, dim3(MG_BLOCK), D, f, L.x, dot_part, L.march_rows);
+                else LAUNCH_COOP(ctx, k_sgs_march<false>, gg, dim3(MG_BLOCK), D, f, L.x, dot_part, L.march_rows);
+                return IMPEC_OK;
+            };
+            TRY(halo_overlapped(ctx, L.dist, (int)gm.y, L.march_rows, L.g.N1, [&]() { return exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO); }, launch));
             if (dot_part && dot_nparts) *dot_nparts = (long long)gm.x * gm.y;
             return IMPEC_OK;
         }
@@ -1236,8 +1319,8 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
             CUDA_TRY(ctx, cudaMemsetAsync(L.x, 0, grid_elems(L.g) * sizeof(double), ctx->stream));
             if (L.dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
             for (int s = 0; s < C.ncoarse; s++) {
-                TRY(fused_plain(C, l, f, true));  if (L.dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
-                TRY(fused_plain(C, l, f, false)); if (L.dist && s + 1 < C.ncoarse) TRY(exchange_rows(ctx, L.x, L.g, 2));
+                TRY(fused_plain(C, l, f, true, s > 0 ? 2 : 0));          // (the first sweep starts from x = 0: nothing to exchange)
+                TRY(fused_plain(C, l, f, false, 2));
             }
         } else
             for (int s = 0; s < C.ncoarse; s++) { TRY(smooth(C, l, f, x, true, s == 0)); TRY(smooth(C, l, f, x, false, false)); }
@@ -1248,22 +1331,20 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
     if (fused) {
         // On a slab level every kernel that reads a field with a halo is preceded by the exchange of exactly the rows it
         // reads (f: 3, x: 2); with the halos in place each rank computes the same values a single GPU would.
+        // (the exchanges live in fused_pre / fused_post / fused_plain, which overlap them with the interior row chunks on the marching path)
         const bool dist = L.dist, tr = at_transition(ctx, l);
-        if (dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
-        TRY(fused_pre(C, l, f));                                      // pre-smooth(0) + residual + restrict; writes x on 2 halo rows too
+        TRY(fused_pre(C, l, f));                                      // [f: 3 halo rows] pre-smooth(0) + residual + restrict; writes x on 2 halo rows too
         if (dist && use_staged(ctx)) TRY(exchange_rows(ctx, L.x, L.g, 2));   // (the staged variant writes its interior only)
         TRY(gather_coarse_rhs(ctx, l));
         TRY(mg_cycle(C, l + 1, Lc.f));
-        if (Lc.dist) TRY(exchange_rows(ctx, Lc.x, Lc.g, 2));
         for (int gc = 1; gc < gamma; gc++) {
-            TRY(fused_post(C, l, f, nullptr, nullptr));               // prolong + correct + backward sweep
-            if (dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
+            TRY(fused_post(C, l, f, nullptr, nullptr));               // [coarse x: 2 halo rows] prolong + correct + backward sweep
             if (!dist && ctx->fused_mid && !use_staged(ctx)) {
                 // sweep + residual + restriction in one tile kernel (needs 4 halo rows: single-GPU / replicated levels only)
                 LAUNCH_FUSED(ctx, FUSED_MID, L.th, fused_grid<FUSED_MID>(L.g, L.th), C.D[l], f, (const double *)L.x, L.t, 0, Lc.g, (const double *)nullptr, Lc.f, (double *)nullptr);
                 std::swap(L.x, L.t);
             } else {
-            TRY(fused_plain(C, l, f, true));
+            TRY(fused_plain(C, l, f, true, 2));                       // [x: 2 halo rows]
             if (dist) TRY(exchange_rows(ctx, L.x, L.g, 2));
             LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1 + 2), kBlock, C.D[l], f, (const double *)L.x, L.r);
             if (tr) LAUNCH(ctx, k_restrict, grid2d(Lc.gl.N2, Lc.gl.N1), kBlock, L.g, L.r, Lc.gl, Lc.fl);
@@ -1271,7 +1352,6 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
             }
             TRY(gather_coarse_rhs(ctx, l));
             TRY(mg_cycle(C, l + 1, Lc.f));
-            if (Lc.dist) TRY(exchange_rows(ctx, Lc.x, Lc.g, 2));
         }
         TRY(fused_post(C, l, f, dot_part, dot_nparts));               // prolong + correct + post-smooth (+ <f,x>)
         return IMPEC_OK;
@@ -1381,11 +1461,17 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         it++;
         if (fuse_dir) {
             // beta = gamma_new / gamma_old sits in scal[S_BETA_NUM], scal[S_BETA_DEN] (set at the end of the previous pass)
-            TRY(exchange_rows2(ctx, ctx->L[0].x, first_dir ? nullptr : dcur, g, 1));
             if (ctx->matvec_march) {
-                if (first_dir) LAUNCH_COOP(ctx, k_pcg_matvec_march<true>, gmm, dim3(MV_BLOCK), A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part, mvrows);
-                else LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, gmm, dim3(MV_BLOCK), A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part, mvrows);
+                // [z and d: 1 halo row each, one exchange] overlapped with the interior row chunks
+                auto launch = [&](int y0, int ys, int ny) -> int {
+                    const dim3 gg(gmm.x, (unsigned)ny); const LevelDev D = chunked(A, y0, ys);
+                    if (first_dir) LAUNCH_COOP(ctx, k_pcg_matvec_march<true>, gg, dim3(MV_BLOCK), D, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part, mvrows);
+                    else LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, gg, dim3(MV_BLOCK), D, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part, mvrows);
+                    return IMPEC_OK;
+                };
+                TRY(halo_overlapped(ctx, ctx->L[0].dist, (int)gmm.y, mvrows, g.N1, [&]() { return exchange_rows2(ctx, ctx->L[0].x, first_dir ? nullptr : dcur, g, 1); }, launch));
             } else {
+                TRY(exchange_rows2(ctx, ctx->L[0].x, first_dir ? nullptr : dcur, g, 1));
                 if (first_dir) LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<true>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
                 else LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, gmv, kFusedBlock, kFusedSmem, A, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part);
             }

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(MV_BLOCK, 3) k_pcg_matvec_march(LevelDev L, co
     const size_t ld = (size_t)g.ld;
     const int lane = threadIdx.x & 31;
     const int jA = 2 * (int)(blockIdx.x * MV_BLOCK + threadIdx.x);       // columns jA, jA+1
-    const int ia = (int)blockIdx.y * nrows;
+    const int ia = chunk_of(L) * nrows;
     const int ib = (ia + nrows < g.N1) ? ia + nrows : g.N1;               // rows [ia, ib)
     const bool ok = jA < g.N2, two = jA + 1 < g.N2;
     // lane 0 also evaluates column jA-1, lane 31 column jA+2 (allocated: pad columns on both sides of a row)
@@ -467,5 +467,5 @@ __global__ void __launch_bounds__(MV_BLOCK, 3) k_pcg_matvec_march(LevelDev L, co
         }
     }
     dotv = block_reduce<RED_SUM>(dotv);
-    if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
+    if (threadIdx.x == 0) part[chunk_of(L) * gridDim.x + blockIdx.x] = dotv;
 }

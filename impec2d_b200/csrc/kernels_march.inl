@@ -67,22 +67,17 @@ IMPEC_D double sum4(double w0, double w1, double w2, double w3, double v0, doubl
 
 // ================================================================ PRE: sweep from zero + residual + restriction
 template <bool F32> struct PreRow { d2 f; CoefRow<F32> c; };
-// (k is a valid address for every lane: columns outside the level are clamped to column 0 by the caller and every use of the loaded
-// values is masked by the act* / own flags, so the loads need no guard -- and no zero-fill of 12 registers per row)
-template <bool F32> IMPEC_D PreRow<F32> pre_load(const Coef<F32> &A, const double *__restrict__ f, long long k, bool) {
-    PreRow<F32> R;
-    R.f = ld2(f + k); R.c = coef_load<F32>(A, (size_t)k);
+template <bool F32> IMPEC_D PreRow<F32> pre_load(const Coef<F32> &A, const double *__restrict__ f, long long k, bool ok) {
+    PreRow<F32> R; R.f.x = R.f.y = 0.; R.c = coef_zero<F32>();
+    if (ok) { R.f = ld2(f + k); R.c = coef_load<F32>(A, (size_t)k); }
     return R;
 }
-// Pipeline state in FOUR ROTATING SLOTS: the data of row r lives in slot r & 3 for as long as it is needed (links and right-hand side
-// for 3 steps, final iterate values for 3 steps, the j-restricted residual for 4).  The march is unrolled four rows deep and the
-// slot of every access is a compile-time constant of the unrolled step (template parameter PH = row & 3), so the state never moves:
-// the earlier formulation shifted ~45 registers per row with IMAD.MOV (22 % of the kernel's instructions, ncu: issue-bound at 50 %).
 template <bool F32> struct PreState {
-    double xF[4], e0[4];                   // first-colour value of the row and the first-colour value next to its second-colour cell
-    d2 f[4]; CoefRow<F32> c[4];
-    double xl[4], xA[4], xB[4], xr[4];     // final values of the row: columns jA-1 | jA, jA+1 | jA+2
-    double h[4];                           // j-restricted residual of the row
+    double xF1, e01;                       // row t-1: its first-colour value and the first-colour value next to its second-colour cell
+    d2 f1; CoefRow<F32> c1;                // row t-1
+    double xl2, xA2, xB2, xr2; CoefRow<F32> c2;   // row t-2 (final)
+    double xl3, xA3, xB3, xr3;             // row t-3 (final)
+    double h0, h1, h2, h3;                 // j-restricted residual of rows t-5 .. t-2
 };
 struct PreGeom {
     int t_rlo, t_rhi;                      // active rows
@@ -94,10 +89,9 @@ struct PreGeom {
     long long kcb, ldc;                    // coarse: index of (row 0, J), pitch
 };
 
-// AF: on row t the even-column cell A carries the first colour.  PH = t & 3 (slot of row t).
-template <bool F32, bool AF, int PH>
+// AF: on row t the even-column cell A carries the first colour
+template <bool F32, bool AF>
 IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const PreGeom &G, double *__restrict__ x, double *__restrict__ fc) {
-    constexpr int s0 = PH, s1 = (PH + 3) & 3, s2 = (PH + 2) & 3, s3 = (PH + 1) & 3;      // slots of rows t, t-1, t-2, t-3
     // 1. first colour on row t (zero guess: no neighbours)
     const bool act0 = G.colok && t >= G.t_rlo && t < G.t_rhi;
     const double xF = act0 ? (AF ? R.f.x * (double)R.c.dinv.x : R.f.y * (double)R.c.dinv.y) : 0.;
@@ -106,15 +100,15 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
     const bool act1 = G.colok && t - 1 >= G.t_rlo && t - 1 < G.t_rhi;
     double xl1, xA1, xB1, xr1;
     if (AF) {   // row t-1: B first, A second
-        double off = (double)S.c[s1].aw.x * S.xA[s2];
-        off = fma((double)R.c.aw.x, xF, off); off = fma((double)S.c[s1].as.x, S.e0[s1], off); off = fma((double)S.c[s1].as.y, S.xF[s1], off);
-        const double xS = act1 ? (S.f[s1].x + off) * (double)S.c[s1].dinv.x : 0.;
-        xA1 = xS; xB1 = S.xF[s1]; xl1 = S.e0[s1]; xr1 = IMPEC_SHFL_DOWN(xS, 1);
+        double off = (double)S.c1.aw.x * S.xA2;
+        off = fma((double)R.c.aw.x, xF, off); off = fma((double)S.c1.as.x, S.e01, off); off = fma((double)S.c1.as.y, S.xF1, off);
+        const double xS = act1 ? (S.f1.x + off) * (double)S.c1.dinv.x : 0.;
+        xA1 = xS; xB1 = S.xF1; xl1 = S.e01; xr1 = IMPEC_SHFL_DOWN(xS, 1);
     } else {    // row t-1: A first, B second
-        double off = (double)S.c[s1].aw.y * S.xB[s2];
-        off = fma((double)R.c.aw.y, xF, off); off = fma((double)S.c[s1].as.y, S.xF[s1], off); off = fma((double)S.c[s1].as2, S.e0[s1], off);
-        const double xS = act1 ? (S.f[s1].y + off) * (double)S.c[s1].dinv.y : 0.;
-        xA1 = S.xF[s1]; xB1 = xS; xr1 = S.e0[s1]; xl1 = IMPEC_SHFL_UP(xS, 1);
+        double off = (double)S.c1.aw.y * S.xB2;
+        off = fma((double)R.c.aw.y, xF, off); off = fma((double)S.c1.as.y, S.xF1, off); off = fma((double)S.c1.as2, S.e01, off);
+        const double xS = act1 ? (S.f1.y + off) * (double)S.c1.dinv.y : 0.;
+        xA1 = S.xF1; xB1 = xS; xr1 = S.e01; xl1 = IMPEC_SHFL_UP(xS, 1);
     }
     if (G.own && t - 1 >= G.wlo && t - 1 < G.whi) st2(x + G.kb + (long long)(t - 1) * G.ld, xA1, xB1);
     // 3. residual on row t-2 (same parity as row t).  After a sweep from zero: first colour = sum over all 8 neighbours,
@@ -123,13 +117,13 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
     const long long k2 = G.kb + (long long)(t - 2) * G.ld;
     double rA, rB;
     if (AF) {
-        rA = sum8((double)S.c[s2].aw.x, (double)S.c[s1].aw.x, (double)S.c[s2].as.x, (double)S.c[s2].as.y, (double)S.c[s2].av.x, (double)S.c[s1].av.x, (double)S.c[s2].av.y, (double)S.c[s1].av.y,
-                  S.xA[s3], xA1, S.xl[s2], S.xB[s2], S.xl[s3], xl1, S.xB[s3], xB1);
-        rB = sum4((double)S.c[s2].av.y, (double)S.c[s1].av.y, (double)S.c[s2].av2, (double)S.c[s1].av2, S.xA[s3], xA1, S.xr[s3], xr1);
+        rA = sum8((double)S.c2.aw.x, (double)S.c1.aw.x, (double)S.c2.as.x, (double)S.c2.as.y, (double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y,
+                  S.xA3, xA1, S.xl2, S.xB2, S.xl3, xl1, S.xB3, xB1);
+        rB = sum4((double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2, S.xA3, xA1, S.xr3, xr1);
     } else {
-        rB = sum8((double)S.c[s2].aw.y, (double)S.c[s1].aw.y, (double)S.c[s2].as.y, (double)S.c[s2].as2, (double)S.c[s2].av.y, (double)S.c[s1].av.y, (double)S.c[s2].av2, (double)S.c[s1].av2,
-                  S.xB[s3], xB1, S.xA[s2], S.xr[s2], S.xA[s3], xA1, S.xr[s3], xr1);
-        rA = sum4((double)S.c[s2].av.x, (double)S.c[s1].av.x, (double)S.c[s2].av.y, (double)S.c[s1].av.y, S.xl[s3], xl1, S.xB[s3], xB1);
+        rB = sum8((double)S.c2.aw.y, (double)S.c1.aw.y, (double)S.c2.as.y, (double)S.c2.as2, (double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2,
+                  S.xB3, xB1, S.xA2, S.xr2, S.xA3, xA1, S.xr3, xr1);
+        rA = sum4((double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y, S.xl3, xl1, S.xB3, xB1);
     }
     if (!act2 || k2 == G.pin) rA = 0.;
     if (!act2 || k2 + 1 == G.pin) rB = 0.;
@@ -139,28 +133,28 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
     if (G.clamp_r) rr = rB;
     double h = 0.25 * rl;
     h += 0.75 * rA; h += 0.75 * rB; h += 0.25 * rr;
-    S.h[s2] = h;                                   // rows t-5, t-4, t-3, t-2 of h sit in slots s1, s0, s3, s2
-    if (AF) {                                      // t even: rows t-5 .. t-2 are rows 2I-1 .. 2I+2 of coarse row I
+    S.h0 = S.h1; S.h1 = S.h2; S.h2 = S.h3; S.h3 = h;
+    if (AF) {                                  // t even: rows t-5 .. t-2 are rows 2I-1 .. 2I+2 of coarse row I
         const int I = (t - 4) >> 1;
         if (G.own_c && I >= G.Ilo && I < G.Ihi) {
-            const double t0 = (I == 0 && G.wall_lo) ? S.h[s0] : S.h[s1];                  // row -1 mirrors onto row 0
-            const double t3 = (2 * I + 2 > G.N1 - 1 && G.wall_hi) ? S.h[s3] : S.h[s2];   // row N1 mirrors onto row N1-1
-            fc[G.kcb + (long long)I * G.ldc] = 0.25 * (0.25 * t0 + 0.75 * S.h[s0] + 0.75 * S.h[s3] + 0.25 * t3);
+            const double t0 = (I == 0 && G.wall_lo) ? S.h1 : S.h0;                   // row -1 mirrors onto row 0
+            const double t3 = (2 * I + 2 > G.N1 - 1 && G.wall_hi) ? S.h2 : S.h3;     // row N1 mirrors onto row N1-1
+            fc[G.kcb + (long long)I * G.ldc] = 0.25 * (0.25 * t0 + 0.75 * S.h1 + 0.75 * S.h2 + 0.25 * t3);
         }
     }
-    // the row's data stay where they are: only the new values are written into the slots of rows t and t-1
-    S.xl[s1] = xl1; S.xA[s1] = xA1; S.xB[s1] = xB1; S.xr[s1] = xr1;
-    S.xF[s0] = xF; S.e0[s0] = e0; S.f[s0] = R.f; S.c[s0] = R.c;
+    // shift the pipeline
+    S.xl3 = S.xl2; S.xA3 = S.xA2; S.xB3 = S.xB2; S.xr3 = S.xr2;
+    S.xl2 = xl1; S.xA2 = xA1; S.xB2 = xB1; S.xr2 = xr1; S.c2 = S.c1;
+    S.xF1 = xF; S.e01 = e0; S.f1 = R.f; S.c1 = R.c;
 }
 
 template <bool F32, int PF, int MINB>
 __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_pre(LevelDev L, const double *__restrict__ f, double *__restrict__ x, Grid gc, double *__restrict__ fc, int nrows) {
-    static_assert(PF == 2 || PF == 4, "rows in flight");
     const Grid g = L.g;
     const Coef<F32> A(L);
     const int lane = threadIdx.x & 31;
     const int gw = (int)blockIdx.x * (MG_BLOCK / 32) + (int)(threadIdx.x >> 5);
-    const int ia = (int)blockIdx.y * nrows;        // nrows is a multiple of 4: the slot of a row is a constant of the unrolled step
+    const int ia = chunk_of(L) * nrows;
     const int ib = (ia + nrows < g.N1) ? ia + nrows : g.N1;
     PreGeom G;
     G.jA = MGP_OWN * gw - 4 + 2 * lane; G.J = G.jA >> 1;
@@ -177,55 +171,47 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_pre(LevelDev L, con
     G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
     G.ldc = gc.ld; G.kcb = (long long)IMPEC_GH * gc.ld + (G.colok ? G.J : 0) + IMPEC_PJ;
     PreState<F32> S;
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        S.xF[a] = S.e0[a] = 0.; S.f[a].x = S.f[a].y = 0.; S.c[a] = coef_zero<F32>();
-        S.xl[a] = S.xA[a] = S.xB[a] = S.xr[a] = 0.; S.h[a] = 0.;
-    }
-    const int t0 = ia - 3, t1 = ib + 2;        // rows marched: [t0, t1]; t0 = 1 (mod 4)
+    S.xF1 = S.e01 = 0.; S.f1.x = S.f1.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
+    S.xl2 = S.xA2 = S.xB2 = S.xr2 = S.xl3 = S.xA3 = S.xB3 = S.xr3 = 0.; S.h0 = S.h1 = S.h2 = S.h3 = 0.;
+    const int t0 = ia - 3, t1 = ib + 2;        // rows marched: [t0, t1]; t0 is odd
     PreRow<F32> q[PF];
 #pragma unroll
     for (int u = 0; u < PF; u++) q[u] = pre_load<F32>(A, f, G.kb + (long long)((t0 + u <= t1) ? t0 + u : t1) * G.ld, G.colok);
-    for (int t = t0; t <= t1; t += 4) {
+    for (int t = t0; t <= t1; t += PF) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < PF; u++) {
             if (t + u > t1) continue;
-            const PreRow<F32> R = q[u % PF];
-            q[u % PF] = pre_load<F32>(A, f, G.kb + (long long)((t + u + PF <= t1) ? t + u + PF : t1) * G.ld, G.colok);
-            // row t + u: slot (1 + u) & 3; A carries the first colour on even rows (u odd)
-            if (u == 0) pre_step<F32, false, 1>(t, R, S, G, x, fc);
-            else if (u == 1) pre_step<F32, true, 2>(t + 1, R, S, G, x, fc);
-            else if (u == 2) pre_step<F32, false, 3>(t + 2, R, S, G, x, fc);
-            else pre_step<F32, true, 0>(t + 3, R, S, G, x, fc);
+            const PreRow<F32> R = q[u];
+            q[u] = pre_load<F32>(A, f, G.kb + (long long)((t + u + PF <= t1) ? t + u + PF : t1) * G.ld, G.colok);
+            if (u & 1) pre_step<F32, true>(t + u, R, S, G, x, fc);
+            else pre_step<F32, false>(t + u, R, S, G, x, fc);
         }
     }
 }
 
 // ================================================================ POST / PLAIN: (prolongation +) sweep from the current iterate
 template <bool F32, bool PROLONG> struct PostRow { d2 xin, f; CoefRow<F32> c; double e[6]; };
-// Rotating slots as in PreState (row r in slot r & 3): the iterate before the sweep, the new first-colour value and its neighbour
-// value, the right-hand side and the links of the rows t-1 .. t-3
 template <bool F32> struct PostState {
-    double il[4], iA[4], iB[4], ir[4];     // iterate before the sweep: columns jA-1 | jA, jA+1 | jA+2
-    double yF[4], e[4];                    // new first-colour value of the row; first-colour value next to its second-colour cell
-    d2 f[4]; CoefRow<F32> c[4];
+    double il1, iA1, iB1, ir1, il2, iA2, iB2, ir2, il3, iA3, iB3, ir3;   // iterate before the sweep on rows t-1, t-2, t-3
+    double yF2, yF3, e2;                   // new first-colour values of rows t-2, t-3; first-colour value next to row t-2's second-colour cell
+    d2 f1, f2; CoefRow<F32> c1, c2;        // rows t-1, t-2
 };
 struct PostGeom {
     int t_rlo, t_rhi, ia, ib;
     int jA; bool colok, own;
     long long kb, ld, pin;
 };
-// (as for pre_load: the address is valid for every lane and every use of the values is masked by act* / own)
 template <bool F32, bool PROLONG>
 IMPEC_D PostRow<F32, PROLONG> post_load(const Coef<F32> &A, const double *__restrict__ f, const double *__restrict__ xin, const Grid &g, const Grid &gc,
                                          const double *__restrict__ ec, const PostGeom &G, int t) {
     PostRow<F32, PROLONG> R;
-    const long long k = G.kb + (long long)t * G.ld;
-    R.xin = ld2(xin + k); R.f = ld2(f + k); R.c = coef_load<F32>(A, (size_t)k);
-    if (PROLONG) {
+    R.xin.x = R.xin.y = R.f.x = R.f.y = 0.; R.c = coef_zero<F32>();
 #pragma unroll
-        for (int a = 0; a < 6; a++) R.e[a] = 0.;
-        if (G.colok && t >= G.t_rlo && t < G.t_rhi) {
+    for (int a = 0; a < 6; a++) R.e[a] = 0.;
+    if (G.colok) {
+        const long long k = G.kb + (long long)t * G.ld;
+        R.xin = ld2(xin + k); R.f = ld2(f + k); R.c = coef_load<F32>(A, (size_t)k);
+        if (PROLONG && t >= G.t_rlo && t < G.t_rhi) {
             // cell-centred bilinear prolongation with edge replication (same clamps as k_mg_fused)
             const int I = t >> 1, J = G.jA >> 1;
             int In = (t & 1) ? I + 1 : I - 1, Jm = J - 1, Jp = J + 1;
@@ -239,13 +225,11 @@ IMPEC_D PostRow<F32, PROLONG> post_load(const Coef<F32> &A, const double *__rest
     return R;
 }
 
-// AF: on row t the even-column cell A carries the first colour (so do rows t-2; rows t-1, t-3 have B first).  PH = t & 3.
-template <bool F32, bool PROLONG, bool AF, int PH>
+// AF: on row t the even-column cell A carries the first colour (so do rows t-2; rows t-1, t-3 have B first)
+template <bool F32, bool PROLONG, bool AF>
 IMPEC_D void post_step(const int t, const PostRow<F32, PROLONG> &R, PostState<F32> &S, const PostGeom &G, double *__restrict__ x, double &dotv) {
-    constexpr int s0 = PH, s1 = (PH + 3) & 3, s2 = (PH + 2) & 3, s3 = (PH + 1) & 3;      // slots of rows t, t-1, t-2, t-3
     // 1. iterate on row t: x + P ec
     double a = R.xin.x, b = R.xin.y;
-    if (!G.colok) { a = 0.; b = 0.; }
     if (PROLONG && G.colok && t >= G.t_rlo && t < G.t_rhi) {
         const double pc = 0.75 * R.e[0] + 0.25 * R.e[1];
         const double pm = 0.75 * R.e[2] + 0.25 * R.e[3];
@@ -259,35 +243,38 @@ IMPEC_D void post_step(const int t, const PostRow<F32, PROLONG> &R, PostState<F3
     const bool act1 = G.colok && t - 1 >= G.t_rlo && t - 1 < G.t_rhi;
     double y, e1;
     if (AF) {   // row t-1: B first
-        const double off = sum8((double)S.c[s1].aw.y, (double)R.c.aw.y, (double)S.c[s1].as.y, (double)S.c[s1].as2, (double)S.c[s1].av.y, (double)R.c.av.y, (double)S.c[s1].av2, (double)R.c.av2,
-                                S.iB[s2], b, S.iA[s1], S.ir[s1], S.iA[s2], a, S.ir[s2], ir0);
-        y = act1 ? (S.f[s1].y + off) * (double)S.c[s1].dinv.y : S.iB[s1];
+        const double off = sum8((double)S.c1.aw.y, (double)R.c.aw.y, (double)S.c1.as.y, (double)S.c1.as2, (double)S.c1.av.y, (double)R.c.av.y, (double)S.c1.av2, (double)R.c.av2,
+                                S.iB2, b, S.iA1, S.ir1, S.iA2, a, S.ir2, ir0);
+        y = act1 ? (S.f1.y + off) * (double)S.c1.dinv.y : S.iB1;
         e1 = IMPEC_SHFL_UP(y, 1);
     } else {    // row t-1: A first
-        const double off = sum8((double)S.c[s1].aw.x, (double)R.c.aw.x, (double)S.c[s1].as.x, (double)S.c[s1].as.y, (double)S.c[s1].av.x, (double)R.c.av.x, (double)S.c[s1].av.y, (double)R.c.av.y,
-                                S.iA[s2], a, S.il[s1], S.iB[s1], S.il[s2], il0, S.iB[s2], b);
-        y = act1 ? (S.f[s1].x + off) * (double)S.c[s1].dinv.x : S.iA[s1];
+        const double off = sum8((double)S.c1.aw.x, (double)R.c.aw.x, (double)S.c1.as.x, (double)S.c1.as.y, (double)S.c1.av.x, (double)R.c.av.x, (double)S.c1.av.y, (double)R.c.av.y,
+                                S.iA2, a, S.il1, S.iB1, S.il2, il0, S.iB2, b);
+        y = act1 ? (S.f1.x + off) * (double)S.c1.dinv.x : S.iA1;
         e1 = IMPEC_SHFL_DOWN(y, 1);
     }
     // 3. second colour on row t-2: face neighbours new, diagonal neighbours (its own colour) old
     const bool act2 = G.colok && t - 2 >= G.t_rlo && t - 2 < G.t_rhi;
     double xA, xB;
-    if (AF) {   // row t-2: A first (new value yF), B second
-        const double off = sum8((double)S.c[s2].aw.y, (double)S.c[s1].aw.y, (double)S.c[s2].as.y, (double)S.c[s2].as2, (double)S.c[s2].av.y, (double)S.c[s1].av.y, (double)S.c[s2].av2, (double)S.c[s1].av2,
-                                S.yF[s3], y, S.yF[s2], S.e[s2], S.iA[s3], S.iA[s1], S.ir[s3], S.ir[s1]);
-        xA = S.yF[s2]; xB = act2 ? (S.f[s2].y + off) * (double)S.c[s2].dinv.y : S.iB[s2];
+    if (AF) {   // row t-2: A first (new value yF2), B second
+        const double off = sum8((double)S.c2.aw.y, (double)S.c1.aw.y, (double)S.c2.as.y, (double)S.c2.as2, (double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2,
+                                S.yF3, y, S.yF2, S.e2, S.iA3, S.iA1, S.ir3, S.ir1);
+        xA = S.yF2; xB = act2 ? (S.f2.y + off) * (double)S.c2.dinv.y : S.iB2;
     } else {    // row t-2: B first, A second
-        const double off = sum8((double)S.c[s2].aw.x, (double)S.c[s1].aw.x, (double)S.c[s2].as.x, (double)S.c[s2].as.y, (double)S.c[s2].av.x, (double)S.c[s1].av.x, (double)S.c[s2].av.y, (double)S.c[s1].av.y,
-                                S.yF[s3], y, S.e[s2], S.yF[s2], S.il[s3], S.il[s1], S.iB[s3], S.iB[s1]);
-        xB = S.yF[s2]; xA = act2 ? (S.f[s2].x + off) * (double)S.c[s2].dinv.x : S.iA[s2];
+        const double off = sum8((double)S.c2.aw.x, (double)S.c1.aw.x, (double)S.c2.as.x, (double)S.c2.as.y, (double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y,
+                                S.yF3, y, S.e2, S.yF2, S.il3, S.il1, S.iB3, S.iB1);
+        xB = S.yF2; xA = act2 ? (S.f2.x + off) * (double)S.c2.dinv.x : S.iA2;
     }
     if (G.own && t - 2 >= G.ia && t - 2 < G.ib) {
         st2(x + G.kb + (long long)(t - 2) * G.ld, xA, xB);
-        dotv = fma(S.f[s2].x, xA, dotv); dotv = fma(S.f[s2].y, xB, dotv);
+        dotv = fma(S.f2.x, xA, dotv); dotv = fma(S.f2.y, xB, dotv);
     }
-    // nothing moves: the new values go into the slots of rows t and t-1
-    S.il[s0] = il0; S.iA[s0] = a; S.iB[s0] = b; S.ir[s0] = ir0; S.f[s0] = R.f; S.c[s0] = R.c;
-    S.yF[s1] = y; S.e[s1] = e1;
+    // shift the pipeline
+    S.il3 = S.il2; S.iA3 = S.iA2; S.iB3 = S.iB2; S.ir3 = S.ir2;
+    S.il2 = S.il1; S.iA2 = S.iA1; S.iB2 = S.iB1; S.ir2 = S.ir1;
+    S.il1 = il0; S.iA1 = a; S.iB1 = b; S.ir1 = ir0;
+    S.yF3 = S.yF2; S.yF2 = y; S.e2 = e1;
+    S.f2 = S.f1; S.f1 = R.f; S.c2 = S.c1; S.c1 = R.c;
 }
 
 // C0: colour of the first stage (0 forward, 1 backward); part: per-CTA partial sums of <f, x> (or nullptr)
@@ -299,7 +286,7 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_post(LevelDev L, co
     const int lane = threadIdx.x & 31;
     const int gw = (int)blockIdx.x * (MG_BLOCK / 32) + (int)(threadIdx.x >> 5);
     PostGeom G;
-    G.ia = (int)blockIdx.y * nrows;            // nrows is a multiple of 4: the slot of a row is a constant of the unrolled step
+    G.ia = chunk_of(L) * nrows;
     G.ib = (G.ia + nrows < g.N1) ? G.ia + nrows : g.N1;
     G.jA = MGS_OWN * gw - 2 + 2 * lane;
     G.colok = G.jA >= 0 && G.jA < g.N2;
@@ -307,27 +294,20 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_post(LevelDev L, co
     G.t_rlo = g.rlo; G.t_rhi = g.rhi;
     G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
     PostState<F32> S;
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        S.il[a] = S.iA[a] = S.iB[a] = S.ir[a] = 0.; S.yF[a] = S.e[a] = 0.; S.f[a].x = S.f[a].y = 0.; S.c[a] = coef_zero<F32>();
-    }
+    S.il1 = S.iA1 = S.iB1 = S.ir1 = S.il2 = S.iA2 = S.iB2 = S.ir2 = S.il3 = S.iA3 = S.iB3 = S.ir3 = 0.;
+    S.yF2 = S.yF3 = S.e2 = 0.; S.f1.x = S.f1.y = S.f2.x = S.f2.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
     double dotv = 0.;
-    const int t0 = G.ia - 2, t1 = G.ib + 1;    // rows marched: [t0, t1]; t0 = 2 (mod 4)
+    const int t0 = G.ia - 2, t1 = G.ib + 1;    // rows marched: [t0, t1], an even count; t0 is even
     PostRow<F32, PROLONG> q0 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, t0), q1 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, t0 + 1);
-    for (int t = t0; t <= t1; t += 4) {
+    for (int t = t0; t <= t1; t += 2) {
         { const PostRow<F32, PROLONG> R = q0; q0 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 2 <= t1) ? t + 2 : t1);
-          post_step<F32, PROLONG, C0 == 0, 2>(t, R, S, G, x, dotv); }
+          post_step<F32, PROLONG, C0 == 0>(t, R, S, G, x, dotv); }
         { const PostRow<F32, PROLONG> R = q1; q1 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 3 <= t1) ? t + 3 : t1);
-          post_step<F32, PROLONG, C0 != 0, 3>(t + 1, R, S, G, x, dotv); }
-        if (t + 2 > t1) break;                 // (the row count is even, not always a multiple of 4)
-        { const PostRow<F32, PROLONG> R = q0; q0 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 4 <= t1) ? t + 4 : t1);
-          post_step<F32, PROLONG, C0 == 0, 0>(t + 2, R, S, G, x, dotv); }
-        { const PostRow<F32, PROLONG> R = q1; q1 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 5 <= t1) ? t + 5 : t1);
-          post_step<F32, PROLONG, C0 != 0, 1>(t + 3, R, S, G, x, dotv); }
+          post_step<F32, PROLONG, C0 != 0>(t + 1, R, S, G, x, dotv); }
     }
     if (part) {
         dotv = block_reduce<RED_SUM>(dotv);
-        if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
+        if (threadIdx.x == 0) part[chunk_of(L) * gridDim.x + blockIdx.x] = dotv;
     }
 }
 
@@ -340,14 +320,8 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_post(LevelDev L, co
 // The arithmetic per cell is that of the three launches (the forward half is pre_step's, the backward half post_step's), so the
 // result is bit-identical; two halo lanes per side as in PRE.
 template <bool F32> struct SgsFwd { double xF1, e01, xA2, xB2; d2 f1; CoefRow<F32> c1; };
-// backward half: the shifting pipeline of the first-generation POST step (this kernel is 34 B/cell and DRAM-bound as it stands)
-template <bool F32> struct SgsBack {
-    double il1, iA1, iB1, ir1, il2, iA2, iB2, ir2, il3, iA3, iB3, ir3;   // forward result on rows tb-1, tb-2, tb-3
-    double yF2, yF3, e2;
-    d2 f1, f2; CoefRow<F32> c1, c2;
-};
 template <bool F32, bool AF>
-IMPEC_D void sgs_step(const int t, const PreRow<F32> &R, SgsFwd<F32> &F, SgsBack<F32> &S, const PostGeom &G, double *__restrict__ x, double &dotv) {
+IMPEC_D void sgs_step(const int t, const PreRow<F32> &R, SgsFwd<F32> &F, PostState<F32> &S, const PostGeom &G, double *__restrict__ x, double &dotv) {
     // ---- forward sweep from zero (pre_step, parts 1 and 2): colour 0 on row t, colour 1 on row t-1
     const bool act0 = G.colok && t >= G.t_rlo && t < G.t_rhi;
     const double xF = act0 ? (AF ? R.f.x * (double)R.c.dinv.x : R.f.y * (double)R.c.dinv.y) : 0.;
@@ -412,7 +386,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 3) k_sgs_march(LevelDev L, const dou
     const int lane = threadIdx.x & 31;
     const int gw = (int)blockIdx.x * (MG_BLOCK / 32) + (int)(threadIdx.x >> 5);
     PostGeom G;
-    G.ia = (int)blockIdx.y * nrows;
+    G.ia = chunk_of(L) * nrows;
     G.ib = (G.ia + nrows < g.N1) ? G.ia + nrows : g.N1;
     G.jA = MGP_OWN * gw - 4 + 2 * lane;
     G.colok = G.jA >= 0 && G.jA < g.N2;
@@ -421,7 +395,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 3) k_sgs_march(LevelDev L, const dou
     G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
     SgsFwd<F32> F;
     F.xF1 = F.e01 = F.xA2 = F.xB2 = 0.; F.f1.x = F.f1.y = 0.; F.c1 = coef_zero<F32>();
-    SgsBack<F32> S;
+    PostState<F32> S;
     S.il1 = S.iA1 = S.iB1 = S.ir1 = S.il2 = S.iA2 = S.iB2 = S.ir2 = S.il3 = S.iA3 = S.iB3 = S.ir3 = 0.;
     S.yF2 = S.yF3 = S.e2 = 0.; S.f1.x = S.f1.y = S.f2.x = S.f2.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
     double dotv = 0.;
@@ -435,6 +409,6 @@ __global__ void __launch_bounds__(MG_BLOCK, 3) k_sgs_march(LevelDev L, const dou
     }
     if (part) {
         dotv = block_reduce<RED_SUM>(dotv);
-        if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = dotv;
+        if (threadIdx.x == 0) part[chunk_of(L) * gridDim.x + blockIdx.x] = dotv;
     }
 }

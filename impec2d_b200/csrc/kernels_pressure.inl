@@ -144,7 +144,12 @@ struct LevelDev {
     long long pin;               // fine level: padded index of the Dirichlet cell (or -1)
     long long sig_idx;           // coarse levels: padded index of the cell carrying the pin's diagonal shift
     const double *sig;           // device pointer to that shift (k_pin_sigma): kernel arguments stay constant across steps
+    // Row-chunk map of the marching kernels: CTA row blockIdx.y works on chunk cy0 + blockIdx.y * cys.  (0, 1) = all chunks in order; a
+    // slab level launches the first and the last chunk -- the only ones that read halo rows -- as (0, ny - 1) x 2 behind the halo
+    // exchange on a second stream, and the interior chunks (1, 1) x (ny - 2) concurrently with that exchange.
+    int cy0, cys;
 };
+IMPEC_D int chunk_of(const LevelDev &L) { return L.cy0 + (int)blockIdx.y * L.cys; }
 
 IMPEC_D double link_diag(const LevelDev &L, size_t k) {
     const int ld = L.g.ld;

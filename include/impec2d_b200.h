@@ -186,6 +186,7 @@ int   impec_build_operator(impec_ctx *ctx);                              /* a2-a
 int   impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host); /* one MG cycle; NULL/NULL = on the internal residual */
 int   impec_mg_levels(const impec_ctx *ctx);
 long long impec_kernel_launches(const impec_ctx *ctx);                   /* kernels launched by this context so far */
+long long impec_overlapped_exchanges(const impec_ctx *ctx);              /* halo exchanges issued concurrently with the interior row chunks of their consumer (multi-GPU) */
 int   impec_reset_state(impec_ctx *ctx);                                 /* produced mass := 0, sweep parity := Y */
 /* options: "warm_start" (x0 = previous p instead of the reference's 0), "stagnation_guard" (stop PCG at the FP64
  * residual floor instead of iterating the recurrence residual down to eps), "mg_fused", "mg_links_fp32", "mg_staged",

@@ -73,6 +73,8 @@ def main():
         c2 = np.zeros_like(c); ctx.download_c(c2)
         os.remove(path)
         assert dt1 == dt2 and np.array_equal(c1[rows], c2[rows]), "restart from the per-rank checkpoint is not bit-exact"
+    if os.environ.get("IMPEC_REQUIRE_OVERLAP"):
+        assert ctx.overlapped_exchanges() > 0, "no halo exchange was overlapped with interior chunks"
     print("rank %d ok: dc %.2e dp %.2e its %d/%d levels %d" % (rank, dc, dp, info.iterations, info_ref.iterations, ctx.mg_levels()), flush=True)
     ctx.close(); ref.close()
     dist.destroy_process_group()

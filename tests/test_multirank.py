@@ -36,3 +36,10 @@ def test_two_ranks_default_replication_threshold():
     """WITHOUT IMPEC_DIST_MIN_CELLS (ADVICE r1, high): on a small grid every coarse level falls under the default 4M-cell threshold;
     level 0 must still be distributed (its vectors alias the slab-sized PCG vectors) and everything below replicated."""
     run(2, 64, 64, 0, 0, 1, 29616, {"IMPEC_DIST_MIN_CELLS": None})
+
+
+def test_two_ranks_overlapped_halo_exchange():
+    """Halo exchange overlapped with interior compute: with 8-row chunks a 64-row slab has interior chunks, so the marching
+    PRE / POST / PLAIN / mat-vec kernels run as exchange + edge chunks + interior chunks; the result must equal the 1-rank run.  The same
+    split with the exchange switched back to the serial order (IMPEC_HALO_OVERLAP=0) is covered by test_two_ranks_marching_kernels."""
+    run(2, 128, 128, 0, 0, 1, 29617, {"IMPEC_MARCH_MIN_CELLS": "0", "IMPEC_MARCH_ROWS": "8", "IMPEC_REQUIRE_OVERLAP": "1"})
