@@ -106,6 +106,9 @@ struct impec_ctx {
 #endif
     // Halo exchange overlapped with interior compute: the exchange and the two slab-edge row chunks of its consumer run on a
     // second, high-priority stream while the interior chunks of the same kernel run on the main stream (halo_overlapped()).
+    // marching kernels: rows of L2 software prefetch ahead of the march, per kernel family (PRE, POST / PLAIN, mat-vec, CN sweep);
+    // option "l2_prefetch" sets all four, IMPEC_L2_PREFETCH="pre,post,mv,sgs" (or one number) each.  0 = off.
+    int pf_pre = 4, pf_post = 4, pf_mv = 4, pf_sgs = 4;
     bool overlap = true;                            // option "halo_overlap" / IMPEC_HALO_OVERLAP=0/1
     long long overlapped = 0;                       // exchanges issued that way (diagnostic)
 #ifndef IMPEC_EMU
@@ -457,7 +460,7 @@ static int halo_overlapped(impec_ctx *ctx, bool dist, int ny, int rows_per_chunk
     TRY(launch(0, ny - 1, 2));
     return launch(1, 1, ny - 2);
 }
-static LevelDev chunked(LevelDev D, int y0, int ys) { D.cy0 = y0; D.cys = ys; return D; }
+static LevelDev chunked(LevelDev D, int y0, int ys, int pfd) { D.cy0 = y0; D.cys = ys; D.pfd = pfd; return D; }
 
 extern "C" int impec_ctx_set_comm_callbacks(impec_ctx *ctx, const impec_comm_callbacks *cb) {
     if (!cb || !cb->sendrecv || !cb->allreduce || !cb->allgather || !cb->bcast) return fail(ctx, IMPEC_ERR_ARG, "incomplete callback table");
@@ -572,6 +575,9 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     { const char *e = getenv("IMPEC_HALO_OVERLAP"); if (e) ctx->overlap = atoi(e) != 0; }
+    { const char *e = getenv("IMPEC_L2_PREFETCH");
+      if (e) { int v[4]; const int n = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]); for (int a = n; a < 4 && n > 0; a++) v[a] = v[n - 1];
+               if (n > 0) { ctx->pf_pre = v[0]; ctx->pf_post = v[1]; ctx->pf_mv = v[2]; ctx->pf_sgs = v[3]; } } }
 #ifndef IMPEC_EMU
     if (nranks > 1) {
         int prio_lo = 0, prio_hi = 0;
@@ -715,6 +721,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "fast_r0") { ctx->fast_r0 = value != 0.0; return IMPEC_OK; }
     if (k == "sgs_march") { ctx->sgs_march = value != 0.0; return IMPEC_OK; }
     if (k == "halo_overlap") { ctx->overlap = value != 0.0; return IMPEC_OK; }
+    if (k == "l2_prefetch") { ctx->pf_pre = ctx->pf_post = ctx->pf_mv = ctx->pf_sgs = (int)value; return IMPEC_OK; }
     if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
@@ -901,7 +908,7 @@ static LevelDev level_dev(const impec_ctx *ctx, int l, double mass) {
     D.g = L.g; D.AW = L.AW; D.AS = L.AS; D.AV = L.AV; D.DINV = L.DINV; D.mass = mass;
     D.AWf = L.AWf; D.ASf = L.ASf; D.AVf = L.AVf; D.DINVf = L.DINVf;
     D.pin = L.pin; D.sig_idx = L.sig_idx; D.sig = ctx->sigma_dev + l;
-    D.cy0 = 0; D.cys = 1;
+    D.cy0 = 0; D.cys = 1; D.pfd = 0;
     return D;
 }
 
@@ -1048,7 +1055,7 @@ static int fused_plain(Cycle &C, int l, const double *f, bool forward, int xhalo
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGS_OWN);
         auto launch = [&](int y0, int ys, int ny) -> int {
-            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys);
+            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys, ctx->pf_post);
 #define MPLAIN(F32, C0) LAUNCH_COOP(ctx, (k_mg_march_post<F32, false, C0, 3>), gg, dim3(MG_BLOCK), D, f, (const double *)L.x, L.t, L.g, (const double *)nullptr, (double *)nullptr, L.march_rows)
             if (ctx->links_f32) { if (forward) MPLAIN(true, 0); else MPLAIN(true, 1); } else { if (forward) MPLAIN(false, 0); else MPLAIN(false, 1); }
 #undef MPLAIN
@@ -1080,7 +1087,7 @@ static int fused_pre(Cycle &C, int l, const double *f) {
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGP_OWN);
         auto launch = [&](int y0, int ys, int ny) -> int {
-            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys);
+            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys, ctx->pf_pre);
 #define MPRE(F32, PF, MB) LAUNCH_COOP(ctx, (k_mg_march_pre<F32, PF, MB>), gg, dim3(MG_BLOCK), D, f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows)
             if (!ctx->links_f32) MPRE(false, 4, 3);
             else if (ctx->march_variant & 1) MPRE(true, 2, 4);      // 2 rows in flight, 4 CTAs per SM
@@ -1116,7 +1123,7 @@ static int fused_post(Cycle &C, int l, const double *f, double *part, long long 
         ctx->march_launches++;
         const dim3 gm = march_grid(L, MGS_OWN);
         auto launch = [&](int y0, int ys, int ny) -> int {
-            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys);
+            const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys, ctx->pf_post);
 #define MPOST(F32, MB) LAUNCH_COOP(ctx, (k_mg_march_post<F32, true, 1, MB>), gg, dim3(MG_BLOCK), D, f, (const double *)L.x, L.t, at_transition(ctx, l) ? Lc.gl : Lc.g, coarse_x_view(ctx, l), part, L.march_rows)
             // 168 registers, 3 CTAs per SM.  (Forcing 4 CTAs per SM makes ptxas spill ~300 B per thread and DOUBLES the time.)
             if (!ctx->links_f32) MPOST(false, 3); else MPOST(true, 3);
@@ -1306,7 +1313,7 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
             ctx->march_launches++;
             const dim3 gm = march_grid(L, MGP_OWN);
             auto launch = [&](int y0, int ys, int ny) -> int {
-                const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys);
+                const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys, ctx->pf_sgs);
                 if (ctx->links_f32) LAUNCH_COOP(ctx, k_sgs_march<true>, gg, dim3(MG_BLOCK), D, f, L.x, dot_part, L.march_rows);
                 else LAUNCH_COOP(ctx, k_sgs_march<false>, gg, dim3(MG_BLOCK), D, f, L.x, dot_part, L.march_rows);
                 return IMPEC_OK;
@@ -1464,7 +1471,7 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
             if (ctx->matvec_march) {
                 // [z and d: 1 halo row each, one exchange] overlapped with the interior row chunks
                 auto launch = [&](int y0, int ys, int ny) -> int {
-                    const dim3 gg(gmm.x, (unsigned)ny); const LevelDev D = chunked(A, y0, ys);
+                    const dim3 gg(gmm.x, (unsigned)ny); const LevelDev D = chunked(A, y0, ys, ctx->pf_mv);
                     if (first_dir) LAUNCH_COOP(ctx, k_pcg_matvec_march<true>, gg, dim3(MV_BLOCK), D, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part, mvrows);
                     else LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, gg, dim3(MV_BLOCK), D, (const double *)(ctx->scal + S_BETA_NUM), (const double *)ctx->L[0].x, (const double *)dcur, dalt, ctx->s, ctx->part, mvrows);
                     return IMPEC_OK;
@@ -1965,7 +1972,7 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "residual") { LAUNCH(ctx, k_residual, gr, kBlock, C.D[0], ctx->r, (const double *)L0.x, L0.r); return IMPEC_OK; }
         if (k == "restrict") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L0.g, L0.r, Lc.g, Lc.f); return IMPEC_OK; }
         if (k == "prolong_add") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_prolong_add, gr, kBlock, Lc.g, Lc.x, L0.g, L0.x, L0.pin); return IMPEC_OK; }
-        if (k == "pcg_matvec" && ctx->matvec_march) { LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, matvec_march_grid(g), dim3(MV_BLOCK), C.D[0], (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part, matvec_march_rows(g)); return IMPEC_OK; }
+        if (k == "pcg_matvec" && ctx->matvec_march) { LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, matvec_march_grid(g), dim3(MV_BLOCK), chunked(C.D[0], 0, 1, ctx->pf_mv), (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part, matvec_march_rows(g)); return IMPEC_OK; }
         if (k == "pcg_matvec") { LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, fused_grid<FUSED_PLAIN>(g), kFusedBlock, kFusedSmem, C.D[0], (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part); return IMPEC_OK; }
         if (k == "matvec_dot") { LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, C.D[0], ctx->d, ctx->s, ctx->part); return IMPEC_OK; }
         if (k == "update_xr") { LAUNCH_COOP(ctx, k_update_xr, update_xr_grid(g), dim3(UX_BLOCK), g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part); return IMPEC_OK; }

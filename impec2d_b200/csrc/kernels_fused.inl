@@ -437,6 +437,10 @@ __global__ void __launch_bounds__(MV_BLOCK, 3) k_pcg_matvec_march(LevelDev L, co
             if (row > ib) continue;
             const MvRow R = q[u];
             { const int nx = (row + MV_PF < ib) ? row + MV_PF : ib; q[u] = mv_load_row<FIRST>(L, z, din, kb + (size_t)(nx - ia + 1) * ld, ok, eoff); }
+            if (L.pfd > 0 && row + L.pfd <= ib) {                        // L2 software prefetch of the row `pfd` steps ahead (see LevelDev::pfd)
+                const size_t kp = kb + (size_t)(row + L.pfd - ia + 1) * ld;
+                pf_l2(z + kp); if (!FIRST) pf_l2(din + kp); pf_l2(L.AW + kp); pf_l2(L.AV + kp); pf_l2(L.AS + kp);
+            }
             // new direction on this row
             const double a2 = FIRST ? R.z.x : R.z.x + beta * R.d.x;
             const double b2 = FIRST ? R.z.y : R.z.y + beta * R.d.y;

@@ -51,6 +51,7 @@ template <bool F32> IMPEC_D CoefRow<F32> coef_load(const Coef<F32> &A, size_t k)
     c.as2 = A.AS[k + 2]; c.av2 = A.AV[k + 2];
     return c;
 }
+template <bool F32> IMPEC_D void coef_prefetch(const Coef<F32> &A, size_t k) { pf_l2(A.DINV + k); pf_l2(A.AW + k); pf_l2(A.AS + k); pf_l2(A.AV + k); }
 // sum over the 8 neighbours in the order of tile_offsum: up, down, left, right, up-left, down-left, up-right, down-right
 IMPEC_D double sum8(double w_up, double w_dn, double w_l, double w_r, double w_ul, double w_dl, double w_ur, double w_dr,
                     double up, double dn, double l, double r, double ul, double dl, double ur, double dr) {
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_pre(LevelDev L, con
             if (t + u > t1) continue;
             const PreRow<F32> R = q[u];
             q[u] = pre_load<F32>(A, f, G.kb + (long long)((t + u + PF <= t1) ? t + u + PF : t1) * G.ld, G.colok);
+            if (L.pfd > 0 && t + u + L.pfd <= t1) { const long long kp = G.kb + (long long)(t + u + L.pfd) * G.ld; pf_l2(f + kp); coef_prefetch<F32>(A, (size_t)kp); }
             if (u & 1) pre_step<F32, true>(t + u, R, S, G, x, fc);
             else pre_step<F32, false>(t + u, R, S, G, x, fc);
         }
@@ -300,6 +302,12 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_post(LevelDev L, co
     const int t0 = G.ia - 2, t1 = G.ib + 1;    // rows marched: [t0, t1], an even count; t0 is even
     PostRow<F32, PROLONG> q0 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, t0), q1 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, t0 + 1);
     for (int t = t0; t <= t1; t += 2) {
+        if (L.pfd > 0 && t + 1 + L.pfd <= t1) {          // rows t + pfd and t + pfd + 1 (and the coarse row under them) into L2
+            const long long kp = G.kb + (long long)(t + L.pfd) * G.ld;
+            pf_l2(xin + kp); pf_l2(f + kp); coef_prefetch<F32>(A, (size_t)kp);
+            pf_l2(xin + kp + G.ld); pf_l2(f + kp + G.ld); coef_prefetch<F32>(A, (size_t)(kp + G.ld));
+            if (PROLONG) { const int I = (t + L.pfd) >> 1; if (I >= 0 && I < gc.N1 + 1) pf_l2(ec + (long long)(IMPEC_GH + I) * gc.ld + (G.colok ? (G.jA >> 1) : 0) + IMPEC_PJ); }
+        }
         { const PostRow<F32, PROLONG> R = q0; q0 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 2 <= t1) ? t + 2 : t1);
           post_step<F32, PROLONG, C0 == 0>(t, R, S, G, x, dotv); }
         { const PostRow<F32, PROLONG> R = q1; q1 = post_load<F32, PROLONG>(A, f, xin, g, gc, ec, G, (t + 3 <= t1) ? t + 3 : t1);
@@ -402,6 +410,10 @@ __global__ void __launch_bounds__(MG_BLOCK, 3) k_sgs_march(LevelDev L, const dou
     const int t0 = G.ia - 3, t1 = G.ib + 2;    // rows marched: [t0, t1], an even count; t0 is odd
     PreRow<F32> q0 = pre_load<F32>(A, f, G.kb + (long long)t0 * G.ld, G.colok), q1 = pre_load<F32>(A, f, G.kb + (long long)(t0 + 1) * G.ld, G.colok);
     for (int t = t0; t <= t1; t += 2) {
+        if (L.pfd > 0 && t + 1 + L.pfd <= t1) {
+            const long long kp = G.kb + (long long)(t + L.pfd) * G.ld;
+            pf_l2(f + kp); coef_prefetch<F32>(A, (size_t)kp); pf_l2(f + kp + G.ld); coef_prefetch<F32>(A, (size_t)(kp + G.ld));
+        }
         { const PreRow<F32> R = q0; q0 = pre_load<F32>(A, f, G.kb + (long long)((t + 2 <= t1) ? t + 2 : t1) * G.ld, G.colok);
           sgs_step<F32, false>(t, R, F, S, G, x, dotv); }
         { const PreRow<F32> R = q1; q1 = pre_load<F32>(A, f, G.kb + (long long)((t + 3 <= t1) ? t + 3 : t1) * G.ld, G.colok);

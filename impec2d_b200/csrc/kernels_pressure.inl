@@ -148,7 +148,17 @@ struct LevelDev {
     // slab level launches the first and the last chunk -- the only ones that read halo rows -- as (0, ny - 1) x 2 behind the halo
     // exchange on a second stream, and the interior chunks (1, 1) x (ny - 2) concurrently with that exchange.
     int cy0, cys;
+    // Marching kernels: software prefetch into L2 of the rows `pfd` steps ahead of the march (0 = off).  The register prefetch queue is
+    // only 2 rows deep (register pressure); an L2 prefetch costs no register and turns the DRAM latency of those loads into L2 latency.
+    int pfd;
 };
+IMPEC_D void pf_l2(const void *p) {
+#ifndef IMPEC_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 IMPEC_D int chunk_of(const LevelDev &L) { return L.cy0 + (int)blockIdx.y * L.cys; }
 
 IMPEC_D double link_diag(const LevelDev &L, size_t k) {
