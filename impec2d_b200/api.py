@@ -113,6 +113,13 @@ class Context:
 
     def transport_step(self, dt): self._chk(self.L.impec_transport_step(self._h, dt))
 
+    def intercell_flux(self, direction, dt):
+        """CalculateIntercellFlux_F (direction 0, shape (N1+1, N2+2g)) / _G (direction 1, shape (N1+2g, N2+1)) of the current c and velocity."""
+        P = self.P; g = P.g
+        out = np.zeros((P.N1 + 1, P.N2 + 2 * g) if direction == 0 else (P.N1 + 2 * g, P.N2 + 1))
+        self._chk(self.L.impec_intercell_flux(self._h, direction, dt, _ptr(out)))
+        return out
+
     def impes_step(self, t=0.0, t_next_output=0.0):
         dt = C.c_double(); info = _lib.SolveInfo()
         self._chk(self.L.impec_impes_step(self._h, t, t_next_output, C.byref(dt), C.byref(info)))

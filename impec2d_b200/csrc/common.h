@@ -61,6 +61,14 @@ IMPEC_D void st2(double *p, double a, double b) {
     p[0] = a; p[1] = b;
 #endif
 }
+// software prefetch of a line into L2 (no register is held; used by the marching kernels a few rows ahead of their loads)
+IMPEC_D void pf_l2(const void *p) {
+#ifndef IMPEC_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 // ---- reductions -------------------------------------------------------------------------------
 // Stage 1: every block reduces its values with warp shuffles + one shared-memory hop and writes ONE

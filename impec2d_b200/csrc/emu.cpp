@@ -1,26 +1,64 @@
 // emu.cpp -- CPU emulator behind shim.h (IMPEC_EMU builds only; test infrastructure).
 // Blocks run one after another.  Non-cooperative kernels run their threads as plain nested loops;
 // cooperative kernels (those that call __syncthreads or warp shuffles) run every thread of a block
-// as a ucontext coroutine and switch at each barrier.
+// as a coroutine and switch at each barrier.  The switch is a dozen instructions of x86-64 assembly
+// (callee-saved registers + stack pointer; glibc's swapcontext makes a sigprocmask system call per
+// switch, which dominated the run time of the CPU test suite) and the coroutine stacks are reused.
 #ifdef IMPEC_EMU
 #include "shim.h"
-#include <ucontext.h>
 #include <vector>
 #include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+
+#if !defined(__x86_64__)
+#error "the CPU emulator's context switch is written for x86-64"
+#endif
+extern "C" void impec_emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+    .text
+    .globl impec_emu_switch
+    .hidden impec_emu_switch
+    .type impec_emu_switch,@function
+impec_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    subq $8, %rsp
+    stmxcsr (%rsp)
+    fnstcw 4(%rsp)
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    ldmxcsr (%rsp)
+    fldcw 4(%rsp)
+    addq $8, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size impec_emu_switch, .-impec_emu_switch
+)");
 
 namespace emu {
 dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
 unsigned char *dyn_smem = nullptr;
 
 namespace {
+const size_t kStack = 64 * 1024;
 struct Fiber {
-    ucontext_t ctx;
-    std::vector<unsigned char> stack;
+    void *sp = nullptr;
     bool done = false;
     dim3 tid;
 };
 std::vector<Fiber> fibers;
-ucontext_t sched_ctx;
+std::vector<unsigned char *> stacks;             // one per thread of the largest block seen so far; never freed
+void *sched_sp = nullptr;
 int current = -1;
 const std::function<void()> *cur_body = nullptr;
 std::vector<double> exch;
@@ -29,13 +67,28 @@ bool in_coop = false;
 void trampoline() {
     (*cur_body)();
     fibers[current].done = true;
-    swapcontext(&fibers[current].ctx, &sched_ctx);
+    impec_emu_switch(&fibers[current].sp, sched_sp);
+    std::abort();                                 // a finished coroutine is never resumed
+}
+void prepare(Fiber &f, unsigned char *stack) {
+    // initial frame as impec_emu_switch leaves it: [mxcsr | fpu cw][r15][r14][r13][r12][rbx][rbp][return address]
+    uintptr_t top = ((uintptr_t)stack + kStack) & ~(uintptr_t)15;
+    uint64_t *sp = (uint64_t *)(top - 16);        // slot of the return address: 16-byte aligned, so rsp % 16 == 8 on entry
+    sp[0] = (uint64_t)(uintptr_t)&trampoline;
+    sp[1] = 0;
+    sp -= 7;
+    for (int a = 1; a < 7; a++) sp[a] = 0;
+    unsigned mx = 0; unsigned short cw = 0;
+    asm volatile("stmxcsr %0" : "=m"(mx));
+    asm volatile("fnstcw %0" : "=m"(cw));
+    sp[0] = (uint64_t)mx | ((uint64_t)cw << 32);
+    f.sp = sp;
 }
 }  // namespace
 
 void syncthreads() {
     if (!in_coop) { std::fprintf(stderr, "emu: __syncthreads in a kernel launched with IMPEC_LAUNCH (use IMPEC_LAUNCH_COOP)\n"); std::abort(); }
-    swapcontext(&fibers[current].ctx, &sched_ctx);
+    impec_emu_switch(&fibers[current].sp, sched_sp);
     threadIdx_ = fibers[current].tid;
 }
 
@@ -59,6 +112,11 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
     std::vector<unsigned char> smem_buf(smem + 16);
     dyn_smem = smem_buf.data();
     const int nthreads = (int)(block.x * block.y * block.z);
+    if (coop) {
+        while ((int)stacks.size() < nthreads) { void *p = nullptr; if (posix_memalign(&p, 64, kStack)) std::abort(); stacks.push_back((unsigned char *)p); }
+        fibers.assign(nthreads, Fiber());
+        exch.assign(nthreads, 0.0);
+    }
     for (unsigned bz = 0; bz < grid.z; bz++)
         for (unsigned by = 0; by < grid.y; by++)
             for (unsigned bx = 0; bx < grid.x; bx++) {
@@ -70,20 +128,13 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
                     continue;
                 }
                 in_coop = true; cur_body = &body;
-                fibers.assign(nthreads, Fiber());
-                exch.assign(nthreads, 0.0);
                 int t = 0;
                 for (unsigned tz = 0; tz < block.z; tz++)
                     for (unsigned ty = 0; ty < block.y; ty++)
                         for (unsigned tx = 0; tx < block.x; tx++, t++) {
                             Fiber &f = fibers[t];
-                            f.tid = dim3(tx, ty, tz);
-                            f.stack.resize(64 * 1024);
-                            getcontext(&f.ctx);
-                            f.ctx.uc_stack.ss_sp = f.stack.data();
-                            f.ctx.uc_stack.ss_size = f.stack.size();
-                            f.ctx.uc_link = &sched_ctx;
-                            makecontext(&f.ctx, trampoline, 0);
+                            f.tid = dim3(tx, ty, tz); f.done = false;
+                            prepare(f, stacks[t]);
                         }
                 bool any = true;
                 while (any) {
@@ -91,7 +142,7 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
                     for (int k = 0; k < nthreads; k++) {
                         if (fibers[k].done) continue;
                         current = k; threadIdx_ = fibers[k].tid;
-                        swapcontext(&sched_ctx, &fibers[k].ctx);
+                        impec_emu_switch(&sched_sp, fibers[k].sp);
                         if (!fibers[k].done) any = true;
                     }
                 }

@@ -109,6 +109,8 @@ struct impec_ctx {
     // marching kernels: rows of L2 software prefetch ahead of the march, per kernel family (PRE, POST / PLAIN, mat-vec, CN sweep);
     // option "l2_prefetch" sets all four, IMPEC_L2_PREFETCH="pre,post,mv,sgs" (or one number) each.  0 = off.
     int pf_pre = 4, pf_post = 4, pf_mv = 4, pf_sgs = 4;
+    int pf_sweep = 8;                               // MUSCL sweeps (option "sweep_prefetch" / IMPEC_SWEEP_PREFETCH)
+    bool sweep_y_pairs = true;                      // MUSCL y sweep: column pairs per lane + shuffles (k_muscl_y2); 0 = the shared-memory tile kernel k_muscl_y
     bool overlap = true;                            // option "halo_overlap" / IMPEC_HALO_OVERLAP=0/1
     long long overlapped = 0;                       // exchanges issued that way (diagnostic)
 #ifndef IMPEC_EMU
@@ -575,6 +577,8 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     { const char *e = getenv("IMPEC_HALO_OVERLAP"); if (e) ctx->overlap = atoi(e) != 0; }
+    { const char *e = getenv("IMPEC_SWEEP_PREFETCH"); if (e) ctx->pf_sweep = atoi(e); }
+    { const char *e = getenv("IMPEC_SWEEP_Y_PAIRS"); if (e) ctx->sweep_y_pairs = atoi(e) != 0; }
     { const char *e = getenv("IMPEC_L2_PREFETCH");
       if (e) { int v[4]; const int n = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]); for (int a = n; a < 4 && n > 0; a++) v[a] = v[n - 1];
                if (n > 0) { ctx->pf_pre = v[0]; ctx->pf_post = v[1]; ctx->pf_mv = v[2]; ctx->pf_sgs = v[3]; } } }
@@ -721,6 +725,8 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "fast_r0") { ctx->fast_r0 = value != 0.0; return IMPEC_OK; }
     if (k == "sgs_march") { ctx->sgs_march = value != 0.0; return IMPEC_OK; }
     if (k == "halo_overlap") { ctx->overlap = value != 0.0; return IMPEC_OK; }
+    if (k == "sweep_y_pairs") { ctx->sweep_y_pairs = value != 0.0; return IMPEC_OK; }
+    if (k == "sweep_prefetch") { ctx->pf_sweep = (int)value; return IMPEC_OK; }
     if (k == "l2_prefetch") { ctx->pf_pre = ctx->pf_post = ctx->pf_mv = ctx->pf_sgs = (int)value; return IMPEC_OK; }
     if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
     if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
@@ -1663,9 +1669,16 @@ static int sweep(impec_ctx *ctx, const double *cin, double *cout, const double *
         if (DIR == 0) {
             const int jstart = j0 - ((j0 + IMPEC_PJ) & 3);            // 32-byte aligned first column
             const dim3 gx((unsigned)((j1 - jstart + SX_BLOCK - 1) / SX_BLOCK), (unsigned)((i1 - i0 + SX_ROWS - 1) / SX_ROWS));
-#define SWX(PH, AV) do { auto kern = k_muscl_x<PH, AV>; LAUNCH(ctx, kern, gx, dim3(SX_BLOCK), g, cin, vel, cout, other, dt, h, phi, i0, i1, j0, j1, jstart); } while (0)
+#define SWX(PH, AV) do { auto kern = k_muscl_x<PH, AV>; LAUNCH(ctx, kern, gx, dim3(SX_BLOCK), g, cin, vel, cout, other, dt, h, phi, i0, i1, j0, j1, jstart, ctx->pf_sweep); } while (0)
             if (phi1) { if (avg) { SWX(true, true); } else { SWX(true, false); } } else { if (avg) { SWX(false, true); } else { SWX(false, false); } }
 #undef SWX
+        } else if (ctx->sweep_y_pairs && ((j0 + IMPEC_PJ) & 1) == 0) {
+            // column pairs per lane, neighbours by shuffle, no shared memory (k_muscl_y2)
+            const int warps = (j1 - j0 + SY2_OWN - 1) / SY2_OWN;
+            const dim3 gy((unsigned)((warps + SY2_BLOCK / 32 - 1) / (SY2_BLOCK / 32)), (unsigned)((i1 - i0 + SY2_ROWS - 1) / SY2_ROWS));
+#define SWY2(PH, AV) do { auto kern = k_muscl_y2<PH, AV>; LAUNCH_COOP(ctx, kern, gy, dim3(SY2_BLOCK), g, cin, vel, cout, other, dt, h, phi, i0, i1, j0, j1, ctx->pf_sweep); } while (0)
+            if (phi1) { if (avg) { SWY2(true, true); } else { SWY2(true, false); } } else { if (avg) { SWY2(false, true); } else { SWY2(false, false); } }
+#undef SWY2
         } else {
             const dim3 gy((unsigned)((j1 - j0 + SY_BLOCK - 1) / SY_BLOCK), (unsigned)((i1 - i0 + SY_ROWS - 1) / SY_ROWS));
 #define SWY(PH, AV) do { auto kern = k_muscl_y<PH, AV>; LAUNCH_COOP(ctx, kern, gy, dim3(SY_BLOCK), g, cin, vel, cout, other, dt, h, phi, i0, i1, j0, j1); } while (0)
@@ -1701,6 +1714,29 @@ extern "C" int impec_advect_y(impec_ctx *ctx, double dt) {
     ctx->mob_valid = ctx->op_valid = false;
     TRY(copy_field(ctx, ctx->c, ctx->ta));
     return sweep<1>(ctx, ctx->ta, ctx->c, nullptr, dt, -ng, g.N1 + ng, 0, g.N2);
+}
+
+// CalculateIntercellFlux_F / _G (src/HyperbolicSplitSolver.h:19-22): the flux field of the CURRENT c and velocity for a step dt, in the
+// reference's array shapes -- dir 0: F[(N1+1) x (N2+2g)], F(i, j) at out[i * (N2+2g) + (j+g)]; dir 1: G[(N1+2g) x (N2+1)], G(i, j) at
+// out[(i+g) * (N2+1) + j].  c must carry filled ghosts (as for impec_advect_x / _y).  Single GPU.
+extern "C" int impec_intercell_flux(impec_ctx *ctx, int dir, double dt, double *out_host) {
+    if (!out_host || (dir != 0 && dir != 1)) return fail(ctx, IMPEC_ERR_ARG, "impec_intercell_flux: dir must be 0 (F) or 1 (G)");
+    if (ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "impec_intercell_flux runs on one GPU");
+    const Grid &g = ctx->g; const int ng = ctx->P.g;
+    const double phi = ctx->P.porosity; const bool phi1 = (phi == 1.0), up = ctx->P.hyper_method == IMPEC_UPWIND;
+    const int i0 = dir == 0 ? 0 : -ng, i1 = dir == 0 ? g.N1 + 1 : g.N1 + ng, j0 = dir == 0 ? -ng : 0, j1 = dir == 0 ? g.N2 + ng : g.N2 + 1;
+    const dim3 gr = grid2d(j1 - j0, i1 - i0);
+    double *F = ctx->ta;
+    const double *vel = dir == 0 ? ctx->u : ctx->v; const double hstep = dir == 0 ? ctx->D.dx : ctx->D.dy;
+#define FLX(DR, M, PH) do { auto kern = k_intercell_flux<DR, M, PH>; LAUNCH(ctx, kern, gr, kBlock, g, (const double *)ctx->c, vel, F, dt, hstep, phi, i0, i1, j0, j1); } while (0)
+    if (dir == 0) { if (up) { if (phi1) FLX(0, 1, true); else FLX(0, 1, false); } else { if (phi1) FLX(0, 0, true); else FLX(0, 0, false); } }
+    else          { if (up) { if (phi1) FLX(1, 1, true); else FLX(1, 1, false); } else { if (phi1) FLX(1, 0, true); else FLX(1, 0, false); } }
+#undef FLX
+    const size_t w = (size_t)(j1 - j0) * sizeof(double);
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(out_host, w, F + gidx(g, i0, j0), (size_t)g.ld * sizeof(double), w, (size_t)(i1 - i0), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->bytes_d2h += (unsigned long long)w * (unsigned long long)(i1 - i0);
+    return IMPEC_OK;
 }
 
 // src/HyperbolicSplitSolver.cpp:51-106

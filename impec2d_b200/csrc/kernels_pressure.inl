@@ -152,13 +152,7 @@ struct LevelDev {
     // only 2 rows deep (register pressure); an L2 prefetch costs no register and turns the DRAM latency of those loads into L2 latency.
     int pfd;
 };
-IMPEC_D void pf_l2(const void *p) {
-#ifndef IMPEC_EMU
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
+
 IMPEC_D int chunk_of(const LevelDev &L) { return L.cy0 + (int)blockIdx.y * L.cys; }
 
 IMPEC_D double link_diag(const LevelDev &L, size_t k) {

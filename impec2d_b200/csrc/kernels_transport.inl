@@ -160,6 +160,26 @@ __global__ void __launch_bounds__(256) k_sweep(Grid g, const double *__restrict_
     cout[k] = r;
 }
 
+// Intercell fluxes as a field (CalculateIntercellFlux_F / _G of the reference's split solvers, src/MUSCLSplitSolver.cpp:102-189,
+// src/UpwindSplitSolver.cpp:43-61).  The sweeps above never materialise F or G; this kernel exists for callers of the reference's public
+// flux interface.  One thread per face (i, j) = the low face of cell (i, j) along DIR; same device functions as the sweeps.
+template <int DIR, int METHOD, bool PHI1>
+__global__ void __launch_bounds__(256) k_intercell_flux(Grid g, const double *__restrict__ cin, const double *__restrict__ vel, double *__restrict__ F,
+                                                        double dt, double hstep, double phi, int i0, int i1, int j0, int j1) {
+    const int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= i1 || j >= j1) return;
+    const int s = DIR == 0 ? g.ld : 1;
+    const size_t k = gidx(g, i, j);
+    const double v0 = vel[k];
+    if (METHOD == 1) { F[k] = upwind_flux<PHI1>(v0, cin[k - s], cin[k], phi); return; }
+    const double h = 0.5 * dt / hstep;
+    double Llo, Rlo, Lhi, Rhi;
+    muscl_evolve<PHI1>(vel[k - s], v0, cin[k - 2 * s], cin[k - s], cin[k], h, phi, Llo, Rlo);       // cell on the low side of the face
+    muscl_evolve<PHI1>(v0, vel[k + s], cin[k - s], cin[k], cin[k + s], h, phi, Lhi, Rhi);           // cell on the high side
+    F[k] = upwind_flux<PHI1>(v0, Rlo, Lhi, phi);
+}
+
 // ---------------------------------------------------------------- MUSCL sweeps, one reconstruction per cell
 // k_sweep evaluates the reconstruction of cells i-1, i, i+1 in every thread: 9 IEEE divisions per cell, which made the
 // sweep FP64-pipe bound (ncu: 61 % fp64 pipe, 22 % of the HBM roofline).  The two kernels below evaluate every cell's
@@ -176,7 +196,7 @@ __global__ void __launch_bounds__(256) k_sweep(Grid g, const double *__restrict_
 template <bool PHI1, bool AVG>
 __global__ void __launch_bounds__(SX_BLOCK) k_muscl_x(Grid g, const double *__restrict__ cin, const double *__restrict__ vel,
                                                       double *__restrict__ cout, const double *__restrict__ other,
-                                                      double dt, double hstep, double phi, int i0, int i1, int j0, int j1, int jstart) {
+                                                      double dt, double hstep, double phi, int i0, int i1, int j0, int j1, int jstart, int pfd) {
     const int j = jstart + (int)(blockIdx.x * SX_BLOCK + threadIdx.x);
     if (j < j0 || j >= j1) return;
     const int ia = i0 + (int)blockIdx.y * SX_ROWS;
@@ -190,6 +210,13 @@ __global__ void __launch_bounds__(SX_BLOCK) k_muscl_x(Grid g, const double *__re
     muscl_evolve<PHI1>(v0, v1, cm, c0, cp, h, phi, L, Rprev);
     for (int ib0 = ia; ib0 <= ib; ib0 += 4) {
         double cn[4], vn[4], on[4];
+        if (pfd > 0 && ib0 + pfd + 4 <= ib) {                        // the four rows `pfd` ahead into L2
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const size_t kp = kb + (size_t)(ib0 + pfd + u - ia + 2) * ld;
+                pf_l2(cin + kp); pf_l2(vel + kp); if (AVG) pf_l2(other + kp - 2 * ld);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < 4; u++) {                                // rows past ib are clamped: loaded, never used
             const int i = (ib0 + u < ib) ? ib0 + u : ib;
@@ -263,6 +290,68 @@ __global__ void __launch_bounds__(SY_BLOCK) k_muscl_y(Grid g, const double *__re
             if (AVG) r = 0.5 * (other[k] + r);
             cout[k] = r;
         }
+    }
+}
+
+// k_muscl_y2: the y sweep without shared memory or block barriers (the 256 x 4 tile kernel above sits at 39 % of the HBM roofline:
+// 262144 tiny CTAs at 16384^2, a barrier and a serial halo pass each).  A warp owns 64 columns of a row -- one 128-bit column pair
+// (cells A = jA, B = jA + 1) per lane --, every lane evolves its two cells once, the neighbours' values (c(jA-1), c(jA+2), the
+// face velocity v(jA+2), the evolved right state of cell jA-1 and the evolved left state of cell jA+2) come from the adjacent lanes by
+// shuffle.  The two outermost lanes lack a neighbour, so a warp stores 60 of its 64 columns (lanes 1..30).  Rows are independent in
+// a y sweep: a thread walks down SY2_ROWS rows two at a time (two independent dependency chains), with the rows `pfd` ahead
+// prefetched into L2.  Same device functions and operation order per cell as k_sweep / k_muscl_y: bit-identical.
+#define SY2_BLOCK 128
+#define SY2_OWN 60
+#define SY2_ROWS 32
+template <bool PHI1, bool AVG>
+IMPEC_D void muscl_y2_row(const Grid &g, const double *__restrict__ cin, const double *__restrict__ vel, double *__restrict__ cout,
+                          const double *__restrict__ other, size_t k, double dt, double hstep, double h, double phi, bool st2ok, bool st1ok) {
+    const d2 c = ld2(cin + k), v = ld2(vel + k);
+    const double cl = IMPEC_SHFL_UP(c.y, 1), cr = IMPEC_SHFL_DOWN(c.x, 1), vr = IMPEC_SHFL_DOWN(v.x, 1);
+    double LA, RA, LB, RB;
+    muscl_evolve<PHI1>(v.x, v.y, cl, c.x, c.y, h, phi, LA, RA);          // cell A
+    muscl_evolve<PHI1>(v.y, vr, c.x, c.y, cr, h, phi, LB, RB);           // cell B
+    const double Rl = IMPEC_SHFL_UP(RB, 1), Lr = IMPEC_SHFL_DOWN(LA, 1);  // right state of cell jA-1, left state of cell jA+2
+    const double F0 = upwind_flux<PHI1>(v.x, Rl, LA, phi);
+    const double F1 = upwind_flux<PHI1>(v.y, RA, LB, phi);
+    const double F2 = upwind_flux<PHI1>(vr, RB, Lr, phi);
+    double rA = c.x + dt / hstep * (F0 - F1);
+    double rB = c.y + dt / hstep * (F1 - F2);
+    if (st2ok) {
+        if (AVG) { const d2 o = ld2(other + k); rA = 0.5 * (o.x + rA); rB = 0.5 * (o.y + rB); }
+        st2(cout + k, rA, rB);
+    } else if (st1ok) {
+        if (AVG) rA = 0.5 * (other[k] + rA);
+        cout[k] = rA;
+    }
+}
+template <bool PHI1, bool AVG>
+__global__ void __launch_bounds__(SY2_BLOCK) k_muscl_y2(Grid g, const double *__restrict__ cin, const double *__restrict__ vel,
+                                                        double *__restrict__ cout, const double *__restrict__ other,
+                                                        double dt, double hstep, double phi, int i0, int i1, int j0, int j1, int pfd) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)blockIdx.x * (SY2_BLOCK / 32) + (int)(threadIdx.x >> 5);
+    const int jA = j0 - 2 + SY2_OWN * gw + 2 * lane;                 // j0 is even (host): the pair is 16-byte aligned
+    // columns jA, jA+1 are read when they lie in [j0 - 2, j1 + 2) (two ghost columns on either side are allocated and filled)
+    const bool colok = jA + 1 < j1 + 2;
+    const bool own = colok && lane >= 1 && lane < 31 && jA >= j0;
+    const bool st2ok = own && jA + 1 < j1, st1ok = own && jA < j1;
+    const int ia = i0 + (int)blockIdx.y * SY2_ROWS;
+    const int ib = (ia + SY2_ROWS < i1) ? ia + SY2_ROWS : i1;
+    const double h = 0.5 * dt / hstep;
+    const size_t ld = (size_t)g.ld;
+    const size_t kb = gidx(g, ia, colok ? jA : j0);
+    for (int i = ia; i < ib; i += 2) {
+        const size_t k = kb + (size_t)(i - ia) * ld;
+        if (pfd > 0 && i + pfd + 1 < ib) {
+            const size_t kp = k + (size_t)pfd * ld;
+            pf_l2(cin + kp); pf_l2(vel + kp); pf_l2(cin + kp + ld); pf_l2(vel + kp + ld);
+            if (AVG) { pf_l2(other + kp); pf_l2(other + kp + ld); }
+        }
+        muscl_y2_row<PHI1, AVG>(g, cin, vel, cout, other, k, dt, hstep, h, phi, st2ok, st1ok);
+        // (an odd row count: the last iteration repeats row ib - 1 -- identical values stored twice -- so that all lanes of the warp stay
+        //  on one path through the shuffles)
+        muscl_y2_row<PHI1, AVG>(g, cin, vel, cout, other, (i + 1 < ib) ? k + ld : k, dt, hstep, h, phi, st2ok, st1ok);
     }
 }
 

@@ -38,7 +38,8 @@ protected:
     virtual bool Solve(Array2d &c, const Array3d &v, double const *const q, const double dt);
     virtual int MethodId() const = 0;                    // IMPEC_MUSCL | IMPEC_UPWIND
 public:
-    // The reference exposes the raw intercell fluxes; on the device they exist only inside the sweep kernels.
+    // The reference exposes the raw intercell fluxes (src/HyperbolicSplitSolver.h:19-22); the sweep kernels evaluate theirs on the fly, so
+    // these two run a dedicated flux kernel and fill F / G in the reference's shape.
     virtual void CalculateIntercellFlux_F(Array2d &F, const Array2d &c, const Array3d &v, const double dt);
     virtual void CalculateIntercellFlux_G(Array2d &G, const Array2d &c, const Array3d &v, const double dt);
     bool Advect_X(Array2d &c, const Array3d &v, const double dt);

@@ -217,12 +217,21 @@ bool HyperbolicSplitSolver::Solve(Array2d &c, const Array3d &v, double const *co
     c.MarkDeviceNewer();
     return true;
 }
-void HyperbolicSplitSolver::CalculateIntercellFlux_F(Array2d &, const Array2d &, const Array3d &, const double) {
-    throw std::logic_error("CalculateIntercellFlux_F: intercell fluxes are evaluated inside the fused sweep kernel (Advect_X); no standalone F array exists on the device");
+// CalculateIntercellFlux_F / _G (src/MUSCLSplitSolver.cpp:102-189, src/UpwindSplitSolver.cpp:43-61): the sweeps evaluate their fluxes on the
+// fly, so the flux FIELD is produced on request by its own kernel (impec_intercell_flux) and copied into the caller's array, which
+// keeps the reference's shape and index base (F: (N1+1) x (N2+2g) from (0,-g); G: (N1+2g) x (N2+1) from (-g,0)).
+static void intercell_flux(SimParams *sp, int method, int dir, Array2d &F, const Array2d &c, const Array3d &v, const double dt) {
+    impec_ctx *ctx = DeviceContext::Get(sp);
+    DeviceContext::SetMethod(ctx, method);
+    DeviceContext::Use(ctx, &c, nullptr, &v, nullptr, sp);
+    const int g = sp->c_bounds;
+    const int rows = dir == 0 ? sp->N1 + 1 : sp->N1 + 2 * g, cols = dir == 0 ? sp->N2 + 2 * g : sp->N2 + 1;
+    const int bi = dir == 0 ? 0 : -g, bj = dir == 0 ? -g : 0;
+    if (F.extent(0) != rows || F.extent(1) != cols) { F.resize(rows, cols); Idx2d idx; idx[0] = bi; idx[1] = bj; F.reindexSelf(idx); }
+    DeviceContext::Check(ctx, impec_intercell_flux(ctx, dir, dt, F.data()), "impec_intercell_flux");      // row-major, same shape
 }
-void HyperbolicSplitSolver::CalculateIntercellFlux_G(Array2d &, const Array2d &, const Array3d &, const double) {
-    throw std::logic_error("CalculateIntercellFlux_G: intercell fluxes are evaluated inside the fused sweep kernel (Advect_Y); no standalone G array exists on the device");
-}
+void HyperbolicSplitSolver::CalculateIntercellFlux_F(Array2d &F, const Array2d &c, const Array3d &v, const double dt) { intercell_flux(sp, MethodId(), 0, F, c, v, dt); }
+void HyperbolicSplitSolver::CalculateIntercellFlux_G(Array2d &G, const Array2d &c, const Array3d &v, const double dt) { intercell_flux(sp, MethodId(), 1, G, c, v, dt); }
 MUSCLSplitSolver::MUSCLSplitSolver(SimParams *sp) : HyperbolicSplitSolver(sp) {}
 int MUSCLSplitSolver::MethodId() const { return IMPEC_MUSCL; }
 UpwindSplitSolver::UpwindSplitSolver(SimParams *sp) : HyperbolicSplitSolver(sp) {}

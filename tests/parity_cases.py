@@ -81,6 +81,27 @@ def check_single_sweeps_bitexact(emulated, N=24):
     ctx.close()
 
 
+def check_intercell_fluxes(emulated, N=24):
+    """CalculateIntercellFlux_F / _G as fields (src/HyperbolicSplitSolver.h:19-22): bit-exact against the oracle for MUSCL and upwind."""
+    lib = O.lib()
+    for method in (O.MUSCL, O.UPWIND):
+        base, Po, c, u, v = advection_case(N, hyper_method=method)
+        rng = np.random.default_rng(13)
+        u += 0.4 * rng.random(u.shape); v -= 0.3 * rng.random(v.shape)
+        lib.orc_fill_boundaries(C.byref(Po), c)
+        Pi = I.default_params(emulated=emulated, **base)
+        ctx = I.Context(Pi, emulated=emulated)
+        ctx.upload_velocity(aos(u, v)); ctx.upload_q(np.zeros(N * N)); ctx.upload_c(c)
+        g = Po.g
+        F = np.zeros((N + 1, N + 2 * g)); G = np.zeros((N + 2 * g, N + 1))
+        lib.orc_flux_F(C.byref(Po), method, c, u, 0.01, F)
+        lib.orc_flux_G(C.byref(Po), method, c, v, 0.01, G)
+        assert np.array_equal(ctx.intercell_flux(0, 0.01), F)
+        assert np.array_equal(ctx.intercell_flux(1, 0.01), G)
+        assert np.abs(F).max() > 0 and np.abs(G).max() > 0
+        ctx.close()
+
+
 def check_sweep_variants(emulated, N=150):
     """k_muscl_x / k_muscl_y (one reconstruction per cell) against k_sweep (three per cell): bit-identical, any size
     (no oracle needed, so this also runs at sizes the oracle would be slow on)."""

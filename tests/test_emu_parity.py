@@ -20,6 +20,7 @@ def emu_lib():
 def test_ghost_fills(): pc.check_ghost_fills(True)
 def test_velocity_roundtrip(): pc.check_velocity_roundtrip(True)
 def test_single_sweeps_bitexact(): pc.check_single_sweeps_bitexact(True)
+def test_intercell_fluxes_bitexact(): pc.check_intercell_fluxes(True)
 def test_single_sweeps_multitile_bitexact(): pc.check_single_sweeps_bitexact(True, N=300)      # > 64 rows (k_muscl_x chunks) and > 256 columns (k_muscl_y tiles)
 def test_advection_muscl_multitile_bitexact(): pc.check_advection_bitexact(True, N=290, steps=1)
 def test_sweep_kernels_agree(): pc.check_sweep_variants(True, N=150)

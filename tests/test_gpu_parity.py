@@ -20,6 +20,7 @@ def test_ghost_fills(): pc.check_ghost_fills(False)
 def test_velocity_roundtrip(): pc.check_velocity_roundtrip(False)
 def test_single_sweeps_bitexact(): pc.check_single_sweeps_bitexact(False, N=96)
 def test_single_sweeps_multitile_bitexact(): pc.check_single_sweeps_bitexact(False, N=700)
+def test_intercell_fluxes_bitexact(): pc.check_intercell_fluxes(False, N=200)
 def test_sweep_kernels_agree(): pc.check_sweep_variants(False, N=1030)
 def test_advection_muscl_bitexact(): pc.check_advection_bitexact(False, N=200, steps=10)
 def test_advection_muscl_smooth_bitexact(): pc.check_advection_bitexact(False, N=128, steps=20, perturb=False)
@@ -211,3 +212,28 @@ def test_hyperbolic_test_config_at_4096():
 def test_integral_diagnostics_device_vs_host(): pc.check_integral_diagnostics(False, N=512, steps=3)
 def test_fused_operator_build_bitexact(): pc.check_fused_build(False, 512, 777)
 def test_fused_operator_build_bitexact_4096(): pc.check_fused_build(False, 4096, 4096, big=True)
+
+
+def test_cpp_host_layer_on_the_gpu(tmp_path):
+    """The C++ class surface (impec2d_b200/host: EllipticSolver/MGSolver, MUSCLSplitSolver, UpwindSplitSolver ...) linked against the PRODUCT
+    library and run on the B200: tests/host_api_check.cpp (fluxes vs sweeps to the bit, two IMPES steps through the classes) and the
+    `impec2d` driver on examples/parallel.cfg at 512^2."""
+    import os, re, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "impec2d_b200", "host"); lib_dir = os.path.join(root, "impec2d_b200")
+    subprocess.check_call(["make", "-s", "-C", host, "all"])
+    exe = str(tmp_path / "host_api_check")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-I", host, "-o", exe, os.path.join(root, "tests", "host_api_check.cpp"),
+                           "-L", lib_dir, "-limpec2d_host", "-limpec2d_b200", "-Wl,-rpath," + lib_dir])
+    text = open(os.path.join(root, "examples", "parallel.cfg")).read()
+    text = re.sub(r"x_cells\s*=\s*\d+", "x_cells = 512", text); text = re.sub(r"y_cells\s*=\s*\d+", "y_cells = 512", text)
+    text = text.replace('"/tmp', '"' + str(tmp_path))
+    cfg = tmp_path / "parallel.cfg"; cfg.write_text(text)
+    env = dict(os.environ)
+    nccl = [os.path.join(p, "nvidia", "nccl", "lib") for p in __import__("sys").path if os.path.exists(os.path.join(p, "nvidia", "nccl", "lib", "libnccl.so.2"))]
+    if nccl:
+        env["LD_LIBRARY_PATH"] = nccl[0] + ":" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.run([exe, str(cfg)], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "host_api_check ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    out = subprocess.run([os.path.join(lib_dir, "impec2d"), str(cfg), "--steps", "3"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "[3]\tITS_e:" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

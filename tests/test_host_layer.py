@@ -120,3 +120,23 @@ def test_driver_checkpoint_restart(tmp_path):
     assert last_a and last_a == last_b, (last_a, last_b)
     ca = np.loadtxt(str(da / "concentration.dat")); cb = np.loadtxt(str(db / "concentration.dat"))
     assert np.array_equal(ca, cb)
+
+
+def build_api_check(tmp_path, emulated=True):
+    exe = str(tmp_path / "host_api_check")
+    host_lib = "impec2d_host_emu" if emulated else "impec2d_host"
+    kern_lib = "impec2d_emu" if emulated else "impec2d_b200"
+    lib_dir = os.path.join(ROOT, "impec2d_b200")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-I", HOST, "-o", exe, os.path.join(ROOT, "tests", "host_api_check.cpp"),
+                           "-L", lib_dir, "-l" + host_lib, "-l" + kern_lib, "-Wl,-rpath," + lib_dir])
+    return exe
+
+
+def test_class_surface_called_directly(tmp_path):
+    """The C++ classes themselves (not the driver): CalculateIntercellFlux_F/G consistent with Advect_X/Y to the bit for MUSCL and
+    upwind (src/HyperbolicSplitSolver.h:19-22, .cpp:113-159), and the loop body of Impec2DSolver::Solve through EllipticSolver::Solve,
+    CalcVelocities, MaxStableTimestep and HyperbolicSolver::Solve."""
+    exe = build_api_check(tmp_path)
+    cfg = cfg_variant(tmp_path, "parallel.cfg", [(r"x_cells\s*=\s*\d+", "x_cells = 48"), (r"y_cells\s*=\s*\d+", "y_cells = 48")])
+    out = subprocess.run([exe, cfg], capture_output=True, text=True)
+    assert out.returncode == 0 and "host_api_check ok" in out.stdout, out.stdout + out.stderr
