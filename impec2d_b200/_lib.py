@@ -63,9 +63,9 @@ EXPORTS = [
     "impec_ctx_destroy", "impec_last_error", "impec_synchronize", "impec_upload_c", "impec_upload_p", "impec_upload_q",
     "impec_upload_velocity", "impec_download_c", "impec_download_p", "impec_download_velocity", "impec_field_layout",
     "impec_field_dev", "impec_set_q_dev_changed", "impec_fill_boundaries", "impec_pressure_solve", "impec_calc_velocities",
-    "impec_max_stable_dt", "impec_source_split", "impec_advect_x", "impec_advect_y", "impec_advect_split", "impec_intercell_flux",
+    "impec_max_stable_dt", "impec_source_split", "impec_advect_x", "impec_advect_y", "impec_advect_split", "impec_intercell_flux", "impec_gather_rows",
     "impec_diffusion_split", "impec_transport_step", "impec_impes_step", "impec_diagnostics", "impec_integral_diagnostics", "impec_build_operator",
-    "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_overlapped_exchanges", "impec_reset_state", "impec_set_option",
+    "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_overlapped_exchanges", "impec_last_parabolic_info", "impec_reset_state", "impec_set_option",
     "impec_profile_kernel", "impec_init_source", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
     "impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows", "impec_init_source_rows", "impec_synth_state_rows",
     "impec_comm_backend", "impec_transfer_bytes", "impec_project_dims", "impec_project_to_diagonal", "impec_checkpoint_save", "impec_checkpoint_load",
@@ -139,7 +139,9 @@ def load(emulated=False):
     L.impec_vcycle.argtypes = [vp, vp, vp]
     L.impec_mg_levels.argtypes = [vp]
     L.impec_intercell_flux.argtypes = [vp, i, d, vp]
+    L.impec_gather_rows.argtypes = [vp, C.c_char_p, vp]
     L.impec_kernel_launches.argtypes = [vp]; L.impec_kernel_launches.restype = C.c_longlong
+    L.impec_last_parabolic_info.argtypes = [vp, C.POINTER(SolveInfo)]
     L.impec_overlapped_exchanges.argtypes = [vp]; L.impec_overlapped_exchanges.restype = C.c_longlong
     L.impec_set_option.argtypes = [vp, C.c_char_p, d]
     L.impec_profile_kernel.argtypes = [vp, C.c_char_p, i, dptr]

@@ -113,6 +113,13 @@ class Context:
 
     def transport_step(self, dt): self._chk(self.L.impec_transport_step(self._h, dt))
 
+    def gather_rows(self, field):
+        """Whole-grid host copy of a slab-decomposed field ("c", "p": ghosted; "v": AoS velocity); collective over the ranks."""
+        P = self.P; g = P.g
+        out = np.zeros((P.N1 + 2 * g, P.N2 + 2 * g)) if field in ("c", "p") else np.zeros((P.N1 + 1 + 2 * g, P.N2 + 1 + 2 * g, 2))
+        self._chk(self.L.impec_gather_rows(self._h, field.encode(), _ptr(out)))
+        return out
+
     def intercell_flux(self, direction, dt):
         """CalculateIntercellFlux_F (direction 0, shape (N1+1, N2+2g)) / _G (direction 1, shape (N1+2g, N2+1)) of the current c and velocity."""
         P = self.P; g = P.g
@@ -163,6 +170,9 @@ class Context:
 
     def mg_levels(self): return self.L.impec_mg_levels(self._h)
     def kernel_launches(self): return self.L.impec_kernel_launches(self._h)
+    def last_parabolic_info(self):
+        info = _lib.SolveInfo(); self._chk(self.L.impec_last_parabolic_info(self._h, C.byref(info))); return info
+
     def overlapped_exchanges(self): return self.L.impec_overlapped_exchanges(self._h)
     def reset_state(self): self._chk(self.L.impec_reset_state(self._h))
     def set_option(self, key, value): self._chk(self.L.impec_set_option(self._h, key.encode(), float(value)))

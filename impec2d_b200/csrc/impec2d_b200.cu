@@ -81,6 +81,7 @@ struct impec_ctx {
     bool build_fused = true;                        // production runs: c -> links, DINV and FP32 copies in ONE march (kernels_build.inl); 0 = the five-pass build
     bool use_small = true;                          // levels of <= SM_MAXCELLS cells: whole V-cycle in one single-CTA launch (kernels_small.inl)
     long long launches = 0;
+    impec_solve_info last_para = {0, 0., 0., 0};     // the most recent Crank-Nicolson solve inside impec_transport_step (impec_last_parabolic_info)
     unsigned long long bytes_h2d = 0, bytes_d2h = 0;   // bytes of the field transfers this context issued (impec_transfer_bytes)
     double profile_dt = 0.0;                        // time step used by the "transport_step" / "diffusion_split" profiling hooks
     long long march_launches = 0;                   // launches of the marching multigrid kernels (diagnostic, IMPEC_VERBOSE)
@@ -109,7 +110,7 @@ struct impec_ctx {
     // marching kernels: rows of L2 software prefetch ahead of the march, per kernel family (PRE, POST / PLAIN, mat-vec, CN sweep);
     // option "l2_prefetch" sets all four, IMPEC_L2_PREFETCH="pre,post,mv,sgs" (or one number) each.  0 = off.
     int pf_pre = 4, pf_post = 4, pf_mv = 4, pf_sgs = 4;
-    int pf_sweep = 8;                               // MUSCL sweeps (option "sweep_prefetch" / IMPEC_SWEEP_PREFETCH)
+    int pf_sweep = 4;                               // MUSCL sweeps (option "sweep_prefetch" / IMPEC_SWEEP_PREFETCH)
     bool sweep_y_pairs = true;                      // MUSCL y sweep: column pairs per lane + shuffles (k_muscl_y2); 0 = the shared-memory tile kernel k_muscl_y
     bool overlap = true;                            // option "halo_overlap" / IMPEC_HALO_OVERLAP=0/1
     long long overlapped = 0;                       // exchanges issued that way (diagnostic)
@@ -708,6 +709,7 @@ extern "C" const char *impec_comm_backend(const impec_ctx *ctx) {
 extern "C" int impec_synchronize(impec_ctx *ctx) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return IMPEC_OK; }
 extern "C" int impec_mg_levels(const impec_ctx *ctx) { return (int)ctx->L.size(); }
 extern "C" long long impec_kernel_launches(const impec_ctx *ctx) { return ctx->launches; }
+extern "C" int impec_last_parabolic_info(const impec_ctx *ctx, impec_solve_info *info) { if (!ctx || !info) return IMPEC_ERR_ARG; *info = ctx->last_para; return IMPEC_OK; }
 extern "C" long long impec_overlapped_exchanges(const impec_ctx *ctx) { return ctx->overlapped; }
 
 extern "C" int impec_reset_state(impec_ctx *ctx) {
@@ -877,6 +879,47 @@ extern "C" int impec_download_velocity(impec_ctx *ctx, double *v_aos) {
     ctx->bytes_d2h += sizeof(double) * 2 * n;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return IMPEC_OK;
+}
+// Whole-grid copy of a slab-decomposed field for logging: every rank contributes its rows, every rank receives all of them in the
+// reference's host layout (ghosted c / p; AoS velocity).  Collective.  Ghost ROWS of the host array (and the wall face row u(N1,.)) are
+// left as the caller has them; ghost columns come with the rows.  On one rank this is impec_download_*.
+extern "C" int impec_gather_rows(impec_ctx *ctx, const char *field, double *host_full) {
+    if (!field || !host_full) return fail(ctx, IMPEC_ERR_ARG, "impec_gather_rows: null argument");
+    const std::string f(field);
+    if (f != "c" && f != "p" && f != "v") return fail(ctx, IMPEC_ERR_ARG, "impec_gather_rows: field must be c, p or v");
+    if (ctx->nranks == 1) return f == "c" ? impec_download_c(ctx, host_full) : (f == "p" ? impec_download_p(ctx, host_full) : impec_download_velocity(ctx, host_full));
+    const Grid &g = ctx->g; const int ng = ctx->P.g, R = ctx->nranks, N1g = ctx->N1g;
+    const size_t n = (size_t)g.N1 * g.ld, r0 = (size_t)IMPEC_GH * g.ld;
+    const int nf = f == "v" ? 2 : 1;
+    double *tmp = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&tmp, sizeof(double) * n * R * nf));
+    const double *src[2] = { f == "c" ? ctx->c : (f == "p" ? ctx->p : ctx->u), ctx->v };
+    int rc = IMPEC_OK;
+    for (int a = 0; a < nf && rc == IMPEC_OK; a++) rc = comm_allgather(ctx, src[a] + r0, tmp + (size_t)a * n * R, (long long)n);
+    if (rc == IMPEC_OK) {
+        if (nf == 1) {
+            const size_t W = (size_t)g.N2 + 2 * ng, w = W * sizeof(double);
+            if (cudaMemcpy2DAsync(host_full + (size_t)ng * W, w, tmp + (IMPEC_PJ - ng), (size_t)g.ld * sizeof(double), w, (size_t)N1g, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = IMPEC_ERR_CUDA;
+            ctx->bytes_d2h += w * (size_t)N1g;
+            if (rc == IMPEC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = IMPEC_ERR_CUDA;
+        } else {
+            std::vector<double> hu(n * R), hv(n * R);
+            if (cudaMemcpyAsync(hu.data(), tmp, sizeof(double) * n * R, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaMemcpyAsync(hv.data(), tmp + n * R, sizeof(double) * n * R, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = IMPEC_ERR_CUDA;
+            ctx->bytes_d2h += 2 * sizeof(double) * n * R;
+            const size_t W = (size_t)g.N2 + 1 + 2 * ng;
+            if (rc == IMPEC_OK)
+                for (int i = 0; i < N1g; i++)
+                    for (int j = -ng; j < g.N2 + 1 + ng; j++) {
+                        const size_t k = (size_t)i * g.ld + (size_t)(j + IMPEC_PJ), o = ((size_t)(i + ng) * W + (size_t)(j + ng)) * 2;
+                        host_full[o] = hu[k]; host_full[o + 1] = hv[k];
+                    }
+        }
+    }
+    cudaFree(tmp);
+    if (rc == IMPEC_ERR_CUDA) return fail(ctx, rc, "impec_gather_rows: copy failed");
+    return rc;
 }
 extern "C" int impec_transfer_bytes(const impec_ctx *ctx, unsigned long long *h2d, unsigned long long *d2h) {
     if (h2d) *h2d = ctx->bytes_h2d; if (d2h) *d2h = ctx->bytes_d2h;
@@ -1900,11 +1943,11 @@ extern "C" int impec_transport_step(impec_ctx *ctx, double dt) {
     int warn = IMPEC_OK;
     TRY(impec_source_split(ctx, 0.5 * dt));
     TRY(impec_fill_boundaries(ctx));
-    if (ctx->P.diffusion) TRY_WARN(impec_diffusion_split(ctx, 0.5 * dt, nullptr), warn);
+    if (ctx->P.diffusion) TRY_WARN(impec_diffusion_split(ctx, 0.5 * dt, &ctx->last_para), warn);
     TRY(impec_advect_split(ctx, dt));
     TRY(impec_source_split(ctx, 0.5 * dt));
     TRY(impec_fill_boundaries(ctx));
-    if (ctx->P.diffusion) TRY_WARN(impec_diffusion_split(ctx, 0.5 * dt, nullptr), warn);
+    if (ctx->P.diffusion) TRY_WARN(impec_diffusion_split(ctx, 0.5 * dt, &ctx->last_para), warn);
     return warn;
 }
 

@@ -5,8 +5,36 @@
 #include <cstring>
 #include <cstdlib>
 #include <iostream>
+#include <fstream>
+#include <string>
+#include <chrono>
+#include <thread>
+#include <cstdio>
+#include <unistd.h>
 
 namespace {
+int g_rank = 0, g_nranks = 1;
+// NCCL unique id through the file system: rank 0 writes <file>.tmp and renames it into place, the other ranks poll for it
+std::string id_file() {
+    if (const char *e = getenv("IMPEC_NCCL_ID_FILE")) return e;
+    const char *port = getenv("MASTER_PORT");
+    return std::string("/tmp/impec2d_nccl_id.") + (port ? std::string(port) : std::to_string((long)getppid()));
+}
+bool exchange_nccl_id(char id[128]) {
+    const std::string path = id_file();
+    if (g_rank == 0) {
+        if (impec_nccl_unique_id(id) != IMPEC_OK) return false;
+        const std::string tmp = path + ".tmp";
+        { std::ofstream f(tmp.c_str(), std::ios::binary); if (!f.write(id, 128)) return false; }
+        return std::rename(tmp.c_str(), path.c_str()) == 0;
+    }
+    for (int tries = 0; tries < 1200; tries++) {                 // up to 60 s
+        std::ifstream f(path.c_str(), std::ios::binary);
+        if (f && f.read(id, 128)) return true;
+        std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    }
+    return false;
+}
 struct Entry { impec_ctx *ctx = nullptr; impec_params P; const double *q_uploaded = nullptr; };
 std::map<SimParams *, Entry> g_ctx;
 // arrays currently bound to a context: a context is never destroyed under them (DeviceBound::UnbindAll)
@@ -53,9 +81,16 @@ impec_ctx *DeviceContext::Get(SimParams *sp) {
     const impec_params P = ToParams(sp);
     if (e.ctx && std::memcmp(&P, &e.P, sizeof(P)) == 0) return e.ctx;
     if (e.ctx) { DeviceBound::UnbindAll(e.ctx); impec_ctx_destroy(e.ctx); e.ctx = nullptr; }   // grid/physics changed: arrays keep their data on the host
-    const char *dev = getenv("IMPEC_DEVICE");
-    const int rc = impec_ctx_create(&P, dev ? atoi(dev) : 0, 0, 1, nullptr, nullptr, &e.ctx);
+    const char *dev = getenv("IMPEC_DEVICE"), *lr = getenv("LOCAL_RANK");
+    const int device = dev ? atoi(dev) : (g_nranks > 1 ? (lr ? atoi(lr) : g_rank) : 0);
+    char id[128]; const char *idp = nullptr;
+    if (g_nranks > 1) {
+        if (!exchange_nccl_id(id)) { std::cerr << "impec2d_b200: rank " << g_rank << " could not exchange the NCCL id through " << id_file() << std::endl; exit(1); }
+        idp = id;
+    }
+    const int rc = impec_ctx_create(&P, device, g_rank, g_nranks, idp, nullptr, &e.ctx);
     Check(e.ctx, rc, "impec_ctx_create");
+    if (g_nranks > 1 && g_rank == 0) std::remove(id_file().c_str());     // every rank has joined the communicator
     e.P = P; e.q_uploaded = nullptr;
     return e.ctx;
 }
@@ -65,6 +100,15 @@ void DeviceContext::Release(SimParams *sp) {
     if (it == g_ctx.end()) return;
     if (it->second.ctx) { DeviceBound::UnbindAll(it->second.ctx); impec_ctx_destroy(it->second.ctx); }
     g_ctx.erase(it);
+}
+
+void DeviceContext::SetRanks(int rank, int nranks) { g_rank = rank; g_nranks = nranks < 1 ? 1 : nranks; }
+int DeviceContext::Rank() { return g_rank; }
+int DeviceContext::NumRanks() { return g_nranks; }
+void DeviceContext::GatherGlobal(impec_ctx *ctx, const Array2d *c, const Array2d *p, const Array3d *v) {
+    if (c) { if (!c->BoundTo(ctx)) c->Bind(ctx, FIELD_C); c->GatherGlobal("c"); }
+    if (p) { if (!p->BoundTo(ctx)) p->Bind(ctx, FIELD_P); p->GatherGlobal("p"); }
+    if (v) { if (!v->BoundTo(ctx)) v->Bind(ctx, FIELD_V); v->GatherGlobal("v"); }
 }
 
 void DeviceContext::SetMethod(impec_ctx *ctx, int method) { Check(ctx, impec_set_option(ctx, "hyper_method", (double)method), "impec_set_option(hyper_method)"); }
@@ -102,6 +146,12 @@ void DeviceBound::pull() const {
     else if (field_ == FIELD_V) rc = impec_download_velocity(ctx_, raw());
     DeviceContext::Check(ctx_, rc, "download");
     dev_newer_ = false;
+}
+void DeviceBound::GatherGlobal(const char *field) const {
+    if (!ctx_) return;
+    SyncToDevice();                                  // host edits (if any) go up first: the gather reads the device copy
+    DeviceContext::Check(ctx_, impec_gather_rows(ctx_, field, raw()), "impec_gather_rows");
+    dev_newer_ = false;                              // the host copy now holds every rank's rows (own rows included)
 }
 void DeviceBound::SyncToDevice() const {
     if (!ctx_ || !host_dirty_) return;

@@ -22,6 +22,7 @@ public:
     void SetNu(double nu);
     int GetLastIts() { return last_its; }
     int GetLastParabolicIts() { return last_parabolic_its; }
+    void SetLastParabolicIts(int n) { last_parabolic_its = n; }        // extra: the CN solves run inside the fused transport step on the device
     double GetAvgIts() { return calls > 0 ? ((double)total_its) / calls : 0; }
     double GetLastRelativeResidual() { return last_relres; }          // extra: what HYPRE's GetFinalRelativeResidualNorm returned
     double GetLastTrueRelativeResidual() { return last_true_relres; } // extra: ||b - Ax||/||b|| recomputed

@@ -41,6 +41,7 @@ public:
     static void UnbindAll(const impec_ctx *ctx);  // detach every array bound to ctx (called before ctx is destroyed)
     void SyncToDevice() const;         // upload if the host copy is dirty
     void MarkDeviceNewer() const { dev_newer_ = true; host_dirty_ = false; }
+    void GatherGlobal(const char *field) const;   // multi-GPU: fill the host copy with the rows of ALL ranks (collective; impec_gather_rows)
     bool BoundTo(const impec_ctx *c) const { return ctx_ == c; }
 };
 

@@ -19,6 +19,7 @@ protected:
     SWEEP prev_first_sweep;
     bool SourceSplit(Array2d &c, double const *const q, const double dt);
     double Flux(double vel, double conc) { return vel * conc / sp->porosity; }
+    void ReportParabolicIts(int n) { if (mg) mg->SetLastParabolicIts(n); }   // CN solves run inside the fused transport step on the device
 public:
     virtual bool Solve(Array2d &c, const Array3d &v, double const *const q, const double dt) = 0;
     HyperbolicSolver(SimParams *sp);

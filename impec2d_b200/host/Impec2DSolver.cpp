@@ -15,6 +15,7 @@ using namespace std;
 
 Impec2DSolver::Impec2DSolver(const string &configfile, int myid, int num_procs) : es(NULL), hs(NULL), q(NULL), myid(myid), num_procs(num_procs) {
     sp = new SimParams(configfile);          // every rank parses the file itself (no token ring needed: read-only)
+    DeviceContext::SetRanks(myid, num_procs);                          // one process per GPU, slabs of rows (src/Driver.cpp:58-87 passes the MPI rank here)
     if (sp->gnuplot && myid == 0) cout << "(gnuplot live view is not part of this build; results are written to files)" << endl;
     Initialize();
 }
@@ -58,6 +59,9 @@ void Impec2DSolver::InitializeConcentration() {
 }
 void Impec2DSolver::InitializeSource() { InitSource(sp, q); }
 
+// one binary restart file per rank (each holds that rank's slab)
+string Impec2DSolver::RankFile(const string &f) const { if (num_procs <= 1) return f; stringstream ss; ss << f << ".rank" << myid; return ss.str(); }
+
 bool Impec2DSolver::Run() { return sp->is_test ? TestComponent() : Solve(); }
 
 bool Impec2DSolver::Solve() {
@@ -75,7 +79,7 @@ bool Impec2DSolver::Solve() {
     if (!restart_file.empty()) {
         DeviceContext::Use(ctx, &c, &p, &v, q, sp);                    // bind the arrays, upload q; then replace the device state
         long long step0 = 0;
-        DeviceContext::Check(ctx, impec_checkpoint_load(ctx, restart_file.c_str(), &t, &step0), "impec_checkpoint_load");
+        DeviceContext::Check(ctx, impec_checkpoint_load(ctx, RankFile(restart_file).c_str(), &t, &step0), "impec_checkpoint_load");
         c.MarkDeviceNewer(); p.MarkDeviceNewer(); v.MarkDeviceNewer();
         counter = (int)step0;
         while (tidx < sp->times.size() && sp->times[tidx] <= t) tidx++;
@@ -105,16 +109,16 @@ bool Impec2DSolver::Solve() {
         ds.diff_err = sp->check_divergence ? d.divergence_error : -1;
         diagstates.push_back(ds);
         if (myid == 0) OutputState(ds);
-        if (sp->log_to_file && myid == 0) {
+        if (sp->log_to_file) {                                          // (every rank takes the same decisions: LogResults gathers collectively)
             if (find(sp->times.begin(), sp->times.end(), t) != sp->times.end()) LogResults(t, true);
             const bool listed = find(sp->counters.begin(), sp->counters.end(), counter) != sp->counters.end();
             if (listed || (sp->log_skip_steps != 0 && (counter == 1 || counter % sp->log_skip_steps == 0))) LogResults(counter, false);
         }
         maxc = max(maxc, d.c_max); minc = min(minc, d.c_min);
         if (!checkpoint_file.empty() && checkpoint_every > 0 && counter % checkpoint_every == 0)
-            DeviceContext::Check(ctx, impec_checkpoint_save(ctx, checkpoint_file.c_str(), t, counter), "impec_checkpoint_save");
+            DeviceContext::Check(ctx, impec_checkpoint_save(ctx, RankFile(checkpoint_file).c_str(), t, counter), "impec_checkpoint_save");
     }
-    if (!checkpoint_file.empty()) DeviceContext::Check(ctx, impec_checkpoint_save(ctx, checkpoint_file.c_str(), t, counter), "impec_checkpoint_save");
+    if (!checkpoint_file.empty()) DeviceContext::Check(ctx, impec_checkpoint_save(ctx, RankFile(checkpoint_file).c_str(), t, counter), "impec_checkpoint_save");
     if (counter - first_step) avg_fill /= (counter - first_step);
     elapsed_ms = chrono::duration<double, milli>(chrono::steady_clock::now() - t_start).count();
     if (myid == 0) {
@@ -122,9 +126,9 @@ bool Impec2DSolver::Solve() {
         cout << "---------------------------------------------------------" << endl;
         if (counter > 0) cout << "Average no. of Iterations: " << es->GetAvgIts() << endl;
         cout << "Elapsed time [ms]: " << (long)(elapsed_ms + 0.5) << endl;
-        LogResults(-1, false);
         WriteDiagnostics();
     }
+    LogResults(-1, false);
     return state;
 }
 
@@ -175,7 +179,19 @@ void Impec2DSolver::LogResults(double postfix, bool logTime) {
     string dir = sp->log_dir, post = ".dat";
     if (postfix < 0) dir = sp->results_dir;
     else { stringstream ss; ss << "_"; if (logTime) ss << "t_"; ss << postfix; post = ss.str() + ".dat"; }
-    if ((size_t)sp->N1 * sp->N2 > (size_t)4096 * 4096) { if (postfix < 0) cout << "(text output skipped above 4096^2)" << endl; return; }
+    if ((size_t)sp->N1 * sp->N2 > (size_t)4096 * 4096) { if (postfix < 0 && myid == 0) cout << "(text output skipped above 4096^2)" << endl; return; }
+    if (num_procs > 1) {
+        // Slabs: every rank contributes its rows (collective), rank 0 writes.  The parallel -> diagonal projection kernel works on one
+        // GPU's field, so a multi-GPU PARALLEL run writes c and p on the native grid.
+        DeviceContext::GatherGlobal(DeviceContext::Get(sp), &c, postfix < 0 ? &p : NULL, postfix < 0 ? &v : NULL);
+        if (myid != 0) return;
+        PrintDToPlotFile(dir + "/concentration" + post, c, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->c_bounds);
+        if (postfix < 0) {
+            PrintDToPlotFile(dir + "/pressure" + post, p, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->p_bounds);
+            PrintVelToPlotFile(dir + "/velocity_u" + post, dir + "/velocity_v" + post, v, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->v_bounds, sp->N1, sp->N2);
+        }
+        return;
+    }
     if (sp->stype == PARALLEL) {
         int d_N1, d_N2; double d_dx, d_dy;
         Array2d diag_c, diag_p;

@@ -42,6 +42,7 @@ private:
     double Advection();
     void OutputState(const DiagState &ds);
     void WriteDiagnostics();
+    std::string RankFile(const std::string &f) const;
     void LogResults(double postfix, bool logTime);
     void Project(Array2d &arrd, Array2d const *const arrp, int bounds, int &d_N1, int &d_N2, double &d_dx, double &d_dy);   // src/Impec2DSolver.h
 };

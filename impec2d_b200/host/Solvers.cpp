@@ -214,6 +214,7 @@ bool HyperbolicSplitSolver::Solve(Array2d &c, const Array3d &v, double const *co
     DeviceContext::SetMethod(ctx, MethodId());
     DeviceContext::Use(ctx, &c, nullptr, &v, q, sp);
     DeviceContext::Check(ctx, impec_transport_step(ctx, dt), "impec_transport_step");
+    if (sp->diffusion) { impec_solve_info pi; if (impec_last_parabolic_info(ctx, &pi) == IMPEC_OK) ReportParabolicIts(pi.iterations); }
     c.MarkDeviceNewer();
     return true;
 }

@@ -128,6 +128,10 @@ int   impec_upload_velocity(impec_ctx *ctx, const double *v_aos);
 int   impec_download_c(impec_ctx *ctx, double *c_ghosted);
 int   impec_download_p(impec_ctx *ctx, double *p_ghosted);
 int   impec_download_velocity(impec_ctx *ctx, double *v_aos);
+/* multi-GPU logging: the WHOLE field ("c", "p": ghosted scalar layout; "v": AoS velocity) assembled from the slabs of all ranks into
+ * every rank's host array (collective).  Ghost rows and the wall face row are left untouched.  The reference keeps full copies of
+ * p, c, v on every rank (src/MGSolver.cpp:670-706 MapHYPREVectorToVertex + Allgather); here that happens only when asked for. */
+int   impec_gather_rows(impec_ctx *ctx, const char *field, double *host_full);
 /* Multi-rank note: upload/download take the GLOBAL host arrays and move only this rank's slab (plus its ghost rows);
  * the *_rows variants take just the slab: c,p as (nrows+2g) x (N2+2g), q as nrows x N2. */
 int   impec_upload_c_rows(impec_ctx *ctx, const double *c_slab_ghosted);
@@ -190,6 +194,7 @@ int   impec_build_operator(impec_ctx *ctx);                              /* a2-a
 int   impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host); /* one MG cycle; NULL/NULL = on the internal residual */
 int   impec_mg_levels(const impec_ctx *ctx);
 long long impec_kernel_launches(const impec_ctx *ctx);                   /* kernels launched by this context so far */
+int   impec_last_parabolic_info(const impec_ctx *ctx, impec_solve_info *info); /* the last Crank-Nicolson solve run inside impec_transport_step / impec_impes_step (MGSolver::last_parabolic_its, src/MGSolver.cpp:972) */
 long long impec_overlapped_exchanges(const impec_ctx *ctx);              /* halo exchanges issued concurrently with the interior row chunks of their consumer (multi-GPU) */
 int   impec_reset_state(impec_ctx *ctx);                                 /* produced mass := 0, sweep parity := Y */
 /* options: "warm_start" (x0 = previous p instead of the reference's 0), "stagnation_guard" (stop PCG at the FP64

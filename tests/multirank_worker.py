@@ -61,6 +61,10 @@ def main():
     assert abs(d.c_max - dr.c_max) <= 1e-9 and abs(d.c_min - dr.c_min) <= 1e-9, (d.c_max, dr.c_max)
     assert abs(d.divergence_error - dr.divergence_error) <= 1e-9 + 1e-3 * dr.divergence_error, (d.divergence_error, dr.divergence_error)
     assert abs(d.boundary_velocity_error - dr.boundary_velocity_error) <= 1e-9, (d.boundary_velocity_error, dr.boundary_velocity_error)
+    # impec_gather_rows: the whole field assembled from all slabs must equal the 1-rank field (interior rows; all columns of c / p)
+    cga = ctx.gather_rows("c"); pgl = ctx.gather_rows("p"); vg = ctx.gather_rows("v"); vr = ref.download_velocity()
+    assert np.abs(cga[g:-g, :] - cr[g:-g, :]).max() <= 1e-9 and np.abs(pgl[g:-g, g:-g] - pr[g:-g, g:-g]).max() <= 1e-9 * np.abs(pr).max()
+    assert np.abs(vg[g:g + N1, g:-g, :] - vr[g:g + N1, g:-g, :]).max() <= 1e-8 * max(np.abs(vr).max(), 1e-30)
     if os.environ.get("IMPEC_TEST_CKPT"):
         # per-rank binary checkpoint: save, step, restore, step again -> the same slab bit for bit
         import tempfile

@@ -29,3 +29,36 @@ def test_slabs_match_single_gpu(N1, N2, stype, diffusion, steps, march):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(" ok: ") == world, out.stdout
+
+
+def test_cpp_driver_on_two_gpus(tmp_path):
+    """The reference-facing C++ driver (`impec2d cfg`, Impec2DSolver(cfg, myid, num_procs)) as two processes on two GPUs (ranks from the
+    environment, NCCL id through a file) against the same driver on one GPU: diagnostics and the final concentration / pressure /
+    velocity files (gathered from both slabs by rank 0) agree to 1e-9."""
+    import re
+    import numpy as np
+    if ngpus() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    lib_dir = os.path.join(ROOT, "impec2d_b200")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(lib_dir, "host"), "all"])
+    exe = os.path.join(lib_dir, "impec2d")
+    text = open(os.path.join(ROOT, "examples", "diagonal_dispersion.cfg")).read()
+    text = re.sub(r"x_cells\s*=\s*\d+", "x_cells = 256", text); text = re.sub(r"y_cells\s*=\s*\d+", "y_cells = 128", text)
+    outs = {}
+    for world in (1, 2):
+        d = tmp_path / ("w%d" % world); d.mkdir()
+        cfg = d / "run.cfg"; cfg.write_text(text.replace('"/tmp', '"' + str(d)))
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, IMPEC_RANK=str(r), IMPEC_NRANKS=str(world), IMPEC_DEVICE=str(r), IMPEC_NCCL_ID_FILE=str(d / "nccl_id"), IMPEC_DIST_MIN_CELLS="0")
+            procs.append(subprocess.Popen([exe, str(cfg), "--steps", "3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+        logs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(l[-2000:] for l in logs)
+        assert "[3]\tITS_e:" in logs[0], logs[0][-2000:]
+        res = [os.path.join(dp, f) for dp, _, fs in os.walk(str(d)) for f in fs if f.endswith(".dat")]
+        outs[world] = {os.path.basename(f): np.loadtxt(f) for f in res}
+    assert {"concentration.dat", "pressure.dat", "velocity_u.dat", "velocity_v.dat", "diagnostics.dat"} <= set(outs[2]), sorted(outs[2])
+    for name, a in outs[1].items():
+        b = outs[2][name]
+        assert a.shape == b.shape, name
+        assert np.abs(a - b).max() <= 1e-9 * max(np.abs(a).max(), 1.0), (name, np.abs(a - b).max())
