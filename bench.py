@@ -386,9 +386,12 @@ def main():
     step_s = ms_total / K * 1e-3 * world           # GPU-seconds per step
     traffic = None; traffic_src = None             # measured DRAM bytes per launch of the dominant kernel (ncu capture, 1 GPU, same grid)
     if kind == "impes":
-        dom = "fused_post"; dom_name = "k_mg_march_post<PROLONG> (prolong + correct + red-black post-smooth + <r,z>, fine level; register march)"
+        dom = "fused_post"; dom_name = "k_mg_march_post<PROLONG> (prolong + correct + red-black post-smooth + <r,z>, fine level; register march, L2 prefetch 4 rows ahead)"
     else:
-        dom = "sweep_y"; dom_name = "k_muscl_y (MUSCL-Hancock y sweep, fluxes on the fly; 2 of the 4 sweeps of a step)"
+        # the slower of the two sweep kernels (each runs twice per step)
+        dom = "sweep_x" if prof["sweep_x"] >= prof["sweep_y"] else "sweep_y"
+        dom_name = ("k_muscl_x (MUSCL-Hancock x sweep: a thread marches down a column, fluxes on the fly; 2 of the 4 sweeps of a step)" if dom == "sweep_x" else
+                    "k_muscl_y2 (MUSCL-Hancock y sweep: column pairs per lane, neighbours by shuffle, fluxes on the fly; 2 of the 4 sweeps of a step)")
     try:
         cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
         for f in reversed(cands):
@@ -415,7 +418,9 @@ def main():
             # per CN half step: links 32 + DINV/FP32 copies 56 + rhs 40 + n_cn (k_sgs_march 34 + mat-vec 56 + update 48) + copy-out 16; two per step
             cn = 2.0 * (32.0 + 56.0 + 40.0 + 9.0 * (34.0 + 56.0 + 48.0) + 16.0)
         step_model = (32.0 + its_mean * (208.0 + 128.0) + 48.0 + 128.0) * NN
-        step_moved = (ctx_option_bytes_operator() + its_mean * (113.3 + 56.0 + 48.0) + 56.0 + 96.0 + cn) * NN
+        # operator build 74 (one march c -> links, DINV, FP32 copies: 48; coarsening of the links down the hierarchy: 26), per PCG iteration the
+        # cycle 113.3 + mat-vec 56 + update 48, velocity + CFL 32 (+ 8 ghost fills), transport 4 x 24 (+ 8 source / fills)
+        step_moved = (ctx_option_bytes_operator() + its_mean * (113.3 + 56.0 + 48.0) + 40.0 + 104.0 + cn) * NN
         roofline["vcycle"] = {"ms": prof["vcycle"], "moved_bytes": vc_moved, "achieved_moved": vc_moved / (prof["vcycle"] * 1e-3) / 1e9,
                               "frac_moved": vc_moved / (prof["vcycle"] * 1e-3) / 1e9 / peak,
                               "survey_model_bytes": vc_model, "frac_survey_model": vc_model / (prof["vcycle"] * 1e-3) / 1e9 / peak}
@@ -462,6 +467,7 @@ def main():
         run = {"mg_levels": ctx.mg_levels(), "comm_backend": ctx.comm_backend(),
                "parallelism": "1 GPU" if world == 1 else "%d slabs of %d rows along x; halo rows and scalar reductions over %s; multigrid levels below 4M cells replicated after an all-gather" % (world, nrows, ctx.comm_backend()),
                "coefficients": "multigrid cycle reads FP32 copies of the link/diagonal arrays (all arithmetic FP64; PCG mat-vec uses the FP64 operator)"}
+        run["halo_exchanges_overlapped_with_interior_chunks"] = int(ctx.overlapped_exchanges())
         if kind == "impes":
             run.update({"pcg_iterations": its, "relres": relres, "true_relres": true_rr})
         line = {"metric": metric, "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -479,8 +485,9 @@ def main():
 
 
 def ctx_option_bytes_operator():
-    """Bytes per cell the operator build moves: the fused build reads c and writes the FP64 links, DINV and the FP32 copies."""
-    return 64.0
+    """Bytes per cell the operator build moves: the fused build reads c and writes the FP64 links, DINV and the FP32
+    copies (48), then the links are coarsened level by level (26, measured: 1.1 ms at 16384^2)."""
+    return 74.0
 
 
 if __name__ == "__main__":

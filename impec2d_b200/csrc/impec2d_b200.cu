@@ -7,9 +7,7 @@
 #include "kernels_build.inl"
 #include "kernels_fused.inl"
 #include "kernels_march.inl"
-#include "kernels_staged.inl"
 #include "kernels_small.inl"
-#include "kernels_tail.inl"
 #include "../../include/impec2d_b200.h"
 
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
@@ -65,8 +63,6 @@ struct impec_ctx {
     bool mob_valid = false, op_valid = false;
     bool warm_start = false;
     bool fused = true;                              // fused tile kernels (kernels_fused.inl) vs one kernel per colour pass
-    bool staged = false;                            // cp.async-staged 32-row tile kernels (kernels_staged.inl); needs links_f32.
-                                                    // Measured slower than k_mg_fused (shared-memory issue bound, profiles/r1g_*): off by default
     bool stagnation_guard = false;                  // stop PCG once the TRUE residual has hit its floating-point floor (off: reference semantics)
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
     bool fast_r0 = true;                            // initial PCG residual for x0 = 0: copy of rhs + fix-up around the pin instead of a residual pass
@@ -119,14 +115,6 @@ struct impec_ctx {
 #endif
     // CUDA graph of the replicated multigrid tail (levels >= tail_level): identical launch sequence every visit
     int tail_level = -1;
-    // the same tail as ONE persistent launch (kernels_tail.inl): program of phases in device memory, barrier counter, error flag
-    // OFF by default: measured on the B200 it is SLOWER than the CUDA-graph replay of the launches (0.297 vs 0.214 ms per visit at
-    // 16384^2): one CTA per SM (the bottom V-cycle needs 125 KB of shared memory) leaves each phase latency-bound, and a grid barrier
-    // costs about what a kernel boundary inside a graph costs.  Kept as an option (bit-identical results, tests/).
-    bool persist_tail = false, tail_ready = false, tail_ok = false;
-    TailProgram *tail_prog = nullptr; unsigned *tail_ctr = nullptr; double *tail_err = nullptr;
-    std::vector<std::pair<double *, double *> > tail_xt_final;
-    int tail_grid = 0; size_t tail_smem = 0; long long tail_phases = 0;
     bool use_graph = true, graph_ready = false;
     long long graph_launches = 0;
     std::vector<std::pair<double *, double *> > tail_init, tail_final;
@@ -600,9 +588,6 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     SMEM_ATTR(k_mg_coarse_solve<true>); SMEM_ATTR(k_mg_coarse_solve<false>);
 #undef SMEM_ATTR3
 #undef SMEM_ATTR
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_staged<FUSED_POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_pcg_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_W * FT_H * (int)sizeof(double)));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -720,29 +705,27 @@ extern "C" int impec_reset_state(impec_ctx *ctx) {
 extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     const std::string k(key ? key : "");
     if (k == "warm_start") { ctx->warm_start = value != 0.0; return IMPEC_OK; }
-    if (k == "mg_fused") { ctx->fused = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_fused") { ctx->fused = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "stagnation_guard") { ctx->stagnation_guard = value != 0.0; return IMPEC_OK; }
-    if (k == "mg_staged") { ctx->staged = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
-    if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_links_fp32") { ctx->links_f32 = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "fast_r0") { ctx->fast_r0 = value != 0.0; return IMPEC_OK; }
     if (k == "sgs_march") { ctx->sgs_march = value != 0.0; return IMPEC_OK; }
     if (k == "halo_overlap") { ctx->overlap = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_y_pairs") { ctx->sweep_y_pairs = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_prefetch") { ctx->pf_sweep = (int)value; return IMPEC_OK; }
     if (k == "l2_prefetch") { ctx->pf_pre = ctx->pf_post = ctx->pf_mv = ctx->pf_sgs = (int)value; return IMPEC_OK; }
-    if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
-    if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
-    if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "matvec_march") { ctx->matvec_march = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_shared") { ctx->sweep_shared = value != 0.0; return IMPEC_OK; }
     if (k == "vel_march") { ctx->vel_march = value != 0.0; ctx->dt_cached = false; return IMPEC_OK; }
     if (k == "build_fused") { ctx->build_fused = value != 0.0; ctx->op_valid = false; return IMPEC_OK; }
-    if (k == "mg_small") { ctx->use_small = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
-    if (k == "mg_persist_tail") { ctx->persist_tail = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
-    if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
-    if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
-    if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
-    if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; ctx->graph_ready = ctx->tail_ready = false; return IMPEC_OK; }
+    if (k == "mg_small") { ctx->use_small = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_graph") { ctx->use_graph = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_w_from") { ctx->P.mg_w_from = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_w_to") { ctx->P.mg_w_to = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
+    if (k == "mg_ncoarse") { ctx->P.mg_ncoarse = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "max_iter") { ctx->P.max_iter = (int)value; return IMPEC_OK; }
     if (k == "profile_dt") { ctx->profile_dt = value; return IMPEC_OK; }
     if (k == "hyper_method") {                   // MUSCL / upwind is a property of the calling solver object, not of the context
@@ -1081,16 +1064,11 @@ static const int kFusedSmem = FT_W * FT_H * (int)sizeof(double);
             else if ((th) == 32) LAUNCH_COOP_SMEM(ctx, (k_mg_fused<MODE, false, 32>), grid, kFusedBlock, smem_, __VA_ARGS__); \
             else LAUNCH_COOP_SMEM(ctx, (k_mg_fused<MODE, false, 16>), grid, kFusedBlock, smem_, __VA_ARGS__); \
         } } while (0)
-static const dim3 kStagedBlock(FT_W / 2, ST_NTY);
-template <int MODE> static dim3 staged_grid(const Grid &g) {
-    return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + StagedGeom<MODE>::TI - 1) / StagedGeom<MODE>::TI));
-}
-static bool use_staged(const impec_ctx *ctx) { return ctx->staged && ctx->links_f32; }
 template <int MODE> static dim3 fused_grid(const Grid &g, int th = FT_H) {
     const int ti = th - 2 * (int)FusedGeom<MODE>::HI;
     return dim3((unsigned)((g.N2 + FT_TJ - 1) / FT_TJ), (unsigned)((g.N1 + ti - 1) / ti));
 }
-static bool use_march(const impec_ctx *ctx, const Level &L) { return ctx->march && L.march_rows > 0 && !use_staged(ctx); }
+static bool use_march(const impec_ctx *ctx, const Level &L) { return ctx->march && L.march_rows > 0; }
 static dim3 march_grid(const Level &L, int own) {
     const int warps = (L.g.N2 + own - 1) / own;
     return dim3((unsigned)((warps + MG_BLOCK / 32 - 1) / (MG_BLOCK / 32)), (unsigned)((L.g.N1 + L.march_rows - 1) / L.march_rows));
@@ -1115,9 +1093,7 @@ static int fused_plain(Cycle &C, int l, const double *f, bool forward, int xhalo
         return IMPEC_OK;
     }
     if (xhalo > 0 && L.dist) TRY(exchange_rows(ctx, L.x, L.g, xhalo));
-    if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PLAIN>, staged_grid<FUSED_PLAIN>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
-                     (const double *)nullptr, (double *)nullptr, (double *)nullptr);
-    else LAUNCH_FUSED(ctx, FUSED_PLAIN, L.th, fused_grid<FUSED_PLAIN>(L.g, L.th), C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
+    LAUNCH_FUSED(ctx, FUSED_PLAIN, L.th, fused_grid<FUSED_PLAIN>(L.g, L.th), C.D[l], f, (const double *)L.x, L.t, forward ? 0 : 1, L.g,
                       (const double *)nullptr, (double *)nullptr, (double *)nullptr);
     std::swap(L.x, L.t);
     return IMPEC_OK;
@@ -1147,9 +1123,7 @@ static int fused_pre(Cycle &C, int l, const double *f) {
         return halo_overlapped(ctx, L.dist, (int)gm.y, L.march_rows, L.g.N1, [&]() { return exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO); }, launch);
     }
     if (L.dist) TRY(exchange_rows(ctx, const_cast<double *>(f), L.g, IMPEC_HALO));
-    if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_PRE>, staged_grid<FUSED_PRE>(L.g), kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
-                     (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
-    else LAUNCH_FUSED(ctx, FUSED_PRE, L.th, fused_grid<FUSED_PRE>(L.g, L.th), C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
+    LAUNCH_FUSED(ctx, FUSED_PRE, L.th, fused_grid<FUSED_PRE>(L.g, L.th), C.D[l], f, (const double *)nullptr, L.x, 0, tr ? Lc.gl : Lc.g,
                       (const double *)nullptr, tr ? Lc.fl : Lc.f, (double *)nullptr);
     return IMPEC_OK;
 }
@@ -1185,10 +1159,8 @@ static int fused_post(Cycle &C, int l, const double *f, double *part, long long 
         return IMPEC_OK;
     }
     if (Lc.dist) TRY(exchange_rows(ctx, Lc.x, Lc.g, 2));
-    const dim3 gr = use_staged(ctx) ? staged_grid<FUSED_POST>(L.g) : fused_grid<FUSED_POST>(L.g, L.th);
-    if (use_staged(ctx)) LAUNCH_COOP_SMEM(ctx, k_mg_staged<FUSED_POST>, gr, kStagedBlock, ST_SMEM_BYTES, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
-                     coarse_x_view(ctx, l), (double *)nullptr, part);
-    else LAUNCH_FUSED(ctx, FUSED_POST, L.th, gr, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
+    const dim3 gr = fused_grid<FUSED_POST>(L.g, L.th);
+    LAUNCH_FUSED(ctx, FUSED_POST, L.th, gr, C.D[l], f, (const double *)L.x, L.t, 1, at_transition(ctx, l) ? Lc.gl : Lc.g,
                       coarse_x_view(ctx, l), (double *)nullptr, part);
     std::swap(L.x, L.t);
     if (nparts) *nparts = (long long)gr.x * gr.y;
@@ -1198,110 +1170,9 @@ static int fused_post(Cycle &C, int l, const double *f, double *part, long long 
 // One multigrid cycle for S x = f from a zero initial guess; the result is left in ctx->L[l].x (the fused path
 // ping-pongs between the level's two buffers).  dot_part/dot_nparts (level 0, fused path): the last kernel also
 // leaves the partial sums of <f,x> in dot_part.
-// ---- persistent tail (kernels_tail.inl): record the launch sequence of mg_cycle_impl for the levels >= l0 as a program
-struct TailRec { TailProgram P; std::vector<std::pair<double *, double *> > xt; int l0; bool ok; };
-static bool small_eligible(const Cycle &C, int l) {
-    const impec_ctx *ctx = C.ctx; const Level &L = ctx->L[l];
-    return ctx->fused && ctx->use_small && l > 0 && l < C.nl - 1 && l > C.w_to && !L.dist && C.nl - l <= SM_MAXLEV &&
-           (long long)L.g.N1 * L.g.N2 <= SM_MAXCELLS && C.D[l].mass == 0.;
-}
-template <int MODE> static void tail_push(Cycle &C, TailRec &R, int op, int l, const double *f, const double *xin, double *x, int c0, const double *ec, double *fc) {
-    if (R.P.nphases >= TAIL_MAXPHASES) { R.ok = false; return; }
-    impec_ctx *ctx = C.ctx; const Level &L = ctx->L[l]; const Level &Lc = ctx->L[l + 1];
-    TailPhase &ph = R.P.ph[R.P.nphases++];
-    const dim3 gr = fused_grid<MODE>(L.g, TAIL_TH);
-    ph.op = op; ph.c0 = c0; ph.nbx = (int)gr.x; ph.nby = (int)gr.y; ph.D = C.D[l]; ph.gc = Lc.g;
-    ph.f = f; ph.xin = xin; ph.ec = ec; ph.x = x; ph.fc = fc; ph.small_idx = 0;
-}
-static void tail_rec(Cycle &C, TailRec &R, int l, const double *f) {
-    impec_ctx *ctx = C.ctx;
-    if (!R.ok) return;
-    if (ctx->L[l].dist) { R.ok = false; return; }
-    if (small_eligible(C, l)) {
-        if (R.P.nphases >= TAIL_MAXPHASES) { R.ok = false; return; }
-        SmallArgs A; A.nl = C.nl - l; A.ncoarse = C.ncoarse; A.xout = R.xt[l - R.l0].first;
-        for (int k = l; k < C.nl; k++) A.D[k - l] = C.D[k];
-        R.P.small[0] = A;                                   // every visit of the bottom uses the same arguments
-        TailPhase &ph = R.P.ph[R.P.nphases++];
-        memset(&ph, 0, sizeof(ph));
-        ph.op = TAIL_SMALL; ph.f = f; ph.small_idx = 0;
-        return;
-    }
-    if (l >= C.nl - 1) { R.ok = false; return; }            // a coarsest level that is not handled by the small kernel
-    Level &Lc = ctx->L[l + 1];
-    double *&X = R.xt[l - R.l0].first, *&T = R.xt[l - R.l0].second;
-    const int gamma = (l >= C.w_from && l <= C.w_to) ? 2 : 1;
-    tail_push<FUSED_PRE>(C, R, TAIL_PRE, l, f, nullptr, X, 0, nullptr, Lc.f);
-    tail_rec(C, R, l + 1, Lc.f);
-    for (int gc = 1; gc < gamma; gc++) {
-        tail_push<FUSED_POST>(C, R, TAIL_POST, l, f, X, T, 1, R.xt[l + 1 - R.l0].first, nullptr); std::swap(X, T);
-        tail_push<FUSED_MID>(C, R, TAIL_MID, l, f, X, T, 0, nullptr, Lc.f); std::swap(X, T);
-        tail_rec(C, R, l + 1, Lc.f);
-    }
-    tail_push<FUSED_POST>(C, R, TAIL_POST, l, f, X, T, 1, R.xt[l + 1 - R.l0].first, nullptr); std::swap(X, T);
-}
-// build (once) and run the persistent tail for the visit of level l; returns IMPEC_OK, or a positive value if the tail
-// cannot run as one persistent launch (the caller falls back to the graph / the launches)
-static int tail_run(Cycle &C, int l, const double *f) {
-    impec_ctx *ctx = C.ctx;
-    const int nl = (int)ctx->L.size();
-    if (!ctx->tail_ready) {
-        ctx->tail_ready = true; ctx->tail_ok = false;
-        if (!ctx->fused_mid || use_staged(ctx) || f != ctx->L[l].f) return 1;
-        TailRec R; memset(&R.P, 0, sizeof(R.P)); R.l0 = l; R.ok = true;
-        for (int k = l; k < nl; k++) R.xt.push_back(std::make_pair(ctx->L[k].x, ctx->L[k].t));
-        tail_rec(C, R, l, f);
-        if (!R.ok || R.P.nphases < 2) return 1;
-        size_t smem = (size_t)FT_W * TAIL_TH * sizeof(double);
-        smem = std::max(smem, small_smem_doubles(R.P.small[0]) * sizeof(double));
-#ifndef IMPEC_EMU
-        int dev = 0, nsm = 0, coop = 0, per_sm = 0;
-        CUDA_TRY(ctx, cudaGetDevice(&dev));
-        CUDA_TRY(ctx, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-        CUDA_TRY(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        if (!coop) return 1;
-        if (ctx->links_f32) { CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                              CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mg_tail<true>, FT_W / 2 * FT_NTY, smem)); }
-        else { CUDA_TRY(ctx, cudaFuncSetAttribute(k_mg_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-               CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mg_tail<false>, FT_W / 2 * FT_NTY, smem)); }
-        if (per_sm < 1) return 1;
-        ctx->tail_grid = nsm;                              // one CTA per SM: all resident, as the grid barrier requires
-#else
-        ctx->tail_grid = 1;                                // the emulator runs blocks one after another: a single CTA walks all tiles
-#endif
-        if (!ctx->tail_prog) { TRY(dev_alloc(ctx, (double **)&ctx->tail_prog, (sizeof(TailProgram) + 7) / 8)); TRY(dev_alloc(ctx, (double **)&ctx->tail_ctr, 1)); TRY(dev_alloc(ctx, &ctx->tail_err, 1)); }
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tail_prog, &R.P, sizeof(TailProgram), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // R.P is on the stack
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->tail_err, 0, sizeof(double), ctx->stream));
-        ctx->tail_xt_final = R.xt; ctx->tail_smem = smem; ctx->tail_phases = R.P.nphases;
-        ctx->tail_ok = true;
-    }
-    if (!ctx->tail_ok) return 1;
-    if (f != ctx->L[l].f) return 1;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->tail_ctr, 0, sizeof(unsigned), ctx->stream));
-#ifndef IMPEC_EMU
-    {
-        const TailProgram *pp = ctx->tail_prog; unsigned *pc = ctx->tail_ctr; double *pe = ctx->tail_err;
-        void *args[3] = {(void *)&pp, (void *)&pc, (void *)&pe};
-        const void *fn = ctx->links_f32 ? (const void *)k_mg_tail<true> : (const void *)k_mg_tail<false>;
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->tail_grid), kFusedBlock, args, ctx->tail_smem, ctx->stream));
-        ctx->launches++;
-    }
-#else
-    if (ctx->links_f32) LAUNCH_COOP_SMEM(ctx, k_mg_tail<true>, dim3(1), kFusedBlock, ctx->tail_smem, (const TailProgram *)ctx->tail_prog, ctx->tail_ctr, ctx->tail_err);
-    else LAUNCH_COOP_SMEM(ctx, k_mg_tail<false>, dim3(1), kFusedBlock, ctx->tail_smem, (const TailProgram *)ctx->tail_prog, ctx->tail_ctr, ctx->tail_err);
-#endif
-    for (int k = l; k < nl; k++) { ctx->L[k].x = ctx->tail_xt_final[k - l].first; ctx->L[k].t = ctx->tail_xt_final[k - l].second; }
-    return IMPEC_OK;
-}
-
 static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, long long *dot_nparts);
 static int mg_cycle(Cycle &C, int l, const double *f, double *dot_part = nullptr, long long *dot_nparts = nullptr) {
     impec_ctx *ctx = C.ctx; (void)ctx;
-    if (l == ctx->tail_level && ctx->persist_tail && ctx->fused && C.nl == (int)ctx->L.size() && C.D[0].mass == 0.) {
-        const int rc = tail_run(C, l, f);
-        if (rc <= 0) { if (dot_nparts) *dot_nparts = 0; return rc; }          // ran (or failed); > 0: not eligible, fall through
-    }
 #ifndef IMPEC_EMU
     // The replicated tail (levels >= tail_level) is the same launch sequence on the same buffers at every visit: it is
     // captured once into a CUDA graph and replayed, which removes the launch gaps of ~100 tiny kernels per visit.
@@ -1390,12 +1261,11 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
         // (the exchanges live in fused_pre / fused_post / fused_plain, which overlap them with the interior row chunks on the marching path)
         const bool dist = L.dist, tr = at_transition(ctx, l);
         TRY(fused_pre(C, l, f));                                      // [f: 3 halo rows] pre-smooth(0) + residual + restrict; writes x on 2 halo rows too
-        if (dist && use_staged(ctx)) TRY(exchange_rows(ctx, L.x, L.g, 2));   // (the staged variant writes its interior only)
         TRY(gather_coarse_rhs(ctx, l));
         TRY(mg_cycle(C, l + 1, Lc.f));
         for (int gc = 1; gc < gamma; gc++) {
             TRY(fused_post(C, l, f, nullptr, nullptr));               // [coarse x: 2 halo rows] prolong + correct + backward sweep
-            if (!dist && ctx->fused_mid && !use_staged(ctx)) {
+            if (!dist && ctx->fused_mid) {
                 // sweep + residual + restriction in one tile kernel (needs 4 halo rows: single-GPU / replicated levels only)
                 LAUNCH_FUSED(ctx, FUSED_MID, L.th, fused_grid<FUSED_MID>(L.g, L.th), C.D[l], f, (const double *)L.x, L.t, 0, Lc.g, (const double *)nullptr, Lc.f, (double *)nullptr);
                 std::swap(L.x, L.t);

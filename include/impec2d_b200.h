@@ -198,12 +198,16 @@ int   impec_last_parabolic_info(const impec_ctx *ctx, impec_solve_info *info); /
 long long impec_overlapped_exchanges(const impec_ctx *ctx);              /* halo exchanges issued concurrently with the interior row chunks of their consumer (multi-GPU) */
 int   impec_reset_state(impec_ctx *ctx);                                 /* produced mass := 0, sweep parity := Y */
 /* options: "warm_start" (x0 = previous p instead of the reference's 0), "stagnation_guard" (stop PCG at the FP64
- * residual floor instead of iterating the recurrence residual down to eps), "mg_fused", "mg_links_fp32", "mg_staged",
+ * residual floor instead of iterating the recurrence residual down to eps), "mg_fused", "mg_links_fp32",
  * "mg_graph", "mg_small", "mg_w_from", "mg_w_to", "mg_ncoarse", "max_iter".  Defaults reproduce the reference's semantics.
  * Kernel-generation switches (results identical, for A/B measurements and tests): "mg_march" (register-march multigrid kernels
  * on the big levels, default 1), "mg_march_variant", "matvec_march" (1), "sweep_shared" (MUSCL with one reconstruction per cell, 1),
- * "mg_fused_mid" (1), "sgs_march" (one-march Crank-Nicolson preconditioner, 1), "mg_persist_tail" (persistent tail kernel, 0).
- * Environment, read at context creation: IMPEC_MARCH_MIN_CELLS, IMPEC_TH32_BELOW, IMPEC_TH16_BELOW, IMPEC_DIST_MIN_CELLS. */
+ * "sweep_y_pairs" (y sweep with column pairs per lane, 1), "mg_fused_mid" (1), "sgs_march" (one-march Crank-Nicolson preconditioner, 1),
+ * "l2_prefetch" / "sweep_prefetch" (rows of L2 software prefetch ahead of the marching kernels, 4 / 4; 0 = off),
+ * "halo_overlap" (multi-GPU: halo exchange concurrent with the interior row chunks of its consumer, 1).
+ * Environment, read at context creation: IMPEC_MARCH_MIN_CELLS, IMPEC_TH32_BELOW, IMPEC_TH16_BELOW, IMPEC_DIST_MIN_CELLS,
+ * IMPEC_L2_PREFETCH ("pre,post,matvec,sgs"), IMPEC_SWEEP_PREFETCH, IMPEC_SWEEP_Y_PAIRS, IMPEC_HALO_OVERLAP, IMPEC_P2P, IMPEC_P2P_HALO,
+ * IMPEC_P2P_GATHER. */
 int   impec_set_option(impec_ctx *ctx, const char *key, double value);
 /* average device time of one named piece of the path ("smooth_sweep", "residual", "vcycle", "sweep_x", ...) over
  * `reps` launches, measured with CUDA events on the context stream */

@@ -374,27 +374,6 @@ def check_march_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
         os.environ.pop("IMPEC_MARCH_MIN_CELLS", None)
 
 
-def check_persistent_tail(emulated, N1=256, N2=384, stype=O.DIAGONAL):
-    """The multigrid tail as ONE persistent launch (kernels_tail.inl: a program of phases interpreted by resident CTAs, grid
-    barriers instead of kernel boundaries) against the same tail issued as separate launches: the phases run the very same
-    tile / small-level bodies in the same order, so the cycle must agree BIT FOR BIT (FP64 and FP32 coefficients), and
-    repeated cycles must be repeatable (stale-L1 / barrier bugs show up as run-to-run differences)."""
-    base, Po, c, q = production_case(N1, N2, stype=stype)
-    Pi = I.default_params(emulated=emulated, **base)
-    r = np.random.default_rng(6).standard_normal(N1 * N2)
-    for f32 in (0, 1):
-        out = []
-        for persist in (0, 1):
-            ctx = I.Context(Pi, emulated=emulated)
-            ctx.set_option("mg_persist_tail", persist); ctx.set_option("mg_links_fp32", f32)      # (off by default: slower on the B200)
-            ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
-            zs = [ctx.vcycle(r) for _ in range(3)]
-            assert np.array_equal(zs[0], zs[1]) and np.array_equal(zs[0], zs[2]), "cycle is not repeatable (race?)"
-            out.append(zs[0])
-            ctx.close()
-        assert np.array_equal(out[0], out[1]), "persistent tail vs launches (fp32 links %d): max diff %g of %g" % (f32, np.abs(out[0] - out[1]).max(), np.abs(out[0]).max())
-
-
 def check_sgs_march(emulated, N1=64, N2=96, stype=O.DIAGONAL):
     """The Crank-Nicolson preconditioner (one symmetric red-black sweep from zero) as ONE march (k_sgs_march) against the
     same sweep issued as memset + forward PLAIN + backward PLAIN: identical arithmetic per cell, so the dispersion half
@@ -497,26 +476,6 @@ def check_dispersion(emulated, N1=32, N2=32, stype=O.PARALLEL, steps=1):
     ctx.close()
 
 
-def check_staged_vs_fused(emulated, N1=256, N2=384, stype=O.DIAGONAL):
-    """The cp.async-staged 32-row tile kernels against the 64-row fused kernels, both on FP32 coefficient copies:
-    same arithmetic per cell, so the cycle must agree bit for bit."""
-    base, Po, c, q = production_case(N1, N2, stype=stype)
-    Pi = I.default_params(emulated=emulated, **base)
-    r = np.random.default_rng(2).standard_normal(N1 * N2)
-    out = []
-    for staged in (0, 1):
-        ctx = I.Context(Pi, emulated=emulated)
-        ctx.set_option("mg_links_fp32", 1); ctx.set_option("mg_staged", staged)
-        ctx.set_option("mg_fused_mid", 0)      # the staged variant has no MID kernel; compare like with like
-        ctx.upload_c(c); ctx.upload_q(q); ctx.fill_boundaries(); ctx.build_operator()
-        z1 = ctx.vcycle(r); z2 = ctx.vcycle(r)
-        assert np.array_equal(z1, z2), "cycle is not repeatable (race?)"
-        out.append(z1)
-        ctx.close()
-    assert np.array_equal(out[0], out[1]), np.abs(out[0] - out[1]).max()
-
-
-# ---------------------------------------------------------------------------------------------------- round 2 additions
 def check_generators(emulated, N=96):
     """impec_synth_state / impec_init_source (the product's input generators used by bench.py) against the oracle's, which are pinned
     to the reference's well model (tests/test_oracle_vs_ref.py): bit for bit, circle and one-cell wells, both grid orientations."""

@@ -45,11 +45,9 @@ def test_elliptic_manufactured_9pt(): pc.check_elliptic_manufactured(True, 20, 3
 def test_fused_vs_unfused_cycle(): pc.check_fused_vs_unfused(True, 256, 384)
 def test_dispersion_parallel(): pc.check_dispersion(True, 32, 32)
 def test_dispersion_diagonal_rect(): pc.check_dispersion(True, 32, 16, stype=O.DIAGONAL)
-def test_staged_vs_fused_cycle(): pc.check_staged_vs_fused(True, 256, 384)
 def test_matvec_march_vs_tiles(): pc.check_matvec_variants(True)
 def test_matvec_march_odd_columns(): pc.check_matvec_variants(True, 20, 31, eps=1e-9)
 def test_march_vs_tile_kernels(): pc.check_march_vs_tiles(True)
-def test_persistent_tail_vs_launches(): pc.check_persistent_tail(True)
 def test_sgs_march_vs_sweeps(): pc.check_sgs_march(True)
 def test_fast_initial_residual(): pc.check_fast_initial_residual(True)
 def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(True, 256, 384)

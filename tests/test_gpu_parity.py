@@ -36,11 +36,9 @@ def test_projection_parallel_to_diagonal(): pc.check_projection(False, N=700)
 def test_checkpoint_restart(tmp_path): pc.check_checkpoint_restart(False, tmp_path, N=256)
 def test_source_step(): pc.check_source_step(False, N=128)
 def test_fused_vs_unfused_cycle(): pc.check_fused_vs_unfused(False, 1024, 1536)
-def test_staged_vs_fused_cycle(): pc.check_staged_vs_fused(False, 1024, 1536)
 def test_matvec_march_vs_tiles(): pc.check_matvec_variants(False, 1152, 2064)
 def test_matvec_march_odd_columns(): pc.check_matvec_variants(False, 20, 31, eps=1e-9)
 def test_march_vs_tile_kernels(): pc.check_march_vs_tiles(False, 1024, 1536)
-def test_persistent_tail_vs_launches(): pc.check_persistent_tail(False, 2048, 3072)
 def test_sgs_march_vs_sweeps(): pc.check_sgs_march(False, 1024, 1536)
 def test_fast_initial_residual(): pc.check_fast_initial_residual(False, 1024, 1536)
 def test_small_vs_tile_kernels(): pc.check_small_vs_tiles(False, 1024, 1536)
