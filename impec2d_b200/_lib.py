@@ -66,7 +66,7 @@ EXPORTS = [
     "impec_max_stable_dt", "impec_source_split", "impec_advect_x", "impec_advect_y", "impec_advect_split", "impec_intercell_flux", "impec_gather_rows",
     "impec_diffusion_split", "impec_transport_step", "impec_impes_step", "impec_diagnostics", "impec_integral_diagnostics", "impec_build_operator",
     "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_overlapped_exchanges", "impec_last_parabolic_info", "impec_reset_state", "impec_set_option",
-    "impec_profile_kernel", "impec_init_source", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
+    "impec_profile_kernel", "impec_init_source", "impec_init_horizontal_front", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
     "impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows", "impec_init_source_rows", "impec_synth_state_rows",
     "impec_comm_backend", "impec_transfer_bytes", "impec_project_dims", "impec_project_to_diagonal", "impec_checkpoint_save", "impec_checkpoint_load",
 ]
@@ -146,6 +146,7 @@ def load(emulated=False):
     L.impec_set_option.argtypes = [vp, C.c_char_p, d]
     L.impec_profile_kernel.argtypes = [vp, C.c_char_p, i, dptr]
     L.impec_init_source.argtypes = [C.POINTER(Params), d, d, i, vp]
+    L.impec_init_horizontal_front.argtypes = [C.POINTER(Params), d, d, i, d, d, d, d, d, vp]
     L.impec_synth_state.argtypes = [C.POINTER(Params), C.c_ulonglong, vp]
     L.impec_ctx_set_comm_callbacks.argtypes = [vp, C.POINTER(CommCallbacks)]
     L.impec_local_rows.argtypes = [vp, C.POINTER(i), C.POINTER(i)]

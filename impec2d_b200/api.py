@@ -205,6 +205,15 @@ class Context:
         return ms.value
 
 
+def init_horizontal_front(params, I=1.0, well_width=0.05, mode=2, q_freq=1.0, q_high_multiple=1.0, tstart=0.0, tfinal=1.0, t=0.0, emulated=False):
+    """InitHorizontalFront (host): q[N1*N2] of source_type "horizontal"; mode 0 pulsing, 1 linear, 2 constant."""
+    q = np.zeros(params.N1 * params.N2)
+    rc = _lib.load(emulated).impec_init_horizontal_front(C.byref(params), I, well_width, mode, q_freq, q_high_multiple, tstart, tfinal, t, _ptr(q))
+    if rc != 0:
+        raise ImpecError("impec_init_horizontal_front failed (%d): the injection layer must be 1 .. N1/2 rows wide" % rc)
+    return q
+
+
 def init_source(params, I=1.0, well_rc=0.05, well_profile=0, emulated=False):
     """Impec2DSolver::InitializeSource (host): returns q[N1*N2]."""
     q = np.zeros(params.N1 * params.N2)

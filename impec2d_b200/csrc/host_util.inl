@@ -37,7 +37,7 @@ extern "C" int impec_init_source(const impec_params *P, double I, double well_rc
 }
 extern "C" int impec_init_source_rows(const impec_params *P, double I, double well_rc, int well_profile, int row0, int nrows, double *q) {
     if (!P || !q || row0 < 0 || row0 + nrows > P->N1) return IMPEC_ERR_ARG;
-    if (P->stype == IMPEC_HORIZONTAL) return IMPEC_ERR_UNSUPPORTED;
+    if (P->stype == IMPEC_HORIZONTAL) return IMPEC_ERR_UNSUPPORTED;           // see impec_init_horizontal_front
     const int N1 = P->N1, N2 = P->N2;
     const double dx = (P->x_ub - P->x_lb) / N1, dy = (P->y_ub - P->y_lb) / N2;
     const double r = well_rc * (P->x_ub - P->x_lb);
@@ -60,6 +60,25 @@ extern "C" int impec_init_source_rows(const impec_params *P, double I, double we
             q[(size_t)il * N2 + j] = par ? ((a + b) - qI(i, N2 - 1 - j)) - qI(N1 - 1 - i, j) : a - b;
         }
     });
+    return IMPEC_OK;
+}
+
+// InitHorizontalFront (src/Util.cpp:607-639): a layer of round(well_width (x_ub - x_lb) / dx) injecting rows at i = 0.. and as many
+// producing rows at the far end; mode 0 pulsing (rate * q_high_multiple in the second half of every period 1/q_freq), 1 linear ramp from
+// the base rate at tstart to q_high_multiple times it at tfinal, 2 constant.  Returns IMPEC_ERR_ARG when the layer is narrower than a cell.
+extern "C" int impec_init_horizontal_front(const impec_params *P, double I, double well_width, int mode, double q_freq, double q_high_multiple,
+                                           double tstart, double tfinal, double t, double *q) {
+    if (!P || !q) return IMPEC_ERR_ARG;
+    const int N1 = P->N1, N2 = P->N2;
+    const double dx = (P->x_ub - P->x_lb) / N1, dy = (P->y_ub - P->y_lb) / N2;
+    const int width = (int)round(well_width * (P->x_ub - P->x_lb) / dx);
+    if (width < 1 || 2 * width > N1) return IMPEC_ERR_ARG;
+    double val = I / (N2 * dx * dy * width);
+    if (mode == 0) { const double tau = 1. / q_freq, x = fmod(t, tau); if (x > tau / 2.) val *= q_high_multiple; }
+    else if (mode == 1) { const double vl = val, vh = val * q_high_multiple; val = vl + (t - tstart) * (vh - vl) / (tfinal - tstart); }
+    const size_t M = (size_t)N1 * N2;
+    for (size_t k = 0; k < M; k++) q[k] = 0.;
+    for (size_t k = 0; k < (size_t)N2 * width; k++) { q[k] = val; q[M - 1 - k] = -val; }
     return IMPEC_OK;
 }
 

@@ -30,7 +30,9 @@ struct Level {
     double *AW = nullptr, *AS = nullptr, *AV = nullptr, *DINV = nullptr;
     float *AWf = nullptr, *ASf = nullptr, *AVf = nullptr, *DINVf = nullptr;      // FP32 copies for the cycle kernels
     double *x = nullptr, *f = nullptr, *t = nullptr, *r = nullptr;
-    long long pin = -1, sig_idx = -1;
+    long long pin = -1, pin_end = -1;       // Dirichlet cells of the fine level: index range [pin, pin_end) (one cell, or one row for source_type horizontal)
+    long long sig_idx = -1, sig_end = -1;   // coarse levels: cells carrying the pins' diagonal shift
+    long long sig_off = 0;                  // offset of this level's shifts in impec_ctx::sigma_dev
     bool dist = false;           // rows of this level are slab-distributed over the ranks
     int th = 64;                 // tile height of the fused kernels on this level (64 / 32 / 16)
     int march_rows = 0;          // > 0: the level runs the marching kernels (kernels_march.inl) with chunks of this many rows
@@ -51,7 +53,8 @@ struct impec_ctx {
     double *MU = nullptr, *KV11 = nullptr, *KV22 = nullptr;
     double *r = nullptr, *z = nullptr, *d = nullptr, *s = nullptr, *rhs = nullptr, *t0 = nullptr, *d2buf = nullptr;
     std::vector<Level> L;
-    double *sigma_dev = nullptr;                    // per-level diagonal shift of the pin
+    double *sigma_dev = nullptr;                    // diagonal shifts of the pins on the coarse levels (Level::sig_off)
+    long long sigma_len = 0;
     // reductions
     double *part = nullptr; long long part_cap = 0;
     double *scal = nullptr;                         // device scalars
@@ -200,6 +203,25 @@ __global__ void k_pin_sigma(Grid g, const double *__restrict__ AW, const double 
     double sg = 0.125 * tot;
     sigma[0] = 0.;
     for (int l = 1; l < nlev; l++) { sigma[l] = sg; sg *= 0.25; }
+}
+// The same for a pinned ROW pi (source_type horizontal): coarse column J of level 1 holds the pinned cells (pi, 2J), (pi, 2J+1); their free
+// siblings are the two cells of the other row of the 2 x 2 block: one face link and one vertex link each.
+__global__ void k_pin_sigma_row(Grid g, const double *__restrict__ AW, const double *__restrict__ AV, int pi, int n, double *__restrict__ sigma1) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    if (J >= n) return;
+    const int iv = (pi & 1) ? pi : pi + 1;                  // row index of the links between row pi and its sibling row
+    const double ta = AW[gidx(g, iv, 2 * J)] + AV[gidx(g, iv, 2 * J + 1)];
+    const double tb = AV[gidx(g, iv, 2 * J + 1)] + AW[gidx(g, iv, 2 * J + 1)];
+    sigma1[J] = 0.125 * ta + 0.125 * tb;
+}
+__global__ void k_sigma_coarsen(int n, const double *__restrict__ fine, double *__restrict__ coarse) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    if (J < n) coarse[J] = 0.25 * (fine[2 * J] + fine[2 * J + 1]);
+}
+// Dirichlet values into x: value for a single cell, or scale * q for a row (its own equation kappa/dA p = -q)
+__global__ void k_set_pins(double *__restrict__ x, const double *__restrict__ q, long long pin, long long pin_end, double value, double scale) {
+    const long long k = pin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < pin_end) x[k] = scale != 0. ? scale * q[k] : value;
 }
 __global__ void k_copy_interior(Grid g, const double *__restrict__ src, double *__restrict__ dst) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -559,7 +581,6 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
         if (P->dim_splitting != IMPEC_SYMMETRIC_PARALLEL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "multi-GPU transport supports dimensional_splitting = parallel only");
         if (P->N1 % (2 * nranks) != 0 || P->N1 / nranks < 8) return fail(ctx, IMPEC_ERR_ARG, "x_cells = %d cannot be cut into %d slabs of an even number (>= 8) of rows", P->N1, nranks);
     }
-    if (P->stype == IMPEC_HORIZONTAL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "source_type horizontal is outside the accelerated path");
     if (P->diffusion && P->alpha_l != P->alpha_t) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t gives a non-symmetric CN operator; not supported");
     { const char *e = getenv("IMPEC_MARCH_VARIANT"); if (e) ctx->march_variant = atoi(e); }
     CUDA_TRY(ctx, cudaSetDevice(device));
@@ -662,11 +683,25 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     }
     for (int l = std::max(ctx->Ld, 1); l < nl; l++)
         if ((double)ctx->L[l].g.N1 * ctx->L[l].g.N2 <= 2097152.0 && l < nl - 1) { ctx->tail_level = l; break; }
-    // pinned cell (1,1): src/MGSolver.cpp:109-118
-    int pi = 1, pj = 1;
-    ctx->L[0].pin = (rank == 0) ? (long long)gidx(ctx->g, pi, pj) : -1;
-    for (int l = 1; l < nl; l++) { pi >>= 1; pj >>= 1; ctx->L[l].sig_idx = (rank == 0 || !ctx->L[l].dist) ? (long long)gidx(ctx->L[l].g, pi, pj) : -1; }
-    TRY(dev_alloc(ctx, &ctx->sigma_dev, (size_t)nl + 1));
+    // Dirichlet cells of the pressure problem (src/MGSolver.cpp:109-140): cell (1,1), or the whole row i = 1 for source_type horizontal.
+    // On the coarse levels they become a diagonal shift of the coarse cells that contain them (k_pin_sigma / k_pin_sigma_row).
+    {
+        const bool row = P->stype == IMPEC_HORIZONTAL;
+        int pi = 1, pj = row ? 0 : 1;
+        ctx->L[0].pin = (rank == 0) ? (long long)gidx(ctx->g, pi, pj) : -1;
+        ctx->L[0].pin_end = (rank == 0) ? ctx->L[0].pin + (row ? P->N2 : 1) : -1;
+        long long off = 1;                                            // (slot 0: level 0 has no shift)
+        for (int l = 1; l < nl; l++) {
+            pi >>= 1; pj >>= 1;
+            Level &L = ctx->L[l];
+            const int cnt = row ? L.g.N2 : 1;
+            L.sig_idx = (rank == 0 || !L.dist) ? (long long)gidx(L.g, pi, pj) : -1;
+            L.sig_end = L.sig_idx >= 0 ? L.sig_idx + cnt : -1;
+            L.sig_off = off; off += cnt;
+        }
+        ctx->sigma_len = off;
+        TRY(dev_alloc(ctx, &ctx->sigma_dev, (size_t)off + 1));
+    }
     // reductions
     const dim3 gg = grid2d(P->N2 + 2, ctx->g.N1 + 2);
     ctx->part_cap = (long long)gg.x * gg.y;
@@ -918,6 +953,12 @@ extern "C" void *impec_field_dev(impec_ctx *ctx, const char *name) {
     if (k == "p") return ctx->p; if (k == "q") return ctx->q;
     if (k == "u") { ctx->dt_cached = false; return ctx->u; }
     if (k == "v") { ctx->dt_cached = false; return ctx->v; }
+    // (diagnostic views for the tests: the pins' coarse-level shifts and the level arrays "AW0", "AV1", "DINV2", ...)
+    if (k == "sigma") return ctx->sigma_dev;
+    if (k.size() >= 3 && isdigit((unsigned char)k.back())) {
+        const size_t l = (size_t)(k.back() - '0'); const std::string a = k.substr(0, k.size() - 1);
+        if (l < ctx->L.size()) { Level &L = ctx->L[l]; if (a == "AW") return L.AW; if (a == "AS") return L.AS; if (a == "AV") return L.AV; if (a == "DINV") return L.DINV; }
+    }
     return nullptr;
 }
 
@@ -939,7 +980,7 @@ static LevelDev level_dev(const impec_ctx *ctx, int l, double mass) {
     LevelDev D;
     D.g = L.g; D.AW = L.AW; D.AS = L.AS; D.AV = L.AV; D.DINV = L.DINV; D.mass = mass;
     D.AWf = L.AWf; D.ASf = L.ASf; D.AVf = L.AVf; D.DINVf = L.DINVf;
-    D.pin = L.pin; D.sig_idx = L.sig_idx; D.sig = ctx->sigma_dev + l;
+    D.pin = L.pin; D.pin_end = L.pin_end; D.sig_idx = L.sig_idx; D.sig_end = L.sig_end; D.sig = ctx->sigma_dev + L.sig_off;
     D.cy0 = 0; D.cys = 1; D.pfd = 0;
     return D;
 }
@@ -984,7 +1025,7 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
         // one march over c: links, inverse diagonal and FP32 copies of level 0 (MU / KV are not materialised: mob_valid stays false)
         BuildArgs A;
         A.g = g; A.c = ctx->c; A.AW = L0.AW; A.AS = L0.AS; A.AV = L0.AV; A.DINV = L0.DINV; A.AWf = L0.AWf; A.ASf = L0.ASf; A.AVf = L0.AVf; A.DINVf = L0.DINVf;
-        A.pin = L0.pin; A.P = ctx->D;
+        A.pin = L0.pin; A.pin_end = L0.pin_end; A.P = ctx->D;
         const int warps = (g.N2 + BL_OWN - 1) / BL_OWN;
         const dim3 gb((unsigned)((warps + BL_BLOCK / 32 - 1) / (BL_BLOCK / 32)), (unsigned)((g.N1 + BL_ROWS - 1) / BL_ROWS));
         if (need_dinv64(ctx)) LAUNCH_COOP(ctx, k_build_links_march<true>, gb, dim3(BL_BLOCK), A, BL_ROWS);
@@ -994,6 +1035,13 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
         TRY(build_mobility(ctx));
         if (ctx->P.is_test) LAUNCH(ctx, k_links<true>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
         else LAUNCH(ctx, k_links<false>, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, ctx->MU, ctx->KV11, ctx->KV22, L0.AW, L0.AS, L0.AV, ctx->D);
+    }
+    if (L0.pin_end - L0.pin > 1) {
+        // A pinned ROW: the links between two Dirichlet cells carry nothing on the fine level (both ends are fixed) and must not be averaged
+        // into the coarse operators either (the oracle's mg_build takes a fixed cell's links from its free neighbours' rows: 0 between two
+        // fixed cells).  AS(1, j) couples (1, j-1) and (1, j).
+        CUDA_TRY(ctx, cudaMemsetAsync(L0.AS + L0.pin, 0, (size_t)(L0.pin_end - L0.pin) * sizeof(double), ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(L0.ASf + L0.pin, 0, (size_t)(L0.pin_end - L0.pin) * sizeof(float), ctx->stream));
     }
     if (L0.dist) { TRY(exchange_rows(ctx, L0.AW, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AS, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AV, L0.g, IMPEC_GH)); }
     for (size_t l = 1; l < ctx->L.size(); l++) {
@@ -1009,8 +1057,17 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
         LAUNCH(ctx, k_coarsen_links, grid2d(C.g.N2 + 1, C.g.N1 + 1), kBlock, F.g, F.AW, F.AS, F.AV, C.g, C.AW, C.AS, C.AV);
         if (C.dist) { TRY(exchange_rows(ctx, C.AW, C.g, IMPEC_GH)); TRY(exchange_rows(ctx, C.AS, C.g, IMPEC_GH)); TRY(exchange_rows(ctx, C.AV, C.g, IMPEC_GH)); }
     }
-    if (ctx->rank == 0) LAUNCH(ctx, k_pin_sigma, dim3(1), dim3(1), g, L0.AW, L0.AS, L0.AV, 1, 1, (int)ctx->L.size(), ctx->sigma_dev);
-    TRY(comm_bcast(ctx, ctx->sigma_dev, (long long)ctx->L.size(), 0));
+    if (ctx->rank == 0) {
+        if (ctx->P.stype == IMPEC_HORIZONTAL) {
+            // a pinned ROW: one shift per coarse column, level by level (same rule as the oracle's mg_build)
+            for (size_t l = 1; l < ctx->L.size(); l++) {
+                const int n = ctx->L[l].g.N2;
+                if (l == 1) LAUNCH(ctx, k_pin_sigma_row, dim3((unsigned)((n + 255) / 256)), dim3(256), g, (const double *)L0.AW, (const double *)L0.AV, 1, n, ctx->sigma_dev + ctx->L[1].sig_off);
+                else LAUNCH(ctx, k_sigma_coarsen, dim3((unsigned)((n + 255) / 256)), dim3(256), n, (const double *)(ctx->sigma_dev + ctx->L[l - 1].sig_off), ctx->sigma_dev + ctx->L[l].sig_off);
+            }
+        } else LAUNCH(ctx, k_pin_sigma, dim3(1), dim3(1), g, L0.AW, L0.AS, L0.AV, 1, 1, (int)ctx->L.size(), ctx->sigma_dev);
+    }
+    TRY(comm_bcast(ctx, ctx->sigma_dev, ctx->sigma_len, 0));
     for (size_t l = 0; l < ctx->L.size(); l++) {
         Level &L = ctx->L[l];
         if (l == 0 && fused_build) {
@@ -1025,7 +1082,7 @@ extern "C" int impec_build_operator(impec_ctx *ctx) {
             }
             continue;
         }
-        TRY(finish_level(ctx, (int)l, level_dev(ctx, (int)l, 0.0), (const double *)(ctx->sigma_dev + l)));
+        TRY(finish_level(ctx, (int)l, level_dev(ctx, (int)l, 0.0), (const double *)(ctx->sigma_dev + L.sig_off)));
     }
     ctx->op_valid = true;
     return IMPEC_OK;
@@ -1287,7 +1344,7 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
         LAUNCH(ctx, k_residual, grid2d(L.g.N2, L.g.N1), kBlock, C.D[l], f, x, L.r);
         LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L.g, L.r, Lc.g, Lc.f);
         TRY(mg_cycle(C, l + 1, Lc.f));
-        LAUNCH(ctx, k_prolong_add, grid2d(L.g.N2, L.g.N1), kBlock, Lc.g, Lc.x, L.g, x, L.pin);
+        LAUNCH(ctx, k_prolong_add, grid2d(L.g.N2, L.g.N1), kBlock, Lc.g, Lc.x, L.g, x, L.pin, L.pin_end);
         if (gc < gamma - 1) { TRY(smooth(C, l, f, x, false, false)); TRY(smooth(C, l, f, x, true, false)); }
     }
     TRY(smooth(C, l, f, x, false, false));
@@ -1297,7 +1354,7 @@ static int mg_cycle_impl(Cycle &C, int l, const double *f, double *dot_part, lon
 static int make_cycle(impec_ctx *ctx, Cycle &C, double mass, int nlevels_used) {
     C.ctx = ctx;
     C.D.clear();
-    for (size_t l = 0; l < ctx->L.size(); l++) { LevelDev D = level_dev(ctx, (int)l, mass); if (mass != 0.) { D.pin = -1; D.sig_idx = -1; } C.D.push_back(D); }
+    for (size_t l = 0; l < ctx->L.size(); l++) { LevelDev D = level_dev(ctx, (int)l, mass); if (mass != 0.) { D.pin = D.pin_end = -1; D.sig_idx = D.sig_end = -1; } C.D.push_back(D); }
     C.ncoarse = ctx->P.mg_ncoarse > 0 ? ctx->P.mg_ncoarse : 8;
     C.w_from = ctx->P.mg_w_from; C.w_to = ctx->P.mg_w_to;
     C.nl = nlevels_used > 0 ? nlevels_used : (int)ctx->L.size();
@@ -1349,7 +1406,9 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
     const long long nparts = (long long)gr.x * gr.y;
     const LevelDev &A = C.D[0];
     const dim3 gres = grid2d(g.N2, g.N1 + 2);                    // k_residual also fills one halo row per neighbouring slab
-    if (x0_pin_only && ctx->fast_r0) {
+    // (a pinned row -- source_type horizontal -- couples into a whole row of neighbours: full residual pass; the choice must be the same on
+    //  every rank, so it keys on the configuration, not on this rank's share of the pins)
+    if (x0_pin_only && ctx->fast_r0 && ctx->P.stype != IMPEC_HORIZONTAL) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->r, rhs, grid_elems(g) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         if (A.pin >= 0) LAUNCH(ctx, k_residual_pin_fix, dim3(1), dim3(32), A, rhs, (const double *)x, ctx->r);
     } else {
@@ -1471,15 +1530,16 @@ extern "C" int impec_pressure_solve(impec_ctx *ctx, double eps, impec_solve_info
         kappa = -dA * q_test_host(ctx->P, x, y) / (cos(x) * cos(y));
     }
     const double p_pin = -ctx->q_pin / (kappa / dA);
+    const double pin_scale = ctx->P.stype == IMPEC_HORIZONTAL ? -dA : 0.;        // a pinned row: p(1,j) = -q(1,j) dA  (kappa = 1)
     double *x = ctx->p;
     if (ctx->warm_start) {
         // keep the previous pressure as initial guess (not the reference's behaviour: x0 = 0, MGSolver.cpp:577)
         LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->p, ctx->d);
-        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
+        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, A.pin_end, p_pin, pin_scale, ctx->part);
         LAUNCH(ctx, k_copy_interior, gr, kBlock, g, ctx->d, x);
-        if (A.pin >= 0) LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), x + A.pin, p_pin);      // only the rank that owns cell (1,1)
+        if (A.pin >= 0) LAUNCH(ctx, k_set_pins, dim3((unsigned)((A.pin_end - A.pin + 255) / 256)), dim3(256), x, (const double *)ctx->q, A.pin, A.pin_end, p_pin, pin_scale);      // only the rank that owns the pinned cells
     } else {
-        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, p_pin, ctx->part);
+        LAUNCH_COOP(ctx, k_setup_rhs, gr, kBlock, g, ctx->q, ctx->rhs, x, A.pin, A.pin_end, p_pin, pin_scale, ctx->part);
     }
     TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
     return pcg_solve(ctx, C, ctx->rhs, x, eps, info, !ctx->warm_start);
@@ -1693,7 +1753,11 @@ extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info
     LAUNCH(ctx, k_disp_links, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, (const double *)ctx->u, (const double *)ctx->v, dt, ctx->D, L0.AW, L0.AS, L0.AV);
     if (L0.dist) { TRY(exchange_rows(ctx, L0.AW, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AS, L0.g, IMPEC_GH)); TRY(exchange_rows(ctx, L0.AV, L0.g, IMPEC_GH)); }
     LevelDev A = level_dev(ctx, 0, 1.0);
-    A.pin = -1; A.sig_idx = -1;
+    A.pin = A.pin_end = -1; A.sig_idx = A.sig_end = -1;
+    if (ctx->P.stype == IMPEC_HORIZONTAL && g.wall_hi) {
+        // Dirichlet row i = N1-2 of the Crank-Nicolson problem (src/MGSolver.cpp:130-139, 1292-1315): c = 0 there (rhs zeroed, :1357-1364)
+        A.pin = (long long)gidx(g, g.N1 - 2, 0); A.pin_end = A.pin + g.N2;
+    }
     TRY(finish_level(ctx, 0, A, nullptr));
     Cycle C; C.ctx = ctx; C.D.assign(1, A); C.ncoarse = 1; C.w_from = 1; C.w_to = 0; C.nl = 1;
     double *x = ctx->ta;
@@ -1920,7 +1984,7 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "smooth_sweep_zero") return smooth(C, 0, ctx->r, L0.x, true, true);
         if (k == "residual") { LAUNCH(ctx, k_residual, gr, kBlock, C.D[0], ctx->r, (const double *)L0.x, L0.r); return IMPEC_OK; }
         if (k == "restrict") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_restrict, grid2d(Lc.g.N2, Lc.g.N1), kBlock, L0.g, L0.r, Lc.g, Lc.f); return IMPEC_OK; }
-        if (k == "prolong_add") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_prolong_add, gr, kBlock, Lc.g, Lc.x, L0.g, L0.x, L0.pin); return IMPEC_OK; }
+        if (k == "prolong_add") { Level &Lc = ctx->L[1]; LAUNCH(ctx, k_prolong_add, gr, kBlock, Lc.g, Lc.x, L0.g, L0.x, L0.pin, L0.pin_end); return IMPEC_OK; }
         if (k == "pcg_matvec" && ctx->matvec_march) { LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, matvec_march_grid(g), dim3(MV_BLOCK), chunked(C.D[0], 0, 1, ctx->pf_mv), (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part, matvec_march_rows(g)); return IMPEC_OK; }
         if (k == "pcg_matvec") { LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, fused_grid<FUSED_PLAIN>(g), kFusedBlock, kFusedSmem, C.D[0], (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part); return IMPEC_OK; }
         if (k == "matvec_dot") { LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, C.D[0], ctx->d, ctx->s, ctx->part); return IMPEC_OK; }

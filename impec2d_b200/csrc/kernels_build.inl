@@ -21,7 +21,7 @@ struct BuildArgs {
     const double *c;
     double *AW, *AS, *AV, *DINV;
     float *AWf, *ASf, *AVf, *DINVf;
-    long long pin;
+    long long pin, pin_end;
     DevParams P;
 };
 
@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(BL_BLOCK) k_build_links_march(BuildArgs A, int
                 const long long k = kb + (long long)i * ld;
                 const double da = (((aw1a + aw0a) + (asa + asb)) + ((av1a + av0a) + (av1b + av0b)));
                 const double db = (((aw1b + aw0b) + (asb + asR)) + ((av1b + av0b) + (av1R + av0R)));
-                const double dia = (k == A.pin) ? 0. : 1. / da;
-                const double dib = (jb < g.N2) ? ((k + 1 == A.pin) ? 0. : 1. / db) : 0.;
+                const double dia = (k >= A.pin && k < A.pin_end) ? 0. : 1. / da;
+                const double dib = (jb < g.N2) ? ((k + 1 >= A.pin && k + 1 < A.pin_end) ? 0. : 1. / db) : 0.;
                 st2(A.AS + k, asa, asb); st2f(A.ASf + k, (float)asa, (float)asb);
                 st2f(A.DINVf + k, (float)dia, (float)dib);
                 if (W64) st2(A.DINV + k, dia, dib);
@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(256) k_level_finish(LevelDev L, const double *
     if (i >= 0 && i < L.g.N1 && j >= 0 && j < L.g.N2) {
         const int ld = L.g.ld;
         double d = L.mass + (((aw + L.AW[k + ld]) + (as + L.AS[k + 1])) + ((av + L.AV[k + ld]) + (L.AV[k + 1] + L.AV[k + ld + 1])));
-        if ((long long)k == L.sig_idx && sigma) d += sigma[0];
-        const double di = ((long long)k == L.pin) ? 0. : 1. / d;
+        if (has_sig(L, (long long)k) && sigma) d += sigma[(long long)k - L.sig_idx];
+        const double di = is_pin(L, (long long)k) ? 0. : 1. / d;
         if (W64) DINV[k] = di;
         DINVf[k] = (float)di;
     } else

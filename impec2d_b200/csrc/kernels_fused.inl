@@ -91,7 +91,7 @@ template <class CF>
 IMPEC_D double tile_diag(const CF &A, const LevelDev &L, int ld, size_t k) {
     double d = L.mass + ((((double)A.AW[k] + (double)A.AW[k + ld]) + ((double)A.AS[k] + (double)A.AS[k + 1])) +
                          (((double)A.AV[k] + (double)A.AV[k + ld]) + ((double)A.AV[k + 1] + (double)A.AV[k + ld + 1])));
-    if ((long long)k == L.sig_idx) d += L.sig[0];
+    if (has_sig(L, (long long)k)) d += L.sig[(long long)k - L.sig_idx];
     return d;
 }
 
@@ -142,8 +142,8 @@ IMPEC_D void fused_body(const LevelDev &L, const double *f, const double *xin, d
                 const double pp = 0.75 * ldv<CG>(e0 + Jp) + 0.25 * ldv<CG>(e1 + Jp);
                 if (!EDGE) { a += 0.75 * pc + 0.25 * pm; b += 0.75 * pc + 0.25 * pp; }
                 else {
-                    if (jg >= 0 && jg < g.N2 && (long long)k != L.pin) a += 0.75 * pc + 0.25 * pm;
-                    if (jg + 1 >= 0 && jg + 1 < g.N2 && (long long)(k + 1) != L.pin) b += 0.75 * pc + 0.25 * pp;
+                    if (jg >= 0 && jg < g.N2 && !is_pin(L, (long long)k)) a += 0.75 * pc + 0.25 * pm;
+                    if (jg + 1 >= 0 && jg + 1 < g.N2 && !is_pin(L, (long long)(k + 1))) b += 0.75 * pc + 0.25 * pp;
                 }
             }
         }
@@ -228,7 +228,7 @@ IMPEC_D void fused_body(const LevelDev &L, const double *f, const double *xin, d
 #pragma unroll
                 for (int off = 0; off < 2; off++) {
                     const int jc = jl + off;
-                    if (jc >= 3 && jc < FT_W - 3 && (!EDGE || (jg + off >= 0 && jg + off < g.N2 && (long long)(k + off) != L.pin)))
+                    if (jc >= 3 && jc < FT_W - 3 && (!EDGE || (jg + off >= 0 && jg + off < g.N2 && !is_pin(L, (long long)(k + off)))))
                         v[off] = ldv<CG>(f + k + off) - (tile_diag(A, L, ld, k + off) * X[r * FT_W + (off << 6) + tx] - tile_offsum(A, ld, X, r, tx, off, k + off));
                 }
             }
@@ -243,9 +243,9 @@ IMPEC_D void fused_body(const LevelDev &L, const double *f, const double *xin, d
             if (r >= 2 && r < TH - 2 && (!EDGE || (ig >= g.rlo && ig < g.rhi))) {
                 const size_t k = (size_t)(kbase + (long long)n * FT_NTY * ld);
                 const int ja = jl + off0, jb = jl + 1 - off0;
-                if (ja >= 2 && ja < FT_W - 2 && (!EDGE || (jg + off0 >= 0 && jg + off0 < g.N2 && (long long)(k + off0) != L.pin)))
+                if (ja >= 2 && ja < FT_W - 2 && (!EDGE || (jg + off0 >= 0 && jg + off0 < g.N2 && !is_pin(L, (long long)(k + off0)))))
                     v0 = tile_offsum(A, ld, X, r, tx, off0, k + off0);
-                if (jb >= 2 && jb < FT_W - 2 && (!EDGE || (jg + 1 - off0 >= 0 && jg + 1 - off0 < g.N2 && (long long)(k + 1 - off0) != L.pin)))
+                if (jb >= 2 && jb < FT_W - 2 && (!EDGE || (jg + 1 - off0 >= 0 && jg + 1 - off0 < g.N2 && !is_pin(L, (long long)(k + 1 - off0)))))
                     v1 = tile_diagsum(A, ld, X, r, tx, 1 - off0, k + 1 - off0);
             }
             ra[n] = off0 == 0 ? v0 : v1;                                 // even-column cell
@@ -292,9 +292,9 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY, (TH == 64 ? 2 : (TH == 32 ?
     const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ, i0 = (int)blockIdx.y * TI - HI;
     // tile (halo included, plus the one-cell reach of the link arrays) strictly inside the domain and free of the pin?
     bool edge = i0 < L.g.rlo || j0 < 0 || i0 + TH >= L.g.rhi || j0 + FT_W >= L.g.N2;
-    if (L.pin >= 0) {
-        const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
-        edge = edge || (pi >= i0 && pi < i0 + TH && pj >= j0 && pj < j0 + FT_W);
+    if (L.pin >= 0) {                                   // the pinned cells are one cell or (part of) one row
+        const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ, pje = pj + (int)(L.pin_end - L.pin);
+        edge = edge || (pi >= i0 && pi < i0 + TH && pje > j0 && pj < j0 + FT_W);
     }
     if (edge) fused_body<MODE, true, F32, TH>(L, f, xin, x, c0, gc, ec, fc, part, X, 1, (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x);
     else fused_body<MODE, false, F32, TH>(L, f, xin, x, c0, gc, ec, fc, part, X, 1, (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x);
@@ -350,9 +350,9 @@ IMPEC_D void pcg_matvec_body_rw(const LevelDev &L, const double *__restrict__ sc
         const double da = X[r * FT_W + tx], db = X[r * FT_W + 64 + tx];
         const bool two = !EDGE || jg + 1 < g.N2;
         const Coef<false> A(L);
-        double sa = ((long long)k == L.pin) ? 0. : link_diag(L, k) * da - tile_offsum(A, ld, X, r, tx, 0, k);
+        double sa = is_pin(L, (long long)k) ? 0. : link_diag(L, k) * da - tile_offsum(A, ld, X, r, tx, 0, k);
         double sb = 0.;
-        if (two) sb = ((long long)(k + 1) == L.pin) ? 0. : link_diag(L, k + 1) * db - tile_offsum(A, ld, X, r, tx, 1, k + 1);
+        if (two) sb = is_pin(L, (long long)(k + 1)) ? 0. : link_diag(L, k + 1) * db - tile_offsum(A, ld, X, r, tx, 1, k + 1);
         if (two) { st2(d + k, da, db); st2(s + k, sa, sb); } else { d[k] = da; s[k] = sa; }
         dotv = fma(sa, da, dotv);
         if (two) dotv = fma(sb, db, dotv);
@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(FT_W / 2 * FT_NTY, 2) k_pcg_matvec(LevelDev L,
     const int j0 = (int)blockIdx.x * FT_TJ - FT_HJ, i0 = (int)blockIdx.y * TI - HI;
     bool edge = i0 < L.g.rlo || j0 < 0 || i0 + FT_H >= L.g.rhi || j0 + FT_W >= L.g.N2;
     if (L.pin >= 0) {
-        const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ;
-        edge = edge || (pi >= i0 && pi < i0 + FT_H && pj >= j0 && pj < j0 + FT_W);
+        const int pi = (int)(L.pin / L.g.ld) - IMPEC_GH, pj = (int)(L.pin % L.g.ld) - IMPEC_PJ, pje = pj + (int)(L.pin_end - L.pin);
+        edge = edge || (pi >= i0 && pi < i0 + FT_H && pje > j0 && pj < j0 + FT_W);
     }
     if (edge) pcg_matvec_body_rw<FIRST, true>(L, scal, z, din, dout, s, part, X);
     else pcg_matvec_body_rw<FIRST, false>(L, scal, z, din, dout, s, part, X);
@@ -452,16 +452,16 @@ __global__ void __launch_bounds__(MV_BLOCK, 3) k_pcg_matvec_march(LevelDev L, co
                 const size_t k = kb + (size_t)(row - ia) * ld;           // cell (row-1, jA)
                 double dA = L.mass + (((awc.x + R.aw.x) + (asc.x + asc.y)) + ((avc.x + R.av.x) + (avc.y + R.av.y)));
                 double dB = L.mass + (((awc.y + R.aw.y) + (asc.y + asc2)) + ((avc.y + R.av.y) + (avc2 + R.av2)));
-                if ((long long)k == L.sig_idx) dA += L.sig[0];
-                if ((long long)(k + 1) == L.sig_idx) dB += L.sig[0];
+                if (has_sig(L, (long long)k)) dA += L.sig[(long long)k - L.sig_idx];
+                if (has_sig(L, (long long)(k + 1))) dB += L.sig[(long long)(k + 1) - L.sig_idx];
                 double oA = awc.x * a0;
                 oA = fma(R.aw.x, a2, oA); oA = fma(asc.x, l1, oA); oA = fma(asc.y, b1, oA);
                 oA = fma(avc.x, l0, oA); oA = fma(R.av.x, l2, oA); oA = fma(avc.y, b0, oA); oA = fma(R.av.y, b2, oA);
                 double oB = awc.y * b0;
                 oB = fma(R.aw.y, b2, oB); oB = fma(asc.y, a1, oB); oB = fma(asc2, r1, oB);
                 oB = fma(avc.y, a0, oB); oB = fma(R.av.y, a2, oB); oB = fma(avc2, r0, oB); oB = fma(R.av2, r2, oB);
-                const double sA = ((long long)k == L.pin) ? 0. : dA * a1 - oA;
-                const double sB = ((long long)(k + 1) == L.pin) ? 0. : dB * b1 - oB;
+                const double sA = is_pin(L, (long long)k) ? 0. : dA * a1 - oA;
+                const double sB = is_pin(L, (long long)(k + 1)) ? 0. : dB * b1 - oB;
                 if (two) { st2(dout + k, a1, b1); st2(s + k, sA, sB); dotv = fma(sA, a1, dotv); dotv = fma(sB, b1, dotv); }
                 else if (ok) { dout[k] = a1; s[k] = sA; dotv = fma(sA, a1, dotv); }
             }

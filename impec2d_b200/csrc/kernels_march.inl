@@ -86,7 +86,7 @@ struct PreGeom {
     int Ilo, Ihi;                          // coarse rows this chunk stores
     int jA, J; bool colok, own, own_c, clamp_l, clamp_r, wall_lo, wall_hi;
     int N1;
-    long long kb, ld, pin;                 // index of (row 0, jA), pitch, pinned cell
+    long long kb, ld, pin, pin_end;                 // index of (row 0, jA), pitch, pinned cell
     long long kcb, ldc;                    // coarse: index of (row 0, J), pitch
 };
 
@@ -126,8 +126,8 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
                   S.xB3, xB1, S.xA2, S.xr2, S.xA3, xA1, S.xr3, xr1);
         rA = sum4((double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y, S.xl3, xl1, S.xB3, xB1);
     }
-    if (!act2 || k2 == G.pin) rA = 0.;
-    if (!act2 || k2 + 1 == G.pin) rB = 0.;
+    if (!act2 || (k2 >= G.pin && k2 < G.pin_end)) rA = 0.;
+    if (!act2 || (k2 + 1 >= G.pin && k2 + 1 < G.pin_end)) rB = 0.;
     // 4. full weighting: along j now, along i when the fourth row of a coarse cell is complete
     double rl = IMPEC_SHFL_UP(rB, 1), rr = IMPEC_SHFL_DOWN(rA, 1);
     if (G.clamp_l) rl = rA;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_pre(LevelDev L, con
     G.wlo = (ia == 0 && !g.wall_lo) ? -2 : ia;
     G.whi = (ib == g.N1 && !g.wall_hi) ? g.N1 + 2 : ib;
     G.Ilo = ia >> 1; G.Ihi = (ib >> 1 < gc.N1) ? ib >> 1 : gc.N1;
-    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
+    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin; G.pin_end = L.pin_end;
     G.ldc = gc.ld; G.kcb = (long long)IMPEC_GH * gc.ld + (G.colok ? G.J : 0) + IMPEC_PJ;
     PreState<F32> S;
     S.xF1 = S.e01 = 0.; S.f1.x = S.f1.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
@@ -201,7 +201,7 @@ template <bool F32> struct PostState {
 struct PostGeom {
     int t_rlo, t_rhi, ia, ib;
     int jA; bool colok, own;
-    long long kb, ld, pin;
+    long long kb, ld, pin, pin_end;
 };
 template <bool F32, bool PROLONG>
 IMPEC_D PostRow<F32, PROLONG> post_load(const Coef<F32> &A, const double *__restrict__ f, const double *__restrict__ xin, const Grid &g, const Grid &gc,
@@ -237,8 +237,8 @@ IMPEC_D void post_step(const int t, const PostRow<F32, PROLONG> &R, PostState<F3
         const double pm = 0.75 * R.e[2] + 0.25 * R.e[3];
         const double pp = 0.75 * R.e[4] + 0.25 * R.e[5];
         const long long k = G.kb + (long long)t * G.ld;
-        if (k != G.pin) a += 0.75 * pc + 0.25 * pm;
-        if (k + 1 != G.pin) b += 0.75 * pc + 0.25 * pp;
+        if (!(k >= G.pin && k < G.pin_end)) a += 0.75 * pc + 0.25 * pm;
+        if (!(k + 1 >= G.pin && k + 1 < G.pin_end)) b += 0.75 * pc + 0.25 * pp;
     }
     const double il0 = IMPEC_SHFL_UP(b, 1), ir0 = IMPEC_SHFL_DOWN(a, 1);
     // 2. first colour on row t-1 (rows t-2, t-1, t of the old iterate; same-colour diagonal neighbours lagged)
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_post(LevelDev L, co
     G.colok = G.jA >= 0 && G.jA < g.N2;
     G.own = G.colok && lane >= 1 && lane < 31;
     G.t_rlo = g.rlo; G.t_rhi = g.rhi;
-    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
+    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin; G.pin_end = L.pin_end;
     PostState<F32> S;
     S.il1 = S.iA1 = S.iB1 = S.ir1 = S.il2 = S.iA2 = S.iB2 = S.ir2 = S.il3 = S.iA3 = S.iB3 = S.ir3 = 0.;
     S.yF2 = S.yF3 = S.e2 = 0.; S.f1.x = S.f1.y = S.f2.x = S.f2.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(MG_BLOCK, 3) k_sgs_march(LevelDev L, const dou
     G.colok = G.jA >= 0 && G.jA < g.N2;
     G.own = G.colok && lane >= 2 && lane < 30;
     G.t_rlo = g.rlo; G.t_rhi = g.rhi;
-    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin;
+    G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin; G.pin_end = L.pin_end;
     SgsFwd<F32> F;
     F.xF1 = F.e01 = F.xA2 = F.xB2 = 0.; F.f1.x = F.f1.y = 0.; F.c1 = coef_zero<F32>();
     PostState<F32> S;

@@ -141,9 +141,13 @@ struct LevelDev {
     // and the PCG mat-vec uses the FP64 links, so this changes the preconditioner by ~6e-8 relative, not the solution)
     const float *AWf, *ASf, *AVf, *DINVf;
     double mass;                 // 0 elliptic, 1 Crank-Nicolson
-    long long pin;               // fine level: padded index of the Dirichlet cell (or -1)
-    long long sig_idx;           // coarse levels: padded index of the cell carrying the pin's diagonal shift
-    const double *sig;           // device pointer to that shift (k_pin_sigma): kernel arguments stay constant across steps
+    // Dirichlet (pinned) cells: a contiguous index range [pin, pin_end) of the padded layout -- the single cell (1,1) of the parallel /
+    // diagonal configurations, or a whole row (source_type horizontal: row i = 1 of the pressure problem, row N1-2 of the Crank-Nicolson
+    // problem; src/MGSolver.cpp:109-140).  pin = pin_end = -1: none.
+    long long pin, pin_end;
+    // coarse levels: the cells [sig_idx, sig_end) carry the pins' diagonal shift sig[k - sig_idx] (k_pin_sigma / k_pin_sigma_row)
+    long long sig_idx, sig_end;
+    const double *sig;           // device pointer to the shifts: kernel arguments stay constant across steps
     // Row-chunk map of the marching kernels: CTA row blockIdx.y works on chunk cy0 + blockIdx.y * cys.  (0, 1) = all chunks in order; a
     // slab level launches the first and the last chunk -- the only ones that read halo rows -- as (0, ny - 1) x 2 behind the halo
     // exchange on a second stream, and the interior chunks (1, 1) x (ny - 2) concurrently with that exchange.
@@ -154,11 +158,13 @@ struct LevelDev {
 };
 
 IMPEC_D int chunk_of(const LevelDev &L) { return L.cy0 + (int)blockIdx.y * L.cys; }
+IMPEC_D bool is_pin(const LevelDev &L, long long k) { return k >= L.pin && k < L.pin_end; }
+IMPEC_D bool has_sig(const LevelDev &L, long long k) { return k >= L.sig_idx && k < L.sig_end; }
 
 IMPEC_D double link_diag(const LevelDev &L, size_t k) {
     const int ld = L.g.ld;
     double d = L.mass + (((L.AW[k] + L.AW[k + ld]) + (L.AS[k] + L.AS[k + 1])) + ((L.AV[k] + L.AV[k + ld]) + (L.AV[k + 1] + L.AV[k + ld + 1])));
-    if ((long long)k == L.sig_idx) d += L.sig[0];
+    if (has_sig(L, (long long)k)) d += L.sig[(long long)k - L.sig_idx];
     return d;
 }
 // order W,E,S,N,SW,SE,NW,NE (same as the oracle's off_sum)
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(256) k_smooth_color(LevelDev L, int color, con
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= L.g.N1 || j >= L.g.N2) return;
     const size_t k = gidx(L.g, i, j);
-    if (((i + j) & 1) != color || (long long)k == L.pin) { xout[k] = ZERO ? 0. : xin[k]; return; }
+    if (((i + j) & 1) != color || is_pin(L, (long long)k)) { xout[k] = ZERO ? 0. : xin[k]; return; }
     xout[k] = ZERO ? f[k] * L.DINV[k] : (f[k] + link_offsum(L, xin, k)) * L.DINV[k];
 }
 
@@ -205,8 +211,8 @@ __global__ void __launch_bounds__(256) k_diag_inv(LevelDev L, const double *__re
     const size_t k = gidx(L.g, i, j);
     const int ld = L.g.ld;
     double d = L.mass + (((L.AW[k] + L.AW[k + ld]) + (L.AS[k] + L.AS[k + 1])) + ((L.AV[k] + L.AV[k + ld]) + (L.AV[k + 1] + L.AV[k + ld + 1])));
-    if ((long long)k == L.sig_idx && sigma) d += sigma[0];
-    DINV[k] = ((long long)k == L.pin) ? 0. : 1. / d;
+    if (has_sig(L, (long long)k) && sigma) d += sigma[(long long)k - L.sig_idx];
+    DINV[k] = is_pin(L, (long long)k) ? 0. : 1. / d;
 }
 
 // r = f - S x  (0 at the pinned cell); optionally accumulates <r,r> partials
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(256) k_residual(LevelDev L, const double *__re
     const int i = (int)(blockIdx.y * blockDim.y + threadIdx.y) - (L.g.wall_lo ? 0 : 1);     // one halo row where a slab continues
     if (i >= L.g.N1 + (L.g.wall_hi ? 0 : 1) || j >= L.g.N2) return;
     const size_t k = gidx(L.g, i, j);
-    r[k] = ((long long)k == L.pin) ? 0. : f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k));
+    r[k] = is_pin(L, (long long)k) ? 0. : f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k));
 }
 
 // Residual r = f - S x when x is zero except at the pinned cell: r equals f everywhere but at the pin (0) and its 8 neighbours, so
@@ -227,7 +233,7 @@ __global__ void k_residual_pin_fix(LevelDev L, const double *__restrict__ f, con
     const int i = pi + t / 3 - 1, j = pj + t % 3 - 1;
     if (i < 0 || i >= L.g.N1 || j < 0 || j >= L.g.N2) return;
     const size_t k = gidx(L.g, i, j);
-    r[k] = ((long long)k == L.pin) ? 0. : f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k));
+    r[k] = is_pin(L, (long long)k) ? 0. : f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k));
 }
 
 // || f - S x ||^2 without storing the residual (the true residual reported with every solve): 40 B/cell in one pass instead of
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(256) k_residual_norm(LevelDev L, const double 
         const int i = (int)blockIdx.y * rows + r + (int)threadIdx.y;
         if (i < L.g.N1 && j < L.g.N2) {
             const size_t k = gidx(L.g, i, j);
-            if ((long long)k != L.pin) { const double rr = f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k)); v += rr * rr; }
+            if (!is_pin(L, (long long)k)) { const double rr = f[k] - (link_diag(L, k) * x[k] - link_offsum(L, x, k)); v += rr * rr; }
         }
     }
     v = block_reduce<RED_SUM>(v);
@@ -270,12 +276,12 @@ __global__ void __launch_bounds__(256) k_restrict(Grid gf, const double *__restr
 }
 
 // x += P e : cell-centred bilinear interpolation with edge replication
-__global__ void __launch_bounds__(256) k_prolong_add(Grid gc, const double *__restrict__ e, Grid gf, double *__restrict__ x, long long pin) {
+__global__ void __launch_bounds__(256) k_prolong_add(Grid gc, const double *__restrict__ e, Grid gf, double *__restrict__ x, long long pin, long long pin_end) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= gf.N1 || j >= gf.N2) return;
     const size_t k = gidx(gf, i, j);
-    if ((long long)k == pin) return;
+    if ((long long)k >= pin && (long long)k < pin_end) return;
     const int I = i >> 1, J = j >> 1;
     int In = (i & 1) ? I + 1 : I - 1;
     if (In < 0 && gc.wall_lo) In = 0;
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(256) k_matvec_dot(LevelDev L, const double *__
     double v = 0.;
     if (i < L.g.N1 && j < L.g.N2) {
         const size_t k = gidx(L.g, i, j);
-        const double sk = ((long long)k == L.pin) ? 0. : link_diag(L, k) * d[k] - link_offsum(L, d, k);
+        const double sk = is_pin(L, (long long)k) ? 0. : link_diag(L, k) * d[k] - link_offsum(L, d, k);
         s[k] = sk;
         v = sk * d[k];
     }
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(256) k_update_d(Grid g, const double *__restri
 
 // b = -q scattered into the padded layout, x0 = 0 except the pinned value; partial <b,b>
 __global__ void __launch_bounds__(256) k_setup_rhs(Grid g, const double *__restrict__ q, double *__restrict__ rhs, double *__restrict__ x,
-                                                   long long pin, double pin_value, double *__restrict__ part) {
+                                                   long long pin, long long pin_end, double pin_value, double pin_scale, double *__restrict__ part) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
     double v = 0.;
@@ -387,7 +393,8 @@ __global__ void __launch_bounds__(256) k_setup_rhs(Grid g, const double *__restr
         const size_t k = gidx(g, i, j);
         const double qk = q[k];
         rhs[k] = qk;                       // SPD form: S x = -b = q
-        x[k] = ((long long)k == pin) ? pin_value : 0.;
+        // Dirichlet cells: one cell with a given value, or a row whose values follow from the row's own equation kappa/dA p = -q (pin_scale = -dA)
+        x[k] = ((long long)k >= pin && (long long)k < pin_end) ? (pin_scale != 0. ? pin_scale * qk : pin_value) : 0.;
         v = qk * qk;                       // <b,b> = <q,q>
     }
     v = block_reduce<RED_SUM>(v);
@@ -443,7 +450,7 @@ __global__ void __launch_bounds__(256) k_cn_rhs(LevelDev L, const double *__rest
     if (i < L.g.N1 && j < L.g.N2) {
         const size_t k = gidx(L.g, i, j);
         const double links = link_diag(L, k) - L.mass;
-        const double b = c[k] + (link_offsum(L, c, k) - links * c[k]);
+        const double b = is_pin(L, (long long)k) ? 0. : c[k] + (link_offsum(L, c, k) - links * c[k]);      // Dirichlet rows: rhs = 0 (src/MGSolver.cpp:1357-1364)
         rhs[k] = b; x[k] = 0.;
         v = b * b;
     }

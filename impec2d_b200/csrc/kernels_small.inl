@@ -180,7 +180,7 @@ IMPEC_D void small_body(const SmallArgs &A, const double *f0, double *S, const i
             for (int m = 0; m < SM_PER; m++) {
                 if (Q.c[m] < 0) continue;
                 double v = 0.;
-                if ((long long)Q.k[m] != D.pin) v = Q.par[m] == 0 ? small_offsum(C, g.ld, (size_t)Q.k[m], x, Q.c[m], W) : small_diagsum(C, g.ld, (size_t)Q.k[m], x, Q.c[m], W);
+                if (!is_pin(D, (long long)Q.k[m])) v = Q.par[m] == 0 ? small_offsum(C, g.ld, (size_t)Q.k[m], x, Q.c[m], W) : small_diagsum(C, g.ld, (size_t)Q.k[m], x, Q.c[m], W);
                 R[Q.t[m]] = v;
             }
         }
@@ -235,7 +235,7 @@ IMPEC_D void small_body(const SmallArgs &A, const double *f0, double *S, const i
         small_cells<NT>(g, Q, tid);
 #pragma unroll
         for (int m = 0; m < SM_PER; m++) {
-            if (Q.c[m] < 0 || (long long)Q.k[m] == D.pin) continue;
+            if (Q.c[m] < 0 || is_pin(D, (long long)Q.k[m])) continue;
             const int i = Q.t[m] / g.N2, j = Q.t[m] - i * g.N2;
             const int I = i >> 1, J = j >> 1;
             int In = (i & 1) ? I + 1 : I - 1, Jn = (j & 1) ? J + 1 : J - 1;

@@ -115,6 +115,7 @@ bool Impec2DSolver::Solve() {
             if (listed || (sp->log_skip_steps != 0 && (counter == 1 || counter % sp->log_skip_steps == 0))) LogResults(counter, false);
         }
         maxc = max(maxc, d.c_max); minc = min(minc, d.c_min);
+        if (sp->stype == HORIZONTAL && sp->im != CONSTANT) InitHorizontalFront(sp, q, t);      // time-dependent injection (:437-438)
         if (!checkpoint_file.empty() && checkpoint_every > 0 && counter % checkpoint_every == 0)
             DeviceContext::Check(ctx, impec_checkpoint_save(ctx, RankFile(checkpoint_file).c_str(), t, counter), "impec_checkpoint_save");
     }

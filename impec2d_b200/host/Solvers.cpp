@@ -38,7 +38,9 @@ void EllipticSolver::CalcVelocities(Array2d &p, Array3d &v, Array2d &c) {
 
 // ------------------------------------------------------------------ MGSolver (src/MGSolver.cpp:50-149, 223-248, 952-976)
 MGSolver::MGSolver(SimParams *sp) : EllipticSolver(sp) {
-    if (sp->stype != PARALLEL && sp->stype != DIAGONAL) { cerr << "MGSolver: source_type horizontal is outside the accelerated path" << endl; exit(1); }
+    // Dirichlet cells (src/MGSolver.cpp:109-140): cell (1,1) for parallel / diagonal wells, the rows i = 1 (pressure) and i = N1-2 (Crank-
+    // Nicolson) for the horizontal front -- both handled inside the device library from sp->stype
+    if (sp->stype != PARALLEL && sp->stype != DIAGONAL && sp->stype != HORIZONTAL) { cerr << "ERROR: Unknown source type!" << endl; exit(1); }
 }
 MGSolver::~MGSolver() {}
 bool MGSolver::SolveLinearMultigrid(Array2d &c_c, int c_bounds, Array2d &p_c, int p_bounds, double const *const q_v) {

@@ -40,7 +40,16 @@ double CalcAdvectionL1Norm(SimParams const *const sp, const Array2d &c, double, 
         s += fabs(f(sp, sp->x_lb + (i + 0.5) * sp->dx, sp->y_lb + (j + 0.5) * sp->dy) - c(i, j));
     return s * sp->dx * sp->dy;
 }
+// InitHorizontalFront (src/Util.cpp:607-639): injection layer at i = 0.., production layer at the far end; pulsing / linear / constant rate
+void InitHorizontalFront(SimParams *sp, double *q, double t) {
+    const impec_params P = DeviceContext::ToParams(sp);
+    const int mode = sp->im == PULSING ? 0 : (sp->im == LINEAR ? 1 : 2);
+    const int rc = impec_init_horizontal_front(&P, sp->I, sp->well_width, mode, sp->q_freq, sp->q_high_multiple, sp->tstart, sp->tfinal, t, q);
+    if (rc != IMPEC_OK) { std::cerr << "Injection layer cannot be represented on this grid: (qlayer_width < 1)" << std::endl; exit(1); }
+    DeviceContext::InvalidateSource(sp);                  // q changed in place: the next solver call uploads it again
+}
 void InitSource(SimParams *sp, double *q) {
+    if (sp->stype == HORIZONTAL) { InitHorizontalFront(sp, q, 0); return; }           // src/Impec2DSolver.cpp:273-274
     if (sp->well_profile == GAUSSIAN) { for (int k = 0; k < sp->M; k++) q[k] = 0.; return; }   // no-op upstream (:253-254)
     const impec_params P = DeviceContext::ToParams(sp);
     const int rc = impec_init_source(&P, sp->I, sp->well_rc, sp->well_profile == ONECELL ? 2 : 0, q);

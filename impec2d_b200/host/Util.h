@@ -9,6 +9,7 @@ double VerticalSine(SimParams const *const sp, double x, double y);
 double Sinewave(SimParams const *const sp, double x, double y);
 double CalcAdvectionL2Norm(SimParams const *const sp, const Array2d &c, double t, double (*fptr)(SimParams const *const, double, double));
 double CalcAdvectionL1Norm(SimParams const *const sp, const Array2d &c, double t, double (*fptr)(SimParams const *const, double, double));
+void InitHorizontalFront(SimParams *sp, double *q, double t);   // src/Util.h:28
 void InitSource(SimParams *sp, double *q);            // Impec2DSolver::InitializeSource (circle / one_cell wells)
 void PrintDToPlotFile(const std::string &file, const Array2d &a, double x_lb, double y_lb, double dx, double dy, int bounds);
 void PrintVelToPlotFile(const std::string &ufile, const std::string &vfile, const Array3d &v, double x_lb, double y_lb, double dx, double dy, int bounds, int N1, int N2);

@@ -216,6 +216,10 @@ int   impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, double *a
 /* host-side setup helpers (no device work) */
 /* Impec2DSolver::InitializeSource  src/Impec2DSolver.cpp:241-280, src/Util.cpp:444-586; well_profile 0 circle, 2 one_cell */
 int   impec_init_source(const impec_params *p, double I, double well_rc, int well_profile, double *q);
+/* InitHorizontalFront (src/Util.cpp:607-639; source_type "horizontal"): injection layer of round(well_width (x_ub-x_lb)/dx) rows at
+ * i = 0.., production layer at the far end.  mode 0 pulsing (q_freq, q_high_multiple), 1 linear ramp tstart..tfinal, 2 constant; t = time. */
+int   impec_init_horizontal_front(const impec_params *P, double I, double well_width, int mode, double q_freq, double q_high_multiple,
+                                  double tstart, double tfinal, double t, double *q);
 /* developed synthetic concentration for benchmarks; writes the interior of a ghosted array */
 int   impec_synth_state(const impec_params *p, unsigned long long seed, double *c_ghosted);
 /* the same restricted to global rows [row0, row0+nrows): q_slab is nrows x N2, c_slab_ghosted is (nrows+2g) x (N2+2g) */

@@ -95,6 +95,7 @@ def lib():
         L.orc_impes_step.argtypes = [pp, sp, dp, dp, dp, dp, dp, d, d]; L.orc_impes_step.restype = d
         L.orc_exact_vol_frac_circle.argtypes = [d] * 5; L.orc_exact_vol_frac_circle.restype = d
         L.orc_init_source.argtypes = [pp, d, d, C.c_int, dp]
+        L.orc_init_horizontal_front.argtypes = [pp, d, d, C.c_int, d, d, d, d, d, dp]; L.orc_init_horizontal_front.restype = C.c_int
         L.orc_profile.argtypes = [pp, C.c_int, d, d]; L.orc_profile.restype = d
         L.orc_advection_norm.argtypes = [pp, dp, C.c_int, C.c_int]; L.orc_advection_norm.restype = d
         L.orc_init_elliptic_test.argtypes = [pp, dp, dp, dp, dp]

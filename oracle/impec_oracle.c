@@ -1103,6 +1103,29 @@ void orc_init_source(const orc_params *P, double I, double well_rc, int well_pro
 
 /* ------------------------------------------------------------------ profiles and norms */
 /* src/Util.cpp:55-114 */
+/* InitHorizontalFront, src/Util.cpp:607-639.  mode: 0 pulsing, 1 linear, 2 constant (enum INJ_MODE, src/SimParams.h:27).  Returns the
+ * layer width in rows (< 1: the reference exits). */
+int orc_init_horizontal_front(const orc_params *P, double I, double well_width, int mode, double q_freq, double q_high_multiple,
+                              double tstart, double tfinal, double t, double *q) {
+    const int N1 = P->N1, N2 = P->N2;
+    const double dx = DX(P), dy = DY(P);
+    const int qlayer_width = (int)round(well_width * (P->x_ub - P->x_lb) / dx);
+    if (qlayer_width < 1) return qlayer_width;
+    double val = I / (N2 * dx * dy * qlayer_width);
+    const size_t M = (size_t)N1 * N2;
+    for (size_t i = 0; i < M; i++) q[i] = 0.;
+    if (mode == 0) {
+        const double tau = 1. / q_freq;
+        const double x = fmod(t, tau);
+        if (x > tau / 2.) val *= q_high_multiple;
+    } else if (mode == 1) {
+        const double vl = val, vh = val * q_high_multiple;
+        val = vl + (t - tstart) * (vh - vl) / (tfinal - tstart);
+    }
+    for (int i = 0; i < N2 * qlayer_width; i++) { q[i] = val; q[M - 1 - i] = -val; }
+    return qlayer_width;
+}
+
 double orc_profile(const orc_params *P, int profile, double x, double y) {
     const double dx = DX(P), dy = DY(P);
     switch (profile) {

@@ -28,7 +28,10 @@ def production_case(N1, N2=None, stype=O.PARALLEL, seed=20260917, **kw):
     c = O.scalar_field(Po)
     lib.orc_synth_state(C.byref(Po), seed, c)
     q = np.zeros(N1 * N2)
-    lib.orc_init_source(C.byref(Po), 1.0, 0.05, 0, q)
+    if stype == O.HORIZONTAL:      # source_type "horizontal": injection layer at i = 0.., production layer at the far end (src/Util.cpp:607-639)
+        assert lib.orc_init_horizontal_front(C.byref(Po), 1.0, 0.05, 2, 1.0, 1.0, 0.0, 1.0, 0.0, q) >= 1
+    else:
+        lib.orc_init_source(C.byref(Po), 1.0, 0.05, 0, q)
     return base, Po, c, q
 
 

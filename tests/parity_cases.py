@@ -268,6 +268,58 @@ def check_impes_step(emulated, N1=48, N2=48, stype=O.PARALLEL, nu=2.0 / 3.0, avg
     ctx.close()
 
 
+def check_horizontal_front(emulated, N1=48, N2=32, diffusion=0, steps=2, links_fp32=1):
+    """source_type "horizontal" (SURVEY 8f rank 4): the Dirichlet ROW i = 1 of the pressure problem (src/MGSolver.cpp:119-140) and, with
+    dispersion, the Dirichlet row i = N1-2 of the Crank-Nicolson problem (:130-139, 1292-1315, 1357-1364), against the oracle."""
+    lib = O.lib()
+    base, Po, c, q = production_case(N1, N2, stype=O.HORIZONTAL, diffusion=diffusion, eps=1e-12)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.set_option("mg_links_fp32", links_fp32)
+    ctx.upload_c(c); ctx.upload_q(q)
+    So = O.new_state(); p = O.scalar_field(Po); u = O.velocity_field(Po); v = O.velocity_field(Po); co = c.copy()
+    t = 0.0
+    for _ in range(steps):
+        dto = lib.orc_impes_step(C.byref(Po), C.byref(So), p, co, u, v, q, t, 0.0)
+        dtg, info = ctx.impes_step(t, 0.0)
+        # With FP64 coefficients in the cycle the iteration counts (and residual histories) equal the oracle's; the default FP32 copies of
+        # the coefficients perturb the preconditioner by 6e-8, which costs 0-2 iterations here (the coarse cells next to the Dirichlet row
+        # carry a large diagonal shift) and nothing in the converged pressure.
+        assert info.converged == 1 and abs(info.iterations - So.last_its) <= (2 if links_fp32 else 0), (info.iterations, So.last_its)
+        assert abs(dtg - dto) <= 1e-9 * dto
+        if diffusion:
+            assert abs(ctx.last_parabolic_info().iterations - So.last_parabolic_its) <= 1
+        t += dto
+    g = Po.g
+    pg = ctx.download_p(); cg = ctx.download_c()
+    assert rel_l2(interior(Po, pg), interior(Po, p)) <= TOL_P
+    assert np.abs(cg - co).max() <= 1e-8
+    # the pinned row holds its Dirichlet values exactly: p(1, j) = -q(1, j) dA, and (with dispersion) c(N1-2, j) = 0 after the last CN half step
+    dA = Po.dx * Po.dy
+    assert np.array_equal(pg[g + 1, g:-g], -q.reshape(N1, N2)[1] * dA)
+    if diffusion:
+        assert np.all(cg[g + N1 - 2, g:-g] == 0.0)
+    ctx.close()
+
+
+def check_horizontal_generators(emulated):
+    """InitHorizontalFront with constant, pulsing and linearly ramped injection (src/Util.cpp:607-639): library == oracle bit for bit."""
+    lib = O.lib()
+    base = dict(N1=40, N2=24, x_ub=2.0, y_ub=1.0, stype=O.HORIZONTAL)
+    Po = O.default_params(**base); Pi = I.default_params(emulated=emulated, **base)
+    for mode in (0, 1, 2):
+        for t in (0.0, 0.13, 0.26, 0.41, 0.9):
+            qo = np.zeros(40 * 24)
+            assert lib.orc_init_horizontal_front(C.byref(Po), 1.5, 0.1, mode, 2.0, 3.0, 0.0, 1.0, t, qo) == 4
+            qg = I.init_horizontal_front(Pi, 1.5, 0.1, mode, 2.0, 3.0, 0.0, 1.0, t, emulated=emulated)
+            assert np.array_equal(qo, qg) and abs(qo.sum()) < 1e-12 and qo[0] > 0 and qo[-1] < 0
+    try:
+        I.init_horizontal_front(Pi, 1.0, 0.001, 2, emulated=emulated)         # layer narrower than one cell: the reference exits
+        assert False
+    except I.ImpecError:
+        pass
+
+
 def check_elliptic_manufactured(emulated, N1=20, N2=30, testno=4, nu=1.0):
     """elliptic_test.cfg: p = cos x cos y, Neumann, K(x,y) test fields; GPU pressure vs oracle and vs exact."""
     lib = O.lib()

@@ -59,3 +59,13 @@ def test_diagnostic_values(): pc.check_diagnostic_values(True, N=40)
 def test_hyperbolic_test_config(): pc.check_hyperbolic_test_config(True, 64, steps=2)
 def test_integral_diagnostics_device_vs_host(): pc.check_integral_diagnostics(True, N=48, steps=2)
 def test_fused_operator_build_bitexact(): pc.check_fused_build(True, 40, 67)
+
+
+# source_type "horizontal" (SURVEY 8f rank 4): Dirichlet rows, horizontal-front source with pulsing / linear injection
+def test_horizontal_front(): pc.check_horizontal_front(True, 48, 32)
+def test_horizontal_front_fp64_cycle_same_iterations(): pc.check_horizontal_front(True, 48, 32, links_fp32=0)
+def test_horizontal_front_dispersion(): pc.check_horizontal_front(True, 48, 32, diffusion=1)
+def test_horizontal_generators(): pc.check_horizontal_generators(True)
+def test_horizontal_front_marching_kernels(monkeypatch):
+    monkeypatch.setenv("IMPEC_MARCH_MIN_CELLS", "0")
+    pc.check_horizontal_front(True, 128, 128, diffusion=1, steps=1)

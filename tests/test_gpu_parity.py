@@ -235,3 +235,10 @@ def test_cpp_host_layer_on_the_gpu(tmp_path):
     assert out.returncode == 0 and "host_api_check ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     out = subprocess.run([os.path.join(lib_dir, "impec2d"), str(cfg), "--steps", "3"], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and "[3]\tITS_e:" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+# source_type "horizontal" 
+def test_horizontal_front(): pc.check_horizontal_front(False, 256, 192)
+def test_horizontal_front_dispersion(): pc.check_horizontal_front(False, 256, 192, diffusion=1)
+def test_horizontal_generators(): pc.check_horizontal_generators(False)
+def test_horizontal_front_production_kernels(): pc.check_horizontal_front(False, 4096, 2048, diffusion=1, steps=1)      # fine level on the marching kernels

@@ -140,3 +140,28 @@ def test_class_surface_called_directly(tmp_path):
     cfg = cfg_variant(tmp_path, "parallel.cfg", [(r"x_cells\s*=\s*\d+", "x_cells = 48"), (r"y_cells\s*=\s*\d+", "y_cells = 48")])
     out = subprocess.run([exe, cfg], capture_output=True, text=True)
     assert out.returncode == 0 and "host_api_check ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_horizontal_front_with_pulsing_injection(tmp_path):
+    """source_type "horizontal" through the driver: Dirichlet row, InitHorizontalFront re-evaluated every step
+    (src/Impec2DSolver.cpp:437-438).  With mode = "pulsing" the rate jumps by q_high_multiple in the second half of each period 1/q_freq,
+    so the CFL time step drops by that factor there; mass stays balanced throughout."""
+    cfg = cfg_variant(tmp_path, "parallel.cfg", [(r"x_cells\s*=\s*\d+", "x_cells = 64"), (r"y_cells\s*=\s*\d+", "y_cells = 48"),
+                                                 (r'source_type\s*=\s*"parallel"', 'source_type = "horizontal"'), (r'(\s)mode\s*=\s*"\w+"', r'\1mode = "pulsing"'),
+                                                 (r"x_ub\s*=\s*[0-9.]+", "x_ub = 1.0"), (r"y_ub\s*=\s*[0-9.]+", "y_ub = 1.0"),
+                                                 (r"q_high_multiple\s*=\s*[0-9.]+", "q_high_multiple = 4.")])
+    out = subprocess.run([EXE, cfg, "--steps", "8"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = [l for l in out.stdout.splitlines() if l.startswith("[")]
+    assert len(rows) == 8
+    t = [float(re.search(r"\st: ([0-9.eE+-]+)", l).group(1)) for l in rows]
+    dt = [float(re.search(r"dt: ([0-9.eE+-]+)", l).group(1)) for l in rows]
+    em = [float(re.search(r"E_m: ([0-9.eE+-]+)", l).group(1)) for l in rows]
+    # q_freq = 20: low rate while fmod(t, 0.05) <= 0.025, 4 x the rate afterwards -> the time step of a step that STARTS in the high
+    # half is about a quarter of the first one
+    high = [k for k in range(1, 8) if (t[k - 1] % 0.05) > 0.025]
+    assert high, t
+    assert all(dt[k] < 0.4 * dt[0] for k in high) and dt[1] > 0.8 * dt[0], (t, dt)
+    # (the reference's mass-balance diagnostic assumes the base rate, src/Impec2DSolver.cpp:391-415: exact while the rate is low, off afterwards)
+    low = [k for k in range(8) if k not in high and all(h > k for h in high)]
+    assert all(em[k] < 1e-6 for k in low), em

@@ -43,3 +43,9 @@ def test_two_ranks_overlapped_halo_exchange():
     PRE / POST / PLAIN / mat-vec kernels run as exchange + edge chunks + interior chunks; the result must equal the 1-rank run.  The same
     split with the exchange switched back to the serial order (IMPEC_HALO_OVERLAP=0) is covered by test_two_ranks_marching_kernels."""
     run(2, 128, 128, 0, 0, 1, 29617, {"IMPEC_MARCH_MIN_CELLS": "0", "IMPEC_MARCH_ROWS": "8", "IMPEC_REQUIRE_OVERLAP": "1"})
+
+
+def test_two_ranks_horizontal_front():
+    """source_type "horizontal": the Dirichlet row i = 1 lives on rank 0, the Crank-Nicolson Dirichlet row i = N1-2 on the last rank; the
+    coarse-level shifts of the pinned row are computed on rank 0 and broadcast."""
+    run(2, 64, 48, 2, 1, 1, 29618)

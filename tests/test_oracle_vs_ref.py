@@ -24,14 +24,14 @@ from oracle import ref as R
 pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (needs /root/reference)")
 lib = O.lib()
 SQRT2 = 1.41421356237
-STYPE = {O.PARALLEL: "parallel", O.DIAGONAL: "diagonal"}
+STYPE = {O.PARALLEL: "parallel", O.DIAGONAL: "diagonal", O.HORIZONTAL: "horizontal"}
 AVG = {O.HARMONIC: "harmonic", O.MEANCONC: "mean_concentration"}
 SPLIT = {O.ALTERNATING: "alternating_sweeps", O.X_FIRST: "x_sweep_first", O.Y_FIRST: "y_sweep_first", O.STRANG: "strang", O.SYMMETRIC_PARALLEL: "parallel"}
 
 
 def pair(N1, N2, stype=O.PARALLEL, nu=2.0 / 3.0, avg=O.HARMONIC, x_ub=None, y_ub=None, mu_res=41.0, mu_inj=1.0, diffusion=0, alpha_l=1.0,
          alpha_t=1.0, ptype=O.CRANKNICOLSON, split=O.SYMMETRIC_PARALLEL, porosity=1.0, cfl=0.5, is_test=0, testno=4, eps=1e-14,
-         well_profile="circle", inj=1.0, dt_diff_limit=0.9):
+         well_profile="circle", inj=1.0, dt_diff_limit=0.9, wells=None, endtime=None):
     """The same configuration as oracle parameters and as a set of reference objects (through a generated cfg file)."""
     L = SQRT2 if stype == O.PARALLEL else 1.0
     x_ub = L if x_ub is None else x_ub
@@ -44,7 +44,7 @@ def pair(N1, N2, stype=O.PARALLEL, nu=2.0 / 3.0, avg=O.HARMONIC, x_ub=None, y_ub
                 hyperbolic=dict(nu=nu, diffusion=bool(diffusion), alpha_l=alpha_l, alpha_t=alpha_t, dimensional_splitting=SPLIT[split],
                                 porosity=porosity, cfl=cfl, inj_fluid_conc=inj, dt_diff_limiter=dt_diff_limit),
                 parabolic=dict(para_method="crank-nicolson" if ptype == O.CRANKNICOLSON else "explicit"),
-                wells=dict(well_profile=well_profile),
+                wells=dict(well_profile=well_profile, **(wells or {})),
                 test=dict(component="elliptic", testno=testno, initial_x_cells=N1, initial_y_cells=N2))
     return Po, ref
 
@@ -377,6 +377,71 @@ def test_impes_steps_match_reference(stype, diffusion, N):
         t += dtr
     assert c.max() > 0.5
     assert abs(S.total_mass_outflux - ref.L.ref_total_mass_outflux(ref.h, 0)) <= 1e-9 * max(1.0, S.total_mass_outflux)
+    ref.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------- 8f-4: source_type "horizontal"
+MODES = {"pulsing": 0, "linear": 1, "constant": 2}
+
+
+@pytest.mark.parametrize("mode", ["constant", "pulsing", "linear"])
+def test_horizontal_front_source_bitexact(mode):
+    """InitHorizontalFront (src/Util.cpp:607-639) through Impec2DSolver::InitializeSource's dispatch (:273-274) at several times: layer
+    width, base rate, pulsing (second half of every period at q_high_multiple times the rate) and the linear ramp."""
+    Po, ref = pair(40, 24, stype=O.HORIZONTAL, x_ub=2.0, y_ub=1.0, wells=dict(mode=mode, well_width=0.1, q_freq=2.0, q_high_multiple=3.0))
+    P = ref.params()
+    for t in (0.0, 0.13, 0.26, 0.41, 0.9):
+        assert ref.L.ref_init_source(ref.h, t) == 0
+        q = np.zeros(40 * 24)
+        assert lib.orc_init_horizontal_front(C.byref(Po), 1.0, 0.1, MODES[mode], 2.0, 3.0, P["tstart"], P["tfinal"], t, q) == 4
+        assert np.array_equal(q, ref.get("q")) and q[0] > 0 and q[-1] < 0, (mode, t)
+    ref.close()
+
+
+@pytest.mark.parametrize("N1,N2,nu", [(32, 32, 2.0 / 3.0), (40, 24, 1.0)])
+def test_horizontal_elliptic_matrix_rhs_solution(N1, N2, nu):
+    """source_type horizontal: the Dirichlet ROW i = 1 (src/MGSolver.cpp:119-129, 517-567) in the assembled matrix, bit for bit, and the
+    converged pressure."""
+    Po, ref = pair(N1, N2, stype=O.HORIZONTAL, nu=nu, x_ub=1.0, y_ub=1.0)
+    c = synth(Po); lib.orc_fill_boundaries(C.byref(Po), c)
+    q = np.zeros(N1 * N2)
+    assert lib.orc_init_horizontal_front(C.byref(Po), 1.0, 0.05, 2, 20.0, 50.0, 0.0, 1.0, 0.0, q) >= 1
+    ref.set("c", c); ref.set("q", q)
+    ref.L.ref_pressure_solve(ref.h)
+    A, b, x, rec = ref.last_system()
+    Ao = np.zeros(N1 * N2 * 9); bo = np.zeros(N1 * N2)
+    lib.orc_assemble_elliptic(C.byref(Po), c, q, Ao, bo)
+    assert np.array_equal(Ao.reshape(N1, N2, 9), A) and np.array_equal(bo.reshape(N1, N2), b)
+    assert np.count_nonzero(A[1, :, 1:]) == 0 and np.all(A[1, :, 0] > 0)           # row 1: diagonal only
+    S = O.new_state(); p = O.scalar_field(Po)
+    assert lib.orc_solve_elliptic(C.byref(Po), C.byref(S), c, q, p) == 0
+    pr = ref.get("p")
+    assert np.linalg.norm(O.interior(Po, p) - O.interior(Po, pr)) <= 1e-10 * np.linalg.norm(O.interior(Po, pr))
+    ref.close()
+
+
+@pytest.mark.parametrize("diffusion", [0, 1])
+def test_horizontal_impes_steps_match_reference(diffusion):
+    """Three steps of the loop body with the horizontal front (with dispersion: the Dirichlet row i = N1-2 of the Crank-Nicolson problem,
+    src/MGSolver.cpp:130-139, 1292-1315, 1357-1364)."""
+    N1, N2 = 40, 32
+    Po, ref = pair(N1, N2, stype=O.HORIZONTAL, diffusion=diffusion, x_ub=1.0, y_ub=1.0)
+    q = np.zeros(N1 * N2)
+    assert lib.orc_init_horizontal_front(C.byref(Po), 1.0, 0.05, 2, 20.0, 50.0, 0.0, 1.0, 0.0, q) >= 1
+    ref.set("q", q)
+    S = O.new_state()
+    p = O.scalar_field(Po); c = O.scalar_field(Po); u = O.velocity_field(Po); v = O.velocity_field(Po)
+    t = 0.0
+    for step in range(3):
+        its = C.c_int()
+        dtr = ref.L.ref_impes_step(ref.h, t, 0.0, C.byref(its))
+        dto = lib.orc_impes_step(C.byref(Po), C.byref(S), p, c, u, v, q, t, 0.0)
+        assert abs(dto - dtr) <= 1e-10 * dtr
+        pr = ref.get("p"); cr = ref.get("c")
+        assert np.linalg.norm(O.interior(Po, p) - O.interior(Po, pr)) <= 1e-9 * np.linalg.norm(O.interior(Po, pr))
+        assert np.abs(c - cr).max() <= 1e-9
+        t += dtr
+    assert c.max() > 0.1
     ref.close()
 
 
