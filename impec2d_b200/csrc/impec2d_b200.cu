@@ -581,7 +581,6 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
         if (P->dim_splitting != IMPEC_SYMMETRIC_PARALLEL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "multi-GPU transport supports dimensional_splitting = parallel only");
         if (P->N1 % (2 * nranks) != 0 || P->N1 / nranks < 8) return fail(ctx, IMPEC_ERR_ARG, "x_cells = %d cannot be cut into %d slabs of an even number (>= 8) of rows", P->N1, nranks);
     }
-    if (P->diffusion && P->alpha_l != P->alpha_t) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t gives a non-symmetric CN operator; not supported");
     { const char *e = getenv("IMPEC_MARCH_VARIANT"); if (e) ctx->march_variant = atoi(e); }
     CUDA_TRY(ctx, cudaSetDevice(device));
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
@@ -1744,7 +1743,77 @@ extern "C" int impec_advect_split(impec_ctx *ctx, double dt) {
 // removes the wall links.  Solved by the same PCG with one symmetric red-black sweep as preconditioner (the system
 // is strongly diagonally dominant: dt D / dx^2 <~ cfl).  c must carry filled ghosts (the caller's FillBoundaries) and
 // u, v their ghost fill (CalcVelocities).  x0 = 0 as upstream (:1379-1391).
+// alpha_l != alpha_t: the Crank-Nicolson matrix is a full, NON-symmetric 9-point operator (src/MGSolver.cpp:923-948); upstream hands it to
+// HYPRE's PCG regardless.  Here: matrix-free operator on the four face arrays of the dispersion tensor (k_cn9_*), solved by BiCGStab with
+// the folded diagonal as preconditioner to the same relative residual (para_eps), x0 = 0.  Same linear system as the reference's (the oracle
+// and the compiled reference agree on its entries bit for bit, tests/test_oracle_vs_ref.py); a general-purpose path, not a tuned one:
+// no shipped cfg uses it.  One GPU.
+static int diffusion_split_general(impec_ctx *ctx, double dt, impec_solve_info *info) {
+    const Grid &g = ctx->g;
+    if (ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t (non-symmetric Crank-Nicolson operator) runs on one GPU");
+    if (ctx->P.stype == IMPEC_HORIZONTAL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t is not combined with source_type horizontal");
+    const dim3 gr = grid2d(g.N2, g.N1);
+    const long long nparts = (long long)gr.x * gr.y;
+    Level &L0 = ctx->L[0];
+    ctx->op_valid = false; ctx->mob_valid = false;          // level-0 link arrays and the mobility scratch are reused
+    Cn9 A; A.F11 = L0.AW; A.F12 = L0.AV; A.G22 = L0.AS; A.G21 = ctx->tb; A.dt = dt;
+    LAUNCH(ctx, k_cn9_faces, grid2d(g.N2 + 1, g.N1 + 1), kBlock, g, (const double *)ctx->u, (const double *)ctx->v, ctx->D, L0.AW, L0.AV, L0.AS, ctx->tb);
+    double *x = ctx->ta, *r = ctx->r, *r0 = ctx->z, *p = ctx->d, *v = ctx->s, *s = ctx->d2buf, *t = ctx->t0, *ph = ctx->MU, *sh = ctx->KV11, *dinv = L0.DINV;
+    LAUNCH_COOP(ctx, k_cn9_rhs, gr, kBlock, g, A, ctx->D, (const double *)ctx->c, ctx->rhs, x, ctx->part);
+    TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_BIPROD));
+    TRY(fetch_scalars(ctx, S_BIPROD, 1));
+    const double bb = ctx->h_scal[S_BIPROD], tol = ctx->P.para_eps;
+    const size_t bytes = grid_elems(g) * sizeof(double);
+    CUDA_TRY(ctx, cudaMemcpyAsync(r, ctx->rhs, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(r0, ctx->rhs, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(v, 0, bytes, ctx->stream));
+    // the folded diagonal (one operator pass on any ghost-filled field; its product is discarded)
+    TRY(fill_scalar(ctx, r, 0));
+    LAUNCH(ctx, k_cn9_apply, gr, kBlock, g, A, ctx->D, (const double *)r, t, dinv);
+    auto dotp = [&](const double *a, const double *b, double *out) -> int {
+        LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, a, b, ctx->part);
+        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_TMP));
+        TRY(fetch_scalars(ctx, S_TMP, 1));
+        *out = ctx->h_scal[S_TMP];
+        return IMPEC_OK;
+    };
+    double rho = 1., alpha = 1., omega = 1., rr = bb;
+    int it = 0, converged = (bb > 0. && rr / bb >= tol * tol) ? 0 : 1;
+    while (!converged && it < ctx->P.max_iter) {
+        it++;
+        double rho1; TRY(dotp(r0, r, &rho1));
+        if (rho1 == 0.) break;
+        const double beta = (rho1 / rho) * (alpha / omega);
+        rho = rho1;
+        LAUNCH(ctx, k_bicg_p, gr, kBlock, g, beta, omega, (const double *)r, (const double *)v, (const double *)dinv, p, ph);
+        TRY(fill_scalar(ctx, ph, 0));
+        LAUNCH(ctx, k_cn9_apply, gr, kBlock, g, A, ctx->D, (const double *)ph, v, (double *)nullptr);
+        double r0v; TRY(dotp(r0, v, &r0v));
+        alpha = rho / r0v;
+        LAUNCH(ctx, k_bicg_s, gr, kBlock, g, alpha, (const double *)r, (const double *)v, (const double *)dinv, s, sh);
+        TRY(fill_scalar(ctx, sh, 0));
+        LAUNCH(ctx, k_cn9_apply, gr, kBlock, g, A, ctx->D, (const double *)sh, t, (double *)nullptr);
+        double tt, ts; TRY(dotp(t, t, &tt)); TRY(dotp(t, s, &ts));
+        omega = tt > 0. ? ts / tt : 0.;
+        LAUNCH_COOP(ctx, k_bicg_xr, gr, kBlock, g, alpha, omega, (const double *)ph, (const double *)sh, (const double *)s, (const double *)t, x, r, ctx->part);
+        TRY(reduce_final(ctx, RED_SUM, nparts, 1, 0, S_IPROD));
+        TRY(fetch_scalars(ctx, S_IPROD, 1));
+        rr = ctx->h_scal[S_IPROD];
+        if (!(rr == rr)) return fail(ctx, IMPEC_ERR_NOCONV, "BiCGStab produced NaN at iteration %d", it);
+        if (rr / bb < tol * tol) { converged = 1; break; }
+        if (omega == 0.) break;
+    }
+    if (info) { info->iterations = it; info->converged = converged; info->relres = bb > 0. ? sqrt(rr / bb) : 0.; info->true_relres = info->relres; }
+    LAUNCH(ctx, k_copy_interior, gr, kBlock, g, (const double *)x, ctx->c);
+    // the face arrays carry values on the wall faces and in the pad entries, which the link kernels expect to be zero (wall links are
+    // never written by the operator build): hand the arrays back clean
+    CUDA_TRY(ctx, cudaMemsetAsync(L0.AW, 0, bytes, ctx->stream)); CUDA_TRY(ctx, cudaMemsetAsync(L0.AS, 0, bytes, ctx->stream)); CUDA_TRY(ctx, cudaMemsetAsync(L0.AV, 0, bytes, ctx->stream));
+    return converged ? IMPEC_OK : fail(ctx, IMPEC_WARN_NOCONV, "BiCGStab did not reach eps=%g in %d iterations (relres %g)", tol, it, sqrt(rr / bb));
+}
+
 extern "C" int impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info *info) {
+    if (ctx->P.alpha_l != ctx->P.alpha_t) return diffusion_split_general(ctx, dt, info);
     const Grid &g = ctx->g;
     const dim3 gr = grid2d(g.N2, g.N1);
     const long long nparts = (long long)gr.x * gr.y;

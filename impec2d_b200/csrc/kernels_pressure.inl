@@ -458,6 +458,141 @@ __global__ void __launch_bounds__(256) k_cn_rhs(LevelDev L, const double *__rest
     if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
 }
 
+// ---- general dispersion tensor (alpha_l != alpha_t): the Crank-Nicolson matrix has all nine entries and is NOT symmetric
+// (src/MGSolver.cpp:923-948).  Stored as the four face arrays it is built from -- d11, d12 on x faces (SetupDiffusionTensorF, :846-882),
+// d22, d21 on y faces (SetupDiffusionTensorG, :886-919) -- and applied matrix-free.  The Neumann folding of :1031-1289 adds every entry
+// whose neighbour lies outside to the entry of that neighbour's mirror image, i.e. A_folded x = A_unfolded x~ with x~ the field with
+// mirrored ghost cells: the operator kernel below reads a ghost-filled x.
+__global__ void __launch_bounds__(256) k_cn9_faces(Grid g, const double *__restrict__ u, const double *__restrict__ v, DevParams P,
+                                                   double *__restrict__ F11, double *__restrict__ F12, double *__restrict__ G22, double *__restrict__ G21) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > g.N1 || j > g.N2) return;
+    const size_t k = gidx(g, i, j);
+    const int ld = g.ld;
+    const double maxdx = P.dx > P.dy ? P.dx : P.dy;
+    const double al = P.alpha_l * maxdx, at = P.alpha_t * maxdx;
+    if (j < g.N2) {
+        const double uu = u[k];
+        const double vv = 1. / 4 * (v[k - ld + 1] + v[k + 1] + v[k - ld] + v[k]);
+        const double u2 = uu * uu, v2 = vv * vv, n2 = u2 + v2;
+        double d11 = 0., d12 = 0.;
+        if (n2 > 0.) {                                   // |u| = 0 gives 0/0 upstream (:868-869); no dispersion here
+            const double fl = P.porosity * al / sqrt(n2), ft = P.porosity * at / sqrt(n2);
+            d11 = fl * u2 + ft * v2;
+            d12 = fl * (uu * vv) + ft * (-uu * vv);
+        }
+        F11[k] = d11; F12[k] = d12;
+    }
+    if (i < g.N1) {
+        const double uu = 1. / 4 * (u[k + ld - 1] + u[k + ld] + u[k - 1] + u[k]);
+        const double vv = v[k];
+        const double u2 = uu * uu, v2 = vv * vv, n2 = u2 + v2;
+        double d22 = 0., d21 = 0.;
+        if (n2 > 0.) {
+            const double fl = P.porosity * al / sqrt(n2), ft = P.porosity * at / sqrt(n2);
+            d21 = fl * (uu * vv) + ft * (-uu * vv);
+            d22 = fl * v2 + ft * u2;
+        }
+        G22[k] = d22; G21[k] = d21;
+    }
+}
+struct Cn9 { const double *F11, *F12, *G22, *G21; double dt; };
+// the nine entries of row (i,j) in the order C, W, SW, S, SE, E, NE, N, NW (src/MGSolver.cpp:286-294, 923-948)
+IMPEC_D void cn9_row(const Grid &g, const Cn9 &A, const DevParams &P, size_t k, double e[9]) {
+    const int ld = g.ld;
+    const double dx = P.dx, dy = P.dy, dt = A.dt;
+    const double d11_im = A.F11[k], d12_im = A.F12[k], d11_ip = A.F11[k + ld], d12_ip = A.F12[k + ld];
+    const double d22_jm = A.G22[k], d21_jm = A.G21[k], d22_jp = A.G22[k + 1], d21_jp = A.G21[k + 1];
+    e[8] = dt / (8. * dx * dy) * (d12_im + d21_jp);                                                    // NW
+    e[6] = -dt / (8. * dx * dy) * (d12_ip + d21_jp);                                                   // NE
+    e[7] = -dt / 8. * (4. / (dy * dy) * d22_jp + 1. / (dx * dy) * (-d12_im + d12_ip));                 // N
+    e[2] = -dt / (8. * dx * dy) * (d12_im + d21_jm);                                                   // SW
+    e[4] = dt / (8. * dx * dy) * (d12_ip + d21_jm);                                                    // SE
+    e[3] = -dt / 8. * (4. / (dy * dy) * d22_jm + 1. / (dx * dy) * (-d12_ip + d12_im));                 // S
+    e[1] = -dt / 8. * (4. / (dx * dx) * d11_im + 1. / (dx * dy) * (-d21_jp + d21_jm));                 // W
+    e[0] = 1. + dt / (2. * dx * dx) * (d11_ip + d11_im) + dt / (2. * dy * dy) * (d22_jp + d22_jm);     // C
+    e[5] = -dt / 8. * (4. / (dx * dx) * d11_ip + 1. / (dx * dy) * (-d21_jm + d21_jp));                 // E
+}
+// y = A x (x with mirrored ghost cells).  DIAG != nullptr: also the inverse of the FOLDED diagonal (the Jacobi preconditioner)
+__global__ void __launch_bounds__(256) k_cn9_apply(Grid g, Cn9 A, DevParams P, const double *__restrict__ x, double *__restrict__ y, double *__restrict__ dinv) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.N1 || j >= g.N2) return;
+    const size_t k = gidx(g, i, j);
+    const int ld = g.ld;
+    double e[9];
+    cn9_row(g, A, P, k, e);
+    const int di[9] = {0, -1, -1, 0, 1, 1, 1, 0, -1}, dj[9] = {0, 0, -1, -1, -1, 0, 1, 1, 1};
+    double s = 0., dg = 0.;
+#pragma unroll
+    for (int a = 0; a < 9; a++) {
+        s += e[a] * x[(long long)k + (long long)di[a] * ld + dj[a]];
+        int ii = i + di[a], jj = j + dj[a];
+        ii = ii < 0 ? 0 : (ii > g.N1 - 1 ? g.N1 - 1 : ii); jj = jj < 0 ? 0 : (jj > g.N2 - 1 ? g.N2 - 1 : jj);
+        if (ii == i && jj == j) dg += e[a];
+    }
+    y[k] = s;
+    if (dinv) dinv[k] = 1. / dg;
+}
+// b = (I + dt/2 L_D) c with the full tensor (src/MGSolver.cpp:1324-1355), x0 = 0, partial <b,b>; c carries filled ghosts
+__global__ void __launch_bounds__(256) k_cn9_rhs(Grid g, Cn9 A, DevParams P, const double *__restrict__ c, double *__restrict__ rhs, double *__restrict__ x, double *__restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double v = 0.;
+    if (i < g.N1 && j < g.N2) {
+        const size_t k = gidx(g, i, j);
+        const int ld = g.ld;
+        const double dx = P.dx, dy = P.dy;
+        const double d11_im = A.F11[k], d12_im = A.F12[k], d11_ip = A.F11[k + ld], d12_ip = A.F12[k + ld];
+        const double d22_jm = A.G22[k], d21_jm = A.G21[k], d22_jp = A.G22[k + 1], d21_jp = A.G21[k + 1];
+#define C_(a, b) c[(long long)k + (long long)(a) * ld + (b)]
+        const double b = C_(0, 0) + A.dt / 8. * (
+            4. / (dx * dx) * (d11_ip * (C_(1, 0) - C_(0, 0)) - d11_im * (C_(0, 0) - C_(-1, 0)))
+            + 1. / (dx * dy) * (d12_ip * (C_(0, 1) + C_(1, 1) - C_(0, -1) - C_(1, -1)) - d12_im * (C_(0, 1) + C_(-1, 1) - C_(-1, -1) - C_(0, -1)))
+            + 1. / (dx * dy) * (d21_jp * (C_(1, 0) + C_(1, 1) - C_(-1, 1) - C_(-1, 0)) - d21_jm * (C_(1, 0) + C_(1, -1) - C_(-1, 0) - C_(-1, -1)))
+            + 4. / (dy * dy) * (d22_jp * (C_(0, 1) - C_(0, 0)) - d22_jm * (C_(0, 0) - C_(0, -1))));
+#undef C_
+        rhs[k] = b; x[k] = 0.;
+        v = b * b;
+    }
+    v = block_reduce<RED_SUM>(v);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+// BiCGStab vector updates (interior cells)
+__global__ void __launch_bounds__(256) k_bicg_p(Grid g, double beta, double omega, const double *__restrict__ r, const double *__restrict__ v, const double *__restrict__ dinv,
+                                                double *__restrict__ p, double *__restrict__ ph) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.N1 || j >= g.N2) return;
+    const size_t k = gidx(g, i, j);
+    const double pn = r[k] + beta * (p[k] - omega * v[k]);
+    p[k] = pn; ph[k] = pn * dinv[k];
+}
+__global__ void __launch_bounds__(256) k_bicg_s(Grid g, double alpha, const double *__restrict__ r, const double *__restrict__ v, const double *__restrict__ dinv,
+                                                double *__restrict__ s, double *__restrict__ sh) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.N1 || j >= g.N2) return;
+    const size_t k = gidx(g, i, j);
+    const double sn = r[k] - alpha * v[k];
+    s[k] = sn; sh[k] = sn * dinv[k];
+}
+__global__ void __launch_bounds__(256) k_bicg_xr(Grid g, double alpha, double omega, const double *__restrict__ ph, const double *__restrict__ sh, const double *__restrict__ s,
+                                                 const double *__restrict__ t, double *__restrict__ x, double *__restrict__ r, double *__restrict__ part) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    double v = 0.;
+    if (i < g.N1 && j < g.N2) {
+        const size_t k = gidx(g, i, j);
+        x[k] += alpha * ph[k] + omega * sh[k];
+        const double rn = s[k] - omega * t[k];
+        r[k] = rn; v = rn * rn;
+    }
+    v = block_reduce<RED_SUM>(v);
+    if (threadIdx.x == 0 && threadIdx.y == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+}
+
 // ---------------------------------------------------------------- a12: Darcy velocity
 // rotated-frame velocity at vertex (i-1/2,j-1/2) rotated back to (x,y): src/EllipticSolver.cpp:554-592
 IMPEC_D void vertex_vel(const DevParams &P, const double *__restrict__ p, double K11, double K22, size_t k, int ld, double &u1, double &u2) {

@@ -165,6 +165,8 @@ int   impec_advect_split(impec_ctx *ctx, double dt);
  * (index base (0,-g)), dir 1: G[N1+2g][N2+1] (index base (-g,0)).  The sweeps never materialise these arrays; single GPU. */
 int   impec_intercell_flux(impec_ctx *ctx, int dir, double dt, double *out_host);
 /* a19  HyperbolicSolver::DiffusionSplitCN -> MGSolver::Solve_Parabolic_cc_to_c  src/HyperbolicSolver.cpp:213-223, src/MGSolver.cpp:952-976 */
+/*      alpha_l == alpha_t: symmetric links operator, PCG with a one-march symmetric Gauss-Seidel preconditioner; alpha_l != alpha_t: the full
+ *      non-symmetric 9-point operator of src/MGSolver.cpp:923-948 applied matrix-free, BiCGStab (one GPU).  Both to para_eps, x0 = 0. */
 int   impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info *info);
 /* a14  HyperbolicSplitSolver::Solve                src/HyperbolicSplitSolver.cpp:162-198 */
 int   impec_transport_step(impec_ctx *ctx, double dt);

@@ -1008,6 +1008,42 @@ void orc_assemble_parabolic(const orc_params *P, const double *c, const double *
     }
 }
 
+/* BiCGStab with diagonal (Jacobi) preconditioning on the reference's 9-entry matrix: for the NON-symmetric Crank-Nicolson matrix of
+ * alpha_l != alpha_t (src/MGSolver.cpp:939-947), to which upstream applies HYPRE's PCG regardless.  Same stop rule as everywhere:
+ * ||r||_2 / ||b||_2 < tol with the recurrence residual, x0 = 0. */
+int orc_bicgstab9(int N1, int N2, const double *A, const double *b, double tol, int max_iter, double *x, int *its, double *relres) {
+    const size_t n = (size_t)N1 * N2;
+    double *r = (double *)malloc(sizeof(double) * n), *r0 = (double *)malloc(sizeof(double) * n), *p = (double *)calloc(n, sizeof(double));
+    double *v = (double *)calloc(n, sizeof(double)), *s = (double *)malloc(sizeof(double) * n), *t = (double *)malloc(sizeof(double) * n);
+    double *ph = (double *)malloc(sizeof(double) * n), *sh = (double *)malloc(sizeof(double) * n);
+    const double bb = dot(b, b, n);
+    for (size_t k = 0; k < n; k++) { x[k] = 0.; r[k] = b[k]; r0[k] = b[k]; }
+    double rho = 1., alpha = 1., omega = 1., rr = bb;
+    int it = 0, ret = (bb > 0. && rr / bb >= tol * tol) ? 1 : 0;
+    while (ret && it < max_iter) {
+        it++;
+        const double rho1 = dot(r0, r, n);
+        if (rho1 == 0.) { ret = -1; break; }
+        const double beta = (rho1 / rho) * (alpha / omega);
+        rho = rho1;
+        for (size_t k = 0; k < n; k++) { p[k] = r[k] + beta * (p[k] - omega * v[k]); ph[k] = p[k] / A[k * 9 + eC]; }
+        orc_matvec9(N1, N2, A, ph, v);
+        alpha = rho / dot(r0, v, n);
+        for (size_t k = 0; k < n; k++) { s[k] = r[k] - alpha * v[k]; sh[k] = s[k] / A[k * 9 + eC]; }
+        orc_matvec9(N1, N2, A, sh, t);
+        const double tt = dot(t, t, n);
+        omega = tt > 0. ? dot(t, s, n) / tt : 0.;
+        for (size_t k = 0; k < n; k++) { x[k] += alpha * ph[k] + omega * sh[k]; r[k] = s[k] - omega * t[k]; }
+        rr = dot(r, r, n);
+        if (rr / bb < tol * tol) { ret = 0; break; }
+        if (omega == 0.) { ret = -1; break; }
+    }
+    if (its) *its = it;
+    if (relres) *relres = bb > 0. ? sqrt(rr / bb) : 0.;
+    free(r); free(r0); free(p); free(v); free(s); free(t); free(ph); free(sh);
+    return ret;
+}
+
 /* src/MGSolver.cpp:952-976 */
 int orc_solve_parabolic(const orc_params *P, orc_state *S, double *c, const double *u, const double *v, double dt) {
     const int N1 = P->N1, N2 = P->N2;
@@ -1016,7 +1052,8 @@ int orc_solve_parabolic(const orc_params *P, orc_state *S, double *c, const doub
     orc_assemble_parabolic(P, c, u, v, dt, A, b);
     int its = 0; double rr = 0.;
     orc_params Q = *P; Q.mg_max_levels = 1; Q.mg_ncoarse = 1;       /* well conditioned: symmetric-GS PCG */
-    const int ret = orc_mgpcg(&Q, N1, N2, A, b, +1, P->para_eps, x, &its, &rr, NULL);
+    const int ret = (P->alpha_l != P->alpha_t) ? orc_bicgstab9(N1, N2, A, b, P->para_eps, P->max_iter, x, &its, &rr)   /* non-symmetric matrix */
+                                               : orc_mgpcg(&Q, N1, N2, A, b, +1, P->para_eps, x, &its, &rr, NULL);
     for (int i = 0; i < N1; i++) for (int j = 0; j < N2; j++) c[ci(P, i, j)] = x[(size_t)i * N2 + j];
     if (S) S->last_parabolic_its = its;
     free(A); free(b); free(x);

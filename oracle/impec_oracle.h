@@ -143,6 +143,7 @@ double orc_impes_step(const orc_params *P, orc_state *S, double *p, double *c, d
 /* wells: src/Util.cpp:444-639, src/Impec2DSolver.cpp:241-280 */
 double orc_exact_vol_frac_circle(double x1, double y1, double r, double dx, double dy);
 void   orc_init_source(const orc_params *P, double I, double well_rc, int well_profile /*0 circle,2 onecell*/, double *q);
+int    orc_bicgstab9(int N1, int N2, const double *A, const double *b, double tol, int max_iter, double *x, int *its, double *relres);   /* non-symmetric CN matrix (alpha_l != alpha_t) */
 int    orc_init_horizontal_front(const orc_params *P, double I, double well_width, int mode /*0 pulsing,1 linear,2 constant*/, double q_freq,
                                  double q_high_multiple, double tstart, double tfinal, double t, double *q);   /* src/Util.cpp:607-639 */
 

@@ -491,11 +491,12 @@ def check_small_vs_tiles(emulated, N1=256, N2=384, stype=O.DIAGONAL):
         assert np.abs(out[0][0] - out[1][0]).max() <= 1e-13 * np.abs(out[0][0]).max()
 
 
-def check_dispersion(emulated, N1=32, N2=32, stype=O.PARALLEL, steps=1):
+def check_dispersion(emulated, N1=32, N2=32, stype=O.PARALLEL, steps=1, alpha_l=1.0, alpha_t=1.0):
     """a19: Crank-Nicolson dispersion half step on its own and inside a full IMPES step of a *_dispersion.cfg
     operator (two CN solves per step).  Tolerance: max|dc| <= 1e-9 (both sides iterate to para_eps = 1e-14)."""
     lib = O.lib()
-    base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=1, eps=1e-12)
+    # alpha_l != alpha_t: the full, non-symmetric 9-point Crank-Nicolson operator (src/MGSolver.cpp:923-948), BiCGStab on both sides
+    base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=1, eps=1e-12, alpha_l=alpha_l, alpha_t=alpha_t)
     Pi = I.default_params(emulated=emulated, **base)
     ctx = I.Context(Pi, emulated=emulated)
     ctx.upload_c(c); ctx.upload_q(q)

@@ -69,3 +69,8 @@ def test_horizontal_generators(): pc.check_horizontal_generators(True)
 def test_horizontal_front_marching_kernels(monkeypatch):
     monkeypatch.setenv("IMPEC_MARCH_MIN_CELLS", "0")
     pc.check_horizontal_front(True, 128, 128, diffusion=1, steps=1)
+
+
+# dispersion with alpha_l != alpha_t: non-symmetric Crank-Nicolson operator (matrix-free 9-point operator + BiCGStab)
+def test_dispersion_anisotropic_tensor(): pc.check_dispersion(True, 40, 32, stype=O.DIAGONAL, steps=2, alpha_l=1.0, alpha_t=0.2)
+def test_dispersion_anisotropic_tensor_parallel(): pc.check_dispersion(True, 32, 32, stype=O.PARALLEL, steps=1, alpha_l=0.3, alpha_t=1.0)

@@ -242,3 +242,7 @@ def test_horizontal_front(): pc.check_horizontal_front(False, 256, 192)
 def test_horizontal_front_dispersion(): pc.check_horizontal_front(False, 256, 192, diffusion=1)
 def test_horizontal_generators(): pc.check_horizontal_generators(False)
 def test_horizontal_front_production_kernels(): pc.check_horizontal_front(False, 4096, 2048, diffusion=1, steps=1)      # fine level on the marching kernels
+
+
+# dispersion with alpha_l != alpha_t (non-symmetric Crank-Nicolson operator)
+def test_dispersion_anisotropic_tensor(): pc.check_dispersion(False, 320, 256, stype=O.DIAGONAL, steps=2, alpha_l=1.0, alpha_t=0.2)

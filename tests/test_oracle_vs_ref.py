@@ -346,12 +346,12 @@ def test_crank_nicolson_matrix_rhs_solution(N1, N2, x_ub, y_ub, al, at):
     assert np.array_equal(Ao.reshape(N1, N2, 9), A)
     assert np.array_equal(bo.reshape(N1, N2), b)
     assert rec.final_relres < 1e-13
-    if al == at:
-        S = O.new_state(); co = c.copy()
-        assert lib.orc_solve_parabolic(C.byref(Po), C.byref(S), co, u, v, dt) == 0
-        cr = ref.get("c")
-        assert np.abs(O.interior(Po, co) - O.interior(Po, cr)).max() <= 1e-11
-        assert np.abs(O.interior(Po, co) - O.interior(Po, c)).max() > 1e-6           # the half step did something
+    # (alpha_l != alpha_t: the oracle solves the non-symmetric system with BiCGStab; the reference build applies its PCG regardless)
+    S = O.new_state(); co = c.copy()
+    assert lib.orc_solve_parabolic(C.byref(Po), C.byref(S), co, u, v, dt) == 0
+    cr = ref.get("c")
+    assert np.abs(O.interior(Po, co) - O.interior(Po, cr)).max() <= 1e-11
+    assert np.abs(O.interior(Po, co) - O.interior(Po, c)).max() > 1e-6           # the half step did something
     ref.close()
 
 
