@@ -36,7 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SQRT2 = 1.41421356237
-CPU_BUDGET_S = 300.0         # the reference arm sizes its sample so that warm-up + timed steps stay within about this much CPU time
+CPU_BUDGET_REFERENCE_S = 180.0   # `--impl reference`: the sample is sized so that warm-up + timed steps stay within about this much CPU time
+CPU_BUDGET_BASELINE_S = 30.0     # `cpu_baseline` inside our own arm's line: a bounded sample of 10-30 s of CPU work
 
 WORKLOADS = {
     "parallel": dict(kind="impes", size=16384, L=SQRT2, stype=0, diffusion=0, cfg="examples/parallel.cfg"),
@@ -149,12 +150,12 @@ def cpu_impes_run(wl, steps, warmup, eps, n):
     return n * n * steps / el / 1e9, el / steps * 1e3, lib.orc_num_threads(), its
 
 
-def cpu_impes_sample_size(wl, steps, warmup, eps, full):
-    """Largest of {full, 8192, 4096, 2048} whose warm-up + timed steps fit CPU_BUDGET_S, from a calibration step at 2048^2."""
+def cpu_impes_sample_size(wl, steps, warmup, eps, full, budget_s):
+    """Largest of {full, 8192, 4096, 2048} whose warm-up + timed steps fit budget_s, from a calibration step at 2048^2."""
     val, ms, cores, its = cpu_impes_run(wl, 1, 0, eps, 2048)
     s_per_cell = ms * 1e-3 / (2048.0 * 2048.0)
     for n in (full, 8192, 4096, 2048):
-        if n <= full and s_per_cell * n * n * (steps + warmup) * 1.15 <= CPU_BUDGET_S:        # 1.15: bigger grids run a little slower per cell
+        if n <= full and s_per_cell * n * n * (steps + warmup) * 1.15 <= budget_s:        # 1.15: bigger grids run a little slower per cell
             return n
     return 2048
 
@@ -193,7 +194,7 @@ def cpu_transport_run(steps, warmup, n):
     return n * n * steps / el / 1e9, el / steps * 1e3, lib.orc_num_threads(), "port"
 
 
-def cpu_arm(wl, N, steps, warmup, eps):
+def cpu_arm(wl, N, steps, warmup, eps, budget_s=CPU_BUDGET_REFERENCE_S):
     """(value, ms/step, cpu_baseline dict, extra config) of the CPU implementation of workload wl."""
     if WORKLOADS[wl]["kind"] == "transport":
         val, ms, cores, kind = cpu_transport_run(steps, warmup, N)
@@ -201,12 +202,12 @@ def cpu_arm(wl, N, steps, warmup, eps):
                 "-DOMPHYPER -DOMPUTIL, OpenMP over all host threads)") if kind == "reference" else "CPU restatement of the reference path (oracle/), OpenMP over all host threads"
         return val, ms, {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "ms_per_step": ms,
                          "sample": "%d transport steps at the FULL %d^2 grid of the workload after %d warm-up; %s" % (steps, N, warmup, what)}, {}
-    n = cpu_impes_sample_size(wl, steps, warmup, eps, N)
+    n = cpu_impes_sample_size(wl, steps, warmup, eps, N, budget_s)
     val, ms, cores, its = cpu_impes_run(wl, steps, warmup, eps, n)
     return val, ms, {"value": val, "unit": "Gcell-updates/s", "cores": cores, "kind": "port", "ms_per_step": ms, "pcg_iterations": its, "sample_grid": [n, n],
                      "sample": "%d IMPES steps on a %d^2 sample of the workload (same operator, eps and state generator; the largest of 16384/8192/4096/2048 "
                                "whose %d steps fit ~%d s of CPU time) after %d warm-up; C restatement of the reference path (oracle/; the reference's own solve "
-                               "is HYPRE, unavailable), OpenMP over all %d host threads" % (steps, n, steps + warmup, int(CPU_BUDGET_S), warmup, cores)}, {}
+                               "is HYPRE, unavailable), OpenMP over all %d host threads" % (steps, n, steps + warmup, int(budget_s), warmup, cores)}, {}
 
 
 def common_config(wl, N, eps):
@@ -461,7 +462,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        _, _, cpu_baseline, _ = cpu_arm(wl, N, 2, 1, args.eps)
+        _, _, cpu_baseline, _ = cpu_arm(wl, N, 2, 1, args.eps, CPU_BUDGET_BASELINE_S)
 
     if rank == 0:
         run = {"mg_levels": ctx.mg_levels(), "comm_backend": ctx.comm_backend(),
