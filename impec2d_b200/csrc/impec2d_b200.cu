@@ -70,7 +70,6 @@ struct impec_ctx {
     bool links_f32 = true;                          // cycle kernels read FP32 copies of the coefficients (FP64 arithmetic)
     bool fast_r0 = true;                            // initial PCG residual for x0 = 0: copy of rhs + fix-up around the pin instead of a residual pass
     bool sgs_march = true;                          // Crank-Nicolson preconditioner (one symmetric sweep from zero) as ONE march (k_sgs_march)
-    int march_variant = 1;                          // bit 0: k_mg_march_pre with 2 rows in flight and 4 CTAs/SM (default) instead of 4 rows and 3 CTAs/SM
     bool march = true;                              // big levels: PRE / POST / PLAIN as register marches (kernels_march.inl); 0 = shared-memory tiles
     bool fused_mid = true;                          // W-cycle revisit: sweep + residual + restriction in one tile kernel (FUSED_MID)
     bool matvec_march = true;                       // PCG direction update + mat-vec as a register march (k_pcg_matvec_march); 0 = shared-memory tiles
@@ -581,7 +580,6 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
         if (P->dim_splitting != IMPEC_SYMMETRIC_PARALLEL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "multi-GPU transport supports dimensional_splitting = parallel only");
         if (P->N1 % (2 * nranks) != 0 || P->N1 / nranks < 8) return fail(ctx, IMPEC_ERR_ARG, "x_cells = %d cannot be cut into %d slabs of an even number (>= 8) of rows", P->N1, nranks);
     }
-    { const char *e = getenv("IMPEC_MARCH_VARIANT"); if (e) ctx->march_variant = atoi(e); }
     CUDA_TRY(ctx, cudaSetDevice(device));
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
@@ -748,7 +746,6 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "sweep_y_pairs") { ctx->sweep_y_pairs = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_prefetch") { ctx->pf_sweep = (int)value; return IMPEC_OK; }
     if (k == "l2_prefetch") { ctx->pf_pre = ctx->pf_post = ctx->pf_mv = ctx->pf_sgs = (int)value; return IMPEC_OK; }
-    if (k == "mg_march_variant") { ctx->march_variant = (int)value; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "matvec_march") { ctx->matvec_march = value != 0.0; return IMPEC_OK; }
@@ -814,10 +811,17 @@ static int scan_wells(impec_ctx *ctx, const double *q, std::vector<int> &wi, std
             const int r0 = (int)((long long)N1 * t / nt), r1 = (int)((long long)N1 * (t + 1) / nt);     // contiguous row blocks keep row-major order
             for (int i = r0; i < r1; i++) {
                 const double *row = q + (size_t)i * N2;
-                for (int j = 0; j < N2; j++) {
-                    const double v = row[j];
-                    if (v != 0.0) { ti[t].push_back(i); tj[t].push_back(j); tq[t].push_back(v); }
+                const unsigned long long *bits = reinterpret_cast<const unsigned long long *>(row);
+                int j = 0;
+                // blocks of 16 values that are all +-0.0 (OR of the bit patterns without the sign bit) are skipped without a per-element
+                // branch: the scan runs at memory speed where q is zero, i.e. almost everywhere
+                for (; j + 16 <= N2; j += 16) {
+                    unsigned long long a = 0;
+                    for (int e = 0; e < 16; e++) a |= bits[j + e];
+                    if ((a << 1) == 0) continue;
+                    for (int e = 0; e < 16; e++) { const double v = row[j + e]; if (v != 0.0) { ti[t].push_back(i); tj[t].push_back(j + e); tq[t].push_back(v); } }
                 }
+                for (; j < N2; j++) { const double v = row[j]; if (v != 0.0) { ti[t].push_back(i); tj[t].push_back(j); tq[t].push_back(v); } }
             }
         });
     for (auto &x : th) x.join();
@@ -1170,9 +1174,9 @@ static int fused_pre(Cycle &C, int l, const double *f) {
         auto launch = [&](int y0, int ys, int ny) -> int {
             const dim3 gg(gm.x, (unsigned)ny); const LevelDev D = chunked(C.D[l], y0, ys, ctx->pf_pre);
 #define MPRE(F32, PF, MB) LAUNCH_COOP(ctx, (k_mg_march_pre<F32, PF, MB>), gg, dim3(MG_BLOCK), D, f, L.x, tr ? Lc.gl : Lc.g, tr ? Lc.fl : Lc.f, L.march_rows)
-            if (!ctx->links_f32) MPRE(false, 4, 3);
-            else if (ctx->march_variant & 1) MPRE(true, 2, 4);      // 2 rows in flight, 4 CTAs per SM
-            else MPRE(true, 4, 3);                                  // 4 rows in flight, 3 CTAs per SM
+            // rotating register slots (kernels_march.inl): 159 registers, 3 CTAs per SM, no spills.  (Capped at 128 registers for 4 CTAs per
+            // SM the rotating form spills and loses what it gains: 1.75 ms against 1.58 at 16384^2, profiles/r2p_rotating_pre.txt.)
+            if (!ctx->links_f32) MPRE(false, 4, 3); else MPRE(true, 2, 3);
 #undef MPRE
             return IMPEC_OK;
         };

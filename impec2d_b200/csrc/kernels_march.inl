@@ -68,17 +68,22 @@ IMPEC_D double sum4(double w0, double w1, double w2, double w3, double v0, doubl
 
 // ================================================================ PRE: sweep from zero + residual + restriction
 template <bool F32> struct PreRow { d2 f; CoefRow<F32> c; };
-template <bool F32> IMPEC_D PreRow<F32> pre_load(const Coef<F32> &A, const double *__restrict__ f, long long k, bool ok) {
-    PreRow<F32> R; R.f.x = R.f.y = 0.; R.c = coef_zero<F32>();
-    if (ok) { R.f = ld2(f + k); R.c = coef_load<F32>(A, (size_t)k); }
+// (k is a valid address for every lane: columns outside the level are clamped to column 0 by the caller and every use of the loaded
+// values is masked by the act* / own flags, so the loads need no guard -- and no zero-fill of 12 registers per row)
+template <bool F32> IMPEC_D PreRow<F32> pre_load(const Coef<F32> &A, const double *__restrict__ f, long long k, bool) {
+    PreRow<F32> R;
+    R.f = ld2(f + k); R.c = coef_load<F32>(A, (size_t)k);
     return R;
 }
+// Pipeline state in FOUR ROTATING SLOTS: the data of row r lives in slot r & 3 for as long as it is needed (links and right-hand side
+// for 3 steps, final iterate values for 3 steps, the j-restricted residual for 4).  The march is unrolled four rows deep and the
+// slot of every access is a compile-time constant of the unrolled step (template parameter PH = row & 3), so the state never moves:
+// the earlier formulation shifted ~45 registers per row with IMAD.MOV (22 % of the kernel's instructions, ncu: issue-bound at 50 %).
 template <bool F32> struct PreState {
-    double xF1, e01;                       // row t-1: its first-colour value and the first-colour value next to its second-colour cell
-    d2 f1; CoefRow<F32> c1;                // row t-1
-    double xl2, xA2, xB2, xr2; CoefRow<F32> c2;   // row t-2 (final)
-    double xl3, xA3, xB3, xr3;             // row t-3 (final)
-    double h0, h1, h2, h3;                 // j-restricted residual of rows t-5 .. t-2
+    double xF[4], e0[4];                   // first-colour value of the row and the first-colour value next to its second-colour cell
+    d2 f[4]; CoefRow<F32> c[4];
+    double xl[4], xA[4], xB[4], xr[4];     // final values of the row: columns jA-1 | jA, jA+1 | jA+2
+    double h[4];                           // j-restricted residual of the row
 };
 struct PreGeom {
     int t_rlo, t_rhi;                      // active rows
@@ -90,9 +95,10 @@ struct PreGeom {
     long long kcb, ldc;                    // coarse: index of (row 0, J), pitch
 };
 
-// AF: on row t the even-column cell A carries the first colour
-template <bool F32, bool AF>
+// AF: on row t the even-column cell A carries the first colour.  PH = t & 3 (slot of row t).
+template <bool F32, bool AF, int PH>
 IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const PreGeom &G, double *__restrict__ x, double *__restrict__ fc) {
+    constexpr int s0 = PH, s1 = (PH + 3) & 3, s2 = (PH + 2) & 3, s3 = (PH + 1) & 3;      // slots of rows t, t-1, t-2, t-3
     // 1. first colour on row t (zero guess: no neighbours)
     const bool act0 = G.colok && t >= G.t_rlo && t < G.t_rhi;
     const double xF = act0 ? (AF ? R.f.x * (double)R.c.dinv.x : R.f.y * (double)R.c.dinv.y) : 0.;
@@ -101,15 +107,15 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
     const bool act1 = G.colok && t - 1 >= G.t_rlo && t - 1 < G.t_rhi;
     double xl1, xA1, xB1, xr1;
     if (AF) {   // row t-1: B first, A second
-        double off = (double)S.c1.aw.x * S.xA2;
-        off = fma((double)R.c.aw.x, xF, off); off = fma((double)S.c1.as.x, S.e01, off); off = fma((double)S.c1.as.y, S.xF1, off);
-        const double xS = act1 ? (S.f1.x + off) * (double)S.c1.dinv.x : 0.;
-        xA1 = xS; xB1 = S.xF1; xl1 = S.e01; xr1 = IMPEC_SHFL_DOWN(xS, 1);
+        double off = (double)S.c[s1].aw.x * S.xA[s2];
+        off = fma((double)R.c.aw.x, xF, off); off = fma((double)S.c[s1].as.x, S.e0[s1], off); off = fma((double)S.c[s1].as.y, S.xF[s1], off);
+        const double xS = act1 ? (S.f[s1].x + off) * (double)S.c[s1].dinv.x : 0.;
+        xA1 = xS; xB1 = S.xF[s1]; xl1 = S.e0[s1]; xr1 = IMPEC_SHFL_DOWN(xS, 1);
     } else {    // row t-1: A first, B second
-        double off = (double)S.c1.aw.y * S.xB2;
-        off = fma((double)R.c.aw.y, xF, off); off = fma((double)S.c1.as.y, S.xF1, off); off = fma((double)S.c1.as2, S.e01, off);
-        const double xS = act1 ? (S.f1.y + off) * (double)S.c1.dinv.y : 0.;
-        xA1 = S.xF1; xB1 = xS; xr1 = S.e01; xl1 = IMPEC_SHFL_UP(xS, 1);
+        double off = (double)S.c[s1].aw.y * S.xB[s2];
+        off = fma((double)R.c.aw.y, xF, off); off = fma((double)S.c[s1].as.y, S.xF[s1], off); off = fma((double)S.c[s1].as2, S.e0[s1], off);
+        const double xS = act1 ? (S.f[s1].y + off) * (double)S.c[s1].dinv.y : 0.;
+        xA1 = S.xF[s1]; xB1 = xS; xr1 = S.e0[s1]; xl1 = IMPEC_SHFL_UP(xS, 1);
     }
     if (G.own && t - 1 >= G.wlo && t - 1 < G.whi) st2(x + G.kb + (long long)(t - 1) * G.ld, xA1, xB1);
     // 3. residual on row t-2 (same parity as row t).  After a sweep from zero: first colour = sum over all 8 neighbours,
@@ -118,13 +124,13 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
     const long long k2 = G.kb + (long long)(t - 2) * G.ld;
     double rA, rB;
     if (AF) {
-        rA = sum8((double)S.c2.aw.x, (double)S.c1.aw.x, (double)S.c2.as.x, (double)S.c2.as.y, (double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y,
-                  S.xA3, xA1, S.xl2, S.xB2, S.xl3, xl1, S.xB3, xB1);
-        rB = sum4((double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2, S.xA3, xA1, S.xr3, xr1);
+        rA = sum8((double)S.c[s2].aw.x, (double)S.c[s1].aw.x, (double)S.c[s2].as.x, (double)S.c[s2].as.y, (double)S.c[s2].av.x, (double)S.c[s1].av.x, (double)S.c[s2].av.y, (double)S.c[s1].av.y,
+                  S.xA[s3], xA1, S.xl[s2], S.xB[s2], S.xl[s3], xl1, S.xB[s3], xB1);
+        rB = sum4((double)S.c[s2].av.y, (double)S.c[s1].av.y, (double)S.c[s2].av2, (double)S.c[s1].av2, S.xA[s3], xA1, S.xr[s3], xr1);
     } else {
-        rB = sum8((double)S.c2.aw.y, (double)S.c1.aw.y, (double)S.c2.as.y, (double)S.c2.as2, (double)S.c2.av.y, (double)S.c1.av.y, (double)S.c2.av2, (double)S.c1.av2,
-                  S.xB3, xB1, S.xA2, S.xr2, S.xA3, xA1, S.xr3, xr1);
-        rA = sum4((double)S.c2.av.x, (double)S.c1.av.x, (double)S.c2.av.y, (double)S.c1.av.y, S.xl3, xl1, S.xB3, xB1);
+        rB = sum8((double)S.c[s2].aw.y, (double)S.c[s1].aw.y, (double)S.c[s2].as.y, (double)S.c[s2].as2, (double)S.c[s2].av.y, (double)S.c[s1].av.y, (double)S.c[s2].av2, (double)S.c[s1].av2,
+                  S.xB[s3], xB1, S.xA[s2], S.xr[s2], S.xA[s3], xA1, S.xr[s3], xr1);
+        rA = sum4((double)S.c[s2].av.x, (double)S.c[s1].av.x, (double)S.c[s2].av.y, (double)S.c[s1].av.y, S.xl[s3], xl1, S.xB[s3], xB1);
     }
     if (!act2 || (k2 >= G.pin && k2 < G.pin_end)) rA = 0.;
     if (!act2 || (k2 + 1 >= G.pin && k2 + 1 < G.pin_end)) rB = 0.;
@@ -134,28 +140,28 @@ IMPEC_D void pre_step(const int t, const PreRow<F32> &R, PreState<F32> &S, const
     if (G.clamp_r) rr = rB;
     double h = 0.25 * rl;
     h += 0.75 * rA; h += 0.75 * rB; h += 0.25 * rr;
-    S.h0 = S.h1; S.h1 = S.h2; S.h2 = S.h3; S.h3 = h;
-    if (AF) {                                  // t even: rows t-5 .. t-2 are rows 2I-1 .. 2I+2 of coarse row I
+    S.h[s2] = h;                                   // rows t-5, t-4, t-3, t-2 of h sit in slots s1, s0, s3, s2
+    if (AF) {                                      // t even: rows t-5 .. t-2 are rows 2I-1 .. 2I+2 of coarse row I
         const int I = (t - 4) >> 1;
         if (G.own_c && I >= G.Ilo && I < G.Ihi) {
-            const double t0 = (I == 0 && G.wall_lo) ? S.h1 : S.h0;                   // row -1 mirrors onto row 0
-            const double t3 = (2 * I + 2 > G.N1 - 1 && G.wall_hi) ? S.h2 : S.h3;     // row N1 mirrors onto row N1-1
-            fc[G.kcb + (long long)I * G.ldc] = 0.25 * (0.25 * t0 + 0.75 * S.h1 + 0.75 * S.h2 + 0.25 * t3);
+            const double t0 = (I == 0 && G.wall_lo) ? S.h[s0] : S.h[s1];                  // row -1 mirrors onto row 0
+            const double t3 = (2 * I + 2 > G.N1 - 1 && G.wall_hi) ? S.h[s3] : S.h[s2];   // row N1 mirrors onto row N1-1
+            fc[G.kcb + (long long)I * G.ldc] = 0.25 * (0.25 * t0 + 0.75 * S.h[s0] + 0.75 * S.h[s3] + 0.25 * t3);
         }
     }
-    // shift the pipeline
-    S.xl3 = S.xl2; S.xA3 = S.xA2; S.xB3 = S.xB2; S.xr3 = S.xr2;
-    S.xl2 = xl1; S.xA2 = xA1; S.xB2 = xB1; S.xr2 = xr1; S.c2 = S.c1;
-    S.xF1 = xF; S.e01 = e0; S.f1 = R.f; S.c1 = R.c;
+    // the row's data stay where they are: only the new values are written into the slots of rows t and t-1
+    S.xl[s1] = xl1; S.xA[s1] = xA1; S.xB[s1] = xB1; S.xr[s1] = xr1;
+    S.xF[s0] = xF; S.e0[s0] = e0; S.f[s0] = R.f; S.c[s0] = R.c;
 }
 
 template <bool F32, int PF, int MINB>
 __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_pre(LevelDev L, const double *__restrict__ f, double *__restrict__ x, Grid gc, double *__restrict__ fc, int nrows) {
+    static_assert(PF == 2 || PF == 4, "rows in flight");
     const Grid g = L.g;
     const Coef<F32> A(L);
     const int lane = threadIdx.x & 31;
     const int gw = (int)blockIdx.x * (MG_BLOCK / 32) + (int)(threadIdx.x >> 5);
-    const int ia = chunk_of(L) * nrows;
+    const int ia = chunk_of(L) * nrows;        // nrows is a multiple of 4: the slot of a row is a constant of the unrolled step
     const int ib = (ia + nrows < g.N1) ? ia + nrows : g.N1;
     PreGeom G;
     G.jA = MGP_OWN * gw - 4 + 2 * lane; G.J = G.jA >> 1;
@@ -172,21 +178,27 @@ __global__ void __launch_bounds__(MG_BLOCK, MINB) k_mg_march_pre(LevelDev L, con
     G.ld = g.ld; G.kb = (long long)IMPEC_GH * g.ld + (G.colok ? G.jA : 0) + IMPEC_PJ; G.pin = L.pin; G.pin_end = L.pin_end;
     G.ldc = gc.ld; G.kcb = (long long)IMPEC_GH * gc.ld + (G.colok ? G.J : 0) + IMPEC_PJ;
     PreState<F32> S;
-    S.xF1 = S.e01 = 0.; S.f1.x = S.f1.y = 0.; S.c1 = coef_zero<F32>(); S.c2 = coef_zero<F32>();
-    S.xl2 = S.xA2 = S.xB2 = S.xr2 = S.xl3 = S.xA3 = S.xB3 = S.xr3 = 0.; S.h0 = S.h1 = S.h2 = S.h3 = 0.;
-    const int t0 = ia - 3, t1 = ib + 2;        // rows marched: [t0, t1]; t0 is odd
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        S.xF[a] = S.e0[a] = 0.; S.f[a].x = S.f[a].y = 0.; S.c[a] = coef_zero<F32>();
+        S.xl[a] = S.xA[a] = S.xB[a] = S.xr[a] = 0.; S.h[a] = 0.;
+    }
+    const int t0 = ia - 3, t1 = ib + 2;        // rows marched: [t0, t1]; t0 = 1 (mod 4)
     PreRow<F32> q[PF];
 #pragma unroll
     for (int u = 0; u < PF; u++) q[u] = pre_load<F32>(A, f, G.kb + (long long)((t0 + u <= t1) ? t0 + u : t1) * G.ld, G.colok);
-    for (int t = t0; t <= t1; t += PF) {
+    for (int t = t0; t <= t1; t += 4) {
 #pragma unroll
-        for (int u = 0; u < PF; u++) {
+        for (int u = 0; u < 4; u++) {
             if (t + u > t1) continue;
-            const PreRow<F32> R = q[u];
-            q[u] = pre_load<F32>(A, f, G.kb + (long long)((t + u + PF <= t1) ? t + u + PF : t1) * G.ld, G.colok);
+            const PreRow<F32> R = q[u % PF];
+            q[u % PF] = pre_load<F32>(A, f, G.kb + (long long)((t + u + PF <= t1) ? t + u + PF : t1) * G.ld, G.colok);
             if (L.pfd > 0 && t + u + L.pfd <= t1) { const long long kp = G.kb + (long long)(t + u + L.pfd) * G.ld; pf_l2(f + kp); coef_prefetch<F32>(A, (size_t)kp); }
-            if (u & 1) pre_step<F32, true>(t + u, R, S, G, x, fc);
-            else pre_step<F32, false>(t + u, R, S, G, x, fc);
+            // row t + u: slot (1 + u) & 3; A carries the first colour on even rows (u odd)
+            if (u == 0) pre_step<F32, false, 1>(t, R, S, G, x, fc);
+            else if (u == 1) pre_step<F32, true, 2>(t + 1, R, S, G, x, fc);
+            else if (u == 2) pre_step<F32, false, 3>(t + 2, R, S, G, x, fc);
+            else pre_step<F32, true, 0>(t + 3, R, S, G, x, fc);
         }
     }
 }

@@ -203,7 +203,7 @@ int   impec_reset_state(impec_ctx *ctx);                                 /* prod
  * residual floor instead of iterating the recurrence residual down to eps), "mg_fused", "mg_links_fp32",
  * "mg_graph", "mg_small", "mg_w_from", "mg_w_to", "mg_ncoarse", "max_iter".  Defaults reproduce the reference's semantics.
  * Kernel-generation switches (results identical, for A/B measurements and tests): "mg_march" (register-march multigrid kernels
- * on the big levels, default 1), "mg_march_variant", "matvec_march" (1), "sweep_shared" (MUSCL with one reconstruction per cell, 1),
+ * on the big levels, default 1), "matvec_march" (1), "sweep_shared" (MUSCL with one reconstruction per cell, 1),
  * "sweep_y_pairs" (y sweep with column pairs per lane, 1), "mg_fused_mid" (1), "sgs_march" (one-march Crank-Nicolson preconditioner, 1),
  * "l2_prefetch" / "sweep_prefetch" (rows of L2 software prefetch ahead of the marching kernels, 4 / 4; 0 = off),
  * "halo_overlap" (multi-GPU: halo exchange concurrent with the interior row chunks of its consumer, 1).
