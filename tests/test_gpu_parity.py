@@ -143,14 +143,14 @@ def test_headline_size_properties():
     ctx.close()
 
 
-def test_full_fingering_run_integral_diagnostics():
-    """North-star check 2: a full quarter-five-spot displacement (parallel.cfg operator, M = 41, 64^2, to t = 0.4).
+@pytest.mark.parametrize("N", [64, 192])
+def test_full_fingering_run_integral_diagnostics(N):
+    """North-star check 2: a full quarter-five-spot displacement (parallel.cfg operator, M = 41, 64^2 and 192^2, to t = 0.4).
     Pointwise agreement with the oracle over early times (max|dc| <= 1e-8 for t <= 0.05), afterwards the integral
     diagnostics computed by the ONE shared post-processor (impec2d_b200/diagnostics.py):
       breakthrough time +-1 %, produced (recovered) mass +-0.5 %, mass in place +-0.5 %, mixing-zone length +-2 %."""
     from impec2d_b200.diagnostics import RunDiagnostics
     lib = O.lib()
-    N = 64
     base, Po, c, q = production_case(N, N, eps=1e-10)
     c[...] = 0.0                                              # the shipped run starts from c = 0 (src/Impec2DSolver.cpp:222-230)
     Pi = I.default_params(**base)
