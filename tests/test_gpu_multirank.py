@@ -15,7 +15,7 @@ def ngpus():
 
 # march = 1: the register-march multigrid kernels (by default only on levels of >= 8M cells) forced onto every slab level
 @pytest.mark.parametrize("N1,N2,stype,diffusion,steps,march", [(512, 512, 0, 0, 2, 0), (256, 128, 1, 1, 2, 0), (2048, 2048, 0, 0, 1, 0), (2048, 2048, 0, 0, 1, 1),
-                                                                 (256, 192, 2, 1, 2, 0)]      # stype 2: horizontal front (Dirichlet rows on the first / last rank))
+                                                                 (256, 192, 2, 1, 2, 0)])      # (the last: stype 2 = horizontal front, Dirichlet rows on the first / last rank)
 def test_slabs_match_single_gpu(N1, N2, stype, diffusion, steps, march):
     world = min(ngpus(), 8)
     if world < 2:
