@@ -74,3 +74,9 @@ def test_horizontal_front_marching_kernels(monkeypatch):
 # dispersion with alpha_l != alpha_t: non-symmetric Crank-Nicolson operator (matrix-free 9-point operator + BiCGStab)
 def test_dispersion_anisotropic_tensor(): pc.check_dispersion(True, 40, 32, stype=O.DIAGONAL, steps=2, alpha_l=1.0, alpha_t=0.2)
 def test_dispersion_anisotropic_tensor_parallel(): pc.check_dispersion(True, 32, 32, stype=O.PARALLEL, steps=1, alpha_l=0.3, alpha_t=1.0)
+
+
+# edge cases: odd and tiny grids (an odd extent leaves a single multigrid level; 4 x 4 is the smallest grid the ABI accepts)
+@pytest.mark.parametrize("N1,N2,stype", [(30, 21, O.DIAGONAL), (21, 30, O.DIAGONAL), (6, 6, O.PARALLEL), (4, 4, O.DIAGONAL), (50, 36, O.DIAGONAL)])
+def test_impes_step_ragged_and_tiny_grids(N1, N2, stype): pc.check_impes_step(True, N1, N2, stype=stype, steps=1)
+def test_horizontal_front_tiny_grid(): pc.check_horizontal_front(True, 12, 8, steps=1)

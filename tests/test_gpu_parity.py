@@ -246,3 +246,9 @@ def test_horizontal_front_production_kernels(): pc.check_horizontal_front(False,
 
 # dispersion with alpha_l != alpha_t (non-symmetric Crank-Nicolson operator)
 def test_dispersion_anisotropic_tensor(): pc.check_dispersion(False, 320, 256, stype=O.DIAGONAL, steps=2, alpha_l=1.0, alpha_t=0.2)
+
+
+# edge cases: odd and tiny grids (an odd extent leaves a single multigrid level; 4 x 4 is the smallest grid the ABI accepts)
+@pytest.mark.parametrize("N1,N2,stype", [(30, 21, O.DIAGONAL), (21, 30, O.DIAGONAL), (6, 6, O.PARALLEL), (4, 4, O.DIAGONAL), (50, 36, O.DIAGONAL)])
+def test_impes_step_ragged_and_tiny_grids(N1, N2, stype): pc.check_impes_step(False, N1, N2, stype=stype, steps=1)
+def test_horizontal_front_tiny_grid(): pc.check_horizontal_front(False, 12, 8, steps=1)
