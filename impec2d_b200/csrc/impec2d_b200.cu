@@ -109,6 +109,7 @@ struct impec_ctx {
     // option "l2_prefetch" sets all four, IMPEC_L2_PREFETCH="pre,post,mv,sgs" (or one number) each.  0 = off.
     int pf_pre = 4, pf_post = 4, pf_mv = 4, pf_sgs = 4;
     int pf_sweep = 4;                               // MUSCL sweeps (option "sweep_prefetch" / IMPEC_SWEEP_PREFETCH)
+    bool defer_x = true;                            // PCG: merge the solution updates of two iterations (k_update_xr MODE 1 / 2; option "defer_x")
     bool sweep_y_pairs = true;                      // MUSCL y sweep: column pairs per lane + shuffles (k_muscl_y2); 0 = the shared-memory tile kernel k_muscl_y
     bool overlap = true;                            // option "halo_overlap" / IMPEC_HALO_OVERLAP=0/1
     long long overlapped = 0;                       // exchanges issued that way (diagnostic)
@@ -126,7 +127,7 @@ struct impec_ctx {
 };
 
 enum { S_GAMMA0 = 0, S_SDOTP = 1, S_IPROD = 2, S_GAMMA1 = 3, S_BIPROD = 4, S_BETA_NUM = 5, S_BETA_DEN = 6, S_TMP = 7, S_SRC = 8, S_OUTFLUX = 9,
-       S_DIAG = 10, S_DT = 20, S_ERR = 31, S_NSCAL = 32 };
+       S_DIAG = 10, S_DT = 20, S_ALPHA_PREV = 30, S_ERR = 31, S_NSCAL = 32 };
 
 static int fail(impec_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
@@ -743,6 +744,7 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "fast_r0") { ctx->fast_r0 = value != 0.0; return IMPEC_OK; }
     if (k == "sgs_march") { ctx->sgs_march = value != 0.0; return IMPEC_OK; }
     if (k == "halo_overlap") { ctx->overlap = value != 0.0; return IMPEC_OK; }
+    if (k == "defer_x") { ctx->defer_x = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_y_pairs") { ctx->sweep_y_pairs = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_prefetch") { ctx->pf_sweep = (int)value; return IMPEC_OK; }
     if (k == "l2_prefetch") { ctx->pf_pre = ctx->pf_post = ctx->pf_mv = ctx->pf_sgs = (int)value; return IMPEC_OK; }
@@ -1439,6 +1441,13 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
     const long long nmv = (long long)gmv.x * gmv.y;
     double *dcur = ctx->d, *dalt = ctx->d2buf;
     bool first_dir = true;
+    // deferred update of the solution: needs the two direction buffers of the fused path (d_k stays intact while d_{k+1} is built)
+    const bool defer_x = ctx->defer_x && fuse_dir;
+    bool x_pending = false;
+    auto flush_x = [&]() -> int {
+        if (x_pending) { LAUNCH(ctx, k_flush_x, gux, dim3(UX_BLOCK), g, (const double *)(ctx->scal + S_ALPHA_PREV), (const double *)dcur, x); x_pending = false; }
+        return IMPEC_OK;
+    };
     if (!converged) {
         TRY(mg_cycle(C, 0, ctx->r, ctx->part, &dparts));
         if (!fuse_dir) LAUNCH(ctx, k_update_d<true>, gr, kBlock, g, ctx->scal, (const double *)ctx->L[0].x, dcur);
@@ -1472,7 +1481,13 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         }
         // alpha = gamma / <s,d>: the kernel reads scal[0]/scal[1], so gamma must sit in slot 0
         if (ig != S_GAMMA0) { CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal + S_GAMMA0, ctx->scal + ig, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)); ig = S_GAMMA0; }
-        LAUNCH_COOP(ctx, k_update_xr, gux, dim3(UX_BLOCK), g, ctx->scal, (const double *)dcur, ctx->s, x, ctx->r, ctx->part);
+        if (defer_x) {
+            // deferred solution update (k_update_xr MODE 1 / 2): odd iterations touch r only, even ones add both pending directions to x
+            if (!x_pending) LAUNCH_COOP(ctx, k_update_xr<1>, gux, dim3(UX_BLOCK), g, ctx->scal, (const double *)dcur, ctx->s, x, ctx->r, ctx->part, (const double *)nullptr, ctx->scal + S_ALPHA_PREV);
+            else LAUNCH_COOP(ctx, k_update_xr<2>, gux, dim3(UX_BLOCK), g, ctx->scal, (const double *)dcur, ctx->s, x, ctx->r, ctx->part, (const double *)dalt, ctx->scal + S_ALPHA_PREV);
+            x_pending = !x_pending;
+        } else
+            LAUNCH_COOP(ctx, k_update_xr<0>, gux, dim3(UX_BLOCK), g, ctx->scal, (const double *)dcur, ctx->s, x, ctx->r, ctx->part, (const double *)nullptr, (double *)nullptr);
         TRY(reduce_final(ctx, RED_SUM, (long long)gux.x * gux.y, 1, 0, S_IPROD));
         TRY(fetch_scalars(ctx, S_IPROD, 1));
         i_prod = ctx->h_scal[S_IPROD];
@@ -1482,6 +1497,7 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
             // Optional: eps = 1e-14 is below what FP64 can deliver on large grids; the recurrence residual keeps
             // falling while b - A x does not.  Every third iteration compare the two; stop when the true residual is an
             // order of magnitude above the recurrence value and no longer improving.
+            TRY(flush_x());
             TRY(exchange_rows(ctx, x, g, 2));
             LAUNCH(ctx, k_residual, gres, kBlock, A, rhs, (const double *)x, ctx->s);
             LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->s, ctx->s, ctx->part);
@@ -1500,6 +1516,7 @@ static int pcg_solve(impec_ctx *ctx, Cycle &C, const double *rhs, double *x, dou
         ig = S_BETA_NUM;
     }
     // true residual with the final x
+    TRY(flush_x());
     TRY(exchange_rows(ctx, x, g, 2));
     { const int rrows = 64;
       const dim3 grn((unsigned)((g.N2 + BX - 1) / BX), (unsigned)((g.N1 + rrows - 1) / rrows));
@@ -2061,7 +2078,9 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "pcg_matvec" && ctx->matvec_march) { LAUNCH_COOP(ctx, k_pcg_matvec_march<false>, matvec_march_grid(g), dim3(MV_BLOCK), chunked(C.D[0], 0, 1, ctx->pf_mv), (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part, matvec_march_rows(g)); return IMPEC_OK; }
         if (k == "pcg_matvec") { LAUNCH_COOP_SMEM(ctx, k_pcg_matvec<false>, fused_grid<FUSED_PLAIN>(g), kFusedBlock, kFusedSmem, C.D[0], (const double *)(ctx->scal + S_TMP), (const double *)L0.x, (const double *)ctx->d, ctx->d2buf, ctx->s, ctx->part); return IMPEC_OK; }
         if (k == "matvec_dot") { LAUNCH_COOP(ctx, k_matvec_dot, gr, kBlock, C.D[0], ctx->d, ctx->s, ctx->part); return IMPEC_OK; }
-        if (k == "update_xr") { LAUNCH_COOP(ctx, k_update_xr, update_xr_grid(g), dim3(UX_BLOCK), g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part); return IMPEC_OK; }
+        if (k == "update_xr") { LAUNCH_COOP(ctx, k_update_xr<0>, update_xr_grid(g), dim3(UX_BLOCK), g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part, (const double *)nullptr, (double *)nullptr); return IMPEC_OK; }
+        if (k == "update_r") { LAUNCH_COOP(ctx, k_update_xr<1>, update_xr_grid(g), dim3(UX_BLOCK), g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part, (const double *)nullptr, ctx->scal + S_ALPHA_PREV); return IMPEC_OK; }
+        if (k == "update_xxr") { LAUNCH_COOP(ctx, k_update_xr<2>, update_xr_grid(g), dim3(UX_BLOCK), g, ctx->scal + S_TMP, ctx->d, ctx->s, ctx->t0, ctx->rhs, ctx->part, (const double *)ctx->d2buf, ctx->scal + S_ALPHA_PREV); return IMPEC_OK; }
         if (k == "dot") { LAUNCH_COOP(ctx, k_dot, gr, kBlock, g, ctx->r, ctx->z, ctx->part); return IMPEC_OK; }
         if (k == "update_d") { LAUNCH(ctx, k_update_d<false>, gr, kBlock, g, ctx->scal + S_TMP, ctx->z, ctx->d); return IMPEC_OK; }
         if (k == "vcycle") return mg_cycle(C, 0, ctx->r);
@@ -2079,7 +2098,7 @@ extern "C" int impec_profile_kernel(impec_ctx *ctx, const char *name, int reps, 
         if (k == "calc_velocities") return impec_calc_velocities(ctx);
         return fail(ctx, IMPEC_ERR_ARG, "unknown kernel name '%s'", k.c_str());
     };
-    if (k == "update_xr" || k == "update_d" || k == "pcg_matvec") {      // alpha = beta = 0/1 so the vectors stay finite
+    if (k == "update_xr" || k == "update_r" || k == "update_xxr" || k == "update_d" || k == "pcg_matvec") {      // alpha = beta = 0/1 so the vectors stay finite
         LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_TMP, 0.0);
         LAUNCH(ctx, k_set_scalar, dim3(1), dim3(1), ctx->scal + S_TMP + 1, 1.0);
     }

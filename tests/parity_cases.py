@@ -302,6 +302,24 @@ def check_horizontal_front(emulated, N1=48, N2=32, diffusion=0, steps=2, links_f
     ctx.close()
 
 
+def check_deferred_solution_update(emulated, N1=48, N2=80, stype=O.DIAGONAL, diffusion=1):
+    """PCG with the solution update of two iterations merged (k_update_xr MODE 1 / 2, option "defer_x") against the plain form: the
+    same operations on x in the same order, so pressure and concentration are BIT-IDENTICAL, for even and odd iteration counts."""
+    base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=diffusion)
+    out = {}
+    for eps in (1e-6, 1e-9, 1e-12):                      # different tolerances: the solve ends on either parity of the iteration count
+        for defer in (1, 0):
+            Pi = I.default_params(emulated=emulated, **dict(base, eps=eps))
+            ctx = I.Context(Pi, emulated=emulated)
+            ctx.set_option("defer_x", defer)
+            ctx.upload_c(c); ctx.upload_q(q)
+            dt, info = ctx.impes_step(0.0, 0.0)
+            out[(eps, defer)] = (ctx.download_p(), ctx.download_c(), info.iterations)
+            ctx.close()
+        a, b = out[(eps, 1)], out[(eps, 0)]
+        assert a[2] == b[2] and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (eps, a[2], b[2], np.abs(a[0] - b[0]).max())
+
+
 def check_horizontal_generators(emulated):
     """InitHorizontalFront with constant, pulsing and linearly ramped injection (src/Util.cpp:607-639): library == oracle bit for bit."""
     lib = O.lib()

@@ -88,3 +88,6 @@ def test_marching_kernels_awkward_extents(monkeypatch, N1, N2):
     monkeypatch.setenv("IMPEC_MARCH_MIN_CELLS", "0")
     pc.check_impes_step(True, N1, N2, stype=O.DIAGONAL, steps=1)
     pc.check_march_vs_tiles(True, N1, N2, stype=O.DIAGONAL)
+
+
+def test_deferred_solution_update_bitexact(): pc.check_deferred_solution_update(True, 48, 80)

@@ -252,3 +252,6 @@ def test_dispersion_anisotropic_tensor(): pc.check_dispersion(False, 320, 256, s
 @pytest.mark.parametrize("N1,N2,stype", [(30, 21, O.DIAGONAL), (21, 30, O.DIAGONAL), (6, 6, O.PARALLEL), (4, 4, O.DIAGONAL), (50, 36, O.DIAGONAL)])
 def test_impes_step_ragged_and_tiny_grids(N1, N2, stype): pc.check_impes_step(False, N1, N2, stype=stype, steps=1)
 def test_horizontal_front_tiny_grid(): pc.check_horizontal_front(False, 12, 8, steps=1)
+
+
+def test_deferred_solution_update_bitexact(): pc.check_deferred_solution_update(False, 1024, 1536)
