@@ -585,6 +585,7 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     if (cuda_stream) ctx->stream = (cudaStream_t)cuda_stream;
     else { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     { const char *e = getenv("IMPEC_HALO_OVERLAP"); if (e) ctx->overlap = atoi(e) != 0; }
+    { const char *e = getenv("IMPEC_DEFER_X"); if (e) ctx->defer_x = atoi(e) != 0; }
     { const char *e = getenv("IMPEC_SWEEP_PREFETCH"); if (e) ctx->pf_sweep = atoi(e); }
     { const char *e = getenv("IMPEC_SWEEP_Y_PAIRS"); if (e) ctx->sweep_y_pairs = atoi(e) != 0; }
     { const char *e = getenv("IMPEC_L2_PREFETCH");
