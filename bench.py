@@ -352,7 +352,7 @@ def main():
     # ------------------------------------------------------------------ per-kernel device times (CUDA events, live)
     prof = {}
     if kind == "impes":
-        names = (("vcycle", 5), ("fused_pre", 10), ("fused_post", 10), ("fused_plain", 10), ("pcg_matvec", 10), ("update_xr", 10),
+        names = (("vcycle", 5), ("fused_pre", 10), ("fused_post", 10), ("fused_plain", 10), ("pcg_matvec", 10), ("update_xr", 10), ("update_r", 10), ("update_xxr", 10),
                  ("sweep_x", 10), ("sweep_y", 10), ("build_operator", 5), ("calc_velocities", 5), ("transport_step", 3))
     else:
         names = (("sweep_x", 10), ("sweep_y", 10), ("transport_step", 5))
@@ -381,7 +381,9 @@ def main():
     #   k_pcg_matvec_march       : R z,d,AW,AS,AV (40) + W d,s (16)                                = 56 B/cell
     #   k_update_xr 48;  k_muscl_x / k_muscl_y: R c,vel + W c = 24 B/cell
     cells = float(N) * N / world                   # cells per GPU: the kernels are timed on this rank's slab
-    kb = {"fused_post": 42.0, "fused_pre": 34.0, "fused_plain": 40.0, "pcg_matvec": 56.0, "update_xr": 48.0, "sweep_x": 24.0, "sweep_y": 24.0}
+    #   k_update_xr<0> 48; the solve runs <1> (r only, 24) and <2> (x with both pending directions + r, 56) alternately: 80 per two iterations
+    kb = {"fused_post": 42.0, "fused_pre": 34.0, "fused_plain": 40.0, "pcg_matvec": 56.0, "update_xr": 48.0, "update_r": 24.0, "update_xxr": 56.0,
+          "sweep_x": 24.0, "sweep_y": 24.0}
     per_kernel = {k: {"ms": prof[k], "algorithmic_bytes": kb[k] * cells, "achieved_gbs": kb[k] * cells / (prof[k] * 1e-3) / 1e9,
                       "frac": kb[k] * cells / (prof[k] * 1e-3) / 1e9 / peak} for k in kb if k in prof}
     step_s = ms_total / K * 1e-3 * world           # GPU-seconds per step
@@ -417,11 +419,11 @@ def main():
         cn = 0.0
         if WORKLOADS[wl]["diffusion"]:
             # per CN half step: links 32 + DINV/FP32 copies 56 + rhs 40 + n_cn (k_sgs_march 34 + mat-vec 56 + update 48) + copy-out 16; two per step
-            cn = 2.0 * (32.0 + 56.0 + 40.0 + 9.0 * (34.0 + 56.0 + 48.0) + 16.0)
+            cn = 2.0 * (32.0 + 56.0 + 40.0 + 9.0 * (34.0 + 56.0 + 40.0) + 16.0)
         step_model = (32.0 + its_mean * (208.0 + 128.0) + 48.0 + 128.0) * NN
         # operator build 74 (one march c -> links, DINV, FP32 copies: 48; coarsening of the links down the hierarchy: 26), per PCG iteration the
-        # cycle 113.3 + mat-vec 56 + update 48, velocity + CFL 32 (+ 8 ghost fills), transport 4 x 24 (+ 8 source / fills)
-        step_moved = (ctx_option_bytes_operator() + its_mean * (113.3 + 56.0 + 48.0) + 40.0 + 104.0 + cn) * NN
+        # cycle 113.3 + mat-vec 56 + update 40 (24 and 56 alternately: deferred solution update), velocity + CFL 32 (+ 8 ghost fills), transport 4 x 24 (+ 8 source / fills)
+        step_moved = (ctx_option_bytes_operator() + its_mean * (113.3 + 56.0 + 40.0) + 40.0 + 104.0 + cn) * NN
         roofline["vcycle"] = {"ms": prof["vcycle"], "moved_bytes": vc_moved, "achieved_moved": vc_moved / (prof["vcycle"] * 1e-3) / 1e9,
                               "frac_moved": vc_moved / (prof["vcycle"] * 1e-3) / 1e9 / peak,
                               "survey_model_bytes": vc_model, "frac_survey_model": vc_model / (prof["vcycle"] * 1e-3) / 1e9 / peak}
