@@ -19,6 +19,8 @@
 #include <cstdarg>
 #include <algorithm>
 #include <thread>
+#include <atomic>
+#include <functional>
 
 #define BX 32
 #define BY 8
@@ -61,6 +63,8 @@ struct impec_ctx {
     double *h_scal = nullptr;                       // pinned host mirror
     // wells
     int nwell = 0, well_cap = 0; int *well_i = nullptr, *well_j = nullptr; double *well_q = nullptr, *well_md = nullptr;
+    int *hw_i = nullptr, *hw_j = nullptr; double *hw_q = nullptr; long long hw_cap = 0;    // pinned staging of the compact well list (scan_wells)
+    cudaEvent_t ev_wells = nullptr;                 // recorded after the copies out of the staging buffers
     double q_pin = 0.0; bool have_q = false;
     int prev_first_sweep = 1;                       // Y_SWEEP (src/HyperbolicSolver.cpp:84)
     bool mob_valid = false, op_valid = false;
@@ -563,6 +567,10 @@ extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
 #endif
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+    for (void *p : {(void *)ctx->hw_i, (void *)ctx->hw_j, (void *)ctx->hw_q}) if (p) cudaFreeHost(p);
+#ifndef IMPEC_EMU
+    if (ctx->ev_wells) cudaEventDestroy(ctx->ev_wells);
+#endif
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -749,6 +757,11 @@ extern "C" int impec_set_option(impec_ctx *ctx, const char *key, double value) {
     if (k == "sweep_y_pairs") { ctx->sweep_y_pairs = value != 0.0; return IMPEC_OK; }
     if (k == "sweep_prefetch") { ctx->pf_sweep = (int)value; return IMPEC_OK; }
     if (k == "l2_prefetch") { ctx->pf_pre = ctx->pf_post = ctx->pf_mv = ctx->pf_sgs = (int)value; return IMPEC_OK; }
+    if (k.rfind("mg_march_rows@", 0) == 0) {           // chunk height of the marching kernels on one level (tuning; the level must already march)
+        const int l = atoi(k.c_str() + 14), r = (int)value;
+        if (l < 0 || l >= (int)ctx->L.size() || ctx->L[l].march_rows <= 0 || r < 16 || r % 4) return fail(ctx, IMPEC_ERR_ARG, "mg_march_rows: level %d does not march or %d is not a multiple of 4 >= 16", l, r);
+        ctx->L[l].march_rows = r; ctx->graph_ready = false; return IMPEC_OK;
+    }
     if (k == "mg_march") { ctx->march = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "mg_fused_mid") { ctx->fused_mid = value != 0.0; ctx->graph_ready = false; return IMPEC_OK; }
     if (k == "matvec_march") { ctx->matvec_march = value != 0.0; return IMPEC_OK; }
@@ -803,37 +816,69 @@ __global__ void k_scatter_wells(int n, const int *__restrict__ wi, const int *__
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) q[gidx(g, wi[t], wj[t])] = wq[t];
 }
-static int scan_wells(impec_ctx *ctx, const double *q, std::vector<int> &wi, std::vector<int> &wj, std::vector<double> &wq) {
+// Non-zero cells of rows [i0, i1) of a dense row-major array; FILL = false only counts.  Blocks of 32 values that are all +-0.0 (OR of the
+// bit patterns without the sign bit) are skipped without a per-element branch: the scan runs at memory speed where q is zero, i.e. almost
+// everywhere.
+template <bool FILL> static long long scan_rows_nonzero(const double *q, int N2, int i0, int i1, int *oi, int *oj, double *oq) {
+    long long n = 0;
+    for (int i = i0; i < i1; i++) {
+        const double *row = q + (size_t)i * N2;
+        const unsigned long long *bits = reinterpret_cast<const unsigned long long *>(row);
+        int j = 0;
+        for (; j + 32 <= N2; j += 32) {
+            unsigned long long a = 0;
+            for (int e = 0; e < 32; e++) a |= bits[j + e];
+            if ((a << 1) == 0) continue;
+            for (int e = 0; e < 32; e++) { const double v = row[j + e]; if (v != 0.0) { if (FILL) { oi[n] = i; oj[n] = j + e; oq[n] = v; } n++; } }
+        }
+        for (; j < N2; j++) { const double v = row[j]; if (v != 0.0) { if (FILL) { oi[n] = i; oj[n] = j; oq[n] = v; } n++; } }
+    }
+    return n;
+}
+// Compact list of the non-zero cells of q in row-major order, written into the context's pinned staging buffers (hw_i / hw_j / hw_q).
+// Two passes over chunks of 16 rows that the host threads pull from a shared counter (the wells sit in a few row blocks: a static
+// partition leaves most threads idle while one or two collect every entry): count per chunk, prefix sum, fill in place.  Only chunks
+// that hold a well are read twice.
+static int scan_wells(impec_ctx *ctx, const double *q, long long *nwell) {
     const int N1 = ctx->g.N1, N2 = ctx->P.N2;
+    const int R = 16, nch = (N1 + R - 1) / R;
     unsigned nt = std::thread::hardware_concurrency();
-    if (nt < 1) nt = 1; if (nt > 64) nt = 64; if ((int)nt > N1) nt = (unsigned)N1;
-    std::vector<std::vector<int> > ti(nt), tj(nt); std::vector<std::vector<double> > tq(nt);
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; t++)
-        th.emplace_back([&, t]() {
-            const int r0 = (int)((long long)N1 * t / nt), r1 = (int)((long long)N1 * (t + 1) / nt);     // contiguous row blocks keep row-major order
-            for (int i = r0; i < r1; i++) {
-                const double *row = q + (size_t)i * N2;
-                const unsigned long long *bits = reinterpret_cast<const unsigned long long *>(row);
-                int j = 0;
-                // blocks of 16 values that are all +-0.0 (OR of the bit patterns without the sign bit) are skipped without a per-element
-                // branch: the scan runs at memory speed where q is zero, i.e. almost everywhere
-                for (; j + 16 <= N2; j += 16) {
-                    unsigned long long a = 0;
-                    for (int e = 0; e < 16; e++) a |= bits[j + e];
-                    if ((a << 1) == 0) continue;
-                    for (int e = 0; e < 16; e++) { const double v = row[j + e]; if (v != 0.0) { ti[t].push_back(i); tj[t].push_back(j + e); tq[t].push_back(v); } }
-                }
-                for (; j < N2; j++) { const double v = row[j]; if (v != 0.0) { ti[t].push_back(i); tj[t].push_back(j); tq[t].push_back(v); } }
-            }
-        });
-    for (auto &x : th) x.join();
-    for (unsigned t = 0; t < nt; t++) { wi.insert(wi.end(), ti[t].begin(), ti[t].end()); wj.insert(wj.end(), tj[t].begin(), tj[t].end()); wq.insert(wq.end(), tq[t].begin(), tq[t].end()); }
+    if (ctx->nranks > 1) nt /= (unsigned)std::min(ctx->nranks, 8);          // the ranks of one node share its cores
+    if (nt < 2) nt = 2; if (nt > 64) nt = 64; if ((int)nt > nch) nt = (unsigned)nch;
+    std::vector<long long> off((size_t)nch + 1, 0);
+    std::atomic<int> next(0);
+    auto run = [&](const std::function<void(int)> &body) {
+        next = 0;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back([&]() { for (;;) { const int c = next.fetch_add(1); if (c >= nch) break; body(c); } });
+        for (auto &x : th) x.join();
+    };
+    run([&](int c) { off[c] = scan_rows_nonzero<false>(q, N2, c * R, std::min(N1, (c + 1) * R), nullptr, nullptr, nullptr); });
+    long long tot = 0;
+    for (int c = 0; c < nch; c++) { const long long n = off[c]; off[c] = tot; tot += n; }
+    off[nch] = tot;
+    if (tot > 0x7fffffffLL) return fail(ctx, IMPEC_ERR_ARG, "source term with more than 2^31 non-zero cells");
+#ifndef IMPEC_EMU
+    // the staging buffers may still be the source of the previous upload's copies
+    if (ctx->ev_wells) CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_wells));
+#endif
+    if (tot > ctx->hw_cap) {
+        for (void *old : {(void *)ctx->hw_i, (void *)ctx->hw_j, (void *)ctx->hw_q}) if (old) cudaFreeHost(old);
+        ctx->hw_i = ctx->hw_j = nullptr; ctx->hw_q = nullptr; ctx->hw_cap = 0;
+        const long long cap = tot + tot / 8 + 1024;
+        CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->hw_i, sizeof(int) * (size_t)cap));
+        CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->hw_j, sizeof(int) * (size_t)cap));
+        CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->hw_q, sizeof(double) * (size_t)cap));
+        ctx->hw_cap = cap;
+    }
+    if (tot) run([&](int c) { if (off[c + 1] > off[c]) scan_rows_nonzero<true>(q, N2, c * R, std::min(N1, (c + 1) * R), ctx->hw_i + off[c], ctx->hw_j + off[c], ctx->hw_q + off[c]); });
+    *nwell = tot;
     return IMPEC_OK;
 }
-static int set_wells(impec_ctx *ctx, const double *q, const std::vector<int> &wi, const std::vector<int> &wj, const std::vector<double> &wq) {
+// device copies of the compact list (asynchronous, from the pinned staging buffers)
+static int set_wells(impec_ctx *ctx, const double *q, long long nwell) {
     const int N1 = ctx->g.N1, N2 = ctx->P.N2;
-    ctx->nwell = (int)wq.size();
+    ctx->nwell = (int)nwell;
     ctx->q_pin = (ctx->rank == 0 && N1 > 1 && N2 > 1) ? q[(size_t)1 * N2 + 1] : 0.0;
     if (ctx->nwell) {
         if (ctx->nwell > ctx->well_cap) {                           // grow (rare): buffers are reused across uploads
@@ -845,9 +890,13 @@ static int set_wells(impec_ctx *ctx, const double *q, const std::vector<int> &wi
             CUDA_TRY(ctx, cudaMalloc(&p, sizeof(double) * ctx->nwell)); ctx->well_md = (double *)p;
             ctx->well_cap = ctx->nwell;
         }
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_i, wi.data(), sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_j, wj.data(), sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_q, wq.data(), sizeof(double) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_i, ctx->hw_i, sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_j, ctx->hw_j, sizeof(int) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->well_q, ctx->hw_q, sizeof(double) * ctx->nwell, cudaMemcpyHostToDevice, ctx->stream));
+#ifndef IMPEC_EMU
+        if (!ctx->ev_wells) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_wells, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_wells, ctx->stream));
+#endif
         ctx->bytes_h2d += (size_t)ctx->nwell * (2 * sizeof(int) + sizeof(double));
     }
     ctx->have_q = true;
@@ -855,18 +904,18 @@ static int set_wells(impec_ctx *ctx, const double *q, const std::vector<int> &wi
 }
 extern "C" int impec_upload_q_rows(impec_ctx *ctx, const double *q) {
     const Grid &g = ctx->g;
-    std::vector<int> wi, wj; std::vector<double> wq;
-    TRY(scan_wells(ctx, q, wi, wj, wq));
-    TRY(set_wells(ctx, q, wi, wj, wq));
+    long long nw = 0;
+    TRY(scan_wells(ctx, q, &nw));
+    TRY(set_wells(ctx, q, nw));
     if ((long long)ctx->nwell * 16 > (long long)g.N1 * g.N2) {      // dense source term: plain copy
         const size_t w = (size_t)g.N2 * sizeof(double);
         CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->q + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), q, w, w, (size_t)g.N1, cudaMemcpyHostToDevice, ctx->stream));
         ctx->bytes_h2d += w * (size_t)g.N1;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));          // the caller may reuse q at return (pageable memory is staged, pinned is not)
     } else {
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->q, 0, grid_elems(g) * sizeof(double), ctx->stream));
         if (ctx->nwell) LAUNCH(ctx, k_scatter_wells, dim3((unsigned)((ctx->nwell + 255) / 256)), dim3(256), ctx->nwell, ctx->well_i, ctx->well_j, ctx->well_q, g, ctx->q);
     }
-    if (ctx->nwell) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // the host vectors die at return
     return IMPEC_OK;
 }
 extern "C" int impec_upload_q(impec_ctx *ctx, const double *q) { return impec_upload_q_rows(ctx, q + (size_t)ctx->g.i_off * ctx->g.N2); }
@@ -876,10 +925,9 @@ extern "C" int impec_set_q_dev_changed(impec_ctx *ctx) {
     const size_t w = (size_t)g.N2 * sizeof(double);
     CUDA_TRY(ctx, cudaMemcpy2DAsync(q.data(), w, ctx->q + gidx(g, 0, 0), (size_t)g.ld * sizeof(double), w, (size_t)g.N1, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<int> wi, wj; std::vector<double> wq;
-    TRY(scan_wells(ctx, q.data(), wi, wj, wq));
-    TRY(set_wells(ctx, q.data(), wi, wj, wq));
-    if (ctx->nwell) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    long long nw = 0;
+    TRY(scan_wells(ctx, q.data(), &nw));
+    TRY(set_wells(ctx, q.data(), nw));
     return IMPEC_OK;
 }
 extern "C" int impec_upload_velocity(impec_ctx *ctx, const double *v_aos) {

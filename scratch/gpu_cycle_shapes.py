@@ -7,7 +7,7 @@ P = I.default_params(N1=N, N2=N, x_ub=1.41421356237, y_ub=1.41421356237, stype=0
 c = I.synth_state(P); q = I.init_source(P)
 out = {}
 ctx = I.Context(P); ctx.upload_c(c); ctx.upload_q(q)
-for (wf, wt) in ((2, 4), (2, 3), (1, 2), (1, 3), (1, 1), (2, 2), (0, 1), (5, 4)):
+for (wf, wt) in ((2, 4), (2, 3), (3, 4), (3, 3), (2, 2), (4, 4), (1, 3), (5, 4)):
     ctx.set_option("mg_w_from", wf); ctx.set_option("mg_w_to", wt)
     ctx.reset_state(); ctx.upload_c(c)
     t = 0.0; its = []
@@ -19,4 +19,4 @@ for (wf, wt) in ((2, 4), (2, 3), (1, 2), (1, 3), (1, 1), (2, 2), (0, 1), (5, 4))
     vc = ctx.profile_kernel("vcycle", 5); tl = ctx.profile_kernel("tail", 20)
     out["w%d-%d" % (wf, wt)] = {"ms_per_step": ms, "iterations": its, "vcycle_ms": vc, "tail_visit_ms": tl, "true_relres": info.true_relres}
     print("W levels %d..%d: %.1f ms/step its %s vcycle %.2f ms tail visit %.3f ms true %.2e" % (wf, wt, ms, its, vc, tl, info.true_relres), flush=True)
-json.dump(out, open('gpurun_out/cycle_shapes.json', 'w'), indent=1)
+json.dump(out, open('gpurun_out/r2x_cycle_shapes.json', 'w'), indent=1)

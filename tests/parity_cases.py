@@ -214,6 +214,38 @@ def check_source_step(emulated, N=32):
     ctx.close()
 
 
+def check_scattered_sources(emulated, N1=70, N2=45):
+    """impec_upload_q: the dense host array is scanned in 16-row chunks / 32-value blocks and only its non-zero cells are copied.
+    Sources scattered over chunk and block edges, a ragged row length, +-0.0 entries, negative rates, and three uploads of
+    different sizes in a row (staging buffers regrown and reused): every source step must equal the oracle's bit for bit."""
+    lib = O.lib()
+    base, Po, c, q0 = production_case(N1, N2)
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    rng = np.random.default_rng(11)
+    interior(Po, c)[...] = rng.random((N1, N2))
+    ctx.upload_c(c)
+    co = c.copy()
+    md = 0.0
+    for density in (0.002, 0.05, 0.0005):
+        q = np.zeros((N1, N2))
+        mask = rng.random((N1, N2)) < density
+        mask[[0, 15, 16, 31, 32, N1 - 1], :] |= rng.random((6, N2)) < 0.2          # chunk edges
+        mask[:, [0, 31, 32, N2 - 1]] |= rng.random((N1, 4)) < 0.2                  # block edges and the ragged tail
+        q[mask] = rng.standard_normal(int(mask.sum()))
+        q[~mask & (rng.random((N1, N2)) < 0.3)] = -0.0                             # negative zeros are not sources
+        qf = np.ascontiguousarray(q.reshape(-1))
+        ctx.upload_q(qf)
+        md += abs(lib.orc_tr_integrate(C.byref(Po), co, qf, 1e-3))
+        ctx.source_split(1e-3)
+        assert np.array_equal(ctx.download_c(), co), density
+    assert abs(ctx.diagnostics().total_mass_outflux - md) <= 1e-13 * abs(md)
+    ctx.upload_q(np.zeros(N1 * N2))                                                # no source at all
+    ctx.source_split(1e-3)
+    assert np.array_equal(ctx.download_c(), co)
+    ctx.close()
+
+
 def check_vcycle(emulated, N1=32, N2=32, stype=O.PARALLEL, nu=2.0 / 3.0):
     lib = O.lib()
     base, Po, c, q = production_case(N1, N2, stype=stype, nu=nu)

@@ -36,6 +36,7 @@ def test_advection_other_splittings_bitexact(split): pc.check_advection_bitexact
 def test_projection_parallel_to_diagonal(): pc.check_projection(True)
 def test_checkpoint_restart(tmp_path): pc.check_checkpoint_restart(True, tmp_path)
 def test_source_step(): pc.check_source_step(True, N=32)
+def test_scattered_sources(): pc.check_scattered_sources(True)
 def test_vcycle_parallel(): pc.check_vcycle(True, 32, 32)
 def test_vcycle_rect_diagonal(): pc.check_vcycle(True, 32, 16, stype=O.DIAGONAL)
 def test_impes_step_parallel(): pc.check_impes_step(True, 32, 32, steps=1)

@@ -35,6 +35,7 @@ def test_advection_other_splittings_bitexact(split): pc.check_advection_bitexact
 def test_projection_parallel_to_diagonal(): pc.check_projection(False, N=700)
 def test_checkpoint_restart(tmp_path): pc.check_checkpoint_restart(False, tmp_path, N=256)
 def test_source_step(): pc.check_source_step(False, N=128)
+def test_scattered_sources(): pc.check_scattered_sources(False)
 def test_fused_vs_unfused_cycle(): pc.check_fused_vs_unfused(False, 1024, 1536)
 def test_matvec_march_vs_tiles(): pc.check_matvec_variants(False, 1152, 2064)
 def test_matvec_march_odd_columns(): pc.check_matvec_variants(False, 20, 31, eps=1e-9)
