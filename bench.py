@@ -273,6 +273,8 @@ def main():
         raise SystemExit("bench.py: %s at %d^2 needs ~%.0f GB per GPU on %d GPU(s); use more GPUs or --size" % (wl, N, need_gb, world))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                  # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # a dedicated (non-default) stream shared by the library, the timing events and torch's collectives: the library keeps a NULL
     # stream argument for "create my own", so the legacy default stream cannot be handed to it
