@@ -230,6 +230,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="library option for A/B runs (impec_set_option), e.g. mg_w_to=3; recorded in the line's run.options")
     ap.add_argument("--profile-mode", action="store_true", help="for runs under ncu: honour --warmup as given, skip e2e / cpu baseline / kernel timing (numbers printed in this mode are not bench values)")
     args = ap.parse_args()
 
@@ -294,6 +295,9 @@ def main():
         dist.broadcast(idt, src=0)
         nccl_id = bytes(idt.cpu().tolist())
     ctx = I.Context(P, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id, stream=C.c_void_p(stream.cuda_stream))
+    options = {}
+    for kv in args.opt:
+        k, v = kv.split("="); ctx.set_option(k, float(v)); options[k] = float(v)
     row0, nrows = ctx.local_rows()
     # host inputs in pinned memory (reference layouts, this rank's rows)
     shape = (nrows + 2 * P.g, N + 2 * P.g)
@@ -473,6 +477,8 @@ def main():
                "parallelism": "1 GPU" if world == 1 else "%d slabs of %d rows along x; halo rows and scalar reductions over %s; multigrid levels below 4M cells replicated after an all-gather" % (world, nrows, ctx.comm_backend()),
                "coefficients": "multigrid cycle reads FP32 copies of the link/diagonal arrays (all arithmetic FP64; PCG mat-vec uses the FP64 operator)"}
         run["halo_exchanges_overlapped_with_interior_chunks"] = int(ctx.overlapped_exchanges())
+        if options:
+            run["options"] = options                       # non-default library options of this run (A/B measurements)
         if kind == "impes":
             run.update({"pcg_iterations": its, "relres": relres, "true_relres": true_rr})
         line = {"metric": metric, "value": value, "unit": "Gcell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
