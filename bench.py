@@ -473,7 +473,7 @@ def main():
         _, _, cpu_baseline, _ = cpu_arm(wl, N, 2, 1, args.eps, CPU_BUDGET_BASELINE_S)
 
     if rank == 0:
-        run = {"mg_levels": ctx.mg_levels(), "comm_backend": ctx.comm_backend(),
+        run = {"mg_levels": ctx.mg_levels(), "mg_w_range": list(ctx.mg_w_range()), "comm_backend": ctx.comm_backend(),
                "parallelism": "1 GPU" if world == 1 else "%d slabs of %d rows along x; halo rows and scalar reductions over %s; multigrid levels below 4M cells replicated after an all-gather" % (world, nrows, ctx.comm_backend()),
                "coefficients": "multigrid cycle reads FP32 copies of the link/diagonal arrays (all arithmetic FP64; PCG mat-vec uses the FP64 operator)"}
         run["halo_exchanges_overlapped_with_interior_chunks"] = int(ctx.overlapped_exchanges())

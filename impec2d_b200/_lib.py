@@ -65,7 +65,7 @@ EXPORTS = [
     "impec_field_dev", "impec_set_q_dev_changed", "impec_fill_boundaries", "impec_pressure_solve", "impec_calc_velocities",
     "impec_max_stable_dt", "impec_source_split", "impec_advect_x", "impec_advect_y", "impec_advect_split", "impec_intercell_flux", "impec_gather_rows",
     "impec_diffusion_split", "impec_transport_step", "impec_impes_step", "impec_diagnostics", "impec_integral_diagnostics", "impec_build_operator",
-    "impec_vcycle", "impec_mg_levels", "impec_kernel_launches", "impec_overlapped_exchanges", "impec_last_parabolic_info", "impec_reset_state", "impec_set_option",
+    "impec_vcycle", "impec_mg_levels", "impec_mg_w_range", "impec_kernel_launches", "impec_overlapped_exchanges", "impec_last_parabolic_info", "impec_reset_state", "impec_set_option",
     "impec_profile_kernel", "impec_init_source", "impec_init_horizontal_front", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
     "impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows", "impec_init_source_rows", "impec_synth_state_rows",
     "impec_comm_backend", "impec_transfer_bytes", "impec_project_dims", "impec_project_to_diagonal", "impec_checkpoint_save", "impec_checkpoint_load",
@@ -138,6 +138,7 @@ def load(emulated=False):
     L.impec_checkpoint_load.argtypes = [vp, C.c_char_p, dptr, C.POINTER(C.c_longlong)]
     L.impec_vcycle.argtypes = [vp, vp, vp]
     L.impec_mg_levels.argtypes = [vp]
+    L.impec_mg_w_range.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.impec_intercell_flux.argtypes = [vp, i, d, vp]
     L.impec_gather_rows.argtypes = [vp, C.c_char_p, vp]
     L.impec_kernel_launches.argtypes = [vp]; L.impec_kernel_launches.restype = C.c_longlong

@@ -169,6 +169,11 @@ class Context:
         return z
 
     def mg_levels(self): return self.L.impec_mg_levels(self._h)
+
+    def mg_w_range(self):
+        a, b = C.c_int(), C.c_int()
+        self._chk(self.L.impec_mg_w_range(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
     def kernel_launches(self): return self.L.impec_kernel_launches(self._h)
     def last_parabolic_info(self):
         info = _lib.SolveInfo(); self._chk(self.L.impec_last_parabolic_info(self._h, C.byref(info))); return info

@@ -581,6 +581,16 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     impec_ctx *ctx = new impec_ctx();
     *out = ctx;                                   // returned even on failure so that the error text can be read
     ctx->P = *P; ctx->device = device; ctx->rank = rank; ctx->nranks = nranks;
+    // Cycle shape by rank count.  The multigrid levels below 4 M cells are replicated on every rank, so their cost does not shrink with the
+    // number of GPUs; once a slab is small enough that this tail is a third of the cycle, entering it 4 x 1 instead of 4 x 2 times per cycle
+    // (W range 2..3 instead of the default 2..4) more than pays for the extra PCG iterations: 16384^2 on 8 B200, 23 iterations at 57.8 ms per
+    // step against 20 at 60.5 (profiles/r2ad_*); on 1 / 2 / 4 GPUs (and for larger slabs) the default range stays the faster one
+    // (profiles/r2x_cycle_shapes.txt).  Only the default range is touched; impec_set_option("mg_w_to", ..) overrides, IMPEC_W_RANGE_AUTO=0 disables.
+    {
+        const char *e = getenv("IMPEC_W_RANGE_AUTO");
+        const double cells_per_rank = (double)P->N1 * P->N2 / (nranks > 0 ? nranks : 1);
+        if ((!e || atoi(e) != 0) && nranks >= 8 && P->mg_w_from == 2 && P->mg_w_to == 4 && cells_per_rank >= 1.0e7 && cells_per_rank <= 5.0e7) ctx->P.mg_w_to = 3;
+    }
     if (P->g != 2) return fail(ctx, IMPEC_ERR_ARG, "num_ghostcells must be 2 (got %d)", P->g);
     if (P->N1 < 4 || P->N2 < 4) return fail(ctx, IMPEC_ERR_ARG, "grid too small: %d x %d", P->N1, P->N2);
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, IMPEC_ERR_ARG, "bad rank %d of %d", rank, nranks);
@@ -735,6 +745,7 @@ extern "C" const char *impec_comm_backend(const impec_ctx *ctx) {
 
 extern "C" int impec_synchronize(impec_ctx *ctx) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); return IMPEC_OK; }
 extern "C" int impec_mg_levels(const impec_ctx *ctx) { return (int)ctx->L.size(); }
+extern "C" int impec_mg_w_range(const impec_ctx *ctx, int *from, int *to) { if (!ctx || !from || !to) return IMPEC_ERR_ARG; *from = ctx->P.mg_w_from; *to = ctx->P.mg_w_to; return IMPEC_OK; }
 extern "C" long long impec_kernel_launches(const impec_ctx *ctx) { return ctx->launches; }
 extern "C" int impec_last_parabolic_info(const impec_ctx *ctx, impec_solve_info *info) { if (!ctx || !info) return IMPEC_ERR_ARG; *info = ctx->last_para; return IMPEC_OK; }
 extern "C" long long impec_overlapped_exchanges(const impec_ctx *ctx) { return ctx->overlapped; }

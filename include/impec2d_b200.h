@@ -61,7 +61,7 @@ typedef struct impec_params {
     int    mg_max_levels;             /* 0 = as deep as the grid allows                            */
     int    mg_nmin;                   /* stop coarsening once min(N1,N2) <= mg_nmin (default 4)    */
     int    mg_ncoarse;                /* symmetric GS sweeps on the coarsest level (default 8)     */
-    int    mg_w_from, mg_w_to;        /* levels visited twice per cycle (default 2..4)             */
+    int    mg_w_from, mg_w_to;        /* levels visited twice per cycle (default 2..4; see impec_mg_w_range) */
 } impec_params;
 
 typedef struct impec_diag {           /* src/Impec2DSolver.h:16-25 plus the per-step extrema        */
@@ -195,6 +195,7 @@ int   impec_checkpoint_load(impec_ctx *ctx, const char *path, double *t, long lo
 int   impec_build_operator(impec_ctx *ctx);                              /* a2-a8: links from the current c */
 int   impec_vcycle(impec_ctx *ctx, const double *r_host, double *z_host); /* one MG cycle; NULL/NULL = on the internal residual */
 int   impec_mg_levels(const impec_ctx *ctx);
+int   impec_mg_w_range(const impec_ctx *ctx, int *from, int *to);        /* levels the cycle visits twice, as in effect (8 or more ranks with 10-50 M cells each: 2..3 instead of the default 2..4) */
 long long impec_kernel_launches(const impec_ctx *ctx);                   /* kernels launched by this context so far */
 int   impec_last_parabolic_info(const impec_ctx *ctx, impec_solve_info *info); /* the last Crank-Nicolson solve run inside impec_transport_step / impec_impes_step (MGSolver::last_parabolic_its, src/MGSolver.cpp:972) */
 long long impec_overlapped_exchanges(const impec_ctx *ctx);              /* halo exchanges issued concurrently with the interior row chunks of their consumer (multi-GPU) */

@@ -95,3 +95,21 @@ def test_argument_errors_are_reported_not_fatal():
         ctx.pressure_solve()
     with pytest.raises(I.ImpecError, match="unknown option"):
         ctx.set_option("nonsense", 1)
+
+
+def test_cycle_shape_follows_the_rank_count():
+    """The W range in effect (impec_mg_w_range): the default 2..4 everywhere except on 8 or more ranks with slabs of 10-50 M cells
+    (16384^2 on 8 GPUs), where the replicated multigrid tail is entered half as often (2..3; measured in profiles/r2ad_*).
+    An explicit mg_w_to always wins.  (Creating a context allocates but does not touch the slab: no compute here.)"""
+    build_emu()
+    for n, nranks, want in ((9088, 8, (2, 3)), (9088, 4, (2, 4)), (1024, 8, (2, 4)), (64, 1, (2, 4))):
+        P = I.default_params(emulated=True, N1=n, N2=n)
+        ctx = I.Context(P, rank=0, nranks=nranks, emulated=True)
+        assert ctx.mg_w_range() == want, (n, nranks, ctx.mg_w_range())
+        ctx.set_option("mg_w_to", 4)
+        assert ctx.mg_w_range() == (2, 4)
+        ctx.close()
+    P = I.default_params(emulated=True, N1=9088, N2=9088, mg_w_to=5)         # not the default range: left alone
+    ctx = I.Context(P, rank=0, nranks=8, emulated=True)
+    assert ctx.mg_w_range() == (2, 5)
+    ctx.close()
