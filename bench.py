@@ -419,7 +419,9 @@ def main():
         #   76 (1 + 1/4) + 160 (1/16 + 2/64 + 4/256) + 76 * 8 (1/1024 + 1/4096 + ...) = 113.3 B per fine cell
         # SURVEY 8d's model of an UNFUSED cycle with FP64 coefficients is 208 B/cell: the fused FP32-coefficient cycle moves fewer bytes,
         # so fractions against that model can exceed 1 and are reported only for reference; frac_moved is the efficiency measure.
-        vc_moved = 113.3 * cells; vc_model = 208.0 * cells
+        w_from, w_to = ctx.mg_w_range()
+        cyc_b = cycle_bytes_per_fine_cell(w_from, w_to, ctx.mg_levels())         # 113.3 for the default range 2..4 on 13 levels
+        vc_moved = cyc_b * cells; vc_model = 208.0 * cells
         its_mean = float(sum(its)) / max(len(its), 1)
         NN = float(N) * N
         cn = 0.0
@@ -429,7 +431,7 @@ def main():
         step_model = (32.0 + its_mean * (208.0 + 128.0) + 48.0 + 128.0) * NN
         # operator build 74 (one march c -> links, DINV, FP32 copies: 48; coarsening of the links down the hierarchy: 26), per PCG iteration the
         # cycle 113.3 + mat-vec 56 + update 40 (24 and 56 alternately: deferred solution update), velocity + CFL 32 (+ 8 ghost fills), transport 4 x 24 (+ 8 source / fills)
-        step_moved = (ctx_option_bytes_operator() + its_mean * (113.3 + 56.0 + 40.0) + 40.0 + 104.0 + cn) * NN
+        step_moved = (ctx_option_bytes_operator() + its_mean * (cyc_b + 56.0 + 40.0) + 40.0 + 104.0 + cn) * NN
         roofline["vcycle"] = {"ms": prof["vcycle"], "moved_bytes": vc_moved, "achieved_moved": vc_moved / (prof["vcycle"] * 1e-3) / 1e9,
                               "frac_moved": vc_moved / (prof["vcycle"] * 1e-3) / 1e9 / peak,
                               "survey_model_bytes": vc_model, "frac_survey_model": vc_model / (prof["vcycle"] * 1e-3) / 1e9 / peak}
@@ -493,6 +495,19 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def cycle_bytes_per_fine_cell(w_from, w_to, nlevels):
+    """Bytes one multigrid cycle reads + writes per FINE cell: a level visited once per visit of its parent moves
+    PRE 34 + POST 42 = 76 B per cell of its own, a level of the W range (visits the next level twice) PRE 34 + POST 42 + MID 42 + POST 42 = 160;
+    level l has 4^-l of the fine cells."""
+    total, visits = 0.0, 1.0
+    for l in range(nlevels):
+        w = w_from <= l <= w_to
+        total += visits * (160.0 if w else 76.0) / 4.0 ** l
+        if w:
+            visits *= 2.0
+    return total
 
 
 def ctx_option_bytes_operator():
