@@ -17,6 +17,7 @@
 #include <vector>
 #include <cstdio>
 #include <cstdarg>
+#include <climits>
 #include <algorithm>
 #include <thread>
 #include <atomic>
@@ -596,7 +597,6 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, IMPEC_ERR_ARG, "bad rank %d of %d", rank, nranks);
     if (nranks > 1) {
         if (P->is_test) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "the periodic/manufactured test modes run on one GPU");
-        if (P->dim_splitting != IMPEC_SYMMETRIC_PARALLEL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "multi-GPU transport supports dimensional_splitting = parallel only");
         if (P->N1 % (2 * nranks) != 0 || P->N1 / nranks < 8) return fail(ctx, IMPEC_ERR_ARG, "x_cells = %d cannot be cut into %d slabs of an even number (>= 8) of rows", P->N1, nranks);
     }
     CUDA_TRY(ctx, cudaSetDevice(device));
@@ -1760,7 +1760,11 @@ extern "C" int impec_advect_x(impec_ctx *ctx, double dt) {
     const Grid &g = ctx->g; const int ng = ctx->P.g;
     ctx->mob_valid = ctx->op_valid = false;
     TRY(copy_field(ctx, ctx->c, ctx->ta));
-    return sweep<0>(ctx, ctx->ta, ctx->c, nullptr, dt, 0, g.N1, -ng, g.N2 + ng);
+    TRY((sweep<0>(ctx, ctx->ta, ctx->c, nullptr, dt, 0, g.N1, -ng, g.N2 + ng)));
+    // Slabs: the x sweep leaves the halo rows with the neighbours' values from BEFORE their sweep, where the undivided array holds the swept
+    // rows; a sweep that follows (Strang: x, y, x) reads them.  The y sweep needs no such exchange: it sweeps the halo rows as well and
+    // reproduces the neighbours' values bit for bit.
+    return exchange_rows(ctx, ctx->c, g, ng);
 }
 extern "C" int impec_advect_y(impec_ctx *ctx, double dt) {
     const Grid &g = ctx->g; const int ng = ctx->P.g;
@@ -1828,10 +1832,9 @@ extern "C" int impec_advect_split(impec_ctx *ctx, double dt) {
 // HYPRE's PCG regardless.  Here: matrix-free operator on the four face arrays of the dispersion tensor (k_cn9_*), solved by BiCGStab with
 // the folded diagonal as preconditioner to the same relative residual (para_eps), x0 = 0.  Same linear system as the reference's (the oracle
 // and the compiled reference agree on its entries bit for bit, tests/test_oracle_vs_ref.py); a general-purpose path, not a tuned one:
-// no shipped cfg uses it.  One GPU.
+// no shipped cfg uses it.  Slabs: one halo row of the operand before every operator pass.
 static int diffusion_split_general(impec_ctx *ctx, double dt, impec_solve_info *info) {
     const Grid &g = ctx->g;
-    if (ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t (non-symmetric Crank-Nicolson operator) runs on one GPU");
     if (ctx->P.stype == IMPEC_HORIZONTAL) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "dispersion with alpha_l != alpha_t is not combined with source_type horizontal");
     const dim3 gr = grid2d(g.N2, g.N1);
     const long long nparts = (long long)gr.x * gr.y;
@@ -1868,12 +1871,12 @@ static int diffusion_split_general(impec_ctx *ctx, double dt, impec_solve_info *
         const double beta = (rho1 / rho) * (alpha / omega);
         rho = rho1;
         LAUNCH(ctx, k_bicg_p, gr, kBlock, g, beta, omega, (const double *)r, (const double *)v, (const double *)dinv, p, ph);
-        TRY(fill_scalar(ctx, ph, 0));
+        TRY(fill_scalar(ctx, ph, 0)); TRY(exchange_rows(ctx, ph, g, 1));        // mirrored ghosts at the walls, the neighbours' rows at slab edges
         LAUNCH(ctx, k_cn9_apply, gr, kBlock, g, A, ctx->D, (const double *)ph, v, (double *)nullptr);
         double r0v; TRY(dotp(r0, v, &r0v));
         alpha = rho / r0v;
         LAUNCH(ctx, k_bicg_s, gr, kBlock, g, alpha, (const double *)r, (const double *)v, (const double *)dinv, s, sh);
-        TRY(fill_scalar(ctx, sh, 0));
+        TRY(fill_scalar(ctx, sh, 0)); TRY(exchange_rows(ctx, sh, g, 1));        // mirrored ghosts at the walls, the neighbours' rows at slab edges
         LAUNCH(ctx, k_cn9_apply, gr, kBlock, g, A, ctx->D, (const double *)sh, t, (double *)nullptr);
         double tt, ts; TRY(dotp(t, t, &tt)); TRY(dotp(t, s, &ts));
         omega = tt > 0. ? ts / tt : 0.;
@@ -1927,7 +1930,6 @@ extern "C" int impec_project_dims(const impec_ctx *ctx, int *dN1, int *dN2) {
     return IMPEC_OK;
 }
 extern "C" int impec_project_to_diagonal(impec_ctx *ctx, int field, double *out_host) {
-    if (ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "projection needs the whole field: single-GPU contexts only");
     if (field != 0 && field != 1) return fail(ctx, IMPEC_ERR_ARG, "field must be 0 (c) or 1 (p)");
     if (!out_host) return fail(ctx, IMPEC_ERR_ARG, "null output");
     const impec_params &P = ctx->P; const Grid &g = ctx->g;
@@ -1938,11 +1940,23 @@ extern "C" int impec_project_to_diagonal(impec_ctx *ctx, int field, double *out_
     A.p_dx = (P.x_ub - P.x_lb) / P.N1; A.p_dy = (P.y_ub - P.y_lb) / P.N2;
     A.d_dx = (P.x_ub - P.x_lb) / (sqrt(2.) * A.dN1); A.d_dy = (P.y_ub - P.y_lb) / (sqrt(2.) * A.dN2);
     A.ng = P.g;
-    const size_t n = (size_t)A.dN1 * A.dN2;
-    if (n > grid_elems(g)) return fail(ctx, IMPEC_ERR_ARG, "diagonal grid larger than the scratch field");
+    // Slabs (collective; every rank receives the whole projected field): the diagonal grid is processed in chunks of rows that fit the
+    // slab-sized scratch field; each rank evaluates the cells whose stencil starts in its rows, the chunk is summed over the ranks.
+    A.N1g = ctx->N1g; A.i_off = g.i_off;
+    A.own_lo = g.wall_lo ? INT_MIN : g.i_off; A.own_hi = g.wall_hi ? INT_MAX : g.i_off + g.N1;
+    const long long chunk = std::min<long long>(A.dN1, (long long)grid_elems(g) / A.dN2);
+    if (chunk < 1) return fail(ctx, IMPEC_ERR_ARG, "diagonal grid row longer than the scratch field");
     double *dst = ctx->tb;                                   // transport scratch (free between steps)
-    LAUNCH(ctx, k_project_parallel, grid2d(A.dN2, A.dN1), kBlock, g, (const double *)(field == 0 ? ctx->c : ctx->p), A, dst);
-    CUDA_TRY(ctx, cudaMemcpyAsync(out_host, dst, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    double *src = field == 0 ? ctx->c : ctx->p;
+    TRY(exchange_rows(ctx, src, g, 1));                       // the stencil of a cell owned through its lower row reaches one row into the next slab
+    for (long long r0 = 0; r0 < A.dN1; r0 += chunk) {
+        A.row0 = (int)r0; A.nrows = (int)std::min<long long>(chunk, A.dN1 - r0);
+        const size_t n = (size_t)A.nrows * A.dN2;
+        LAUNCH(ctx, k_project_parallel, grid2d(A.dN2, A.nrows), kBlock, g, (const double *)src, A, dst);
+        if (ctx->nranks > 1) TRY(comm_allreduce(ctx, dst, (int)n, RED_SUM));
+        CUDA_TRY(ctx, cudaMemcpyAsync(out_host + (size_t)r0 * A.dN2, dst, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->bytes_d2h += n * sizeof(double);
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return IMPEC_OK;
 }

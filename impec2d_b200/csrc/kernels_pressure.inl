@@ -554,7 +554,9 @@ __global__ void __launch_bounds__(256) k_cn9_apply(Grid g, Cn9 A, DevParams P, c
     for (int a = 0; a < 9; a++) {
         s += e[a] * x[(long long)k + (long long)di[a] * ld + dj[a]];
         int ii = i + di[a], jj = j + dj[a];
-        ii = ii < 0 ? 0 : (ii > g.N1 - 1 ? g.N1 - 1 : ii); jj = jj < 0 ? 0 : (jj > g.N2 - 1 ? g.N2 - 1 : jj);
+        if (ii < 0 && g.wall_lo) ii = 0;                       // (a slab edge that is no wall folds nothing: the neighbour row is a real row)
+        if (ii > g.N1 - 1 && g.wall_hi) ii = g.N1 - 1;
+        jj = jj < 0 ? 0 : (jj > g.N2 - 1 ? g.N2 - 1 : jj);
         if (ii == i && jj == j) dg += e[a];
     }
     y[k] = s;

@@ -403,22 +403,27 @@ __global__ void __launch_bounds__(1024) k_reduce_final(const double *__restrict_
 // ParallelProjector::FillDiagonal / GetFromParallel (src/ParallelProjector.cpp:91-199): one thread per cell of the diagonal
 // grid; rotate its centre by -pi/4 into the parallel frame, mirror y, interpolate the ghosted parallel field bilinearly
 // between the cells floor(x/L N) and +1 exactly as upstream (same operation order: bit-identical to the oracle).
-struct ProjectArgs { double x_lb, y_lb, x_ub, y_ub, ca, sa, p_dx, p_dy, d_dx, d_dy; int dN1, dN2, ng; };
+// Slabs: `a` holds rows [i_off, i_off + g.N1) of a field of N1g rows (+ halo / ghost rows); a diagonal cell is evaluated by the rank that
+// owns the lower row x00 of its stencil (the upper row is an own row or the first halo row), the other ranks write 0 and the chunk
+// [row0, row0 + nrows) of the diagonal grid is summed over the ranks afterwards: one rank: own = everything, i_off = 0, N1g = g.N1.
+struct ProjectArgs { double x_lb, y_lb, x_ub, y_ub, ca, sa, p_dx, p_dy, d_dx, d_dy; int dN1, dN2, ng; int N1g, i_off, own_lo, own_hi, row0, nrows; };
 __global__ void __launch_bounds__(256) k_project_parallel(Grid g, const double *__restrict__ a, ProjectArgs A, double *__restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= A.dN1 || j >= A.dN2) return;
+    const int il = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = A.row0 + il;
+    if (il >= A.nrows || j >= A.dN2) return;
     const double xd = A.x_lb + (i + 0.5) * A.d_dx, yd = A.y_lb + (j + 0.5) * A.d_dy;
     const double x = A.ca * xd - A.sa * yd;
     const double y = fabs(A.sa * xd + A.ca * yd);
-    int x00 = (int)floor(x / (A.x_ub - A.x_lb) * g.N1), y00 = (int)floor(y / (A.y_ub - A.y_lb) * g.N2);
+    int x00 = (int)floor(x / (A.x_ub - A.x_lb) * A.N1g), y00 = (int)floor(y / (A.y_ub - A.y_lb) * g.N2);
     // (upstream only warns about points outside the parallel domain; keep the reads inside the ghosted array)
-    x00 = x00 < -A.ng ? -A.ng : (x00 > g.N1 + A.ng - 2 ? g.N1 + A.ng - 2 : x00);
+    x00 = x00 < -A.ng ? -A.ng : (x00 > A.N1g + A.ng - 2 ? A.N1g + A.ng - 2 : x00);
     y00 = y00 < -A.ng ? -A.ng : (y00 > g.N2 + A.ng - 2 ? g.N2 + A.ng - 2 : y00);
+    if (x00 < A.own_lo || x00 >= A.own_hi) { out[(size_t)il * A.dN2 + j] = 0.; return; }
     const double x_00 = A.x_lb + (x00 + 0.5) * A.p_dx, x_11 = A.x_lb + (x00 + 1 + 0.5) * A.p_dx;
     const double y_00 = A.y_lb + (y00 + 0.5) * A.p_dy, y_11 = A.y_lb + (y00 + 1 + 0.5) * A.p_dy;
-    const size_t k = gidx(g, x00, y00);
-    out[(size_t)i * A.dN2 + j] =
+    const size_t k = gidx(g, x00 - A.i_off, y00);
+    out[(size_t)il * A.dN2 + j] =
         1. / ((x_11 - x_00) * (y_11 - y_00)) * (x_11 - x) * (y_11 - y) * a[k] +
         1. / ((x_11 - x_00) * (y_11 - y_00)) * (x - x_00) * (y_11 - y) * a[k + g.ld] +
         1. / ((x_11 - x_00) * (y_11 - y_00)) * (x_11 - x) * (y - y_00) * a[k + 1] +

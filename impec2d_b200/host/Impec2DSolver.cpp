@@ -182,9 +182,24 @@ void Impec2DSolver::LogResults(double postfix, bool logTime) {
     else { stringstream ss; ss << "_"; if (logTime) ss << "t_"; ss << postfix; post = ss.str() + ".dat"; }
     if ((size_t)sp->N1 * sp->N2 > (size_t)4096 * 4096) { if (postfix < 0 && myid == 0) cout << "(text output skipped above 4096^2)" << endl; return; }
     if (num_procs > 1) {
-        // Slabs: every rank contributes its rows (collective), rank 0 writes.  The parallel -> diagonal projection kernel works on one
-        // GPU's field, so a multi-GPU PARALLEL run writes c and p on the native grid.
-        DeviceContext::GatherGlobal(DeviceContext::Get(sp), &c, postfix < 0 ? &p : NULL, postfix < 0 ? &v : NULL);
+        // Slabs: every call below is collective (each rank contributes its rows), rank 0 writes.  A PARALLEL run projects c and p onto
+        // the diagonal grid as on one GPU (impec_project_to_diagonal sums the ranks' parts of every chunk of diagonal rows).
+        impec_ctx *ctx = DeviceContext::Get(sp);
+        if (sp->stype == PARALLEL) {
+            int d_N1, d_N2; double d_dx, d_dy;
+            Array2d diag_c, diag_p;
+            Project(diag_c, &c, sp->c_bounds, d_N1, d_N2, d_dx, d_dy);
+            if (postfix < 0) Project(diag_p, &p, sp->p_bounds, d_N1, d_N2, d_dx, d_dy);
+            if (postfix < 0) DeviceContext::GatherGlobal(ctx, NULL, NULL, &v);
+            if (myid != 0) return;
+            PrintDToPlotFile(dir + "/concentration" + post, diag_c, sp->x_lb, sp->y_lb, d_dx, d_dy, sp->c_bounds);
+            if (postfix < 0) {
+                PrintDToPlotFile(dir + "/pressure" + post, diag_p, sp->x_lb, sp->y_lb, d_dx, d_dy, sp->p_bounds);
+                PrintVelToPlotFile(dir + "/velocity_u" + post, dir + "/velocity_v" + post, v, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->v_bounds, sp->N1, sp->N2);
+            }
+            return;
+        }
+        DeviceContext::GatherGlobal(ctx, &c, postfix < 0 ? &p : NULL, postfix < 0 ? &v : NULL);
         if (myid != 0) return;
         PrintDToPlotFile(dir + "/concentration" + post, c, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->c_bounds);
         if (postfix < 0) {

@@ -18,7 +18,14 @@ def main():
     cuda = len(sys.argv) > 6 and sys.argv[6] == "cuda"      # real library + NCCL on GPUs instead of emulator + gloo
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=diffusion, eps=1e-12)
+    extra = {}
+    if os.environ.get("IMPEC_TEST_SPLITTING"):      # dimensional_splitting other than the symmetric-parallel default
+        extra["dim_splitting"] = int(os.environ["IMPEC_TEST_SPLITTING"])
+    if os.environ.get("IMPEC_TEST_ALPHA_T"):        # alpha_l != alpha_t: non-symmetric Crank-Nicolson operator, BiCGStab
+        extra["alpha_t"] = float(os.environ["IMPEC_TEST_ALPHA_T"])
+    if os.environ.get("IMPEC_TEST_UPWIND"):
+        extra["hyper_method"] = O.UPWIND
+    base, Po, c, q = production_case(N1, N2, stype=stype, diffusion=diffusion, eps=1e-12, **extra)
     Pi = I.default_params(emulated=not cuda, **base)
     dev = int(os.environ.get("LOCAL_RANK", "0")) if cuda else 0
 
@@ -65,6 +72,11 @@ def main():
     cga = ctx.gather_rows("c"); pgl = ctx.gather_rows("p"); vg = ctx.gather_rows("v"); vr = ref.download_velocity()
     assert np.abs(cga[g:-g, :] - cr[g:-g, :]).max() <= 1e-9 and np.abs(pgl[g:-g, g:-g] - pr[g:-g, g:-g]).max() <= 1e-9 * np.abs(pr).max()
     assert np.abs(vg[g:g + N1, g:-g, :] - vr[g:g + N1, g:-g, :]).max() <= 1e-8 * max(np.abs(vr).max(), 1e-30)
+    if stype == O.PARALLEL:
+        # parallel -> diagonal projection of a slab-decomposed field (collective; rows of the diagonal grid in chunks of the scratch field)
+        for field, full in ((0, cr), (1, pr)):
+            a = ctx.project_to_diagonal(field); b = ref.project_to_diagonal(field)
+            assert a.shape == b.shape and np.abs(a - b).max() <= 1e-9 * max(np.abs(full).max(), 1.0), (field, np.abs(a - b).max())
     if os.environ.get("IMPEC_TEST_CKPT"):
         # per-rank binary checkpoint: save, step, restore, step again -> the same slab bit for bit
         import tempfile

@@ -16,7 +16,7 @@ def ngpus():
 # march = 1: the register-march multigrid kernels (by default only on levels of >= 8M cells) forced onto every slab level
 @pytest.mark.parametrize("N1,N2,stype,diffusion,steps,march", [(512, 512, 0, 0, 2, 0), (256, 128, 1, 1, 2, 0), (2048, 2048, 0, 0, 1, 0), (2048, 2048, 0, 0, 1, 1),
                                                                  (256, 192, 2, 1, 2, 0)])      # (the last: stype 2 = horizontal front, Dirichlet rows on the first / last rank)
-def test_slabs_match_single_gpu(N1, N2, stype, diffusion, steps, march):
+def test_slabs_match_single_gpu(N1, N2, stype, diffusion, steps, march, split=None):
     world = min(ngpus(), 8)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -27,15 +27,26 @@ def test_slabs_match_single_gpu(N1, N2, stype, diffusion, steps, march):
     env = dict(os.environ, IMPEC_DIST_MIN_CELLS="0" if N1 < 2048 else "1000000")
     if march:
         env["IMPEC_MARCH_MIN_CELLS"] = "0"
+    if split is not None:
+        env["IMPEC_TEST_SPLITTING"] = str(split)
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(" ok: ") == world, out.stdout
 
 
-def test_cpp_driver_on_two_gpus(tmp_path):
+@pytest.mark.parametrize("split", [0, 3])
+def test_slabs_sequential_splittings(split):
+    """alternating_sweeps / strang on slabs (added after the last GPU session of round 2: run on CPU ranks only so far,
+    tests/test_multirank.py::test_two_ranks_sequential_splittings; the exchange after an x sweep is the same exchange_rows as everywhere)."""
+    test_slabs_match_single_gpu(256, 128, 1, 0, 2, 0, split=split)
+
+
+@pytest.mark.parametrize("cfg_name,n1,n2", [("diagonal_dispersion", 256, 128), ("parallel", 256, 256)])
+def test_cpp_driver_on_two_gpus(tmp_path, cfg_name, n1, n2):
     """The reference-facing C++ driver (`impec2d cfg`, Impec2DSolver(cfg, myid, num_procs)) as two processes on two GPUs (ranks from the
     environment, NCCL id through a file) against the same driver on one GPU: diagnostics and the final concentration / pressure /
-    velocity files (gathered from both slabs by rank 0) agree to 1e-9."""
+    velocity files (gathered from both slabs by rank 0) agree to 1e-9.  parallel.cfg: c and p are written PROJECTED onto the diagonal grid
+    (Impec2DSolver::Project, collective over the slabs) exactly as the one-GPU run writes them."""
     import re
     import numpy as np
     if ngpus() < 2:
@@ -43,8 +54,8 @@ def test_cpp_driver_on_two_gpus(tmp_path):
     lib_dir = os.path.join(ROOT, "impec2d_b200")
     subprocess.check_call(["make", "-s", "-C", os.path.join(lib_dir, "host"), "all"])
     exe = os.path.join(lib_dir, "impec2d")
-    text = open(os.path.join(ROOT, "examples", "diagonal_dispersion.cfg")).read()
-    text = re.sub(r"x_cells\s*=\s*\d+", "x_cells = 256", text); text = re.sub(r"y_cells\s*=\s*\d+", "y_cells = 128", text)
+    text = open(os.path.join(ROOT, "examples", cfg_name + ".cfg")).read()
+    text = re.sub(r"x_cells\s*=\s*\d+", "x_cells = %d" % n1, text); text = re.sub(r"y_cells\s*=\s*\d+", "y_cells = %d" % n2, text)
     outs = {}
     for world in (1, 2):
         d = tmp_path / ("w%d" % world); d.mkdir()

@@ -49,3 +49,26 @@ def test_two_ranks_horizontal_front():
     """source_type "horizontal": the Dirichlet row i = 1 lives on rank 0, the Crank-Nicolson Dirichlet row i = N1-2 on the last rank; the
     coarse-level shifts of the pinned row are computed on rank 0 and broadcast."""
     run(2, 64, 48, 2, 1, 1, 29618)
+
+
+@pytest.mark.parametrize("split,port", [(0, 29619), (3, 29620), (2, 29621)])
+def test_two_ranks_sequential_splittings(split, port):
+    """dimensional_splitting = alternating_sweeps / strang / y_sweep_first on slabs: an x sweep is followed by an
+    exchange of the swept rows, a y sweep recomputes the halo rows; two steps so that the alternating mode runs both orders."""
+    run(2, 64, 64, 1, 0, 2, port, {"IMPEC_TEST_SPLITTING": str(split)})
+
+
+def test_two_ranks_upwind_x_first():
+    run(2, 64, 32, 1, 0, 2, 29622, {"IMPEC_TEST_SPLITTING": "1", "IMPEC_TEST_UPWIND": "1"})
+
+
+def test_two_ranks_anisotropic_dispersion():
+    """alpha_l != alpha_t on slabs: the matrix-free non-symmetric 9-point Crank-Nicolson operator reads one exchanged halo row of its
+    operand per pass and folds ghost entries into the diagonal only at physical walls."""
+    run(2, 64, 48, 1, 1, 2, 29623, {"IMPEC_TEST_ALPHA_T": "0.1"})
+
+
+def test_four_ranks_parallel_projection_in_chunks():
+    """parallel.cfg on four slabs; the 45 x 45 diagonal grid of Impec2DSolver::Project does not fit the 16-row slab's scratch field and is
+    projected in two chunks of rows, each summed over the ranks (worker: projection of c and p against the 1-rank projection)."""
+    run(4, 64, 64, 0, 0, 1, 29624)
