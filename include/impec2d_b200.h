@@ -166,7 +166,7 @@ int   impec_advect_split(impec_ctx *ctx, double dt);
 int   impec_intercell_flux(impec_ctx *ctx, int dir, double dt, double *out_host);
 /* a19  HyperbolicSolver::DiffusionSplitCN -> MGSolver::Solve_Parabolic_cc_to_c  src/HyperbolicSolver.cpp:213-223, src/MGSolver.cpp:952-976 */
 /*      alpha_l == alpha_t: symmetric links operator, PCG with a one-march symmetric Gauss-Seidel preconditioner; alpha_l != alpha_t: the full
- *      non-symmetric 9-point operator of src/MGSolver.cpp:923-948 applied matrix-free, BiCGStab (one GPU).  Both to para_eps, x0 = 0. */
+ *      non-symmetric 9-point operator of src/MGSolver.cpp:923-948 applied matrix-free, BiCGStab.  Both to para_eps, x0 = 0. */
 int   impec_diffusion_split(impec_ctx *ctx, double dt, impec_solve_info *info);
 /* a14  HyperbolicSplitSolver::Solve                src/HyperbolicSplitSolver.cpp:162-198 */
 int   impec_transport_step(impec_ctx *ctx, double dt);
@@ -181,7 +181,7 @@ int   impec_integral_diagnostics(impec_ctx *ctx, double lo, double hi, impec_int
 
 /* 8f  Impec2DSolver::Project / ParallelProjector::FillDiagonal  src/Impec2DSolver.cpp:690-716, src/ParallelProjector.cpp:91-199
  *     field 0 = c, 1 = p (ghosts must be filled: they are after impec_impes_step); out_host: dN1 x dN2 doubles, row-major.
- *     Single-GPU contexts only. */
+ *     Slab contexts: collective, every rank receives the whole projected field (chunks of diagonal rows are summed over the ranks). */
 int   impec_project_dims(const impec_ctx *ctx, int *dN1, int *dN2);
 int   impec_project_to_diagonal(impec_ctx *ctx, int field, double *out_host);
 
