@@ -26,6 +26,9 @@
 #define BX 32
 #define BY 8
 #include "comm_p2p.inl"
+#ifdef IMPEC_EMU
+#include "emu_filecomm.inl"
+#endif
 
 // ------------------------------------------------------------------------------------------------
 struct Level {
@@ -94,6 +97,9 @@ struct impec_ctx {
     int Ld = 0;                                     // levels [0,Ld) are distributed, [Ld,nl) replicated on every rank
     int N1g = 0;                                    // global number of rows
     impec_comm_callbacks cb; bool has_cb = false;
+#ifdef IMPEC_EMU
+    EmuFileComm *filecomm = nullptr;                // emulated multi-process runs without a Python harness (emu_filecomm.inl)
+#endif
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
     ncclComm_t nccl = nullptr;
 #endif
@@ -567,6 +573,9 @@ extern "C" void impec_ctx_destroy(impec_ctx *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
 #endif
+#ifdef IMPEC_EMU
+    if (ctx->filecomm) { ctx->filecomm->finish(); delete ctx->filecomm; }
+#endif
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     for (void *p : {(void *)ctx->hw_i, (void *)ctx->hw_j, (void *)ctx->hw_q}) if (p) cudaFreeHost(p);
 #ifndef IMPEC_EMU
@@ -639,6 +648,16 @@ extern "C" int impec_ctx_create(const impec_params *P, int device, int rank, int
     }
 #else
     (void)nccl_unique_id;
+#endif
+#ifdef IMPEC_EMU
+    if (nranks > 1 && getenv("IMPEC_EMU_COMM_DIR")) {        // emulated ranks as plain processes (the C++ driver on slabs, tests/test_host_layer.py)
+        ctx->filecomm = new EmuFileComm();
+        static int generation = 0;
+        ctx->filecomm->dir = getenv("IMPEC_EMU_COMM_DIR"); ctx->filecomm->rank = rank; ctx->filecomm->nranks = nranks; ctx->filecomm->gen = generation++;
+        ctx->cb.user = ctx->filecomm; ctx->cb.sendrecv = EmuFileComm::sendrecv; ctx->cb.allreduce = EmuFileComm::allreduce;
+        ctx->cb.allgather = EmuFileComm::allgather; ctx->cb.bcast = EmuFileComm::bcast;
+        ctx->has_cb = true; ctx->comm_ready = true;
+    }
 #endif
     fill_dev_params(ctx);
     ctx->N1g = P->N1;

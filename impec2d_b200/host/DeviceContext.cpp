@@ -84,13 +84,13 @@ impec_ctx *DeviceContext::Get(SimParams *sp) {
     const char *dev = getenv("IMPEC_DEVICE"), *lr = getenv("LOCAL_RANK");
     const int device = dev ? atoi(dev) : (g_nranks > 1 ? (lr ? atoi(lr) : g_rank) : 0);
     char id[128]; const char *idp = nullptr;
-    if (g_nranks > 1) {
+    if (g_nranks > 1 && !impec_is_emulated()) {              // (the emulated test build connects its processes through IMPEC_EMU_COMM_DIR instead)
         if (!exchange_nccl_id(id)) { std::cerr << "impec2d_b200: rank " << g_rank << " could not exchange the NCCL id through " << id_file() << std::endl; exit(1); }
         idp = id;
     }
     const int rc = impec_ctx_create(&P, device, g_rank, g_nranks, idp, nullptr, &e.ctx);
     Check(e.ctx, rc, "impec_ctx_create");
-    if (g_nranks > 1 && g_rank == 0) std::remove(id_file().c_str());     // every rank has joined the communicator
+    if (g_nranks > 1 && g_rank == 0 && !impec_is_emulated()) std::remove(id_file().c_str());     // every rank has joined the communicator
     e.P = P; e.q_uploaded = nullptr;
     return e.ctx;
 }

@@ -165,3 +165,65 @@ def test_horizontal_front_with_pulsing_injection(tmp_path):
     # (the reference's mass-balance diagnostic assumes the base rate, src/Impec2DSolver.cpp:391-415: exact while the rate is low, off afterwards)
     low = [k for k in range(8) if k not in high and all(h > k for h in high)]
     assert all(em[k] < 1e-6 for k in low), em
+
+
+@pytest.mark.parametrize("name,n1,n2,world", [("diagonal_dispersion.cfg", 64, 32, 2), ("parallel.cfg", 64, 64, 2), ("parallel.cfg", 64, 64, 4)])
+def test_cpp_driver_on_slabs(tmp_path, name, n1, n2, world):
+    """Impec2DSolver(cfg, myid, num_procs) (src/Impec2DSolver.h:54, src/Driver.cpp:58-87) as `world` PROCESSES of the emulated build, one
+    slab each (ranks from IMPEC_RANK / IMPEC_NRANKS, the processes connected through files in IMPEC_EMU_COMM_DIR: csrc/emu_filecomm.inl),
+    against the same driver as one process: the diagnostics lines and every result file -- the dispersion run's native-grid fields, the
+    parallel run's c and p PROJECTED onto the diagonal grid by the collective Impec2DSolver::Project -- agree to 1e-9.  The GPU twin over
+    NCCL is tests/test_gpu_multirank.py::test_cpp_driver_on_two_gpus."""
+    outs = {}
+    subs = [(r"x_cells\s*=\s*\d+", "x_cells = %d" % n1), (r"y_cells\s*=\s*\d+", "y_cells = %d" % n2)]
+    for w in (1, world):
+        d = tmp_path / ("w%d" % w); d.mkdir()
+        comm = d / "comm"; comm.mkdir()
+        cfg = cfg_variant(d, name, subs)
+        procs = []
+        for r in range(w):
+            env = dict(os.environ, IMPEC_RANK=str(r), IMPEC_NRANKS=str(w), IMPEC_EMU_COMM_DIR=str(comm), IMPEC_DIST_MIN_CELLS="0", OMP_NUM_THREADS="1")
+            procs.append(subprocess.Popen([EXE, cfg, "--steps", "3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+        logs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(l[-2000:] for l in logs)
+        assert "[3]\tITS_e:" in logs[0], logs[0][-2000:]
+        assert not os.listdir(str(comm)), "the file communicator left files behind"
+        res = [os.path.join(dp, f) for dp, _, fs in os.walk(str(d)) for f in fs if f.endswith(".dat")]
+        outs[w] = {os.path.basename(f): np.loadtxt(f) for f in res}
+        outs[w]["__steps__"] = [l for l in logs[0].splitlines() if re.match(r"\[\d+\]\tITS_e:", l)]
+    assert {"concentration.dat", "pressure.dat", "velocity_u.dat", "velocity_v.dat", "diagnostics.dat"} <= set(outs[world]), sorted(outs[world])
+    assert len(outs[1]["__steps__"]) == 3 and len(outs[world]["__steps__"]) == 3
+    for name_, a in outs[1].items():
+        if name_ == "__steps__":
+            continue
+        b = outs[world][name_]
+        assert a.shape == b.shape, (name_, a.shape, b.shape)
+        assert np.abs(a - b).max() <= 1e-9 * max(np.abs(a).max(), 1.0), (name_, np.abs(a - b).max())
+
+
+def test_driver_checkpoint_restart_on_slabs(tmp_path):
+    """`impec2d --checkpoint / --restart` as two processes: every rank writes / reads its own file (RankFile); 2 steps in one go ==
+    1 step, checkpoint, restart, 1 more step -- same diagnostics line, same gathered concentration file."""
+    subs = [(r"x_cells\s*=\s*\d+", "x_cells = 32"), (r"y_cells\s*=\s*\d+", "y_cells = 16")]
+    ck = str(tmp_path / "run.ckpt")
+
+    def run(d, extra):
+        comm = d / ("comm%d" % len(os.listdir(str(d)))); comm.mkdir()
+        procs = []
+        for r in range(2):
+            env = dict(os.environ, IMPEC_RANK=str(r), IMPEC_NRANKS="2", IMPEC_EMU_COMM_DIR=str(comm), IMPEC_DIST_MIN_CELLS="0", OMP_NUM_THREADS="1")
+            procs.append(subprocess.Popen([EXE, cfgs[d]] + extra, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+        logs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(l[-2000:] for l in logs)
+        return logs[0]
+
+    da = tmp_path / "a"; db = tmp_path / "b"; da.mkdir(); db.mkdir()
+    cfgs = {da: cfg_variant(da, "diagonal_dispersion.cfg", subs), db: cfg_variant(db, "diagonal_dispersion.cfg", subs)}
+    last_a = [l for l in run(da, ["--steps", "2"]).splitlines() if l.startswith("[2]")]
+    run(db, ["--steps", "1", "--checkpoint", ck])
+    out = run(db, ["--steps", "1", "--restart", ck])
+    assert "Restarted from" in out
+    last_b = [l for l in out.splitlines() if l.startswith("[2]")]
+    assert last_a and last_a == last_b, (last_a, last_b)
+    find = lambda d: [os.path.join(dp, f) for dp, _, fs in os.walk(str(d)) for f in fs if f == "concentration.dat"][0]
+    assert np.array_equal(np.loadtxt(find(da)), np.loadtxt(find(db)))
