@@ -91,11 +91,16 @@ bool EllipticSolver::TestNeumann(GnuPlotter *gp) {
     sp->btype = NEUMANN;
     bool stat = true;
     sp->N1 = sp->init_x_cells; sp->N2 = sp->init_y_cells;
-    ofstream norm_stream(sp->norm_file.c_str());
-    if (!norm_stream.is_open()) { cerr << "Cannot write norm-file! Convergence test aborted..." << endl; return false; }
-    norm_stream.precision(30);
+    // Several processes (one slab each): every rank runs the test, the norms are taken over the gathered fields, rank 0 writes the files.
+    const bool root = DeviceContext::Rank() == 0, slabs = DeviceContext::NumRanks() > 1;
+    ofstream norm_stream;
+    if (root) {
+        norm_stream.open(sp->norm_file.c_str());
+        if (!norm_stream.is_open()) { cerr << "Cannot write norm-file! Convergence test aborted..." << endl; return false; }
+        norm_stream.precision(30);
+    }
     for (int k = 0; k < sp->levels; k++) {
-        cout << "-> (N1,N2):\t(" << sp->N1 << " , " << sp->N2 << ")";
+        if (root) cout << "-> (N1,N2):\t(" << sp->N1 << " , " << sp->N2 << ")";
         sp->dx = (sp->x_ub - sp->x_lb) / sp->N1; sp->dy = (sp->y_ub - sp->y_lb) / sp->N2; sp->M = sp->N1 * sp->N2;
         EllipticSolver *mg_test = new MGSolver(sp);
         const int g = sp->p_bounds, N1 = sp->N1, N2 = sp->N2;
@@ -116,23 +121,24 @@ bool EllipticSolver::TestNeumann(GnuPlotter *gp) {
         }
         // c = 0 everywhere, so its Neumann ghost fill (:231) is a no-op
         stat = stat && mg_test->Solve(p, c, q);
-        cout << "\tITS:\t" << mg_test->GetLastIts() << endl;
+        if (root) cout << "\tITS:\t" << mg_test->GetLastIts() << endl;
         mg_test->CalcVelocities(p, v, c);
+        if (slabs) DeviceContext::GatherGlobal(DeviceContext::Get(sp), NULL, &p, &v);
         double p_sum = 0, u_sum = 0, v_sum = 0;
         for (int i = 0; i < N1; i++) for (int j = 0; j < N2; j++) p_sum += fabs(p(i, j) - p_ex(i, j));
         for (int i = 0; i <= N1; i++) for (int j = 0; j < N2; j++) u_sum += fabs(v_ex(i, j, 0) - v(i, j, 0));
         for (int i = 0; i < N1; i++) for (int j = 0; j <= N2; j++) v_sum += fabs(v_ex(i, j, 1) - v(i, j, 1));
         p_sum *= sp->dx * sp->dy; u_sum *= sp->dx * sp->dy; v_sum *= sp->dx * sp->dy;
-        if (k == 0) {
+        if (k == 0 && root) {
             PrintDToPlotFile(sp->num_result_file, p, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->p_bounds);
             PrintDToPlotFile(sp->ex_result_file, p_ex, sp->x_lb, sp->y_lb, sp->dx, sp->dy, sp->p_bounds);
         }
-        norm_stream << log(sp->dx) << "\t" << log(p_sum) << "\t" << log(u_sum) << "\t" << log(v_sum) << endl;
+        if (root) norm_stream << log(sp->dx) << "\t" << log(p_sum) << "\t" << log(u_sum) << "\t" << log(v_sum) << endl;
         p.Unbind(); c.Unbind(); v.Unbind();
         delete[] q; delete mg_test;
         sp->N1 *= 2; sp->N2 *= 2;
     }
-    norm_stream.close();
+    if (root) norm_stream.close();
     return stat;
 }
 

@@ -13,11 +13,50 @@ import oracle as O         # noqa: E402
 from helpers import production_case   # noqa: E402
 
 
+def elliptic_self_test(N1, N2, testno, cuda, rank, world):
+    """elliptic_test.cfg on slabs (src/EllipticSolver.cpp:191-239): manufactured K(x,y) fields, p = cos x cos y; the slab solve against the
+    1-rank solve of the same library and against the exact solution."""
+    import ctypes as C
+    from helpers import interior
+    kw = dict(N1=N1, N2=N2, x_ub=2 * np.pi, y_ub=2 * np.pi, mu_res=1.0, mu_inj=1.0, avgproc=O.MEANCONC, nu=float(os.environ.get("IMPEC_TEST_NU", "1.0")),
+              is_test=1, testno=testno, stype=O.DIAGONAL, eps=1e-12)
+    Po = O.default_params(**kw); Pi = I.default_params(emulated=not cuda, **kw)
+    c = O.scalar_field(Po); pex = O.scalar_field(Po); uex = O.velocity_field(Po); vex = O.velocity_field(Po); q = np.zeros(N1 * N2)
+    O.lib().orc_init_elliptic_test(C.byref(Po), pex, q, uex, vex)
+    dev = int(os.environ.get("LOCAL_RANK", "0")) if cuda else 0
+    ref = I.Context(Pi, device=dev, emulated=not cuda)
+    ref.upload_c(c); ref.upload_q(q); info_ref = ref.pressure_solve(); ref.calc_velocities()
+    pr = ref.download_p(); vr = ref.download_velocity()
+    assert not cuda, "CPU ranks only"
+    ctx = I.Context(Pi, rank=rank, nranks=world, emulated=True)
+    I.attach_torch_comm(ctx, rank, world)
+    ctx.upload_c(c); ctx.upload_q(q); info = ctx.pressure_solve(); ctx.calc_velocities()
+    assert info.converged == 1 and abs(info.iterations - info_ref.iterations) <= 1, (info.iterations, info_ref.iterations)
+    pg = ctx.gather_rows("p"); vg = ctx.gather_rows("v")
+    g = Pi.g
+    dp = np.abs(pg[g:-g, g:-g] - pr[g:-g, g:-g]).max() / np.abs(pr).max()
+    dv = max(np.abs(vg[g:g + N1, g:g + N2, 0] - vr[g:g + N1, g:g + N2, 0]).max(), np.abs(vg[g:g + N1, g:g + N2 + 1, 1] - vr[g:g + N1, g:g + N2 + 1, 1]).max())
+    assert dp <= 1e-9 and dv <= 1e-8, (dp, dv)
+    err = np.abs(interior(Po, pg) - interior(Po, pex)).sum() * Po.dx * Po.dy
+    err_ref = np.abs(interior(Po, pr) - interior(Po, pex)).sum() * Po.dx * Po.dy
+    assert abs(err - err_ref) <= 1e-6 * err_ref, (err, err_ref)
+    try:
+        ctx.fill_boundaries()
+        raise AssertionError("the periodic ghost fill must be refused on slabs")
+    except I.ImpecError:
+        pass
+    print("rank %d ok: dp %.2e dv %.2e its %d/%d err %.3e" % (rank, dp, dv, info.iterations, info_ref.iterations, err), flush=True)
+    ctx.close(); ref.close()
+    dist.destroy_process_group()
+
+
 def main():
     N1, N2, stype, diffusion, steps = (int(x) for x in sys.argv[1:6])
     cuda = len(sys.argv) > 6 and sys.argv[6] == "cuda"      # real library + NCCL on GPUs instead of emulator + gloo
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    if os.environ.get("IMPEC_TEST_ELLIPTIC"):
+        return elliptic_self_test(N1, N2, int(os.environ["IMPEC_TEST_ELLIPTIC"]), cuda, rank, world)
     extra = {}
     if os.environ.get("IMPEC_TEST_SPLITTING"):      # dimensional_splitting other than the symmetric-parallel default (SURVEY 8f rank 4)
         extra["dim_splitting"] = int(os.environ["IMPEC_TEST_SPLITTING"])

@@ -227,3 +227,22 @@ def test_driver_checkpoint_restart_on_slabs(tmp_path):
     assert last_a and last_a == last_b, (last_a, last_b)
     find = lambda d: [os.path.join(dp, f) for dp, _, fs in os.walk(str(d)) for f in fs if f == "concentration.dat"][0]
     assert np.array_equal(np.loadtxt(find(da)), np.loadtxt(find(db)))
+
+
+def test_elliptic_test_cfg_on_slabs(tmp_path):
+    """elliptic_test.cfg (EllipticSolver::TestNeumann, src/EllipticSolver.cpp:191-239) as two processes: a new slab context per refinement
+    level, norms over the gathered fields on rank 0 -- the same norm file as the one-process run."""
+    norms = {}
+    for w in (1, 2):
+        d = tmp_path / ("w%d" % w); d.mkdir(); comm = d / "comm"; comm.mkdir()
+        cfg = cfg_variant(d, "elliptic_test.cfg", [(r"levels\s*=\s*6", "levels = 3")])
+        procs = []
+        for r in range(w):
+            env = dict(os.environ, IMPEC_RANK=str(r), IMPEC_NRANKS=str(w), IMPEC_EMU_COMM_DIR=str(comm), IMPEC_DIST_MIN_CELLS="0", OMP_NUM_THREADS="1")
+            procs.append(subprocess.Popen([EXE, cfg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+        logs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(l[-2000:] for l in logs)
+        assert not os.listdir(str(comm))
+        norms[w] = np.loadtxt(str(d / "elliptic_norms.out"))
+    assert norms[1].shape == norms[2].shape == (3, 4)
+    assert np.abs(norms[1] - norms[2]).max() <= 1e-6, np.abs(norms[1] - norms[2]).max()

@@ -72,3 +72,10 @@ def test_four_ranks_parallel_projection_in_chunks():
     """parallel.cfg on four slabs; the 45 x 45 diagonal grid of Impec2DSolver::Project does not fit the 16-row slab's scratch field and is
     projected in two chunks of rows, each summed over the ranks (worker: projection of c and p against the 1-rank projection)."""
     run(4, 64, 64, 0, 0, 1, 29624)
+
+
+@pytest.mark.parametrize("N1,N2,testno,nu,port", [(32, 48, 4, "1.0", 29625), (32, 48, 2, "0.6666666666666666", 29626), (20, 30, 4, "1.0", 29627)])
+def test_two_ranks_elliptic_self_test(N1, N2, testno, nu, port):
+    """The manufactured elliptic test (elliptic_test.cfg) on two slabs: the K(x,y) test fields are evaluated at global coordinates
+    (the device-side x origin is the slab's), the multi-pass operator build exchanges its link rows."""
+    run(2, N1, N2, 1, 0, 1, port, {"IMPEC_TEST_ELLIPTIC": str(testno), "IMPEC_TEST_NU": nu})
