@@ -263,11 +263,14 @@ def attach_torch_comm(ctx, rank, nranks):
         return torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(int(n),)))
 
     def sendrecv(user, send_lo, recv_lo, send_hi, recv_hi, n):
+        # peers modulo the rank count (NULL pointers mark walls; the periodic self test passes all four and closes the ranks to a ring);
+        # one tag per direction: with two ranks both neighbours are the same peer.  Tag 1 = travelling down (send_lo -> the peer's recv_hi).
         ops = []
+        lo, hi = (rank - 1) % nranks, (rank + 1) % nranks
         if send_lo:
-            ops += [dist.P2POp(dist.isend, view(send_lo, n).clone(), rank - 1), dist.P2POp(dist.irecv, view(recv_lo, n), rank - 1)]
+            ops += [dist.P2POp(dist.isend, view(send_lo, n).clone(), lo, tag=1), dist.P2POp(dist.irecv, view(recv_lo, n), lo, tag=2)]
         if send_hi:
-            ops += [dist.P2POp(dist.isend, view(send_hi, n).clone(), rank + 1), dist.P2POp(dist.irecv, view(recv_hi, n), rank + 1)]
+            ops += [dist.P2POp(dist.isend, view(send_hi, n).clone(), hi, tag=2), dist.P2POp(dist.irecv, view(recv_hi, n), hi, tag=1)]
         for r in dist.batch_isend_irecv(ops) if ops else []:
             r.wait()
         return 0

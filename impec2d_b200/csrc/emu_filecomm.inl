@@ -65,10 +65,12 @@ struct EmuFileComm {
     }
     static int sendrecv(void *u, const double *slo, double *rlo, const double *shi, double *rhi, long long n) {
         EmuFileComm &c = *(EmuFileComm *)u; const long long s = ++c.seq; const size_t b = (size_t)n * sizeof(double);
-        if (slo && !c.put(c.name(s, c.rank, c.rank - 1), slo, b)) return 1;
-        if (shi && !c.put(c.name(s, c.rank, c.rank + 1), shi, b)) return 1;
-        if (rlo && !c.get(c.name(s, c.rank - 1, c.rank), rlo, b)) return 1;
-        if (rhi && !c.get(c.name(s, c.rank + 1, c.rank), rhi, b)) return 1;
+        // peers modulo the rank count (a NULL pointer marks a wall; the periodic self test passes all four); "d" = travelling down, "u" = up
+        const int lo = (c.rank + c.nranks - 1) % c.nranks, hi = (c.rank + 1) % c.nranks;
+        if (slo && !c.put(c.name(s, c.rank, lo) + "d", slo, b)) return 1;
+        if (shi && !c.put(c.name(s, c.rank, hi) + "u", shi, b)) return 1;
+        if (rlo && !c.get(c.name(s, lo, c.rank) + "u", rlo, b)) return 1;
+        if (rhi && !c.get(c.name(s, hi, c.rank) + "d", rhi, b)) return 1;
         return 0;
     }
     static int allgather(void *u, const double *send, double *recv, long long n) {

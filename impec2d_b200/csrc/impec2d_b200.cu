@@ -286,6 +286,26 @@ static int comm_sendrecv(impec_ctx *ctx, const double *send_lo, double *recv_lo,
     return fail(ctx, IMPEC_ERR_NCCL, "no communication back end");
 #endif
 }
+// Periodic variant (the hyperbolic self test on slabs): the first rank's lower neighbour is the last rank.  With two ranks both neighbours are
+// the same peer, so the messages are told apart by direction: what leaves through `send_lo` travels DOWN and arrives in the peer's `recv_hi`.
+// Host callbacks receive all four pointers and pair them the same way (peers modulo the rank count, one tag per direction).  NCCL matches
+// sends and receives between a pair of ranks in the order they are issued inside the group: sends down, up; receives from above, from below.
+static int comm_sendrecv_wrap(impec_ctx *ctx, const double *send_lo, double *recv_lo, const double *send_hi, double *recv_hi, long long n) {
+    TRY(comm_check(ctx));
+    if (ctx->has_cb) { if (ctx->cb.sendrecv(ctx->cb.user, send_lo, recv_lo, send_hi, recv_hi, n)) return fail(ctx, IMPEC_ERR_NCCL, "sendrecv callback failed"); return IMPEC_OK; }
+#if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
+    const int lo = (ctx->rank + ctx->nranks - 1) % ctx->nranks, hi = (ctx->rank + 1) % ctx->nranks;
+    NCCL_TRY(ctx, ncclGroupStart());
+    NCCL_TRY(ctx, ncclSend(send_lo, (size_t)n, ncclDouble, lo, ctx->nccl, ctx->stream));
+    NCCL_TRY(ctx, ncclSend(send_hi, (size_t)n, ncclDouble, hi, ctx->nccl, ctx->stream));
+    NCCL_TRY(ctx, ncclRecv(recv_hi, (size_t)n, ncclDouble, hi, ctx->nccl, ctx->stream));
+    NCCL_TRY(ctx, ncclRecv(recv_lo, (size_t)n, ncclDouble, lo, ctx->nccl, ctx->stream));
+    NCCL_TRY(ctx, ncclGroupEnd());
+    return IMPEC_OK;
+#else
+    return fail(ctx, IMPEC_ERR_NCCL, "no communication back end");
+#endif
+}
 #if !defined(IMPEC_EMU) && defined(IMPEC_WITH_NCCL)
 static int p2p_allreduce(impec_ctx *ctx, double *buf, int n, int op);
 #endif
@@ -428,6 +448,13 @@ static int exchange_rows(impec_ctx *ctx, double *a, const Grid &g, int n) {
     const bool prev = !g.wall_lo, next = !g.wall_hi;
     return comm_sendrecv(ctx, prev ? a + (size_t)IMPEC_GH * ld : nullptr, prev ? a + (size_t)(IMPEC_GH - n) * ld : nullptr,
                          next ? a + (size_t)(g.N1 - n + IMPEC_GH) * ld : nullptr, next ? a + (size_t)(g.N1 + IMPEC_GH) * ld : nullptr, (long long)n * g.ld);
+}
+// The same with the ranks closed to a ring (periodic domain): every rank has both neighbours.  Plain NCCL send / recv (a test mode: the
+// peer-memory mailboxes are laid out for walls at both ends of the rank line).
+static int exchange_rows_periodic(impec_ctx *ctx, double *a, const Grid &g, int n) {
+    if (ctx->nranks == 1) return IMPEC_OK;
+    const size_t ld = (size_t)g.ld;
+    return comm_sendrecv_wrap(ctx, a + (size_t)IMPEC_GH * ld, a + (size_t)(IMPEC_GH - n) * ld, a + (size_t)(g.N1 - n + IMPEC_GH) * ld, a + (size_t)(g.N1 + IMPEC_GH) * ld, (long long)n * g.ld);
 }
 // two fields in one NCCL group (one launch instead of two)
 static int exchange_rows2(impec_ctx *ctx, double *a, double *b, const Grid &g, int n) {
@@ -1054,7 +1081,15 @@ static int fill_scalar(impec_ctx *ctx, double *a, int periodic) {
     return IMPEC_OK;
 }
 extern "C" int impec_fill_boundaries(impec_ctx *ctx) {
-    if (ctx->P.is_test && ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "the periodic ghost fill of the hyperbolic self test wraps within one GPU's rows: run it on one GPU");
+    if (ctx->P.is_test && ctx->nranks > 1) {
+        // periodic domain on slabs (src/Util.cpp:215-256): the ghost columns wrap inside every row, the ghost rows are the rows of the
+        // neighbouring rank with the ranks closed to a ring -- columns first, so that the rows travel with their corner cells
+        Grid gp = ctx->g; gp.wall_lo = gp.wall_hi = 0;
+        const int ng = ctx->P.g;
+        const long long total = 2LL * ng * (gp.N2 + 2 * ng) + 2LL * ng * gp.N1;
+        LAUNCH(ctx, k_fill_scalar, dim3((unsigned)((total + 255) / 256)), dim3(256), gp, ctx->c, 1, ng);
+        return exchange_rows_periodic(ctx, ctx->c, ctx->g, ng);
+    }
     TRY(fill_scalar(ctx, ctx->c, ctx->P.is_test ? 1 : 0));
     return exchange_rows(ctx, ctx->c, ctx->g, ctx->P.g);          // halo rows (with their ghost columns) from the neighbouring slabs
 }

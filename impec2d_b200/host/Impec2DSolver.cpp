@@ -235,18 +235,24 @@ bool Impec2DSolver::TestComponent() {
 }
 bool Impec2DSolver::TestAdvection() {
     sp->N1 = sp->init_x_cells; sp->N2 = sp->init_y_cells;
-    ofstream norm_stream(sp->norm_file.c_str());
-    if (!norm_stream.is_open()) { cerr << "Cannot write norm-file! Convergence test aborted..." << endl; return false; }
-    norm_stream.precision(30);
+    // several processes: every rank advects its slab, the norm is taken over the gathered field, rank 0 reports
+    ofstream norm_stream;
+    if (myid == 0) {
+        norm_stream.open(sp->norm_file.c_str());
+        if (!norm_stream.is_open()) { cerr << "Cannot write norm-file! Convergence test aborted..." << endl; return false; }
+        norm_stream.precision(30);
+    }
     for (int k = 0; k < sp->levels; k++) {
         sp->dx = (sp->x_ub - sp->x_lb) / sp->N1; sp->dy = (sp->y_ub - sp->y_lb) / sp->N2; sp->M = sp->N1 * sp->N2;
         p.Unbind(); c.Unbind(); v.Unbind();
         ResizeArrays();
         for (int i = 0; i < sp->M; i++) q[i] = 0.;
-        cout << "->Resolution:\t" << sp->N1 << "  x  " << sp->N2 << flush;
+        if (myid == 0) cout << "->Resolution:\t" << sp->N1 << "  x  " << sp->N2 << flush;
         const double lpnorm = Advection();
-        cout << "\t\tL" << sp->hyp_norm + 1 << ":\t" << lpnorm << endl;
-        norm_stream << log(sp->dx) << "\t" << log(lpnorm) << endl;
+        if (myid == 0) {
+            cout << "\t\tL" << sp->hyp_norm + 1 << ":\t" << lpnorm << endl;
+            norm_stream << log(sp->dx) << "\t" << log(lpnorm) << endl;
+        }
         sp->N1 *= 2; sp->N2 *= 2;
     }
     return true;
@@ -269,6 +275,7 @@ double Impec2DSolver::Advection() {
         if (!hs->Solve(c, v, q, dt)) break;
         t += dt;
     }
-    cout << "\ttime [ms]: " << (long)(chrono::duration<double, milli>(chrono::steady_clock::now() - t0).count() + 0.5) << flush;
+    if (myid == 0) cout << "\ttime [ms]: " << (long)(chrono::duration<double, milli>(chrono::steady_clock::now() - t0).count() + 0.5) << flush;
+    if (num_procs > 1) DeviceContext::GatherGlobal(DeviceContext::Get(sp), &c, NULL, NULL);
     return sp->hyp_norm == L2 ? CalcAdvectionL2Norm(sp, c, t, fptr) : CalcAdvectionL1Norm(sp, c, t, fptr);
 }

@@ -4,7 +4,7 @@
 # exchange_rows / comm_allreduce calls.  Needs 2 GPUs:  gpurun --gpus 2 --timeout 1500 -- bash profiles/scripts/gpu_r2ae_pending.sh
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-# 1. slabs: sequential splitting modes, parallel.cfg through the C++ driver with the collective projection
+# 1. slabs: sequential splitting modes, both self tests, parallel.cfg through the C++ driver with the collective projection
 timeout 1200 python -m pytest tests/test_gpu_multirank.py -x -q -m gpu > gpurun_out/r2ae_pytest_multirank_n2.txt 2>&1
 tail -3 gpurun_out/r2ae_pytest_multirank_n2.txt
 # 2. one GPU: the whole parity suite (k_project_parallel and k_cn9_apply changed their argument lists)

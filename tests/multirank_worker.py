@@ -13,6 +13,22 @@ import oracle as O         # noqa: E402
 from helpers import production_case   # noqa: E402
 
 
+def slab_context(Pi, cuda, rank, world, dev):
+    """This rank's slab context: the real library over NCCL on GPUs, or the emulator over gloo."""
+    if cuda:
+        import ctypes as C
+        ids = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            assert I.load().impec_nccl_unique_id(buf) == 0
+            ids = [buf.raw]
+        dist.broadcast_object_list(ids, src=0)
+        return I.Context(Pi, device=dev, rank=rank, nranks=world, nccl_id=ids[0])
+    ctx = I.Context(Pi, rank=rank, nranks=world, emulated=True)
+    I.attach_torch_comm(ctx, rank, world)
+    return ctx
+
+
 def elliptic_self_test(N1, N2, testno, cuda, rank, world):
     """elliptic_test.cfg on slabs (src/EllipticSolver.cpp:191-239): manufactured K(x,y) fields, p = cos x cos y; the slab solve against the
     1-rank solve of the same library and against the exact solution."""
@@ -27,9 +43,7 @@ def elliptic_self_test(N1, N2, testno, cuda, rank, world):
     ref = I.Context(Pi, device=dev, emulated=not cuda)
     ref.upload_c(c); ref.upload_q(q); info_ref = ref.pressure_solve(); ref.calc_velocities()
     pr = ref.download_p(); vr = ref.download_velocity()
-    assert not cuda, "CPU ranks only"
-    ctx = I.Context(Pi, rank=rank, nranks=world, emulated=True)
-    I.attach_torch_comm(ctx, rank, world)
+    ctx = slab_context(Pi, cuda, rank, world, dev)
     ctx.upload_c(c); ctx.upload_q(q); info = ctx.pressure_solve(); ctx.calc_velocities()
     assert info.converged == 1 and abs(info.iterations - info_ref.iterations) <= 1, (info.iterations, info_ref.iterations)
     pg = ctx.gather_rows("p"); vg = ctx.gather_rows("v")
@@ -40,12 +54,35 @@ def elliptic_self_test(N1, N2, testno, cuda, rank, world):
     err = np.abs(interior(Po, pg) - interior(Po, pex)).sum() * Po.dx * Po.dy
     err_ref = np.abs(interior(Po, pr) - interior(Po, pex)).sum() * Po.dx * Po.dy
     assert abs(err - err_ref) <= 1e-6 * err_ref, (err, err_ref)
-    try:
-        ctx.fill_boundaries()
-        raise AssertionError("the periodic ghost fill must be refused on slabs")
-    except I.ImpecError:
-        pass
     print("rank %d ok: dp %.2e dv %.2e its %d/%d err %.3e" % (rank, dp, dv, info.iterations, info_ref.iterations, err), flush=True)
+    ctx.close(); ref.close()
+    dist.destroy_process_group()
+
+
+def periodic_self_test(N, steps, upwind, cuda, rank, world):
+    """hyperbolic_test.cfg on slabs: periodic advection with the prescribed velocity (-1, +1); the ranks are closed to a ring for the ghost
+    rows.  The transport path is explicit, so the slab run equals the 1-rank run BIT FOR BIT."""
+    from helpers import advection_case, aos
+    kw = dict(hyper_method=O.UPWIND) if upwind else {}
+    base, Po, c, u, v = advection_case(N, **kw)
+    Pi = I.default_params(emulated=not cuda, **base)
+    q = np.zeros(N * N)
+    dev = int(os.environ.get("LOCAL_RANK", "0")) if cuda else 0
+    ref = I.Context(Pi, device=dev, emulated=not cuda)
+    ctx = slab_context(Pi, cuda, rank, world, dev)
+    out = []
+    for k in (ref, ctx):
+        k.upload_c(c); k.upload_velocity(aos(u, v)); k.upload_q(q)
+        dt = k.max_stable_dt()
+        for _ in range(steps):
+            k.transport_step(dt)
+        out.append((dt, k.gather_rows("c"), k.diagnostics().total_mass))
+    g = Pi.g
+    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+    assert np.array_equal(out[0][1][g:-g, g:-g], out[1][1][g:-g, g:-g]), np.abs(out[0][1][g:-g, g:-g] - out[1][1][g:-g, g:-g]).max()
+    assert abs(out[0][2] - out[1][2]) <= 1e-12 * abs(out[0][2])
+    assert np.abs(out[1][1][g:-g, g:-g] - c[g:-g, g:-g]).max() > 1e-3, "the profile did not move"
+    print("rank %d ok: periodic advection on %d slabs bit-identical after %d steps" % (rank, world, steps), flush=True)
     ctx.close(); ref.close()
     dist.destroy_process_group()
 
@@ -55,6 +92,8 @@ def main():
     cuda = len(sys.argv) > 6 and sys.argv[6] == "cuda"      # real library + NCCL on GPUs instead of emulator + gloo
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    if os.environ.get("IMPEC_TEST_PERIODIC"):
+        return periodic_self_test(N1, steps, os.environ["IMPEC_TEST_PERIODIC"] == "upwind", cuda, rank, world)
     if os.environ.get("IMPEC_TEST_ELLIPTIC"):
         return elliptic_self_test(N1, N2, int(os.environ["IMPEC_TEST_ELLIPTIC"]), cuda, rank, world)
     extra = {}
@@ -70,18 +109,7 @@ def main():
 
     ref = I.Context(Pi, device=dev, emulated=not cuda)      # single-rank reference (same library, same kernels)
     ref.upload_c(c); ref.upload_q(q)
-    if cuda:
-        import ctypes as C
-        ids = [None]
-        if rank == 0:
-            buf = C.create_string_buffer(128)
-            assert I.load().impec_nccl_unique_id(buf) == 0
-            ids = [buf.raw]
-        dist.broadcast_object_list(ids, src=0)
-        ctx = I.Context(Pi, device=dev, rank=rank, nranks=world, nccl_id=ids[0])
-    else:
-        ctx = I.Context(Pi, rank=rank, nranks=world, emulated=True)
-        I.attach_torch_comm(ctx, rank, world)
+    ctx = slab_context(Pi, cuda, rank, world, dev)
     ctx.upload_c(c); ctx.upload_q(q)
     r0, n = ctx.local_rows()
     assert n == N1 // world and r0 == rank * n

@@ -16,7 +16,7 @@ def ngpus():
 # march = 1: the register-march multigrid kernels (by default only on levels of >= 8M cells) forced onto every slab level
 @pytest.mark.parametrize("N1,N2,stype,diffusion,steps,march", [(512, 512, 0, 0, 2, 0), (256, 128, 1, 1, 2, 0), (2048, 2048, 0, 0, 1, 0), (2048, 2048, 0, 0, 1, 1),
                                                                  (256, 192, 2, 1, 2, 0)])      # (the last: stype 2 = horizontal front, Dirichlet rows on the first / last rank)
-def test_slabs_match_single_gpu(N1, N2, stype, diffusion, steps, march, split=None):
+def test_slabs_match_single_gpu(N1, N2, stype, diffusion, steps, march, split=None, extra_env=None):
     world = min(ngpus(), 8)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -29,6 +29,7 @@ def test_slabs_match_single_gpu(N1, N2, stype, diffusion, steps, march, split=No
         env["IMPEC_MARCH_MIN_CELLS"] = "0"
     if split is not None:
         env["IMPEC_TEST_SPLITTING"] = str(split)
+    env.update(extra_env or {})
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(" ok: ") == world, out.stdout
@@ -39,6 +40,14 @@ def test_slabs_sequential_splittings(split):
     """alternating_sweeps / strang on slabs (added after the last GPU session of round 2: run on CPU ranks only so far,
     tests/test_multirank.py::test_two_ranks_sequential_splittings; the exchange after an x sweep is the same exchange_rows as everywhere)."""
     test_slabs_match_single_gpu(256, 128, 1, 0, 2, 0, split=split)
+
+
+def test_slabs_self_tests():
+    """The two self tests on slabs over NCCL (added after the last GPU session of round 2; CPU twins: test_two_ranks_elliptic_self_test,
+    test_periodic_self_test_on_slabs): the manufactured elliptic test against the one-GPU solve, the periodic advection test (ranks
+    closed to a ring, plain NCCL send / recv) bit for bit against the one-GPU run."""
+    test_slabs_match_single_gpu(256, 384, 1, 0, 1, 0, extra_env={"IMPEC_TEST_ELLIPTIC": "4"})
+    test_slabs_match_single_gpu(256, 256, 1, 0, 5, 0, extra_env={"IMPEC_TEST_PERIODIC": "muscl"})
 
 
 @pytest.mark.parametrize("cfg_name,n1,n2", [("diagonal_dispersion", 256, 128), ("parallel", 256, 256)])

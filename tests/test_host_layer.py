@@ -246,3 +246,25 @@ def test_elliptic_test_cfg_on_slabs(tmp_path):
         norms[w] = np.loadtxt(str(d / "elliptic_norms.out"))
     assert norms[1].shape == norms[2].shape == (3, 4)
     assert np.abs(norms[1] - norms[2]).max() <= 1e-6, np.abs(norms[1] - norms[2]).max()
+
+
+def test_hyperbolic_test_cfg_on_slabs(tmp_path):
+    """hyperbolic_test.cfg (Impec2DSolver::TestAdvection) as two processes: the periodic ghost rows come from the other rank (ranks closed to a
+    ring); the transport path is explicit, so the norm file equals the one-process file to the last digit.  48^2 / 96^2 instead of the shipped
+    50^2: a slab needs an even number of rows."""
+    norms = {}
+    subs = [(r"levels\s*=\s*4", "levels = 2"), (r"initial_x_cells\s*=\s*\d+", "initial_x_cells = 48"), (r"initial_y_cells\s*=\s*\d+", "initial_y_cells = 48")]
+    for w in (1, 2):
+        d = tmp_path / ("w%d" % w); d.mkdir(); comm = d / "comm"; comm.mkdir()
+        cfg = cfg_variant(d, "hyperbolic_test.cfg", subs)
+        procs = []
+        for r in range(w):
+            env = dict(os.environ, IMPEC_RANK=str(r), IMPEC_NRANKS=str(w), IMPEC_EMU_COMM_DIR=str(comm), IMPEC_DIST_MIN_CELLS="0", OMP_NUM_THREADS="1")
+            procs.append(subprocess.Popen([EXE, cfg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+        logs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), "\n".join(l[-2000:] for l in logs)
+        assert not os.listdir(str(comm))
+        norms[w] = np.loadtxt(str(d / "hyperbolic_norms.out"))
+    assert norms[1].shape == (2, 2) and np.array_equal(norms[1], norms[2]), (norms[1], norms[2])
+    order = (norms[1][1, 1] - norms[1][0, 1]) / (norms[1][1, 0] - norms[1][0, 0])
+    assert 1.7 < order < 2.0, order

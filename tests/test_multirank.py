@@ -79,3 +79,10 @@ def test_two_ranks_elliptic_self_test(N1, N2, testno, nu, port):
     """The manufactured elliptic test (elliptic_test.cfg) on two slabs: the K(x,y) test fields are evaluated at global coordinates
     (the device-side x origin is the slab's), the multi-pass operator build exchanges its link rows."""
     run(2, N1, N2, 1, 0, 1, port, {"IMPEC_TEST_ELLIPTIC": str(testno), "IMPEC_TEST_NU": nu})
+
+
+@pytest.mark.parametrize("world,N,method,port", [(2, 48, "muscl", 29628), (4, 64, "muscl", 29629), (2, 32, "upwind", 29630)])
+def test_periodic_self_test_on_slabs(world, N, method, port):
+    """hyperbolic_test.cfg (periodic advection) on 2 and 4 slabs: ghost rows from the neighbouring rank with the ranks closed to a ring
+    (two ranks: both neighbours are the same peer, messages told apart by direction); bit-identical to the 1-rank run."""
+    run(world, N, N, 1, 0, 5, port, {"IMPEC_TEST_PERIODIC": method})
