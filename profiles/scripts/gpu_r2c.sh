@@ -5,7 +5,7 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 K=vcycle,fused_pre,fused_post,fused_plain,pcg_matvec,build_operator,calc_velocities
 timeout 300 python tools/ncu_kernels.py 16384 $K 10 > gpurun_out/r2c_ab_new.txt 2>&1
-cp impec2d_b200/libimpec2d_b200.so /tmp/new.so; cp scratch/ab/libold.so impec2d_b200/libimpec2d_b200.so
+cp impec2d_b200/libimpec2d_b200.so /tmp/new.so; cp tools/studies/ab/libold.so impec2d_b200/libimpec2d_b200.so
 timeout 300 python tools/ncu_kernels.py 16384 $K 10 > gpurun_out/r2c_ab_old.txt 2>&1
 cp /tmp/new.so impec2d_b200/libimpec2d_b200.so
 paste gpurun_out/r2c_ab_new.txt gpurun_out/r2c_ab_old.txt

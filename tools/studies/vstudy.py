@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo/scratch')
+sys.path.insert(0, '/root/repo/tools/studies')
 import mgproto as M
 def pcg(levels, b, cfg, tol=1e-14, maxit=200):
     A = levels[0]

@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo/scratch')
+sys.path.insert(0, '/root/repo/tools/studies')
 import mgproto as M
 from vstudy import pcg  # noqa
 def build_nopin(AW, AS, AV, cfg, nmin=4):
