@@ -1830,10 +1830,9 @@ extern "C" int impec_advect_y(impec_ctx *ctx, double dt) {
 
 // CalculateIntercellFlux_F / _G (src/HyperbolicSplitSolver.h:19-22): the flux field of the CURRENT c and velocity for a step dt, in the
 // reference's array shapes -- dir 0: F[(N1+1) x (N2+2g)], F(i, j) at out[i * (N2+2g) + (j+g)]; dir 1: G[(N1+2g) x (N2+1)], G(i, j) at
-// out[(i+g) * (N2+1) + j].  c must carry filled ghosts (as for impec_advect_x / _y).  Single GPU.
+// out[(i+g) * (N2+1) + j].  c must carry filled ghosts (as for impec_advect_x / _y).  Slabs: every rank fills its own rows of the array.
 extern "C" int impec_intercell_flux(impec_ctx *ctx, int dir, double dt, double *out_host) {
     if (!out_host || (dir != 0 && dir != 1)) return fail(ctx, IMPEC_ERR_ARG, "impec_intercell_flux: dir must be 0 (F) or 1 (G)");
-    if (ctx->nranks > 1) return fail(ctx, IMPEC_ERR_UNSUPPORTED, "impec_intercell_flux runs on one GPU");
     const Grid &g = ctx->g; const int ng = ctx->P.g;
     const double phi = ctx->P.porosity; const bool phi1 = (phi == 1.0), up = ctx->P.hyper_method == IMPEC_UPWIND;
     const int i0 = dir == 0 ? 0 : -ng, i1 = dir == 0 ? g.N1 + 1 : g.N1 + ng, j0 = dir == 0 ? -ng : 0, j1 = dir == 0 ? g.N2 + ng : g.N2 + 1;
@@ -1845,6 +1844,7 @@ extern "C" int impec_intercell_flux(impec_ctx *ctx, int dir, double dt, double *
     else          { if (up) { if (phi1) FLX(1, 1, true); else FLX(1, 1, false); } else { if (phi1) FLX(1, 0, true); else FLX(1, 0, false); } }
 #undef FLX
     const size_t w = (size_t)(j1 - j0) * sizeof(double);
+    out_host += (size_t)g.i_off * (size_t)(j1 - j0);          // slabs: this rank's rows of the caller's whole-grid array (halo rows included: neighbours agree on them)
     CUDA_TRY(ctx, cudaMemcpy2DAsync(out_host, w, F + gidx(g, i0, j0), (size_t)g.ld * sizeof(double), w, (size_t)(i1 - i0), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->bytes_d2h += (unsigned long long)w * (unsigned long long)(i1 - i0);

@@ -162,7 +162,8 @@ int   impec_advect_y(impec_ctx *ctx, double dt);
 int   impec_advect_split(impec_ctx *ctx, double dt);
 /* CalculateIntercellFlux_F / _G (src/HyperbolicSplitSolver.h:19-22; src/MUSCLSplitSolver.cpp:102-189, src/UpwindSplitSolver.cpp:43-61):
  * the intercell fluxes of the current c and velocity for a step dt as a HOST array in the reference's shape -- dir 0: F[(N1+1)][N2+2g]
- * (index base (0,-g)), dir 1: G[N1+2g][N2+1] (index base (-g,0)).  The sweeps never materialise these arrays; single GPU. */
+ * (index base (0,-g)), dir 1: G[N1+2g][N2+1] (index base (-g,0)).  The sweeps never materialise these arrays.  Slab contexts: every rank fills its
+ * own rows (with the halo rows it shares with its neighbours) of the caller's whole-grid array. */
 int   impec_intercell_flux(impec_ctx *ctx, int dir, double dt, double *out_host);
 /* a19  HyperbolicSolver::DiffusionSplitCN -> MGSolver::Solve_Parabolic_cc_to_c  src/HyperbolicSolver.cpp:213-223, src/MGSolver.cpp:952-976 */
 /*      alpha_l == alpha_t: symmetric links operator, PCG with a one-march symmetric Gauss-Seidel preconditioner; alpha_l != alpha_t: the full

@@ -139,6 +139,12 @@ def main():
     cga = ctx.gather_rows("c"); pgl = ctx.gather_rows("p"); vg = ctx.gather_rows("v"); vr = ref.download_velocity()
     assert np.abs(cga[g:-g, :] - cr[g:-g, :]).max() <= 1e-9 and np.abs(pgl[g:-g, g:-g] - pr[g:-g, g:-g]).max() <= 1e-9 * np.abs(pr).max()
     assert np.abs(vg[g:g + N1, g:-g, :] - vr[g:g + N1, g:-g, :]).max() <= 1e-8 * max(np.abs(vr).max(), 1e-30)
+    # CalculateIntercellFlux_F / _G on slabs: this rank's rows of the whole-grid flux arrays against the 1-rank arrays
+    ctx.fill_boundaries(); ref.fill_boundaries()
+    for d in (0, 1):
+        Fs = ctx.intercell_flux(d, dt_ref); Fr = ref.intercell_flux(d, dt_ref)
+        own = slice(r0, r0 + n + 1) if d == 0 else slice(r0, r0 + n + 2 * g)
+        assert np.abs(Fs[own] - Fr[own]).max() <= 1e-9 * max(np.abs(Fr).max(), 1e-30), (d, np.abs(Fs[own] - Fr[own]).max())
     if stype == O.PARALLEL:
         # parallel -> diagonal projection of a slab-decomposed field (collective; rows of the diagonal grid in chunks of the scratch field)
         for field, full in ((0, cr), (1, pr)):
