@@ -107,8 +107,14 @@ double shfl(double v, int arg, int mode) {
     return out;
 }
 
+// IMPEC_EMU_ORDER=reverse runs the blocks of a grid, the threads of a block and the coroutines between two barriers in the opposite order.
+// A kernel without data races gives the same bits either way; one that reads what another thread or block writes in the same launch
+// (an in-place stencil, a missing barrier) does not: tools/sanitize_emu.sh order runs the parity tests this way (a race check without a GPU).
+static bool reverse_order() { static const bool r = [] { const char *e = getenv("IMPEC_EMU_ORDER"); return e && e[0] == 'r'; }(); return r; }
+
 void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<void()> &body) {
     gridDim_ = grid; blockDim_ = block;
+    const bool rev = reverse_order();
     std::vector<unsigned char> smem_buf(smem + 16);
     dyn_smem = smem_buf.data();
     const int nthreads = (int)(block.x * block.y * block.z);
@@ -117,14 +123,18 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
         fibers.assign(nthreads, Fiber());
         exch.assign(nthreads, 0.0);
     }
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++) {
+    for (unsigned bz_ = 0; bz_ < grid.z; bz_++)
+        for (unsigned by_ = 0; by_ < grid.y; by_++)
+            for (unsigned bx_ = 0; bx_ < grid.x; bx_++) {
+                const unsigned bx = rev ? grid.x - 1 - bx_ : bx_, by = rev ? grid.y - 1 - by_ : by_, bz = rev ? grid.z - 1 - bz_ : bz_;
                 blockIdx_ = dim3(bx, by, bz);
                 if (!coop) {
-                    for (unsigned tz = 0; tz < block.z; tz++)
-                        for (unsigned ty = 0; ty < block.y; ty++)
-                            for (unsigned tx = 0; tx < block.x; tx++) { threadIdx_ = dim3(tx, ty, tz); body(); }
+                    for (unsigned tz_ = 0; tz_ < block.z; tz_++)
+                        for (unsigned ty_ = 0; ty_ < block.y; ty_++)
+                            for (unsigned tx_ = 0; tx_ < block.x; tx_++) {
+                                threadIdx_ = rev ? dim3(block.x - 1 - tx_, block.y - 1 - ty_, block.z - 1 - tz_) : dim3(tx_, ty_, tz_);
+                                body();
+                            }
                     continue;
                 }
                 in_coop = true; cur_body = &body;
@@ -139,7 +149,8 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
                 bool any = true;
                 while (any) {
                     any = false;
-                    for (int k = 0; k < nthreads; k++) {
+                    for (int k_ = 0; k_ < nthreads; k_++) {
+                        const int k = rev ? nthreads - 1 - k_ : k_;
                         if (fibers[k].done) continue;
                         current = k; threadIdx_ = fibers[k].tid;
                         impec_emu_switch(&sched_sp, fibers[k].sp);
