@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 
 #if !defined(__x86_64__)
 #error "the CPU emulator's context switch is written for x86-64"
@@ -110,11 +111,21 @@ double shfl(double v, int arg, int mode) {
 // IMPEC_EMU_ORDER=reverse runs the blocks of a grid, the threads of a block and the coroutines between two barriers in the opposite order.
 // A kernel without data races gives the same bits either way; one that reads what another thread or block writes in the same launch
 // (an in-place stencil, a missing barrier) does not: tools/sanitize_emu.sh order runs the parity tests this way (a race check without a GPU).
-static bool reverse_order() { static const bool r = [] { const char *e = getenv("IMPEC_EMU_ORDER"); return e && e[0] == 'r'; }(); return r; }
+// IMPEC_EMU_ORDER=shuffle: a pseudo-random permutation instead (a new one for every launch and for every round between two barriers).
+static int order_mode() { static const int m = [] { const char *e = getenv("IMPEC_EMU_ORDER"); return !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 's' ? 2 : 0)); }(); return m; }
+static unsigned long long rng_state = 0x9E3779B97F4A7C15ULL;
+static unsigned rng() { rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL; return (unsigned)(rng_state >> 33); }
+static void make_order(std::vector<int> &o, int n, int mode) {
+    o.resize(n);
+    for (int k = 0; k < n; k++) o[k] = mode == 1 ? n - 1 - k : k;
+    if (mode == 2) for (int k = n - 1; k > 0; k--) std::swap(o[k], o[rng() % (unsigned)(k + 1)]);
+}
 
 void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<void()> &body) {
     gridDim_ = grid; blockDim_ = block;
-    const bool rev = reverse_order();
+    const int mode = order_mode();
+    std::vector<int> border, torder;
+    make_order(border, (int)(grid.x * grid.y * grid.z), mode);
     std::vector<unsigned char> smem_buf(smem + 16);
     dyn_smem = smem_buf.data();
     const int nthreads = (int)(block.x * block.y * block.z);
@@ -123,18 +134,20 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
         fibers.assign(nthreads, Fiber());
         exch.assign(nthreads, 0.0);
     }
-    for (unsigned bz_ = 0; bz_ < grid.z; bz_++)
-        for (unsigned by_ = 0; by_ < grid.y; by_++)
-            for (unsigned bx_ = 0; bx_ < grid.x; bx_++) {
-                const unsigned bx = rev ? grid.x - 1 - bx_ : bx_, by = rev ? grid.y - 1 - by_ : by_, bz = rev ? grid.z - 1 - bz_ : bz_;
+    for (size_t bb = 0; bb < border.size(); bb++) {
+            {
+                const unsigned lin = (unsigned)border[bb];
+                const unsigned bx = lin % grid.x, by = (lin / grid.x) % grid.y, bz = lin / (grid.x * grid.y);
                 blockIdx_ = dim3(bx, by, bz);
                 if (!coop) {
-                    for (unsigned tz_ = 0; tz_ < block.z; tz_++)
-                        for (unsigned ty_ = 0; ty_ < block.y; ty_++)
-                            for (unsigned tx_ = 0; tx_ < block.x; tx_++) {
-                                threadIdx_ = rev ? dim3(block.x - 1 - tx_, block.y - 1 - ty_, block.z - 1 - tz_) : dim3(tx_, ty_, tz_);
-                                body();
-                            }
+                    if (mode == 0) {
+                        for (unsigned tz = 0; tz < block.z; tz++)
+                            for (unsigned ty = 0; ty < block.y; ty++)
+                                for (unsigned tx = 0; tx < block.x; tx++) { threadIdx_ = dim3(tx, ty, tz); body(); }
+                    } else {
+                        make_order(torder, nthreads, mode);
+                        for (int t : torder) { threadIdx_ = dim3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)); body(); }
+                    }
                     continue;
                 }
                 in_coop = true; cur_body = &body;
@@ -149,8 +162,9 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
                 bool any = true;
                 while (any) {
                     any = false;
+                    if (mode != 0) make_order(torder, nthreads, mode);
                     for (int k_ = 0; k_ < nthreads; k_++) {
-                        const int k = rev ? nthreads - 1 - k_ : k_;
+                        const int k = mode == 0 ? k_ : torder[k_];
                         if (fibers[k].done) continue;
                         current = k; threadIdx_ = fibers[k].tid;
                         impec_emu_switch(&sched_sp, fibers[k].sp);
@@ -159,6 +173,7 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
                 }
                 in_coop = false; current = -1;
             }
+    }
     dyn_smem = nullptr;
 }
 }  // namespace emu

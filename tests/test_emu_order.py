@@ -1,4 +1,4 @@
-"""Race check without a GPU (tools/emu_order_check.py): the emulated kernels executed with blocks, threads and coroutines in REVERSE order
+"""Race check without a GPU (tools/emu_order_check.py): the emulated kernels executed with blocks, threads and coroutines in REVERSE and in a pseudo-random order
 must give the same bits as in forward order -- a kernel that reads what another thread or block of the same launch writes would not."""
 import os
 import subprocess

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Race check without a GPU: the emulated kernels run with blocks / threads / coroutines in forward and in REVERSE order
+"""Race check without a GPU: the emulated kernels run with blocks / threads / coroutines in forward, in REVERSE and in a pseudo-random order
 (IMPEC_EMU_ORDER, csrc/emu.cpp) must produce the same BITS.  A kernel that reads what another thread or block of the same launch
 writes (in-place stencil, missing barrier) would differ.  Scenarios: IMPES steps with and without dispersion on awkward extents, the
 anisotropic-dispersion path, the sequential splittings with upwind fluxes, the horizontal front, marching kernels forced onto
@@ -55,13 +55,13 @@ def main():
     with tempfile.TemporaryDirectory() as d:
         for k, cs in enumerate(CASES):
             outs = []
-            for order in ("forward", "reverse"):
+            for order in ("forward", "reverse", "shuffle"):
                 out = os.path.join(d, "%s_%s.npz" % (cs["name"], order))
                 env = dict(os.environ, IMPEC_EMU_ORDER=order, OMP_NUM_THREADS="1"); env.update(cs.get("env", {}))
                 subprocess.check_call([sys.executable, os.path.abspath(__file__), "--child", str(k), out], env=env)
                 outs.append(np.load(out))
-            same = all(np.array_equal(outs[0][f], outs[1][f]) for f in outs[0].files)
-            worst = max(float(np.abs(np.asarray(outs[0][f], dtype=float) - np.asarray(outs[1][f], dtype=float)).max()) for f in outs[0].files)
+            same = all(np.array_equal(outs[0][f], o[f]) for f in outs[0].files for o in outs[1:])
+            worst = max(float(np.abs(np.asarray(outs[0][f], dtype=float) - np.asarray(o[f], dtype=float)).max()) for f in outs[0].files for o in outs[1:])
             print("%-34s %s (max difference %.3e; fields %s)" % (cs["name"], "bit-identical" if same else "DIFFERS", worst, ",".join(outs[0].files)))
             bad += not same
     return 1 if bad else 0
