@@ -63,6 +63,7 @@ void *sched_sp = nullptr;
 int current = -1;
 const std::function<void()> *cur_body = nullptr;
 std::vector<double> exch;
+std::vector<int> shfl_count;                      // shuffles issued by every thread of the current block (all lanes of a warp must agree)
 bool in_coop = false;
 
 void trampoline() {
@@ -97,7 +98,15 @@ double shfl(double v, int arg, int mode) {
     const int nthreads = (int)fibers.size();
     const int me = current, lane = me & 31, base = me & ~31;
     exch[me] = v;
+    shfl_count[me]++;
     syncthreads();
+    // the kernels shuffle with the full mask: every lane of the warp must still be running (a lane that returned early is undefined
+    // behaviour on the GPU, where the emulator would silently hand out its last value)
+    for (int l = 0; l < 32 && base + l < nthreads; l++)
+        if (fibers[base + l].done || shfl_count[base + l] != shfl_count[me]) {
+            std::fprintf(stderr, "emu: full-mask warp shuffle, but lane %d of warp %d %s\n", l, base / 32, fibers[base + l].done ? "has already exited" : "is not at the same shuffle (divergent control flow)");
+            std::abort();
+        }
     int src = lane;
     if (mode == 0) src = lane + arg;
     else if (mode == 1) src = lane - arg;
@@ -151,6 +160,7 @@ void launch(dim3 grid, dim3 block, size_t smem, bool coop, const std::function<v
                     continue;
                 }
                 in_coop = true; cur_body = &body;
+                shfl_count.assign(nthreads, 0);
                 int t = 0;
                 for (unsigned tz = 0; tz < block.z; tz++)
                     for (unsigned ty = 0; ty < block.y; ty++)
