@@ -16,3 +16,15 @@ def orc():
     import oracle
     oracle.lib()
     return oracle
+
+
+def pytest_collection_modifyitems(config, items):
+    """Run order of the GPU suite: single-GPU parity first, the multi-GPU cases (skipped on a one-GPU box) after it, and of those the cases
+    that have only run on CPU ranks so far last -- under `-x` a failure in a multi-process case must not hide the parity suite proper."""
+    def key(item):
+        name = item.nodeid
+        if "test_gpu_multirank" not in name:
+            return 0
+        never_on_hardware = ("test_slabs_sequential_splittings", "test_slabs_self_tests", "test_cpp_driver_on_two_gpus[parallel")
+        return 2 if any(s in name for s in never_on_hardware) else 1
+    items.sort(key=key)          # stable: the order inside each group is unchanged
