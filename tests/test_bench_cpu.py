@@ -1,0 +1,79 @@
+"""bench.py without a GPU: the reference arm (`--impl reference`, the CPU implementations timed on the host cores) on small grids, the
+behaviour of the arm under torchrun's environment (rank > 0 prints nothing, OMP_NUM_THREADS = 1 is ignored), the byte model helpers, and
+that our own arm refuses to run without a CUDA device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BENCH = os.path.join(ROOT, "bench.py")
+REQUIRED = ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+            "config", "cpu_baseline", "e2e")
+
+
+def run_bench(*args, env=None):
+    out = subprocess.run([sys.executable, BENCH] + list(args), capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
+    return out
+
+
+def test_reference_arm_transport_line():
+    """hyperbolic_test through the reference's own code where oracle/_ref is built, else the oracle port; one JSON line, contract keys."""
+    out = run_bench("--impl", "reference", "--workload", "hyperbolic_test", "--size", "256", "--steps", "2", "--warmup", "1")
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    for k in REQUIRED:
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "Gcell-updates/s" and line["higher_is_better"] is True and line["dtype"] == "f64"
+    assert line["value"] > 0 and line["ms_per_step"] > 0 and line["steps"] == 2 and line["warmup"] == 3       # W >= 3 is enforced
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["grid"] == [256, 256] and "hyperbolic_test.cfg" in line["config"]["workload"]
+    assert line["gpu_launches"] == 0
+
+
+def test_reference_arm_under_torchrun_environment():
+    """torchrun exports OMP_NUM_THREADS=1: rank 0 still uses every host thread; the other ranks exit 0 without output."""
+    env = {"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}
+    out = run_bench("--impl", "reference", "--gpus", "2", "--workload", "hyperbolic_test", "--size", "128", "--steps", "1", "--warmup", "1", env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    out = run_bench("--impl", "reference", "--gpus", "2", "--workload", "hyperbolic_test", "--size", "128", "--steps", "1", "--warmup", "1",
+                    env=dict(env, RANK="1", LOCAL_RANK="1"))
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_impes_sample():
+    """The IMPES workloads run the oracle port (the reference's solve is HYPRE) on a bounded sample: at --size 2048 that is the grid itself."""
+    out = run_bench("--impl", "reference", "--workload", "diagonal_dispersion", "--size", "2048", "--steps", "1", "--warmup", "0", "--eps", "1e-8")
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    b = line["cpu_baseline"]
+    assert b["kind"] == "port" and b["sample_grid"] == [2048, 2048] and len(b["pcg_iterations"]) == 1 and b["pcg_iterations"][0] > 0
+    assert line["config"]["eps"] == 1e-8 and "diagonal_dispersion.cfg" in line["config"]["workload"]
+
+
+def test_our_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    out = run_bench("--steps", "1", "--warmup", "1", "--size", "256")
+    assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_cycle_byte_model():
+    """Bytes per fine cell of one multigrid cycle as bench.py derives them from the W range in effect."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert abs(bench.cycle_bytes_per_fine_cell(2, 4, 13) - 113.3) < 0.05          # default on 1-4 ranks
+    assert abs(bench.cycle_bytes_per_fine_cell(2, 3, 13) - 111.6) < 0.05          # default on >= 8 ranks
+    v = bench.cycle_bytes_per_fine_cell(99, 99, 13)                               # plain V cycle: 76 * 4/3
+    assert abs(v - 76.0 * (1 - 0.25 ** 13) / 0.75) < 1e-9
+    for wl, w in bench.WORKLOADS.items():
+        assert os.path.exists(os.path.join(ROOT, w["cfg"])), wl
