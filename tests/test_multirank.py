@@ -9,15 +9,61 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(world, N1, N2, stype, diffusion, steps, port, extra_env=None):
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "impec2d_b200", "csrc"), "emu"])
+_pool = None
+_futures = {}
+_calls = []          # the arguments of every run(...) call of this module's tests (filled by _collect)
+_collecting = False
+
+
+def _collect():
+    """Dry pass over the tests of this module (with their parametrizations): run() only records its arguments."""
+    global _collecting
+    _collecting = True
+    try:
+        for name, fn in list(globals().items()):
+            if not name.startswith("test_") or not callable(fn):
+                continue
+            marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
+            if not marks:
+                fn()
+                continue
+            names = [n.strip() for n in marks[0].args[0].split(",")]
+            for vals in marks[0].args[1]:
+                fn(**dict(zip(names, vals if isinstance(vals, (tuple, list)) else (vals,))))
+    finally:
+        _collecting = False
+
+
+def _launch(world, N1, N2, stype, diffusion, steps, port, extra_env):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multirank_worker.py"), str(N1), str(N2), str(stype), str(diffusion), str(steps)]
     env = dict(os.environ, OMP_NUM_THREADS="1", IMPEC_DIST_MIN_CELLS="0")
     env.update(extra_env or {})
     for k in [k for k, v in env.items() if v is None]:
         del env[k]
-    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    return subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+
+
+def run(world, N1, N2, stype, diffusion, steps, port, extra_env=None):
+    """One scenario = one torchrun launch of tests/multirank_worker.py (distinct rendezvous port each).  Most of a launch is start-up
+    (three or five interpreters importing torch), so the first call starts ALL scenarios of this module on a small thread pool and every
+    test waits for its own (8 cores: 105 s for the module instead of 290 s one after the other)."""
+    global _pool
+    if _collecting:
+        _calls.append((world, N1, N2, stype, diffusion, steps, port, extra_env))
+        return
+    key = (world, N1, N2, stype, diffusion, steps, port, tuple(sorted((extra_env or {}).items(), key=lambda kv: kv[0])))
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "impec2d_b200", "csrc"), "emu"])
+        _pool = ThreadPoolExecutor(max_workers=max(1, min(6, (os.cpu_count() or 2) // 2)))
+        _collect()
+        for args in _calls:
+            k = args[:7] + (tuple(sorted((args[7] or {}).items(), key=lambda kv: kv[0])),)
+            _futures[k] = _pool.submit(_launch, *args)
+    if key not in _futures:                                  # a scenario that is not in CASES: run it now
+        _futures[key] = _pool.submit(_launch, world, N1, N2, stype, diffusion, steps, port, extra_env)
+    out = _futures[key].result()
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(" ok: ") == world, out.stdout
 
