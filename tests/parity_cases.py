@@ -334,6 +334,31 @@ def check_horizontal_front(emulated, N1=48, N2=32, diffusion=0, steps=2, links_f
     ctx.close()
 
 
+def check_one_dimensional_flow_with_dispersion(emulated, N1=48, N2=32, steps=3):
+    """c = 0, horizontal front with constant injection, dispersion on: an exactly one-dimensional flow.  The transverse velocity is zero up
+    to the round-off of the pressure solve; wherever both velocity components of a face are EXACTLY zero the reference's dispersion tensor is
+    0/0 (src/MGSolver.cpp:868-869, 904-905) and its Crank-Nicolson matrix NaN.  The product gives such a face no dispersion (k_disp_links):
+    every field stays finite, the solution stays one-dimensional to round-off and mass is injected."""
+    base, Po, c, q = production_case(N1, N2, stype=O.HORIZONTAL, diffusion=1, eps=1e-12)
+    c[...] = 0.0
+    Pi = I.default_params(emulated=emulated, **base)
+    ctx = I.Context(Pi, emulated=emulated)
+    ctx.upload_c(c); ctx.upload_q(q)
+    t = 0.0
+    for _ in range(steps):
+        dt, info = ctx.impes_step(t, 0.0)
+        assert info.converged == 1 and np.isfinite(dt) and dt > 0
+        assert ctx.last_parabolic_info().converged == 1
+        t += dt
+    g = Po.g
+    cg = ctx.download_c()[g:-g, g:-g]; pg = ctx.download_p()[g:-g, g:-g]
+    assert np.isfinite(cg).all() and np.isfinite(pg).all()
+    assert cg.max() > 0.05 and cg.min() >= -1e-12
+    assert np.abs(cg - cg[:, :1]).max() <= 1e-9                     # still a function of x alone
+    assert np.all(cg[N1 - 2] == 0.0)                                # the Dirichlet row of the Crank-Nicolson problem
+    ctx.close()
+
+
 def check_deferred_solution_update(emulated, N1=48, N2=80, stype=O.DIAGONAL, diffusion=1):
     """PCG with the solution update of two iterations merged (k_update_xr MODE 1 / 2, option "defer_x") against the plain form: the
     same operations on x in the same order, so pressure and concentration are BIT-IDENTICAL, for even and odd iteration counts."""

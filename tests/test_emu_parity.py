@@ -81,6 +81,7 @@ def test_dispersion_anisotropic_tensor_parallel(): pc.check_dispersion(True, 32,
 @pytest.mark.parametrize("N1,N2,stype", [(30, 21, O.DIAGONAL), (21, 30, O.DIAGONAL), (6, 6, O.PARALLEL), (4, 4, O.DIAGONAL), (50, 36, O.DIAGONAL)])
 def test_impes_step_ragged_and_tiny_grids(N1, N2, stype): pc.check_impes_step(True, N1, N2, stype=stype, steps=1)
 def test_horizontal_front_tiny_grid(): pc.check_horizontal_front(True, 12, 8, steps=1)
+def test_one_dimensional_flow_with_dispersion(): pc.check_one_dimensional_flow_with_dispersion(True)
 
 
 # marching kernels (forced onto small levels) on extents that are even but not multiples of 4 / of the chunk height / of a warp's 56-60 columns

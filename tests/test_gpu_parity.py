@@ -256,3 +256,7 @@ def test_horizontal_front_tiny_grid(): pc.check_horizontal_front(False, 12, 8, s
 
 
 def test_deferred_solution_update_bitexact(): pc.check_deferred_solution_update(False, 1024, 1536)
+
+
+# an exactly one-dimensional flow with dispersion: faces with zero velocity (0/0 in the reference's dispersion tensor) get no dispersion
+def test_one_dimensional_flow_with_dispersion(): pc.check_one_dimensional_flow_with_dispersion(False, 256, 192)
