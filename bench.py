@@ -273,6 +273,16 @@ def main():
     if need_gb > 165.0:
         raise SystemExit("bench.py: %s at %d^2 needs ~%.0f GB per GPU on %d GPU(s); use more GPUs or --size" % (wl, N, need_gb, world))
     torch.cuda.set_device(local_rank)
+    host_binding = None
+    if world > 1 and os.environ.get("IMPEC_BENCH_BIND", "1") != "0":
+        # one process per GPU: keep this rank's host threads, its pinned buffers (allocated below) and the library's staging buffers on the
+        # NUMA node its GPU hangs off -- with 8 ranks half of the host <-> device traffic of the end-to-end arm would otherwise cross the
+        # socket interconnect.  Not at N = 1: the cpu_baseline leg of that line uses every host thread of the box.
+        try:
+            ncpu, cpus = I.bind_host_to_device(local_rank)
+            host_binding = {"cpus": ncpu, "cpulist": cpus} if ncpu else "unavailable (topology not visible to this process): unbound"
+        except Exception as e:                               # never let placement stop a measurement
+            host_binding = "failed: %s" % e
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"                  # NCCL prints its version banner on stdout: keep stdout to the one JSON line
@@ -479,6 +489,8 @@ def main():
                "parallelism": "1 GPU" if world == 1 else "%d slabs of %d rows along x; halo rows and scalar reductions over %s; multigrid levels below 4M cells replicated after an all-gather" % (world, nrows, ctx.comm_backend()),
                "coefficients": "multigrid cycle reads FP32 copies of the link/diagonal arrays (all arithmetic FP64; PCG mat-vec uses the FP64 operator)"}
         run["halo_exchanges_overlapped_with_interior_chunks"] = int(ctx.overlapped_exchanges())
+        if world > 1:
+            run["host_binding_rank0"] = host_binding           # impec_bind_host_to_device: CPUs local to the rank's GPU
         if options:
             run["options"] = options                       # non-default library options of this run (A/B measurements)
         if kind == "impes":

@@ -7,7 +7,7 @@ bench.py drive; it adds no numerics of its own.
 """
 from ._lib import Params, Diag, SolveInfo, load, library_path, EXPORTS  # noqa: F401
 from .api import (Context, default_params, ImpecError, init_source, init_horizontal_front, synth_state, init_source_rows, synth_state_rows,  # noqa: F401
-                  attach_torch_comm)
+                  attach_torch_comm, bind_host_to_device)
 
 PARALLEL, DIAGONAL, HORIZONTAL = 0, 1, 2
 MEANCONC, HARMONIC = 0, 1

@@ -68,7 +68,7 @@ EXPORTS = [
     "impec_vcycle", "impec_mg_levels", "impec_mg_w_range", "impec_kernel_launches", "impec_overlapped_exchanges", "impec_last_parabolic_info", "impec_reset_state", "impec_set_option",
     "impec_profile_kernel", "impec_init_source", "impec_init_horizontal_front", "impec_synth_state", "impec_ctx_set_comm_callbacks", "impec_local_rows",
     "impec_upload_c_rows", "impec_upload_q_rows", "impec_download_c_rows", "impec_init_source_rows", "impec_synth_state_rows",
-    "impec_comm_backend", "impec_transfer_bytes", "impec_project_dims", "impec_project_to_diagonal", "impec_checkpoint_save", "impec_checkpoint_load",
+    "impec_comm_backend", "impec_transfer_bytes", "impec_bind_host_to_device", "impec_project_dims", "impec_project_to_diagonal", "impec_checkpoint_save", "impec_checkpoint_load",
 ]
 
 
@@ -112,6 +112,7 @@ def load(emulated=False):
     L.impec_default_params.argtypes = [C.POINTER(Params)]
     L.impec_version.restype = C.c_char_p
     L.impec_nccl_unique_id.argtypes = [C.c_char_p]
+    L.impec_bind_host_to_device.argtypes = [C.c_int, C.c_char_p, C.c_int]
     L.impec_ctx_create.argtypes = [C.POINTER(Params), i, i, i, C.c_char_p, vp, C.POINTER(vp)]
     L.impec_ctx_destroy.argtypes = [vp]; L.impec_ctx_destroy.restype = None
     L.impec_last_error.argtypes = [vp]; L.impec_last_error.restype = C.c_char_p

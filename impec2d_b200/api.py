@@ -253,6 +253,15 @@ def synth_state(params, seed=20260917, out=None, emulated=False):
     return c
 
 
+def bind_host_to_device(device, emulated=False):
+    """impec_bind_host_to_device: restrict this thread (and the threads it starts later) to the CPUs local to `device`.  Returns
+    (number of CPUs, the kernel's cpu list) or (0, None) when the topology is not visible / not allowed to this process (mask unchanged)."""
+    L = _lib.load(emulated)
+    buf = C.create_string_buffer(4096)
+    n = L.impec_bind_host_to_device(int(device), buf, len(buf))
+    return (n, buf.value.decode()) if n > 0 else (0, None)
+
+
 def attach_torch_comm(ctx, rank, nranks):
     """Tests only (CPU-emulated library): route the slab halo exchanges and small collectives of a multi-rank context
     through torch.distributed (gloo).  The CUDA library talks NCCL itself and does not use this."""

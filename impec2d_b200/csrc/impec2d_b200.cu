@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <climits>
+#include <sched.h>
 #include <algorithm>
 #include <thread>
 #include <atomic>
@@ -567,6 +568,53 @@ extern "C" int impec_is_emulated(void) {
 #else
     return 0;
 #endif
+}
+// Host placement (include/impec2d_b200.h): the CPUs local to a device, from the kernel's view of its PCI function.
+// "0-55,112-167" -> cpu set; false on a malformed list
+static bool parse_cpulist(const char *s, cpu_set_t *set) {
+    CPU_ZERO(set);
+    const char *p = s;
+    while (*p && *p != '\n') {
+        char *e;
+        const long a = strtol(p, &e, 10);
+        if (e == p || a < 0) return false;
+        long b = a;
+        p = e;
+        if (*p == '-') { b = strtol(p + 1, &e, 10); if (e == p + 1 || b < a) return false; p = e; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET((int)c, set);
+        if (*p == ',') p++;
+        else if (*p && *p != '\n') return false;
+    }
+    return true;
+}
+extern "C" int impec_bind_host_to_device(int device, char *cpulist_out, int len) {
+    if (cpulist_out && len > 0) cpulist_out[0] = 0;
+    char line[4096] = {0};
+#ifdef IMPEC_EMU
+    (void)device;
+    const char *fake = getenv("IMPEC_EMU_LOCAL_CPULIST");          // test hook of the emulated build: there is no PCI device to ask
+    if (!fake) return IMPEC_ERR_UNSUPPORTED;
+    snprintf(line, sizeof line, "%s", fake);
+#else
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return IMPEC_ERR_CUDA; }
+    for (char *c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');        // sysfs spells the bus id in lower case
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return IMPEC_ERR_UNSUPPORTED;
+    const bool got = fgets(line, (int)sizeof line, f) != nullptr;
+    fclose(f);
+    if (!got) return IMPEC_ERR_UNSUPPORTED;
+#endif
+    cpu_set_t want, cur, both;
+    if (!parse_cpulist(line, &want) || CPU_COUNT(&want) == 0) return IMPEC_ERR_UNSUPPORTED;
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return IMPEC_ERR_UNSUPPORTED;
+    CPU_AND(&both, &want, &cur);
+    const int n = CPU_COUNT(&both);
+    if (n == 0) return IMPEC_ERR_UNSUPPORTED;                     // e.g. a container cpuset on the other socket: leave the mask alone
+    if (sched_setaffinity(0, sizeof both, &both) != 0) return IMPEC_ERR_UNSUPPORTED;
+    if (cpulist_out && len > 0) { snprintf(cpulist_out, (size_t)len, "%s", line); for (char *c = cpulist_out; *c; ++c) if (*c == '\n') *c = 0; }
+    return n;
 }
 extern "C" int impec_nccl_unique_id(char id_out[128]) {
     memset(id_out, 0, 128);

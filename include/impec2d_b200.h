@@ -107,6 +107,13 @@ int   impec_is_emulated(void);        /* 1 only for the CPU-emulated test build 
  * impec_nccl_unique_id on rank 0 (NULL when nranks == 1).  cuda_stream: a cudaStream_t to enqueue on, or
  * NULL for a context-owned stream. */
 int   impec_nccl_unique_id(char id_out[128]);
+/* Host placement for one-process-per-GPU runs (ours; upstream leaves process placement to mpirun, src/Driver.cpp:58-87): restricts the CALLING
+ * thread (threads it creates later inherit) to the CPUs that are local to `device` -- /sys/bus/pci/devices/<bus id>/local_cpulist, intersected
+ * with the affinity mask the process already has -- so that pinned host buffers allocated afterwards and the host scan of q live on the NUMA node
+ * the GPU hangs off.  Call before allocating host buffers / creating the context.  Returns the number of CPUs bound to (> 0) and writes the
+ * kernel's list ("0-55,112-167") to cpulist_out when given; IMPEC_ERR_UNSUPPORTED, with the mask unchanged, when the topology is not visible or
+ * none of those CPUs is allowed to this process. */
+int   impec_bind_host_to_device(int device, char *cpulist_out, int len);
 int   impec_ctx_create(const impec_params *p, int device, int rank, int nranks, const char *nccl_unique_id,
                        void *cuda_stream, impec_ctx **out);
 void  impec_ctx_destroy(impec_ctx *ctx);

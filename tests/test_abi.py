@@ -113,3 +113,30 @@ def test_cycle_shape_follows_the_rank_count():
     ctx = I.Context(P, rank=0, nranks=8, emulated=True)
     assert ctx.mg_w_range() == (2, 5)
     ctx.close()
+
+
+def test_bind_host_to_device_logic():
+    """impec_bind_host_to_device (host placement of one-process-per-GPU runs): the device's local CPU list is intersected with the mask the
+    process has; nothing changes when the list is unreadable, malformed or disjoint from the mask.  The emulated build has no PCI device
+    and takes the list from IMPEC_EMU_LOCAL_CPULIST; run in a child process because the call changes the caller's affinity."""
+    build_emu()
+    have = sorted(os.sched_getaffinity(0))
+    if len(have) < 2:
+        pytest.skip("needs two allowed CPUs")
+    code = ("import os, sys, json; sys.path.insert(0, %r); import impec2d_b200 as I; "
+            "r = I.bind_host_to_device(0, emulated=True); print(json.dumps([r[0], r[1], sorted(os.sched_getaffinity(0))]))" % ROOT)
+
+    def child(cpulist):
+        env = dict(os.environ)
+        env.pop("IMPEC_EMU_LOCAL_CPULIST", None)
+        if cpulist is not None:
+            env["IMPEC_EMU_LOCAL_CPULIST"] = cpulist
+        import json
+        import sys
+        return json.loads(subprocess.check_output([sys.executable, "-c", code], env=env).decode().strip().splitlines()[-1])
+
+    a, b = have[0], have[-1]
+    assert child("%d,%d" % (a, b)) == [2, "%d,%d" % (a, b), [a, b]]
+    assert child("%d-%d,100000-100003" % (a, a)) == [1, "%d-%d,100000-100003" % (a, a), [a]]          # CPUs beyond the mask are ignored
+    for bad in (None, "", "x", "3-1", "100000-100003"):                                                  # no list / malformed / disjoint: unchanged
+        assert child(bad) == [0, None, have], bad
