@@ -24,7 +24,8 @@ def pytest_collection_modifyitems(config, items):
     def key(item):
         name = item.nodeid
         if "test_gpu_multirank" not in name:
-            return 0
+            # (single-GPU cases added after the last GPU session run after the ones that are known to pass on the B200)
+            return 0.5 if "test_one_dimensional_flow_with_dispersion" in name else 0
         never_on_hardware = ("test_slabs_sequential_splittings", "test_slabs_self_tests", "test_cpp_driver_on_two_gpus[parallel")
         return 2 if any(s in name for s in never_on_hardware) else 1
     items.sort(key=key)          # stable: the order inside each group is unchanged
