@@ -140,3 +140,27 @@ def test_bind_host_to_device_logic():
     assert child("%d-%d,100000-100003" % (a, a)) == [1, "%d-%d,100000-100003" % (a, a), [a]]          # CPUs beyond the mask are ignored
     for bad in (None, "", "x", "3-1", "100000-100003"):                                                  # no list / malformed / disjoint: unchanged
         assert child(bad) == [0, None, have], bad
+
+
+def test_product_does_not_reference_the_oracle():
+    """oracle/ is test infrastructure: no source file of the product (package, kernels, host layer, header) imports, includes, links or
+    dlopens anything under it, and the built libraries neither depend on it nor carry its symbols."""
+    pkg = os.path.join(ROOT, "impec2d_b200")
+    offenders = []
+    for base in (pkg, os.path.join(ROOT, "include")):
+        for dp, _, fs in os.walk(base):
+            for f in fs:
+                if not f.endswith((".py", ".cu", ".inl", ".h", ".cpp", ".hpp", "Makefile")):
+                    continue
+                text = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"^\s*(import|from)\s+oracle\b|#\s*include\s*[\"<][^\"<>]*oracle|liboracle|impec_oracle|\borc_[a-z_]+\s*\(", text, flags=re.M):
+                    offenders.append(os.path.relpath(os.path.join(dp, f), ROOT))
+    assert not offenders, offenders
+    for name in ("libimpec2d_b200.so", "libimpec2d_host.so"):
+        path = os.path.join(pkg, name)
+        if not os.path.exists(path):
+            continue
+        needed = subprocess.check_output(["readelf", "-d", path]).decode()
+        assert "oracle" not in needed and "impec_ref" not in needed, needed
+        syms = subprocess.check_output(["nm", "-D", path]).decode()
+        assert not re.search(r"\borc_[a-z_]+", syms)
