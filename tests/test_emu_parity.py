@@ -93,3 +93,12 @@ def test_marching_kernels_awkward_extents(monkeypatch, N1, N2):
 
 
 def test_deferred_solution_update_bitexact(): pc.check_deferred_solution_update(True, 48, 80)
+
+
+def test_random_shapes_fuzz():
+    """Three cases of tools/emu_fuzz.py (random workload, grid extents and parameters; the tool itself was run over 120 cases)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("emu_fuzz", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "emu_fuzz.py"))
+    fuzz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fuzz)
+    assert fuzz.main(20261018, 3) == 0
