@@ -103,7 +103,8 @@ void  impec_default_params(impec_params *p);
 const char *impec_version(void);
 int   impec_is_emulated(void);        /* 1 only for the CPU-emulated test build (never shipped)    */
 
-/* rank/nranks: slab decomposition along i over the GPUs of one node; nccl_unique_id = 128 bytes from
+/* rank/nranks: slab decomposition along i over the GPUs of one node (x_cells a multiple of 2 * nranks with at least 8 rows per slab, y_cells even:
+ * the slab levels need one coarser level below them; anything else is refused with IMPEC_ERR_ARG and a message); nccl_unique_id = 128 bytes from
  * impec_nccl_unique_id on rank 0 (NULL when nranks == 1).  cuda_stream: a cudaStream_t to enqueue on, or
  * NULL for a context-owned stream. */
 int   impec_nccl_unique_id(char id_out[128]);

@@ -95,6 +95,11 @@ def test_argument_errors_are_reported_not_fatal():
         ctx.pressure_solve()
     with pytest.raises(I.ImpecError, match="unknown option"):
         ctx.set_option("nonsense", 1)
+    # slab contexts: extents that cannot be cut / coarsened are refused at creation, before any communication
+    with pytest.raises(I.ImpecError, match="cannot be cut into 2 slabs"):
+        I.Context(I.default_params(emulated=True, N1=42, N2=32), rank=0, nranks=2, emulated=True)
+    with pytest.raises(I.ImpecError, match="no coarser level"):
+        I.Context(I.default_params(emulated=True, N1=48, N2=37), rank=1, nranks=2, emulated=True)
 
 
 def test_cycle_shape_follows_the_rank_count():
