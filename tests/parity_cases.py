@@ -269,9 +269,11 @@ def check_vcycle(emulated, N1=32, N2=32, stype=O.PARALLEL, nu=2.0 / 3.0):
     ctx.close()
 
 
-def check_impes_step(emulated, N1=48, N2=48, stype=O.PARALLEL, nu=2.0 / 3.0, avg=O.HARMONIC, eps=1e-12, steps=2):
+def check_impes_step(emulated, N1=48, N2=48, stype=O.PARALLEL, nu=2.0 / 3.0, avg=O.HARMONIC, eps=1e-12, steps=2, its_tol=1):
     """One and two full IMPES steps (a20): pressure to TOL_P, velocities/dt/c to the tolerance the pressure
-    tolerance implies, same iteration count +-1."""
+    tolerance implies, same iteration count +-1 (its_tol = None: not compared -- with nu < 1/2 on cells of aspect ratio > 2 the
+    rotated-frame operator is far from an M-matrix, the point-smoother cycle is a weak preconditioner (60-80 iterations on both sides)
+    and the count moves by several iterations with the summation order of the dot products or the FP32 coefficient copies)."""
     lib = O.lib()
     base, Po, c, q = production_case(N1, N2, stype=stype, nu=nu, avgproc=avg, eps=eps)
     Pi = I.default_params(emulated=emulated, **base)
@@ -286,7 +288,7 @@ def check_impes_step(emulated, N1=48, N2=48, stype=O.PARALLEL, nu=2.0 / 3.0, avg
         dtg, info = ctx.impes_step(t, 0.0)
         assert info.converged == 1 and info.relres < eps
         assert info.true_relres < 50 * eps
-        assert abs(info.iterations - So.last_its) <= 1
+        assert its_tol is None or abs(info.iterations - So.last_its) <= its_tol
         assert abs(dtg - dto) <= 1e-9 * dto
         t += dto
     pg = ctx.download_p(); cg = ctx.download_c(); vg = ctx.download_velocity()
